@@ -1,0 +1,157 @@
+/* b200surv.h -- C ABI of libb200surv.so: the B200 (sm_100a) survival-training hot path.
+ *
+ * Drop-in boundary for baek0203/multimodal_survival_prediction (reference paths below are relative
+ * to the reference checkout).  The reference is pure Python; what it binds for this path is
+ *   torchsurv.loss.cox.neg_partial_log_likelihood(log_hz, event, time)
+ *       scripts/training/partial_modality_training.py:285-288, simple_fusion.py:270,311,
+ *       final_multimodal.py:158-162
+ *   torchsurv.metrics.cindex.ConcordanceIndex()(estimate, event, time)
+ *       partial_modality_training.py:290-294, simple_fusion.py:330-331
+ *   PartialModalityNet.forward / MultiModalSurvivalNet.forward (the fusion head)
+ *       partial_modality_training.py:234-277, final_multimodal.py:122-150
+ * A maintainer binds these entry points with ctypes (INTEGRATION.md shows the stub); the Python
+ * host layer in multimodal_survival_prediction_b200/ is exactly such a binding.
+ *
+ * Conventions for EVERY function:
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless named *_host;
+ *   - the caller owns every buffer (inputs, outputs, state, workspace); the library never allocates
+ *     device memory, never synchronises and never throws; work is ordered on `stream` only;
+ *   - `event` is one byte per row (torch.bool storage), non-zero = event observed;
+ *   - returns B200SURV_OK (0) or a negative b200surv_status; b200surv_last_error() (thread-local)
+ *     describes the last failure, including the CUDA error string for B200SURV_CUDA_ERROR;
+ *   - stateless and re-entrant: safe from PyTorch's autograd worker threads.
+ */
+#ifndef B200SURV_H_
+#define B200SURV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *b200surv_stream_t; /* == cudaStream_t */
+
+typedef enum {
+    B200SURV_OK = 0,
+    B200SURV_BAD_ARG = -1,
+    B200SURV_WORKSPACE_TOO_SMALL = -2,
+    B200SURV_UNSUPPORTED_ARCH = -3,
+    B200SURV_CUDA_ERROR = -4,
+    B200SURV_UNSUPPORTED = -5
+} b200surv_status;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int32_t b200surv_version(void);                 /* 1000*major + minor */
+int32_t b200surv_arch_check(int32_t device);    /* OK iff the device is compute capability 10.x */
+const char *b200surv_last_error(void);
+
+/* ---- Cox negative partial log-likelihood ------------------------------------------------- */
+/* ties: tie handling of the partial likelihood (replaces torchsurv's ties_method string). */
+#define B200SURV_TIES_BRESLOW 1
+#define B200SURV_TIES_EFRON 2
+/* reduction: MEAN_TERMS averages over the terms the method yields (one per event for Breslow,
+ * one per distinct event time for Efron -- torchsurv's "mean" as recollected);
+ * MEAN_EVENTS always divides by the number of events (the reference fallback's rule,
+ * partial_modality_training.py:309); SUM does not divide. */
+#define B200SURV_REDUCE_MEAN_TERMS 0
+#define B200SURV_REDUCE_SUM 1
+#define B200SURV_REDUCE_MEAN_EVENTS 2
+/* mode: which device algorithm runs.
+ *   SMALL  : one CTA per segment, any float times, every segment <= B200SURV_COX_SMALL_MAX rows.
+ *   BINNED : times must be integer-valued in [0, nbins) (days); no sort: two streaming passes over
+ *            (log_hz, time, event) = 22 algorithmic bytes per row for fwd+bwd.  Rows that violate
+ *            the precondition raise B200SURV_COXF_NOT_BINNABLE in the header and poison the loss
+ *            with NaN; the caller then re-runs with SORTED.
+ *   SORTED : any non-negative float times; radix sort on (time, event) + segmented scans. */
+#define B200SURV_COX_SMALL 1
+#define B200SURV_COX_BINNED 2
+#define B200SURV_COX_SORTED 3
+#define B200SURV_COX_SMALL_MAX 2048
+#define B200SURV_COX_MAX_BINS 16384
+
+/* header flags */
+#define B200SURV_COXF_NOT_BINNABLE 1u /* a time was non-integer or outside [0, nbins)            */
+#define B200SURV_COXF_EXP_RANGE 2u    /* max(log_hz) - shift > 80: exp() may overflow; re-run with
+                                         shift = max_log_hz (reported in the header)            */
+#define B200SURV_COXF_BAD_TIME 4u     /* NaN or negative time                                     */
+
+/* One header per segment at the start of the state buffer (device memory, 64 bytes each). */
+typedef struct {
+    uint32_t flags;        /* B200SURV_COXF_* */
+    int32_t mode;
+    float loss;            /* same value as out_loss[seg] */
+    float scale;           /* d loss / d pll = -1/normaliser (0 when the segment has no event) */
+    float shift;           /* exponent shift used: weights are exp(log_hz - shift) */
+    float max_log_hz;
+    float max_time;
+    int32_t nbins;
+    int64_t n_events;
+    int64_t n_event_times; /* distinct times carrying at least one event */
+    double pll;            /* partial log-likelihood before reduction */
+    int64_t reserved;
+} b200surv_cox_header;
+
+/* Bytes of caller-owned state (kept from fwd to bwd) and scratch workspace. */
+size_t b200surv_cox_state_bytes(int64_t n, int64_t n_seg, int32_t mode, int32_t nbins);
+size_t b200surv_cox_workspace_bytes(int64_t n, int64_t n_seg, int32_t mode, int32_t nbins);
+
+/* Forward: out_loss[n_seg] (device fp32) and the state buffer (headers + what bwd needs).
+ * seg_offsets: device int64[n_seg+1] row offsets of independent cohorts packed back to back, or
+ * NULL for one cohort of n rows.  shift: exponent shift (0 is right unless |log_hz| is huge).
+ * A segment with no event yields loss 0 and a zero gradient (reference fallback rule,
+ * partial_modality_training.py:298-301). */
+int32_t b200surv_cox_fwd(const float *log_hz, const float *time, const uint8_t *event,
+                         const int64_t *seg_offsets, int64_t n, int64_t n_seg, int32_t ties,
+                         int32_t reduction, int32_t mode, int32_t nbins, float shift,
+                         float *out_loss, void *state, size_t state_bytes, void *workspace,
+                         size_t workspace_bytes, b200surv_stream_t stream);
+
+/* Backward: out_grad[n] = grad_out[seg] * d loss[seg] / d log_hz, original row order. */
+int32_t b200surv_cox_bwd(const float *grad_out, const void *state, size_t state_bytes,
+                         const float *log_hz, const float *time, const uint8_t *event,
+                         const int64_t *seg_offsets, int64_t n, int64_t n_seg, int32_t mode,
+                         int32_t nbins, float *out_grad, b200surv_stream_t stream);
+
+/* Row-block sharded BINNED forward for multi-GPU: each rank accumulates its rows'
+ * per-bin aggregates, the caller all-reduces them (SUM over bins_sum, MAX over bins_max) with
+ * NCCL, then every rank finalises identically and runs b200surv_cox_bwd on its own rows.
+ *   bins_sum : double[n_seg][3*nbins + 4]  = S_all[nbins], S_event[nbins], m[nbins], sum of event
+ *              log_hz, then three violation counters (!= 0 means the flag is raised on some rank):
+ *              NOT_BINNABLE, (reserved), BAD_TIME  -- all SUM-reducible
+ *   bins_max : float[n_seg][2] = max log_hz, max time  -- MAX-reducible
+ * n is the rank-local row count in both calls (it sizes the workspace). */
+size_t b200surv_cox_bins_sum_count(int32_t nbins);
+int32_t b200surv_cox_binned_partial(const float *log_hz, const float *time, const uint8_t *event,
+                                    const int64_t *seg_offsets, int64_t n, int64_t n_seg,
+                                    int32_t nbins, float shift, double *bins_sum, float *bins_max,
+                                    void *workspace, size_t workspace_bytes,
+                                    b200surv_stream_t stream);
+int32_t b200surv_cox_binned_finalize(const double *bins_sum, const float *bins_max, int64_t n,
+                                     int64_t n_seg, int32_t ties, int32_t reduction, int32_t nbins, float shift,
+                                     float *out_loss, void *state, size_t state_bytes,
+                                     void *workspace, size_t workspace_bytes,
+                                     b200surv_stream_t stream);
+
+/* ---- Harrell's concordance index: integer pair counts -------------------------------------- */
+/* out_counts: int64[n_seg][6], ADDED to (caller zeroes): over rows i in [row_begin, row_end) of
+ * each segment and all columns j of the same segment,
+ *   strict pairs    (event_i && t_i <  t_j)            : [0] conc  [1] disc  [2] tied_risk
+ *   same-time pairs (event_i && !event_j && t_i == t_j) : [3] conc  [4] disc  [5] tied_risk
+ * with tie <=> fabsf(est_i - est_j) <= tied_tol (fp32), conc <=> !tie && est_j < est_i.
+ * Row-block sharding across GPUs = disjoint [row_begin,row_end) per rank + an int64 SUM
+ * all-reduce of the 6 counters (bit-exact, order independent).
+ * algo 0 = direct all-pairs tiles (no preprocessing); algo 1 = sort by (time, event) first so that
+ * every event row's comparable set is a suffix, then count over upper-triangular tiles only. */
+size_t b200surv_cindex_workspace_bytes(int64_t n, int64_t n_seg, int32_t algo);
+int32_t b200surv_cindex_counts(const float *estimate, const float *time, const uint8_t *event,
+                               const int64_t *seg_offsets, int64_t n, int64_t n_seg,
+                               int64_t row_begin, int64_t row_end, float tied_tol, int32_t algo,
+                               int64_t *out_counts, void *workspace, size_t workspace_bytes,
+                               b200surv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SURV_H_ */

@@ -1,0 +1,98 @@
+"""ctypes binding of libb200surv.so (include/b200surv.h).  No CPU fallback: if the library is
+missing or the device is not a B200-class (sm_100) GPU, every entry point raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200surv.so")
+
+OK = 0
+TIES = {"breslow": 1, "efron": 2}
+REDUCE_MEAN_TERMS, REDUCE_SUM, REDUCE_MEAN_EVENTS = 0, 1, 2
+COX_SMALL, COX_BINNED, COX_SORTED = 1, 2, 3
+COX_SMALL_MAX = 2048
+COX_MAX_BINS = 16384
+COXF_NOT_BINNABLE, COXF_EXP_RANGE, COXF_BAD_TIME = 1, 2, 4
+COX_HEADER_BYTES = 64
+
+
+class B200SurvError(RuntimeError):
+    pass
+
+
+class CoxHeader(ctypes.Structure):
+    _fields_ = [("flags", ctypes.c_uint32), ("mode", c_int32), ("loss", c_float), ("scale", c_float),
+                ("shift", c_float), ("max_log_hz", c_float), ("max_time", c_float), ("nbins", c_int32),
+                ("n_events", c_int64), ("n_event_times", c_int64), ("pll", ctypes.c_double),
+                ("reserved", c_int64)]
+
+
+assert ctypes.sizeof(CoxHeader) == COX_HEADER_BYTES
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+SIGNATURES = {
+    "b200surv_version": (c_int32, []),
+    "b200surv_arch_check": (c_int32, [c_int32]),
+    "b200surv_last_error": (c_char_p, []),
+    "b200surv_cox_state_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32]),
+    "b200surv_cox_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32]),
+    "b200surv_cox_bins_sum_count": (c_size_t, [c_int32]),
+    "b200surv_cox_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
+                                   c_int32, c_int32, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
+                                   c_void_p]),
+    "b200surv_cox_bwd": (c_int32, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                   c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200surv_cox_binned_partial": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+                                              c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200surv_cox_binned_finalize": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32,
+                                               c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
+                                               c_void_p]),
+    "b200surv_cindex_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
+    "b200surv_cindex_counts": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                         c_int64, c_float, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+_arch_ok = set()
+
+
+def load():
+    """Load the shared library (building is the job of build.py / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200SurvError(
+                f"{LIB_PATH} not found: build it with `python -m multimodal_survival_prediction_b200.build` "
+                "(there is no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != OK:
+        msg = load().b200surv_last_error()
+        raise B200SurvError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")
+
+
+def require_device(device_index: int):
+    """Fail loudly unless the CUDA device is compute capability 10.x."""
+    if device_index not in _arch_ok:
+        check(load().b200surv_arch_check(device_index), "b200surv_arch_check")
+        _arch_ok.add(device_index)
+
+
+def ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def stream_ptr(device):
+    import torch
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,50 @@
+// Library-level entry points of libb200surv: version, architecture gate, error string.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace b200surv {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int num_sms() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            cached = sms;
+        else
+            return 148;
+    }
+    return cached;
+}
+
+}  // namespace b200surv
+
+extern "C" {
+
+int32_t b200surv_version(void) { return 1000 * 0 + 1; }
+
+const char *b200surv_last_error(void) { return b200surv::g_err; }
+
+int32_t b200surv_arch_check(int32_t device) {
+    int major = 0, minor = 0;
+    B200_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    B200_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    if (major != 10) {
+        b200surv::set_error("device %d is sm_%d%d; libb200surv contains sm_100a code only", device, major,
+                            minor);
+        return B200SURV_UNSUPPORTED_ARCH;
+    }
+    return B200SURV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,353 @@
+// Harrell's concordance index: int64 pair counts on the GPU (tiled O(n^2) pair counting).
+//
+// Replaces torchsurv.metrics.cindex.ConcordanceIndex()(estimate, event, time) as called by the
+// reference at scripts/training/partial_modality_training.py:290-294 and simple_fusion.py:330-331;
+// pair rule and the six counters: include/b200surv.h, oracle/cindex_oracle.c.
+//
+// algo 0: literal all-pairs tiles, no preprocessing (kept as an independent cross-check).
+// algo 1: sort rows by (time, events first).  Then the comparable set of an event row is a SUFFIX of
+//   the sorted order: same-time censored rows [s, ge) followed by all later rows [ge, n).  Event rows
+//   selected by [row_begin,row_end) are compacted, their tie thresholds lo/hi (tie <=> lo <= e_j <= hi,
+//   found by bisection on the exact fp32 predicate) precomputed, and a tiled kernel counts
+//   #(e_j < lo) and #(e_j <= hi) over upper-triangular tiles only.  Column tiles are staged in shared
+//   memory and broadcast; each thread keeps 8 rows in registers; per-thread 32-bit counters are
+//   reduced with warp shuffles into int64 atomics once per CTA.
+// The radix sort / prefix sum of the preprocessing are CUB (library) in this round.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <climits>
+
+#include "common.cuh"
+
+namespace b200surv {
+namespace {
+
+__device__ __forceinline__ bool is_tie(float a, float b, float tol) { return fabsf(__fsub_rn(a, b)) <= tol; }
+
+// ------------------------------------------------------------------ algo 0: direct
+constexpr int A0_THREADS = 256;
+constexpr int A0_TILE = 1024;
+
+__global__ void __launch_bounds__(A0_THREADS)
+cindex_direct(const float *__restrict__ est, const float *__restrict__ time,
+              const uint8_t *__restrict__ event, int64_t n, int64_t row_begin, int64_t row_end,
+              float tol, unsigned long long *__restrict__ out) {
+    __shared__ float s_e[A0_TILE], s_t[A0_TILE];
+    __shared__ uint8_t s_v[A0_TILE];
+    __shared__ long long red[32];
+    const int64_t i = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < row_end && event[i] != 0;
+    const float ei = live ? est[i] : 0.f, ti = live ? time[i] : 0.f;
+    long long c[6] = {0, 0, 0, 0, 0, 0};
+    const int64_t c_begin = (int64_t)blockIdx.y * A0_TILE * 16, c_end = min(n, c_begin + (int64_t)A0_TILE * 16);
+    for (int64_t c0 = c_begin; c0 < c_end; c0 += A0_TILE) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < A0_TILE; k += blockDim.x) {
+            const int64_t j = c0 + k;
+            s_e[k] = j < n ? est[j] : 0.f;
+            s_t[k] = j < n ? time[j] : -INFINITY;  // never comparable: not > ti, not == ti (ti >= 0)
+            s_v[k] = j < n ? event[j] : 1;
+        }
+        __syncthreads();
+        if (live) {
+            const int lim = (int)min((int64_t)A0_TILE, n - c0);
+            for (int k = 0; k < lim; ++k) {
+                const float tj = s_t[k], ej = s_e[k];
+                const bool strict = tj > ti;
+                const bool same = (tj == ti) && !s_v[k];
+                if (strict || same) {
+                    const bool tie = is_tie(ei, ej, tol);
+                    const bool conc = !tie && (ej < ei);
+                    const int base = strict ? 0 : 3;
+                    c[base + (tie ? 2 : (conc ? 0 : 1))] += 1;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const long long v = block_reduce<long long>(c[q], 0ll, OpAddLL(), red);
+        if (threadIdx.x == 0 && v) atomicAdd(out + q, (unsigned long long)v);
+    }
+}
+
+// ------------------------------------------------------------------ algo 1: sorted suffix counting
+constexpr int CT_THREADS = 256;
+constexpr int CT_R = 8;                       // rows per thread
+constexpr int CT_ROWS = CT_THREADS * CT_R;    // 2048 rows per CTA
+constexpr int CT_TILE = 1024;                 // columns per shared-memory tile
+constexpr int CT_CHUNK_TILES = 8;             // column tiles per CTA
+
+struct Acc1 {
+    unsigned long long conc_s, le_s, conc_t, le_t, tot_s, tot_t;
+    unsigned long long n_rows, pad;
+};
+
+__device__ __forceinline__ uint32_t time_key(float t, bool ev) {
+    return (__float_as_uint(t + 0.f) << 1) | (ev ? 0u : 1u);
+}
+__device__ __forceinline__ uint32_t f2o(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float o2f(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+__global__ void __launch_bounds__(256)
+k_ci_keys(const float *__restrict__ time, const uint8_t *__restrict__ event, int64_t n,
+          uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, Acc1 *acc) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *acc = Acc1{0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        keys[i] = time_key(time[i], event[i] != 0);
+        vals[i] = (uint32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ci_flag(const float *__restrict__ est, const uint32_t *__restrict__ keys_s,
+          const uint32_t *__restrict__ idx_s, int64_t n, int64_t row_begin, int64_t row_end,
+          float *__restrict__ est_s, int *__restrict__ isrow) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = idx_s[p];
+        est_s[p] = est[i];
+        isrow[p] = (!(keys_s[p] & 1u) && (int64_t)i >= row_begin && (int64_t)i < row_end) ? 1 : 0;
+    }
+}
+
+__device__ __forceinline__ int lower_bound_u32(const uint32_t *a, int n, uint32_t v) {  // first a[q] >= v
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (int)(((unsigned)lo + (unsigned)hi) >> 1); if (a[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// per selected event row: comparable range [s, ge | ge, n), tie thresholds, row totals
+__global__ void __launch_bounds__(256)
+k_ci_rows(const uint32_t *__restrict__ keys_s, const float *__restrict__ est_s,
+          const int *__restrict__ isrow, const int *__restrict__ rank, int64_t n, float tol,
+          float *__restrict__ r_lo, float *__restrict__ r_hi, int *__restrict__ r_s,
+          int *__restrict__ r_ge, Acc1 *acc) {
+    __shared__ long long red[32];
+    long long tot_s = 0, tot_t = 0, nrows = 0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        if (!isrow[p]) continue;
+        const int k = rank[p];
+        const uint32_t key = keys_s[p], grp = key >> 1;
+        const int s = lower_bound_u32(keys_s, (int)n, (grp << 1) | 1u);
+        // grp + 1 cannot overflow 31 bits for finite non-negative times
+        const int ge = lower_bound_u32(keys_s, (int)n, (grp + 1u) << 1);
+        const float e = est_s[p];
+        float lo = e, hi = e;
+        if (!is_tie(e, e, tol)) {        // +-inf or NaN: nothing ties with it, not even itself
+            lo = e;                      // conc <=> e_j < e
+            hi = (e == e) ? ((e > 0.f) ? 3.402823466e+38f : __int_as_float(0x7fc00000)) : e;  // e_j <= hi <=> e_j < e
+        } else {
+            uint32_t a = f2o(-INFINITY), b = f2o(e);  // smallest o in [a,b] with tie
+            while (a < b) { const uint32_t mid = a + ((b - a) >> 1); if (is_tie(e, o2f(mid), tol)) b = mid; else a = mid + 1; }
+            lo = o2f(a);
+            a = f2o(e); b = f2o(INFINITY);            // largest o in [a,b] with tie
+            while (a < b) { const uint32_t mid = a + ((b - a + 1) >> 1); if (is_tie(e, o2f(mid), tol)) a = mid; else b = mid - 1; }
+            hi = o2f(a);
+        }
+        r_lo[k] = lo; r_hi[k] = hi; r_s[k] = s; r_ge[k] = ge;
+        tot_s += (long long)n - ge;
+        tot_t += (long long)ge - s;
+        nrows += 1;
+    }
+    tot_s = block_reduce<long long>(tot_s, 0ll, OpAddLL(), red);
+    tot_t = block_reduce<long long>(tot_t, 0ll, OpAddLL(), red);
+    nrows = block_reduce<long long>(nrows, 0ll, OpAddLL(), red);
+    if (threadIdx.x == 0) {
+        if (tot_s) atomicAdd(&acc->tot_s, (unsigned long long)tot_s);
+        if (tot_t) atomicAdd(&acc->tot_t, (unsigned long long)tot_t);
+        if (nrows) atomicAdd(&acc->n_rows, (unsigned long long)nrows);
+    }
+}
+
+// grid: x = column chunk, y = row tile (of compacted selected event rows)
+__global__ void __launch_bounds__(CT_THREADS)
+k_ci_count(const float *__restrict__ est_s, int64_t n, const float *__restrict__ r_lo,
+           const float *__restrict__ r_hi, const int *__restrict__ r_s, const int *__restrict__ r_ge,
+           Acc1 *acc) {
+    __shared__ __align__(16) float s_e[CT_TILE];
+    __shared__ int s_red[2][32];
+    __shared__ long long red[32];
+    const long long n_rows = (long long)acc->n_rows;
+    const long long k0 = (long long)blockIdx.y * CT_ROWS;
+    if (k0 >= n_rows) return;
+    const int chunk0 = blockIdx.x * (CT_TILE * CT_CHUNK_TILES);
+    const int chunk1 = (int)min((long long)n, (long long)chunk0 + CT_TILE * CT_CHUNK_TILES);
+
+    float lo[CT_R], hi[CT_R];
+    int rs[CT_R], rg[CT_R];
+    int mins = INT_MAX, maxge = 0;
+#pragma unroll
+    for (int u = 0; u < CT_R; ++u) {
+        const long long k = k0 + threadIdx.x + (long long)u * CT_THREADS;
+        if (k < n_rows) {
+            lo[u] = r_lo[k]; hi[u] = r_hi[k]; rs[u] = r_s[k]; rg[u] = r_ge[k];
+            mins = min(mins, rs[u]); maxge = max(maxge, rg[u]);
+        } else {  // padding row: empty comparable range, NaN thresholds never compare true
+            lo[u] = __int_as_float(0x7fc00000); hi[u] = lo[u]; rs[u] = INT_MAX; rg[u] = INT_MAX;
+        }
+    }
+    // CTA-wide min(s) and max(ge) decide, per column tile, between skip / fast / general
+    {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mins = min(mins, __shfl_xor_sync(FULL, mins, o));
+            maxge = max(maxge, __shfl_xor_sync(FULL, maxge, o));
+        }
+        if (lane == 0) { s_red[0][wid] = mins; s_red[1][wid] = maxge; }
+        __syncthreads();
+        mins = INT_MAX; maxge = 0;
+        for (int w = 0; w < CT_THREADS / 32; ++w) { mins = min(mins, s_red[0][w]); maxge = max(maxge, s_red[1][w]); }
+    }
+    if (chunk1 <= mins) return;  // whole chunk precedes every row's comparable range
+
+    unsigned cs[CT_R], ls[CT_R];      // strict: #(e_j < lo), #(e_j <= hi)
+    unsigned long long conc_t = 0, le_t = 0;  // same-time (rare, general path only)
+#pragma unroll
+    for (int u = 0; u < CT_R; ++u) { cs[u] = 0; ls[u] = 0; }
+
+    for (int c0 = chunk0; c0 < chunk1; c0 += CT_TILE) {
+        const int c1 = min(c0 + CT_TILE, chunk1);
+        if (c1 <= mins) continue;
+        __syncthreads();
+        for (int q = threadIdx.x; q < CT_TILE; q += CT_THREADS) s_e[q] = (c0 + q < n) ? est_s[c0 + q] : 0.f;
+        __syncthreads();
+        if (c0 >= maxge && c1 - c0 == CT_TILE) {
+            // fast path: every (row, column) pair of this tile is a strict comparable pair
+#pragma unroll 2
+            for (int q = 0; q < CT_TILE; q += 4) {
+                const float4 e4 = *reinterpret_cast<const float4 *>(s_e + q);
+#pragma unroll
+                for (int u = 0; u < CT_R; ++u) {
+                    cs[u] += (e4.x < lo[u]) + (e4.y < lo[u]) + (e4.z < lo[u]) + (e4.w < lo[u]);
+                    ls[u] += (e4.x <= hi[u]) + (e4.y <= hi[u]) + (e4.z <= hi[u]) + (e4.w <= hi[u]);
+                }
+            }
+        } else {
+            const int lim = c1 - c0;
+            for (int q = 0; q < lim; ++q) {
+                const float ej = s_e[q];
+                const int j = c0 + q;
+#pragma unroll
+                for (int u = 0; u < CT_R; ++u) {
+                    const bool lt = ej < lo[u], le = ej <= hi[u];
+                    if (j >= rg[u]) { cs[u] += lt; ls[u] += le; }
+                    else if (j >= rs[u]) { conc_t += lt; le_t += le; }
+                }
+            }
+        }
+    }
+    long long a = 0, b = 0;
+#pragma unroll
+    for (int u = 0; u < CT_R; ++u) { a += cs[u]; b += ls[u]; }
+    a = block_reduce<long long>(a, 0ll, OpAddLL(), red);
+    b = block_reduce<long long>(b, 0ll, OpAddLL(), red);
+    const long long c = block_reduce<long long>((long long)conc_t, 0ll, OpAddLL(), red);
+    const long long d = block_reduce<long long>((long long)le_t, 0ll, OpAddLL(), red);
+    if (threadIdx.x == 0) {
+        if (a) atomicAdd(&acc->conc_s, (unsigned long long)a);
+        if (b) atomicAdd(&acc->le_s, (unsigned long long)b);
+        if (c) atomicAdd(&acc->conc_t, (unsigned long long)c);
+        if (d) atomicAdd(&acc->le_t, (unsigned long long)d);
+    }
+}
+
+__global__ void k_ci_final(const Acc1 *acc, long long *out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        out[0] += (long long)acc->conc_s;
+        out[1] += (long long)(acc->tot_s - acc->le_s);
+        out[2] += (long long)(acc->le_s - acc->conc_s);
+        out[3] += (long long)acc->conc_t;
+        out[4] += (long long)(acc->tot_t - acc->le_t);
+        out[5] += (long long)(acc->le_t - acc->conc_t);
+    }
+}
+
+struct CiLayout {
+    size_t off_acc, off_keys, off_vals, off_keys_s, off_idx_s, off_est_s, off_isrow, off_rank, off_lo, off_hi,
+        off_s, off_ge, off_cub, cub_bytes, total;
+};
+CiLayout ci_layout(int64_t n) {
+    CiLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    const size_t N = (size_t)(n > 0 ? n : 1);
+    L.off_acc = take(sizeof(Acc1));
+    L.off_keys = take(N * 4); L.off_vals = take(N * 4); L.off_keys_s = take(N * 4); L.off_idx_s = take(N * 4);
+    L.off_est_s = take(N * 4 + 16); L.off_isrow = take(N * 4); L.off_rank = take(N * 4);
+    L.off_lo = take(N * 4); L.off_hi = take(N * 4); L.off_s = take(N * 4); L.off_ge = take(N * 4);
+    size_t mx = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, (int)N);
+    mx = b > mx ? b : mx;
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (int *)nullptr, (int *)nullptr, (int)N);
+    mx = b > mx ? b : mx;
+    L.cub_bytes = mx + 256;
+    L.off_cub = take(L.cub_bytes);
+    L.total = o;
+    return L;
+}
+
+}  // namespace
+
+size_t cindex_workspace_bytes(int64_t n, int algo) { return algo == 0 ? 256 : ci_layout(n).total; }
+
+int32_t cindex_counts_launch(const float *est, const float *time, const uint8_t *event, int64_t n,
+                             int64_t row_begin, int64_t row_end, float tol, int algo, int64_t *out, void *ws,
+                             size_t ws_bytes, cudaStream_t st) {
+    B200_REQUIRE(n >= 0 && n < (int64_t)INT_MAX, "n must be < 2^31");
+    B200_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n, "row range");
+    B200_REQUIRE(tol >= 0.f, "tied_tol must be >= 0");
+    if (n == 0 || row_begin == row_end) return B200SURV_OK;
+    if (algo == 0) {
+        const int64_t rows = row_end - row_begin;
+        const unsigned gx = (unsigned)((rows + A0_THREADS - 1) / A0_THREADS);
+        const unsigned gy = (unsigned)((n + A0_TILE * 16 - 1) / (A0_TILE * 16));
+        B200_REQUIRE(gy <= 65535, "algo 0 supports n <= 2^30");
+        cindex_direct<<<dim3(gx, gy), A0_THREADS, 0, st>>>(est, time, event, n, row_begin, row_end, tol,
+                                                           reinterpret_cast<unsigned long long *>(out));
+        B200_CHECK_CUDA(cudaGetLastError());
+        return B200SURV_OK;
+    }
+    B200_REQUIRE(algo == 1, "algo must be 0 or 1");
+    const CiLayout L = ci_layout(n);
+    if (ws_bytes < L.total) { set_error("cindex: workspace %zu < %zu", ws_bytes, L.total); return B200SURV_WORKSPACE_TOO_SMALL; }
+    unsigned char *w8 = static_cast<unsigned char *>(ws);
+    Acc1 *acc = reinterpret_cast<Acc1 *>(w8 + L.off_acc);
+    uint32_t *keys = reinterpret_cast<uint32_t *>(w8 + L.off_keys), *vals = reinterpret_cast<uint32_t *>(w8 + L.off_vals),
+             *keys_s = reinterpret_cast<uint32_t *>(w8 + L.off_keys_s), *idx_s = reinterpret_cast<uint32_t *>(w8 + L.off_idx_s);
+    float *est_s = reinterpret_cast<float *>(w8 + L.off_est_s);
+    int *isrow = reinterpret_cast<int *>(w8 + L.off_isrow), *rank = reinterpret_cast<int *>(w8 + L.off_rank);
+    float *r_lo = reinterpret_cast<float *>(w8 + L.off_lo), *r_hi = reinterpret_cast<float *>(w8 + L.off_hi);
+    int *r_s = reinterpret_cast<int *>(w8 + L.off_s), *r_ge = reinterpret_cast<int *>(w8 + L.off_ge);
+    void *cub_tmp = w8 + L.off_cub;
+    size_t cb = L.cub_bytes;
+    int grid = (int)((n + 255) / 256);
+    const int cap = 16 * num_sms();
+    if (grid > cap) grid = cap;
+    k_ci_keys<<<grid, 256, 0, st>>>(time, event, n, keys, vals, acc);
+    B200_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys, keys_s, vals, idx_s, (int)n, 0, 32, st));
+    k_ci_flag<<<grid, 256, 0, st>>>(est, keys_s, idx_s, n, row_begin, row_end, est_s, isrow);
+    cb = L.cub_bytes;
+    B200_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cb, isrow, rank, (int)n, st));
+    k_ci_rows<<<grid, 256, 0, st>>>(keys_s, est_s, isrow, rank, n, tol, r_lo, r_hi, r_s, r_ge, acc);
+    {
+        // upper bound on selected rows known to the host: min(n, row_end - row_begin)
+        const int64_t max_rows = row_end - row_begin;
+        const unsigned gy = (unsigned)((max_rows + CT_ROWS - 1) / CT_ROWS);
+        const unsigned gx = (unsigned)((n + CT_TILE * CT_CHUNK_TILES - 1) / (CT_TILE * CT_CHUNK_TILES));
+        B200_REQUIRE(gy <= 65535, "too many row tiles");
+        k_ci_count<<<dim3(gx, gy), CT_THREADS, 0, st>>>(est_s, n, r_lo, r_hi, r_s, r_ge, acc);
+    }
+    k_ci_final<<<1, 32, 0, st>>>(acc, reinterpret_cast<long long *>(out));
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+}  // namespace b200surv

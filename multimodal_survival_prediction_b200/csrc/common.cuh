@@ -1,0 +1,116 @@
+// Shared device/host helpers for libb200surv (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200surv.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libb200surv is written for sm_100a (B200) only"
+#endif
+
+namespace b200surv {
+
+void set_error(const char *fmt, ...);
+
+#define B200_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            ::b200surv::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                \
+                                  cudaGetErrorString(_e));                                     \
+            return B200SURV_CUDA_ERROR;                                                        \
+        }                                                                                      \
+    } while (0)
+
+#define B200_REQUIRE(cond, msg)                                                                \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            ::b200surv::set_error("%s:%d: bad argument: %s (%s)", __FILE__, __LINE__, msg, #cond); \
+            return B200SURV_BAD_ARG;                                                           \
+        }                                                                                      \
+    } while (0)
+
+inline cudaStream_t as_stream(b200surv_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int num_sms();  // cached per process (148 on B200)
+
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned warp_or(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// Block-wide reductions through a caller-provided shared scratch of >= 32 elements.
+// Result valid in every thread.  All threads of the block must call.
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, T identity, Op op, T *scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(FULL, v, o));
+    __syncthreads();  // scratch may still be read from a previous call
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    T r = (lane < nw) ? scratch[lane] : identity;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = op(r, __shfl_xor_sync(FULL, r, o));
+    return r;
+}
+struct OpAddD { __device__ double operator()(double a, double b) const { return a + b; } };
+struct OpAddF { __device__ float operator()(float a, float b) const { return a + b; } };
+struct OpAddLL { __device__ long long operator()(long long a, long long b) const { return a + b; } };
+struct OpMaxF { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct OpOrU { __device__ unsigned operator()(unsigned a, unsigned b) const { return a | b; } };
+
+// float atomic max for any sign (CAS free): positive floats order as ints, negative as reversed uints
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned *>(addr), __float_as_uint(v));
+}
+
+// streaming (read-once) 128-bit / 32-bit loads that do not pollute L1
+__device__ __forceinline__ float4 ldg_stream_f4(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float *p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w) : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace b200surv

@@ -1,0 +1,140 @@
+// extern "C" entry points for the Cox loss and the C-index (declared in include/b200surv.h).
+#include "common.cuh"
+
+namespace b200surv {
+// cox_binned.cu
+size_t cox_binned_state_bytes(int64_t n_seg, int nb);
+size_t cox_binned_workspace_bytes(int64_t n, int64_t n_seg, int nb);
+int32_t cox_binned_partial(const float *, const float *, const uint8_t *, const int64_t *, int64_t, int64_t, int,
+                           float, double *, float *, void *, size_t, cudaStream_t);
+int32_t cox_binned_finalize(const double *, const float *, int64_t, int64_t, int, int, int, float, float *, void *,
+                            size_t, void *, size_t, cudaStream_t);
+int32_t cox_binned_fwd(const float *, const float *, const uint8_t *, const int64_t *, int64_t, int64_t, int, int,
+                       int, float, float *, void *, size_t, void *, size_t, cudaStream_t);
+int32_t cox_binned_bwd_launch(const float *, const void *, size_t, const float *, const float *, const uint8_t *,
+                              const int64_t *, int64_t, int64_t, int, float *, cudaStream_t);
+// cox_small.cu
+int32_t cox_small_fwd_launch(const float *, const float *, const uint8_t *, const int64_t *, int64_t, int64_t, int,
+                             int, float *, void *, size_t, cudaStream_t);
+int32_t cox_scale_grad_launch(const float *, const void *, const int64_t *, int64_t, int64_t, float *, cudaStream_t);
+// cox_sorted.cu
+size_t cox_sorted_workspace_bytes(int64_t n);
+int32_t cox_sorted_fwd_launch(const float *, const float *, const uint8_t *, int64_t, int, int, float *, void *,
+                              size_t, void *, size_t, cudaStream_t);
+// cindex.cu
+size_t cindex_workspace_bytes(int64_t n, int algo);
+int32_t cindex_counts_launch(const float *, const float *, const uint8_t *, int64_t, int64_t, int64_t, float, int,
+                             int64_t *, void *, size_t, cudaStream_t);
+}  // namespace b200surv
+
+using namespace b200surv;
+
+extern "C" {
+
+size_t b200surv_cox_state_bytes(int64_t n, int64_t n_seg, int32_t mode, int32_t nbins) {
+    if (n < 0 || n_seg < 1) return 0;
+    if (mode == B200SURV_COX_BINNED) return cox_binned_state_bytes(n_seg, nbins);
+    return (size_t)n_seg * sizeof(b200surv_cox_header) + (size_t)n * sizeof(float);
+}
+
+size_t b200surv_cox_workspace_bytes(int64_t n, int64_t n_seg, int32_t mode, int32_t nbins) {
+    if (n < 0 || n_seg < 1) return 0;
+    if (mode == B200SURV_COX_BINNED) return cox_binned_workspace_bytes(n, n_seg, nbins);
+    if (mode == B200SURV_COX_SORTED) return cox_sorted_workspace_bytes(n);
+    return 256;
+}
+
+size_t b200surv_cox_bins_sum_count(int32_t nbins) { return 3 * (size_t)nbins + 4; }
+
+int32_t b200surv_cox_fwd(const float *log_hz, const float *time, const uint8_t *event,
+                         const int64_t *seg_offsets, int64_t n, int64_t n_seg, int32_t ties,
+                         int32_t reduction, int32_t mode, int32_t nbins, float shift, float *out_loss,
+                         void *state, size_t state_bytes, void *workspace, size_t workspace_bytes,
+                         b200surv_stream_t stream) {
+    B200_REQUIRE(log_hz && time && event && out_loss && state, "null pointer");
+    B200_REQUIRE(n >= 1, "n must be >= 1");
+    B200_REQUIRE(n_seg >= 1, "n_seg must be >= 1");
+    B200_REQUIRE(n_seg == 1 || seg_offsets != nullptr, "seg_offsets required when n_seg > 1");
+    cudaStream_t st = as_stream(stream);
+    switch (mode) {
+        case B200SURV_COX_SMALL:
+            return cox_small_fwd_launch(log_hz, time, event, seg_offsets, n, n_seg, ties, reduction, out_loss, state,
+                                        state_bytes, st);
+        case B200SURV_COX_BINNED:
+            B200_REQUIRE(workspace != nullptr, "workspace");
+            return cox_binned_fwd(log_hz, time, event, seg_offsets, n, n_seg, ties, reduction, nbins, shift, out_loss,
+                                  state, state_bytes, workspace, workspace_bytes, st);
+        case B200SURV_COX_SORTED:
+            B200_REQUIRE(workspace != nullptr, "workspace");
+            if (n_seg != 1) { set_error("SORTED mode handles one cohort per call"); return B200SURV_UNSUPPORTED; }
+            return cox_sorted_fwd_launch(log_hz, time, event, n, ties, reduction, out_loss, state, state_bytes,
+                                         workspace, workspace_bytes, st);
+        default:
+            set_error("unknown cox mode %d", mode);
+            return B200SURV_BAD_ARG;
+    }
+}
+
+int32_t b200surv_cox_bwd(const float *grad_out, const void *state, size_t state_bytes, const float *log_hz,
+                         const float *time, const uint8_t *event, const int64_t *seg_offsets, int64_t n,
+                         int64_t n_seg, int32_t mode, int32_t nbins, float *out_grad, b200surv_stream_t stream) {
+    B200_REQUIRE(grad_out && state && out_grad, "null pointer");
+    B200_REQUIRE(n >= 1 && n_seg >= 1, "n, n_seg");
+    B200_REQUIRE(n_seg == 1 || seg_offsets != nullptr, "seg_offsets required when n_seg > 1");
+    cudaStream_t st = as_stream(stream);
+    if (mode == B200SURV_COX_BINNED) {
+        B200_REQUIRE(log_hz && time && event, "BINNED backward re-reads the inputs");
+        return cox_binned_bwd_launch(grad_out, state, state_bytes, log_hz, time, event, seg_offsets, n, n_seg, nbins,
+                                     out_grad, st);
+    }
+    if (mode == B200SURV_COX_SMALL || mode == B200SURV_COX_SORTED) {
+        const size_t need = (size_t)n_seg * sizeof(b200surv_cox_header) + (size_t)n * sizeof(float);
+        if (state_bytes < need) { set_error("cox bwd: state buffer %zu < %zu", state_bytes, need); return B200SURV_WORKSPACE_TOO_SMALL; }
+        return cox_scale_grad_launch(grad_out, state, seg_offsets, n, n_seg, out_grad, st);
+    }
+    set_error("unknown cox mode %d", mode);
+    return B200SURV_BAD_ARG;
+}
+
+int32_t b200surv_cox_binned_partial(const float *log_hz, const float *time, const uint8_t *event,
+                                    const int64_t *seg_offsets, int64_t n, int64_t n_seg, int32_t nbins,
+                                    float shift, double *bins_sum, float *bins_max, void *workspace,
+                                    size_t workspace_bytes, b200surv_stream_t stream) {
+    B200_REQUIRE(log_hz && time && event && bins_sum && bins_max && workspace, "null pointer");
+    B200_REQUIRE(n >= 1 && n_seg >= 1, "n, n_seg");
+    B200_REQUIRE(n_seg == 1 || seg_offsets != nullptr, "seg_offsets required when n_seg > 1");
+    return cox_binned_partial(log_hz, time, event, seg_offsets, n, n_seg, nbins, shift, bins_sum, bins_max, workspace,
+                              workspace_bytes, as_stream(stream));
+}
+
+int32_t b200surv_cox_binned_finalize(const double *bins_sum, const float *bins_max, int64_t n, int64_t n_seg,
+                                     int32_t ties, int32_t reduction, int32_t nbins, float shift, float *out_loss,
+                                     void *state, size_t state_bytes, void *workspace, size_t workspace_bytes,
+                                     b200surv_stream_t stream) {
+    B200_REQUIRE(bins_sum && bins_max && out_loss && state && workspace, "null pointer");
+    B200_REQUIRE(n >= 1 && n_seg >= 1, "n, n_seg");
+    return cox_binned_finalize(bins_sum, bins_max, n, n_seg, ties, reduction, nbins, shift, out_loss, state,
+                               state_bytes, workspace, workspace_bytes, as_stream(stream));
+}
+
+size_t b200surv_cindex_workspace_bytes(int64_t n, int64_t n_seg, int32_t algo) {
+    if (n < 0 || n_seg < 1) return 0;
+    return cindex_workspace_bytes(n, algo);
+}
+
+int32_t b200surv_cindex_counts(const float *estimate, const float *time, const uint8_t *event,
+                               const int64_t *seg_offsets, int64_t n, int64_t n_seg, int64_t row_begin,
+                               int64_t row_end, float tied_tol, int32_t algo, int64_t *out_counts, void *workspace,
+                               size_t workspace_bytes, b200surv_stream_t stream) {
+    B200_REQUIRE(estimate && time && event && out_counts, "null pointer");
+    B200_REQUIRE(n >= 0, "n");
+    if (n_seg != 1 || seg_offsets != nullptr) {
+        set_error("segmented C-index: call once per cohort (n_seg must be 1 in this version)");
+        return B200SURV_UNSUPPORTED;
+    }
+    B200_REQUIRE(algo == 0 || workspace != nullptr, "workspace");
+    return cindex_counts_launch(estimate, time, event, n, row_begin, row_end, tied_tol, algo, out_counts, workspace,
+                                workspace_bytes, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+"""Row-block sharding of the hot path across the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink).  The reference has no distributed code;
+this is the scale-out of the two operators it calls:
+
+* C-index: every rank holds the full (estimate, event, time) vectors (9 bytes/row), counts the pairs
+  of its own row block against all columns, then ONE int64 SUM all-reduce of the six counters
+  (48 bytes) -- integer, so the result is bit-identical to the single-GPU result.
+* Cox loss (BINNED mode): every rank accumulates per-bin aggregates of its own rows
+  (b200surv_cox_binned_partial), ONE fp64 SUM all-reduce of 3*nbins+4 doubles plus a 2-float MAX
+  all-reduce, then every rank finalises identically (b200surv_cox_binned_finalize) and computes the
+  gradient of its own rows (b200surv_cox_bwd).  The gradient stays sharded like the input.
+
+The host logic (shard bounds, which collectives with which reduce op) is backend-agnostic and is
+covered on CPU with gloo at world_size 2 (tests/test_dist_cpu.py) by injecting the per-shard compute.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous row block [a, b) of rank; blocks differ by at most one row."""
+    base, rem = divmod(n, world)
+    a = rank * base + min(rank, rem)
+    return a, a + base + (1 if rank < rem else 0)
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+# ------------------------------------------------------------------ C-index
+def cindex_counts_sharded(estimate, event, time, tied_tol=1e-8, algo=1, group=None, _count_fn=None):
+    """All ranks pass the same full vectors; returns the global int64[6] counters on every rank."""
+    rank, world = _world()
+    a, b = shard_bounds(estimate.numel(), rank, world)
+    if _count_fn is None:
+        from .cindex import cindex_counts as _count_fn
+    counts = _count_fn(estimate, event, time, tied_tol, a, b, algo)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+# ------------------------------------------------------------------ Cox (BINNED)
+class ShardedCoxBinned:
+    """Pre-allocated buffers for repeated sharded fwd+bwd over this rank's rows."""
+
+    def __init__(self, n_local: int, device, nbins: int = 4096, ties: str = "efron", reduction: int = L.REDUCE_MEAN_TERMS):
+        self.lib = L.load()
+        L.require_device(device.index)
+        self.n, self.nb, self.dev = n_local, nbins, device
+        self.ties, self.red = L.TIES[ties], reduction
+        self.cnt = self.lib.b200surv_cox_bins_sum_count(nbins)
+        self.bins_sum = torch.empty(self.cnt, dtype=torch.float64, device=device)
+        self.bins_max = torch.empty(2, dtype=torch.float32, device=device)
+        self.sb = self.lib.b200surv_cox_state_bytes(n_local, 1, L.COX_BINNED, nbins)
+        self.wb = self.lib.b200surv_cox_workspace_bytes(n_local, 1, L.COX_BINNED, nbins)
+        self.state = torch.empty(self.sb, dtype=torch.uint8, device=device)
+        self.ws = torch.empty(self.wb, dtype=torch.uint8, device=device)
+        self.loss = torch.empty(1, dtype=torch.float32, device=device)
+        self.ones = torch.ones(1, dtype=torch.float32, device=device)
+
+    def forward(self, log_hz, time, event, shift: float = 0.0, group=None):
+        st = L.stream_ptr(self.dev)
+        rc = self.lib.b200surv_cox_binned_partial(L.ptr(log_hz), L.ptr(time), L.ptr(event), None, self.n, 1, self.nb,
+                                                  ctypes.c_float(shift), L.ptr(self.bins_sum), L.ptr(self.bins_max),
+                                                  L.ptr(self.ws), self.wb, st)
+        L.check(rc, "b200surv_cox_binned_partial")
+        _, world = _world()
+        if world > 1:
+            dist.all_reduce(self.bins_sum, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.bins_max, op=dist.ReduceOp.MAX, group=group)
+        rc = self.lib.b200surv_cox_binned_finalize(L.ptr(self.bins_sum), L.ptr(self.bins_max), self.n, 1, self.ties,
+                                                   self.red, self.nb, ctypes.c_float(shift), L.ptr(self.loss),
+                                                   L.ptr(self.state), self.sb, L.ptr(self.ws), self.wb, st)
+        L.check(rc, "b200surv_cox_binned_finalize")
+        return self.loss
+
+    def backward(self, log_hz, time, event, out_grad, grad_out=None):
+        g = self.ones if grad_out is None else grad_out
+        rc = self.lib.b200surv_cox_bwd(L.ptr(g), L.ptr(self.state), self.sb, L.ptr(log_hz), L.ptr(time), L.ptr(event),
+                                       None, self.n, 1, L.COX_BINNED, self.nb, L.ptr(out_grad), L.stream_ptr(self.dev))
+        L.check(rc, "b200surv_cox_bwd")
+        return out_grad

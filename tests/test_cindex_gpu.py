@@ -1,0 +1,103 @@
+"""GPU parity tests of the C-index pair counters: bit-exact int64 counts vs the C oracle."""
+import numpy as np
+import pytest
+import torch
+
+import multimodal_survival_prediction_b200 as pkg
+from multimodal_survival_prediction_b200 import synth
+from oracle import cindex as oci
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_counts(est, ev, t, tol=1e-8, algo=1, row_begin=0, row_end=None):
+    out = pkg.cindex_counts(torch.as_tensor(est, dtype=torch.float32).cuda(), torch.as_tensor(ev).bool().cuda(),
+                            torch.as_tensor(t, dtype=torch.float32).cuda(), tol, row_begin, row_end, algo)
+    return out.cpu().numpy()
+
+
+def cohort(n, seed, tmax=7, risk_ties=False):
+    rng = np.random.default_rng(seed)
+    t = rng.integers(0, tmax + 1, n).astype(np.float32)
+    ev = rng.random(n) < 0.5
+    est = rng.normal(size=n).astype(np.float32)
+    if risk_ties:
+        est = (np.round(est * 3) / 3).astype(np.float32)
+    return est, ev, t
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_golden_reference_fallback_vectors(golden, algo):
+    g = golden("cindex_fallback.npz")
+    for c in g["cases"]:
+        est, ev, t = g[f"{c}/est"], g[f"{c}/event"], g[f"{c}/time"]
+        counts = gpu_counts(est, ev, t, 0.0, algo)
+        assert (counts == oci.counts_brute(est, ev, t, 0.0)).all(), c
+        assert np.float32(pkg.cindex_from_counts(counts, "fallback")) == g[f"{c}/value"], c
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("tol", [0.0, 1e-8, 0.3])
+def test_counts_bit_exact_small_and_ragged(algo, tol):
+    for n, seed, tmax, rt in ((1, 0, 3, False), (2, 1, 1, False), (5, 2, 2, True), (100, 3, 7, True),
+                              (1000, 4, 30, False), (2047, 5, 5, True), (2049, 6, 500, True), (5000, 7, 4000, False)):
+        est, ev, t = cohort(n, seed, tmax, rt)
+        assert (gpu_counts(est, ev, t, tol, algo) == oci.counts_brute(est, ev, t, tol)).all(), (n, seed)
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_known_answers_and_special_values(algo):
+    est = np.zeros(64, np.float32); ev = np.ones(64, bool); t = np.arange(64, dtype=np.float32)
+    c = gpu_counts(est, ev, t, 1e-8, algo)
+    assert list(c) == [0, 0, 64 * 63 // 2, 0, 0, 0]                      # KA3
+    c = gpu_counts(-t, ev, t, 1e-8, algo)
+    assert list(c) == [64 * 63 // 2, 0, 0, 0, 0, 0]                      # KA4
+    c = gpu_counts(est, ev, np.ones(64, np.float32), 1e-8, algo)
+    assert c.sum() == 0                                                   # KA2
+    # infinities and NaN estimates follow the fp32 predicate literally
+    est, ev, t = cohort(300, 11, 9, True)
+    est[::7] = np.inf; est[3::11] = -np.inf; est[5::13] = np.nan
+    assert (gpu_counts(est, ev, t, 1e-8, algo) == oci.counts_brute(est, ev, t, 1e-8)).all()
+    assert (gpu_counts(est, ev, t, 0.5, algo) == oci.counts_brute(est, ev, t, 0.5)).all()
+    # times: zero, huge, infinite
+    t2 = t.copy(); t2[::5] = 0.0; t2[1::9] = 3e38; t2[2::17] = np.inf
+    assert (gpu_counts(est, ev, t2, 1e-8, algo) == oci.counts_brute(est, ev, t2, 1e-8)).all()
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_row_sharding_adds_up(algo):
+    lh, ev, t = synth.cohort(30_000, 5, risk_tie_frac=0.1)
+    full = oci.counts_fast(lh.numpy(), ev.numpy(), t.numpy())
+    cuts = [0, 7000, 7001, 19_999, 30_000]
+    acc = np.zeros(6, np.int64)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        part = gpu_counts(lh, ev, t, 1e-8, algo, a, b)
+        assert (part == oci.counts_brute(lh.numpy(), ev.numpy(), t.numpy(), 1e-8, a, b)).all()
+        acc += part
+    assert (acc == full).all()
+
+
+def test_moderate_and_full_size():
+    for n, seed in ((100_000, 1), (1 << 20, 1234)):        # BASELINE.json configs[3]: 1M patients
+        for frac in (0.0, 0.1):
+            lh, ev, t = synth.cohort(n, seed, risk_tie_frac=frac)
+            ref = oci.counts_fast(lh.numpy(), ev.numpy(), t.numpy())
+            assert (gpu_counts(lh, ev, t, 1e-8, 1) == ref).all(), (n, frac)
+    lh, ev, t = synth.cohort(200_000, 2, risk_tie_frac=0.1)
+    assert (gpu_counts(lh, ev, t, 1e-8, 0) == oci.counts_fast(lh.numpy(), ev.numpy(), t.numpy())).all()
+    # few ties in time (float times)
+    lh, ev, t = synth.cohort(100_000, 3, few_ties=True)
+    assert (gpu_counts(lh, ev, t, 1e-8, 1) == oci.counts_fast(lh.numpy(), ev.numpy(), t.numpy())).all()
+
+
+def test_concordance_index_object_api():
+    lh, ev, t = synth.cohort(348, 0)
+    ci = pkg.ConcordanceIndex()
+    val = ci(lh, ev, t)                      # CPU tensors in, like the reference's validate()
+    assert val.device.type == "cpu" and val.dtype == torch.float32 and val.dim() == 0
+    ref = oci.counts_brute(lh.numpy(), ev.numpy(), t.numpy())
+    assert ci.counts == list(ref)
+    assert val.item() == np.float32(oci.cindex_from_counts(ref))
+    val_gpu = pkg.ConcordanceIndex(convention="fallback")(lh.cuda(), ev.cuda(), t.cuda())
+    assert val_gpu.is_cuda and val_gpu.item() == np.float32(oci.cindex_from_counts(ref, "fallback"))
+    assert pkg.ConcordanceIndex()(lh[:0], ev[:0], t[:0]).item() == 0.5
