@@ -208,6 +208,15 @@ def run_b200(args):
     value = world * n / (ms_step * 1e-3)
     loss_val = float(op.loss.item())
 
+    if args.skip_extras:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "patients/s", "n_gpus": world,
+                              "steps": args.steps, "ms_per_step": ms_step, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+                              "note": "--skip-extras: partial line, not a bench result"}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- e2e: public Python API, pinned host inputs -> H2D -> fwd (auto mode) -> bwd -> loss D2H
     def e2e_step():
         xd = pin[0].to(dev, non_blocking=True).requires_grad_(True)
@@ -297,6 +306,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=N_ROWS, help="rows per GPU (default: the BASELINE 16,777,216)")
+    ap.add_argument("--skip-extras", action="store_true", help="only the timed fwd+bwd loop (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

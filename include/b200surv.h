@@ -60,7 +60,7 @@ const char *b200surv_last_error(void);
 #define B200SURV_REDUCE_MEAN_EVENTS 2
 /* mode: which device algorithm runs.
  *   SMALL  : one CTA per segment, any float times, every segment <= B200SURV_COX_SMALL_MAX rows.
- *   BINNED : times must be integer-valued in [0, nbins) (days); no sort: two streaming passes over
+ *   BINNED : times must be integer-valued in [0, nbins), nbins <= 8192 (days); no sort: two streaming passes over
  *            (log_hz, time, event) = 22 algorithmic bytes per row for fwd+bwd.  Rows that violate
  *            the precondition raise B200SURV_COXF_NOT_BINNABLE in the header and poison the loss
  *            with NaN; the caller then re-runs with SORTED.
@@ -69,12 +69,13 @@ const char *b200surv_last_error(void);
 #define B200SURV_COX_BINNED 2
 #define B200SURV_COX_SORTED 3
 #define B200SURV_COX_SMALL_MAX 2048
-#define B200SURV_COX_MAX_BINS 16384
+#define B200SURV_COX_MAX_BINS 8192
 
 /* header flags */
 #define B200SURV_COXF_NOT_BINNABLE 1u /* a time was non-integer or outside [0, nbins)            */
-#define B200SURV_COXF_EXP_RANGE 2u    /* max(log_hz) - shift > 80: exp() may overflow; re-run with
-                                         shift = max_log_hz (reported in the header)            */
+#define B200SURV_COXF_EXP_RANGE 2u    /* shift unsuitable for the 32.32 fixed-point weights
+                                         (max(log_hz) - shift outside [-16, 20], or sum of weights
+                                         >= 2^30): re-run with shift near max_log_hz (header)    */
 #define B200SURV_COXF_BAD_TIME 4u     /* NaN or negative time                                     */
 
 /* One header per segment at the start of the state buffer (device memory, 64 bytes each). */
@@ -117,18 +118,19 @@ int32_t b200surv_cox_bwd(const float *grad_out, const void *state, size_t state_
 /* Row-block sharded BINNED forward for multi-GPU: each rank accumulates its rows'
  * per-bin aggregates, the caller all-reduces them (SUM over bins_sum, MAX over bins_max) with
  * NCCL, then every rank finalises identically and runs b200surv_cox_bwd on its own rows.
- *   bins_sum : double[n_seg][3*nbins + 4]  = S_all[nbins], S_event[nbins], m[nbins], sum of event
- *              log_hz, then three violation counters (!= 0 means the flag is raised on some rank):
- *              NOT_BINNABLE, (reserved), BAD_TIME  -- all SUM-reducible
+ *   bins_sum : int64[n_seg][3*nbins + 4]  = S_censored[nbins], S_event[nbins] (sums of
+ *              exp(log_hz - shift) in 32.32 fixed point), m[nbins] (event counts), sum of event
+ *              log_hz in 2^-24 fixed point, NOT_BINNABLE count, ceil(sum of weights), BAD_TIME count
+ *              -- integers, so the SUM all-reduce is exact and independent of the sharding
  *   bins_max : float[n_seg][2] = max log_hz, max time  -- MAX-reducible
  * n is the rank-local row count in both calls (it sizes the workspace). */
 size_t b200surv_cox_bins_sum_count(int32_t nbins);
 int32_t b200surv_cox_binned_partial(const float *log_hz, const float *time, const uint8_t *event,
                                     const int64_t *seg_offsets, int64_t n, int64_t n_seg,
-                                    int32_t nbins, float shift, double *bins_sum, float *bins_max,
+                                    int32_t nbins, float shift, int64_t *bins_sum, float *bins_max,
                                     void *workspace, size_t workspace_bytes,
                                     b200surv_stream_t stream);
-int32_t b200surv_cox_binned_finalize(const double *bins_sum, const float *bins_max, int64_t n,
+int32_t b200surv_cox_binned_finalize(const int64_t *bins_sum, const float *bins_max, int64_t n,
                                      int64_t n_seg, int32_t ties, int32_t reduction, int32_t nbins, float shift,
                                      float *out_loss, void *state, size_t state_bytes,
                                      void *workspace, size_t workspace_bytes,

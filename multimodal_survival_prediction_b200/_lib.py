@@ -14,7 +14,7 @@ TIES = {"breslow": 1, "efron": 2}
 REDUCE_MEAN_TERMS, REDUCE_SUM, REDUCE_MEAN_EVENTS = 0, 1, 2
 COX_SMALL, COX_BINNED, COX_SORTED = 1, 2, 3
 COX_SMALL_MAX = 2048
-COX_MAX_BINS = 16384
+COX_MAX_BINS = 8192
 COXF_NOT_BINNABLE, COXF_EXP_RANGE, COXF_BAD_TIME = 1, 2, 4
 COX_HEADER_BYTES = 64
 

@@ -141,7 +141,9 @@ def _plan_and_run(log_hz, time, event, seg_offsets, n_seg, max_seg, ties, reduct
                 continue
             break
         if flags & L.COXF_EXP_RANGE:
-            shift = max(h.max_log_hz for h in hdrs)
+            # largest weight 2^k with n * 2^k <= 2^29: full fixed-point precision without overflow
+            k = min(28, max(0, 29 - max(1, (n - 1).bit_length())))
+            shift = max(h.max_log_hz for h in hdrs) - k * 0.6931471805599453
             continue
     if n_seg != 1:
         raise L.B200SurvError("segmented cohorts larger than 2048 rows need integer day counts < 16384 "

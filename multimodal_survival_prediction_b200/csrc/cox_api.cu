@@ -6,8 +6,8 @@ namespace b200surv {
 size_t cox_binned_state_bytes(int64_t n_seg, int nb);
 size_t cox_binned_workspace_bytes(int64_t n, int64_t n_seg, int nb);
 int32_t cox_binned_partial(const float *, const float *, const uint8_t *, const int64_t *, int64_t, int64_t, int,
-                           float, double *, float *, void *, size_t, cudaStream_t);
-int32_t cox_binned_finalize(const double *, const float *, int64_t, int64_t, int, int, int, float, float *, void *,
+                           float, int64_t *, float *, void *, size_t, cudaStream_t);
+int32_t cox_binned_finalize(const int64_t *, const float *, int64_t, int64_t, int, int, int, float, float *, void *,
                             size_t, void *, size_t, cudaStream_t);
 int32_t cox_binned_fwd(const float *, const float *, const uint8_t *, const int64_t *, int64_t, int64_t, int, int,
                        int, float, float *, void *, size_t, void *, size_t, cudaStream_t);
@@ -98,7 +98,7 @@ int32_t b200surv_cox_bwd(const float *grad_out, const void *state, size_t state_
 
 int32_t b200surv_cox_binned_partial(const float *log_hz, const float *time, const uint8_t *event,
                                     const int64_t *seg_offsets, int64_t n, int64_t n_seg, int32_t nbins,
-                                    float shift, double *bins_sum, float *bins_max, void *workspace,
+                                    float shift, int64_t *bins_sum, float *bins_max, void *workspace,
                                     size_t workspace_bytes, b200surv_stream_t stream) {
     B200_REQUIRE(log_hz && time && event && bins_sum && bins_max && workspace, "null pointer");
     B200_REQUIRE(n >= 1 && n_seg >= 1, "n, n_seg");
@@ -107,7 +107,7 @@ int32_t b200surv_cox_binned_partial(const float *log_hz, const float *time, cons
                               workspace_bytes, as_stream(stream));
 }
 
-int32_t b200surv_cox_binned_finalize(const double *bins_sum, const float *bins_max, int64_t n, int64_t n_seg,
+int32_t b200surv_cox_binned_finalize(const int64_t *bins_sum, const float *bins_max, int64_t n, int64_t n_seg,
                                      int32_t ties, int32_t reduction, int32_t nbins, float shift, float *out_loss,
                                      void *state, size_t state_bytes, void *workspace, size_t workspace_bytes,
                                      b200surv_stream_t stream) {

@@ -7,7 +7,8 @@ this is the scale-out of the two operators it calls:
   of its own row block against all columns, then ONE int64 SUM all-reduce of the six counters
   (48 bytes) -- integer, so the result is bit-identical to the single-GPU result.
 * Cox loss (BINNED mode): every rank accumulates per-bin aggregates of its own rows
-  (b200surv_cox_binned_partial), ONE fp64 SUM all-reduce of 3*nbins+4 doubles plus a 2-float MAX
+  (b200surv_cox_binned_partial; 32.32 fixed-point integers), ONE int64 SUM all-reduce of
+  3*nbins+4 words (exact, so the loss is bit-identical for every sharding) plus a 2-float MAX
   all-reduce, then every rank finalises identically (b200surv_cox_binned_finalize) and computes the
   gradient of its own rows (b200surv_cox_bwd).  The gradient stays sharded like the input.
 
@@ -60,7 +61,7 @@ class ShardedCoxBinned:
         self.n, self.nb, self.dev = n_local, nbins, device
         self.ties, self.red = L.TIES[ties], reduction
         self.cnt = self.lib.b200surv_cox_bins_sum_count(nbins)
-        self.bins_sum = torch.empty(self.cnt, dtype=torch.float64, device=device)
+        self.bins_sum = torch.empty(self.cnt, dtype=torch.int64, device=device)
         self.bins_max = torch.empty(2, dtype=torch.float32, device=device)
         self.sb = self.lib.b200surv_cox_state_bytes(n_local, 1, L.COX_BINNED, nbins)
         self.wb = self.lib.b200surv_cox_workspace_bytes(n_local, 1, L.COX_BINNED, nbins)
