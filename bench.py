@@ -279,13 +279,14 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": "cox_binned_bwd (13 B/row: 9 read + 4 written)",
                          "achieved": achieved_bwd, "peak": peak, "unit": "GB/s", "frac": achieved_bwd / peak,
                          "traffic": None, "peak_source": peak_src, "ms": bwd_ms,
-                         "fwd": {"kernels": "cox_binned_pass1+reduce+scan+efron_items+finish (9 B/row)",
+                         "fwd": {"kernels": "cox_binned_pass1 + reduce(+scan) + items_finish (9 B/row)",
                                  "achieved": achieved_fwd, "frac": achieved_fwd / peak, "ms": fwd_ms},
                          "step": {"bytes_per_row": ALGO_BYTES_PER_ROW, "achieved": achieved_step,
                                   "frac": achieved_step / peak, "frac_of_8TBs": achieved_step / 8000.0}},
             "e2e": {"value": e2e_val, "unit": "patients/s", "h2d_bytes_per_step": 9 * n, "d2h_bytes_per_step": 4,
                     "ms_per_step": float(e2e_t.item()) * 1e3, "api": "neg_partial_log_likelihood(log_hz, event, time) + backward, mode=auto"},
-            "gpu_launches": 6 * args.steps,
+            # per step: pass1, reduce(+scan), items_finish, bwd (+ a stand-alone scan when bins are all-reduced)
+            "gpu_launches": (4 if world == 1 else 5) * args.steps,
             "clocks": clocks,
             "extra": {"cindex_1m": {"n": cn, "ms": ci_ms, "patients_per_s": cn / (ci_ms * 1e-3),
                                     "ordered_pairs_per_s": sum(counts) / (ci_ms * 1e-3), "counts": counts,

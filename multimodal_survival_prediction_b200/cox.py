@@ -135,8 +135,7 @@ def _plan_and_run(log_hz, time, event, seg_offsets, n_seg, max_seg, ties, reduct
         if flags & L.COXF_BAD_TIME:
             raise ValueError("Input 'time' should be non-negative and free of NaN")
         if flags & L.COXF_NOT_BINNABLE:
-            mt = max(h.max_time for h in hdrs)
-            if nbins is None and nb < L.COX_MAX_BINS and nb <= mt < L.COX_MAX_BINS:
+            if nbins is None and nb < L.COX_MAX_BINS:   # maybe integer days beyond 4095: one wider try
                 nb = L.COX_MAX_BINS
                 continue
             break
@@ -146,7 +145,7 @@ def _plan_and_run(log_hz, time, event, seg_offsets, n_seg, max_seg, ties, reduct
             shift = max(h.max_log_hz for h in hdrs) - k * 0.6931471805599453
             continue
     if n_seg != 1:
-        raise L.B200SurvError("segmented cohorts larger than 2048 rows need integer day counts < 16384 "
+        raise L.B200SurvError("segmented cohorts larger than 2048 rows need integer day counts < 8192 "
                               "(BINNED mode); the SORTED mode handles one cohort per call")
     loss, state = cox_fwd_raw(log_hz, time, event, None, 1, ties, reduction, L.COX_SORTED, 0)
     return loss, state, L.COX_SORTED, 0

@@ -95,18 +95,10 @@ __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
     else atomicMin(reinterpret_cast<unsigned *>(addr), __float_as_uint(v));
 }
 
-// streaming (read-once) 128-bit / 32-bit loads that do not pollute L1
-__device__ __forceinline__ float4 ldg_stream_f4(const float *p) {
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) {
-    uint32_t r;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
-    return r;
-}
+// streaming (read-once) 128-bit / 32-bit loads: ld.global.cs (evict-first).  Intrinsics rather than
+// asm volatile so that the compiler may hoist them above shared-memory atomics (memory-level parallelism).
+__device__ __forceinline__ float4 ldg_stream_f4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) { return __ldcs(reinterpret_cast<const unsigned int *>(p)); }
 __device__ __forceinline__ void stg_stream_f4(float *p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
                  "f"(v.z), "f"(v.w) : "memory");

@@ -72,6 +72,13 @@ class ShardedCoxBinned:
 
     def forward(self, log_hz, time, event, shift: float = 0.0, group=None):
         st = L.stream_ptr(self.dev)
+        _, world = _world()
+        if world == 1:  # nothing to exchange: the fused single-GPU forward (one launch fewer)
+            rc = self.lib.b200surv_cox_fwd(L.ptr(log_hz), L.ptr(time), L.ptr(event), None, self.n, 1, self.ties,
+                                           self.red, L.COX_BINNED, self.nb, ctypes.c_float(shift), L.ptr(self.loss),
+                                           L.ptr(self.state), self.sb, L.ptr(self.ws), self.wb, st)
+            L.check(rc, "b200surv_cox_fwd")
+            return self.loss
         rc = self.lib.b200surv_cox_binned_partial(L.ptr(log_hz), L.ptr(time), L.ptr(event), None, self.n, 1, self.nb,
                                                   ctypes.c_float(shift), L.ptr(self.bins_sum), L.ptr(self.bins_max),
                                                   L.ptr(self.ws), self.wb, st)
