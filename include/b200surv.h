@@ -153,6 +153,22 @@ int32_t b200surv_cindex_counts(const float *estimate, const float *time, const u
                                int64_t *out_counts, void *workspace, size_t workspace_bytes,
                                b200surv_stream_t stream);
 
+/* ---- fusion head: tensor-core GEMM primitive ----------------------------------------------- */
+/* C[M][N] (fp32 and/or bf16 copy) = A * B (+ bias[n]) (ReLU), bf16 operands, fp32 accumulation in
+ * TMEM (tcgen05.mma), operands staged by TMA.  Replaces the nn.Linear GEMMs of the heads
+ * (partial_modality_training.py:196-232) and their gradients:
+ *   a_mn == 0: A is row-major [M][K] (lda >= K)     a_mn == 1: A is row-major [K][M] (lda >= M)
+ *   b_mn == 0: B is row-major [N][K] (ldb >= K)     b_mn == 1: B is row-major [K][N] (ldb >= N)
+ * forward   y = x W^T + b : A = x [B][in], B = W [out][in]              (a_mn = 0, b_mn = 0)
+ * dgrad     dx = dy W     : A = dy [B][out], B = W [out][in] as [K][N]  (a_mn = 0, b_mn = 1)
+ * wgrad     dW = dy^T x   : A = dy [B][out] as [K][M], B = x [B][in] as [K][N]  (a_mn = 1, b_mn = 1)
+ * Operand pointers must be 16-byte aligned with row pitches that are multiples of 8 elements; ragged
+ * M, N, K are handled (TMA zero-fills out-of-bounds reads). */
+int32_t b200surv_gemm_bf16(const void *a, int64_t lda, int32_t a_mn, const void *b, int64_t ldb,
+                           int32_t b_mn, int32_t M, int32_t N, int32_t K, float *c, int64_t ldc,
+                           void *c_bf16, int64_t ldc_bf16, const float *bias, int32_t relu,
+                           b200surv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
