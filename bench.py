@@ -260,6 +260,32 @@ def run_b200(args):
     ci_ms = float(ci_ms.item())
     counts = counts.cpu().tolist()
 
+    # ---- gated fusion head fwd+bwd, B = 4096 rows, bf16 tcgen05 GEMMs (BASELINE.json configs[1]); per rank
+    from multimodal_survival_prediction_b200 import head as ghead
+    hb = 4096
+    net = ghead.PartialModalityNet().to(dev).train()
+    hct, hrna, hclin, hmask = [x.to(dev) for x in synth.modality_batch(hb, seed=SEED)]
+    hw = torch.randn(hb, device=dev) / hb ** 0.5
+
+    def head_step():
+        for prm in net.parameters():
+            prm.grad = None
+        hz, gt = net.forward_features(hct, hrna, hclin, hmask)
+        ((hz * hw).sum() + 0.01 * ghead.gate_entropy_loss(gt)).backward()
+
+    for _ in range(3):
+        head_step()
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hreps = 10
+    h0.record()
+    for _ in range(hreps):
+        head_step()
+    h1.record()
+    barrier()
+    head_ms = h0.elapsed_time(h1) / hreps
+    head_flop_per_row = 11_396_224          # fwd 5,507,136 + bwd 5,889,088
+
     if rank == 0:
         peak, peak_src = load_peaks()
         achieved_bwd = BWD_BYTES_PER_ROW * n / (bwd_ms * 1e-3) / 1e9
@@ -290,7 +316,12 @@ def run_b200(args):
             "clocks": clocks,
             "extra": {"cindex_1m": {"n": cn, "ms": ci_ms, "patients_per_s": cn / (ci_ms * 1e-3),
                                     "ordered_pairs_per_s": sum(counts) / (ci_ms * 1e-3), "counts": counts,
-                                    "n_gpus": world, "scaling": "strong (rows sharded, int64 all-reduce)"}},
+                                    "n_gpus": world, "scaling": "strong (rows sharded, int64 all-reduce)"},
+                      "head_b4096": {"rows": hb, "ms_fwd_bwd": head_ms, "rows_per_s": hb / (head_ms * 1e-3),
+                                     "tflops": hb * head_flop_per_row / (head_ms * 1e-3) / 1e12,
+                                     "dtype": "bf16 operands, fp32 accumulate (tcgen05)", "dropout_p": 0.3,
+                                     "note": "gated head fwd+bwd through the nn.Module (includes host launch "
+                                             "overhead of ~60 kernels); per rank"}},
         }
         if cpu_val is not None:
             out["cpu_baseline"] = {"value": cpu_val, "unit": "patients/s", "cores": cores, "kind": "port",

@@ -169,6 +169,54 @@ int32_t b200surv_gemm_bf16(const void *a, int64_t lda, int32_t a_mn, const void 
                            void *c_bf16, int64_t ldc_bf16, const float *bias, int32_t relu,
                            b200surv_stream_t stream);
 
+/* ---- fusion head: forward / backward -------------------------------------------------------- */
+/* Parameters of the head, fp32 row-major [out][in], one pointer per reference state_dict entry
+ * (PartialModalityNet: partial_modality_training.py:193-232; MultiModalSurvivalNet:
+ * final_multimodal.py:95-120 has the same entries minus gate.*, which are then NULL):
+ *   rna0 = rna_encoder.0 (512 x rna_dim), bn1 = rna_encoder.1 (512; running stats updated in training),
+ *   rna4 = rna_encoder.4 (128 x 512), clin = clinical_encoder.0 (32 x 1), gate0 = gate.0 (64 x 291),
+ *   gate2 = gate.2 (3 x 64), fus0 = fusion.0 (256 x 288), bn2 = fusion.1 (256), fus4 = fusion.4
+ *   (128 x 256), cox = cox_head (1 x 128). */
+typedef struct {
+    const float *rna0_w, *rna0_b, *bn1_w, *bn1_b;
+    float *bn1_rm, *bn1_rv;
+    const float *rna4_w, *rna4_b, *clin_w, *clin_b, *gate0_w, *gate0_b, *gate2_w, *gate2_b, *fus0_w, *fus0_b,
+        *bn2_w, *bn2_b;
+    float *bn2_rm, *bn2_rv;
+    const float *fus4_w, *fus4_b, *cox_w, *cox_b;
+} b200surv_head_params;
+/* Gradient outputs, same shapes as the parameters (written, not accumulated). */
+typedef struct {
+    float *rna0_w, *rna0_b, *bn1_w, *bn1_b, *rna4_w, *rna4_b, *clin_w, *clin_b, *gate0_w, *gate0_b, *gate2_w,
+        *gate2_b, *fus0_w, *fus0_b, *bn2_w, *bn2_b, *fus4_w, *fus4_b, *cox_w, *cox_b;
+} b200surv_head_grads;
+
+size_t b200surv_head_saved_bytes(int64_t B, int32_t rna_dim);     /* activations kept fwd -> bwd */
+size_t b200surv_head_workspace_bytes(int64_t B, int32_t rna_dim); /* scratch of one call         */
+
+/* Forward.  ct_feat [B][128] (output of the CT encoder, contract a4), rna [B][rna_dim], clinical [B][1],
+ * mask [B][3] = [image, rnaseq, clinical] or NULL for the ungated head (then gate must be NULL).
+ * training != 0: BatchNorm uses batch statistics (B >= 2) and updates the running statistics, dropout
+ * with probability dropout_p from a counter-based generator keyed by (seed, layer, element) -- backward
+ * re-derives the same mask; keep1 [B][512] / keep2 [B][256] (nullable) export the keep masks.
+ * Outputs: hazard [B], gate [B][3]. */
+int32_t b200surv_head_fwd(const b200surv_head_params *params, const float *ct_feat, const float *rna,
+                          const float *clinical, const float *mask, int64_t B, int32_t rna_dim,
+                          int32_t training, float dropout_p, uint64_t seed, float *hazard, float *gate,
+                          uint8_t *keep1, uint8_t *keep2, void *saved, size_t saved_bytes,
+                          void *workspace, size_t workspace_bytes, b200surv_stream_t stream);
+
+/* Backward of the same call (same B, rna_dim, training, dropout_p, seed, mask, clinical, saved).
+ * d_hazard [B]; d_gate [B][3] or NULL (gradient flowing into the gate weights from outside, e.g. the
+ * gate-entropy regulariser, partial_modality_training.py:322-331); outputs: grads, d_ct_feat [B][128]
+ * (nullable). */
+int32_t b200surv_head_bwd(const b200surv_head_params *params, const b200surv_head_grads *grads,
+                          const float *d_hazard, const float *d_gate, const float *clinical,
+                          const float *mask, int64_t B, int32_t rna_dim, int32_t training,
+                          float dropout_p, uint64_t seed, float *d_ct_feat, const void *saved,
+                          size_t saved_bytes, void *workspace, size_t workspace_bytes,
+                          b200surv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,577 @@
+// Gated late-fusion survival head, forward and backward, for B200.
+//
+// Replaces what PartialModalityNet.forward (scripts/training/partial_modality_training.py:234-277,
+// layers :193-232) and MultiModalSurvivalNet.forward (scripts/training/final_multimodal.py:122-150)
+// compute from the 128-d CT feature onward, plus the autograd backward of those layers:
+//   rna 5005->512 (BatchNorm, ReLU, Dropout .3) ->128 (ReLU); clinical 1->32 (ReLU); per-modality mask
+//   multiply; gate 291->64 (ReLU)->3 softmax over [ct, rna, clin, mask]; gate-weighted concat (288);
+//   fusion 288->256 (BatchNorm, ReLU, Dropout .3) ->128 (ReLU); cox head 128->1.
+// Every Linear layer and every weight/input gradient runs on the tensor cores through gemm_tc.cu
+// (tcgen05 + TMEM + TMA, bf16 operands, fp32 accumulation); the kernels in this file are the fused
+// element-wise / reduction glue between the GEMMs (BatchNorm statistics and application, dropout with a
+// counter-based RNG that backward re-derives, mask/gate/softmax, the 128->1 Cox head).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace b200surv {
+
+int32_t gemm_bf16(const void *a, int64_t lda, int a_mn, const void *b, int64_t ldb, int b_mn, int M, int N, int K,
+                  float *c, int64_t ldc, void *c_bf16, int64_t ldc_bf16, const float *bias, int relu, cudaStream_t st);
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+constexpr int H1 = 512, R1 = 128, CL = 32, CT = 128, FEAT = CT + R1 + CL;  // 288
+constexpr int GZ = FEAT + 3, GZP = 296;                                      // gate input 291, padded to 296
+constexpr int GH = 64, H2 = 256, F2N = 128;
+constexpr float BN_EPS = 1e-5f, BN_MOM = 0.1f;
+constexpr int RS_MAX = 32;  // row slices of the column reductions
+
+__device__ __forceinline__ uint32_t rng32(uint64_t seed, uint32_t layer, uint64_t idx) {  // splitmix64
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + (uint64_t)layer * 0xD1B54A32D192ED03ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
+__device__ __forceinline__ bool keep_elem(uint64_t seed, uint32_t layer, uint64_t idx, uint32_t thresh) {
+    return rng32(seed, layer, idx) >= thresh;  // P(drop) = thresh / 2^32
+}
+
+// ---------------------------------------------------------------- casts
+__global__ void k_cast_pad(const float *__restrict__ src, int64_t lds, bf16 *__restrict__ dst, int64_t ldd, int64_t R,
+                           int C, int Cp) {
+    const int64_t total = R * Cp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / Cp;
+        const int c = (int)(i - r * Cp);
+        dst[r * ldd + c] = __float2bfloat16_rn(c < C ? src[r * lds + c] : 0.f);
+    }
+}
+
+// ---------------------------------------------------------------- column reductions (deterministic)
+// partial[slice][2][N] (double).  MODE 0: (sum a, sum a^2)   MODE 1: (sum a, sum a * xhat), xhat from x, mu, rstd
+// MODE 2: (sum a * s[row], sum s[row])   MODE 3: (sum a, 0)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_colreduce(const float *__restrict__ a, int64_t lda, const float *__restrict__ x, int64_t ldx,
+            const float *__restrict__ mu, const float *__restrict__ rstd, const float *__restrict__ s, int64_t s_stride,
+            int64_t B, int N, double *__restrict__ partial) {
+    __shared__ double sh0[8][32], sh1[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    const int slice = blockIdx.y, nslices = gridDim.y;
+    const int64_t rows_per = (B + nslices - 1) / nslices;
+    const int64_t r0 = slice * rows_per, r1 = min(B, r0 + rows_per);
+    double v0 = 0.0, v1 = 0.0;
+    if (n < N) {
+        const float m = (MODE == 1) ? mu[n] : 0.f, rs = (MODE == 1) ? rstd[n] : 0.f;
+        for (int64_t r = r0 + ty; r < r1; r += 8) {
+            const float av = a[r * lda + n];
+            if (MODE == 0) { v0 += av; v1 += (double)av * av; }
+            if (MODE == 1) { v0 += av; v1 += (double)av * ((x[r * ldx + n] - m) * rs); }
+            if (MODE == 2) { const float sv = s[r * s_stride]; v0 += (double)av * sv; v1 += sv; }
+            if (MODE == 3) { v0 += av; }
+        }
+    }
+    sh0[ty][tx] = v0; sh1[ty][tx] = v1;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { v0 += sh0[k][tx]; v1 += sh1[k][tx]; }
+        partial[((size_t)slice * 2 + 0) * N + n] = v0;
+        partial[((size_t)slice * 2 + 1) * N + n] = v1;
+    }
+}
+// sums the slices: out0[n], out1[n] (float, nullable), scaled
+__global__ void k_colreduce_final(const double *__restrict__ partial, int nslices, int N, float scale, float *out0,
+                                  float *out1) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double v0 = 0.0, v1 = 0.0;
+    for (int k = 0; k < nslices; ++k) { v0 += partial[((size_t)k * 2 + 0) * N + n]; v1 += partial[((size_t)k * 2 + 1) * N + n]; }
+    if (out0) out0[n] = (float)(v0 * scale);
+    if (out1) out1[n] = (float)(v1 * scale);
+}
+
+// ---------------------------------------------------------------- BatchNorm1d
+// train: mu, rstd from the batch; running <- 0.9 running + 0.1 (mu, unbiased var).  eval: from running stats.
+__global__ void k_bn_finalize(const double *__restrict__ partial, int nslices, int64_t B, int N, int training,
+                              float *__restrict__ run_mean, float *__restrict__ run_var, float *__restrict__ mu,
+                              float *__restrict__ rstd) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    if (training) {
+        double s = 0.0, ss = 0.0;
+        for (int k = 0; k < nslices; ++k) { s += partial[((size_t)k * 2 + 0) * N + n]; ss += partial[((size_t)k * 2 + 1) * N + n]; }
+        const double m = s / (double)B;
+        double var = ss / (double)B - m * m;
+        if (var < 0.0) var = 0.0;
+        mu[n] = (float)m;
+        rstd[n] = (float)(1.0 / sqrt(var + (double)BN_EPS));
+        if (run_mean) {
+            const double unb = var * ((double)B / (double)(B - 1));
+            run_mean[n] = (1.f - BN_MOM) * run_mean[n] + BN_MOM * (float)m;
+            run_var[n] = (1.f - BN_MOM) * run_var[n] + BN_MOM * (float)unb;
+        }
+    } else {
+        mu[n] = run_mean[n];
+        rstd[n] = rsqrtf(run_var[n] + BN_EPS);
+    }
+}
+// y = dropout(relu(bn(x))) as bf16 (the next GEMM's A operand); optional keep-mask export for tests
+__global__ void k_bn_apply(const float *__restrict__ x, int64_t ldx, const float *__restrict__ mu,
+                           const float *__restrict__ rstd, const float *__restrict__ gamma,
+                           const float *__restrict__ beta, int64_t B, int N, uint32_t thresh, float inv_keep,
+                           uint64_t seed, uint32_t layer, bf16 *__restrict__ y, int64_t ldy,
+                           uint8_t *__restrict__ keep_out) {
+    const int64_t total = B * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / N;
+        const int n = (int)(i - r * N);
+        float v = (x[r * ldx + n] - mu[n]) * rstd[n] * gamma[n] + beta[n];
+        v = fmaxf(v, 0.f);
+        bool keep = true;
+        if (thresh) { keep = keep_elem(seed, layer, (uint64_t)i, thresh); v = keep ? v * inv_keep : 0.f; }
+        if (keep_out) keep_out[i] = keep ? 1 : 0;
+        y[r * ldy + n] = __float2bfloat16_rn(v);
+    }
+}
+// dy = dA * keep/(1-p) * [bn(x) > 0]
+__global__ void k_bn_bwd_dy(const float *__restrict__ dA, int64_t ldd, const float *__restrict__ x, int64_t ldx,
+                            const float *__restrict__ mu, const float *__restrict__ rstd,
+                            const float *__restrict__ gamma, const float *__restrict__ beta, int64_t B, int N,
+                            uint32_t thresh, float inv_keep, uint64_t seed, uint32_t layer, float *__restrict__ dy) {
+    const int64_t total = B * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / N;
+        const int n = (int)(i - r * N);
+        const float v = (x[r * ldx + n] - mu[n]) * rstd[n] * gamma[n] + beta[n];
+        float g = dA[r * ldd + n];
+        if (thresh) g = keep_elem(seed, layer, (uint64_t)i, thresh) ? g * inv_keep : 0.f;
+        dy[i] = v > 0.f ? g : 0.f;
+    }
+}
+// dx (bf16) from dy, column sums sdy = sum dy, sdyx = sum dy*xhat:
+// train: dx = gamma*rstd*(dy - sdy/B - xhat*sdyx/B);  eval: dx = gamma*rstd*dy
+__global__ void k_bn_bwd_dx(const float *__restrict__ dy, const float *__restrict__ x, int64_t ldx,
+                            const float *__restrict__ mu, const float *__restrict__ rstd,
+                            const float *__restrict__ gamma, const float *__restrict__ sdy,
+                            const float *__restrict__ sdyx, int64_t B, int N, int training, bf16 *__restrict__ dx,
+                            int64_t lddx) {
+    const int64_t total = B * N;
+    const float invB = 1.f / (float)B;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / N;
+        const int n = (int)(i - r * N);
+        float v = dy[i];
+        if (training) {
+            const float xh = (x[r * ldx + n] - mu[n]) * rstd[n];
+            v = v - sdy[n] * invB - xh * sdyx[n] * invB;
+        }
+        dx[r * lddx + n] = __float2bfloat16_rn(v * gamma[n] * rstd[n]);
+    }
+}
+// bias gradient of the Linear feeding a BatchNorm: sum_rows dx = (train ? 0 : gamma*rstd*sdy)
+__global__ void k_bn_bias_grad(const float *__restrict__ sdy, const float *__restrict__ gamma,
+                               const float *__restrict__ rstd, int N, int training, float *__restrict__ db) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) db[n] = training ? 0.f : gamma[n] * rstd[n] * sdy[n];
+}
+
+// ---------------------------------------------------------------- mask / clinical encoder / gate
+// feat[b] = [ct*m0 (128) | R*m1 (128) | relu(clin*Wc+bc)*m2 (32)] (fp32); gated: z = bf16([feat | mask | 0 pad]);
+// ungated (mask == nullptr): no masking, fused = bf16(feat)
+__global__ void k_gate_prep(const float *__restrict__ ct, const float *__restrict__ R, const float *__restrict__ clin,
+                            const float *__restrict__ mask, const float *__restrict__ wc, const float *__restrict__ bc,
+                            int64_t B, float *__restrict__ feat, bf16 *__restrict__ z, bf16 *__restrict__ fused) {
+    const int64_t total = B * GZP;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / GZP;
+        const int j = (int)(i - b * GZP);
+        float v = 0.f;
+        if (j < FEAT) {
+            if (j < CT) v = ct[b * CT + j] * (mask ? mask[b * 3 + 0] : 1.f);
+            else if (j < CT + R1) v = R[b * R1 + (j - CT)] * (mask ? mask[b * 3 + 1] : 1.f);
+            else {
+                const int k = j - CT - R1;
+                v = fmaxf(clin[b] * wc[k] + bc[k], 0.f) * (mask ? mask[b * 3 + 2] : 1.f);
+            }
+            feat[b * FEAT + j] = v;
+            if (fused) fused[b * FEAT + j] = __float2bfloat16_rn(v);
+        } else if (j < GZ) {
+            v = mask ? mask[b * 3 + (j - FEAT)] : 0.f;
+        }
+        if (z) z[b * GZP + j] = __float2bfloat16_rn(v);
+    }
+}
+// one warp per row: logits = zh Wg2^T + bg2, gate = softmax, fused = bf16(feat * gate[group])
+__global__ void __launch_bounds__(256)
+k_gate_apply(const float *__restrict__ zh, const float *__restrict__ wg2, const float *__restrict__ bg2,
+             const float *__restrict__ feat, int64_t B, float *__restrict__ gate, bf16 *__restrict__ fused) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < B; b += (int64_t)gridDim.x * 8) {
+        const float z0 = zh[b * GH + lane], z1 = zh[b * GH + 32 + lane];
+        float l0 = z0 * wg2[lane] + z1 * wg2[32 + lane];
+        float l1 = z0 * wg2[GH + lane] + z1 * wg2[GH + 32 + lane];
+        float l2 = z0 * wg2[2 * GH + lane] + z1 * wg2[2 * GH + 32 + lane];
+        l0 = warp_sum(l0) + bg2[0]; l1 = warp_sum(l1) + bg2[1]; l2 = warp_sum(l2) + bg2[2];
+        const float mx = fmaxf(l0, fmaxf(l1, l2));
+        const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx);
+        const float inv = 1.f / (e0 + e1 + e2);
+        const float g0 = e0 * inv, g1 = e1 * inv, g2 = e2 * inv;
+        if (lane == 0) { gate[b * 3 + 0] = g0; gate[b * 3 + 1] = g1; gate[b * 3 + 2] = g2; }
+        for (int j = lane; j < FEAT; j += 32) {
+            const float g = j < CT ? g0 : (j < CT + R1 ? g1 : g2);
+            fused[b * FEAT + j] = __float2bfloat16_rn(feat[b * FEAT + j] * g);
+        }
+    }
+}
+// one warp per row.  in: dfused [B][288], feat, gate, zh, d_gate_ext (nullable).
+// out: dfeat = dfused * gate (fp32 [B][288]); dlogit [B][3]; dzh = bf16((dlogit Wg2) * [zh > 0]) [B][64]
+__global__ void __launch_bounds__(256)
+k_gate_apply_bwd(const float *__restrict__ dfused, const float *__restrict__ feat, const float *__restrict__ gate,
+                 const float *__restrict__ zh, const float *__restrict__ wg2, const float *__restrict__ d_gate_ext,
+                 int64_t B, float *__restrict__ dfeat, float *__restrict__ dlogit, bf16 *__restrict__ dzh) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < B; b += (int64_t)gridDim.x * 8) {
+        const float g0 = gate[b * 3], g1 = gate[b * 3 + 1], g2 = gate[b * 3 + 2];
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        for (int j = lane; j < FEAT; j += 32) {
+            const float df = dfused[b * FEAT + j], f = feat[b * FEAT + j];
+            if (j < CT) { d0 += df * f; dfeat[b * FEAT + j] = df * g0; }
+            else if (j < CT + R1) { d1 += df * f; dfeat[b * FEAT + j] = df * g1; }
+            else { d2 += df * f; dfeat[b * FEAT + j] = df * g2; }
+        }
+        d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
+        if (d_gate_ext) { d0 += d_gate_ext[b * 3]; d1 += d_gate_ext[b * 3 + 1]; d2 += d_gate_ext[b * 3 + 2]; }
+        const float dot = g0 * d0 + g1 * d1 + g2 * d2;
+        const float dl0 = g0 * (d0 - dot), dl1 = g1 * (d1 - dot), dl2 = g2 * (d2 - dot);
+        if (lane == 0) { dlogit[b * 3] = dl0; dlogit[b * 3 + 1] = dl1; dlogit[b * 3 + 2] = dl2; }
+        for (int k = lane; k < GH; k += 32) {
+            const float v = dl0 * wg2[k] + dl1 * wg2[GH + k] + dl2 * wg2[2 * GH + k];
+            dzh[b * GH + k] = __float2bfloat16_rn(zh[b * GH + k] > 0.f ? v : 0.f);
+        }
+    }
+}
+// dtot = dfeat (+ dz[:, :288]); d_ct = dtot[0:128]*m0; dR = bf16(dtot[128:256]*m1*[R>0]); dC = dtot[256:288]*m2*[C>0]
+__global__ void k_gate_prep_bwd(const float *__restrict__ dfeat, const float *__restrict__ dz, int64_t lddz,
+                                const float *__restrict__ mask, const float *__restrict__ R,
+                                const float *__restrict__ clin, const float *__restrict__ wc,
+                                const float *__restrict__ bc, int64_t B, float *__restrict__ d_ct,
+                                bf16 *__restrict__ dR, float *__restrict__ dC) {
+    const int64_t total = B * FEAT;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / FEAT;
+        const int j = (int)(i - b * FEAT);
+        float v = dfeat[i] + (dz ? dz[b * lddz + j] : 0.f);
+        if (j < CT) {
+            if (d_ct) d_ct[b * CT + j] = v * (mask ? mask[b * 3] : 1.f);
+        } else if (j < CT + R1) {
+            const int k = j - CT;
+            v *= (mask ? mask[b * 3 + 1] : 1.f);
+            dR[b * R1 + k] = __float2bfloat16_rn(R[b * R1 + k] > 0.f ? v : 0.f);
+        } else {
+            const int k = j - CT - R1;
+            v *= (mask ? mask[b * 3 + 2] : 1.f);
+            dC[b * CL + k] = (clin[b] * wc[k] + bc[k] > 0.f) ? v : 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- Cox head 128 -> 1
+__global__ void __launch_bounds__(256)
+k_cox_head(const float *__restrict__ f2, const float *__restrict__ w, const float *__restrict__ bias, int64_t B,
+           float *__restrict__ hazard) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < B; b += (int64_t)gridDim.x * 8) {
+        float s = 0.f;
+        for (int j = lane; j < F2N; j += 32) s += f2[b * F2N + j] * w[j];
+        s = warp_sum(s);
+        if (lane == 0) hazard[b] = s + bias[0];
+    }
+}
+// dF2r = bf16(dhz[b] * w[j] * [f2 > 0])
+__global__ void k_cox_head_bwd(const float *__restrict__ dhz, const float *__restrict__ f2, const float *__restrict__ w,
+                               int64_t B, bf16 *__restrict__ df2) {
+    const int64_t total = B * F2N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / F2N;
+        const int j = (int)(i - b * F2N);
+        df2[i] = __float2bfloat16_rn(f2[i] > 0.f ? dhz[b] * w[j] : 0.f);
+    }
+}
+__global__ void k_bf16_to_f32(const bf16 *__restrict__ src, float *__restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __bfloat162float(src[i]);
+}
+
+// ---------------------------------------------------------------- host orchestration
+inline int gs(int64_t total) {  // grid for grid-stride element-wise kernels
+    int64_t g = (total + 255) / 256;
+    const int64_t cap = 8 * (int64_t)num_sms();
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+inline int nslices_for(int64_t B) { int64_t s = (B + 255) / 256; return (int)(s < 1 ? 1 : (s > RS_MAX ? RS_MAX : s)); }
+
+struct Carver {
+    unsigned char *base;
+    size_t off;
+    template <typename T>
+    T *take(size_t count) {
+        T *p = reinterpret_cast<T *>(base + off);
+        off = align_up(off + count * sizeof(T), 256);
+        return p;
+    }
+};
+
+// activations kept from forward to backward (the `saved` buffer)
+struct Saved {
+    bf16 *xb, *w1b, *w2b, *wg1b, *wf1b, *wf2b;  // bf16 operand copies: x [B][Kp], weights
+    float *h1, *mu1, *rstd1;                     // pre-BN activations and statistics
+    bf16 *a1;                                    // [B][512]
+    float *r;                                    // [B][128] relu(rna_encoder.4)
+    float *feat;                                 // [B][288]
+    bf16 *z;                                     // [B][296]
+    float *zh, *gate;                            // [B][64], [B][3]
+    bf16 *fused;                                 // [B][288]
+    float *h2, *mu2, *rstd2;
+    bf16 *a2;                                    // [B][256]
+    float *f2;                                   // [B][128]
+};
+inline int kpad(int rna_dim) { return (rna_dim + 7) / 8 * 8; }
+Saved carve_saved(void *buf, int64_t B, int rna_dim, size_t *bytes) {
+    Carver c{static_cast<unsigned char *>(buf), 0};
+    const int Kp = kpad(rna_dim);
+    Saved s;
+    s.xb = c.take<bf16>((size_t)B * Kp); s.w1b = c.take<bf16>((size_t)H1 * Kp); s.w2b = c.take<bf16>((size_t)R1 * H1);
+    s.wg1b = c.take<bf16>((size_t)GH * GZP); s.wf1b = c.take<bf16>((size_t)H2 * FEAT); s.wf2b = c.take<bf16>((size_t)F2N * H2);
+    s.h1 = c.take<float>((size_t)B * H1); s.mu1 = c.take<float>(H1); s.rstd1 = c.take<float>(H1);
+    s.a1 = c.take<bf16>((size_t)B * H1); s.r = c.take<float>((size_t)B * R1); s.feat = c.take<float>((size_t)B * FEAT);
+    s.z = c.take<bf16>((size_t)B * GZP); s.zh = c.take<float>((size_t)B * GH); s.gate = c.take<float>((size_t)B * 3);
+    s.fused = c.take<bf16>((size_t)B * FEAT); s.h2 = c.take<float>((size_t)B * H2); s.mu2 = c.take<float>(H2);
+    s.rstd2 = c.take<float>(H2); s.a2 = c.take<bf16>((size_t)B * H2); s.f2 = c.take<float>((size_t)B * F2N);
+    *bytes = c.off;
+    return s;
+}
+
+// scratch used inside one call (the `workspace` buffer)
+struct Scratch {
+    double *partial;          // [RS_MAX][2][max N]
+    float *t0, *t1, *t2;      // [B][512] fp32 temporaries
+    bf16 *b0, *b1;            // [B][512] bf16 temporaries
+    float *v0, *v1;           // [max N] vectors
+    float *dlogit, *dC;       // [B][3], [B][32]
+};
+Scratch carve_scratch(void *buf, int64_t B, size_t *bytes) {
+    Carver c{static_cast<unsigned char *>(buf), 0};
+    Scratch s;
+    s.partial = c.take<double>((size_t)RS_MAX * 2 * 8192);
+    s.t0 = c.take<float>((size_t)B * H1); s.t1 = c.take<float>((size_t)B * H1); s.t2 = c.take<float>((size_t)B * H1);
+    s.b0 = c.take<bf16>((size_t)B * H1); s.b1 = c.take<bf16>((size_t)B * H1);
+    s.v0 = c.take<float>(8192); s.v1 = c.take<float>(8192);
+    s.dlogit = c.take<float>((size_t)B * 4); s.dC = c.take<float>((size_t)B * CL);
+    *bytes = c.off;
+    return s;
+}
+
+template <int MODE>
+void colreduce(const float *a, int64_t lda, const float *x, int64_t ldx, const float *mu, const float *rstd,
+               const float *s, int64_t s_stride, int64_t B, int N, double *partial, int nsl, cudaStream_t st) {
+    k_colreduce<MODE><<<dim3((N + 31) / 32, nsl), 256, 0, st>>>(a, lda, x, ldx, mu, rstd, s, s_stride, B, N, partial);
+}
+// out0[n] = sum_b a[b][n] * s[b*s_stride]
+void rowscale_sum(const float *a, int64_t lda, const float *s, int64_t s_stride, int64_t B, int N, double *partial,
+                  float *out0, float *out1, cudaStream_t st) {
+    const int nsl = nslices_for(B);
+    colreduce<2>(a, lda, nullptr, 0, nullptr, nullptr, s, s_stride, B, N, partial, nsl, st);
+    k_colreduce_final<<<(N + 255) / 256, 256, 0, st>>>(partial, nsl, N, 1.f, out0, out1);
+}
+void col_sum(const float *a, int64_t lda, int64_t B, int N, double *partial, float *out0, cudaStream_t st) {
+    const int nsl = nslices_for(B);
+    colreduce<3>(a, lda, nullptr, 0, nullptr, nullptr, nullptr, 0, B, N, partial, nsl, st);
+    k_colreduce_final<<<(N + 255) / 256, 256, 0, st>>>(partial, nsl, N, 1.f, out0, nullptr);
+}
+void col_sum_bf16(const bf16 *a, int64_t B, int N, float *tmp, double *partial, float *out0, cudaStream_t st) {
+    k_bf16_to_f32<<<gs(B * N), 256, 0, st>>>(a, tmp, B * N);
+    col_sum(tmp, N, B, N, partial, out0, st);
+}
+
+uint32_t drop_thresh(float p) {
+    if (p <= 0.f) return 0;
+    double t = (double)p * 4294967296.0;
+    if (t > 4294967295.0) t = 4294967295.0;
+    return (uint32_t)t;
+}
+
+}  // namespace
+
+}  // namespace b200surv
+
+using namespace b200surv;
+
+extern "C" {
+
+size_t b200surv_head_saved_bytes(int64_t B, int32_t rna_dim) {
+    size_t bytes = 0;
+    carve_saved(nullptr, B, rna_dim, &bytes);
+    return bytes;
+}
+size_t b200surv_head_workspace_bytes(int64_t B, int32_t rna_dim) {
+    (void)rna_dim;
+    size_t bytes = 0;
+    carve_scratch(nullptr, B, &bytes);
+    return bytes;
+}
+
+int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, const float *rna, const float *clinical,
+                          const float *mask, int64_t B, int32_t rna_dim, int32_t training, float dropout_p,
+                          uint64_t seed, float *hazard, float *gate, uint8_t *keep1, uint8_t *keep2, void *saved,
+                          size_t saved_bytes, void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
+    B200_REQUIRE(p && ct_feat && rna && clinical && hazard && saved && workspace, "null pointer");
+    B200_REQUIRE(B >= 1 && B < (int64_t)1 << 24, "batch size must be in [1, 2^24)");
+    B200_REQUIRE(rna_dim >= 1 && rna_dim <= 65536, "rna_dim");
+    B200_REQUIRE(!(training && B < 2), "Expected more than 1 value per channel when training (BatchNorm1d)");
+    B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p");
+    const bool gated = mask != nullptr;
+    B200_REQUIRE(!gated || (p->gate0_w && p->gate0_b && p->gate2_w && p->gate2_b && gate), "gated head needs gate params");
+    size_t need = 0;
+    const Saved s = carve_saved(saved, B, rna_dim, &need);
+    if (saved_bytes < need) { set_error("head fwd: saved buffer %zu < %zu", saved_bytes, need); return B200SURV_WORKSPACE_TOO_SMALL; }
+    const Scratch w = carve_scratch(workspace, B, &need);
+    if (workspace_bytes < need) { set_error("head fwd: workspace %zu < %zu", workspace_bytes, need); return B200SURV_WORKSPACE_TOO_SMALL; }
+    cudaStream_t st = as_stream(stream);
+    const int Kp = kpad(rna_dim);
+    const uint32_t thresh = training ? drop_thresh(dropout_p) : 0;
+    const float inv_keep = 1.f / (1.f - dropout_p);
+    const int nsl = nslices_for(B);
+    int32_t rc;
+
+    // bf16 operand copies (K padded to a multiple of 8 for the TMA row pitch)
+    k_cast_pad<<<gs(B * Kp), 256, 0, st>>>(rna, rna_dim, s.xb, Kp, B, rna_dim, Kp);
+    k_cast_pad<<<gs((int64_t)H1 * Kp), 256, 0, st>>>(p->rna0_w, rna_dim, s.w1b, Kp, H1, rna_dim, Kp);
+    k_cast_pad<<<gs(R1 * H1), 256, 0, st>>>(p->rna4_w, H1, s.w2b, H1, R1, H1, H1);
+    if (gated) k_cast_pad<<<gs(GH * GZP), 256, 0, st>>>(p->gate0_w, GZ, s.wg1b, GZP, GH, GZ, GZP);
+    k_cast_pad<<<gs(H2 * FEAT), 256, 0, st>>>(p->fus0_w, FEAT, s.wf1b, FEAT, H2, FEAT, FEAT);
+    k_cast_pad<<<gs(F2N * H2), 256, 0, st>>>(p->fus4_w, H2, s.wf2b, H2, F2N, H2, H2);
+
+    // rna encoder: Linear(rna_dim, 512) -> BN -> ReLU -> Dropout -> Linear(512, 128) -> ReLU
+    rc = gemm_bf16(s.xb, Kp, 0, s.w1b, Kp, 0, (int)B, H1, rna_dim, s.h1, H1, nullptr, 0, p->rna0_b, 0, st);
+    if (rc) return rc;
+    if (training) colreduce<0>(s.h1, H1, nullptr, 0, nullptr, nullptr, nullptr, 0, B, H1, w.partial, nsl, st);
+    k_bn_finalize<<<(H1 + 255) / 256, 256, 0, st>>>(w.partial, nsl, B, H1, training, p->bn1_rm, p->bn1_rv, s.mu1, s.rstd1);
+    k_bn_apply<<<gs(B * H1), 256, 0, st>>>(s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh, inv_keep, seed, 1,
+                                           s.a1, H1, keep1);
+    rc = gemm_bf16(s.a1, H1, 0, s.w2b, H1, 0, (int)B, R1, H1, s.r, R1, nullptr, 0, p->rna4_b, 1, st);
+    if (rc) return rc;
+
+    // clinical encoder, masks, gate
+    k_gate_prep<<<gs(B * GZP), 256, 0, st>>>(ct_feat, s.r, clinical, mask, p->clin_w, p->clin_b, B, s.feat,
+                                             gated ? s.z : nullptr, gated ? nullptr : s.fused);
+    if (gated) {
+        rc = gemm_bf16(s.z, GZP, 0, s.wg1b, GZP, 0, (int)B, GH, GZ, s.zh, GH, nullptr, 0, p->gate0_b, 1, st);
+        if (rc) return rc;
+        k_gate_apply<<<gs(B * 32), 256, 0, st>>>(s.zh, p->gate2_w, p->gate2_b, s.feat, B, s.gate, s.fused);
+        B200_CHECK_CUDA(cudaMemcpyAsync(gate, s.gate, (size_t)B * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    // fusion: Linear(288, 256) -> BN -> ReLU -> Dropout -> Linear(256, 128) -> ReLU ; cox head
+    rc = gemm_bf16(s.fused, FEAT, 0, s.wf1b, FEAT, 0, (int)B, H2, FEAT, s.h2, H2, nullptr, 0, p->fus0_b, 0, st);
+    if (rc) return rc;
+    if (training) colreduce<0>(s.h2, H2, nullptr, 0, nullptr, nullptr, nullptr, 0, B, H2, w.partial, nsl, st);
+    k_bn_finalize<<<(H2 + 255) / 256, 256, 0, st>>>(w.partial, nsl, B, H2, training, p->bn2_rm, p->bn2_rv, s.mu2, s.rstd2);
+    k_bn_apply<<<gs(B * H2), 256, 0, st>>>(s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh, inv_keep, seed, 2,
+                                           s.a2, H2, keep2);
+    rc = gemm_bf16(s.a2, H2, 0, s.wf2b, H2, 0, (int)B, F2N, H2, s.f2, F2N, nullptr, 0, p->fus4_b, 1, st);
+    if (rc) return rc;
+    k_cox_head<<<gs(B * 32), 256, 0, st>>>(s.f2, p->cox_w, p->cox_b, B, hazard);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_grads *g, const float *d_hazard,
+                          const float *d_gate, const float *clinical, const float *mask, int64_t B, int32_t rna_dim,
+                          int32_t training, float dropout_p, uint64_t seed, float *d_ct_feat, const void *saved,
+                          size_t saved_bytes, void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
+    B200_REQUIRE(p && g && d_hazard && clinical && saved && workspace, "null pointer");
+    B200_REQUIRE(B >= 1 && rna_dim >= 1, "B, rna_dim");
+    const bool gated = mask != nullptr;
+    size_t need = 0;
+    const Saved s = carve_saved(const_cast<void *>(saved), B, rna_dim, &need);
+    if (saved_bytes < need) { set_error("head bwd: saved buffer %zu < %zu", saved_bytes, need); return B200SURV_WORKSPACE_TOO_SMALL; }
+    const Scratch w = carve_scratch(workspace, B, &need);
+    if (workspace_bytes < need) { set_error("head bwd: workspace %zu < %zu", workspace_bytes, need); return B200SURV_WORKSPACE_TOO_SMALL; }
+    cudaStream_t st = as_stream(stream);
+    const int Kp = kpad(rna_dim);
+    const uint32_t thresh = training ? drop_thresh(dropout_p) : 0;
+    const float inv_keep = 1.f / (1.f - dropout_p);
+    const int nsl = nslices_for(B);
+    int32_t rc;
+
+    // ---- cox head: dwcox = sum_b dhz[b] f2[b], dbcox = sum dhz; dF2 (ReLU-masked, bf16)
+    rowscale_sum(s.f2, F2N, d_hazard, 1, B, F2N, w.partial, g->cox_w, w.v1, st);
+    B200_CHECK_CUDA(cudaMemcpyAsync(g->cox_b, w.v1, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    k_cox_head_bwd<<<gs(B * F2N), 256, 0, st>>>(d_hazard, s.f2, p->cox_w, B, w.b0);           // b0 = dF2 [B][128]
+    // ---- fusion.4: dW = dF2^T a2, db = colsum dF2, dA2 = dF2 Wf2
+    rc = gemm_bf16(w.b0, F2N, 1, s.a2, H2, 1, F2N, H2, (int)B, g->fus4_w, H2, nullptr, 0, nullptr, 0, st);
+    if (rc) return rc;
+    col_sum_bf16(w.b0, B, F2N, w.t2, w.partial, g->fus4_b, st);
+    rc = gemm_bf16(w.b0, F2N, 0, s.wf2b, H2, 1, (int)B, H2, F2N, w.t0, H2, nullptr, 0, nullptr, 0, st);  // t0 = dA2 [B][256]
+    if (rc) return rc;
+    // ---- fusion.1-3 (BN, ReLU, Dropout) backward -> dH2 (bf16, b1)
+    k_bn_bwd_dy<<<gs(B * H2), 256, 0, st>>>(w.t0, H2, s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh, inv_keep,
+                                            seed, 2, w.t1);                                       // t1 = dy
+    colreduce<1>(w.t1, H2, s.h2, H2, s.mu2, s.rstd2, nullptr, 0, B, H2, w.partial, nsl, st);
+    k_colreduce_final<<<(H2 + 255) / 256, 256, 0, st>>>(w.partial, nsl, H2, 1.f, g->bn2_b, g->bn2_w);  // dbeta, dgamma
+    k_bn_bwd_dx<<<gs(B * H2), 256, 0, st>>>(w.t1, s.h2, H2, s.mu2, s.rstd2, p->bn2_w, g->bn2_b, g->bn2_w, B, H2, training,
+                                            w.b1, H2);                                            // b1 = dH2
+    k_bn_bias_grad<<<(H2 + 255) / 256, 256, 0, st>>>(g->bn2_b, p->bn2_w, s.rstd2, H2, training, g->fus0_b);
+    // ---- fusion.0: dW = dH2^T fused, dfused = dH2 Wf1
+    rc = gemm_bf16(w.b1, H2, 1, s.fused, FEAT, 1, H2, FEAT, (int)B, g->fus0_w, FEAT, nullptr, 0, nullptr, 0, st);
+    if (rc) return rc;
+    rc = gemm_bf16(w.b1, H2, 0, s.wf1b, FEAT, 1, (int)B, FEAT, H2, w.t0, FEAT, nullptr, 0, nullptr, 0, st);  // t0 = dfused
+    if (rc) return rc;
+    const float *dfeat = w.t0;
+    const float *dz = nullptr;
+    if (gated) {
+        // ---- gate: softmax / scaling backward, gate.2 and gate.0
+        k_gate_apply_bwd<<<gs(B * 32), 256, 0, st>>>(w.t0, s.feat, s.gate, s.zh, p->gate2_w, d_gate, B, w.t1, w.dlogit,
+                                                     w.b0);                       // t1 = dfeat, b0 = dzh [B][64]
+        for (int k = 0; k < 3; ++k)
+            rowscale_sum(s.zh, GH, w.dlogit + k, 3, B, GH, w.partial, g->gate2_w + k * GH, w.v0 + k, st);
+        B200_CHECK_CUDA(cudaMemcpyAsync(g->gate2_b, w.v0, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        rc = gemm_bf16(w.b0, GH, 1, s.z, GZP, 1, GH, GZ, (int)B, g->gate0_w, GZ, nullptr, 0, nullptr, 0, st);
+        if (rc) return rc;
+        col_sum_bf16(w.b0, B, GH, w.t2, w.partial, g->gate0_b, st);
+        rc = gemm_bf16(w.b0, GH, 0, s.wg1b, GZP, 1, (int)B, GZP, GH, w.t0, GZP, nullptr, 0, nullptr, 0, st);  // t0 = dz
+        if (rc) return rc;
+        dfeat = w.t1;
+        dz = w.t0;
+    }
+    // ---- masks, clinical encoder
+    k_gate_prep_bwd<<<gs(B * FEAT), 256, 0, st>>>(dfeat, dz, GZP, mask, s.r, clinical, p->clin_w, p->clin_b, B, d_ct_feat,
+                                                  w.b1, w.dC);                    // b1 = dR [B][128]
+    rowscale_sum(w.dC, CL, clinical, 1, B, CL, w.partial, g->clin_w, nullptr, st);
+    col_sum(w.dC, CL, B, CL, w.partial, g->clin_b, st);
+    // ---- rna_encoder.4: dW = dR^T a1, db, dA1 = dR W2
+    rc = gemm_bf16(w.b1, R1, 1, s.a1, H1, 1, R1, H1, (int)B, g->rna4_w, H1, nullptr, 0, nullptr, 0, st);
+    if (rc) return rc;
+    col_sum_bf16(w.b1, B, R1, w.t2, w.partial, g->rna4_b, st);
+    rc = gemm_bf16(w.b1, R1, 0, s.w2b, H1, 1, (int)B, H1, R1, w.t0, H1, nullptr, 0, nullptr, 0, st);  // t0 = dA1 [B][512]
+    if (rc) return rc;
+    // ---- rna_encoder.1-3 backward -> dH1 (bf16, b0)
+    k_bn_bwd_dy<<<gs(B * H1), 256, 0, st>>>(w.t0, H1, s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh, inv_keep,
+                                            seed, 1, w.t1);
+    colreduce<1>(w.t1, H1, s.h1, H1, s.mu1, s.rstd1, nullptr, 0, B, H1, w.partial, nsl, st);
+    k_colreduce_final<<<(H1 + 255) / 256, 256, 0, st>>>(w.partial, nsl, H1, 1.f, g->bn1_b, g->bn1_w);
+    k_bn_bwd_dx<<<gs(B * H1), 256, 0, st>>>(w.t1, s.h1, H1, s.mu1, s.rstd1, p->bn1_w, g->bn1_b, g->bn1_w, B, H1, training,
+                                            w.b0, H1);                             // b0 = dH1
+    k_bn_bias_grad<<<(H1 + 255) / 256, 256, 0, st>>>(g->bn1_b, p->bn1_w, s.rstd1, H1, training, g->rna0_b);
+    // ---- rna_encoder.0: dW1 [512][rna_dim] = dH1^T x  (the big one; x is an input, no dx)
+    rc = gemm_bf16(w.b0, H1, 1, s.xb, Kp, 1, H1, rna_dim, (int)B, g->rna0_w, rna_dim, nullptr, 0, nullptr, 0, st);
+    if (rc) return rc;
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+}  // extern "C"

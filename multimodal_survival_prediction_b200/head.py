@@ -1,0 +1,196 @@
+"""Late-fusion survival heads on B200 -- host-side mirror of the reference's model classes.
+
+``PartialModalityNet(rna_dim=5005, clinical_dim=1).forward(ct, rna, clinical, mask) -> (hazard, gate)``
+mirrors scripts/training/partial_modality_training.py:165-277, and
+``MultiModalSurvivalNet(rna_dim=5005, clinical_dim=1).forward(ct, rna, clinical) -> hazard`` mirrors
+scripts/training/final_multimodal.py:59-150: same constructor arguments, forward signatures, return
+types and ``state_dict`` keys/shapes (so ``.pth`` files interchange).  The sub-modules exist as
+parameter containers; everything from the 128-d CT feature onward runs in libb200surv.so
+(csrc/head.cu + csrc/gemm_tc.cu: tcgen05/TMEM GEMMs, fused BatchNorm/dropout/gate kernels) through
+``b200surv_head_fwd`` / ``b200surv_head_bwd``.  The CT encoder stays a PyTorch/cuDNN sub-module
+(outside the head).  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+_P_FIELDS = ["rna0_w", "rna0_b", "bn1_w", "bn1_b", "bn1_rm", "bn1_rv", "rna4_w", "rna4_b", "clin_w", "clin_b",
+             "gate0_w", "gate0_b", "gate2_w", "gate2_b", "fus0_w", "fus0_b", "bn2_w", "bn2_b", "bn2_rm", "bn2_rv",
+             "fus4_w", "fus4_b", "cox_w", "cox_b"]
+_G_FIELDS = [f for f in _P_FIELDS if not f.endswith(("_rm", "_rv"))]
+# field -> reference state_dict key
+KEYS = {"rna0_w": "rna_encoder.0.weight", "rna0_b": "rna_encoder.0.bias", "bn1_w": "rna_encoder.1.weight",
+        "bn1_b": "rna_encoder.1.bias", "bn1_rm": "rna_encoder.1.running_mean", "bn1_rv": "rna_encoder.1.running_var",
+        "rna4_w": "rna_encoder.4.weight", "rna4_b": "rna_encoder.4.bias", "clin_w": "clinical_encoder.0.weight",
+        "clin_b": "clinical_encoder.0.bias", "gate0_w": "gate.0.weight", "gate0_b": "gate.0.bias",
+        "gate2_w": "gate.2.weight", "gate2_b": "gate.2.bias", "fus0_w": "fusion.0.weight", "fus0_b": "fusion.0.bias",
+        "bn2_w": "fusion.1.weight", "bn2_b": "fusion.1.bias", "bn2_rm": "fusion.1.running_mean",
+        "bn2_rv": "fusion.1.running_var", "fus4_w": "fusion.4.weight", "fus4_b": "fusion.4.bias",
+        "cox_w": "cox_head.weight", "cox_b": "cox_head.bias"}
+
+
+class HeadParams(ctypes.Structure):
+    _fields_ = [(f, ctypes.c_void_p) for f in _P_FIELDS]
+
+
+class HeadGrads(ctypes.Structure):
+    _fields_ = [(f, ctypes.c_void_p) for f in _G_FIELDS]
+
+
+def _f32c(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+class _HeadFn(torch.autograd.Function):
+    """(ct_feat, rna, clinical, mask|None, training, dropout_p, seed, want_masks, *24 parameter tensors)."""
+
+    @staticmethod
+    def forward(ctx, ct_feat, rna, clinical, mask, training, dropout_p, seed, want_masks, *params):
+        dev = ct_feat.device
+        if dev.type != "cuda":
+            raise L.B200SurvError("the B200 fusion head has no CPU path: move the module and its inputs to CUDA")
+        L.require_device(dev.index)
+        lib = L.load()
+        gated = mask is not None
+        B, rna_dim = rna.shape[0], rna.shape[1]
+        ct_c, rna_c, clin_c = _f32c(ct_feat, dev), _f32c(rna, dev), _f32c(clinical, dev).reshape(B, 1)
+        mask_c = _f32c(mask, dev) if gated else None
+        tens = {}
+        for f, t in zip(_P_FIELDS, params):
+            tens[f] = None if t is None else (t.detach() if f.endswith(("_rm", "_rv")) else _f32c(t, dev))
+        ps = HeadParams(**{f: (t.data_ptr() if t is not None else None) for f, t in tens.items()})
+        sb = lib.b200surv_head_saved_bytes(B, rna_dim)
+        wb = lib.b200surv_head_workspace_bytes(B, rna_dim)
+        saved = torch.empty(sb, dtype=torch.uint8, device=dev)
+        ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+        hazard = torch.empty(B, dtype=torch.float32, device=dev)
+        gate = torch.empty(B, 3, dtype=torch.float32, device=dev) if gated else None
+        keep1 = torch.empty(B, 512, dtype=torch.uint8, device=dev) if want_masks else None
+        keep2 = torch.empty(B, 256, dtype=torch.uint8, device=dev) if want_masks else None
+        with torch.cuda.device(dev):
+            rc = lib.b200surv_head_fwd(ctypes.byref(ps), L.ptr(ct_c), L.ptr(rna_c), L.ptr(clin_c), L.ptr(mask_c), B,
+                                       rna_dim, int(training), ctypes.c_float(dropout_p), ctypes.c_uint64(seed),
+                                       L.ptr(hazard), L.ptr(gate), L.ptr(keep1), L.ptr(keep2), L.ptr(saved), sb,
+                                       L.ptr(ws), wb, L.stream_ptr(dev))
+        L.check(rc, "b200surv_head_fwd")
+        ctx.held = (tens, clin_c, mask_c, saved, ws)
+        ctx.meta = (B, rna_dim, int(training), float(dropout_p), int(seed), gated, [None if p is None else (p.dtype, p.shape) for p in params])
+        ctx.keep_masks = (keep1, keep2)
+        outs = (hazard, gate) if gated else (hazard,)
+        if want_masks:
+            ctx.mark_non_differentiable(keep1, keep2)
+            outs = outs + (keep1, keep2)
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_hazard, *rest):
+        tens, clin_c, mask_c, saved, ws = ctx.held
+        B, rna_dim, training, dropout_p, seed, gated, pmeta = ctx.meta
+        dev = saved.device
+        lib = L.load()
+        d_gate = rest[0] if gated and len(rest) > 0 else None
+        dh = torch.zeros(B, dtype=torch.float32, device=dev) if d_hazard is None else _f32c(d_hazard, dev)
+        dg = None if d_gate is None else _f32c(d_gate, dev)
+        grads = {f: (torch.empty_like(tens[f]) if tens[f] is not None else None) for f in _G_FIELDS}
+        ps = HeadParams(**{f: (t.data_ptr() if t is not None else None) for f, t in tens.items()})
+        gs = HeadGrads(**{f: (t.data_ptr() if t is not None else None) for f, t in grads.items()})
+        d_ct = torch.empty(B, 128, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.b200surv_head_bwd(ctypes.byref(ps), ctypes.byref(gs), L.ptr(dh), L.ptr(dg), L.ptr(clin_c),
+                                       L.ptr(mask_c), B, rna_dim, training, ctypes.c_float(dropout_p),
+                                       ctypes.c_uint64(seed), L.ptr(d_ct), L.ptr(saved), saved.numel(), L.ptr(ws),
+                                       ws.numel(), L.stream_ptr(dev))
+        L.check(rc, "b200surv_head_bwd")
+        out = [d_ct, None, None, None, None, None, None, None]
+        for f, meta in zip(_P_FIELDS, pmeta):
+            if f.endswith(("_rm", "_rv")) or meta is None:
+                out.append(None)
+            else:
+                out.append(grads[f].to(meta[0]).reshape(meta[1]))
+        return tuple(out)
+
+
+def fused_head(module, ct_feat, rna, clinical, mask=None, want_masks=False, seed=None):
+    """Run the head of ``module`` (a PartialModalityNet / MultiModalSurvivalNet from this file) on CUDA."""
+    sd = dict(module.named_parameters())
+    sd.update(dict(module.named_buffers()))
+    params = [sd.get(KEYS[f]) for f in _P_FIELDS]
+    training = module.training
+    p_drop = float(module.rna_encoder[3].p) if training else 0.0
+    if seed is None:
+        seed = int(torch.empty((), dtype=torch.int64).random_().item()) & ((1 << 62) - 1) if (training and p_drop > 0) else 0
+    outs = _HeadFn.apply(ct_feat, rna, clinical, mask, training, p_drop, seed, want_masks, *params)
+    if training:
+        with torch.no_grad():
+            module.rna_encoder[1].num_batches_tracked += 1
+            module.fusion[1].num_batches_tracked += 1
+    return outs
+
+
+def _ct_cnn():
+    # the reference's non-MONAI CT encoder (partial_modality_training.py:179-190): a PyTorch/cuDNN sub-module
+    return nn.Sequential(
+        nn.Conv3d(1, 32, 3, stride=2, padding=1), nn.BatchNorm3d(32), nn.ReLU(),
+        nn.Conv3d(32, 64, 3, stride=2, padding=1), nn.BatchNorm3d(64), nn.ReLU(),
+        nn.Conv3d(64, 128, 3, stride=2, padding=1), nn.BatchNorm3d(128), nn.ReLU(),
+        nn.AdaptiveAvgPool3d(1),
+    )
+
+
+class _HeadBase(nn.Module):
+    def __init__(self, rna_dim=5005, clinical_dim=1, gated=True):
+        super().__init__()
+        if clinical_dim != 1:
+            raise NotImplementedError("the reference only uses clinical_dim=1 (age/100)")
+        self.ct_encoder = _ct_cnn()
+        self.use_monai = False
+        self.ct_pool = nn.AdaptiveAvgPool3d(1)
+        self.rna_encoder = nn.Sequential(nn.Linear(rna_dim, 512), nn.BatchNorm1d(512), nn.ReLU(), nn.Dropout(0.3),
+                                         nn.Linear(512, 128), nn.ReLU())
+        self.clinical_encoder = nn.Sequential(nn.Linear(clinical_dim, 32), nn.ReLU())
+        if gated:
+            self.gate = nn.Sequential(nn.Linear(128 + 128 + 32 + 3, 64), nn.ReLU(), nn.Linear(64, 3), nn.Softmax(dim=1))
+        self.fusion = nn.Sequential(nn.Linear(128 + 128 + 32, 256), nn.BatchNorm1d(256), nn.ReLU(), nn.Dropout(0.3),
+                                    nn.Linear(256, 128), nn.ReLU())
+        self.cox_head = nn.Linear(128, 1)
+
+    def _ct_features(self, ct):
+        return self.ct_encoder(ct).view(ct.size(0), -1)
+
+
+class PartialModalityNet(_HeadBase):
+    """Gated head: forward(ct, rna, clinical, mask) -> (hazard [B], gate_weights [B,3])."""
+
+    def __init__(self, rna_dim=5005, clinical_dim=1):
+        super().__init__(rna_dim, clinical_dim, gated=True)
+
+    def forward(self, ct, rna, clinical, mask):
+        hazard, gate = fused_head(self, self._ct_features(ct), rna, clinical, mask)
+        return hazard, gate
+
+    def forward_features(self, ct_feat, rna, clinical, mask):
+        """Head only, from a precomputed CT feature [B,128] (benchmarks, BASELINE.json configs[1])."""
+        return fused_head(self, ct_feat, rna, clinical, mask)
+
+
+class MultiModalSurvivalNet(_HeadBase):
+    """Ungated head: forward(ct, rna, clinical) -> hazard [B]."""
+
+    def __init__(self, rna_dim=5005, clinical_dim=1):
+        super().__init__(rna_dim, clinical_dim, gated=False)
+
+    def forward(self, ct, rna, clinical):
+        return fused_head(self, self._ct_features(ct), rna, clinical, None)[0]
+
+    def forward_features(self, ct_feat, rna, clinical):
+        return fused_head(self, ct_feat, rna, clinical, None)[0]
+
+
+def gate_entropy_loss(gate_weights, eps=1e-8):
+    """partial_modality_training.py:322-331 (plain autograd; its gradient enters the head through d_gate)."""
+    return -(-(gate_weights * torch.log(gate_weights + eps)).sum(dim=1)).mean()

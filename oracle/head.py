@@ -63,12 +63,28 @@ def _drop(x, keep):
     return x * keep.to(x.dtype) / (1.0 - DROP_P)
 
 
+def _q_bf16(t):
+    """Round to bf16 with a straight-through gradient (models the GEMM operand precision of the B200 path)."""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
 def head_forward(p, ct_feat, rna, clinical, mask=None, train=False, drop1=None, drop2=None,
-                 stats_out=None):
+                 stats_out=None, bf16_operands=False):
     """p: dict of tensors keyed like the reference state_dict.  mask=None selects the ungated head.
 
-    Returns (hazard, gate) for the gated head, hazard for the ungated one."""
-    lin = torch.nn.functional.linear
+    bf16_operands=True rounds both operands of the five large Linear layers to bf16 (products and sums stay in
+    the working precision): the exact function the tensor-core path evaluates, so that ReLU/dropout decisions
+    and therefore gradients can be compared tightly.  Returns (hazard, gate) for the gated head, hazard for the
+    ungated one."""
+    if bf16_operands:
+        big = ("rna_encoder.0", "rna_encoder.4", "gate.0", "fusion.0", "fusion.4")
+
+        def lin(x, w, b):
+            if any(w is p.get(k + ".weight") for k in big):
+                return torch.nn.functional.linear(_q_bf16(x), _q_bf16(w), b)
+            return torch.nn.functional.linear(x, w, b)
+    else:
+        lin = torch.nn.functional.linear
     h = lin(rna, p["rna_encoder.0.weight"], p["rna_encoder.0.bias"])
     h = torch.relu(_bn(h, p, "rna_encoder.1", train, stats_out))
     h = _drop(h, drop1)
