@@ -183,10 +183,18 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-             torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     ev0.record()
+    for i in range(args.steps):      # the headline loop: exactly K steps, nothing else on the stream
+        op.forward(x, tt, e)
+        op.backward(x, tt, e, grad)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    ms_step = ms_total / args.steps
+    # per-kernel durations for the roofline: same loop again with CUDA events around each call
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+             torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
         a, b, c = k_ev[i]
         a.record()
@@ -194,11 +202,8 @@ def run_b200(args):
         b.record()
         op.backward(x, tt, e, grad)
         c.record()
-    ev1.record()
     barrier()
     clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    ms_step = ms_total / args.steps
     fwd_ms = sum(a.elapsed_time(b) for a, b, _ in k_ev) / args.steps
     bwd_ms = sum(b.elapsed_time(c) for _, b, c in k_ev) / args.steps
     tmax = torch.tensor([ms_step], device=dev)
@@ -305,14 +310,16 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": "cox_binned_bwd (13 B/row: 9 read + 4 written)",
                          "achieved": achieved_bwd, "peak": peak, "unit": "GB/s", "frac": achieved_bwd / peak,
                          "traffic": None, "peak_source": peak_src, "ms": bwd_ms,
-                         "fwd": {"kernels": "cox_binned_pass1 + reduce(+scan) + items_finish (9 B/row)",
+                         "fwd": {"kernels": "cox_binned_fwd_fused: pass 1 + reduce + scan + Efron terms + finish (9 B/row)"
+                                 if world == 1 else "cox_binned_pass1, reduce, all-reduce, scan, items_finish (9 B/row)",
                                  "achieved": achieved_fwd, "frac": achieved_fwd / peak, "ms": fwd_ms},
                          "step": {"bytes_per_row": ALGO_BYTES_PER_ROW, "achieved": achieved_step,
                                   "frac": achieved_step / peak, "frac_of_8TBs": achieved_step / 8000.0}},
             "e2e": {"value": e2e_val, "unit": "patients/s", "h2d_bytes_per_step": 9 * n, "d2h_bytes_per_step": 4,
                     "ms_per_step": float(e2e_t.item()) * 1e3, "api": "neg_partial_log_likelihood(log_hz, event, time) + backward, mode=auto"},
-            # per step: pass1, reduce(+scan), items_finish, bwd (+ a stand-alone scan when bins are all-reduced)
-            "gpu_launches": (4 if world == 1 else 5) * args.steps,
+            # per step at N=1: cox_binned_fwd_fused (cooperative) + cox_binned_bwd; at N>1 the forward is split
+            # around the all-reduce: pass1, reduce, scan, items_finish, then bwd
+            "gpu_launches": (2 if world == 1 else 5) * args.steps,
             "clocks": clocks,
             "extra": {"cindex_1m": {"n": cn, "ms": ci_ms, "patients_per_s": cn / (ci_ms * 1e-3),
                                     "ordered_pairs_per_s": sum(counts) / (ci_ms * 1e-3), "counts": counts,

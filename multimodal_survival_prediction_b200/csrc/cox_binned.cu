@@ -20,9 +20,14 @@
 //   K4 pass 2  (backward) streams the rows again, 9 B read + 4 B write:
 //              grad = scale * (d - w * (P[b] - d * F[b]))
 // Algorithmic HBM bytes: 22 per row for fwd+bwd; everything else is O(nbins).
+#include <cooperative_groups.h>
+
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace b200surv {
 namespace {
@@ -168,19 +173,42 @@ __device__ __forceinline__ void p1_row(float eta, float t, bool ev, float c2, un
 // partial layout per (seg, cta): u64 S_cens[nb], u64 S_event[nb], u32 m[nb]   (20 B/bin)
 constexpr size_t PARTIAL_BYTES_PER_BIN = 20;
 
-__global__ void __launch_bounds__(P1_THREADS, 1)
-cox_binned_pass1(const float *__restrict__ log_hz, const float *__restrict__ time,
-                 const uint8_t *__restrict__ event, const int64_t *__restrict__ seg_off, int64_t n,
-                 int nb, float shift, int vec_ok, unsigned char *__restrict__ partial,
-                 CtaRec *__restrict__ recs, unsigned *__restrict__ tickets_k2) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned *h = reinterpret_cast<unsigned *>(smem_raw);
+// end of pass 1: flush the CTA histogram with plain coalesced stores (summed exactly by the reduce step) and
+// write the CTA record.  All threads of the block must call.
+__device__ __forceinline__ void pass1_flush(const unsigned *h, const P1Acc &acc, double se_d, double sw_d,
+                                            unsigned char *__restrict__ partial, CtaRec *__restrict__ recs, int seg,
+                                            int cta, int nctas, int nb, double *red_d, float *red_f, unsigned *red_u) {
+    __syncthreads();
+    unsigned char *out = partial + ((size_t)seg * nctas + cta) * PARTIAL_BYTES_PER_BIN * (size_t)nb;
+    unsigned long long *o64 = reinterpret_cast<unsigned long long *>(out);
+    unsigned *o32 = reinterpret_cast<unsigned *>(out + 16 * (size_t)nb);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        const unsigned *hb = h + 5 * i;
+        o64[i] = ((unsigned long long)hb[1] << 32) | hb[0];
+        o64[nb + i] = ((unsigned long long)hb[3] << 32) | hb[2];
+        o32[i] = hb[4];
+    }
+    const unsigned flags = (acc.notbin ? B200SURV_COXF_NOT_BINNABLE : 0u) | (acc.badt ? B200SURV_COXF_BAD_TIME : 0u);
+    const double sw = block_reduce<double>(sw_d * FIX_INV, 0.0, OpAddD(), red_d);
+    const double se = block_reduce<double>(se_d, 0.0, OpAddD(), red_d);
+    const float mx = block_reduce<float>(acc.mx, -INFINITY, OpMaxF(), red_f);
+    const unsigned fl = block_reduce<unsigned>(flags, 0u, OpOrU(), red_u);
+    if (threadIdx.x == 0) {
+        CtaRec rec;
+        rec.sum_ev_eta = se; rec.sum_w = sw; rec.max_eta = mx; rec.flags = fl;
+        recs[(size_t)seg * nctas + cta] = rec;
+    }
+}
+
+// body of pass 1 for CTA `cta` of `nctas` of segment `seg` (shared by the stand-alone and the fused kernel)
+__device__ __forceinline__ void pass1_body(const float *__restrict__ log_hz, const float *__restrict__ time,
+                                           const uint8_t *__restrict__ event, const int64_t *__restrict__ seg_off,
+                                           int64_t n, int nb, float shift, int vec_ok,
+                                           unsigned char *__restrict__ partial, CtaRec *__restrict__ recs,
+                                           int seg, int cta, int nctas, unsigned *h) {
     __shared__ double red_d[32];
     __shared__ float red_f[32];
     __shared__ unsigned red_u[32];
-
-    const int seg = blockIdx.y, cta = blockIdx.x, nctas = gridDim.x;
-    if (cta == 0 && threadIdx.x == 0) tickets_k2[seg] = 0;  // "last CTA done" ticket of the reduce kernel
     for (int i = threadIdx.x; i < 5 * nb; i += blockDim.x) h[i] = 0u;
     __syncthreads();
 
@@ -224,28 +252,99 @@ cox_binned_pass1(const float *__restrict__ log_hz, const float *__restrict__ tim
         }
     }
     se_d += (double)acc.se; sw_d += (double)acc.sw;
+    pass1_flush(h, acc, se_d, sw_d, partial, recs, seg, cta, nctas, nb, red_d, red_f, red_u);
+}
+
+// TMA-staged variant of the pass-1 body (one cohort, 16-byte aligned inputs, nbins <= 4096): warp 31 is a
+// producer that keeps TMA_STAGES bulk copies (cp.async.bulk, mbarrier tx-count) of 3968-row tiles in flight;
+// the other 31 warps bin the rows out of shared memory.  Memory latency is hidden by the ring instead of by
+// registers (a 1024-thread CTA only has 64 registers per thread).
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_CONSUMERS = P1_THREADS - 32;
+constexpr int TMA_TILE = TMA_CONSUMERS * 4;       // 3968 rows
+constexpr int TMA_STAGE_BYTES = TMA_TILE * 9;     // eta f32 | time f32 | event u8 = 35,712 B
+__host__ __device__ inline size_t tma_hist_bytes(int nb) { return ((size_t)nb * 24 + 16 + 127) / 128 * 128; }
+__host__ __device__ inline size_t tma_smem_bytes(int nb) {
+    return tma_hist_bytes(nb) + (size_t)TMA_STAGES * TMA_STAGE_BYTES + 2 * TMA_STAGES * sizeof(uint64_t);
+}
+
+__device__ __forceinline__ void pass1_body_tma(const float *__restrict__ log_hz, const float *__restrict__ time,
+                                               const uint8_t *__restrict__ event, int64_t n, int nb, float shift,
+                                               unsigned char *__restrict__ partial, CtaRec *__restrict__ recs,
+                                               int cta, int nctas, unsigned char *smem_raw) {
+    __shared__ double red_d[32];
+    __shared__ float red_f[32];
+    __shared__ unsigned red_u[32];
+    unsigned *h = reinterpret_cast<unsigned *>(smem_raw);
+    unsigned char *stages = smem_raw + tma_hist_bytes(nb);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stages + (size_t)TMA_STAGES * TMA_STAGE_BYTES);  // full[S], empty[S]
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < 5 * nb; i += blockDim.x) h[i] = 0u;
+    if (t == 0) {
+        for (int s = 0; s < TMA_STAGES; ++s) {
+            mbarrier_init(smem_addr_u32(bars + s), 1);
+            mbarrier_init(smem_addr_u32(bars + TMA_STAGES + s), TMA_CONSUMERS / 32);
+        }
+        mbarrier_init_fence();
+    }
     __syncthreads();
 
-    // flush the CTA histogram with plain coalesced stores (summed exactly by the reduce kernel)
-    unsigned char *out = partial + ((size_t)seg * nctas + cta) * PARTIAL_BYTES_PER_BIN * (size_t)nb;
-    unsigned long long *o64 = reinterpret_cast<unsigned long long *>(out);
-    unsigned *o32 = reinterpret_cast<unsigned *>(out + 16 * (size_t)nb);
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-        const unsigned *hb = h + 5 * i;
-        o64[i] = ((unsigned long long)hb[1] << 32) | hb[0];
-        o64[nb + i] = ((unsigned long long)hb[3] << 32) | hb[2];
-        o32[i] = hb[4];
+    const float c2 = (float)FIX_BITS - shift * LOG2E;
+    const unsigned nbu = (unsigned)nb;
+    const uint32_t h_addr = smem_addr_u32(h);
+    P1Acc acc{0.f, -INFINITY, 0.f, false, false};
+    double se_d = 0.0, sw_d = 0.0;
+    const int64_t ntiles = n / TMA_TILE;  // full tiles; the remainder goes through direct loads below
+    if (warp == P1_THREADS / 32 - 1) {
+        if (lane == 0) {  // producer
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t tile = cta; tile < ntiles; tile += nctas) {
+                mbarrier_wait(smem_addr_u32(bars + TMA_STAGES + s), ph ^ 1);
+                const uint32_t full = smem_addr_u32(bars + s);
+                mbarrier_expect_tx(full, TMA_STAGE_BYTES);
+                const uint32_t dst = smem_addr_u32(stages + (size_t)s * TMA_STAGE_BYTES);
+                const int64_t row0 = tile * TMA_TILE;
+                bulk_load_1d(dst, log_hz + row0, TMA_TILE * 4, full);
+                bulk_load_1d(dst + TMA_TILE * 4, time + row0, TMA_TILE * 4, full);
+                bulk_load_1d(dst + TMA_TILE * 8, event + row0, TMA_TILE, full);
+                if (++s == TMA_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {  // consumers: thread t bins rows 4t .. 4t+3 of every tile
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t tile = cta; tile < ntiles; tile += nctas) {
+            mbarrier_wait(smem_addr_u32(bars + s), ph);
+            const unsigned char *st = stages + (size_t)s * TMA_STAGE_BYTES;
+            const float4 e4 = *reinterpret_cast<const float4 *>(st + 16 * t);
+            const float4 t4 = *reinterpret_cast<const float4 *>(st + TMA_TILE * 4 + 16 * t);
+            const uint32_t v4 = *reinterpret_cast<const uint32_t *>(st + TMA_TILE * 8 + 4 * t);
+            __syncwarp();
+            if (lane == 0) mbarrier_arrive(smem_addr_u32(bars + TMA_STAGES + s));  // data is in registers: free the slot
+            p1_group(e4, t4, v4, c2, nbu, h_addr, acc);
+            se_d += (double)acc.se; sw_d += (double)acc.sw; acc.se = 0.f; acc.sw = 0.f;
+            if (++s == TMA_STAGES) { s = 0; ph ^= 1; }
+        }
     }
-    const unsigned flags = (acc.notbin ? B200SURV_COXF_NOT_BINNABLE : 0u) | (acc.badt ? B200SURV_COXF_BAD_TIME : 0u);
-    const double sw = block_reduce<double>(sw_d * FIX_INV, 0.0, OpAddD(), red_d);
-    const double se = block_reduce<double>(se_d, 0.0, OpAddD(), red_d);
-    const float mx = block_reduce<float>(acc.mx, -INFINITY, OpMaxF(), red_f);
-    const unsigned fl = block_reduce<unsigned>(flags, 0u, OpOrU(), red_u);
-    if (threadIdx.x == 0) {
-        CtaRec rec;
-        rec.sum_ev_eta = se; rec.sum_w = sw; rec.max_eta = mx; rec.flags = fl;
-        recs[(size_t)seg * nctas + cta] = rec;
+    {  // remainder rows (fewer than one tile): direct loads, spread over the whole grid
+        const int64_t rem0 = ntiles * TMA_TILE;
+        for (int64_t row = rem0 + (int64_t)cta * blockDim.x + t; row < n; row += (int64_t)nctas * blockDim.x)
+            p1_row(log_hz[row], time[row], event[row] != 0, c2, nbu, h_addr, acc);
     }
+    se_d += (double)acc.se; sw_d += (double)acc.sw;
+    pass1_flush(h, acc, se_d, sw_d, partial, recs, 0, cta, nctas, nb, red_d, red_f, red_u);
+}
+
+__global__ void __launch_bounds__(P1_THREADS, 1)
+cox_binned_pass1(const float *__restrict__ log_hz, const float *__restrict__ time,
+                 const uint8_t *__restrict__ event, const int64_t *__restrict__ seg_off, int64_t n,
+                 int nb, float shift, int vec_ok, unsigned char *__restrict__ partial,
+                 CtaRec *__restrict__ recs, unsigned *__restrict__ tickets_k2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (blockIdx.x == 0 && threadIdx.x == 0) tickets_k2[blockIdx.y] = 0;  // "last CTA done" ticket of the reduce kernel
+    pass1_body(log_hz, time, event, seg_off, n, nb, shift, vec_ok, partial, recs, blockIdx.y, blockIdx.x, gridDim.x,
+               reinterpret_cast<unsigned *>(smem_raw));
 }
 
 // ================================================================ block scans (1024 threads)
@@ -594,6 +693,232 @@ cox_binned_items_finish(const long long *__restrict__ bins, const float *__restr
     }
 }
 
+// ================================================================ fused forward (one cohort, one launch)
+// pass 1, the exact reduction of the CTA partials, the suffix scan, the Efron terms and the finish in ONE
+// cooperative kernel (one CTA per SM, grid barriers between the phases): removes two launches and the two
+// single-CTA tails of the K2/K3 pipeline.  Every CTA scans the nbins sums redundantly in shared memory.
+struct FusedArgs {
+    long long *bins;   // [3 nb + 4]
+    float *bins_max;   // [2]
+    double *tgf;       // [3][nb]
+    int ties, reduction;
+    float *out_loss;
+    unsigned char *state;
+};
+
+template <int MAXPER>
+__global__ void __launch_bounds__(P1_THREADS, 1)
+cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__ time,
+                     const uint8_t *__restrict__ event, int64_t n, int nb, float shift, int vec_ok,
+                     unsigned char *__restrict__ partial, CtaRec *__restrict__ recs, FusedArgs fa, int use_tma) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double shd[33];
+    __shared__ int shi[33];
+    cg::grid_group grid = cg::this_grid();
+    const int cta = blockIdx.x, nctas = gridDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (use_tma)
+        pass1_body_tma(log_hz, time, event, n, nb, shift, partial, recs, cta, nctas, smem_raw);
+    else
+        pass1_body(log_hz, time, event, nullptr, n, nb, shift, vec_ok, partial, recs, 0, cta, nctas,
+                   reinterpret_cast<unsigned *>(smem_raw));
+    grid.sync();
+
+    // ---- phase 2: exact reduction of the partials, bins [b0, b1) of this CTA, one warp per bin
+    long long *bs = fa.bins;
+    {
+        const int nbpc = (nb + nctas - 1) / nctas;
+        const int b0 = cta * nbpc, b1 = min(nb, b0 + nbpc);
+        for (int b = b0 + warp; b < b1; b += P1_THREADS / 32) {
+            unsigned long long vc[RED_MAX_ITERS], ve[RED_MAX_ITERS];
+            unsigned vm[RED_MAX_ITERS];
+#pragma unroll
+            for (int k = 0; k < RED_MAX_ITERS; ++k) {  // all loads in flight together (nctas <= 160)
+                const int c = lane + 32 * k;
+                const bool in = c < nctas;
+                const unsigned char *pc = partial + (size_t)(in ? c : 0) * PARTIAL_BYTES_PER_BIN * (size_t)nb;
+                vc[k] = in ? __ldcg(reinterpret_cast<const unsigned long long *>(pc) + b) : 0ull;
+                ve[k] = in ? __ldcg(reinterpret_cast<const unsigned long long *>(pc) + nb + b) : 0ull;
+                vm[k] = in ? __ldcg(reinterpret_cast<const unsigned *>(pc + 16 * (size_t)nb) + b) : 0u;
+            }
+            unsigned long long sc = 0, se = 0;
+            unsigned m = 0;
+#pragma unroll
+            for (int k = 0; k < RED_MAX_ITERS; ++k) { sc += vc[k]; se += ve[k]; m += vm[k]; }
+            const long long tc = warp_sum((long long)sc), te = warp_sum((long long)se), tm = warp_sum((long long)m);
+            if (lane == 0) {
+                bs[b] = tc; bs[nb + b] = te; bs[2 * nb + b] = tm;
+                fa.tgf[b] = 0.0; fa.tgf[nb + b] = 0.0; fa.tgf[2 * nb + b] = 0.0;
+            }
+        }
+        if (cta == 0 && warp == P1_THREADS / 32 - 1) {
+            double se = 0.0, sw = 0.0;
+            float mx = -INFINITY;
+            unsigned fl = 0;
+            for (int c = lane; c < nctas; c += 32) {
+                const CtaRec *rp = recs + c;
+                se += __ldcg(&rp->sum_ev_eta); sw += __ldcg(&rp->sum_w); mx = fmaxf(mx, __ldcg(&rp->max_eta));
+                fl |= __ldcg(&rp->flags);
+            }
+            se = warp_sum(se); sw = warp_sum(sw); mx = warp_max(mx); fl = warp_or(fl);
+            if (lane == 0) {
+                bs[3 * (size_t)nb + 0] = __double2ll_rn(se * ETA_SCALE);
+                bs[3 * (size_t)nb + 1] = (fl & B200SURV_COXF_NOT_BINNABLE) ? 1 : 0;
+                bs[3 * (size_t)nb + 2] = (long long)fmin(ceil(sw), 9.0e18);
+                bs[3 * (size_t)nb + 3] = (fl & B200SURV_COXF_BAD_TIME) ? 1 : 0;
+                fa.bins_max[0] = mx;
+                fa.bins_max[1] = -1.f;
+            }
+        }
+    }
+    grid.sync();
+
+    // ---- phase 3: redundant suffix scan into shared memory (reuses the histogram storage: 20 B/bin)
+    double *sD = reinterpret_cast<double *>(smem_raw);
+    double *s_rm = sD + nb;
+    int *s_m = reinterpret_cast<int *>(s_rm + nb);
+    int *s_big = s_m + nb;  // list of the bins with more than BIG_M events (the fused launch allocates 24 B/bin)
+    __shared__ int s_nbig;
+    const int per = nb / P1_THREADS > 0 ? nb / P1_THREADS : 1;
+    const int hi_b = nb - t * per;
+    int n_events, n_times;
+    if (t == 0) s_nbig = 0;
+    __syncthreads();
+    {
+        long long rc[MAXPER], re[MAXPER], rmv[MAXPER];
+#pragma unroll
+        for (int k = 0; k < MAXPER; ++k) {
+            const int b = hi_b - 1 - k;
+            const bool in = (k < per) && (b >= 0);
+            rc[k] = in ? __ldcg(bs + b) : 0ll;
+            re[k] = in ? __ldcg(bs + nb + b) : 0ll;
+            rmv[k] = in ? __ldcg(bs + 2 * nb + b) : 0ll;
+        }
+        double sv[MAXPER];
+        double loc = 0.0;
+        int locm = 0, net = 0;
+#pragma unroll
+        for (int k = 0; k < MAXPER; ++k) {
+            sv[k] = ((double)(unsigned long long)rc[k] + (double)(unsigned long long)re[k]) * FIX_INV;
+            loc += sv[k];
+            locm += (int)rmv[k];
+            net += rmv[k] > 0 ? 1 : 0;
+        }
+        double tot;
+        double run = block_exscan<double>(loc, shd, &tot);
+        block_exscan<int>(locm, shi, &n_events);
+        block_exscan<int>(net, shi, &n_times);
+#pragma unroll
+        for (int k = 0; k < MAXPER; ++k) {
+            const int b = hi_b - 1 - k;
+            if (k < per && b >= 0) {
+                run += sv[k];
+                const int m = (int)rmv[k];
+                sD[b] = run;
+                s_rm[b] = m > 0 ? ((double)(unsigned long long)re[k] * FIX_INV) / (run * (double)m) : 0.0;
+                s_m[b] = m;
+                if (m > BIG_M) s_big[atomicAdd(&s_nbig, 1)] = b;
+            }
+        }
+    }
+    __syncthreads();
+    const bool efron = fa.ties == B200SURV_TIES_EFRON;
+    {
+        // per-bin terms: warp gw owns bins gw, gw + W, ... (consecutive bins on different SMs)
+        const int gw = warp * nctas + cta, W = nctas * (P1_THREADS / 32);
+        for (int b = gw; b < nb; b += W) {
+            const int m = s_m[b];
+            if (m == 0 || (efron && m > BIG_M)) continue;
+            const double D = sD[b];
+            float vt = 0.f, vg = 0.f, vf = 0.f;
+            if (efron) {
+                efron_terms(0, m, lane, s_rm[b], 1.f / (float)m, vt, vg, vf);
+                vt = warp_sum(vt); vg = warp_sum(vg); vf = warp_sum(vf);
+            }
+            if (lane == 0) {
+                const double invD = 1.0 / D;
+                fa.tgf[b] = (double)vt + (double)m * log(D);
+                fa.tgf[nb + b] = efron ? (double)vg * invD : (double)m * invD;
+                fa.tgf[2 * nb + b] = (double)vf * invD;
+            }
+        }
+        if (efron) {
+            const int nbig = s_nbig;
+            for (int i = 0; i < nbig; ++i) {  // bins with more than BIG_M events: all warps of the grid share each
+                const int b = s_big[i];
+                const int m = s_m[b];
+                const double D = sD[b], rm = s_rm[b];
+                const float inv_m = 1.f / (float)m;
+                double at = 0.0, ag = 0.0, af = 0.0;
+                bool any = false;
+                for (int l0 = gw * BIG_CHUNK; l0 < m; l0 += W * BIG_CHUNK) {
+                    float vt = 0.f, vg = 0.f, vf = 0.f;
+                    efron_terms(l0, min(m, l0 + BIG_CHUNK), lane, rm, inv_m, vt, vg, vf);
+                    at += (double)vt; ag += (double)vg; af += (double)vf;
+                    any = true;
+                }
+                if (any) {
+                    at = warp_sum(at); ag = warp_sum(ag); af = warp_sum(af);
+                    if (lane == 0) {
+                        const double invD = 1.0 / D;
+                        if (gw == 0) at += (double)m * log(D);
+                        atomicAdd(fa.tgf + b, at);
+                        atomicAdd(fa.tgf + nb + b, ag * invD);
+                        atomicAdd(fa.tgf + 2 * nb + b, af * invD);
+                    }
+                }
+            }
+        }
+    }
+    grid.sync();
+    if (cta != 0) return;
+
+    // ---- phase 4 (CTA 0): P = prefix(G), loss, header, (P,F) table
+    b200surv_cox_header *hdr = reinterpret_cast<b200surv_cox_header *>(fa.state);
+    float2 *table = reinterpret_cast<float2 *>(fa.state + sizeof(b200surv_cox_header));
+    const int lo_b = t * per;
+    double tv[MAXPER], gv[MAXPER], fv[MAXPER];
+#pragma unroll
+    for (int k = 0; k < MAXPER; ++k) {
+        const int b = lo_b + k;
+        const bool in = (k < per) && (b < nb) && s_m[b] > 0;
+        tv[k] = in ? __ldcg(fa.tgf + b) : 0.0;
+        gv[k] = in ? __ldcg(fa.tgf + nb + b) : 0.0;
+        fv[k] = in ? __ldcg(fa.tgf + 2 * nb + b) : 0.0;
+    }
+    double tsum = 0.0, gsum = 0.0;
+#pragma unroll
+    for (int k = 0; k < MAXPER; ++k) { tsum += tv[k]; gsum += gv[k]; }
+    double tot;
+    double run = block_exscan<double>(gsum, shd, &tot);
+#pragma unroll
+    for (int k = 0; k < MAXPER; ++k) {
+        const int b = lo_b + k;
+        if (k < per && b < nb) { run += gv[k]; table[b] = make_float2((float)run, (float)fv[k]); }
+    }
+    const double T = block_reduce<double>(tsum, 0.0, OpAddD(), shd);
+    if (t == 0) {
+        const double sum_ev_eta = (double)__ldcg(bs + 3 * (size_t)nb) * ETA_INV;
+        const double pll = sum_ev_eta - (T + (double)n_events * (double)shift);
+        double norm = 1.0;
+        if (fa.reduction == B200SURV_REDUCE_MEAN_EVENTS) norm = (double)n_events;
+        else if (fa.reduction == B200SURV_REDUCE_MEAN_TERMS) norm = efron ? (double)n_times : (double)n_events;
+        unsigned flags = 0;
+        if (__ldcg(bs + 3 * (size_t)nb + 1) != 0) flags |= B200SURV_COXF_NOT_BINNABLE;
+        if (__ldcg(bs + 3 * (size_t)nb + 3) != 0) flags |= B200SURV_COXF_BAD_TIME;
+        const float mx = __ldcg(fa.bins_max);
+        const double sumw = (double)__ldcg(bs + 3 * (size_t)nb + 2);
+        if (!(mx - shift <= SHIFT_HI) || !(mx - shift >= SHIFT_LO) || sumw >= SUMW_LIMIT) flags |= B200SURV_COXF_EXP_RANGE;
+        float loss = 0.f, scale = 0.f;
+        if (n_events > 0) { loss = (float)(-pll / norm); scale = (float)(-1.0 / norm); }
+        if (flags) { loss = __int_as_float(0x7fc00000); scale = loss; }
+        hdr->flags = flags; hdr->mode = B200SURV_COX_BINNED; hdr->loss = loss; hdr->scale = scale;
+        hdr->shift = shift; hdr->max_log_hz = mx; hdr->max_time = -1.f;
+        hdr->nbins = nb; hdr->n_events = n_events; hdr->n_event_times = n_times; hdr->pll = pll;
+        hdr->reserved = 0;
+        fa.out_loss[0] = loss;
+    }
+}
+
 // ================================================================ K4: pass 2 (backward)
 __device__ __forceinline__ float p2_row(float eta, float t, bool ev, float c2, float k, const float2 *tab, int nb) {
     const float w = ex2_approx(fmaf(eta, LOG2E, c2));  // c2 = -shift * log2(e)
@@ -632,29 +957,32 @@ cox_binned_bwd(const float *__restrict__ grad_out, const unsigned char *__restri
     {
         float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), t0 = e0, e1 = e0, t1 = e0;
         uint32_t v0 = 0, v1 = 0;
+        // REVERSE traversal (virtual index q counts down from the last group): the rows pass 1 read last are
+        // still L2-resident, so the backward pass starts there
+        const int64_t last = ngroups - 1;
         bool h0 = g < ngroups, h1 = g + stride < ngroups;
-        if (h0) { e0 = ldg_stream_f4(lh + 4 * g); t0 = ldg_stream_f4(tm + 4 * g); v0 = ldg_stream_u32(evp + 4 * g); }
-        if (h1) { e1 = ldg_stream_f4(lh + 4 * (g + stride)); t1 = ldg_stream_f4(tm + 4 * (g + stride)); v1 = ldg_stream_u32(evp + 4 * (g + stride)); }
+        if (h0) { e0 = ldg_stream_f4(lh + 4 * (last - g)); t0 = ldg_stream_f4(tm + 4 * (last - g)); v0 = ldg_stream_u32(evp + 4 * (last - g)); }
+        if (h1) { e1 = ldg_stream_f4(lh + 4 * (last - g - stride)); t1 = ldg_stream_f4(tm + 4 * (last - g - stride)); v1 = ldg_stream_u32(evp + 4 * (last - g - stride)); }
         while (h0) {
             const int64_t gn = g + 2 * stride;
             const bool n0 = gn < ngroups, n1 = gn + stride < ngroups;
             float4 ne0 = e0, nt0 = t0, ne1 = e1, nt1 = t1;
             uint32_t nv0 = 0, nv1 = 0;
-            if (n0) { ne0 = ldg_stream_f4(lh + 4 * gn); nt0 = ldg_stream_f4(tm + 4 * gn); nv0 = ldg_stream_u32(evp + 4 * gn); }
-            if (n1) { ne1 = ldg_stream_f4(lh + 4 * (gn + stride)); nt1 = ldg_stream_f4(tm + 4 * (gn + stride)); nv1 = ldg_stream_u32(evp + 4 * (gn + stride)); }
+            if (n0) { ne0 = ldg_stream_f4(lh + 4 * (last - gn)); nt0 = ldg_stream_f4(tm + 4 * (last - gn)); nv0 = ldg_stream_u32(evp + 4 * (last - gn)); }
+            if (n1) { ne1 = ldg_stream_f4(lh + 4 * (last - gn - stride)); nt1 = ldg_stream_f4(tm + 4 * (last - gn - stride)); nv1 = ldg_stream_u32(evp + 4 * (last - gn - stride)); }
             float4 o0;
             o0.x = p2_row(e0.x, t0.x, (v0 & 0xffu) != 0, c2, k, tab, nb);
             o0.y = p2_row(e0.y, t0.y, (v0 & 0xff00u) != 0, c2, k, tab, nb);
             o0.z = p2_row(e0.z, t0.z, (v0 & 0xff0000u) != 0, c2, k, tab, nb);
             o0.w = p2_row(e0.w, t0.w, (v0 & 0xff000000u) != 0, c2, k, tab, nb);
-            stg_stream_f4(og + 4 * g, o0);
+            stg_stream_f4(og + 4 * (last - g), o0);
             if (h1) {
                 float4 o1;
                 o1.x = p2_row(e1.x, t1.x, (v1 & 0xffu) != 0, c2, k, tab, nb);
                 o1.y = p2_row(e1.y, t1.y, (v1 & 0xff00u) != 0, c2, k, tab, nb);
                 o1.z = p2_row(e1.z, t1.z, (v1 & 0xff0000u) != 0, c2, k, tab, nb);
                 o1.w = p2_row(e1.w, t1.w, (v1 & 0xff000000u) != 0, c2, k, tab, nb);
-                stg_stream_f4(og + 4 * (g + stride), o1);
+                stg_stream_f4(og + 4 * (last - g - stride), o1);
             }
             e0 = ne0; t0 = nt0; v0 = nv0; e1 = ne1; t1 = nt1; v1 = nv1;
             h0 = n0; h1 = n1; g = gn;
@@ -722,6 +1050,16 @@ ScanBase make_scan_base(const BinnedLayout &L, unsigned char *w8, int64_t n_seg)
 }
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+bool coop_supported() {
+    static int cached = -1;
+    if (cached < 0) {
+        int dev = 0, v = 0;
+        cached = (cudaGetDevice(&dev) == cudaSuccess &&
+                  cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v) ? 1 : 0;
+    }
+    return cached == 1;
+}
 
 int32_t check_common(int64_t n, int64_t n_seg, int nb) {
     B200_REQUIRE(nb >= 32 && nb <= B200SURV_COX_MAX_BINS && (nb & (nb - 1)) == 0,
@@ -826,6 +1164,35 @@ int32_t cox_binned_fwd(const float *log_hz, const float *time, const uint8_t *ev
     unsigned char *w8 = static_cast<unsigned char *>(ws);
     long long *bins = reinterpret_cast<long long *>(w8 + L.off_bins);
     float *bins_max = reinterpret_cast<float *>(w8 + L.off_bins_max);
+    if (n_seg == 1 && seg_off == nullptr && coop_supported()) {
+        // one cooperative launch: pass 1 + reduce + scan + Efron terms + finish
+        int vec_ok = aligned16(log_hz) && aligned16(time) && ((reinterpret_cast<uintptr_t>(event) & 3) == 0);
+        // The TMA-staged pass 1 (pass1_body_tma) is opt-in: measured 78.9 us vs 72.8 us for the register-staged
+        // loop at 16.7M rows (profiles/r1_v10_tma_ab.txt) -- with 31 consumer warps the ring hides the latency
+        // but the CTA loses a warp and pays an mbarrier round trip per 4 rows/thread.
+        static const bool tma_on = getenv("B200SURV_USE_TMA") != nullptr;
+        int use_tma = tma_on && vec_ok && nb <= 4096 && n >= 4 * (int64_t)TMA_TILE;
+        const size_t smem = use_tma ? tma_smem_bytes(nb) : (size_t)nb * 24 + 16;
+        static bool attr_done = false;
+        if (!attr_done) {
+            const size_t mx = tma_smem_bytes(4096) > (size_t)B200SURV_COX_MAX_BINS * 24 + 16
+                                  ? tma_smem_bytes(4096) : (size_t)B200SURV_COX_MAX_BINS * 24 + 16;
+            B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+            B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+            attr_done = true;
+        }
+        unsigned char *partial = w8 + L.off_partial;
+        CtaRec *recs = reinterpret_cast<CtaRec *>(w8 + L.off_recs);
+        FusedArgs fa;
+        fa.bins = bins; fa.bins_max = bins_max; fa.tgf = reinterpret_cast<double *>(w8 + L.off_tgf);
+        fa.ties = ties; fa.reduction = reduction; fa.out_loss = out_loss; fa.state = static_cast<unsigned char *>(state);
+        int nb_i = nb;
+        void *args[] = {(void *)&log_hz, (void *)&time, (void *)&event, (void *)&n, (void *)&nb_i, (void *)&shift,
+                        (void *)&vec_ok, (void *)&partial, (void *)&recs, (void *)&fa, (void *)&use_tma};
+        const void *fn = nb <= 4 * P1_THREADS ? (const void *)cox_binned_fwd_fused<4> : (const void *)cox_binned_fwd_fused<8>;
+        B200_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.nctas), dim3(P1_THREADS), args, smem, st));
+        return B200SURV_OK;
+    }
     rc = launch_pass1_reduce(log_hz, time, event, seg_off, n, n_seg, nb, shift, bins, bins_max, L, w8,
                              /*fuse_scan=*/1, st);
     if (rc) return rc;

@@ -55,8 +55,10 @@ def cindex_counts_sharded(estimate, event, time, tied_tol=1e-8, algo=1, group=No
 class ShardedCoxBinned:
     """Pre-allocated buffers for repeated sharded fwd+bwd over this rank's rows."""
 
-    def __init__(self, n_local: int, device, nbins: int = 4096, ties: str = "efron", reduction: int = L.REDUCE_MEAN_TERMS):
+    def __init__(self, n_local: int, device, nbins: int = 4096, ties: str = "efron", reduction: int = L.REDUCE_MEAN_TERMS,
+                 sync_max: bool = False):
         self.lib = L.load()
+        self.sync_max = sync_max
         L.require_device(device.index)
         self.n, self.nb, self.dev = n_local, nbins, device
         self.ties, self.red = L.TIES[ties], reduction
@@ -85,8 +87,12 @@ class ShardedCoxBinned:
         L.check(rc, "b200surv_cox_binned_partial")
         _, world = _world()
         if world > 1:
+            # one collective per step: the per-bin aggregates (exact int64 SUM).  bins_max stays rank-local: it only
+            # feeds the EXP_RANGE check of the explicit `shift`, which every rank then evaluates on its own rows
+            # (pass sync_max=True to all-reduce it as well, e.g. to pick a common shift for the next call).
             dist.all_reduce(self.bins_sum, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(self.bins_max, op=dist.ReduceOp.MAX, group=group)
+            if self.sync_max:
+                dist.all_reduce(self.bins_max, op=dist.ReduceOp.MAX, group=group)
         rc = self.lib.b200surv_cox_binned_finalize(L.ptr(self.bins_sum), L.ptr(self.bins_max), self.n, 1, self.ties,
                                                    self.red, self.nb, ctypes.c_float(shift), L.ptr(self.loss),
                                                    L.ptr(self.state), self.sb, L.ptr(self.ws), self.wb, st)
