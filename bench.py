@@ -161,7 +161,8 @@ def run_b200(args):
     pin = [x.pin_memory() for x in (lh, ev, t)]
     x, e, tt = lh.to(dev), ev.to(dev), t.to(dev)
     grad = torch.empty(n, dtype=torch.float32, device=dev)
-    op = gdist.ShardedCoxBinned(n, dev, nbins=4096, ties="efron")
+    op = gdist.ShardedCoxBinned(n, dev, nbins=4096, ties="efron", exchange=args.exchange)
+    fused = world == 1 or op.exchange == "peer"   # forward is one cooperative launch
 
     def step():
         op.forward(x, tt, e)
@@ -217,6 +218,7 @@ def run_b200(args):
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": "patients/s", "n_gpus": world,
                               "steps": args.steps, "ms_per_step": ms_step, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+                              "exchange": op.exchange if world > 1 else None, "loss": loss_val,
                               "note": "--skip-extras: partial line, not a bench result"}))
         if world > 1:
             dist.destroy_process_group()
@@ -304,14 +306,17 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "cox_nll_fwd_bwd_efron_16M_heavy_ties", "rows_per_gpu": n, "ties": "efron",
                        "time": "integer days clamp(floor(Exp(1000)),1,4000)", "event_rate": 0.30, "mode": "binned",
-                       "nbins": 4096, "parallelism": f"row-block shards x{world}, NCCL all-reduce of per-bin aggregates",
+                       "nbins": 4096,
+                       "parallelism": "single GPU" if world == 1 else
+                       (f"row-block shards x{world}, per-bin int64 sums exchanged inside the forward kernel over NVLink peer memory"
+                        if op.exchange == "peer" else f"row-block shards x{world}, NCCL all-reduce of per-bin int64 sums"),
                        "l2": "no flush needed: each step streams 151 MB in + 67 MB out, larger than the 126 MB L2"},
             "loss": loss_val,
             "roofline": {"bound": "hbm", "kernel": "cox_binned_bwd (13 B/row: 9 read + 4 written)",
                          "achieved": achieved_bwd, "peak": peak, "unit": "GB/s", "frac": achieved_bwd / peak,
                          "traffic": None, "peak_source": peak_src, "ms": bwd_ms,
                          "fwd": {"kernels": "cox_binned_fwd_fused: pass 1 + reduce + scan + Efron terms + finish (9 B/row)"
-                                 if world == 1 else "cox_binned_pass1, reduce, all-reduce, scan, items_finish (9 B/row)",
+                                 if fused else "cox_binned_pass1, reduce, all-reduce, scan, items_finish (9 B/row)",
                                  "achieved": achieved_fwd, "frac": achieved_fwd / peak, "ms": fwd_ms},
                          "step": {"bytes_per_row": ALGO_BYTES_PER_ROW, "achieved": achieved_step,
                                   "frac": achieved_step / peak, "frac_of_8TBs": achieved_step / 8000.0}},
@@ -319,7 +324,7 @@ def run_b200(args):
                     "ms_per_step": float(e2e_t.item()) * 1e3, "api": "neg_partial_log_likelihood(log_hz, event, time) + backward, mode=auto"},
             # per step at N=1: cox_binned_fwd_fused (cooperative) + cox_binned_bwd; at N>1 the forward is split
             # around the all-reduce: pass1, reduce, scan, items_finish, then bwd
-            "gpu_launches": (2 if world == 1 else 5) * args.steps,
+            "gpu_launches": (2 if fused else 5) * args.steps,
             "clocks": clocks,
             "extra": {"cindex_1m": {"n": cn, "ms": ci_ms, "patients_per_s": cn / (ci_ms * 1e-3),
                                     "ordered_pairs_per_s": sum(counts) / (ci_ms * 1e-3), "counts": counts,
@@ -346,6 +351,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=N_ROWS, help="rows per GPU (default: the BASELINE 16,777,216)")
     ap.add_argument("--skip-extras", action="store_true", help="only the timed fwd+bwd loop (for ncu launch lists)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1: per-bin sums meet inside the kernel over NVLink peer memory, or through an NCCL all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -73,10 +73,11 @@ const char *b200surv_last_error(void);
 
 /* header flags */
 #define B200SURV_COXF_NOT_BINNABLE 1u /* a time was non-integer or outside [0, nbins)            */
-#define B200SURV_COXF_EXP_RANGE 2u    /* shift unsuitable for the 32.32 fixed-point weights
-                                         (max(log_hz) - shift outside [-16, 20], or sum of weights
+#define B200SURV_COXF_EXP_RANGE 2u    /* shift unsuitable for the 36.28 fixed-point weights
+                                         (max(log_hz) - shift outside [-8, 20], or sum of weights
                                          >= 2^30): re-run with shift near max_log_hz (header)    */
 #define B200SURV_COXF_BAD_TIME 4u     /* NaN or negative time                                     */
+#define B200SURV_COXF_PEER_TIMEOUT 8u /* b200surv_cox_binned_fwd_peer: a peer rank never arrived   */
 
 /* One header per segment at the start of the state buffer (device memory, 64 bytes each). */
 typedef struct {
@@ -119,7 +120,7 @@ int32_t b200surv_cox_bwd(const float *grad_out, const void *state, size_t state_
  * per-bin aggregates, the caller all-reduces them (SUM over bins_sum, MAX over bins_max) with
  * NCCL, then every rank finalises identically and runs b200surv_cox_bwd on its own rows.
  *   bins_sum : int64[n_seg][3*nbins + 4]  = S_censored[nbins], S_event[nbins] (sums of
- *              exp(log_hz - shift) in 32.32 fixed point), m[nbins] (event counts), sum of event
+ *              exp(log_hz - shift) in 36.28 fixed point), m[nbins] (event counts), sum of event
  *              log_hz in 2^-24 fixed point, NOT_BINNABLE count, ceil(sum of weights), BAD_TIME count
  *              -- integers, so the SUM all-reduce is exact and independent of the sharding
  *   bins_max : float[n_seg][2] = max log_hz, max time  -- MAX-reducible
@@ -135,6 +136,36 @@ int32_t b200surv_cox_binned_finalize(const int64_t *bins_sum, const float *bins_
                                      float *out_loss, void *state, size_t state_bytes,
                                      void *workspace, size_t workspace_bytes,
                                      b200surv_stream_t stream);
+
+/* The same sharded forward with the exchange FUSED into the kernel over peer memory (NVLink / NVSwitch): no
+ * NCCL call on the data path.  Every rank of the box allocates one peer buffer of
+ * b200surv_cox_peer_buffer_bytes(nbins) bytes, zero-filled once, that all ranks can address (CUDA IPC / VMM
+ * fabric handles / torch symmetric memory); peer_bufs[r] (HOST array of `world` device pointers, 256-byte
+ * aligned) is rank r's buffer as mapped into THIS process.  One cooperative launch per rank: pass 1 ->
+ * per-bin int64 sums into this rank's slot -> flag to every peer, wait for every peer's flag (2 s time-out
+ * -> B200SURV_COXF_PEER_TIMEOUT, loss NaN) -> each CTA pulls its slice of bins from all peers and adds them
+ * -> scan, Efron terms, loss, header and (P,F) table exactly as b200surv_cox_fwd.  Integer sums: every rank
+ * obtains the bit-identical loss for any sharding.  epoch: 1, 2, 3, ... the same sequence on every rank
+ * (slots are double-buffered on its parity); n, log_hz, time, event are the rank-local rows.  Then
+ * b200surv_cox_bwd(mode BINNED) on the local rows. */
+size_t b200surv_cox_peer_buffer_bytes(int32_t nbins);
+/* Diagnostics: with B200SURV_PEER_TRACE set in the environment, b200surv_cox_binned_fwd_peer leaves 11 int64
+ * %globaltimer stamps (ns; kernel start, pass 1, reduce, flag sent, peers seen, pulled, Efron terms, end) at this
+ * byte offset of the workspace. */
+size_t b200surv_cox_peer_trace_offset(int64_t n, int32_t nbins);
+/* Peer-buffer plumbing for callers without their own symmetric allocator: alloc (cudaMalloc on the current
+ * device, zero-filled) returns the pointer and a 64-byte CUDA IPC handle to hand to the other ranks of the
+ * box (any byte transport); open maps a peer's handle into this process (peer access enabled lazily). */
+#define B200SURV_PEER_HANDLE_BYTES 64
+int32_t b200surv_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle);
+int32_t b200surv_peer_open(const unsigned char *handle, void **dev_ptr);
+int32_t b200surv_peer_close(void *dev_ptr);
+int32_t b200surv_peer_free(void *dev_ptr);
+int32_t b200surv_cox_binned_fwd_peer(const float *log_hz, const float *time, const uint8_t *event, int64_t n,
+                                     int32_t ties, int32_t reduction, int32_t nbins, float shift,
+                                     float *out_loss, void *state, size_t state_bytes, void *workspace,
+                                     size_t workspace_bytes, void *const *peer_bufs, int32_t world,
+                                     int32_t rank, uint32_t epoch, b200surv_stream_t stream);
 
 /* ---- Harrell's concordance index: integer pair counts -------------------------------------- */
 /* out_counts: int64[n_seg][6], ADDED to (caller zeroes): over rows i in [row_begin, row_end) of

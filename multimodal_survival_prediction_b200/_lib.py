@@ -15,7 +15,7 @@ REDUCE_MEAN_TERMS, REDUCE_SUM, REDUCE_MEAN_EVENTS = 0, 1, 2
 COX_SMALL, COX_BINNED, COX_SORTED = 1, 2, 3
 COX_SMALL_MAX = 2048
 COX_MAX_BINS = 8192
-COXF_NOT_BINNABLE, COXF_EXP_RANGE, COXF_BAD_TIME = 1, 2, 4
+COXF_NOT_BINNABLE, COXF_EXP_RANGE, COXF_BAD_TIME, COXF_PEER_TIMEOUT = 1, 2, 4, 8
 COX_HEADER_BYTES = 64
 
 
@@ -50,6 +50,15 @@ SIGNATURES = {
     "b200surv_cox_binned_finalize": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32,
                                                c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
                                                c_void_p]),
+    "b200surv_cox_peer_buffer_bytes": (c_size_t, [c_int32]),
+    "b200surv_cox_peer_trace_offset": (c_size_t, [c_int64, c_int32]),
+    "b200surv_peer_alloc": (c_int32, [c_size_t, ctypes.POINTER(c_void_p), c_void_p]),
+    "b200surv_peer_open": (c_int32, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "b200surv_peer_close": (c_int32, [c_void_p]),
+    "b200surv_peer_free": (c_int32, [c_void_p]),
+    "b200surv_cox_binned_fwd_peer": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
+                                               c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p,
+                                               c_int32, c_int32, ctypes.c_uint32, c_void_p]),
     "b200surv_gemm_bf16": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                      c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
     "b200surv_head_saved_bytes": (c_size_t, [c_int64, c_int32]),

@@ -47,4 +47,42 @@ int32_t b200surv_arch_check(int32_t device) {
     return B200SURV_OK;
 }
 
+// ---- peer buffers: device memory of one rank that the other ranks of the box map through CUDA IPC
+int32_t b200surv_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle) {
+    B200_REQUIRE(bytes > 0 && dev_ptr && handle, "bytes, dev_ptr, handle");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200SURV_PEER_HANDLE_BYTES, "IPC handle size");
+    void *p = nullptr;
+    B200_CHECK_CUDA(cudaMalloc(&p, bytes));
+    B200_CHECK_CUDA(cudaMemset(p, 0, bytes));
+    B200_CHECK_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        b200surv::set_error("cudaIpcGetMemHandle -> %s", cudaGetErrorString(e));
+        cudaFree(p);
+        return B200SURV_CUDA_ERROR;
+    }
+    memcpy(handle, &h, sizeof(h));
+    *dev_ptr = p;
+    return B200SURV_OK;
+}
+
+int32_t b200surv_peer_open(const unsigned char *handle, void **dev_ptr) {
+    B200_REQUIRE(handle && dev_ptr, "handle, dev_ptr");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    B200_CHECK_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200SURV_OK;
+}
+
+int32_t b200surv_peer_close(void *dev_ptr) {
+    if (dev_ptr) B200_CHECK_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return B200SURV_OK;
+}
+
+int32_t b200surv_peer_free(void *dev_ptr) {
+    if (dev_ptr) B200_CHECK_CUDA(cudaFree(dev_ptr));
+    return B200SURV_OK;
+}
+
 }  // extern "C"

@@ -13,6 +13,10 @@ int32_t cox_binned_fwd(const float *, const float *, const uint8_t *, const int6
                        int, float, float *, void *, size_t, void *, size_t, cudaStream_t);
 int32_t cox_binned_bwd_launch(const float *, const void *, size_t, const float *, const float *, const uint8_t *,
                               const int64_t *, int64_t, int64_t, int, float *, cudaStream_t);
+size_t cox_binned_peer_buffer_bytes(int nb);
+size_t cox_binned_peer_trace_offset(int64_t n, int nb);
+int32_t cox_binned_fwd_peer(const float *, const float *, const uint8_t *, int64_t, int, int, int, float, float *,
+                            void *, size_t, void *, size_t, void *const *, int, int, unsigned, cudaStream_t);
 // cox_small.cu
 int32_t cox_small_fwd_launch(const float *, const float *, const uint8_t *, const int64_t *, int64_t, int64_t, int,
                              int, float *, void *, size_t, cudaStream_t);
@@ -115,6 +119,20 @@ int32_t b200surv_cox_binned_finalize(const int64_t *bins_sum, const float *bins_
     B200_REQUIRE(n >= 1 && n_seg >= 1, "n, n_seg");
     return cox_binned_finalize(bins_sum, bins_max, n, n_seg, ties, reduction, nbins, shift, out_loss, state,
                                state_bytes, workspace, workspace_bytes, as_stream(stream));
+}
+
+size_t b200surv_cox_peer_buffer_bytes(int32_t nbins) { return cox_binned_peer_buffer_bytes(nbins); }
+size_t b200surv_cox_peer_trace_offset(int64_t n, int32_t nbins) { return cox_binned_peer_trace_offset(n, nbins); }
+
+int32_t b200surv_cox_binned_fwd_peer(const float *log_hz, const float *time, const uint8_t *event, int64_t n,
+                                     int32_t ties, int32_t reduction, int32_t nbins, float shift, float *out_loss,
+                                     void *state, size_t state_bytes, void *workspace, size_t workspace_bytes,
+                                     void *const *peer_bufs, int32_t world, int32_t rank, uint32_t epoch,
+                                     b200surv_stream_t stream) {
+    B200_REQUIRE(log_hz && time && event && out_loss && state && workspace && peer_bufs, "null pointer");
+    B200_REQUIRE(n >= 1, "n must be >= 1");
+    return cox_binned_fwd_peer(log_hz, time, event, n, ties, reduction, nbins, shift, out_loss, state, state_bytes,
+                               workspace, workspace_bytes, peer_bufs, world, rank, epoch, as_stream(stream));
 }
 
 size_t b200surv_cindex_workspace_bytes(int64_t n, int64_t n_seg, int32_t algo) {

@@ -42,6 +42,9 @@ constexpr int MAX_P1_CTAS = RED_NG * RED_MAX_ITERS;
 constexpr int IT_THREADS = 1024;   // items / finish
 constexpr int BIG_M = 8192;        // bins with more events are split over all warps
 constexpr int BIG_CHUNK = 256;
+constexpr int EF_CHUNK = 256;                    // fused forward: granule of the Efron work split
+constexpr double EF_SCALE = 134217728.0;         // 2^27 fixed point of the per-bin Efron sums (|sum| < 2^36)
+constexpr double EF_INV = 1.0 / 134217728.0;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int FIX_BITS = 28;
 constexpr double FIX_INV = 1.0 / 268435456.0;    // 2^-28
@@ -382,7 +385,7 @@ struct ScanBufs {
     double *rm;         // [nb] E / (D m)  (0 where m == 0)
     double *tgf;        // [3][nb] Efron T, G, F per bin
     long long *totals;  // [2] n_events, n_event_times
-    int *big;           // [1 + nb] count, then the bins with more than BIG_M events
+    int *cp;            // [nb + 1] exclusive prefix of the Efron chunk counts in scan order (see efron_chunks)
     unsigned *ticket;   // "last CTA done" counter of K3
 };
 struct ScanBase {
@@ -394,7 +397,7 @@ struct ScanBase {
 __device__ __forceinline__ ScanBufs scan_bufs(const ScanBase &w, int seg, int nb) {
     ScanBufs o;
     o.D = w.D + (size_t)seg * nb; o.rm = w.rm + (size_t)seg * nb; o.tgf = w.tgf + (size_t)seg * 3 * nb;
-    o.totals = w.totals + 2 * (size_t)seg; o.big = w.big + (size_t)seg * (nb + 1); o.ticket = w.tickets_k3 + seg;
+    o.totals = w.totals + 2 * (size_t)seg; o.cp = w.big + (size_t)seg * (nb + 1); o.ticket = w.tickets_k3 + seg;
     return o;
 }
 
@@ -416,22 +419,24 @@ __device__ void scan_segment(const long long *bs, int nb, ScanBufs o, double *sh
         re[k] = in ? __ldcg(bs + nb + b) : 0ll;
         rmv[k] = in ? __ldcg(bs + 2 * nb + b) : 0ll;
     }
-    if (t == 0) { o.big[0] = 0; *o.ticket = 0; }
+    if (t == 0) *o.ticket = 0;
     double sv[MAXPER];
     double loc = 0.0;
-    int locm = 0, net = 0;
+    int locm = 0, net = 0, locc = 0;
 #pragma unroll
     for (int k = 0; k < MAXPER; ++k) {
         sv[k] = ((double)(unsigned long long)rc[k] + (double)(unsigned long long)re[k]) * FIX_INV;
         loc += sv[k];
         locm += (int)rmv[k];
         net += rmv[k] > 0 ? 1 : 0;
+        locc += ((int)rmv[k] + EF_CHUNK - 1) / EF_CHUNK;
     }
     double tot;
-    double run = block_exscan<double>(loc, shd, &tot);  // sum over all later chunks (syncs make big[0]=0 visible)
-    int totm, totn;
+    double run = block_exscan<double>(loc, shd, &tot);  // sum over all later chunks
+    int totm, totn, totc;
     block_exscan<int>(locm, shi, &totm);
     block_exscan<int>(net, shi, &totn);
+    int crun = block_exscan<int>(locc, shi, &totc);
 #pragma unroll
     for (int k = 0; k < MAXPER; ++k) {
         const int b = hi_b - 1 - k;
@@ -440,14 +445,61 @@ __device__ void scan_segment(const long long *bs, int nb, ScanBufs o, double *sh
             const int m = (int)rmv[k];
             o.D[b] = run;
             o.rm[b] = m > 0 ? ((double)(unsigned long long)re[k] * FIX_INV) / (run * (double)m) : 0.0;
-            if (m > BIG_M) {
-                const int slot = atomicAdd(o.big, 1);
-                o.big[1 + slot] = b;
-                o.tgf[b] = 0.0; o.tgf[nb + b] = 0.0; o.tgf[2 * nb + b] = 0.0;  // accumulated with atomics
-            }
+            o.cp[t * per + k] = crun;  // scan order p = nb-1-b
+            crun += (m + EF_CHUNK - 1) / EF_CHUNK;
+            o.tgf[b] = 0.0; o.tgf[nb + b] = 0.0; o.tgf[2 * nb + b] = 0.0;  // Efron accumulators (all-zero bits)
         }
     }
-    if (t == 0) { o.totals[0] = totm; o.totals[1] = totn; }
+    if (t == 0) { o.totals[0] = totm; o.totals[1] = totn; o.cp[nb] = totc; }
+}
+
+// Efron terms of one cohort, shared by the fused forward and the K3 kernel: the (bin, l) pairs of ALL bins, cut
+// into chunks of EF_CHUNK consecutive l of one bin, are dealt out in equal contiguous runs to the W warps taking
+// part -- balanced whatever the tie structure (one bin holding every event, or thousands of moderately tied
+// ones; the work is the number of events).  A warp sums its run bin by bin (fp32, fp64 where x < 0.5) and adds the
+// three sums to per-bin 2^-27 fixed-point integers: exact and order independent, so the loss is bit-reproducible
+// and identical on every code path.  cp[p], p = nb-1-b: exclusive prefix of the chunk counts, cp[nb] = total.
+__device__ __forceinline__ void efron_terms(int l0, int l1, int lane, double rm, float inv_m, float &vt, float &vg,
+                                            float &vf);
+template <typename MFn, typename RmFn>
+__device__ __forceinline__ void efron_chunks(const int *cp, int nb, int gw, int W, int lane, MFn m_of, RmFn rm_of,
+                                             long long *acc) {
+    const int C = cp[nb], q = (C + W - 1) / W;
+    int c = gw * q;
+    const int c1 = min(C, c + q);
+    if (c >= c1) return;
+    int lo = 0, hi = nb;  // cp[lo] <= c < cp[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (cp[mid] <= c) lo = mid; else hi = mid;
+    }
+    int p = lo;
+    while (c < c1) {
+        const int base = cp[p], cend = min(c1, cp[p + 1]);
+        if (cend > c) {
+            const int b = nb - 1 - p, m = m_of(b);
+            const double rm = rm_of(b);
+            const float inv_m = 1.f / (float)m;
+            long long it = 0, ig = 0, iff = 0;
+            // one chunk = one unit of floating-point summation, converted to fixed point before it meets any other:
+            // the per-bin sums do not depend on how the chunks are dealt out (grid size, sharding, code path)
+            for (int l0 = (c - base) * EF_CHUNK; l0 < (cend - base) * EF_CHUNK; l0 += EF_CHUNK) {
+                float vt = 0.f, vg = 0.f, vf = 0.f;
+                efron_terms(l0, min(m, l0 + EF_CHUNK), lane, rm, inv_m, vt, vg, vf);
+                vt = warp_sum(vt); vg = warp_sum(vg); vf = warp_sum(vf);
+                it += __double2ll_rn((double)vt * EF_SCALE);
+                ig += __double2ll_rn((double)vg * EF_SCALE);
+                iff += __double2ll_rn((double)vf * EF_SCALE);
+            }
+            if (lane == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long *>(acc + b), (unsigned long long)it);
+                atomicAdd(reinterpret_cast<unsigned long long *>(acc + nb + b), (unsigned long long)ig);
+                atomicAdd(reinterpret_cast<unsigned long long *>(acc + 2 * nb + b), (unsigned long long)iff);
+            }
+            c = cend;
+        }
+        ++p;
+    }
 }
 
 // ================================================================ K2: reduce partials (+ fused scan)
@@ -578,48 +630,14 @@ cox_binned_items_finish(const long long *__restrict__ bins, const float *__restr
     const bool efron = ties == B200SURV_TIES_EFRON;
 
     if (efron) {
-        const int lane = t & 31;
-        // consecutive bins go to different CTAs: early days carry the most events (balance across SMs)
+        __shared__ int s_cp[B200SURV_COX_MAX_BINS + 1];
+        for (int i = t; i <= nb; i += IT_THREADS) s_cp[i] = o.cp[i];
+        __syncthreads();
+        // consecutive warp ids go to different CTAs (balance across SMs when the runs are short)
         const int gw = (t >> 5) * gridDim.x + blockIdx.x, W = gridDim.x * (IT_THREADS / 32);
-        for (int b = gw; b < nb; b += W) {  // one warp per bin
-            const int m = (int)bs[2 * nb + b];
-            if (m == 0 || m > BIG_M) continue;
-            const double D = o.D[b], rm = o.rm[b];
-            float vt = 0.f, vg = 0.f, vf = 0.f;
-            efron_terms(0, m, lane, rm, 1.f / (float)m, vt, vg, vf);
-            vt = warp_sum(vt); vg = warp_sum(vg); vf = warp_sum(vf);
-            if (lane == 0) {
-                const double invD = 1.0 / D;
-                o.tgf[b] = (double)vt + (double)m * log(D);
-                o.tgf[nb + b] = (double)vg * invD;
-                o.tgf[2 * nb + b] = (double)vf * invD;
-            }
-        }
-        const int nbig = o.big[0];
-        for (int i = 0; i < nbig; ++i) {  // bins with more than BIG_M events: all warps share each of them
-            const int b = o.big[1 + i];
-            const int m = (int)bs[2 * nb + b];
-            const double D = o.D[b], rm = o.rm[b];
-            const float inv_m = 1.f / (float)m;
-            double at = 0.0, ag = 0.0, af = 0.0;
-            bool any = false;
-            for (int l0 = gw * BIG_CHUNK; l0 < m; l0 += W * BIG_CHUNK) {
-                float vt = 0.f, vg = 0.f, vf = 0.f;
-                efron_terms(l0, min(m, l0 + BIG_CHUNK), lane, rm, inv_m, vt, vg, vf);
-                at += (double)vt; ag += (double)vg; af += (double)vf;
-                any = true;
-            }
-            if (any) {
-                at = warp_sum(at); ag = warp_sum(ag); af = warp_sum(af);
-                if (lane == 0) {
-                    const double invD = 1.0 / D;
-                    if (gw == 0) at += (double)m * log(D);
-                    atomicAdd(o.tgf + b, at);
-                    atomicAdd(o.tgf + nb + b, ag * invD);
-                    atomicAdd(o.tgf + 2 * nb + b, af * invD);
-                }
-            }
-        }
+        efron_chunks(
+            s_cp, nb, gw, W, t & 31, [&](int b) { return (int)bs[2 * nb + b]; }, [&](int b) { return o.rm[b]; },
+            reinterpret_cast<long long *>(o.tgf));
     }
     // ---- last CTA of the segment to arrive finishes
     __syncthreads();
@@ -640,26 +658,22 @@ cox_binned_items_finish(const long long *__restrict__ bins, const float *__restr
     for (int k = 0; k < MAXPER; ++k) {  // tgf was written by other CTAs of this launch: read through L2
         const int b = lo_b + k;
         const bool in = (k < per) && (b < nb);
+        const long long *acc = reinterpret_cast<const long long *>(o.tgf);
         mv[k] = in ? (int)bs[2 * nb + b] : 0;
-        tv[k] = (in && efron) ? __ldcg(o.tgf + b) : 0.0;
-        gv[k] = (in && efron) ? __ldcg(o.tgf + nb + b) : 0.0;
-        fv[k] = (in && efron) ? __ldcg(o.tgf + 2 * nb + b) : 0.0;
+        const bool live = mv[k] > 0;
+        const long long at = live ? __ldcg(acc + b) : 0ll, ag = live ? __ldcg(acc + nb + b) : 0ll,
+                        af = live ? __ldcg(acc + 2 * nb + b) : 0ll;
+        tv[k] = gv[k] = fv[k] = 0.0;
+        if (live) {  // the same expressions as the fused forward: bit-identical results on both paths
+            const double D = o.D[b], invD = 1.0 / D, m = (double)mv[k];
+            tv[k] = (double)at * EF_INV + m * log(D);
+            gv[k] = efron ? (double)ag * EF_INV * invD : m * invD;
+            fv[k] = (double)af * EF_INV * invD;
+        }
     }
     double tsum = 0.0, gsum = 0.0;
 #pragma unroll
-    for (int k = 0; k < MAXPER; ++k) {
-        const int b = lo_b + k;
-        if (mv[k] > 0) {
-            if (!efron) {  // Breslow: closed form per bin
-                const double D = o.D[b];
-                tv[k] = (double)mv[k] * log(D);
-                gv[k] = (double)mv[k] / D;
-            }
-        } else {
-            tv[k] = 0.0; gv[k] = 0.0; fv[k] = 0.0;  // empty bins never had their slots written
-        }
-        tsum += tv[k]; gsum += gv[k];
-    }
+    for (int k = 0; k < MAXPER; ++k) { tsum += tv[k]; gsum += gv[k]; }
     double tot;
     double run = block_exscan<double>(gsum, shd, &tot);
 #pragma unroll
@@ -706,27 +720,91 @@ struct FusedArgs {
     unsigned char *state;
 };
 
-template <int MAXPER>
+// ---- multi-GPU exchange through peer memory (NVLink / NVSwitch), fused into the cooperative forward.
+// Every rank owns one "peer buffer" that all ranks of the box have mapped (symmetric allocation):
+//   [ flags: PEER_MAX_WORLD x 128 B, slot r is written by rank r ]
+//   [ slot 0 | slot 1 ]   each: int64 bins[3 nb + 4], float max[2]     (slot = epoch & 1)
+// Step k: a rank writes its own per-bin sums into its slot k&1, publishes flag[rank] = k in every peer's
+// buffer (release, system scope), waits until its own flags show k for every peer, then sums the peers'
+// slots bin slice by bin slice (each CTA pulls ~nb/148 bins from every peer: (world-1) * 24 nb bytes per GPU
+// over NVLink in total).  Integer sums, so every rank obtains bit-identical totals.  Double buffering is
+// enough: a rank rewrites slot k&1 in step k+2, after it passed the barrier of step k+1, which every peer
+// only signals once its step-k kernel (the one reading this slot) has finished.
+constexpr int PEER_MAX_WORLD = 16;
+constexpr int PEER_FLAG_STRIDE = 32;  // unsigned words (128 B)
+constexpr size_t PEER_FLAGS_BYTES = (size_t)PEER_MAX_WORLD * PEER_FLAG_STRIDE * sizeof(unsigned);
+constexpr long long PEER_SPIN_LIMIT_NS = 2000000000ll;  // 2 s: a missing peer must not hang the GPU
+
+struct PeerArgs {
+    int world, rank;
+    unsigned epoch;
+    int *status;  // local: set to 1 when the wait timed out
+    long long *trace;  // optional (may be null): globaltimer stamps of the phases, CTA 0
+    unsigned char *buf[PEER_MAX_WORLD];
+};
+
+__host__ __device__ inline size_t peer_slot_bytes(int nb) {
+    return ((3 * (size_t)nb + 4) * sizeof(long long) + 2 * sizeof(float) + 255) / 256 * 256;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_relaxed_sys_s64(const long long *p) {
+    long long v;
+    asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float *p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ long long global_timer_ns() {
+    long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+
+template <int MAXPER, bool PEER>
 __global__ void __launch_bounds__(P1_THREADS, 1)
 cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__ time,
                      const uint8_t *__restrict__ event, int64_t n, int nb, float shift, int vec_ok,
-                     unsigned char *__restrict__ partial, CtaRec *__restrict__ recs, FusedArgs fa, int use_tma) {
+                     unsigned char *__restrict__ partial, CtaRec *__restrict__ recs, FusedArgs fa, int use_tma,
+                     PeerArgs pa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double shd[33];
     __shared__ int shi[33];
     cg::grid_group grid = cg::this_grid();
     const int cta = blockIdx.x, nctas = gridDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (PEER && cta == 0 && t == 0) *pa.status = 0;  // set again (after a grid barrier) if a peer never arrives
+#define PEER_TRACE(i)                                                                          \
+    do {                                                                                       \
+        if (PEER && pa.trace != nullptr && cta == 0 && t == 0) pa.trace[i] = global_timer_ns(); \
+    } while (0)
+    PEER_TRACE(0);
     if (use_tma)
         pass1_body_tma(log_hz, time, event, n, nb, shift, partial, recs, cta, nctas, smem_raw);
     else
         pass1_body(log_hz, time, event, nullptr, n, nb, shift, vec_ok, partial, recs, 0, cta, nctas,
                    reinterpret_cast<unsigned *>(smem_raw));
+    PEER_TRACE(1);
     grid.sync();
+    PEER_TRACE(2);
 
     // ---- phase 2: exact reduction of the partials, bins [b0, b1) of this CTA, one warp per bin
     long long *bs = fa.bins;
+    const size_t slot_off = PEER ? PEER_FLAGS_BYTES + (size_t)(pa.epoch & 1u) * peer_slot_bytes(nb) : 0;
+    const int nbpc = (nb + nctas - 1) / nctas;
     {
-        const int nbpc = (nb + nctas - 1) / nctas;
+        // with peers the rank-local sums go to this rank's slot of the peer buffer; fa.bins receives the totals
+        long long *bs = PEER ? reinterpret_cast<long long *>(pa.buf[pa.rank] + slot_off) : fa.bins;
+        float *bmax = PEER ? reinterpret_cast<float *>(bs + 3 * (size_t)nb + 4) : fa.bins_max;
         const int b0 = cta * nbpc, b1 = min(nb, b0 + nbpc);
         for (int b = b0 + warp; b < b1; b += P1_THREADS / 32) {
             unsigned long long vc[RED_MAX_ITERS], ve[RED_MAX_ITERS];
@@ -765,24 +843,87 @@ cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__
                 bs[3 * (size_t)nb + 1] = (fl & B200SURV_COXF_NOT_BINNABLE) ? 1 : 0;
                 bs[3 * (size_t)nb + 2] = (long long)fmin(ceil(sw), 9.0e18);
                 bs[3 * (size_t)nb + 3] = (fl & B200SURV_COXF_BAD_TIME) ? 1 : 0;
-                fa.bins_max[0] = mx;
-                fa.bins_max[1] = -1.f;
+                bmax[0] = mx;
+                bmax[1] = -1.f;
             }
         }
     }
+    PEER_TRACE(3);
     grid.sync();
+    PEER_TRACE(4);
+
+    if constexpr (PEER) {
+        // ---- phase 2x: publish, wait for every peer, pull and add their sums for this CTA's bin slice
+        __shared__ int s_timeout;
+        if (t == 0) s_timeout = 0;
+        if (cta == 0 && t < pa.world) {
+            __threadfence_system();  // the slot written by all CTAs (ordered by the grid barrier) before the flag
+            st_release_sys_u32(reinterpret_cast<unsigned *>(pa.buf[t]) + pa.rank * PEER_FLAG_STRIDE, pa.epoch);
+        }
+        __syncthreads();
+        PEER_TRACE(5);
+        if (t < pa.world) {
+            const unsigned *f = reinterpret_cast<const unsigned *>(pa.buf[pa.rank]) + t * PEER_FLAG_STRIDE;
+            const long long t0 = global_timer_ns();
+            while ((int)(ld_acquire_sys_u32(f) - pa.epoch) < 0) {
+                if (global_timer_ns() - t0 > PEER_SPIN_LIMIT_NS) { s_timeout = 1; break; }
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        PEER_TRACE(6);
+        if (s_timeout) {  // a peer never arrived: flag it and leave an empty cohort behind (no stale sums)
+            if (t == 0) atomicExch(pa.status, 1);
+            const int b0 = cta * nbpc, b1 = min(nb, b0 + nbpc);
+            for (int b = b0 + t; b < b1; b += P1_THREADS) { bs[b] = 0; bs[nb + b] = 0; bs[2 * (size_t)nb + b] = 0; }
+            if (cta == nctas - 1 && t < 4) bs[3 * (size_t)nb + t] = 0;
+            if (cta == nctas - 1 && t == 4) { fa.bins_max[0] = 0.f; fa.bins_max[1] = -1.f; }
+        } else {
+            const int b0 = cta * nbpc, b1 = min(nb, b0 + nbpc);
+            const int cnt = max(b1 - b0, 0);
+            for (int i = t; i < 3 * cnt; i += P1_THREADS) {
+                const size_t idx = (size_t)(i / cnt) * nb + b0 + (i % cnt);
+                long long v[PEER_MAX_WORLD];
+#pragma unroll
+                for (int p = 0; p < PEER_MAX_WORLD; ++p)  // all peers' loads in flight together
+                    v[p] = p < pa.world ? ld_relaxed_sys_s64(reinterpret_cast<const long long *>(pa.buf[p] + slot_off) + idx) : 0ll;
+                long long s = 0;
+#pragma unroll
+                for (int p = 0; p < PEER_MAX_WORLD; ++p) s += v[p];
+                bs[idx] = s;
+            }
+            if (cta == nctas - 1 && t >= P1_THREADS - 5) {  // the four scalar words and the maximum
+                const int k = t - (P1_THREADS - 5);
+                if (k < 4) {
+                    long long s = 0;
+                    for (int p = 0; p < pa.world; ++p)
+                        s += ld_relaxed_sys_s64(reinterpret_cast<const long long *>(pa.buf[p] + slot_off) + 3 * (size_t)nb + k);
+                    bs[3 * (size_t)nb + k] = s;
+                } else {
+                    float mx = -INFINITY;
+                    for (int p = 0; p < pa.world; ++p)
+                        mx = fmaxf(mx, ld_relaxed_sys_f32(reinterpret_cast<const float *>(
+                                           reinterpret_cast<const long long *>(pa.buf[p] + slot_off) + 3 * (size_t)nb + 4)));
+                    fa.bins_max[0] = mx;
+                    fa.bins_max[1] = -1.f;
+                }
+            }
+        }
+        grid.sync();
+        PEER_TRACE(7);
+    }
 
     // ---- phase 3: redundant suffix scan into shared memory (reuses the histogram storage: 20 B/bin)
     double *sD = reinterpret_cast<double *>(smem_raw);
     double *s_rm = sD + nb;
     int *s_m = reinterpret_cast<int *>(s_rm + nb);
-    int *s_big = s_m + nb;  // list of the bins with more than BIG_M events (the fused launch allocates 24 B/bin)
-    __shared__ int s_nbig;
+    // s_cp[p], p = nb-1-b (scan order): exclusive prefix of the Efron chunk counts ceil(m/EF_CHUNK); [nb] = total
+    // (the fused launch allocates 24 B/bin + 16)
+    int *s_cp = s_m + nb;
+    const bool efron = fa.ties == B200SURV_TIES_EFRON;
     const int per = nb / P1_THREADS > 0 ? nb / P1_THREADS : 1;
     const int hi_b = nb - t * per;
     int n_events, n_times;
-    if (t == 0) s_nbig = 0;
-    __syncthreads();
     {
         long long rc[MAXPER], re[MAXPER], rmv[MAXPER];
 #pragma unroll
@@ -795,18 +936,21 @@ cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__
         }
         double sv[MAXPER];
         double loc = 0.0;
-        int locm = 0, net = 0;
+        int locm = 0, net = 0, locc = 0;
 #pragma unroll
         for (int k = 0; k < MAXPER; ++k) {
             sv[k] = ((double)(unsigned long long)rc[k] + (double)(unsigned long long)re[k]) * FIX_INV;
             loc += sv[k];
             locm += (int)rmv[k];
             net += rmv[k] > 0 ? 1 : 0;
+            locc += ((int)rmv[k] + EF_CHUNK - 1) / EF_CHUNK;
         }
         double tot;
         double run = block_exscan<double>(loc, shd, &tot);
         block_exscan<int>(locm, shi, &n_events);
         block_exscan<int>(net, shi, &n_times);
+        int n_chunks;
+        int crun = block_exscan<int>(locc, shi, &n_chunks);
 #pragma unroll
         for (int k = 0; k < MAXPER; ++k) {
             const int b = hi_b - 1 - k;
@@ -816,60 +960,21 @@ cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__
                 sD[b] = run;
                 s_rm[b] = m > 0 ? ((double)(unsigned long long)re[k] * FIX_INV) / (run * (double)m) : 0.0;
                 s_m[b] = m;
-                if (m > BIG_M) s_big[atomicAdd(&s_nbig, 1)] = b;
+                s_cp[t * per + k] = crun;
+                crun += (m + EF_CHUNK - 1) / EF_CHUNK;
             }
         }
+        if (t == 0) s_cp[nb] = n_chunks;
     }
     __syncthreads();
-    const bool efron = fa.ties == B200SURV_TIES_EFRON;
-    {
-        // per-bin terms: warp gw owns bins gw, gw + W, ... (consecutive bins on different SMs)
-        const int gw = warp * nctas + cta, W = nctas * (P1_THREADS / 32);
-        for (int b = gw; b < nb; b += W) {
-            const int m = s_m[b];
-            if (m == 0 || (efron && m > BIG_M)) continue;
-            const double D = sD[b];
-            float vt = 0.f, vg = 0.f, vf = 0.f;
-            if (efron) {
-                efron_terms(0, m, lane, s_rm[b], 1.f / (float)m, vt, vg, vf);
-                vt = warp_sum(vt); vg = warp_sum(vg); vf = warp_sum(vf);
-            }
-            if (lane == 0) {
-                const double invD = 1.0 / D;
-                fa.tgf[b] = (double)vt + (double)m * log(D);
-                fa.tgf[nb + b] = efron ? (double)vg * invD : (double)m * invD;
-                fa.tgf[2 * nb + b] = (double)vf * invD;
-            }
-        }
-        if (efron) {
-            const int nbig = s_nbig;
-            for (int i = 0; i < nbig; ++i) {  // bins with more than BIG_M events: all warps of the grid share each
-                const int b = s_big[i];
-                const int m = s_m[b];
-                const double D = sD[b], rm = s_rm[b];
-                const float inv_m = 1.f / (float)m;
-                double at = 0.0, ag = 0.0, af = 0.0;
-                bool any = false;
-                for (int l0 = gw * BIG_CHUNK; l0 < m; l0 += W * BIG_CHUNK) {
-                    float vt = 0.f, vg = 0.f, vf = 0.f;
-                    efron_terms(l0, min(m, l0 + BIG_CHUNK), lane, rm, inv_m, vt, vg, vf);
-                    at += (double)vt; ag += (double)vg; af += (double)vf;
-                    any = true;
-                }
-                if (any) {
-                    at = warp_sum(at); ag = warp_sum(ag); af = warp_sum(af);
-                    if (lane == 0) {
-                        const double invD = 1.0 / D;
-                        if (gw == 0) at += (double)m * log(D);
-                        atomicAdd(fa.tgf + b, at);
-                        atomicAdd(fa.tgf + nb + b, ag * invD);
-                        atomicAdd(fa.tgf + 2 * nb + b, af * invD);
-                    }
-                }
-            }
-        }
+    if (efron) {
+        efron_chunks(
+            s_cp, nb, warp * nctas + cta, nctas * (P1_THREADS / 32), lane, [&](int b) { return s_m[b]; },
+            [&](int b) { return s_rm[b]; }, reinterpret_cast<long long *>(fa.tgf));
     }
+    PEER_TRACE(8);
     grid.sync();
+    PEER_TRACE(9);
     if (cta != 0) return;
 
     // ---- phase 4 (CTA 0): P = prefix(G), loss, header, (P,F) table
@@ -881,9 +986,16 @@ cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__
     for (int k = 0; k < MAXPER; ++k) {
         const int b = lo_b + k;
         const bool in = (k < per) && (b < nb) && s_m[b] > 0;
-        tv[k] = in ? __ldcg(fa.tgf + b) : 0.0;
-        gv[k] = in ? __ldcg(fa.tgf + nb + b) : 0.0;
-        fv[k] = in ? __ldcg(fa.tgf + 2 * nb + b) : 0.0;
+        const long long *acc = reinterpret_cast<const long long *>(fa.tgf);
+        const long long at = in ? __ldcg(acc + b) : 0ll, ag = in ? __ldcg(acc + nb + b) : 0ll,
+                        af = in ? __ldcg(acc + 2 * nb + b) : 0ll;
+        tv[k] = gv[k] = fv[k] = 0.0;
+        if (in) {
+            const double D = sD[b], invD = 1.0 / D, m = (double)s_m[b];
+            tv[k] = (double)at * EF_INV + m * log(D);
+            gv[k] = efron ? (double)ag * EF_INV * invD : m * invD;
+            fv[k] = (double)af * EF_INV * invD;
+        }
     }
     double tsum = 0.0, gsum = 0.0;
 #pragma unroll
@@ -908,6 +1020,7 @@ cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__
         const float mx = __ldcg(fa.bins_max);
         const double sumw = (double)__ldcg(bs + 3 * (size_t)nb + 2);
         if (!(mx - shift <= SHIFT_HI) || !(mx - shift >= SHIFT_LO) || sumw >= SUMW_LIMIT) flags |= B200SURV_COXF_EXP_RANGE;
+        if (PEER && __ldcg(pa.status) != 0) flags |= B200SURV_COXF_PEER_TIMEOUT;
         float loss = 0.f, scale = 0.f;
         if (n_events > 0) { loss = (float)(-pll / norm); scale = (float)(-1.0 / norm); }
         if (flags) { loss = __int_as_float(0x7fc00000); scale = loss; }
@@ -916,7 +1029,9 @@ cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__
         hdr->nbins = nb; hdr->n_events = n_events; hdr->n_event_times = n_times; hdr->pll = pll;
         hdr->reserved = 0;
         fa.out_loss[0] = loss;
+        PEER_TRACE(10);
     }
+#undef PEER_TRACE
 }
 
 // ================================================================ K4: pass 2 (backward)
@@ -1118,6 +1233,10 @@ int32_t launch_items_finish(const long long *bins, const float *bins_max, int64_
     return B200SURV_OK;
 }
 
+int32_t launch_fused(const float *log_hz, const float *time, const uint8_t *event, int64_t n, int ties, int reduction,
+                     int nb, float shift, float *out_loss, void *state, const BinnedLayout &L, unsigned char *w8,
+                     const PeerArgs *peer, cudaStream_t st);
+
 }  // namespace
 
 // ================================================================ internal entry points
@@ -1164,8 +1283,54 @@ int32_t cox_binned_fwd(const float *log_hz, const float *time, const uint8_t *ev
     unsigned char *w8 = static_cast<unsigned char *>(ws);
     long long *bins = reinterpret_cast<long long *>(w8 + L.off_bins);
     float *bins_max = reinterpret_cast<float *>(w8 + L.off_bins_max);
-    if (n_seg == 1 && seg_off == nullptr && coop_supported()) {
-        // one cooperative launch: pass 1 + reduce + scan + Efron terms + finish
+    if (n_seg == 1 && seg_off == nullptr && coop_supported())
+        return launch_fused(log_hz, time, event, n, ties, reduction, nb, shift, out_loss, state, L, w8, nullptr, st);
+    rc = launch_pass1_reduce(log_hz, time, event, seg_off, n, n_seg, nb, shift, bins, bins_max, L, w8,
+                             /*fuse_scan=*/1, st);
+    if (rc) return rc;
+    return launch_items_finish(bins, bins_max, n_seg, ties, reduction, nb, shift, out_loss, state, L, w8,
+                               /*run_scan=*/0, st);
+}
+
+size_t cox_binned_peer_buffer_bytes(int nb) { return PEER_FLAGS_BYTES + 2 * peer_slot_bytes(nb); }
+size_t cox_binned_peer_trace_offset(int64_t n, int nb) { return binned_layout(n, 1, nb).off_D; }
+
+int32_t cox_binned_fwd_peer(const float *log_hz, const float *time, const uint8_t *event, int64_t n, int ties,
+                            int reduction, int nb, float shift, float *out_loss, void *state, size_t state_bytes,
+                            void *ws, size_t ws_bytes, void *const *peer_bufs, int world, int rank, unsigned epoch,
+                            cudaStream_t st) {
+    int32_t rc = check_common(n, 1, nb);
+    if (rc) return rc;
+    B200_REQUIRE(ties == B200SURV_TIES_EFRON || ties == B200SURV_TIES_BRESLOW, "ties");
+    B200_REQUIRE(reduction >= 0 && reduction <= 2, "reduction");
+    B200_REQUIRE(world >= 1 && world <= PEER_MAX_WORLD && rank >= 0 && rank < world, "world in [1,16], rank in [0,world)");
+    B200_REQUIRE(peer_bufs != nullptr && epoch != 0, "peer_bufs must hold `world` pointers and epoch starts at 1");
+    if (!coop_supported()) { set_error("cox binned peer exchange needs cooperative launch"); return B200SURV_UNSUPPORTED; }
+    const BinnedLayout L = binned_layout(n, 1, nb);
+    if (ws_bytes < L.total) { set_error("cox binned: workspace %zu < %zu", ws_bytes, L.total); return B200SURV_WORKSPACE_TOO_SMALL; }
+    if (state_bytes < cox_binned_state_bytes(1, nb)) { set_error("cox binned: state buffer too small"); return B200SURV_WORKSPACE_TOO_SMALL; }
+    unsigned char *w8 = static_cast<unsigned char *>(ws);
+    PeerArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.world = world; pa.rank = rank; pa.epoch = epoch;
+    pa.status = reinterpret_cast<int *>(w8 + L.off_totals);  // unused by the fused path otherwise
+    static const bool trace_on = getenv("B200SURV_PEER_TRACE") != nullptr;
+    pa.trace = trace_on ? reinterpret_cast<long long *>(w8 + L.off_D) : nullptr;  // 11 stamps, see cox_binned_peer_trace_offset
+    for (int p = 0; p < world; ++p) {
+        B200_REQUIRE(peer_bufs[p] != nullptr && (reinterpret_cast<uintptr_t>(peer_bufs[p]) & 255) == 0, "peer buffer alignment (256)");
+        pa.buf[p] = static_cast<unsigned char *>(peer_bufs[p]);
+    }
+    return launch_fused(log_hz, time, event, n, ties, reduction, nb, shift, out_loss, state, L, w8, &pa, st);
+}
+
+namespace {
+int32_t launch_fused(const float *log_hz, const float *time, const uint8_t *event, int64_t n, int ties, int reduction,
+                     int nb, float shift, float *out_loss, void *state, const BinnedLayout &L, unsigned char *w8,
+                     const PeerArgs *peer, cudaStream_t st) {
+    long long *bins = reinterpret_cast<long long *>(w8 + L.off_bins);
+    float *bins_max = reinterpret_cast<float *>(w8 + L.off_bins_max);
+    {
+        // one cooperative launch: pass 1 + reduce (+ peer exchange) + scan + Efron terms + finish
         int vec_ok = aligned16(log_hz) && aligned16(time) && ((reinterpret_cast<uintptr_t>(event) & 3) == 0);
         // The TMA-staged pass 1 (pass1_body_tma) is opt-in: measured 78.9 us vs 72.8 us for the register-staged
         // loop at 16.7M rows (profiles/r1_v10_tma_ab.txt) -- with 31 consumer warps the ring hides the latency
@@ -1177,8 +1342,10 @@ int32_t cox_binned_fwd(const float *log_hz, const float *time, const uint8_t *ev
         if (!attr_done) {
             const size_t mx = tma_smem_bytes(4096) > (size_t)B200SURV_COX_MAX_BINS * 24 + 16
                                   ? tma_smem_bytes(4096) : (size_t)B200SURV_COX_MAX_BINS * 24 + 16;
-            B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-            B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+            B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+            B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+            B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+            B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
             attr_done = true;
         }
         unsigned char *partial = w8 + L.off_partial;
@@ -1187,18 +1354,18 @@ int32_t cox_binned_fwd(const float *log_hz, const float *time, const uint8_t *ev
         fa.bins = bins; fa.bins_max = bins_max; fa.tgf = reinterpret_cast<double *>(w8 + L.off_tgf);
         fa.ties = ties; fa.reduction = reduction; fa.out_loss = out_loss; fa.state = static_cast<unsigned char *>(state);
         int nb_i = nb;
+        PeerArgs pa;
+        if (peer) pa = *peer; else memset(&pa, 0, sizeof(pa));
         void *args[] = {(void *)&log_hz, (void *)&time, (void *)&event, (void *)&n, (void *)&nb_i, (void *)&shift,
-                        (void *)&vec_ok, (void *)&partial, (void *)&recs, (void *)&fa, (void *)&use_tma};
-        const void *fn = nb <= 4 * P1_THREADS ? (const void *)cox_binned_fwd_fused<4> : (const void *)cox_binned_fwd_fused<8>;
+                        (void *)&vec_ok, (void *)&partial, (void *)&recs, (void *)&fa, (void *)&use_tma, (void *)&pa};
+        const bool small = nb <= 4 * P1_THREADS;
+        const void *fn = peer ? (small ? (const void *)cox_binned_fwd_fused<4, true> : (const void *)cox_binned_fwd_fused<8, true>)
+                              : (small ? (const void *)cox_binned_fwd_fused<4, false> : (const void *)cox_binned_fwd_fused<8, false>);
         B200_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.nctas), dim3(P1_THREADS), args, smem, st));
         return B200SURV_OK;
     }
-    rc = launch_pass1_reduce(log_hz, time, event, seg_off, n, n_seg, nb, shift, bins, bins_max, L, w8,
-                             /*fuse_scan=*/1, st);
-    if (rc) return rc;
-    return launch_items_finish(bins, bins_max, n_seg, ties, reduction, nb, shift, out_loss, state, L, w8,
-                               /*run_scan=*/0, st);
 }
+}  // namespace
 
 int32_t cox_binned_bwd_launch(const float *grad_out, const void *state, size_t state_bytes, const float *log_hz,
                               const float *time, const uint8_t *event, const int64_t *seg_off, int64_t n,

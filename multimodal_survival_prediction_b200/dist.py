@@ -51,14 +51,76 @@ def cindex_counts_sharded(estimate, event, time, tied_tol=1e-8, algo=1, group=No
     return counts
 
 
+# ------------------------------------------------------------------ peer buffers (CUDA IPC over NVLink)
+class PeerBuffers:
+    """One zero-filled device buffer per rank, mapped into every rank of the box (b200surv_peer_alloc/open).
+    The 64-byte IPC handles travel through the process group's object all-gather (host side, once)."""
+
+    def __init__(self, nbytes: int, group=None):
+        self.lib = L.load()
+        self.rank, self.world = _world()
+        self.error = None            # every rank runs every collective below, whatever fails locally
+        own = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        rc = self.lib.b200surv_peer_alloc(nbytes, ctypes.byref(own), handle)
+        if rc != L.OK:
+            self.error = "b200surv_peer_alloc: " + (self.lib.b200surv_last_error() or b"").decode()
+        self.own = own.value if rc == L.OK else None
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle) if rc == L.OK else b"", group=group)
+        self.ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.own)
+                continue
+            p = ctypes.c_void_p()
+            if len(h) != 64:
+                self.error = self.error or f"rank {r} exported no handle"
+            elif self.lib.b200surv_peer_open((ctypes.c_ubyte * 64).from_buffer_copy(h), ctypes.byref(p)) != L.OK:
+                self.error = self.error or "b200surv_peer_open: " + (self.lib.b200surv_last_error() or b"").decode()
+            self.ptrs.append(p.value)
+        self.array = (ctypes.c_void_p * self.world)(*[x or 0 for x in self.ptrs])
+        oks = [None] * self.world     # doubles as the barrier: every buffer is mapped and zero-filled before first use
+        dist.all_gather_object(oks, self.error is None, group=group)
+        if not all(oks) and self.error is None:
+            self.error = "a peer rank could not map the buffers"
+
+    def close(self):
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank and p:
+                self.lib.b200surv_peer_close(ctypes.c_void_p(p))
+        if self.own:
+            self.lib.b200surv_peer_free(ctypes.c_void_p(self.own))
+        self.ptrs, self.own = [], None
+
+
 # ------------------------------------------------------------------ Cox (BINNED)
 class ShardedCoxBinned:
-    """Pre-allocated buffers for repeated sharded fwd+bwd over this rank's rows."""
+    """Pre-allocated buffers for repeated sharded fwd+bwd over this rank's rows.
+
+    exchange: how the per-bin sums meet across ranks
+      "peer" -- fused into the forward kernel over peer memory (b200surv_cox_binned_fwd_peer): ONE launch, no
+                collective call; needs all ranks on one box (CUDA IPC);
+      "nccl" -- partial -> one int64 SUM all-reduce (torch.distributed) -> finalize;
+      "auto" -- "peer" when the peer buffers can be set up on every rank, else "nccl".
+    Both give the bit-identical loss (integer sums)."""
 
     def __init__(self, n_local: int, device, nbins: int = 4096, ties: str = "efron", reduction: int = L.REDUCE_MEAN_TERMS,
-                 sync_max: bool = False):
+                 sync_max: bool = False, exchange: str = "auto", group=None):
         self.lib = L.load()
         self.sync_max = sync_max
+        self.peers, self.epoch, self.exchange = None, 0, "nccl"
+        _, world = _world()
+        if world > 1 and exchange in ("auto", "peer") and not sync_max:
+            self.peers = PeerBuffers(self.lib.b200surv_cox_peer_buffer_bytes(nbins), group)
+            if self.peers.error is None:       # the same verdict on every rank (PeerBuffers gathers it)
+                self.exchange = "peer"
+            else:
+                err = self.peers.error
+                self.peers.close()
+                self.peers = None
+                if exchange == "peer":
+                    raise L.B200SurvError("peer exchange unavailable: " + err)
         L.require_device(device.index)
         self.n, self.nb, self.dev = n_local, nbins, device
         self.ties, self.red = L.TIES[ties], reduction
@@ -80,6 +142,15 @@ class ShardedCoxBinned:
                                            self.red, L.COX_BINNED, self.nb, ctypes.c_float(shift), L.ptr(self.loss),
                                            L.ptr(self.state), self.sb, L.ptr(self.ws), self.wb, st)
             L.check(rc, "b200surv_cox_fwd")
+            return self.loss
+        if self.exchange == "peer":   # the exchange happens inside the kernel, over NVLink peer memory
+            self.epoch += 1
+            rc = self.lib.b200surv_cox_binned_fwd_peer(L.ptr(log_hz), L.ptr(time), L.ptr(event), self.n, self.ties,
+                                                       self.red, self.nb, ctypes.c_float(shift), L.ptr(self.loss),
+                                                       L.ptr(self.state), self.sb, L.ptr(self.ws), self.wb,
+                                                       self.peers.array, self.peers.world, self.peers.rank,
+                                                       self.epoch & 0xFFFFFFFF or 1, st)
+            L.check(rc, "b200surv_cox_binned_fwd_peer")
             return self.loss
         rc = self.lib.b200surv_cox_binned_partial(L.ptr(log_hz), L.ptr(time), L.ptr(event), None, self.n, 1, self.nb,
                                                   ctypes.c_float(shift), L.ptr(self.bins_sum), L.ptr(self.bins_max),

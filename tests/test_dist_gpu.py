@@ -1,0 +1,91 @@
+"""Two-GPU parity of the row-sharded Cox forward/backward: both exchanges -- the one fused into the
+forward kernel over NVLink peer memory and the NCCL all-reduce -- must reproduce the single-GPU loss BIT FOR BIT
+(per-bin sums are integers) and the single-GPU gradient on every rank's rows.  Skipped on a one-GPU box."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, out_q):
+    import ctypes
+
+    import torch.distributed as dist
+    from multimodal_survival_prediction_b200 import _lib as L
+    from multimodal_survival_prediction_b200 import dist as bd
+    from multimodal_survival_prediction_b200 import synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    res = {}
+    try:
+        a, b = bd.shard_bounds(n, rank, world)
+        for exchange in ("peer", "nccl"):
+            op = bd.ShardedCoxBinned(b - a, dev, nbins=4096, ties="efron", exchange=exchange)
+            assert op.exchange == exchange
+            for it in range(4):                    # several epochs: exercises the double-buffered slots
+                lh, ev, t = synth.cohort(n, 100 + it)
+                x, e, tt = lh[a:b].to(dev), ev[a:b].to(dev), t[a:b].to(dev)
+                grad = torch.empty(b - a, dtype=torch.float32, device=dev)
+                loss = op.forward(x, tt, e)
+                op.backward(x, tt, e, grad)
+                # single-GPU result for the whole cohort on this rank's device, same kernels
+                xf, ef, tf = lh.to(dev), ev.to(dev), t.to(dev)
+                lib = L.load()
+                sb = lib.b200surv_cox_state_bytes(n, 1, L.COX_BINNED, 4096)
+                wb = lib.b200surv_cox_workspace_bytes(n, 1, L.COX_BINNED, 4096)
+                state = torch.empty(sb, dtype=torch.uint8, device=dev)
+                ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+                l1 = torch.empty(1, dtype=torch.float32, device=dev)
+                L.check(lib.b200surv_cox_fwd(L.ptr(xf), L.ptr(tf), L.ptr(ef), None, n, 1, 2, 0, L.COX_BINNED, 4096,
+                                             ctypes.c_float(0.0), L.ptr(l1), L.ptr(state), sb, L.ptr(ws), wb,
+                                             L.stream_ptr(dev)), "fwd")
+                gf = torch.empty(n, dtype=torch.float32, device=dev)
+                one = torch.ones(1, dtype=torch.float32, device=dev)
+                L.check(lib.b200surv_cox_bwd(L.ptr(one), L.ptr(state), sb, L.ptr(xf), L.ptr(tf), L.ptr(ef), None, n, 1,
+                                             L.COX_BINNED, 4096, L.ptr(gf), L.stream_ptr(dev)), "bwd")
+                torch.cuda.synchronize()
+                res[(exchange, it)] = (loss.item(), l1.item(), bool(torch.equal(grad, gf[a:b])))
+            if op.peers is not None:
+                dist.barrier()
+                op.peers.close()
+        out_q.put((rank, res, None))
+    except Exception as ex:  # noqa: BLE001 -- reported to the parent
+        out_q.put((rank, res, repr(ex)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_cox_two_gpus_bit_identical():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    n, world = (1 << 20) + 37, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, res, err in got:
+        assert err is None, f"rank {rank}: {err}"
+        assert len(res) == 8
+        for key, (loss, loss_single, grad_equal) in res.items():
+            assert loss == loss_single, (rank, key, loss, loss_single)   # bit-identical fp32 loss
+            assert grad_equal, (rank, key)
