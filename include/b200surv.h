@@ -183,6 +183,15 @@ int32_t b200surv_cindex_counts(const float *estimate, const float *time, const u
                                int64_t row_begin, int64_t row_end, float tied_tol, int32_t algo,
                                int64_t *out_counts, void *workspace, size_t workspace_bytes,
                                b200surv_stream_t stream);
+/* Many independent cohorts packed back to back (the CV sweep evaluates one C-index per fold and replica,
+ * partial_modality_training.py:438-485 called per fold): cohort c is rows
+ * [cohort_offsets_host[c], cohort_offsets_host[c+1]) -- a HOST array of n_cohorts+1 offsets -- and
+ * out_counts is device int64[n_cohorts][6] (ADDED to).  Stream-ordered launches, one per cohort, sharing a
+ * workspace sized for the largest cohort (b200surv_cindex_workspace_bytes(n_max, 1, algo)). */
+int32_t b200surv_cindex_counts_cohorts(const float *estimate, const float *time, const uint8_t *event,
+                                       const int64_t *cohort_offsets_host, int64_t n_cohorts,
+                                       float tied_tol, int32_t algo, int64_t *out_counts, void *workspace,
+                                       size_t workspace_bytes, b200surv_stream_t stream);
 
 /* ---- fusion head: tensor-core GEMM primitive ----------------------------------------------- */
 /* C[M][N] (fp32 and/or bf16 copy) = A * B (+ bias[n]) (ReLU), bf16 operands, fp32 accumulation in

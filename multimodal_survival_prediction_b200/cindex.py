@@ -42,6 +42,28 @@ def cindex_counts(estimate, event, time, tied_tol=1e-8, row_begin=0, row_end=Non
     return out
 
 
+def cindex_counts_cohorts(estimate, event, time, offsets, tied_tol=1e-8, algo=1):
+    """int64[n_cohorts][6] pair counters for cohorts packed back to back; ``offsets`` is a host sequence of
+    n_cohorts+1 row offsets (the CV sweep: one C-index per fold and replica).  Asynchronous."""
+    dev = estimate.device
+    L.require_device(dev.index)
+    lib = L.load()
+    offs = [int(o) for o in offsets]
+    nc = len(offs) - 1
+    if nc < 1 or offs[0] != 0 or offs[-1] != estimate.numel() or any(b < a for a, b in zip(offs, offs[1:])):
+        raise ValueError("offsets must run from 0 to n, non-decreasing, with at least one cohort")
+    out = torch.zeros(nc, 6, dtype=torch.int64, device=dev)
+    n_max = max(b - a for a, b in zip(offs, offs[1:]))
+    wb = lib.b200surv_cindex_workspace_bytes(n_max, 1, algo)
+    ws = torch.empty(max(wb, 256), dtype=torch.uint8, device=dev)
+    host = (ctypes.c_int64 * (nc + 1))(*offs)
+    rc = lib.b200surv_cindex_counts_cohorts(L.ptr(estimate), L.ptr(time), L.ptr(event), host, nc,
+                                            ctypes.c_float(tied_tol), algo, L.ptr(out), L.ptr(ws), ws.numel(),
+                                            L.stream_ptr(dev))
+    L.check(rc, "b200surv_cindex_counts_cohorts")
+    return out
+
+
 def cindex_from_counts(counts, convention="harrell"):
     """float64 ratio from the six counters (host ints)."""
     c = [int(x) for x in counts]

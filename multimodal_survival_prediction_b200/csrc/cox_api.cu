@@ -155,4 +155,22 @@ int32_t b200surv_cindex_counts(const float *estimate, const float *time, const u
                                 workspace_bytes, as_stream(stream));
 }
 
+int32_t b200surv_cindex_counts_cohorts(const float *estimate, const float *time, const uint8_t *event,
+                                       const int64_t *cohort_offsets_host, int64_t n_cohorts, float tied_tol,
+                                       int32_t algo, int64_t *out_counts, void *workspace, size_t workspace_bytes,
+                                       b200surv_stream_t stream) {
+    B200_REQUIRE(estimate && time && event && out_counts && cohort_offsets_host, "null pointer");
+    B200_REQUIRE(n_cohorts >= 1, "n_cohorts");
+    B200_REQUIRE(algo == 0 || workspace != nullptr, "workspace");
+    for (int64_t c = 0; c < n_cohorts; ++c) {  // stream-ordered: the cohorts share the workspace
+        const int64_t a = cohort_offsets_host[c], b = cohort_offsets_host[c + 1];
+        B200_REQUIRE(a >= 0 && b >= a, "cohort_offsets_host must be non-decreasing");
+        if (b == a) continue;
+        const int32_t rc = cindex_counts_launch(estimate + a, time + a, event + a, b - a, 0, b - a, tied_tol, algo,
+                                                out_counts + 6 * c, workspace, workspace_bytes, as_stream(stream));
+        if (rc != B200SURV_OK) return rc;
+    }
+    return B200SURV_OK;
+}
+
 }  // extern "C"

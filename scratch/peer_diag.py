@@ -51,13 +51,26 @@ def f_single():
 
 timeit("single fused fwd", f_single)
 timeit("single fwd+bwd", lambda: (f_single(), single.backward(x, tt, e, grad)))
-peer = bd.ShardedCoxBinned(n, dev, exchange="peer")
+if world == 1:   # the peer kernel against its own buffer: phase trace of the single-GPU forward
+    peer = bd.ShardedCoxBinned(n, dev, exchange="nccl")
+    peer.peers = bd.PeerBuffers(lib.b200surv_cox_peer_buffer_bytes(4096))
+
+    def f_peer1():
+        peer.epoch += 1
+        rc = lib.b200surv_cox_binned_fwd_peer(L.ptr(x), L.ptr(tt), L.ptr(e), n, 2, 0, 4096, ctypes.c_float(0.0),
+                                              L.ptr(peer.loss), L.ptr(peer.state), peer.sb, L.ptr(peer.ws), peer.wb,
+                                              peer.peers.array, 1, 0, peer.epoch, st)
+        assert rc == 0
+    peer.forward = lambda *a: f_peer1()
+else:
+    peer = bd.ShardedCoxBinned(n, dev, exchange="peer")
 timeit("peer fwd", lambda: peer.forward(x, tt, e))
 if os.environ.get("B200SURV_PEER_TRACE"):
     off = lib.b200surv_cox_peer_trace_offset(n, 4096)
     torch.cuda.synchronize()
-    tr = peer.ws[off:off + 88].view(torch.int64).cpu().tolist()
-    names = ["start", "pass1", "sync1", "reduce", "sync2", "flag_sent", "peers_seen", "pulled+sync", "efron", "sync4", "end"]
+    tr = peer.ws[off:off + 120].view(torch.int64).cpu().tolist()
+    names = ["start", "pass1", "sync1", "reduce", "sync2", "flag_sent", "peers_seen", "pulled+sync", "cta0_ready", "sync4", "end",
+             "f_loaded", "f_exscan", "cta1_scanned", "cta1_efron_done(t0)"]
     print(f"rank {rank} trace (us since start): " + ", ".join(f"{nm} {(v - tr[0]) / 1e3:.1f}" for nm, v in zip(names, tr)),
           flush=True)
 timeit("peer fwd+bwd", lambda: (peer.forward(x, tt, e), peer.backward(x, tt, e, grad)))

@@ -101,3 +101,17 @@ def test_concordance_index_object_api():
     val_gpu = pkg.ConcordanceIndex(convention="fallback")(lh.cuda(), ev.cuda(), t.cuda())
     assert val_gpu.is_cuda and val_gpu.item() == np.float32(oci.cindex_from_counts(ref, "fallback"))
     assert pkg.ConcordanceIndex()(lh[:0], ev[:0], t[:0]).item() == 0.5
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_packed_cohorts_match_per_cohort_counts(algo):
+    """CV-sweep shape: ragged cohorts packed back to back (one empty), one launch sequence, counts per cohort."""
+    from multimodal_survival_prediction_b200.cindex import cindex_counts_cohorts
+    sizes = [1, 0, 37, 1000, 2049, 5]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    est, ev, t = cohort(int(offs[-1]), 11, tmax=9, risk_ties=True)
+    out = cindex_counts_cohorts(torch.from_numpy(est).cuda(), torch.from_numpy(ev).cuda(), torch.from_numpy(t).cuda(),
+                                offs.tolist(), 1e-8, algo).cpu().numpy()
+    for c, (a, b) in enumerate(zip(offs[:-1], offs[1:])):
+        ref = oci.counts_brute(est[a:b], ev[a:b], t[a:b], 1e-8) if b > a else np.zeros(6, dtype=np.int64)
+        assert (out[c] == ref).all(), (c, a, b)
