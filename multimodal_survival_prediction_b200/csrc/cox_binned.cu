@@ -325,6 +325,83 @@ __device__ __forceinline__ void pass1_body_tma(const float *__restrict__ log_hz,
     pass1_flush(h, acc, se_d, sw_d, partial, recs, 0, cta, nctas, nb, red_d, red_f, red_u);
 }
 
+// cp.async ring variant of the pass-1 body (one cohort, 16-byte aligned inputs, nbins <= 4096): every thread
+// keeps RING_STAGES - 1 iterations of its OWN three loads (16 B log_hz, 16 B time, 4 B event) in flight as
+// asynchronous global->shared copies and bins the oldest one.  A thread only ever reads back what it copied
+// itself, so cp.async.wait_group is the only synchronisation (no barrier, no producer warp).
+constexpr int RING_STAGES = 3;
+constexpr int RING_STAGE_BYTES = P1_THREADS * 36;  // 36,864 B
+__host__ __device__ inline size_t ring_smem_bytes(int nb) { return tma_hist_bytes(nb) + (size_t)RING_STAGES * RING_STAGE_BYTES; }
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void pass1_body_ring(const float *__restrict__ log_hz, const float *__restrict__ time,
+                                                const uint8_t *__restrict__ event, int64_t n, int nb, float shift,
+                                                unsigned char *__restrict__ partial, CtaRec *__restrict__ recs,
+                                                int cta, int nctas, unsigned char *smem_raw) {
+    __shared__ double red_d[32];
+    __shared__ float red_f[32];
+    __shared__ unsigned red_u[32];
+    unsigned *h = reinterpret_cast<unsigned *>(smem_raw);
+    const int t = threadIdx.x;
+    for (int i = t; i < 5 * nb; i += blockDim.x) h[i] = 0u;
+    __syncthreads();
+
+    const float c2 = (float)FIX_BITS - shift * LOG2E;
+    const unsigned nbu = (unsigned)nb;
+    const uint32_t h_addr = smem_addr_u32(h);
+    const uint32_t ring = smem_addr_u32(smem_raw + tma_hist_bytes(nb));
+    const uint32_t my_e = ring + 16u * t, my_t = ring + 16u * P1_THREADS + 16u * t, my_v = ring + 32u * P1_THREADS + 4u * t;
+    P1Acc acc{0.f, -INFINITY, 0.f, false, false};
+    double se_d = 0.0, sw_d = 0.0;
+    const int64_t ngroups = n >> 2, stride = (int64_t)nctas * P1_THREADS;
+    const int64_t g0 = (int64_t)cta * P1_THREADS + t;
+    const int64_t iters = g0 < ngroups ? (ngroups - g0 + stride - 1) / stride : 0;
+    auto issue = [&](int64_t i, int s) {
+        if (i < iters) {
+            const int64_t g = g0 + i * stride;
+            const uint32_t so = (uint32_t)s * RING_STAGE_BYTES;
+            cp_async_16(my_e + so, log_hz + 4 * g);
+            cp_async_16(my_t + so, time + 4 * g);
+            cp_async_4(my_v + so, event + 4 * g);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < RING_STAGES - 1; ++s) issue(s, s);
+    int s = 0;
+    for (int64_t i = 0; i < iters; ++i) {
+        int sn = s + RING_STAGES - 1;
+        if (sn >= RING_STAGES) sn -= RING_STAGES;
+        issue(i + RING_STAGES - 1, sn);
+        cp_async_wait<RING_STAGES - 1>();
+        const uint32_t so = (uint32_t)s * RING_STAGE_BYTES;
+        float4 e4, t4;
+        uint32_t v4;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e4.x), "=f"(e4.y), "=f"(e4.z), "=f"(e4.w) : "r"(my_e + so));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w) : "r"(my_t + so));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v4) : "r"(my_v + so));
+        p1_group(e4, t4, v4, c2, nbu, h_addr, acc);
+        se_d += (double)acc.se; sw_d += (double)acc.sw; acc.se = 0.f; acc.sw = 0.f;
+        if (++s == RING_STAGES) s = 0;
+    }
+    cp_async_wait<0>();
+    {  // rows beyond the last full 4-row group: direct loads
+        for (int64_t row = (ngroups << 2) + (int64_t)cta * blockDim.x + t; row < n; row += stride)
+            p1_row(log_hz[row], time[row], event[row] != 0, c2, nbu, h_addr, acc);
+    }
+    se_d += (double)acc.se; sw_d += (double)acc.sw;
+    pass1_flush(h, acc, se_d, sw_d, partial, recs, 0, cta, nctas, nb, red_d, red_f, red_u);
+}
+
 __global__ void __launch_bounds__(P1_THREADS, 1)
 cox_binned_pass1(const float *__restrict__ log_hz, const float *__restrict__ time,
                  const uint8_t *__restrict__ event, const int64_t *__restrict__ seg_off, int64_t n,
@@ -855,7 +932,9 @@ cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__
         if (PEER && pa.trace != nullptr && cta == 0 && t == 0) pa.trace[i] = global_timer_ns(); \
     } while (0)
     PEER_TRACE(0);
-    if (use_tma)
+    if (use_tma == 2)
+        pass1_body_ring(log_hz, time, event, n, nb, shift, partial, recs, cta, nctas, smem_raw);
+    else if (use_tma == 1)
         pass1_body_tma(log_hz, time, event, n, nb, shift, partial, recs, cta, nctas, smem_raw);
     else
         pass1_body(log_hz, time, event, nullptr, n, nb, shift, vec_ok, partial, recs, 0, cta, nctas,
@@ -1484,13 +1563,22 @@ int32_t launch_fused(const float *log_hz, const float *time, const uint8_t *even
         // The TMA-staged pass 1 (pass1_body_tma) is opt-in: measured 78.9 us vs 72.8 us for the register-staged
         // loop at 16.7M rows (profiles/r1_v10_tma_ab.txt) -- with 31 consumer warps the ring hides the latency
         // but the CTA loses a warp and pays an mbarrier round trip per 4 rows/thread.
-        static const bool tma_on = getenv("B200SURV_USE_TMA") != nullptr;
-        int use_tma = tma_on && vec_ok && nb <= 4096 && n >= 4 * (int64_t)TMA_TILE;
-        const size_t smem = use_tma ? tma_smem_bytes(nb) : (size_t)nb * 24 + 16;
+        // Pass-1 staging, B200SURV_P1 = ring (default) | reg | tma.  Measured at 16.7M rows, forward only:
+        // per-thread cp.async ring 64.4 us, register-staged loads 70.3 us, TMA bulk ring + producer warp 78.9 us
+        // (profiles/r1_v12_p1_staging_ab.txt, r1_v10_tma_ab.txt).
+        static const int p1_mode = [] {
+            const char *e = getenv("B200SURV_P1");
+            if (e && !strcmp(e, "tma")) return 1;
+            if (e && !strcmp(e, "reg")) return 0;
+            return 2;
+        }();
+        int use_tma = (vec_ok && nb <= 4096 && n >= 4 * (int64_t)TMA_TILE) ? p1_mode : 0;
+        const size_t smem = use_tma == 2 ? ring_smem_bytes(nb) : use_tma == 1 ? tma_smem_bytes(nb) : (size_t)nb * 24 + 16;
         static bool attr_done = false;
         if (!attr_done) {
-            const size_t mx = tma_smem_bytes(4096) > (size_t)B200SURV_COX_MAX_BINS * 24 + 16
-                                  ? tma_smem_bytes(4096) : (size_t)B200SURV_COX_MAX_BINS * 24 + 16;
+            size_t mx = (size_t)B200SURV_COX_MAX_BINS * 24 + 16;
+            if (tma_smem_bytes(4096) > mx) mx = tma_smem_bytes(4096);
+            if (ring_smem_bytes(4096) > mx) mx = ring_smem_bytes(4096);
             B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
             B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
             B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
