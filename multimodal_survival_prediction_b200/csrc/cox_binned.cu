@@ -12,18 +12,16 @@
 //              the atomics or how rows are sharded over GPUs.
 //              (fp32 atomicAdd in shared memory compiles to a CAS loop and is 7x slower --
 //              measured, profiles/r1_hist_microbench.txt.)
-//   K2 reduce  per-CTA partials -> per-bin int64 sums (this is what multi-GPU exchanges); the
-//              last CTA to finish suffix-scans them (fp64): D[b] = sum_{b' >= b} S[b'], E/(D m).
-//   K3 items   Efron: log(x), 1/x, (l/m)/x summed over l < m, x = 1 - (l/m) E/D.  The (bin, l) pairs of
-//              all bins are cut into 256-term chunks dealt out evenly to the warps (efron_chunks), each
-//              chunk sum converted to 2^-27 fixed point and added with integer atomics: balanced for any
-//              tie structure, exact, order independent.  The last CTA to finish forms
+//   K2 reduce  per-CTA partials -> per-bin int64 sums (this is what multi-GPU exchanges).
+//   K3 finish  O(nbins): integer suffix sums D[b] = sum_{b' >= b} S[b'], the per-bin Breslow / Efron terms
+//              (Efron's sums over the m tied events of a bin in closed form, Euler-Maclaurin: bin_terms),
 //              P[b] = sum_{b' <= b} G[b'], the loss, the header and the (P,F) table.
 //   K4 pass 2  (backward) streams the rows again, 9 B read + 4 B write:
 //              grad = scale * (d - w * (P[b] - d * F[b]))
-// One cohort per call (the headline case) runs K1..K3 as ONE cooperative kernel, cox_binned_fwd_fused
-// (grid barriers between the phases); with peers it also carries the multi-GPU exchange of the per-bin
-// sums over NVLink peer memory (PeerArgs).  Every path produces bit-identical results.
+// One cohort per call (the headline case) runs K1..K3 as ONE cooperative kernel, cox_binned_fwd_fused: a single
+// grid barrier after pass 1, then one warp per 32-bin block with decoupled look-back between the blocks; with
+// peers it also carries the multi-GPU exchange of the per-bin sums over NVLink peer memory (PeerArgs).  Every
+// path produces bit-identical results (integer sums; one canonical tree of floating-point additions).
 // Algorithmic HBM bytes: 22 per row for fwd+bwd; everything else is O(nbins).
 #include <cooperative_groups.h>
 
@@ -39,15 +37,12 @@ namespace {
 
 constexpr int P1_THREADS = 1024;
 constexpr int P2_THREADS = 512;
-constexpr int RED_THREADS = 1024;  // reduce: 32 bins x 32 groups of partials; also the scan block
+constexpr int RED_THREADS = 1024;  // reduce: 32 bins x 32 groups of partials
 constexpr int RED_BINS = 32;
 constexpr int RED_NG = RED_THREADS / RED_BINS;
 constexpr int RED_MAX_ITERS = 5;   // ceil(max pass-1 CTAs per segment / RED_NG): up to 160 CTAs
 constexpr int MAX_P1_CTAS = RED_NG * RED_MAX_ITERS;
-constexpr int IT_THREADS = 1024;   // items / finish
-constexpr int EF_CHUNK = 256;                    // fused forward: granule of the Efron work split
-constexpr double EF_SCALE = 134217728.0;         // 2^27 fixed point of the per-bin Efron sums (|sum| < 2^36)
-constexpr double EF_INV = 1.0 / 134217728.0;
+constexpr int IT_THREADS = 1024;   // finish
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int FIX_BITS = 28;
 constexpr double FIX_INV = 1.0 / 268435456.0;    // 2^-28
@@ -406,252 +401,122 @@ __global__ void __launch_bounds__(P1_THREADS, 1)
 cox_binned_pass1(const float *__restrict__ log_hz, const float *__restrict__ time,
                  const uint8_t *__restrict__ event, const int64_t *__restrict__ seg_off, int64_t n,
                  int nb, float shift, int vec_ok, unsigned char *__restrict__ partial,
-                 CtaRec *__restrict__ recs, unsigned *__restrict__ tickets_k2) {
+                 CtaRec *__restrict__ recs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    if (blockIdx.x == 0 && threadIdx.x == 0) tickets_k2[blockIdx.y] = 0;  // "last CTA done" ticket of the reduce kernel
     pass1_body(log_hz, time, event, seg_off, n, nb, shift, vec_ok, partial, recs, blockIdx.y, blockIdx.x, gridDim.x,
                reinterpret_cast<unsigned *>(smem_raw));
 }
 
-// ================================================================ block scans (1024 threads)
-// exclusive scan of one value per thread; returns the exclusive prefix, *total = block total
-template <typename T>
-__device__ __forceinline__ T block_exscan(T v, T *sh /*[33]*/, T *total) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    T inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const T u = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += u;
-    }
-    __syncthreads();
-    if (lane == 31) sh[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        T w = (lane < nw) ? sh[lane] : T(0), winc = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const T u = __shfl_up_sync(FULL, winc, o);
-            if (lane >= o) winc += u;
-        }
-        sh[lane] = winc - w;  // exclusive warp offsets
-        if (lane == 31) sh[32] = winc;
-    }
-    __syncthreads();
-    *total = sh[32];
-    return sh[wid] + (inc - v);
-}
+// ================================================================ per-bin terms (Breslow / Efron)
+// A bin with m tied events, event weight E and risk-set weight D contributes
+//   T = m log D + sum_{l<m} log x_l,   G = (1/D) sum_{l<m} 1/x_l,   F = (1/D) sum_{l<m} (l/m)/x_l,   x_l = 1 - (l/m) E/D
+// (Breslow: x_l = 1).  The three sums over l are smooth functions of l sampled at the integers, so they are
+// evaluated in O(1) per bin with the Euler-Maclaurin formula (integral + end-point term + five Bernoulli
+// corrections) over l in [0, L), where L is the largest index that keeps the derivative ratio
+// a / (1 - a L) <= 1/EM_Q, a = E/(D m): the first omitted correction is then < 1e-12 of the sum.  The at most
+// EM_Q + 1 remaining terms (risk sets that are almost only the tied events) are summed directly.  The whole tail of
+// the forward pass is therefore O(nbins), independent of the number of events (scratch/em_efron.py checks the
+// expansion against direct long-double summation: relative error <= 1e-11 for m up to 3e6 and any E/D in [0,1]).
+constexpr int EM_Q = 16;
+struct BinTerms { double T, G, F; };
 
-// The block-wide part of the per-bin scan in one pass (three barriers): exclusive scans of a double and an int over
-// the threads, and the block totals of two more ints.  shd[33], shi[36].
-struct BinScan {
-    double run;  // exclusive prefix of loc
-    int crun;    // exclusive prefix of locc
-    int n_chunks, n_events, n_times;
-};
-__device__ __forceinline__ BinScan block_bin_scan(double loc, int locc, int locm, int net, double *shd, int *shi) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    double incd = loc;
-    int incc = locc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double ud = __shfl_up_sync(FULL, incd, o);
-        const int uc = __shfl_up_sync(FULL, incc, o);
-        if (lane >= o) { incd += ud; incc += uc; }
-    }
-    const int wm = __reduce_add_sync(FULL, locm), wt = __reduce_add_sync(FULL, net);
-    if (threadIdx.x == 0) { shi[33] = 0; shi[34] = 0; }
-    __syncthreads();
-    if (lane == 31) { shd[wid] = incd; shi[wid] = incc; }
-    if (lane == 0) { atomicAdd(&shi[33], wm); atomicAdd(&shi[34], wt); }
-    __syncthreads();
-    if (wid == 0) {
-        const double wd = (lane < nw) ? shd[lane] : 0.0;
-        const int wc = (lane < nw) ? shi[lane] : 0;
-        double id = wd;
-        int ic = wc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double ud = __shfl_up_sync(FULL, id, o);
-            const int uc = __shfl_up_sync(FULL, ic, o);
-            if (lane >= o) { id += ud; ic += uc; }
-        }
-        shd[lane] = id - wd;  // exclusive warp offsets
-        shi[lane] = ic - wc;
-        if (lane == 31) { shd[32] = id; shi[32] = ic; }
-    }
-    __syncthreads();
-    BinScan r;
-    r.run = shd[wid] + (incd - loc);
-    r.crun = shi[wid] + (incc - locc);
-    r.n_chunks = shi[32]; r.n_events = shi[33]; r.n_times = shi[34];
-    return r;
-}
+// (one out-of-line copy of log keeps the tail's code small)
+__device__ __noinline__ double log_f64(double x) { return log(x); }
 
-// The block-wide part of the finish in one pass (three barriers): exclusive scan of g over the threads and the block
-// sum of tv (fixed butterfly order: deterministic).  shd[33], shd2[33].
-__device__ __forceinline__ double block_exscan_and_sum(double g, double tv, double *shd, double *shd2, double *tsum) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    double inc = g;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double u = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += u;
+__device__ __noinline__ BinTerms bin_terms(long long Dq, long long Eq, int m, int efron) {
+    BinTerms o;
+    o.T = 0.0; o.G = 0.0; o.F = 0.0;
+    if (m <= 0) return o;
+    const double md = (double)m, invm = 1.0 / md;
+    const double D = (double)Dq * FIX_INV, invD = 1.0 / D;
+    double T = md * log_f64(D);
+    if (!efron) { o.T = T; o.G = md * invD; return o; }
+    const double r = ((double)Eq * FIX_INV) * invD;  // in [0, 1]: the bin's events are part of its risk set
+    const double a = r * invm;
+    int L = m;
+    if (1.0 - r < (double)EM_Q * a) {
+        const double Lf = floor(1.0 / a - (double)EM_Q);
+        L = Lf < 2.0 ? 0 : (int)fmin(Lf, md);
     }
-    const double wt = warp_sum(tv);
-    __syncthreads();
-    if (lane == 31) shd[wid] = inc;
-    if (lane == 0) shd2[wid] = wt;
-    __syncthreads();
-    if (wid == 0) {
-        const double w = (lane < nw) ? shd[lane] : 0.0;
-        double winc = w;
+    if (L < 2) L = 0;
+    double sg = 0.0, sf = 0.0;
+    if (L > 0) {
+        const double Ld = (double)L, z = a * Ld;  // z <= 1 - EM_Q a < 1
+        // ps = -log(1-z)/z, ph = (ps - 1)/z, lz = log(1-z); power series where the closed forms cancel
+        double ps, ph, lz;
+        if (z < 0.03125) {
+            ps = 1.0 / 14.0; ph = 1.0 / 15.0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double u = __shfl_up_sync(FULL, winc, o);
-            if (lane >= o) winc += u;
+            for (int j = 12; j >= 0; --j) { ps = fma(ps, z, 1.0 / (double)(j + 1)); ph = fma(ph, z, 1.0 / (double)(j + 2)); }
+            lz = -z * ps;
+        } else {
+            const double invz = 1.0 / z;
+            lz = log_f64(1.0 - z);
+            ps = -lz * invz;
+            ph = (ps - 1.0) * invz;
         }
-        shd[lane] = winc - w;
-        const double ts = warp_sum((lane < nw) ? shd2[lane] : 0.0);
-        if (lane == 0) shd2[32] = ts;
+        const double u = 1.0 / (1.0 - z), u2 = u * u, a2 = a * a;
+        double st = -Ld * z * (ps - ph) - 0.5 * lz;
+        sg = Ld * ps + 0.5 * (1.0 - u);
+        sf = (Ld * Ld * invm) * ph - 0.5 * (Ld * invm) * u;
+        // Bernoulli corrections k = 1..5:  -B2k/(2k(2k-1)) for the logs,  B2k/(2k) for the reciprocals
+        const double CL[5] = {-1.0 / 12.0, 1.0 / 360.0, -1.0 / 1260.0, 1.0 / 1680.0, -1.0 / 1188.0};
+        const double CI[5] = {1.0 / 12.0, -1.0 / 120.0, 1.0 / 252.0, -1.0 / 240.0, 1.0 / 132.0};
+        double pw_odd = u, pw_even = u2, ak = a, akm = invm;  // (1-z)^-(2k-1), (1-z)^-2k, a^(2k-1), a^(2k-2)/m
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            st = fma(CL[k] * ak, pw_odd - 1.0, st);
+            sg = fma(CI[k] * ak, pw_even - 1.0, sg);
+            sf = fma(CI[k] * akm, pw_even - 1.0, sf);
+            pw_odd *= u2; pw_even *= u2; ak *= a2; akm *= a2;
+        }
+        T += st;
     }
-    __syncthreads();
-    *tsum = shd2[32];
-    return shd[wid] + (inc - g);
-}
-
-// per-segment scratch in the workspace, produced by the scan and consumed by K3
-struct ScanBufs {
-    double *D;          // [nb] risk-set sums
-    double *rm;         // [nb] E / (D m)  (0 where m == 0)
-    double *tgf;        // [3][nb] Efron T, G, F per bin
-    long long *totals;  // [2] n_events, n_event_times
-    int *cp;            // [nb + 1] exclusive prefix of the Efron chunk counts in scan order (see efron_chunks)
-    unsigned *ticket;   // "last CTA done" counter of K3
-};
-struct ScanBase {
-    double *D, *rm, *tgf;
-    long long *totals;
-    int *big;
-    unsigned *tickets_k2, *tickets_k3;
-};
-__device__ __forceinline__ ScanBufs scan_bufs(const ScanBase &w, int seg, int nb) {
-    ScanBufs o;
-    o.D = w.D + (size_t)seg * nb; o.rm = w.rm + (size_t)seg * nb; o.tgf = w.tgf + (size_t)seg * 3 * nb;
-    o.totals = w.totals + 2 * (size_t)seg; o.cp = w.big + (size_t)seg * (nb + 1); o.ticket = w.tickets_k3 + seg;
+    if (L < m) {  // at most EM_Q + 1 terms; the logs as the log of the product (every factor >= 1/m)
+        double prod = 1.0;
+#pragma unroll 1
+        for (int l = L; l < m; ++l) {
+            const double x = 1.0 - (double)l * a, rx = 1.0 / x;
+            prod *= x;
+            sg += rx;
+            sf = fma((double)l * invm, rx, sf);
+        }
+        T += log_f64(prod);
+    }
+    o.T = T; o.G = sg * invD; o.F = sf * invD;
     return o;
 }
 
-// bins layout per segment (int64): S_cens_q[nb], S_event_q[nb], m[nb], sum_ev_eta_q (2^-24 fixed point),
-// n_not_binnable, ceil(sum_w), n_bad_time.
-// One block of 1024 threads: suffix sums D, E/(D m), totals, list of big bins.  `bs` may have been written by
-// other CTAs of the same launch (fused path): it is read through L2.
-template <int MAXPER>
-__device__ void scan_segment(const long long *bs, int nb, ScanBufs o, double *shd, int *shi) {
-    const int t = threadIdx.x;
-    const int per = nb / RED_THREADS > 0 ? nb / RED_THREADS : 1;  // threads beyond nb idle
-    const int hi_b = nb - t * per;  // reversed chunk [hi_b - per, hi_b)
-    long long rc[MAXPER], re[MAXPER], rmv[MAXPER];
+// ================================================================ canonical warp scans
+// P[b] = sum_{b' <= b} G[b'] and the total of T are formed by the SAME tree of additions on every code path
+// (fused forward on any grid, multi-GPU, stand-alone finish kernel), so that the loss and the (P,F) table -- and
+// with them every gradient -- are bit-identical across the paths: level 1 is a Hillis-Steele scan over the 32
+// bins of a block, level 2 the same scan over the 32 block totals of a superblock (1024 bins), level 3 a
+// sequential sum over the superblocks.  The suffix sums D are integers (any order is exact).
+__device__ __forceinline__ double hs_scan(double v, int lane) {
 #pragma unroll
-    for (int k = 0; k < MAXPER; ++k) {  // all loads in flight together
-        const int b = hi_b - 1 - k;
-        const bool in = (k < per) && (b >= 0);
-        rc[k] = in ? __ldcg(bs + b) : 0ll;
-        re[k] = in ? __ldcg(bs + nb + b) : 0ll;
-        rmv[k] = in ? __ldcg(bs + 2 * nb + b) : 0ll;
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(FULL, v, o);
+        if (lane >= o) v += u;
     }
-    if (t == 0) *o.ticket = 0;
-    double sv[MAXPER];
-    double loc = 0.0;
-    int locm = 0, net = 0, locc = 0;
+    return v;
+}
+__device__ __forceinline__ long long suffix_scan(long long v, int lane) {
 #pragma unroll
-    for (int k = 0; k < MAXPER; ++k) {
-        sv[k] = ((double)(unsigned long long)rc[k] + (double)(unsigned long long)re[k]) * FIX_INV;
-        loc += sv[k];
-        locm += (int)rmv[k];
-        net += rmv[k] > 0 ? 1 : 0;
-        locc += ((int)rmv[k] + EF_CHUNK - 1) / EF_CHUNK;
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long u = __shfl_down_sync(FULL, v, o);
+        if (lane + o < 32) v += u;
     }
-    const BinScan sc = block_bin_scan(loc, locc, locm, net, shd, shi);  // run: sum over all later bins
-    double run = sc.run;
-    int crun = sc.crun;
-    const int totm = sc.n_events, totn = sc.n_times, totc = sc.n_chunks;
-#pragma unroll
-    for (int k = 0; k < MAXPER; ++k) {
-        const int b = hi_b - 1 - k;
-        if (k < per && b >= 0) {
-            run += sv[k];
-            const int m = (int)rmv[k];
-            o.D[b] = run;
-            o.rm[b] = m > 0 ? ((double)(unsigned long long)re[k] * FIX_INV) / (run * (double)m) : 0.0;
-            o.cp[t * per + k] = crun;  // scan order p = nb-1-b
-            crun += (m + EF_CHUNK - 1) / EF_CHUNK;
-            o.tgf[b] = 0.0; o.tgf[nb + b] = 0.0; o.tgf[2 * nb + b] = 0.0;  // Efron accumulators (all-zero bits)
-        }
-    }
-    if (t == 0) { o.totals[0] = totm; o.totals[1] = totn; o.cp[nb] = totc; }
+    return v;
 }
 
-// Efron terms of one cohort, shared by the fused forward and the K3 kernel: the (bin, l) pairs of ALL bins, cut
-// into chunks of EF_CHUNK consecutive l of one bin, are dealt out in equal contiguous runs to the W warps taking
-// part -- balanced whatever the tie structure (one bin holding every event, or thousands of moderately tied
-// ones; the work is the number of events).  A warp sums its run bin by bin (fp32, fp64 where x < 0.5) and adds the
-// three sums to per-bin 2^-27 fixed-point integers: exact and order independent, so the loss is bit-reproducible
-// and identical on every code path.  cp[p], p = nb-1-b: exclusive prefix of the chunk counts, cp[nb] = total.
-__device__ __forceinline__ void efron_terms(int l0, int l1, int lane, double rm, float inv_m, float &vt, float &vg,
-                                            float &vf);
-template <typename MFn, typename RmFn>
-__device__ __forceinline__ void efron_chunks(const int *cp, int nb, int gw, int W, int lane, MFn m_of, RmFn rm_of,
-                                             long long *acc) {
-    const int C = cp[nb], q = (C + W - 1) / W;
-    int c = gw * q;
-    const int c1 = min(C, c + q);
-    if (c >= c1) return;
-    int lo = 0, hi = nb;  // cp[lo] <= c < cp[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (cp[mid] <= c) lo = mid; else hi = mid;
-    }
-    int p = lo;
-    while (c < c1) {
-        const int base = cp[p], cend = min(c1, cp[p + 1]);
-        if (cend > c) {
-            const int b = nb - 1 - p, m = m_of(b);
-            const double rm = rm_of(b);
-            const float inv_m = __frcp_rn((float)m);
-            long long it = 0, ig = 0, iff = 0;
-            // one chunk = one unit of floating-point summation, converted to fixed point before it meets any other:
-            // the per-bin sums do not depend on how the chunks are dealt out (grid size, sharding, code path)
-            for (int l0 = (c - base) * EF_CHUNK; l0 < (cend - base) * EF_CHUNK; l0 += EF_CHUNK) {
-                float vt = 0.f, vg = 0.f, vf = 0.f;
-                efron_terms(l0, min(m, l0 + EF_CHUNK), lane, rm, inv_m, vt, vg, vf);
-                vt = warp_sum(vt); vg = warp_sum(vg); vf = warp_sum(vf);
-                it += __double2ll_rn((double)vt * EF_SCALE);
-                ig += __double2ll_rn((double)vg * EF_SCALE);
-                iff += __double2ll_rn((double)vf * EF_SCALE);
-            }
-            if (lane == 0) {
-                atomicAdd(reinterpret_cast<unsigned long long *>(acc + b), (unsigned long long)it);
-                atomicAdd(reinterpret_cast<unsigned long long *>(acc + nb + b), (unsigned long long)ig);
-                atomicAdd(reinterpret_cast<unsigned long long *>(acc + 2 * nb + b), (unsigned long long)iff);
-            }
-            c = cend;
-        }
-        ++p;
-    }
-}
-
-// ================================================================ K2: reduce partials (+ fused scan)
+// ================================================================ K2: reduce partials
 // grid (nb / 32, n_seg), 1024 threads = 32 bins x 32 groups of partials.
-template <int MAXPER>
 __global__ void __launch_bounds__(RED_THREADS)
 cox_binned_reduce(const unsigned char *__restrict__ partial, const CtaRec *__restrict__ recs, int nctas, int nb,
-                  long long *bins, float *__restrict__ bins_max, ScanBase sb, int fuse_scan) {
+                  long long *bins, float *__restrict__ bins_max) {
     __shared__ long long s_c[RED_NG][RED_BINS], s_e[RED_NG][RED_BINS];
     __shared__ unsigned s_m[RED_NG][RED_BINS];
-    __shared__ double shd[33];
-    __shared__ int shi[36];
-    __shared__ int s_last;
     const int seg = blockIdx.y;
     const int lb = threadIdx.x & (RED_BINS - 1), grp = threadIdx.x / RED_BINS;
     const int b = blockIdx.x * RED_BINS + lb;
@@ -700,180 +565,174 @@ cox_binned_reduce(const unsigned char *__restrict__ partial, const CtaRec *__res
             bins_max[2 * seg + 1] = -1.f;  // reserved
         }
     }
-    if (!fuse_scan) return;
-    // ---- the last CTA of this segment to arrive scans the finished bins
-    __syncthreads();
-    if (threadIdx.x == 0) { __threadfence();
-
-        const unsigned prev = atomicAdd(sb.tickets_k2 + seg, 1u);  // zeroed by pass 1
-        s_last = (prev == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    scan_segment<MAXPER>(bs, nb, scan_bufs(sb, seg, nb), shd, shi);
 }
 
-// stand-alone scan for the multi-GPU path (bins come out of an all-reduce): grid n_seg, 1024 threads
-template <int MAXPER>
-__global__ void __launch_bounds__(RED_THREADS)
-cox_binned_scan(const long long *bins, int nb, ScanBase sb) {
-    __shared__ double shd[33];
-    __shared__ int shi[36];
-    const int seg = blockIdx.x;
-    scan_segment<MAXPER>(bins + (size_t)seg * (3 * (size_t)nb + 4), nb, scan_bufs(sb, seg, nb), shd, shi);
-}
-
-// ================================================================ K3: items + finish
+// ================================================================ header
 // state per segment: header (64 B) | float2 (P, F)[nb]
 __host__ __device__ inline size_t seg_state_stride(int nb) {
     return sizeof(b200surv_cox_header) + (size_t)nb * sizeof(float2);
 }
 
-// sum over l in [l0, l1), stride 32 per lane, of log(x), 1/x, (l/m)/x with x = 1 - l * rm
-__device__ __forceinline__ void efron_terms(int l0, int l1, int lane, double rm, float inv_m, float &vt, float &vg,
-                                            float &vf) {
-    if ((double)(l1 - 1) * rm <= 0.5) {  // x >= 0.5: fp32 is accurate to ~1e-7 relative
-        const float rmf = (float)rm;
-        // sum of logs = log of the product: a call covers at most EF_CHUNK = 256 terms, 8 per lane, and 8 factors in
-        // [0.5, 1] stay >= 2^-8 -- one MUFU.LG2 per lane instead of one per term
-        float pr = 1.f;
-#pragma unroll 2
-        for (int l = l0 + lane; l < l1; l += 32) {
-            const float x = fmaf(-(float)l, rmf, 1.f);
-            const float rx = rcp_approx(x);
-            pr *= x;
-            vg += rx;
-            vf = fmaf((float)l * inv_m, rx, vf);
-        }
-        vt += __logf(pr);
-    } else {  // the events are a large part of the risk set: keep the difference in fp64
-#pragma unroll 1
-        for (int l = l0 + lane; l < l1; l += 32) {
-            const double xd = 1.0 - (double)l * rm;
-            const float x = (float)xd;
-            const float rx = (float)(1.0 / xd);
-            vt += __logf(x);
-            vg += rx;
-            vf = fmaf((float)l * inv_m, rx, vf);
-        }
-    }
+struct HeaderIn {
+    long long sum_ev_eta_q, n_not_binnable, sum_w_ceil, n_bad_time;  // the four scalar words of the per-bin sums
+    float max_eta;
+    long long n_events, n_times;
+    double T;  // sum over the bins of m log D + sum_l log x_l
+    int peer_timeout;
+};
+__device__ __forceinline__ void write_header(const HeaderIn &h, int efron, int reduction, float shift, int nb,
+                                             b200surv_cox_header *hdr, float *out_loss) {
+    const double sum_ev_eta = (double)h.sum_ev_eta_q * ETA_INV;
+    const double pll = sum_ev_eta - (h.T + (double)h.n_events * (double)shift);
+    double norm = 1.0;
+    if (reduction == B200SURV_REDUCE_MEAN_EVENTS) norm = (double)h.n_events;
+    else if (reduction == B200SURV_REDUCE_MEAN_TERMS) norm = efron ? (double)h.n_times : (double)h.n_events;
+    unsigned flags = 0;
+    if (h.n_not_binnable != 0) flags |= B200SURV_COXF_NOT_BINNABLE;
+    if (h.n_bad_time != 0) flags |= B200SURV_COXF_BAD_TIME;
+    const float mx = h.max_eta;
+    if (!(mx - shift <= SHIFT_HI) || !(mx - shift >= SHIFT_LO) || (double)h.sum_w_ceil >= SUMW_LIMIT)
+        flags |= B200SURV_COXF_EXP_RANGE;
+    if (h.peer_timeout) flags |= B200SURV_COXF_PEER_TIMEOUT;
+    float loss = 0.f, scale = 0.f;
+    if (h.n_events > 0) { loss = (float)(-pll / norm); scale = (float)(-1.0 / norm); }
+    if (flags) { loss = __int_as_float(0x7fc00000); scale = loss; }
+    hdr->flags = flags; hdr->mode = B200SURV_COX_BINNED; hdr->loss = loss; hdr->scale = scale;
+    hdr->shift = shift; hdr->max_log_hz = mx; hdr->max_time = -1.f;
+    hdr->nbins = nb; hdr->n_events = h.n_events; hdr->n_event_times = h.n_times; hdr->pll = pll;
+    hdr->reserved = 0;
+    *out_loss = loss;
 }
 
-// grid (gx, n_seg), 1024 threads, no shared-memory staging: warp gw owns bins gw, gw + W, ...
-template <int MAXPER>
+// ================================================================ K3: finish (stand-alone: segmented cohorts, NCCL path)
+// One CTA of 1024 threads per cohort, straight from the per-bin int64 sums: suffix sums D, per-bin terms, prefix
+// sums P, loss, header and the (P,F) table.  Warp w owns the 32-bin blocks w, w + 32, ...
 __global__ void __launch_bounds__(IT_THREADS, 1)
-cox_binned_items_finish(const long long *__restrict__ bins, const float *__restrict__ bins_max, int nb, int ties,
-                        int reduction, float shift, ScanBase sb, float *__restrict__ out_loss,
-                        unsigned char *__restrict__ state) {
-    __shared__ double shd[33];
-    __shared__ int s_last;
-    const int seg = blockIdx.y, t = threadIdx.x;
+cox_binned_finish(const long long *__restrict__ bins, const float *__restrict__ bins_max, int nb, int ties,
+                  int reduction, float shift, double *__restrict__ scr_g, double *__restrict__ scr_f,
+                  float *__restrict__ out_loss, unsigned char *__restrict__ state) {
+    constexpr int MAXBLK = B200SURV_COX_MAX_BINS / 32;
+    __shared__ long long s_tot[MAXBLK], s_off[MAXBLK];
+    __shared__ double s_g[MAXBLK], s_t[MAXBLK];
+    __shared__ int s_ne, s_nt;
+    const int seg = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long *bs = bins + (size_t)seg * (3 * (size_t)nb + 4);
-    const ScanBufs o = scan_bufs(sb, seg, nb);
+    double *sg = scr_g + (size_t)seg * nb, *sf = scr_f + (size_t)seg * nb;
     const bool efron = ties == B200SURV_TIES_EFRON;
-
-    if (efron) {
-        __shared__ int s_cp[B200SURV_COX_MAX_BINS + 1];
-        for (int i = t; i <= nb; i += IT_THREADS) s_cp[i] = o.cp[i];
-        __syncthreads();
-        // consecutive warp ids go to different CTAs (balance across SMs when the runs are short)
-        const int gw = (t >> 5) * gridDim.x + blockIdx.x, W = gridDim.x * (IT_THREADS / 32);
-        efron_chunks(
-            s_cp, nb, gw, W, t & 31, [&](int b) { return (int)bs[2 * nb + b]; }, [&](int b) { return o.rm[b]; },
-            reinterpret_cast<long long *>(o.tgf));
+    const int nblk = nb >> 5, nsup = (nblk + 31) >> 5;
+    if (t == 0) { s_ne = 0; s_nt = 0; }
+    __syncthreads();
+    for (int j = 0; j < nsup; ++j) {  // block totals of S = S_cens + S_event, event counts
+        const int k = warp + 32 * j;
+        if (k >= nblk) break;
+        const int b = 32 * k + lane;
+        const long long s = bs[b] + bs[nb + b];
+        const int m = (int)bs[2 * nb + b];
+        const long long sfx = suffix_scan(s, lane);
+        const int ne = __reduce_add_sync(FULL, m), nt = __reduce_add_sync(FULL, m > 0 ? 1 : 0);
+        if (lane == 0) { s_tot[k] = sfx; atomicAdd(&s_ne, ne); atomicAdd(&s_nt, nt); }
     }
-    // ---- last CTA of the segment to arrive finishes
     __syncthreads();
-
-    if (t == 0) { __threadfence(); s_last = (atomicAdd(o.ticket, 1u) == gridDim.x - 1); }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-
-    unsigned char *seg_state = state + seg * seg_state_stride(nb);
-    b200surv_cox_header *hdr = reinterpret_cast<b200surv_cox_header *>(seg_state);
-    float2 *table = reinterpret_cast<float2 *>(seg_state + sizeof(b200surv_cox_header));
-    const int per = nb / IT_THREADS > 0 ? nb / IT_THREADS : 1;
-    const int lo_b = t * per;
-    double tv[MAXPER], gv[MAXPER], fv[MAXPER];
-    int mv[MAXPER];
-#pragma unroll
-    for (int k = 0; k < MAXPER; ++k) {  // tgf was written by other CTAs of this launch: read through L2
-        const int b = lo_b + k;
-        const bool in = (k < per) && (b < nb);
-        const long long *acc = reinterpret_cast<const long long *>(o.tgf);
-        mv[k] = in ? (int)bs[2 * nb + b] : 0;
-        const bool live = mv[k] > 0;
-        const long long at = live ? __ldcg(acc + b) : 0ll, ag = live ? __ldcg(acc + nb + b) : 0ll,
-                        af = live ? __ldcg(acc + 2 * nb + b) : 0ll;
-        tv[k] = gv[k] = fv[k] = 0.0;
-        if (live) {  // the same expressions as the fused forward: bit-identical results on both paths
-            const double D = o.D[b], invD = 1.0 / D, m = (double)mv[k];
-            tv[k] = (double)at * EF_INV + m * log(D);
-            gv[k] = efron ? (double)ag * EF_INV * invD : m * invD;
-            fv[k] = (double)af * EF_INV * invD;
+    if (warp == 0) {  // exclusive suffix sums of the block totals
+        long long carry = 0;
+        for (int j = nsup - 1; j >= 0; --j) {
+            const int k = 32 * j + lane;
+            const long long v = k < nblk ? s_tot[k] : 0;
+            const long long sfx = suffix_scan(v, lane);
+            if (k < nblk) s_off[k] = carry + sfx - v;
+            carry += __shfl_sync(FULL, sfx, 0);
         }
     }
-    double tsum = 0.0, gsum = 0.0;
-#pragma unroll
-    for (int k = 0; k < MAXPER; ++k) { tsum += tv[k]; gsum += gv[k]; }
-    __shared__ double shd2[33];
-    double T;
-    double run = block_exscan_and_sum(gsum, tsum, shd, shd2, &T);
-#pragma unroll
-    for (int k = 0; k < MAXPER; ++k) {
-        const int b = lo_b + k;
-        if (k < per && b < nb) { run += gv[k]; table[b] = make_float2((float)run, (float)fv[k]); }
+    __syncthreads();
+    for (int j = 0; j < nsup; ++j) {  // per-bin terms, level-1 scans
+        const int k = warp + 32 * j;
+        if (k >= nblk) break;
+        const int b = 32 * k + lane;
+        const long long e = bs[nb + b];
+        const long long s = bs[b] + e;
+        const int m = (int)bs[2 * nb + b];
+        const long long sfx = suffix_scan(s, lane);
+        const BinTerms bt = bin_terms(s_off[k] + sfx, e, m, efron ? 1 : 0);
+        __syncwarp();
+        const double gi = hs_scan(bt.G, lane), ti = hs_scan(bt.T, lane);
+        sg[b] = gi; sf[b] = bt.F;
+        if (lane == 31) { s_g[k] = gi; s_t[k] = ti; }
+    }
+    __syncthreads();
+    unsigned char *seg_state = state + seg * seg_state_stride(nb);
+    float2 *table = reinterpret_cast<float2 *>(seg_state + sizeof(b200surv_cox_header));
+    double run_g = 0.0, run_t = 0.0;
+    for (int j = 0; j < nsup; ++j) {  // levels 2 and 3 (every warp redundantly), table
+        const int kk = 32 * j + lane;
+        const double vg = kk < nblk ? s_g[kk] : 0.0, vt = kk < nblk ? s_t[kk] : 0.0;
+        const double ig = hs_scan(vg, lane), it = hs_scan(vt, lane);
+        const double ex = __shfl_sync(FULL, ig, warp > 0 ? warp - 1 : 0);
+        const int k = warp + 32 * j;
+        if (k < nblk) {
+            const int b = 32 * k + lane;
+            const double P = (run_g + (warp > 0 ? ex : 0.0)) + sg[b];
+            table[b] = make_float2((float)P, (float)sf[b]);
+        }
+        const int lastpos = min(31, nblk - 1 - 32 * j);
+        run_g += __shfl_sync(FULL, ig, lastpos);
+        run_t += __shfl_sync(FULL, it, lastpos);
     }
     if (t == 0) {
-        const long long n_events = o.totals[0], n_times = o.totals[1];
-        const double sum_ev_eta = (double)bs[3 * (size_t)nb] * ETA_INV;
-        const double pll = sum_ev_eta - (T + (double)n_events * (double)shift);
-        double norm = 1.0;
-        if (reduction == B200SURV_REDUCE_MEAN_EVENTS) norm = (double)n_events;
-        else if (reduction == B200SURV_REDUCE_MEAN_TERMS) norm = efron ? (double)n_times : (double)n_events;
-        unsigned flags = 0;
-        if (bs[3 * (size_t)nb + 1] != 0) flags |= B200SURV_COXF_NOT_BINNABLE;
-        if (bs[3 * (size_t)nb + 3] != 0) flags |= B200SURV_COXF_BAD_TIME;
-        const float mx = bins_max[2 * seg];
-        const double sumw = (double)bs[3 * (size_t)nb + 2];
-        if (!(mx - shift <= SHIFT_HI) || !(mx - shift >= SHIFT_LO) || sumw >= SUMW_LIMIT)
-            flags |= B200SURV_COXF_EXP_RANGE;
-        float loss = 0.f, scale = 0.f;
-        if (n_events > 0) { loss = (float)(-pll / norm); scale = (float)(-1.0 / norm); }
-        if (flags) { loss = __int_as_float(0x7fc00000); scale = loss; }
-        hdr->flags = flags; hdr->mode = B200SURV_COX_BINNED; hdr->loss = loss; hdr->scale = scale;
-        hdr->shift = shift; hdr->max_log_hz = mx; hdr->max_time = -1.f;
-        hdr->nbins = nb; hdr->n_events = n_events; hdr->n_event_times = n_times; hdr->pll = pll;
-        hdr->reserved = 0;
-        out_loss[seg] = loss;
+        HeaderIn h;
+        h.sum_ev_eta_q = bs[3 * (size_t)nb]; h.n_not_binnable = bs[3 * (size_t)nb + 1];
+        h.sum_w_ceil = bs[3 * (size_t)nb + 2]; h.n_bad_time = bs[3 * (size_t)nb + 3];
+        h.max_eta = bins_max[2 * seg];
+        h.n_events = s_ne; h.n_times = s_nt; h.T = run_t; h.peer_timeout = 0;
+        write_header(h, efron ? 1 : 0, reduction, shift, nb, reinterpret_cast<b200surv_cox_header *>(seg_state),
+                     out_loss + seg);
     }
 }
 
 // ================================================================ fused forward (one cohort, one launch)
-// pass 1, the exact reduction of the CTA partials, the suffix scan, the Efron terms and the finish in ONE
-// cooperative kernel (one CTA per SM, grid barriers between the phases): removes two launches and the two
-// single-CTA tails of the K2/K3 pipeline.  Every CTA scans the nbins sums redundantly in shared memory.
-struct FusedArgs {
-    long long *bins;   // [3 nb + 4]
-    float *bins_max;   // [2]
-    double *tgf;       // [3][nb]
-    int ties, reduction;
-    float *out_loss;
-    unsigned char *state;
+// Pass 1, the exact reduction of the CTA partials and the whole O(nbins) tail in ONE cooperative kernel with a
+// single grid barrier (after the partial histograms are flushed).  The bins are dealt out in blocks of 32 (one warp
+// per block, one or two blocks per CTA on a 148-SM grid); the cross-block dependencies of the tail -- the suffix
+// sums D and the prefix sums P -- travel through self-flagged 64-bit words in global memory (decoupled look-back:
+// a block publishes its total, then reads the totals of the blocks after / before it), not through grid barriers.
+struct TailSlot {
+    unsigned long long A;  // block total of S (36.28 fixed point, < 2^62) | SLOT_FLAG
+    unsigned long long C;  // events << 32 | distinct event times of the block | SLOT_FLAG
+    unsigned long long G;  // block total of G (double bits); SLOT_EMPTY until published
+    unsigned long long T;  // block total of T
 };
+constexpr unsigned long long SLOT_FLAG = 1ull << 63;
+constexpr unsigned long long SLOT_EMPTY = ~0ull;  // a NaN pattern no arithmetic result carries
+constexpr int SLOT_SPIN_MAX = 1 << 22;            // a bug must not hang the GPU: give up after ~seconds
+
+__device__ __forceinline__ unsigned long long ld_slot(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_slot(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long wait_flagged(const unsigned long long *p) {
+    unsigned long long v = ld_slot(p);
+    for (int it = 0; !(v & SLOT_FLAG) && it < SLOT_SPIN_MAX; ++it) v = ld_slot(p);
+    return v & ~SLOT_FLAG;
+}
+__device__ __forceinline__ double wait_double(const unsigned long long *p) {
+    unsigned long long v = ld_slot(p);
+    for (int it = 0; v == SLOT_EMPTY && it < SLOT_SPIN_MAX; ++it) v = ld_slot(p);
+    return __longlong_as_double((long long)v);
+}
 
 // ---- multi-GPU exchange through peer memory (NVLink / NVSwitch), fused into the cooperative forward.
 // Every rank owns one "peer buffer" that all ranks of the box have mapped (symmetric allocation):
 //   [ flags: PEER_MAX_WORLD x 128 B, slot r is written by rank r ]
 //   [ slot 0 | slot 1 ]   each: int64 bins[3 nb + 4], float max[2]     (slot = epoch & 1)
 // Step k: a rank writes its own per-bin sums into its slot k&1, publishes flag[rank] = k in every peer's
-// buffer (release, system scope), waits until its own flags show k for every peer, then sums the peers'
-// slots bin slice by bin slice (each CTA pulls ~nb/148 bins from every peer: (world-1) * 24 nb bytes per GPU
-// over NVLink in total).  Integer sums, so every rank obtains bit-identical totals.  Double buffering is
-// enough: a rank rewrites slot k&1 in step k+2, after it passed the barrier of step k+1, which every peer
-// only signals once its step-k kernel (the one reading this slot) has finished.
+// buffer (release, system scope), waits until its own flags show k for every peer, then every block warp pulls
+// its 32 bins from every peer ((world-1) * 24 nb bytes per GPU over NVLink in total).  Integer sums, so every
+// rank obtains bit-identical totals.  Double buffering is enough: a rank rewrites slot k&1 in step k+2, after it
+// passed the barrier of step k+1, which every peer only signals once its step-k kernel (the one reading this
+// slot) has finished.
 constexpr int PEER_MAX_WORLD = 16;
 constexpr int PEER_FLAG_STRIDE = 32;  // unsigned words (128 B)
 constexpr size_t PEER_FLAGS_BYTES = (size_t)PEER_MAX_WORLD * PEER_FLAG_STRIDE * sizeof(unsigned);
@@ -883,7 +742,6 @@ struct PeerArgs {
     int world, rank;
     unsigned epoch;
     int *status;  // local: set to 1 when the wait timed out
-    long long *trace;  // optional (may be null): globaltimer stamps of the phases, CTA 0
     unsigned char *buf[PEER_MAX_WORLD];
 };
 
@@ -915,88 +773,185 @@ __device__ __forceinline__ long long global_timer_ns() {
     return v;
 }
 
-template <int MAXPER, bool PEER>
+struct FusedArgs {
+    int ties, reduction;
+    float *out_loss;
+    unsigned char *state;
+    TailSlot *slots;   // [nb / 32]
+    long long *trace;  // optional (may be null): globaltimer stamps of the phases
+    int nparts;        // CTAs [0, nparts) take part in pass 1 and own a partial histogram + CtaRec
+};
+
+struct TailArgs {
+    TailSlot *slots;
+    int nb, efron, reduction;
+    float shift;
+    float2 *table;
+    b200surv_cox_header *hdr;
+    float *out_loss;
+    const CtaRec *recs;  // single GPU: the header scalars come from the CTA records
+    int nparts;
+    const PeerArgs *peer;  // multi GPU: from the scalar words of every peer's slot
+    size_t peer_slot_off;
+    int peer_timeout;
+    long long *trace;
+};
+
+// The tail of one 32-bin block, run by one warp (lane = bin).  s = S_cens + S_event, e = S_event (fixed point),
+// m = event count of the lane's bin.  Data flow, no barrier: the block waits for the A words of the later blocks and
+// for the G words of the earlier ones, each lane polling the words it needs.  (A __syncwarp() follows every section
+// in which the lanes may drift apart -- polls, bin_terms: a shuffle on a diverged warp takes a ~100-cycle slow path
+// per instruction, microseconds for a scan.)
+__device__ __noinline__ void tail_block(const TailArgs &a, int blk, int lane, long long s, long long e, int m) {
+    TailSlot *slots = a.slots;
+    const int nblk = a.nb >> 5;
+    const bool tr = a.trace != nullptr && blk == 0 && lane == 0;
+    // ---- D: suffix sums (integers).  Publish the block total, look back over the later blocks.
+    const long long sfx = suffix_scan(s, lane);
+    const unsigned ne = __reduce_add_sync(FULL, (unsigned)m), nt = __reduce_add_sync(FULL, m > 0 ? 1u : 0u);
+    if (lane == 0) {
+        st_slot(&slots[blk].A, (unsigned long long)sfx | SLOT_FLAG);
+        st_slot(&slots[blk].C, ((unsigned long long)ne << 32) | nt | SLOT_FLAG);
+    }
+    long long off = 0;
+    for (int k = blk + 1 + lane; k < nblk; k += 32) off += (long long)wait_flagged(&slots[k].A);
+    __syncwarp();
+    off = warp_sum(off);
+    if (tr) a.trace[7] = global_timer_ns();
+    // ---- per-bin terms, level-1 scans, publish the block totals
+    const BinTerms bt = bin_terms(off + sfx, e, m, a.efron);
+    __syncwarp();
+    const double gi = hs_scan(bt.G, lane), ti = hs_scan(bt.T, lane);
+    if (lane == 31) {
+        st_slot(&slots[blk].G, (unsigned long long)__double_as_longlong(gi));
+        st_slot(&slots[blk].T, (unsigned long long)__double_as_longlong(ti));
+    }
+    if (tr) a.trace[8] = global_timer_ns();
+    // ---- P: look back over the earlier blocks (levels 2 and 3 of the canonical tree)
+    const int sblk = blk >> 5, pos = blk & 31;
+    double run_g = 0.0;
+    for (int s2 = 0; s2 < sblk; ++s2) {
+        const double v = wait_double(&slots[32 * s2 + lane].G);
+        __syncwarp();
+        run_g += __shfl_sync(FULL, hs_scan(v, lane), 31);
+    }
+    double vg = 0.0;  // (zero from this block on: the inclusive scan at a lane only depends on the lanes before it)
+    if (lane < pos) vg = wait_double(&slots[32 * sblk + lane].G);
+    __syncwarp();
+    const double ig = hs_scan(vg, lane);
+    const double ex = __shfl_sync(FULL, ig, pos > 0 ? pos - 1 : 0);
+    const double P = (run_g + (pos > 0 ? ex : 0.0)) + gi;
+    a.table[32 * blk + lane] = make_float2((float)P, (float)bt.F);
+    if (tr) a.trace[9] = global_timer_ns();
+}
+
+// Loss and header, by a warp that owns no block: waits for the T totals and the event counts of all blocks, forms the
+// total of T along the canonical tree, writes the header.
+__device__ __noinline__ void tail_header(const TailArgs &a, int lane) {
+    TailSlot *slots = a.slots;
+    const int nblk = a.nb >> 5;
+    HeaderIn h;
+    if (a.peer == nullptr) {
+        double se = 0.0, sw = 0.0;
+        float mx = -INFINITY;
+        unsigned fl = 0;
+        for (int c = lane; c < a.nparts; c += 32) {
+            const CtaRec *rp = a.recs + c;
+            se += __ldcg(&rp->sum_ev_eta); sw += __ldcg(&rp->sum_w); mx = fmaxf(mx, __ldcg(&rp->max_eta));
+            fl |= __ldcg(&rp->flags);
+        }
+        se = warp_sum(se); sw = warp_sum(sw); mx = warp_max(mx); fl = warp_or(fl);
+        h.sum_ev_eta_q = __double2ll_rn(se * ETA_SCALE);
+        h.n_not_binnable = (fl & B200SURV_COXF_NOT_BINNABLE) ? 1 : 0;
+        h.sum_w_ceil = (long long)fmin(ceil(sw), 9.0e18);
+        h.n_bad_time = (fl & B200SURV_COXF_BAD_TIME) ? 1 : 0;
+        h.max_eta = mx;
+    } else {
+        long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        float mx = -INFINITY;
+        if (lane < a.peer->world && !a.peer_timeout) {
+            const long long *ps = reinterpret_cast<const long long *>(a.peer->buf[lane] + a.peer_slot_off) + 3 * (size_t)a.nb;
+            w0 = ld_relaxed_sys_s64(ps); w1 = ld_relaxed_sys_s64(ps + 1); w2 = ld_relaxed_sys_s64(ps + 2);
+            w3 = ld_relaxed_sys_s64(ps + 3);
+            mx = ld_relaxed_sys_f32(reinterpret_cast<const float *>(ps + 4));
+        }
+        h.sum_ev_eta_q = warp_sum(w0); h.n_not_binnable = warp_sum(w1); h.sum_w_ceil = warp_sum(w2);
+        h.n_bad_time = warp_sum(w3);
+        h.max_eta = a.peer_timeout ? 0.f : warp_max(mx);
+    }
+    long long cnt_e = 0, cnt_t = 0;
+    for (int k = lane; k < nblk; k += 32) {
+        const unsigned long long c = wait_flagged(&slots[k].C);
+        cnt_e += (long long)(c >> 32); cnt_t += (long long)(c & 0xffffffffull);
+    }
+    __syncwarp();
+    cnt_e = warp_sum(cnt_e); cnt_t = warp_sum(cnt_t);
+    double run_t = 0.0;
+    for (int s2 = 0; 32 * s2 < nblk; ++s2) {
+        const int k = 32 * s2 + lane;
+        double v = 0.0;
+        if (k < nblk) v = wait_double(&slots[k].T);
+        __syncwarp();
+        run_t += __shfl_sync(FULL, hs_scan(v, lane), min(31, nblk - 1 - 32 * s2));
+    }
+    h.n_events = cnt_e; h.n_times = cnt_t; h.T = run_t; h.peer_timeout = a.peer_timeout;
+    if (lane == 0) {
+        write_header(h, a.efron, a.reduction, a.shift, a.nb, a.hdr, a.out_loss);
+        if (a.trace != nullptr) a.trace[10] = global_timer_ns();
+    }
+}
+
+template <bool PEER>
 __global__ void __launch_bounds__(P1_THREADS, 1)
 cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__ time,
                      const uint8_t *__restrict__ event, int64_t n, int nb, float shift, int vec_ok,
-                     unsigned char *__restrict__ partial, CtaRec *__restrict__ recs, FusedArgs fa, int use_tma,
-                     PeerArgs pa) {
+                     unsigned char *__restrict__ partial, CtaRec *__restrict__ recs, const FusedArgs fa, int p1_mode,
+                     const __grid_constant__ PeerArgs pa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double shd[33];
-    __shared__ int shi[36];
     cg::grid_group grid = cg::this_grid();
-    const int cta = blockIdx.x, nctas = gridDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (PEER && cta == 0 && t == 0) *pa.status = 0;  // set again (after a grid barrier) if a peer never arrives
-#define PEER_TRACE(i)                                                                          \
-    do {                                                                                       \
-        if (PEER && pa.trace != nullptr && cta == 0 && t == 0) pa.trace[i] = global_timer_ns(); \
+    const int cta = blockIdx.x, G = gridDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int nblk = nb >> 5, bpc = (nblk + G - 1) / G;  // 32-bin blocks per CTA (host: bpc <= 32)
+    const int blk0 = cta * bpc, nparts = fa.nparts;
+#define TRACE(i)                                                                          \
+    do {                                                                                  \
+        if (fa.trace != nullptr && cta == 0 && t == 0) fa.trace[i] = global_timer_ns();  \
     } while (0)
-    PEER_TRACE(0);
-    if (use_tma == 2)
-        pass1_body_ring(log_hz, time, event, n, nb, shift, partial, recs, cta, nctas, smem_raw);
-    else if (use_tma == 1)
-        pass1_body_tma(log_hz, time, event, n, nb, shift, partial, recs, cta, nctas, smem_raw);
-    else
-        pass1_body(log_hz, time, event, nullptr, n, nb, shift, vec_ok, partial, recs, 0, cta, nctas,
-                   reinterpret_cast<unsigned *>(smem_raw));
-    PEER_TRACE(1);
+    TRACE(0);
+    if (t < bpc && blk0 + t < nblk) {  // look-back slots of this CTA's blocks (ordered by the grid barrier)
+        TailSlot *sl = fa.slots + blk0 + t;
+        sl->A = 0; sl->C = 0; sl->G = SLOT_EMPTY; sl->T = SLOT_EMPTY;
+    }
+    if (PEER && cta == 0 && t == 0) *pa.status = 0;  // set again if a peer never arrives
+    if (cta < nparts) {
+        if (p1_mode == 2)
+            pass1_body_ring(log_hz, time, event, n, nb, shift, partial, recs, cta, nparts, smem_raw);
+        else if (p1_mode == 1)
+            pass1_body_tma(log_hz, time, event, n, nb, shift, partial, recs, cta, nparts, smem_raw);
+        else
+            pass1_body(log_hz, time, event, nullptr, n, nb, shift, vec_ok, partial, recs, 0, cta, nparts,
+                       reinterpret_cast<unsigned *>(smem_raw));
+    }
+    TRACE(1);
     grid.sync();
-    PEER_TRACE(2);
+    TRACE(2);
 
-    // ---- phase 2: exact reduction of the partials, bins [b0, b1) of this CTA, one warp per bin
-    long long *bs = fa.bins;
-    const size_t slot_off = PEER ? PEER_FLAGS_BYTES + (size_t)(pa.epoch & 1u) * peer_slot_bytes(nb) : 0;
-    const int nbpc = (nb + nctas - 1) / nctas;
+    // ---- exact reduction of the partials for this CTA's blocks: lanes along the 32 bins of a block (contiguous
+    // 256-byte reads of every partial record), warps along the records, then a cross-warp sum through shared
+    // memory (the histogram storage is free again); warp j keeps the sums of block blk0 + j
+    long long my_c = 0, my_e = 0;
+    int my_m = 0;
     {
-        // with peers the rank-local sums go to this rank's slot of the peer buffer; fa.bins receives the totals
-        long long *bs = PEER ? reinterpret_cast<long long *>(pa.buf[pa.rank] + slot_off) : fa.bins;
-        float *bmax = PEER ? reinterpret_cast<float *>(bs + 3 * (size_t)nb + 4) : fa.bins_max;
-        const int b0 = cta * nbpc, b1 = min(nb, b0 + nbpc);
-        const bool wide = nctas >= 32 && nb >= 1024;  // (the shared histogram storage, free again, holds 20 KB)
-        if (wide) {
-            // lanes along the bins (contiguous 256-byte reads of every partial record), warps along the records,
-            // then a cross-warp sum through shared memory
-            unsigned long long *s_c = reinterpret_cast<unsigned long long *>(smem_raw);  // [32 warps][32 bins]
-            unsigned long long *s_e = s_c + 1024;
-            unsigned *s_mm = reinterpret_cast<unsigned *>(s_e + 1024);
-            for (int g0 = b0; g0 < b1; g0 += 32) {
-                const int b = g0 + lane;
-                const bool bin_ok = b < b1;
-                unsigned long long vc[RED_MAX_ITERS], ve[RED_MAX_ITERS];
-                unsigned vm[RED_MAX_ITERS];
-#pragma unroll
-                for (int k = 0; k < RED_MAX_ITERS; ++k) {
-                    const int c = warp + 32 * k;
-                    const bool in = bin_ok && c < nctas;
-                    const unsigned char *pc = partial + (size_t)(in ? c : 0) * PARTIAL_BYTES_PER_BIN * (size_t)nb;
-                    vc[k] = in ? __ldcg(reinterpret_cast<const unsigned long long *>(pc) + b) : 0ull;
-                    ve[k] = in ? __ldcg(reinterpret_cast<const unsigned long long *>(pc) + nb + b) : 0ull;
-                    vm[k] = in ? __ldcg(reinterpret_cast<const unsigned *>(pc + 16 * (size_t)nb) + b) : 0u;
-                }
-                unsigned long long sc = 0, se = 0;
-                unsigned m = 0;
-#pragma unroll
-                for (int k = 0; k < RED_MAX_ITERS; ++k) { sc += vc[k]; se += ve[k]; m += vm[k]; }
-                if (g0 != b0) __syncthreads();  // the previous group's sums have been read
-                s_c[t] = sc; s_e[t] = se; s_mm[t] = m;
-                __syncthreads();
-                if (warp < 3 && bin_ok) {  // warp 0: censored sums, warp 1: event sums, warp 2: event counts
-                    long long tot = 0;
-                    if (warp == 0) { for (int w = 0; w < 32; ++w) tot += (long long)s_c[w * 32 + lane]; }
-                    else if (warp == 1) { for (int w = 0; w < 32; ++w) tot += (long long)s_e[w * 32 + lane]; }
-                    else { for (int w = 0; w < 32; ++w) tot += (long long)s_mm[w * 32 + lane]; }
-                    bs[(size_t)warp * nb + b] = tot;
-                    fa.tgf[(size_t)warp * nb + b] = 0.0;
-                }
-            }
-        }
-        for (int b = b0 + warp; b < b1 && !wide; b += P1_THREADS / 32) {
+        unsigned long long *s_c = reinterpret_cast<unsigned long long *>(smem_raw);  // [32 warps][32 bins]
+        unsigned long long *s_e = s_c + 1024;
+        unsigned *s_mm = reinterpret_cast<unsigned *>(s_e + 1024);
+        for (int j = 0; j < bpc && blk0 + j < nblk; ++j) {
+            const int b = 32 * (blk0 + j) + lane;
             unsigned long long vc[RED_MAX_ITERS], ve[RED_MAX_ITERS];
             unsigned vm[RED_MAX_ITERS];
 #pragma unroll
-            for (int k = 0; k < RED_MAX_ITERS; ++k) {  // all loads in flight together (nctas <= 160)
-                const int c = lane + 32 * k;
-                const bool in = c < nctas;
+            for (int k = 0; k < RED_MAX_ITERS; ++k) {
+                const int c = warp + 32 * k;
+                const bool in = c < nparts;
                 const unsigned char *pc = partial + (size_t)(in ? c : 0) * PARTIAL_BYTES_PER_BIN * (size_t)nb;
                 vc[k] = in ? __ldcg(reinterpret_cast<const unsigned long long *>(pc) + b) : 0ull;
                 ve[k] = in ? __ldcg(reinterpret_cast<const unsigned long long *>(pc) + nb + b) : 0ull;
@@ -1006,46 +961,62 @@ cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__
             unsigned m = 0;
 #pragma unroll
             for (int k = 0; k < RED_MAX_ITERS; ++k) { sc += vc[k]; se += ve[k]; m += vm[k]; }
-            const long long tc = warp_sum((long long)sc), te = warp_sum((long long)se), tm = warp_sum((long long)m);
-            if (lane == 0) {
-                bs[b] = tc; bs[nb + b] = te; bs[2 * nb + b] = tm;
-                fa.tgf[b] = 0.0; fa.tgf[nb + b] = 0.0; fa.tgf[2 * nb + b] = 0.0;
+            if (j) __syncthreads();  // the previous block's sums have been read
+            s_c[t] = sc; s_e[t] = se; s_mm[t] = m;
+            __syncthreads();
+            if (warp == j) {
+                unsigned long long c0 = 0, c1 = 0, e0 = 0, e1 = 0;
+                unsigned m0 = 0, m1 = 0;
+#pragma unroll 8
+                for (int w = 0; w < 32; w += 2) {
+                    c0 += s_c[w * 32 + lane]; c1 += s_c[w * 32 + 32 + lane];
+                    e0 += s_e[w * 32 + lane]; e1 += s_e[w * 32 + 32 + lane];
+                    m0 += s_mm[w * 32 + lane]; m1 += s_mm[w * 32 + 32 + lane];
+                }
+                my_c = (long long)(c0 + c1); my_e = (long long)(e0 + e1); my_m = (int)(m0 + m1);
             }
         }
-        if (cta == 0 && warp == P1_THREADS / 32 - 1) {
+    }
+    TRACE(3);
+    const bool has_blk = warp < bpc && blk0 + warp < nblk;
+    const int blk = blk0 + warp;
+    const size_t slot_off = PEER ? PEER_FLAGS_BYTES + (size_t)(pa.epoch & 1u) * peer_slot_bytes(nb) : 0;
+    int peer_timeout = 0;
+    if constexpr (PEER) {
+        // ---- publish this rank's sums, wait for every peer, pull and add their sums for this warp's block
+        __shared__ int s_timeout;
+        long long *own = reinterpret_cast<long long *>(pa.buf[pa.rank] + slot_off);
+        if (has_blk) {
+            const int b = 32 * blk + lane;
+            own[b] = my_c; own[nb + b] = my_e; own[2 * (size_t)nb + b] = my_m;
+        }
+        if (cta == G - 1 && warp == P1_THREADS / 32 - 2) {  // the four scalar words and the maximum of this rank
             double se = 0.0, sw = 0.0;
             float mx = -INFINITY;
             unsigned fl = 0;
-            for (int c = lane; c < nctas; c += 32) {
+            for (int c = lane; c < nparts; c += 32) {
                 const CtaRec *rp = recs + c;
                 se += __ldcg(&rp->sum_ev_eta); sw += __ldcg(&rp->sum_w); mx = fmaxf(mx, __ldcg(&rp->max_eta));
                 fl |= __ldcg(&rp->flags);
             }
             se = warp_sum(se); sw = warp_sum(sw); mx = warp_max(mx); fl = warp_or(fl);
             if (lane == 0) {
-                bs[3 * (size_t)nb + 0] = __double2ll_rn(se * ETA_SCALE);
-                bs[3 * (size_t)nb + 1] = (fl & B200SURV_COXF_NOT_BINNABLE) ? 1 : 0;
-                bs[3 * (size_t)nb + 2] = (long long)fmin(ceil(sw), 9.0e18);
-                bs[3 * (size_t)nb + 3] = (fl & B200SURV_COXF_BAD_TIME) ? 1 : 0;
-                bmax[0] = mx;
-                bmax[1] = -1.f;
+                own[3 * (size_t)nb + 0] = __double2ll_rn(se * ETA_SCALE);
+                own[3 * (size_t)nb + 1] = (fl & B200SURV_COXF_NOT_BINNABLE) ? 1 : 0;
+                own[3 * (size_t)nb + 2] = (long long)fmin(ceil(sw), 9.0e18);
+                own[3 * (size_t)nb + 3] = (fl & B200SURV_COXF_BAD_TIME) ? 1 : 0;
+                float *bmax = reinterpret_cast<float *>(own + 3 * (size_t)nb + 4);
+                bmax[0] = mx; bmax[1] = -1.f;
             }
         }
-    }
-    PEER_TRACE(3);
-    grid.sync();
-    PEER_TRACE(4);
-
-    if constexpr (PEER) {
-        // ---- phase 2x: publish, wait for every peer, pull and add their sums for this CTA's bin slice
-        __shared__ int s_timeout;
         if (t == 0) s_timeout = 0;
+        grid.sync();  // the whole slot is written
+        TRACE(4);
         if (cta == 0 && t < pa.world) {
-            __threadfence_system();  // the slot written by all CTAs (ordered by the grid barrier) before the flag
+            __threadfence_system();
             st_release_sys_u32(reinterpret_cast<unsigned *>(pa.buf[t]) + pa.rank * PEER_FLAG_STRIDE, pa.epoch);
         }
-        __syncthreads();
-        PEER_TRACE(5);
+        TRACE(5);
         if (t < pa.world) {
             const unsigned *f = reinterpret_cast<const unsigned *>(pa.buf[pa.rank]) + t * PEER_FLAG_STRIDE;
             const long long t0 = global_timer_ns();
@@ -1055,212 +1026,48 @@ cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__
             }
         }
         __syncthreads();
-        PEER_TRACE(6);
-        if (s_timeout) {  // a peer never arrived: flag it and leave an empty cohort behind (no stale sums)
-            if (t == 0) atomicExch(pa.status, 1);
-            const int b0 = cta * nbpc, b1 = min(nb, b0 + nbpc);
-            for (int b = b0 + t; b < b1; b += P1_THREADS) { bs[b] = 0; bs[nb + b] = 0; bs[2 * (size_t)nb + b] = 0; }
-            if (cta == nctas - 1 && t < 4) bs[3 * (size_t)nb + t] = 0;
-            if (cta == nctas - 1 && t == 4) { fa.bins_max[0] = 0.f; fa.bins_max[1] = -1.f; }
-        } else {
-            const int b0 = cta * nbpc, b1 = min(nb, b0 + nbpc);
-            const int cnt = max(b1 - b0, 0);
-            for (int i = t; i < 3 * cnt; i += P1_THREADS) {
-                const size_t idx = (size_t)(i / cnt) * nb + b0 + (i % cnt);
-                long long v[PEER_MAX_WORLD];
+        peer_timeout = s_timeout;
+        if (peer_timeout && t == 0) atomicExch(pa.status, 1);
+        if (has_blk) {
+            my_c = 0; my_e = 0;
+            long long mm = 0;  // a peer that never arrived leaves an empty cohort behind (no stale sums)
+            if (!peer_timeout) {
+                const size_t b = 32 * (size_t)blk + lane;
+                long long vc[PEER_MAX_WORLD], ve[PEER_MAX_WORLD], vm[PEER_MAX_WORLD];
 #pragma unroll
-                for (int p = 0; p < PEER_MAX_WORLD; ++p)  // all peers' loads in flight together
-                    v[p] = p < pa.world ? ld_relaxed_sys_s64(reinterpret_cast<const long long *>(pa.buf[p] + slot_off) + idx) : 0ll;
-                long long s = 0;
-#pragma unroll
-                for (int p = 0; p < PEER_MAX_WORLD; ++p) s += v[p];
-                bs[idx] = s;
-            }
-            if (cta == nctas - 1 && t >= P1_THREADS - 5) {  // the four scalar words and the maximum
-                const int k = t - (P1_THREADS - 5);
-                if (k < 4) {
-                    long long s = 0;
-                    for (int p = 0; p < pa.world; ++p)
-                        s += ld_relaxed_sys_s64(reinterpret_cast<const long long *>(pa.buf[p] + slot_off) + 3 * (size_t)nb + k);
-                    bs[3 * (size_t)nb + k] = s;
-                } else {
-                    float mx = -INFINITY;
-                    for (int p = 0; p < pa.world; ++p)
-                        mx = fmaxf(mx, ld_relaxed_sys_f32(reinterpret_cast<const float *>(
-                                           reinterpret_cast<const long long *>(pa.buf[p] + slot_off) + 3 * (size_t)nb + 4)));
-                    fa.bins_max[0] = mx;
-                    fa.bins_max[1] = -1.f;
+                for (int p = 0; p < PEER_MAX_WORLD; ++p) {  // all peers' loads in flight together
+                    const long long *ps = reinterpret_cast<const long long *>(pa.buf[p < pa.world ? p : 0] + slot_off);
+                    vc[p] = p < pa.world ? ld_relaxed_sys_s64(ps + b) : 0ll;
+                    ve[p] = p < pa.world ? ld_relaxed_sys_s64(ps + nb + b) : 0ll;
+                    vm[p] = p < pa.world ? ld_relaxed_sys_s64(ps + 2 * (size_t)nb + b) : 0ll;
                 }
+#pragma unroll
+                for (int p = 0; p < PEER_MAX_WORLD; ++p) { my_c += vc[p]; my_e += ve[p]; mm += vm[p]; }
             }
+            my_m = (int)mm;
         }
-        grid.sync();
-        PEER_TRACE(7);
+        TRACE(6);
     }
 
-    // ---- phase 3: redundant suffix scan into shared memory (reuses the histogram storage: 20 B/bin)
-    double *sD = reinterpret_cast<double *>(smem_raw);
-    double *s_rm = sD + nb;
-    int *s_m = reinterpret_cast<int *>(s_rm + nb);
-    // s_cp[p], p = nb-1-b (scan order): exclusive prefix of the Efron chunk counts ceil(m/EF_CHUNK); [nb] = total
-    // (the fused launch allocates 24 B/bin + 16)
-    int *s_cp = s_m + nb;
-    const bool efron = fa.ties == B200SURV_TIES_EFRON;
-    const bool solo = nctas > 1;
-    const bool skip_efron = !efron || (solo && cta == 0);
-    const int per = nb / P1_THREADS > 0 ? nb / P1_THREADS : 1;
-    const int hi_b = nb - t * per;
-    int n_events, n_times;
-    {
-        long long rc[MAXPER], re[MAXPER], rmv[MAXPER];
-#pragma unroll
-        for (int k = 0; k < MAXPER; ++k) {
-            const int b = hi_b - 1 - k;
-            const bool in = (k < per) && (b >= 0);
-            rc[k] = in ? __ldcg(bs + b) : 0ll;
-            re[k] = in ? __ldcg(bs + nb + b) : 0ll;
-            rmv[k] = in ? __ldcg(bs + 2 * nb + b) : 0ll;
-        }
-        double sv[MAXPER];
-        double loc = 0.0;
-        int locm = 0, net = 0, locc = 0;
-#pragma unroll
-        for (int k = 0; k < MAXPER; ++k) {
-            sv[k] = ((double)(unsigned long long)rc[k] + (double)(unsigned long long)re[k]) * FIX_INV;
-            loc += sv[k];
-            locm += (int)rmv[k];
-            net += rmv[k] > 0 ? 1 : 0;
-            locc += ((int)rmv[k] + EF_CHUNK - 1) / EF_CHUNK;
-        }
-        const BinScan sc = block_bin_scan(loc, locc, locm, net, shd, shi);
-        n_events = sc.n_events; n_times = sc.n_times;
-        double run = sc.run;
-        int crun = sc.crun;
-#pragma unroll
-        for (int k = 0; k < MAXPER; ++k) {
-            const int b = hi_b - 1 - k;
-            if (k < per && b >= 0) {
-                run += sv[k];
-                const int m = (int)rmv[k];
-                sD[b] = run;
-                s_m[b] = m;
-                if (!skip_efron) {  // (CTA 0 of a multi-CTA grid takes no Efron work: it is on the critical path)
-                    s_rm[b] = m > 0 ? ((double)(unsigned long long)re[k] * FIX_INV) / (run * (double)m) : 0.0;
-                    s_cp[t * per + k] = crun;
-                    crun += (m + EF_CHUNK - 1) / EF_CHUNK;
-                }
-            }
-        }
-        if (t == 0) s_cp[nb] = sc.n_chunks;
+    // ---- the O(nbins) tail: one warp per block (the first warps of the CTA), the header by the last warp of the CTA
+    // that owns the last block; no further barrier
+    const bool is_hdr = cta == (nblk - 1) / bpc && warp == P1_THREADS / 32 - 1;
+    if (has_blk || is_hdr) {
+        TailArgs ta;
+        ta.slots = fa.slots; ta.nb = nb; ta.efron = fa.ties == B200SURV_TIES_EFRON ? 1 : 0; ta.reduction = fa.reduction;
+        ta.shift = shift;
+        ta.table = reinterpret_cast<float2 *>(fa.state + sizeof(b200surv_cox_header));
+        ta.hdr = reinterpret_cast<b200surv_cox_header *>(fa.state);
+        ta.out_loss = fa.out_loss;
+        ta.recs = recs; ta.nparts = nparts;
+        ta.peer = PEER ? &pa : nullptr; ta.peer_slot_off = slot_off; ta.peer_timeout = peer_timeout;
+        ta.trace = fa.trace;
+        if (has_blk) tail_block(ta, blk, lane, my_c + my_e, my_e, my_m);
+        else tail_header(ta, lane);
     }
-    __syncthreads();
-    // CTA 0 finishes alone after the last grid barrier; while the other CTAs work through the Efron terms it prepares
-    // what does not depend on them (m log D and 1/D of its bins, the scalar words)
-    const int lo_b = t * per;
-    double pre_ml[MAXPER], pre_inv[MAXPER];
-    long long sc_eta = 0, sc_nb = 0, sc_sw = 0, sc_bt = 0;
-    float sc_mx = 0.f;
-    if (cta == 0) {
-#pragma unroll
-        for (int k = 0; k < MAXPER; ++k) {
-            const int b = lo_b + k;
-            const bool in = (k < per) && (b < nb) && s_m[b] > 0;
-            const double D = in ? sD[b] : 1.0;
-            pre_inv[k] = 1.0 / D;
-            pre_ml[k] = in ? (double)s_m[b] * log(D) : 0.0;
-        }
-        if (t == 0) {
-            sc_eta = __ldcg(bs + 3 * (size_t)nb); sc_nb = __ldcg(bs + 3 * (size_t)nb + 1);
-            sc_sw = __ldcg(bs + 3 * (size_t)nb + 2); sc_bt = __ldcg(bs + 3 * (size_t)nb + 3);
-            sc_mx = __ldcg(fa.bins_max);
-        }
-    }
-    if (PEER && pa.trace != nullptr && cta == 1 && t == 0) pa.trace[13] = global_timer_ns();
-    if (efron && !(solo && cta == 0)) {
-        const int wc = solo ? nctas - 1 : 1, ci = solo ? cta - 1 : 0;
-        efron_chunks(
-            s_cp, nb, warp * wc + ci, wc * (P1_THREADS / 32), lane, [&](int b) { return s_m[b]; },
-            [&](int b) { return s_rm[b]; }, reinterpret_cast<long long *>(fa.tgf));
-    }
-    if (PEER && pa.trace != nullptr && cta == 1 && t == 0) pa.trace[14] = global_timer_ns();
-    if (cta != 0) { grid.sync(); return; }
-
-    // ---- phase 4 (CTA 0): P = prefix(G), loss, header, (P,F) table
-    // The finish is ~500 instructions that run once per launch on one SM: executed cold it is bound by instruction
-    // fetch (every 128-byte line a serial L2 round trip; measured 9 us for ~2 us of work).  So CTA 0, which has
-    // nothing else to do while the other CTAs work through the Efron terms, runs it twice: a rehearsal on whatever the
-    // accumulators hold (stores suppressed) that pulls the code into the SM's instruction cache, then, after the
-    // grid barrier, the real pass.
-    b200surv_cox_header *hdr = reinterpret_cast<b200surv_cox_header *>(fa.state);
-    float2 *table = reinterpret_cast<float2 *>(fa.state + sizeof(b200surv_cox_header));
-    const int npass = solo ? 2 : 1;
-#pragma unroll 1
-    for (int pass = 0; pass < npass; ++pass) {
-    const bool live = pass == npass - 1;
-    if (live) {
-        PEER_TRACE(8);
-        grid.sync();
-        PEER_TRACE(9);
-    }
-    double tv[MAXPER], gv[MAXPER], fv[MAXPER];
-#pragma unroll
-    for (int k = 0; k < MAXPER; ++k) {
-        const int b = lo_b + k;
-        const bool in = (k < per) && (b < nb) && s_m[b] > 0;
-        const long long *acc = reinterpret_cast<const long long *>(fa.tgf);
-        const long long at = in ? __ldcg(acc + b) : 0ll, ag = in ? __ldcg(acc + nb + b) : 0ll,
-                        af = in ? __ldcg(acc + 2 * nb + b) : 0ll;
-        tv[k] = gv[k] = fv[k] = 0.0;
-        if (in) {
-            const double invD = pre_inv[k], m = (double)s_m[b];
-            tv[k] = (double)at * EF_INV + pre_ml[k];
-            gv[k] = efron ? (double)ag * EF_INV * invD : m * invD;
-            fv[k] = (double)af * EF_INV * invD;
-        }
-    }
-    double tsum = 0.0, gsum = 0.0;
-#pragma unroll
-    for (int k = 0; k < MAXPER; ++k) { tsum += tv[k]; gsum += gv[k]; }
-    if (PEER && pa.trace != nullptr && t == 0) pa.trace[11] = global_timer_ns() + (tsum > 1e300 ? 1 : 0);
-    __shared__ double shd2[33];
-    double T;
-    double run = block_exscan_and_sum(gsum, tsum, shd, shd2, &T);
-    if (PEER && pa.trace != nullptr && t == 0) pa.trace[12] = global_timer_ns() + (run > 1e300 ? 1 : 0);
-    // the rehearsal stores into shared scratch (the D array is no longer needed; shd2 after its last read)
-    float2 *table_w = live ? table : reinterpret_cast<float2 *>(sD);
-    b200surv_cox_header *hdr_w = live ? hdr : reinterpret_cast<b200surv_cox_header *>(shd2);
-    float *loss_w = live ? fa.out_loss : reinterpret_cast<float *>(shd2 + 16);
-#pragma unroll
-    for (int k = 0; k < MAXPER; ++k) {
-        const int b = lo_b + k;
-        if (k < per && b < nb) { run += gv[k]; table_w[b] = make_float2((float)run, (float)fv[k]); }
-    }
-    if (t == 0) {
-        const double sum_ev_eta = (double)sc_eta * ETA_INV;
-        const double pll = sum_ev_eta - (T + (double)n_events * (double)shift);
-        double norm = 1.0;
-        if (fa.reduction == B200SURV_REDUCE_MEAN_EVENTS) norm = (double)n_events;
-        else if (fa.reduction == B200SURV_REDUCE_MEAN_TERMS) norm = efron ? (double)n_times : (double)n_events;
-        unsigned flags = 0;
-        if (sc_nb != 0) flags |= B200SURV_COXF_NOT_BINNABLE;
-        if (sc_bt != 0) flags |= B200SURV_COXF_BAD_TIME;
-        const float mx = sc_mx;
-        const double sumw = (double)sc_sw;
-        if (!(mx - shift <= SHIFT_HI) || !(mx - shift >= SHIFT_LO) || sumw >= SUMW_LIMIT) flags |= B200SURV_COXF_EXP_RANGE;
-        if (PEER && __ldcg(pa.status) != 0) flags |= B200SURV_COXF_PEER_TIMEOUT;
-        float loss = 0.f, scale = 0.f;
-        if (n_events > 0) { loss = (float)(-pll / norm); scale = (float)(-1.0 / norm); }
-        if (flags) { loss = __int_as_float(0x7fc00000); scale = loss; }
-        hdr_w->flags = flags; hdr_w->mode = B200SURV_COX_BINNED; hdr_w->loss = loss; hdr_w->scale = scale;
-        hdr_w->shift = shift; hdr_w->max_log_hz = mx; hdr_w->max_time = -1.f;
-        hdr_w->nbins = nb; hdr_w->n_events = n_events; hdr_w->n_event_times = n_times; hdr_w->pll = pll;
-        hdr_w->reserved = 0;
-        loss_w[0] = loss;
-        PEER_TRACE(10);
-    }
-    __syncthreads();  // rehearsal scratch (shd2) is reused by the live pass
-    }
-#undef PEER_TRACE
+#undef TRACE
 }
+
 
 // ================================================================ K4: pass 2 (backward)
 __device__ __forceinline__ float p2_row(float eta, float t, bool ev, float c2, float k, const float2 *tab, int nb) {
@@ -1343,8 +1150,7 @@ cox_binned_bwd(const float *__restrict__ grad_out, const unsigned char *__restri
 // ================================================================ host-side layout
 struct BinnedLayout {
     int nctas;  // pass-1 CTAs per segment
-    size_t off_partial, off_recs, off_tickets, off_bins, off_bins_max, off_D, off_rm, off_tgf, off_totals, off_big,
-        total;
+    size_t off_status, off_trace, off_slots, off_partial, off_recs, off_bins, off_bins_max, off_scr_g, off_scr_f, total;
 };
 
 BinnedLayout binned_layout(int64_t n, int64_t n_seg, int nb) {
@@ -1364,32 +1170,17 @@ BinnedLayout binned_layout(int64_t n, int64_t n_seg, int nb) {
     L.nctas = (int)c;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-    // the tickets come first: the caller-visible contract is that a fresh workspace starts zero-filled
-    // in its first 256-byte-aligned block of 2 * n_seg words (see cox_binned_workspace_init_bytes)
-    L.off_tickets = take((size_t)n_seg * 2 * sizeof(unsigned));
+    L.off_status = take(sizeof(int));
+    L.off_trace = take(16 * sizeof(long long));
+    L.off_slots = take((size_t)(nb / 32) * sizeof(TailSlot));
     L.off_partial = take((size_t)n_seg * L.nctas * PARTIAL_BYTES_PER_BIN * nb);
     L.off_recs = take((size_t)n_seg * L.nctas * sizeof(CtaRec));
     L.off_bins = take((size_t)n_seg * (3 * (size_t)nb + 4) * sizeof(long long));
     L.off_bins_max = take((size_t)n_seg * 2 * sizeof(float));
-    L.off_D = take((size_t)n_seg * nb * sizeof(double));
-    L.off_rm = take((size_t)n_seg * nb * sizeof(double));
-    L.off_tgf = take((size_t)n_seg * 3 * nb * sizeof(double));
-    L.off_totals = take((size_t)n_seg * 2 * sizeof(long long));
-    L.off_big = take((size_t)n_seg * (nb + 1) * sizeof(int));
+    L.off_scr_g = take((size_t)n_seg * nb * sizeof(double));
+    L.off_scr_f = take((size_t)n_seg * nb * sizeof(double));
     L.total = o;
     return L;
-}
-
-ScanBase make_scan_base(const BinnedLayout &L, unsigned char *w8, int64_t n_seg) {
-    ScanBase s;
-    s.D = reinterpret_cast<double *>(w8 + L.off_D);
-    s.rm = reinterpret_cast<double *>(w8 + L.off_rm);
-    s.tgf = reinterpret_cast<double *>(w8 + L.off_tgf);
-    s.totals = reinterpret_cast<long long *>(w8 + L.off_totals);
-    s.big = reinterpret_cast<int *>(w8 + L.off_big);
-    s.tickets_k2 = reinterpret_cast<unsigned *>(w8 + L.off_tickets);
-    s.tickets_k3 = s.tickets_k2 + n_seg;
-    return s;
 }
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -1399,7 +1190,8 @@ bool coop_supported() {
     if (cached < 0) {
         int dev = 0, v = 0;
         cached = (cudaGetDevice(&dev) == cudaSuccess &&
-                  cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v) ? 1 : 0;
+                  cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v &&
+                  num_sms() >= 16) ? 1 : 0;  // (the fused kernel wants bpc < 32 blocks of bins per CTA)
     }
     return cached == 1;
 }
@@ -1414,7 +1206,7 @@ int32_t check_common(int64_t n, int64_t n_seg, int nb) {
 
 int32_t launch_pass1_reduce(const float *log_hz, const float *time, const uint8_t *event, const int64_t *seg_off,
                             int64_t n, int64_t n_seg, int nb, float shift, long long *bins, float *bins_max,
-                            const BinnedLayout &L, unsigned char *w8, int fuse_scan, cudaStream_t st) {
+                            const BinnedLayout &L, unsigned char *w8, cudaStream_t st) {
     const int vec_ok = aligned16(log_hz) && aligned16(time) && ((reinterpret_cast<uintptr_t>(event) & 3) == 0);
     const size_t smem = (size_t)nb * PARTIAL_BYTES_PER_BIN;
     static bool attr_done = false;
@@ -1425,45 +1217,68 @@ int32_t launch_pass1_reduce(const float *log_hz, const float *time, const uint8_
     }
     unsigned char *partial = w8 + L.off_partial;
     CtaRec *recs = reinterpret_cast<CtaRec *>(w8 + L.off_recs);
-    const ScanBase sb = make_scan_base(L, w8, n_seg);
     cox_binned_pass1<<<dim3(L.nctas, (unsigned)n_seg), P1_THREADS, smem, st>>>(
-        log_hz, time, event, seg_off, n, nb, shift, vec_ok, partial, recs, sb.tickets_k2);
-    const dim3 grid(nb / RED_BINS, (unsigned)n_seg);
-    if (nb <= 4 * RED_THREADS)
-        cox_binned_reduce<4><<<grid, RED_THREADS, 0, st>>>(partial, recs, L.nctas, nb, bins, bins_max, sb, fuse_scan);
-    else
-        cox_binned_reduce<8><<<grid, RED_THREADS, 0, st>>>(partial, recs, L.nctas, nb, bins, bins_max, sb, fuse_scan);
+        log_hz, time, event, seg_off, n, nb, shift, vec_ok, partial, recs);
+    cox_binned_reduce<<<dim3(nb / RED_BINS, (unsigned)n_seg), RED_THREADS, 0, st>>>(partial, recs, L.nctas, nb, bins,
+                                                                                    bins_max);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
 
-int32_t launch_items_finish(const long long *bins, const float *bins_max, int64_t n_seg, int ties, int reduction,
-                            int nb, float shift, float *out_loss, void *state, const BinnedLayout &L,
-                            unsigned char *w8, int run_scan, cudaStream_t st) {
-    const ScanBase sb = make_scan_base(L, w8, n_seg);
-    if (run_scan) {
-        if (nb <= 4 * RED_THREADS) cox_binned_scan<4><<<(unsigned)n_seg, RED_THREADS, 0, st>>>(bins, nb, sb);
-        else cox_binned_scan<8><<<(unsigned)n_seg, RED_THREADS, 0, st>>>(bins, nb, sb);
-    }
-    int gx = 1;
-    if (ties == B200SURV_TIES_EFRON) {
-        gx = n_seg == 1 ? num_sms() : (int)((num_sms() + n_seg - 1) / n_seg);
-        if (gx < 1) gx = 1;
-    }
-    const dim3 grid(gx, (unsigned)n_seg);
-    if (nb <= 4 * IT_THREADS)
-        cox_binned_items_finish<4><<<grid, IT_THREADS, 0, st>>>(bins, bins_max, nb, ties, reduction, shift, sb,
-                                                                out_loss, static_cast<unsigned char *>(state));
-    else
-        cox_binned_items_finish<8><<<grid, IT_THREADS, 0, st>>>(bins, bins_max, nb, ties, reduction, shift, sb,
-                                                                out_loss, static_cast<unsigned char *>(state));
+int32_t launch_finish(const long long *bins, const float *bins_max, int64_t n_seg, int ties, int reduction, int nb,
+                      float shift, float *out_loss, void *state, const BinnedLayout &L, unsigned char *w8,
+                      cudaStream_t st) {
+    cox_binned_finish<<<(unsigned)n_seg, IT_THREADS, 0, st>>>(
+        bins, bins_max, nb, ties, reduction, shift, reinterpret_cast<double *>(w8 + L.off_scr_g),
+        reinterpret_cast<double *>(w8 + L.off_scr_f), out_loss, static_cast<unsigned char *>(state));
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
 
+// one cooperative launch: pass 1 + reduce (+ peer exchange) + the O(nbins) tail
 int32_t launch_fused(const float *log_hz, const float *time, const uint8_t *event, int64_t n, int ties, int reduction,
                      int nb, float shift, float *out_loss, void *state, const BinnedLayout &L, unsigned char *w8,
-                     const PeerArgs *peer, cudaStream_t st);
+                     const PeerArgs *peer, cudaStream_t st) {
+    int vec_ok = aligned16(log_hz) && aligned16(time) && ((reinterpret_cast<uintptr_t>(event) & 3) == 0);
+    // Pass-1 staging, B200SURV_P1 = ring (default) | reg | tma.  Measured at 16.7M rows, forward only:
+    // per-thread cp.async ring 64.4 us, register-staged loads 70.3 us, TMA bulk ring + producer warp 78.9 us
+    // (profiles/r1_v12_p1_staging_ab.txt, r1_v10_tma_ab.txt).
+    static const int p1_env = [] {
+        const char *e = getenv("B200SURV_P1");
+        if (e && !strcmp(e, "tma")) return 1;
+        if (e && !strcmp(e, "reg")) return 0;
+        return 2;
+    }();
+    int p1_mode = (vec_ok && nb <= 4096 && n >= 4 * (int64_t)TMA_TILE) ? p1_env : 0;
+    size_t smem = p1_mode == 2 ? ring_smem_bytes(nb) : p1_mode == 1 ? tma_smem_bytes(nb) : (size_t)nb * 24 + 16;
+    if (smem < 20480) smem = 20480;  // the reduce step stages 32 x 32 x (8 + 8 + 4) bytes
+    static bool attr_done = false;
+    if (!attr_done) {
+        size_t mx = (size_t)B200SURV_COX_MAX_BINS * 24 + 16;
+        if (tma_smem_bytes(4096) > mx) mx = tma_smem_bytes(4096);
+        if (ring_smem_bytes(4096) > mx) mx = ring_smem_bytes(4096);
+        B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        attr_done = true;
+    }
+    unsigned char *partial = w8 + L.off_partial;
+    CtaRec *recs = reinterpret_cast<CtaRec *>(w8 + L.off_recs);
+    static const bool trace_on = getenv("B200SURV_PEER_TRACE") != nullptr;
+    FusedArgs fa;
+    fa.ties = ties; fa.reduction = reduction; fa.out_loss = out_loss; fa.state = static_cast<unsigned char *>(state);
+    fa.slots = reinterpret_cast<TailSlot *>(w8 + L.off_slots);
+    fa.trace = trace_on ? reinterpret_cast<long long *>(w8 + L.off_trace) : nullptr;
+    fa.nparts = L.nctas;
+    int nb_i = nb;
+    PeerArgs pa;
+    if (peer) pa = *peer; else memset(&pa, 0, sizeof(pa));
+    void *args[] = {(void *)&log_hz, (void *)&time, (void *)&event, (void *)&n, (void *)&nb_i, (void *)&shift,
+                    (void *)&vec_ok, (void *)&partial, (void *)&recs, (void *)&fa, (void *)&p1_mode, (void *)&pa};
+    const void *fn = peer ? (const void *)cox_binned_fwd_fused<true> : (const void *)cox_binned_fwd_fused<false>;
+    // the full grid always: CTAs beyond the pass-1 participants still own blocks of bins in the reduce step and the tail
+    B200_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms()), dim3(P1_THREADS), args, smem, st));
+    return B200SURV_OK;
+}
 
 }  // namespace
 
@@ -1479,8 +1294,7 @@ int32_t cox_binned_partial(const float *log_hz, const float *time, const uint8_t
     const BinnedLayout L = binned_layout(n, n_seg, nb);
     if (ws_bytes < L.total) { set_error("cox binned: workspace %zu < %zu", ws_bytes, L.total); return B200SURV_WORKSPACE_TOO_SMALL; }
     return launch_pass1_reduce(log_hz, time, event, seg_off, n, n_seg, nb, shift,
-                               reinterpret_cast<long long *>(bins_sum), bins_max, L, static_cast<unsigned char *>(ws),
-                               /*fuse_scan=*/0, st);
+                               reinterpret_cast<long long *>(bins_sum), bins_max, L, static_cast<unsigned char *>(ws), st);
 }
 
 int32_t cox_binned_finalize(const int64_t *bins_sum, const float *bins_max, int64_t n, int64_t n_seg, int ties,
@@ -1493,8 +1307,8 @@ int32_t cox_binned_finalize(const int64_t *bins_sum, const float *bins_max, int6
     const BinnedLayout L = binned_layout(n, n_seg, nb);
     if (ws_bytes < L.total) { set_error("cox binned: workspace %zu < %zu", ws_bytes, L.total); return B200SURV_WORKSPACE_TOO_SMALL; }
     if (state_bytes < cox_binned_state_bytes(n_seg, nb)) { set_error("cox binned: state buffer too small"); return B200SURV_WORKSPACE_TOO_SMALL; }
-    return launch_items_finish(reinterpret_cast<const long long *>(bins_sum), bins_max, n_seg, ties, reduction, nb,
-                               shift, out_loss, state, L, static_cast<unsigned char *>(ws), /*run_scan=*/1, st);
+    return launch_finish(reinterpret_cast<const long long *>(bins_sum), bins_max, n_seg, ties, reduction, nb, shift,
+                         out_loss, state, L, static_cast<unsigned char *>(ws), st);
 }
 
 int32_t cox_binned_fwd(const float *log_hz, const float *time, const uint8_t *event, const int64_t *seg_off,
@@ -1511,17 +1325,16 @@ int32_t cox_binned_fwd(const float *log_hz, const float *time, const uint8_t *ev
     unsigned char *w8 = static_cast<unsigned char *>(ws);
     long long *bins = reinterpret_cast<long long *>(w8 + L.off_bins);
     float *bins_max = reinterpret_cast<float *>(w8 + L.off_bins_max);
-    if (n_seg == 1 && seg_off == nullptr && coop_supported())
+    static const bool no_fuse = getenv("B200SURV_NO_FUSE") != nullptr;  // diagnostics: force the three-kernel path
+    if (n_seg == 1 && seg_off == nullptr && coop_supported() && !no_fuse)
         return launch_fused(log_hz, time, event, n, ties, reduction, nb, shift, out_loss, state, L, w8, nullptr, st);
-    rc = launch_pass1_reduce(log_hz, time, event, seg_off, n, n_seg, nb, shift, bins, bins_max, L, w8,
-                             /*fuse_scan=*/1, st);
+    rc = launch_pass1_reduce(log_hz, time, event, seg_off, n, n_seg, nb, shift, bins, bins_max, L, w8, st);
     if (rc) return rc;
-    return launch_items_finish(bins, bins_max, n_seg, ties, reduction, nb, shift, out_loss, state, L, w8,
-                               /*run_scan=*/0, st);
+    return launch_finish(bins, bins_max, n_seg, ties, reduction, nb, shift, out_loss, state, L, w8, st);
 }
 
 size_t cox_binned_peer_buffer_bytes(int nb) { return PEER_FLAGS_BYTES + 2 * peer_slot_bytes(nb); }
-size_t cox_binned_peer_trace_offset(int64_t n, int nb) { return binned_layout(n, 1, nb).off_D; }
+size_t cox_binned_peer_trace_offset(int64_t n, int nb) { return binned_layout(n, 1, nb).off_trace; }
 
 int32_t cox_binned_fwd_peer(const float *log_hz, const float *time, const uint8_t *event, int64_t n, int ties,
                             int reduction, int nb, float shift, float *out_loss, void *state, size_t state_bytes,
@@ -1541,9 +1354,7 @@ int32_t cox_binned_fwd_peer(const float *log_hz, const float *time, const uint8_
     PeerArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.world = world; pa.rank = rank; pa.epoch = epoch;
-    pa.status = reinterpret_cast<int *>(w8 + L.off_totals);  // unused by the fused path otherwise
-    static const bool trace_on = getenv("B200SURV_PEER_TRACE") != nullptr;
-    pa.trace = trace_on ? reinterpret_cast<long long *>(w8 + L.off_D) : nullptr;  // 11 stamps, see cox_binned_peer_trace_offset
+    pa.status = reinterpret_cast<int *>(w8 + L.off_status);
     for (int p = 0; p < world; ++p) {
         B200_REQUIRE(peer_bufs[p] != nullptr && (reinterpret_cast<uintptr_t>(peer_bufs[p]) & 255) == 0, "peer buffer alignment (256)");
         pa.buf[p] = static_cast<unsigned char *>(peer_bufs[p]);
@@ -1551,58 +1362,6 @@ int32_t cox_binned_fwd_peer(const float *log_hz, const float *time, const uint8_
     return launch_fused(log_hz, time, event, n, ties, reduction, nb, shift, out_loss, state, L, w8, &pa, st);
 }
 
-namespace {
-int32_t launch_fused(const float *log_hz, const float *time, const uint8_t *event, int64_t n, int ties, int reduction,
-                     int nb, float shift, float *out_loss, void *state, const BinnedLayout &L, unsigned char *w8,
-                     const PeerArgs *peer, cudaStream_t st) {
-    long long *bins = reinterpret_cast<long long *>(w8 + L.off_bins);
-    float *bins_max = reinterpret_cast<float *>(w8 + L.off_bins_max);
-    {
-        // one cooperative launch: pass 1 + reduce (+ peer exchange) + scan + Efron terms + finish
-        int vec_ok = aligned16(log_hz) && aligned16(time) && ((reinterpret_cast<uintptr_t>(event) & 3) == 0);
-        // The TMA-staged pass 1 (pass1_body_tma) is opt-in: measured 78.9 us vs 72.8 us for the register-staged
-        // loop at 16.7M rows (profiles/r1_v10_tma_ab.txt) -- with 31 consumer warps the ring hides the latency
-        // but the CTA loses a warp and pays an mbarrier round trip per 4 rows/thread.
-        // Pass-1 staging, B200SURV_P1 = ring (default) | reg | tma.  Measured at 16.7M rows, forward only:
-        // per-thread cp.async ring 64.4 us, register-staged loads 70.3 us, TMA bulk ring + producer warp 78.9 us
-        // (profiles/r1_v12_p1_staging_ab.txt, r1_v10_tma_ab.txt).
-        static const int p1_mode = [] {
-            const char *e = getenv("B200SURV_P1");
-            if (e && !strcmp(e, "tma")) return 1;
-            if (e && !strcmp(e, "reg")) return 0;
-            return 2;
-        }();
-        int use_tma = (vec_ok && nb <= 4096 && n >= 4 * (int64_t)TMA_TILE) ? p1_mode : 0;
-        const size_t smem = use_tma == 2 ? ring_smem_bytes(nb) : use_tma == 1 ? tma_smem_bytes(nb) : (size_t)nb * 24 + 16;
-        static bool attr_done = false;
-        if (!attr_done) {
-            size_t mx = (size_t)B200SURV_COX_MAX_BINS * 24 + 16;
-            if (tma_smem_bytes(4096) > mx) mx = tma_smem_bytes(4096);
-            if (ring_smem_bytes(4096) > mx) mx = ring_smem_bytes(4096);
-            B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-            B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-            B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-            B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-            attr_done = true;
-        }
-        unsigned char *partial = w8 + L.off_partial;
-        CtaRec *recs = reinterpret_cast<CtaRec *>(w8 + L.off_recs);
-        FusedArgs fa;
-        fa.bins = bins; fa.bins_max = bins_max; fa.tgf = reinterpret_cast<double *>(w8 + L.off_tgf);
-        fa.ties = ties; fa.reduction = reduction; fa.out_loss = out_loss; fa.state = static_cast<unsigned char *>(state);
-        int nb_i = nb;
-        PeerArgs pa;
-        if (peer) pa = *peer; else memset(&pa, 0, sizeof(pa));
-        void *args[] = {(void *)&log_hz, (void *)&time, (void *)&event, (void *)&n, (void *)&nb_i, (void *)&shift,
-                        (void *)&vec_ok, (void *)&partial, (void *)&recs, (void *)&fa, (void *)&use_tma, (void *)&pa};
-        const bool small = nb <= 4 * P1_THREADS;
-        const void *fn = peer ? (small ? (const void *)cox_binned_fwd_fused<4, true> : (const void *)cox_binned_fwd_fused<8, true>)
-                              : (small ? (const void *)cox_binned_fwd_fused<4, false> : (const void *)cox_binned_fwd_fused<8, false>);
-        B200_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(L.nctas), dim3(P1_THREADS), args, smem, st));
-        return B200SURV_OK;
-    }
-}
-}  // namespace
 
 int32_t cox_binned_bwd_launch(const float *grad_out, const void *state, size_t state_bytes, const float *log_hz,
                               const float *time, const uint8_t *event, const int64_t *seg_off, int64_t n,

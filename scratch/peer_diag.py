@@ -65,14 +65,22 @@ if world == 1:   # the peer kernel against its own buffer: phase trace of the si
 else:
     peer = bd.ShardedCoxBinned(n, dev, exchange="peer")
 timeit("peer fwd", lambda: peer.forward(x, tt, e))
-if os.environ.get("B200SURV_PEER_TRACE"):
+NAMES = ["start", "pass1", "sync1", "reduced", "sync2(peer)", "flag_sent", "pulled", "lookback1", "terms", "lookback2", "end", "rehearsed"]
+
+
+def show_trace(tag, ws):
+    if not os.environ.get("B200SURV_PEER_TRACE"):
+        return
     off = lib.b200surv_cox_peer_trace_offset(n, 4096)
     torch.cuda.synchronize()
-    tr = peer.ws[off:off + 120].view(torch.int64).cpu().tolist()
-    names = ["start", "pass1", "sync1", "reduce", "sync2", "flag_sent", "peers_seen", "pulled+sync", "cta0_ready", "sync4", "end",
-             "f_loaded", "f_exscan", "cta1_scanned", "cta1_efron_done(t0)"]
-    print(f"rank {rank} trace (us since start): " + ", ".join(f"{nm} {(v - tr[0]) / 1e3:.1f}" for nm, v in zip(names, tr)),
+    tr = ws[off:off + 96].view(torch.int64).cpu().tolist()
+    print(f"rank {rank} {tag} trace (us since start): " + ", ".join(f"{nm} {(v - tr[0]) / 1e3:.1f}" for nm, v in zip(NAMES, tr)),
           flush=True)
+
+
+show_trace("peer", peer.ws)
+f_single()
+show_trace("single", single.ws)
 timeit("peer fwd+bwd", lambda: (peer.forward(x, tt, e), peer.backward(x, tt, e, grad)))
 timeit("nccl fwd", lambda: single.forward(x, tt, e))
 timeit("nccl fwd+bwd", lambda: (single.forward(x, tt, e), single.backward(x, tt, e, grad)))
