@@ -280,17 +280,24 @@ def run_b200(args):
         hz, gt = net.forward_features(hct, hrna, hclin, hmask)
         ((hz * hw).sum() + 0.01 * ghead.gate_entropy_loss(gt)).backward()
 
-    for _ in range(3):
-        head_step()
-    barrier()
-    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    hreps = 10
-    h0.record()
-    for _ in range(hreps):
-        head_step()
-    h1.record()
-    barrier()
-    head_ms = h0.elapsed_time(h1) / hreps
+    def timed_head(fn, reps=10):
+        for _ in range(3):
+            fn()
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(reps):
+            fn()
+        h1.record()
+        barrier()
+        return h0.elapsed_time(h1) / reps
+
+    head_eager_ms = timed_head(head_step)
+    # the same step as ONE CUDA graph (head.GraphedHeadStep): the eager step is bound by the host (~100 launches)
+    graphed = ghead.GraphedHeadStep(net, hct, hrna, hclin, hmask,
+                                    lambda hz, gt: (hz * hw).sum() + 0.01 * ghead.gate_entropy_loss(gt))
+    fresh = [x.clone() for x in (hct, hrna, hclin, hmask)]       # a "new batch": copied into the static buffers each step
+    head_ms = timed_head(lambda: graphed.step(*fresh), reps=20)
     head_flop_per_row = 11_396_224          # fwd 5,507,136 + bwd 5,889,088
 
     if rank == 0:
@@ -312,12 +319,20 @@ def run_b200(args):
                         if op.exchange == "peer" else f"row-block shards x{world}, NCCL all-reduce of per-bin int64 sums"),
                        "l2": "no flush needed: each step streams 151 MB in + 67 MB out, larger than the 126 MB L2"},
             "loss": loss_val,
-            "roofline": {"bound": "hbm", "kernel": "cox_binned_bwd (13 B/row: 9 read + 4 written)",
-                         "achieved": achieved_bwd, "peak": peak, "unit": "GB/s", "frac": achieved_bwd / peak,
-                         "traffic": None, "peak_source": peak_src, "ms": bwd_ms,
-                         "fwd": {"kernels": "cox_binned_fwd_fused: pass 1 + reduce + scan + Efron terms + finish (9 B/row)"
-                                 if fused else "cox_binned_pass1, reduce, all-reduce, scan, items_finish (9 B/row)",
-                                 "achieved": achieved_fwd, "frac": achieved_fwd / peak, "ms": fwd_ms},
+            # dominant kernel of the step = the fused forward (57 % of the step in the ncu launch list,
+            # profiles/r1_v13_launches.csv).  `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of one launch
+            # from the ncu --set full capture of this command (profiles/r1_v13_ncu_full_cox.csv), valid for the
+            # default 16,777,216-row workload only.
+            "roofline": {"bound": "hbm",
+                         "kernel": ("cox_binned_fwd_fused (9 B/row read: pass 1 + reduce + O(nbins) tail in one cooperative launch)"
+                                    if fused else "cox_binned_pass1 + reduce + all-reduce + finish (9 B/row read)"),
+                         "achieved": achieved_fwd, "peak": peak, "unit": "GB/s", "frac": achieved_fwd / peak,
+                         "traffic": (151.086592e6 + 3.994368e6) if (fused and n == N_ROWS) else None,
+                         "peak_source": peak_src, "ms": fwd_ms,
+                         "bwd": {"kernel": "cox_binned_bwd (13 B/row: 9 read + 4 written)", "achieved": achieved_bwd,
+                                 "frac": achieved_bwd / peak, "ms": bwd_ms,
+                                 "traffic": (151.044352e6 + 33.467392e6) if n == N_ROWS else None,
+                                 "traffic_note": "gradient stores still in L2 when the kernel ends are not in dram__bytes_write"},
                          "step": {"bytes_per_row": ALGO_BYTES_PER_ROW, "achieved": achieved_step,
                                   "frac": achieved_step / peak, "frac_of_8TBs": achieved_step / 8000.0}},
             "e2e": {"value": e2e_val, "unit": "patients/s", "h2d_bytes_per_step": 9 * n, "d2h_bytes_per_step": 4,
@@ -332,8 +347,11 @@ def run_b200(args):
                       "head_b4096": {"rows": hb, "ms_fwd_bwd": head_ms, "rows_per_s": hb / (head_ms * 1e-3),
                                      "tflops": hb * head_flop_per_row / (head_ms * 1e-3) / 1e12,
                                      "dtype": "bf16 operands, fp32 accumulate (tcgen05)", "dropout_p": 0.3,
-                                     "note": "gated head fwd+bwd through the nn.Module (includes host launch "
-                                             "overhead of ~60 kernels); per rank"}},
+                                     "ms_fwd_bwd_eager": head_eager_ms,
+                                     "note": "gated head fwd + loss + bwd replayed as one CUDA graph (head.GraphedHeadStep), "
+                                             "batch copied into the static buffers inside the timed region; "
+                                             "ms_fwd_bwd_eager = the same step through the nn.Module call by call "
+                                             "(host-bound: ~100 launches); per rank"}},
         }
         if cpu_val is not None:
             out["cpu_baseline"] = {"value": cpu_val, "unit": "patients/s", "cores": cores, "kind": "port",

@@ -239,7 +239,11 @@ size_t b200surv_head_workspace_bytes(int64_t B, int32_t rna_dim); /* scratch of 
  * training != 0: BatchNorm uses batch statistics (B >= 2) and updates the running statistics, dropout
  * with probability dropout_p from a counter-based generator keyed by (seed, layer, element) -- backward
  * re-derives the same mask; keep1 [B][512] / keep2 [B][256] (nullable) export the keep masks.
+ * training == B200SURV_HEAD_TRAIN_SEED_DEV: as training, but `seed` carries the ADDRESS of a uint64 in device memory
+ * that the kernels read when they run -- a captured CUDA graph of fwd+bwd then draws a fresh dropout mask on every
+ * replay once the caller bumps that word between replays.
  * Outputs: hazard [B], gate [B][3]. */
+#define B200SURV_HEAD_TRAIN_SEED_DEV 2
 int32_t b200surv_head_fwd(const b200surv_head_params *params, const float *ct_feat, const float *rna,
                           const float *clinical, const float *mask, int64_t B, int32_t rna_dim,
                           int32_t training, float dropout_p, uint64_t seed, float *hazard, float *gate,

@@ -74,6 +74,8 @@ SIGNATURES = {
                                          c_int64, c_float, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
+HEAD_TRAIN_SEED_DEV = 2
+
 _lib = None
 _arch_ok = set()
 

@@ -109,6 +109,8 @@ struct Epilogue {
     const float *bias;      // [N] (nullable)
     int64_t ldc, ldc_bf16;
     int relu;
+    int kb_per;             // split-K: k-blocks per grid.z slice (slice z writes c + z * split_stride)
+    int64_t split_stride;
 };
 
 // A_MN / B_MN: operand is stored [K][cols] (MN-major) instead of [rows][K] (K-major)
@@ -127,7 +129,7 @@ gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_m = blockIdx.y, tile_n = blockIdx.x;
-    const int num_kb = (K + BK - 1) / BK;
+    const int kb0 = blockIdx.z * ep.kb_per, kb1 = min((K + BK - 1) / BK, kb0 + ep.kb_per);  // this slice's k-blocks
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -152,7 +154,7 @@ gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(smem_u32(bars + STAGES + stage), phase ^ 1);
                 const uint32_t full = smem_u32(bars + stage);
                 mbar_expect_tx(full, 2 * TILE_BYTES);
@@ -179,7 +181,7 @@ gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(smem_u32(bars + stage), phase);
                 tcgen05_fence_after();
                 const uint32_t sa = smem_u32(tiles_a + (size_t)stage * TILE_BYTES);
@@ -191,7 +193,7 @@ gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                     //           16 k = 2 groups = 2048 B
                     const uint64_t da = A_MN ? make_desc(sa + k * 2048, TILE_BYTES / 2, 1024) : make_desc(sa + k * 32, 16, 1024);
                     const uint64_t db = B_MN ? make_desc(sb + k * 2048, TILE_BYTES / 2, 1024) : make_desc(sb + k * 32, 16, 1024);
-                    umma_f16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_f16(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(smem_u32(bars + STAGES + stage));  // frees this smem stage when the MMAs retire
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -219,7 +221,7 @@ gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                     f[j] = x;
                 }
                 if (ep.c != nullptr) {
-                    float *dst = ep.c + (int64_t)row * ep.ldc + col0;
+                    float *dst = ep.c + (int64_t)blockIdx.z * ep.split_stride + (int64_t)row * ep.ldc + col0;
                     if (col0 + 32 <= N && (ep.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(ep.c) & 15) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -290,14 +292,15 @@ int32_t make_map(CUtensorMap *map, const void *ptr, int64_t inner, int64_t outer
 }
 
 template <bool A_MN, bool B_MN>
-int32_t launch(const CUtensorMap &ma, const CUtensorMap &mb, int M, int N, int K, const Epilogue &ep, cudaStream_t st) {
+int32_t launch(const CUtensorMap &ma, const CUtensorMap &mb, int M, int N, int K, const Epilogue &ep, int splits,
+               cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)GEMM_SMEM));
         attr_done = true;
     }
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
     gemm_bf16_tc<A_MN, B_MN><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ma, mb, M, N, K, ep);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
@@ -308,8 +311,22 @@ int32_t launch(const CUtensorMap &ma, const CUtensorMap &mb, int M, int N, int K
 // C[M][N] = op(A) * op(B)^T-like contraction over K:
 //   a_mn == 0: A is [M][K] (lda >= K)      a_mn == 1: A is [K][M] (lda >= M)
 //   b_mn == 0: B is [N][K] (ldb >= K)      b_mn == 1: B is [K][N] (ldb >= N)
+// slices a split-K launch of this shape uses (1 = not worth splitting): fill the SMs, at least 4 k-blocks a slice,
+// no empty slice; *kb_per = k-blocks per slice
+int splitk_slices(int M, int N, int K, int *kb_per) {
+    const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM), num_kb = (K + BK - 1) / BK;
+    int s = num_sms() / tiles;
+    if (s > num_kb / 4) s = num_kb / 4;
+    if (s > 32) s = 32;
+    if (s < 2) { if (kb_per) *kb_per = num_kb; return 1; }
+    const int per = (num_kb + s - 1) / s;
+    if (kb_per) *kb_per = per;
+    return (num_kb + per - 1) / per;
+}
+
 int32_t gemm_bf16(const void *a, int64_t lda, int a_mn, const void *b, int64_t ldb, int b_mn, int M, int N, int K,
-                  float *c, int64_t ldc, void *c_bf16, int64_t ldc_bf16, const float *bias, int relu, cudaStream_t st) {
+                  float *c, int64_t ldc, void *c_bf16, int64_t ldc_bf16, const float *bias, int relu, float *splitk_ws,
+                  cudaStream_t st) {
     B200_REQUIRE(a && b && (c || c_bf16), "null pointer");
     B200_REQUIRE(M >= 1 && N >= 1 && K >= 1, "M, N, K must be positive");
     CUtensorMap ma, mb;
@@ -321,10 +338,18 @@ int32_t gemm_bf16(const void *a, int64_t lda, int a_mn, const void *b, int64_t l
     Epilogue ep;
     ep.c = c; ep.c_bf16 = static_cast<__nv_bfloat16 *>(c_bf16); ep.bias = bias; ep.ldc = ldc; ep.ldc_bf16 = ldc_bf16;
     ep.relu = relu;
-    if (a_mn && b_mn) return launch<true, true>(ma, mb, M, N, K, ep, st);
-    if (a_mn && !b_mn) return launch<true, false>(ma, mb, M, N, K, ep, st);
-    if (!a_mn && b_mn) return launch<false, true>(ma, mb, M, N, K, ep, st);
-    return launch<false, false>(ma, mb, M, N, K, ep, st);
+    const int num_kb = (K + BK - 1) / BK;
+    ep.kb_per = num_kb; ep.split_stride = 0;
+    int splits = 1;
+    if (splitk_ws != nullptr) {  // split-K into `splits` fp32 slices of [M][ldc] in the workspace (summed by the caller)
+        B200_REQUIRE(c != nullptr && c_bf16 == nullptr && bias == nullptr && !relu, "split-K: plain fp32 output only");
+        splits = splitk_slices(M, N, K, &ep.kb_per);
+        ep.c = splitk_ws; ep.split_stride = (int64_t)M * ldc;
+    }
+    if (a_mn && b_mn) return launch<true, true>(ma, mb, M, N, K, ep, splits, st);
+    if (a_mn && !b_mn) return launch<true, false>(ma, mb, M, N, K, ep, splits, st);
+    if (!a_mn && b_mn) return launch<false, true>(ma, mb, M, N, K, ep, splits, st);
+    return launch<false, false>(ma, mb, M, N, K, ep, splits, st);
 }
 
 }  // namespace b200surv
@@ -332,6 +357,6 @@ int32_t gemm_bf16(const void *a, int64_t lda, int a_mn, const void *b, int64_t l
 extern "C" int32_t b200surv_gemm_bf16(const void *a, int64_t lda, int32_t a_mn, const void *b, int64_t ldb, int32_t b_mn,
                                       int32_t M, int32_t N, int32_t K, float *c, int64_t ldc, void *c_bf16,
                                       int64_t ldc_bf16, const float *bias, int32_t relu, b200surv_stream_t stream) {
-    return b200surv::gemm_bf16(a, lda, a_mn, b, ldb, b_mn, M, N, K, c, ldc, c_bf16, ldc_bf16, bias, relu,
+    return b200surv::gemm_bf16(a, lda, a_mn, b, ldb, b_mn, M, N, K, c, ldc, c_bf16, ldc_bf16, bias, relu, nullptr,
                                b200surv::as_stream(stream));
 }

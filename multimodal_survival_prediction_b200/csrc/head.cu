@@ -17,7 +17,9 @@
 namespace b200surv {
 
 int32_t gemm_bf16(const void *a, int64_t lda, int a_mn, const void *b, int64_t ldb, int b_mn, int M, int N, int K,
-                  float *c, int64_t ldc, void *c_bf16, int64_t ldc_bf16, const float *bias, int relu, cudaStream_t st);
+                  float *c, int64_t ldc, void *c_bf16, int64_t ldc_bf16, const float *bias, int relu, float *splitk_ws,
+                  cudaStream_t st);
+int splitk_slices(int M, int N, int K, int *kb_per);
 
 namespace {
 
@@ -26,7 +28,8 @@ constexpr int H1 = 512, R1 = 128, CL = 32, CT = 128, FEAT = CT + R1 + CL;  // 28
 constexpr int GZ = FEAT + 3, GZP = 296;                                      // gate input 291, padded to 296
 constexpr int GH = 64, H2 = 256, F2N = 128;
 constexpr float BN_EPS = 1e-5f, BN_MOM = 0.1f;
-constexpr int RS_MAX = 32;  // row slices of the column reductions
+constexpr int RS_MAX = 128;  // row slices of the column reductions
+constexpr int SPLITK_ELEMS = 256 * 512;  // largest weight gradient that is split along K (all but rna_encoder.0)
 
 __device__ __forceinline__ uint32_t rng32(uint64_t seed, uint32_t layer, uint64_t idx) {  // splitmix64
     uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + (uint64_t)layer * 0xD1B54A32D192ED03ull;
@@ -67,13 +70,26 @@ k_colreduce(const float *__restrict__ a, int64_t lda, const float *__restrict__ 
     double v0 = 0.0, v1 = 0.0;
     if (n < N) {
         const float m = (MODE == 1) ? mu[n] : 0.f, rs = (MODE == 1) ? rstd[n] : 0.f;
-        for (int64_t r = r0 + ty; r < r1; r += 8) {
-            const float av = a[r * lda + n];
+        auto acc = [&](int64_t r, float av, float xv, float sv) {
             if (MODE == 0) { v0 += av; v1 += (double)av * av; }
-            if (MODE == 1) { v0 += av; v1 += (double)av * ((x[r * ldx + n] - m) * rs); }
-            if (MODE == 2) { const float sv = s[r * s_stride]; v0 += (double)av * sv; v1 += sv; }
+            if (MODE == 1) { v0 += av; v1 += (double)av * ((xv - m) * rs); }
+            if (MODE == 2) { v0 += (double)av * sv; v1 += sv; }
             if (MODE == 3) { v0 += av; }
+        };
+        int64_t r = r0 + ty;
+        for (; r + 24 < r1; r += 32) {  // four rows in flight per thread
+            float av[4], xv[4], sv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                av[u] = a[(r + 8 * u) * lda + n];
+                xv[u] = (MODE == 1) ? x[(r + 8 * u) * ldx + n] : 0.f;
+                sv[u] = (MODE == 2) ? s[(r + 8 * u) * s_stride] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc(r + 8 * u, av[u], xv[u], sv[u]);
         }
+        for (; r < r1; r += 8)
+            acc(r, a[r * lda + n], (MODE == 1) ? x[r * ldx + n] : 0.f, (MODE == 2) ? s[r * s_stride] : 0.f);
     }
     sh0[ty][tx] = v0; sh1[ty][tx] = v1;
     __syncthreads();
@@ -124,8 +140,9 @@ __global__ void k_bn_finalize(const double *__restrict__ partial, int nslices, i
 __global__ void k_bn_apply(const float *__restrict__ x, int64_t ldx, const float *__restrict__ mu,
                            const float *__restrict__ rstd, const float *__restrict__ gamma,
                            const float *__restrict__ beta, int64_t B, int N, uint32_t thresh, float inv_keep,
-                           uint64_t seed, uint32_t layer, bf16 *__restrict__ y, int64_t ldy,
-                           uint8_t *__restrict__ keep_out) {
+                           uint64_t seed, const uint64_t *__restrict__ seed_dev, uint32_t layer, bf16 *__restrict__ y,
+                           int64_t ldy, uint8_t *__restrict__ keep_out) {
+    if (seed_dev != nullptr) seed = *seed_dev;  // (CUDA-graph replays: the seed lives in device memory)
     const int64_t total = B * N;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / N;
@@ -142,7 +159,9 @@ __global__ void k_bn_apply(const float *__restrict__ x, int64_t ldx, const float
 __global__ void k_bn_bwd_dy(const float *__restrict__ dA, int64_t ldd, const float *__restrict__ x, int64_t ldx,
                             const float *__restrict__ mu, const float *__restrict__ rstd,
                             const float *__restrict__ gamma, const float *__restrict__ beta, int64_t B, int N,
-                            uint32_t thresh, float inv_keep, uint64_t seed, uint32_t layer, float *__restrict__ dy) {
+                            uint32_t thresh, float inv_keep, uint64_t seed, const uint64_t *__restrict__ seed_dev,
+                            uint32_t layer, float *__restrict__ dy) {
+    if (seed_dev != nullptr) seed = *seed_dev;
     const int64_t total = B * N;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / N;
@@ -313,7 +332,7 @@ inline int gs(int64_t total) {  // grid for grid-stride element-wise kernels
     const int64_t cap = 8 * (int64_t)num_sms();
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
-inline int nslices_for(int64_t B) { int64_t s = (B + 255) / 256; return (int)(s < 1 ? 1 : (s > RS_MAX ? RS_MAX : s)); }
+inline int nslices_for(int64_t B) { int64_t s = (B + 31) / 32; return (int)(s < 1 ? 1 : (s > RS_MAX ? RS_MAX : s)); }
 
 struct Carver {
     unsigned char *base;
@@ -363,6 +382,7 @@ struct Scratch {
     bf16 *b0, *b1;            // [B][512] bf16 temporaries
     float *v0, *v1;           // [max N] vectors
     float *dlogit, *dC;       // [B][3], [B][32]
+    float *splitk;            // [32 slices][SPLITK_ELEMS] fp32 partial weight gradients
 };
 Scratch carve_scratch(void *buf, int64_t B, size_t *bytes) {
     Carver c{static_cast<unsigned char *>(buf), 0};
@@ -372,6 +392,7 @@ Scratch carve_scratch(void *buf, int64_t B, size_t *bytes) {
     s.b0 = c.take<bf16>((size_t)B * H1); s.b1 = c.take<bf16>((size_t)B * H1);
     s.v0 = c.take<float>(8192); s.v1 = c.take<float>(8192);
     s.dlogit = c.take<float>((size_t)B * 4); s.dC = c.take<float>((size_t)B * CL);
+    s.splitk = c.take<float>((size_t)32 * SPLITK_ELEMS);
     *bytes = c.off;
     return s;
 }
@@ -396,6 +417,26 @@ void col_sum(const float *a, int64_t lda, int64_t B, int N, double *partial, flo
 void col_sum_bf16(const bf16 *a, int64_t B, int N, float *tmp, double *partial, float *out0, cudaStream_t st) {
     k_bf16_to_f32<<<gs(B * N), 256, 0, st>>>(a, tmp, B * N);
     col_sum(tmp, N, B, N, partial, out0, st);
+}
+
+// weight gradient dW[M][N] = A^T B over K = batch rows (both operands MN-major).  The small ones (one to six output
+// tiles for 64 k-blocks) are split along K over the SMs into fp32 slices and summed in a fixed order (deterministic).
+__global__ void k_splitk_sum(const float *__restrict__ part, int slices, int64_t elems, float *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        for (int k = 0; k < slices; ++k) v += part[(size_t)k * elems + i];
+        out[i] = v;
+    }
+}
+int32_t gemm_wgrad(const void *a, int64_t lda, const void *b, int64_t ldb, int M, int N, int K, float *c, int64_t ldc,
+                   float *splitk_ws, cudaStream_t st) {
+    const int slices = ((int64_t)M * ldc <= SPLITK_ELEMS) ? splitk_slices(M, N, K, nullptr) : 1;
+    if (slices == 1) return gemm_bf16(a, lda, 1, b, ldb, 1, M, N, K, c, ldc, nullptr, 0, nullptr, 0, nullptr, st);
+    const int32_t rc = gemm_bf16(a, lda, 1, b, ldb, 1, M, N, K, c, ldc, nullptr, 0, nullptr, 0, splitk_ws, st);
+    if (rc) return rc;
+    const int64_t elems = (int64_t)M * ldc;
+    k_splitk_sum<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(splitk_ws, slices, elems, c);
+    return B200SURV_OK;
 }
 
 uint32_t drop_thresh(float p) {
@@ -444,6 +485,8 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
     cudaStream_t st = as_stream(stream);
     const int Kp = kpad(rna_dim);
     const uint32_t thresh = training ? drop_thresh(dropout_p) : 0;
+    // training == B200SURV_HEAD_TRAIN_SEED_DEV: `seed` is the address of a uint64 in device memory
+    const uint64_t *seed_dev = training == B200SURV_HEAD_TRAIN_SEED_DEV ? reinterpret_cast<const uint64_t *>(static_cast<uintptr_t>(seed)) : nullptr;
     const float inv_keep = 1.f / (1.f - dropout_p);
     const int nsl = nslices_for(B);
     int32_t rc;
@@ -457,32 +500,32 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
     k_cast_pad<<<gs(F2N * H2), 256, 0, st>>>(p->fus4_w, H2, s.wf2b, H2, F2N, H2, H2);
 
     // rna encoder: Linear(rna_dim, 512) -> BN -> ReLU -> Dropout -> Linear(512, 128) -> ReLU
-    rc = gemm_bf16(s.xb, Kp, 0, s.w1b, Kp, 0, (int)B, H1, rna_dim, s.h1, H1, nullptr, 0, p->rna0_b, 0, st);
+    rc = gemm_bf16(s.xb, Kp, 0, s.w1b, Kp, 0, (int)B, H1, rna_dim, s.h1, H1, nullptr, 0, p->rna0_b, 0, nullptr, st);
     if (rc) return rc;
     if (training) colreduce<0>(s.h1, H1, nullptr, 0, nullptr, nullptr, nullptr, 0, B, H1, w.partial, nsl, st);
     k_bn_finalize<<<(H1 + 255) / 256, 256, 0, st>>>(w.partial, nsl, B, H1, training, p->bn1_rm, p->bn1_rv, s.mu1, s.rstd1);
-    k_bn_apply<<<gs(B * H1), 256, 0, st>>>(s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh, inv_keep, seed, 1,
+    k_bn_apply<<<gs(B * H1), 256, 0, st>>>(s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh, inv_keep, seed, seed_dev, 1,
                                            s.a1, H1, keep1);
-    rc = gemm_bf16(s.a1, H1, 0, s.w2b, H1, 0, (int)B, R1, H1, s.r, R1, nullptr, 0, p->rna4_b, 1, st);
+    rc = gemm_bf16(s.a1, H1, 0, s.w2b, H1, 0, (int)B, R1, H1, s.r, R1, nullptr, 0, p->rna4_b, 1, nullptr, st);
     if (rc) return rc;
 
     // clinical encoder, masks, gate
     k_gate_prep<<<gs(B * GZP), 256, 0, st>>>(ct_feat, s.r, clinical, mask, p->clin_w, p->clin_b, B, s.feat,
                                              gated ? s.z : nullptr, gated ? nullptr : s.fused);
     if (gated) {
-        rc = gemm_bf16(s.z, GZP, 0, s.wg1b, GZP, 0, (int)B, GH, GZ, s.zh, GH, nullptr, 0, p->gate0_b, 1, st);
+        rc = gemm_bf16(s.z, GZP, 0, s.wg1b, GZP, 0, (int)B, GH, GZ, s.zh, GH, nullptr, 0, p->gate0_b, 1, nullptr, st);
         if (rc) return rc;
         k_gate_apply<<<gs(B * 32), 256, 0, st>>>(s.zh, p->gate2_w, p->gate2_b, s.feat, B, s.gate, s.fused);
         B200_CHECK_CUDA(cudaMemcpyAsync(gate, s.gate, (size_t)B * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     // fusion: Linear(288, 256) -> BN -> ReLU -> Dropout -> Linear(256, 128) -> ReLU ; cox head
-    rc = gemm_bf16(s.fused, FEAT, 0, s.wf1b, FEAT, 0, (int)B, H2, FEAT, s.h2, H2, nullptr, 0, p->fus0_b, 0, st);
+    rc = gemm_bf16(s.fused, FEAT, 0, s.wf1b, FEAT, 0, (int)B, H2, FEAT, s.h2, H2, nullptr, 0, p->fus0_b, 0, nullptr, st);
     if (rc) return rc;
     if (training) colreduce<0>(s.h2, H2, nullptr, 0, nullptr, nullptr, nullptr, 0, B, H2, w.partial, nsl, st);
     k_bn_finalize<<<(H2 + 255) / 256, 256, 0, st>>>(w.partial, nsl, B, H2, training, p->bn2_rm, p->bn2_rv, s.mu2, s.rstd2);
-    k_bn_apply<<<gs(B * H2), 256, 0, st>>>(s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh, inv_keep, seed, 2,
+    k_bn_apply<<<gs(B * H2), 256, 0, st>>>(s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh, inv_keep, seed, seed_dev, 2,
                                            s.a2, H2, keep2);
-    rc = gemm_bf16(s.a2, H2, 0, s.wf2b, H2, 0, (int)B, F2N, H2, s.f2, F2N, nullptr, 0, p->fus4_b, 1, st);
+    rc = gemm_bf16(s.a2, H2, 0, s.wf2b, H2, 0, (int)B, F2N, H2, s.f2, F2N, nullptr, 0, p->fus4_b, 1, nullptr, st);
     if (rc) return rc;
     k_cox_head<<<gs(B * 32), 256, 0, st>>>(s.f2, p->cox_w, p->cox_b, B, hazard);
     B200_CHECK_CUDA(cudaGetLastError());
@@ -504,6 +547,8 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     cudaStream_t st = as_stream(stream);
     const int Kp = kpad(rna_dim);
     const uint32_t thresh = training ? drop_thresh(dropout_p) : 0;
+    // training == B200SURV_HEAD_TRAIN_SEED_DEV: `seed` is the address of a uint64 in device memory
+    const uint64_t *seed_dev = training == B200SURV_HEAD_TRAIN_SEED_DEV ? reinterpret_cast<const uint64_t *>(static_cast<uintptr_t>(seed)) : nullptr;
     const float inv_keep = 1.f / (1.f - dropout_p);
     const int nsl = nslices_for(B);
     int32_t rc;
@@ -513,23 +558,23 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     B200_CHECK_CUDA(cudaMemcpyAsync(g->cox_b, w.v1, sizeof(float), cudaMemcpyDeviceToDevice, st));
     k_cox_head_bwd<<<gs(B * F2N), 256, 0, st>>>(d_hazard, s.f2, p->cox_w, B, w.b0);           // b0 = dF2 [B][128]
     // ---- fusion.4: dW = dF2^T a2, db = colsum dF2, dA2 = dF2 Wf2
-    rc = gemm_bf16(w.b0, F2N, 1, s.a2, H2, 1, F2N, H2, (int)B, g->fus4_w, H2, nullptr, 0, nullptr, 0, st);
+    rc = gemm_wgrad(w.b0, F2N, s.a2, H2, F2N, H2, (int)B, g->fus4_w, H2, w.splitk, st);
     if (rc) return rc;
     col_sum_bf16(w.b0, B, F2N, w.t2, w.partial, g->fus4_b, st);
-    rc = gemm_bf16(w.b0, F2N, 0, s.wf2b, H2, 1, (int)B, H2, F2N, w.t0, H2, nullptr, 0, nullptr, 0, st);  // t0 = dA2 [B][256]
+    rc = gemm_bf16(w.b0, F2N, 0, s.wf2b, H2, 1, (int)B, H2, F2N, w.t0, H2, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dA2 [B][256]
     if (rc) return rc;
     // ---- fusion.1-3 (BN, ReLU, Dropout) backward -> dH2 (bf16, b1)
     k_bn_bwd_dy<<<gs(B * H2), 256, 0, st>>>(w.t0, H2, s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh, inv_keep,
-                                            seed, 2, w.t1);                                       // t1 = dy
+                                            seed, seed_dev, 2, w.t1);                                       // t1 = dy
     colreduce<1>(w.t1, H2, s.h2, H2, s.mu2, s.rstd2, nullptr, 0, B, H2, w.partial, nsl, st);
     k_colreduce_final<<<(H2 + 255) / 256, 256, 0, st>>>(w.partial, nsl, H2, 1.f, g->bn2_b, g->bn2_w);  // dbeta, dgamma
     k_bn_bwd_dx<<<gs(B * H2), 256, 0, st>>>(w.t1, s.h2, H2, s.mu2, s.rstd2, p->bn2_w, g->bn2_b, g->bn2_w, B, H2, training,
                                             w.b1, H2);                                            // b1 = dH2
     k_bn_bias_grad<<<(H2 + 255) / 256, 256, 0, st>>>(g->bn2_b, p->bn2_w, s.rstd2, H2, training, g->fus0_b);
     // ---- fusion.0: dW = dH2^T fused, dfused = dH2 Wf1
-    rc = gemm_bf16(w.b1, H2, 1, s.fused, FEAT, 1, H2, FEAT, (int)B, g->fus0_w, FEAT, nullptr, 0, nullptr, 0, st);
+    rc = gemm_wgrad(w.b1, H2, s.fused, FEAT, H2, FEAT, (int)B, g->fus0_w, FEAT, w.splitk, st);
     if (rc) return rc;
-    rc = gemm_bf16(w.b1, H2, 0, s.wf1b, FEAT, 1, (int)B, FEAT, H2, w.t0, FEAT, nullptr, 0, nullptr, 0, st);  // t0 = dfused
+    rc = gemm_bf16(w.b1, H2, 0, s.wf1b, FEAT, 1, (int)B, FEAT, H2, w.t0, FEAT, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dfused
     if (rc) return rc;
     const float *dfeat = w.t0;
     const float *dz = nullptr;
@@ -540,10 +585,10 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
         for (int k = 0; k < 3; ++k)
             rowscale_sum(s.zh, GH, w.dlogit + k, 3, B, GH, w.partial, g->gate2_w + k * GH, w.v0 + k, st);
         B200_CHECK_CUDA(cudaMemcpyAsync(g->gate2_b, w.v0, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        rc = gemm_bf16(w.b0, GH, 1, s.z, GZP, 1, GH, GZ, (int)B, g->gate0_w, GZ, nullptr, 0, nullptr, 0, st);
+        rc = gemm_wgrad(w.b0, GH, s.z, GZP, GH, GZ, (int)B, g->gate0_w, GZ, w.splitk, st);
         if (rc) return rc;
         col_sum_bf16(w.b0, B, GH, w.t2, w.partial, g->gate0_b, st);
-        rc = gemm_bf16(w.b0, GH, 0, s.wg1b, GZP, 1, (int)B, GZP, GH, w.t0, GZP, nullptr, 0, nullptr, 0, st);  // t0 = dz
+        rc = gemm_bf16(w.b0, GH, 0, s.wg1b, GZP, 1, (int)B, GZP, GH, w.t0, GZP, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dz
         if (rc) return rc;
         dfeat = w.t1;
         dz = w.t0;
@@ -554,21 +599,21 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     rowscale_sum(w.dC, CL, clinical, 1, B, CL, w.partial, g->clin_w, nullptr, st);
     col_sum(w.dC, CL, B, CL, w.partial, g->clin_b, st);
     // ---- rna_encoder.4: dW = dR^T a1, db, dA1 = dR W2
-    rc = gemm_bf16(w.b1, R1, 1, s.a1, H1, 1, R1, H1, (int)B, g->rna4_w, H1, nullptr, 0, nullptr, 0, st);
+    rc = gemm_wgrad(w.b1, R1, s.a1, H1, R1, H1, (int)B, g->rna4_w, H1, w.splitk, st);
     if (rc) return rc;
     col_sum_bf16(w.b1, B, R1, w.t2, w.partial, g->rna4_b, st);
-    rc = gemm_bf16(w.b1, R1, 0, s.w2b, H1, 1, (int)B, H1, R1, w.t0, H1, nullptr, 0, nullptr, 0, st);  // t0 = dA1 [B][512]
+    rc = gemm_bf16(w.b1, R1, 0, s.w2b, H1, 1, (int)B, H1, R1, w.t0, H1, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dA1 [B][512]
     if (rc) return rc;
     // ---- rna_encoder.1-3 backward -> dH1 (bf16, b0)
     k_bn_bwd_dy<<<gs(B * H1), 256, 0, st>>>(w.t0, H1, s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh, inv_keep,
-                                            seed, 1, w.t1);
+                                            seed, seed_dev, 1, w.t1);
     colreduce<1>(w.t1, H1, s.h1, H1, s.mu1, s.rstd1, nullptr, 0, B, H1, w.partial, nsl, st);
     k_colreduce_final<<<(H1 + 255) / 256, 256, 0, st>>>(w.partial, nsl, H1, 1.f, g->bn1_b, g->bn1_w);
     k_bn_bwd_dx<<<gs(B * H1), 256, 0, st>>>(w.t1, s.h1, H1, s.mu1, s.rstd1, p->bn1_w, g->bn1_b, g->bn1_w, B, H1, training,
                                             w.b0, H1);                             // b0 = dH1
     k_bn_bias_grad<<<(H1 + 255) / 256, 256, 0, st>>>(g->bn1_b, p->bn1_w, s.rstd1, H1, training, g->rna0_b);
     // ---- rna_encoder.0: dW1 [512][rna_dim] = dH1^T x  (the big one; x is an input, no dx)
-    rc = gemm_bf16(w.b0, H1, 1, s.xb, Kp, 1, H1, rna_dim, (int)B, g->rna0_w, rna_dim, nullptr, 0, nullptr, 0, st);
+    rc = gemm_wgrad(w.b0, H1, s.xb, Kp, H1, rna_dim, (int)B, g->rna0_w, rna_dim, w.splitk, st);
     if (rc) return rc;
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;

@@ -43,6 +43,9 @@ class HeadGrads(ctypes.Structure):
 
 
 def _f32c(t, dev):
+    # fast path: already what the C ABI wants (every torch call costs microseconds; the head makes ~50 of them)
+    if t.dtype is torch.float32 and t.device == dev and t.is_contiguous():
+        return t.detach() if t.requires_grad else t
     return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
 
@@ -72,6 +75,9 @@ class _HeadFn(torch.autograd.Function):
         gate = torch.empty(B, 3, dtype=torch.float32, device=dev) if gated else None
         keep1 = torch.empty(B, 512, dtype=torch.uint8, device=dev) if want_masks else None
         keep2 = torch.empty(B, 256, dtype=torch.uint8, device=dev) if want_masks else None
+        if isinstance(seed, torch.Tensor):   # device-resident seed (CUDA-graph replays): pass its address
+            ctx.seed_keep = seed
+            training, seed = (L.HEAD_TRAIN_SEED_DEV if training else 0), seed.data_ptr()
         with torch.cuda.device(dev):
             rc = lib.b200surv_head_fwd(ctypes.byref(ps), L.ptr(ct_c), L.ptr(rna_c), L.ptr(clin_c), L.ptr(mask_c), B,
                                        rna_dim, int(training), ctypes.c_float(dropout_p), ctypes.c_uint64(seed),
@@ -96,7 +102,12 @@ class _HeadFn(torch.autograd.Function):
         d_gate = rest[0] if gated and len(rest) > 0 else None
         dh = torch.zeros(B, dtype=torch.float32, device=dev) if d_hazard is None else _f32c(d_hazard, dev)
         dg = None if d_gate is None else _f32c(d_gate, dev)
-        grads = {f: (torch.empty_like(tens[f]) if tens[f] is not None else None) for f in _G_FIELDS}
+        # one allocation for all parameter gradients, handed out as views
+        live = [f for f in _G_FIELDS if tens[f] is not None]
+        flat = torch.empty(sum(tens[f].numel() for f in live), dtype=torch.float32, device=dev)
+        grads = {f: None for f in _G_FIELDS}
+        for f, g in zip(live, flat.split([tens[f].numel() for f in live])):
+            grads[f] = g
         ps = HeadParams(**{f: (t.data_ptr() if t is not None else None) for f, t in tens.items()})
         gs = HeadGrads(**{f: (t.data_ptr() if t is not None else None) for f, t in grads.items()})
         d_ct = torch.empty(B, 128, dtype=torch.float32, device=dev)
@@ -111,15 +122,26 @@ class _HeadFn(torch.autograd.Function):
             if f.endswith(("_rm", "_rv")) or meta is None:
                 out.append(None)
             else:
-                out.append(grads[f].to(meta[0]).reshape(meta[1]))
+                g = grads[f].view(meta[1])
+                out.append(g if meta[0] is torch.float32 else g.to(meta[0]))
         return tuple(out)
+
+
+def _param_list(module):
+    """The 24 tensors of _P_FIELDS by direct attribute access (cheaper than walking named_parameters())."""
+    r, f = module.rna_encoder, module.fusion
+    g = getattr(module, "gate", None)
+    return [r[0].weight, r[0].bias, r[1].weight, r[1].bias, r[1].running_mean, r[1].running_var, r[4].weight, r[4].bias,
+            module.clinical_encoder[0].weight, module.clinical_encoder[0].bias,
+            g[0].weight if g is not None else None, g[0].bias if g is not None else None,
+            g[2].weight if g is not None else None, g[2].bias if g is not None else None,
+            f[0].weight, f[0].bias, f[1].weight, f[1].bias, f[1].running_mean, f[1].running_var, f[4].weight, f[4].bias,
+            module.cox_head.weight, module.cox_head.bias]
 
 
 def fused_head(module, ct_feat, rna, clinical, mask=None, want_masks=False, seed=None):
     """Run the head of ``module`` (a PartialModalityNet / MultiModalSurvivalNet from this file) on CUDA."""
-    sd = dict(module.named_parameters())
-    sd.update(dict(module.named_buffers()))
-    params = [sd.get(KEYS[f]) for f in _P_FIELDS]
+    params = _param_list(module)
     training = module.training
     p_drop = float(module.rna_encoder[3].p) if training else 0.0
     if seed is None:
@@ -189,6 +211,53 @@ class MultiModalSurvivalNet(_HeadBase):
 
     def forward_features(self, ct_feat, rna, clinical):
         return fused_head(self, ct_feat, rna, clinical, None)[0]
+
+
+class GraphedHeadStep:
+    """One training step of the head -- forward_features, ``loss_fn(*outputs)``, backward -- captured in ONE CUDA graph.
+
+    The eager step is bound by the host (about a hundred kernel launches plus the autograd bookkeeping cost ~1 ms at
+    B = 4096, three times the GPU work); a replay costs one launch.  Shapes are fixed at construction.  ``step(...)``
+    copies a batch into the static input buffers (or write into ``self.inputs`` yourself and call ``replay()``),
+    replays, and returns ``(loss, outputs)``; the gradients are left in ``param.grad`` (static tensors that every replay
+    overwrites -- step the optimizer before the next replay and do not set them to None).  The dropout seed lives in
+    device memory and advances inside the graph, so every replay draws new masks (B200SURV_HEAD_TRAIN_SEED_DEV).
+    """
+
+    def __init__(self, module, ct_feat, rna, clinical, mask, loss_fn, warmup: int = 3):
+        dev = ct_feat.device
+        self.module, self.loss_fn = module, loss_fn
+        self.inputs = [None if t is None else t.detach().clone() for t in (ct_feat, rna, clinical, mask)]
+        self.seed = torch.empty((), dtype=torch.int64, device=dev).random_()
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):       # warm-up off the capture stream (lazy initialisation, allocator pools)
+            for _ in range(warmup):
+                self._eager()
+        cur.wait_stream(side)
+        for p in module.parameters():
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.outputs = self._eager()
+
+    def _eager(self):
+        self.seed += 1
+        outs = fused_head(self.module, *self.inputs, seed=self.seed)
+        loss = self.loss_fn(*outs)
+        loss.backward()
+        return loss, outs
+
+    def replay(self):
+        self.graph.replay()
+        return self.loss, self.outputs
+
+    def step(self, ct_feat, rna, clinical, mask=None):
+        for dst, src in zip(self.inputs, (ct_feat, rna, clinical, mask)):
+            if dst is not None and src is not dst:
+                dst.copy_(src, non_blocking=True)
+        return self.replay()
 
 
 def gate_entropy_loss(gate_weights, eps=1e-8):

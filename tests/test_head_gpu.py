@@ -188,3 +188,49 @@ def test_module_api_with_ct_encoder_and_errors():
         m.forward_features(torch.rand(1, 128).cuda(), rna[:1], clin[:1], mask[:1])
     with pytest.raises(Exception):                                   # no CPU path
         ghead.PartialModalityNet().forward_features(torch.rand(2, 128), rna[:2].cpu(), clin[:2].cpu(), mask[:2].cpu())
+
+
+def test_graphed_step_matches_eager_and_redraws_dropout():
+    """GraphedHeadStep (one CUDA graph per fwd+loss+bwd) reproduces the eager step bit for bit without dropout, and
+    with dropout draws a new mask on every replay (device-side seed)."""
+    dev = torch.device("cuda", 0)
+    B = 512
+    torch.manual_seed(3)
+    ct, rna, clin, mask = [t.to(dev) for t in synth.modality_batch(B, seed=5)]
+    wts = (torch.randn(B, device=dev) / B ** 0.5)
+
+    def loss_fn(hz, gate):
+        return (hz * wts).sum() + 0.01 * ghead.gate_entropy_loss(gate)
+
+    m = ghead.PartialModalityNet().to(dev).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    hz, gate = m.forward_features(ct, rna, clin, mask)
+    loss_fn(hz, gate).backward()
+    ref = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    ref_loss, ref_rm = float(loss_fn(hz, gate)), m.rna_encoder[1].running_mean.clone()
+
+    m2 = ghead.PartialModalityNet().to(dev).train()
+    for mod in m2.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    g = ghead.GraphedHeadStep(m2, ct, rna, clin, mask, loss_fn, warmup=2)
+    m2.load_state_dict(before)          # the warm-up and the capture ran real steps: restore, then replay once
+    loss, (hz2, gate2) = g.step(ct.clone(), rna.clone(), clin.clone(), mask.clone())
+    torch.cuda.synchronize()
+    assert float(loss) == ref_loss
+    assert torch.equal(hz2, hz.detach()) and torch.equal(gate2, gate.detach())
+    for k, p in m2.named_parameters():
+        if k in ref:
+            assert torch.equal(p.grad, ref[k]), k
+    assert torch.equal(m2.rna_encoder[1].running_mean, ref_rm)
+
+    m3 = ghead.PartialModalityNet().to(dev).train()      # dropout 0.3: consecutive replays differ
+    g3 = ghead.GraphedHeadStep(m3, ct, rna, clin, mask, loss_fn, warmup=2)
+    m3.load_state_dict(before)
+    a = g3.replay()[1][0].clone()
+    m3.load_state_dict(before)
+    b = g3.replay()[1][0].clone()
+    assert not torch.equal(a, b)
