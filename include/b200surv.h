@@ -183,6 +183,16 @@ int32_t b200surv_cindex_counts(const float *estimate, const float *time, const u
                                int64_t row_begin, int64_t row_end, float tied_tol, int32_t algo,
                                int64_t *out_counts, void *workspace, size_t workspace_bytes,
                                b200surv_stream_t stream);
+/* Strong scaling of ONE cohort over the GPUs of a box (every rank holds the full vectors): the event rows, in
+ * (time, events first) order, are cut into tiles of 2048 rows that are dealt out round-robin; shard `shard` of
+ * `n_shards` counts the pairs of its tiles against all columns.  The shards partition the pairs, so an int64 SUM
+ * all-reduce of the six counters gives the single-GPU result bit for bit.  Unlike contiguous [row_begin,row_end)
+ * blocks of the caller's row order, whose rows are scattered over the sorted order, a shard's tiles keep the
+ * upper-triangular structure of the single-GPU run (the same fast-path share), and the triangle is balanced.
+ * algo 1 only; out_counts is ADDED to. */
+int32_t b200surv_cindex_counts_shard(const float *estimate, const float *time, const uint8_t *event, int64_t n,
+                                     int32_t shard, int32_t n_shards, float tied_tol, int64_t *out_counts,
+                                     void *workspace, size_t workspace_bytes, b200surv_stream_t stream);
 /* Many independent cohorts packed back to back (the CV sweep evaluates one C-index per fold and replica,
  * partial_modality_training.py:438-485 called per fold): cohort c is rows
  * [cohort_offsets_host[c], cohort_offsets_host[c+1]) -- a HOST array of n_cohorts+1 offsets -- and

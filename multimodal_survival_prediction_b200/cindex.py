@@ -42,6 +42,25 @@ def cindex_counts(estimate, event, time, tied_tol=1e-8, row_begin=0, row_end=Non
     return out
 
 
+def cindex_counts_shard(estimate, event, time, shard, n_shards, tied_tol=1e-8, out=None):
+    """Six int64 counters of shard ``shard`` of ``n_shards`` (row tiles of the sorted event rows dealt out round-robin,
+    b200surv_cindex_counts_shard); the shards' counters sum to cindex_counts(...) exactly."""
+    dev = estimate.device
+    L.require_device(dev.index)
+    lib = L.load()
+    n = estimate.numel()
+    if out is None:
+        out = torch.zeros(6, dtype=torch.int64, device=dev)
+    if n == 0:
+        return out
+    wb = lib.b200surv_cindex_workspace_bytes(n, 1, 1)
+    ws = torch.empty(max(wb, 256), dtype=torch.uint8, device=dev)
+    rc = lib.b200surv_cindex_counts_shard(L.ptr(estimate), L.ptr(time), L.ptr(event), n, shard, n_shards,
+                                          ctypes.c_float(tied_tol), L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "b200surv_cindex_counts_shard")
+    return out
+
+
 def cindex_counts_cohorts(estimate, event, time, offsets, tied_tol=1e-8, algo=1):
     """int64[n_cohorts][6] pair counters for cohorts packed back to back; ``offsets`` is a host sequence of
     n_cohorts+1 row offsets (the CV sweep: one C-index per fold and replica).  Asynchronous."""

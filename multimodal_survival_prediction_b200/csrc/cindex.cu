@@ -77,7 +77,7 @@ constexpr int CT_THREADS = 256;
 constexpr int CT_R = 8;                       // rows per thread
 constexpr int CT_ROWS = CT_THREADS * CT_R;    // 2048 rows per CTA
 constexpr int CT_TILE = 1024;                 // columns per shared-memory tile
-constexpr int CT_CHUNK_TILES = 8;             // column tiles per CTA
+constexpr int CT_CHUNK_TILES = 8;             // column tiles per CTA, at most (fewer when there are few row tiles)
 
 struct Acc1 {
     unsigned long long conc_s, le_s, conc_t, le_t, tot_s, tot_t;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256)
 k_ci_rows(const uint32_t *__restrict__ keys_s, const float *__restrict__ est_s,
           const int *__restrict__ isrow, const int *__restrict__ rank, int64_t n, float tol,
           float *__restrict__ r_lo, float *__restrict__ r_hi, int *__restrict__ r_s,
-          int *__restrict__ r_ge, Acc1 *acc) {
+          int *__restrict__ r_ge, int shard, int n_shards, Acc1 *acc) {
     __shared__ long long red[32];
     long long tot_s = 0, tot_t = 0, nrows = 0;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
@@ -151,8 +151,10 @@ k_ci_rows(const uint32_t *__restrict__ keys_s, const float *__restrict__ est_s,
             hi = o2f(a);
         }
         r_lo[k] = lo; r_hi[k] = hi; r_s[k] = s; r_ge[k] = ge;
-        tot_s += (long long)n - ge;
-        tot_t += (long long)ge - s;
+        if ((k / CT_ROWS) % n_shards == shard) {  // the row tiles are dealt out round-robin to the shards
+            tot_s += (long long)n - ge;
+            tot_t += (long long)ge - s;
+        }
         nrows += 1;
     }
     tot_s = block_reduce<long long>(tot_s, 0ll, OpAddLL(), red);
@@ -169,15 +171,15 @@ k_ci_rows(const uint32_t *__restrict__ keys_s, const float *__restrict__ est_s,
 __global__ void __launch_bounds__(CT_THREADS)
 k_ci_count(const float *__restrict__ est_s, int64_t n, const float *__restrict__ r_lo,
            const float *__restrict__ r_hi, const int *__restrict__ r_s, const int *__restrict__ r_ge,
-           Acc1 *acc) {
+           int shard, int n_shards, int chunk_tiles, Acc1 *acc) {
     __shared__ __align__(16) float s_e[CT_TILE];
     __shared__ int s_red[2][32];
     __shared__ long long red[32];
     const long long n_rows = (long long)acc->n_rows;
-    const long long k0 = (long long)blockIdx.y * CT_ROWS;
+    const long long k0 = ((long long)blockIdx.y * n_shards + shard) * CT_ROWS;  // row tile blockIdx.y of this shard
     if (k0 >= n_rows) return;
-    const int chunk0 = blockIdx.x * (CT_TILE * CT_CHUNK_TILES);
-    const int chunk1 = (int)min((long long)n, (long long)chunk0 + CT_TILE * CT_CHUNK_TILES);
+    const int chunk0 = blockIdx.x * (CT_TILE * chunk_tiles);
+    const int chunk1 = (int)min((long long)n, (long long)chunk0 + CT_TILE * chunk_tiles);
 
     float lo[CT_R], hi[CT_R];
     int rs[CT_R], rg[CT_R];
@@ -299,11 +301,13 @@ CiLayout ci_layout(int64_t n) {
 size_t cindex_workspace_bytes(int64_t n, int algo) { return algo == 0 ? 256 : ci_layout(n).total; }
 
 int32_t cindex_counts_launch(const float *est, const float *time, const uint8_t *event, int64_t n,
-                             int64_t row_begin, int64_t row_end, float tol, int algo, int64_t *out, void *ws,
-                             size_t ws_bytes, cudaStream_t st) {
+                             int64_t row_begin, int64_t row_end, float tol, int algo, int shard, int n_shards,
+                             int64_t *out, void *ws, size_t ws_bytes, cudaStream_t st) {
     B200_REQUIRE(n >= 0 && n < (int64_t)INT_MAX, "n must be < 2^31");
     B200_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n, "row range");
     B200_REQUIRE(tol >= 0.f, "tied_tol must be >= 0");
+    B200_REQUIRE(n_shards >= 1 && shard >= 0 && shard < n_shards, "shard in [0, n_shards)");
+    B200_REQUIRE(algo == 1 || n_shards == 1, "tile shards need algo 1");
     if (n == 0 || row_begin == row_end) return B200SURV_OK;
     if (algo == 0) {
         const int64_t rows = row_end - row_begin;
@@ -336,14 +340,22 @@ int32_t cindex_counts_launch(const float *est, const float *time, const uint8_t 
     k_ci_flag<<<grid, 256, 0, st>>>(est, keys_s, idx_s, n, row_begin, row_end, est_s, isrow);
     cb = L.cub_bytes;
     B200_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cb, isrow, rank, (int)n, st));
-    k_ci_rows<<<grid, 256, 0, st>>>(keys_s, est_s, isrow, rank, n, tol, r_lo, r_hi, r_s, r_ge, acc);
+    k_ci_rows<<<grid, 256, 0, st>>>(keys_s, est_s, isrow, rank, n, tol, r_lo, r_hi, r_s, r_ge, shard, n_shards, acc);
     {
         // upper bound on selected rows known to the host: min(n, row_end - row_begin)
         const int64_t max_rows = row_end - row_begin;
-        const unsigned gy = (unsigned)((max_rows + CT_ROWS - 1) / CT_ROWS);
-        const unsigned gx = (unsigned)((n + CT_TILE * CT_CHUNK_TILES - 1) / (CT_TILE * CT_CHUNK_TILES));
+        const int64_t tiles = (max_rows + CT_ROWS - 1) / CT_ROWS;
+        const unsigned gy = (unsigned)((tiles + n_shards - 1) / n_shards);
+        // column tiles per CTA: enough CTAs (about half of the grid is above the diagonal and does the work) for
+        // ~8 waves of 8 CTAs per SM, or the last, partly filled wave costs milliseconds (measured: a 1/8 shard took
+        // 7.1 ms with 8 tiles per CTA against 4.8 ms of work)
+        const int64_t col_tiles = (n + CT_TILE - 1) / CT_TILE;
+        int64_t ct = (int64_t)gy * col_tiles / 2 / (64 * (int64_t)num_sms());
+        if (ct < 1) ct = 1;
+        if (ct > CT_CHUNK_TILES) ct = CT_CHUNK_TILES;
+        const unsigned gx = (unsigned)((col_tiles + ct - 1) / ct);
         B200_REQUIRE(gy <= 65535, "too many row tiles");
-        k_ci_count<<<dim3(gx, gy), CT_THREADS, 0, st>>>(est_s, n, r_lo, r_hi, r_s, r_ge, acc);
+        k_ci_count<<<dim3(gx, gy), CT_THREADS, 0, st>>>(est_s, n, r_lo, r_hi, r_s, r_ge, shard, n_shards, (int)ct, acc);
     }
     k_ci_final<<<1, 32, 0, st>>>(acc, reinterpret_cast<long long *>(out));
     B200_CHECK_CUDA(cudaGetLastError());

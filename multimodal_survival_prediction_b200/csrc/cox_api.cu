@@ -27,8 +27,8 @@ int32_t cox_sorted_fwd_launch(const float *, const float *, const uint8_t *, int
                               size_t, void *, size_t, cudaStream_t);
 // cindex.cu
 size_t cindex_workspace_bytes(int64_t n, int algo);
-int32_t cindex_counts_launch(const float *, const float *, const uint8_t *, int64_t, int64_t, int64_t, float, int,
-                             int64_t *, void *, size_t, cudaStream_t);
+int32_t cindex_counts_launch(const float *, const float *, const uint8_t *, int64_t, int64_t, int64_t, float, int, int,
+                             int, int64_t *, void *, size_t, cudaStream_t);
 }  // namespace b200surv
 
 using namespace b200surv;
@@ -151,7 +151,16 @@ int32_t b200surv_cindex_counts(const float *estimate, const float *time, const u
         return B200SURV_UNSUPPORTED;
     }
     B200_REQUIRE(algo == 0 || workspace != nullptr, "workspace");
-    return cindex_counts_launch(estimate, time, event, n, row_begin, row_end, tied_tol, algo, out_counts, workspace,
+    return cindex_counts_launch(estimate, time, event, n, row_begin, row_end, tied_tol, algo, 0, 1, out_counts, workspace,
+                                workspace_bytes, as_stream(stream));
+}
+
+int32_t b200surv_cindex_counts_shard(const float *estimate, const float *time, const uint8_t *event, int64_t n,
+                                     int32_t shard, int32_t n_shards, float tied_tol, int64_t *out_counts,
+                                     void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
+    B200_REQUIRE(estimate && time && event && out_counts && workspace, "null pointer");
+    B200_REQUIRE(n >= 0, "n");
+    return cindex_counts_launch(estimate, time, event, n, 0, n, tied_tol, 1, shard, n_shards, out_counts, workspace,
                                 workspace_bytes, as_stream(stream));
 }
 
@@ -166,7 +175,7 @@ int32_t b200surv_cindex_counts_cohorts(const float *estimate, const float *time,
         const int64_t a = cohort_offsets_host[c], b = cohort_offsets_host[c + 1];
         B200_REQUIRE(a >= 0 && b >= a, "cohort_offsets_host must be non-decreasing");
         if (b == a) continue;
-        const int32_t rc = cindex_counts_launch(estimate + a, time + a, event + a, b - a, 0, b - a, tied_tol, algo,
+        const int32_t rc = cindex_counts_launch(estimate + a, time + a, event + a, b - a, 0, b - a, tied_tol, algo, 0, 1,
                                                 out_counts + 6 * c, workspace, workspace_bytes, as_stream(stream));
         if (rc != B200SURV_OK) return rc;
     }

@@ -4,7 +4,7 @@ One process per GPU (torch.distributed, NCCL over NVLink).  The reference has no
 this is the scale-out of the two operators it calls:
 
 * C-index: every rank holds the full (estimate, event, time) vectors (9 bytes/row), counts the pairs
-  of its own row block against all columns, then ONE int64 SUM all-reduce of the six counters
+  of its own row tiles (dealt out round-robin in sorted order) against all columns, then ONE int64 SUM all-reduce of the six counters
   (48 bytes) -- integer, so the result is bit-identical to the single-GPU result.
 * Cox loss (BINNED mode): every rank accumulates per-bin aggregates of its own rows
   (b200surv_cox_binned_partial; 32.32 fixed-point integers), ONE int64 SUM all-reduce of
@@ -40,12 +40,20 @@ def _world():
 
 # ------------------------------------------------------------------ C-index
 def cindex_counts_sharded(estimate, event, time, tied_tol=1e-8, algo=1, group=None, _count_fn=None):
-    """All ranks pass the same full vectors; returns the global int64[6] counters on every rank."""
+    """All ranks pass the same full vectors; returns the global int64[6] counters on every rank.
+
+    On the GPU rank r counts the row TILES r, r + world, ... of the sorted event rows (cindex_counts_shard): its
+    kernel keeps the tile structure of the single-GPU run.  A caller-supplied ``_count_fn(est, ev, time, tol, a, b,
+    algo)`` (the CPU tests of this host logic) gets the contiguous row block ``shard_bounds(n, rank, world)``."""
     rank, world = _world()
-    a, b = shard_bounds(estimate.numel(), rank, world)
-    if _count_fn is None:
-        from .cindex import cindex_counts as _count_fn
-    counts = _count_fn(estimate, event, time, tied_tol, a, b, algo)
+    if _count_fn is None and algo == 1:
+        from .cindex import cindex_counts_shard
+        counts = cindex_counts_shard(estimate, event, time, rank, world, tied_tol)
+    else:
+        if _count_fn is None:
+            from .cindex import cindex_counts as _count_fn
+        a, b = shard_bounds(estimate.numel(), rank, world)
+        counts = _count_fn(estimate, event, time, tied_tol, a, b, algo)
     if world > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
     return counts

@@ -115,3 +115,20 @@ def test_packed_cohorts_match_per_cohort_counts(algo):
     for c, (a, b) in enumerate(zip(offs[:-1], offs[1:])):
         ref = oci.counts_brute(est[a:b], ev[a:b], t[a:b], 1e-8) if b > a else np.zeros(6, dtype=np.int64)
         assert (out[c] == ref).all(), (c, a, b)
+
+
+@pytest.mark.parametrize("n_shards", [2, 3, 8])
+def test_tile_shards_partition_the_pairs(n_shards):
+    """b200surv_cindex_counts_shard: the shards' counters add up to the single-GPU counters bit for bit (what the
+    multi-GPU int64 all-reduce relies on), on a cohort with time ties, risk ties and several row tiles."""
+    from multimodal_survival_prediction_b200 import synth
+    from multimodal_survival_prediction_b200.cindex import cindex_counts, cindex_counts_shard
+    lh, ev, t = synth.cohort(30_011, 21, risk_tie_frac=0.1)
+    x, e, tt = lh.cuda(), ev.cuda(), t.cuda()
+    full = cindex_counts(x, e, tt, 1e-8).cpu()
+    acc = torch.zeros(6, dtype=torch.int64)
+    for s in range(n_shards):
+        part = cindex_counts_shard(x, e, tt, s, n_shards, 1e-8).cpu()
+        assert (part >= 0).all()
+        acc += part
+    assert torch.equal(acc, full), (acc.tolist(), full.tolist())
