@@ -440,11 +440,12 @@ __device__ __noinline__ double log_f64(double x) { return log(x); }
 __device__ __noinline__ BinTerms bin_terms(long long Dq, long long Eq, int m, int efron) {
     BinTerms o;
     o.T = 0.0; o.G = 0.0; o.F = 0.0;
-    if (m <= 0) return o;
+    const bool empty = m <= 0;  // (no early return: the lanes of a block stay together; an empty bin computes on 1, 1)
+    if (empty) { m = 1; Dq = 1ll << FIX_BITS; Eq = 0; }
     const double md = (double)m, invm = 1.0 / md;
     const double D = (double)Dq * FIX_INV, invD = 1.0 / D;
     double T = md * log_f64(D);
-    if (!efron) { o.T = T; o.G = md * invD; return o; }
+    if (!efron) { o.T = empty ? 0.0 : T; o.G = empty ? 0.0 : md * invD; return o; }
     const double r = ((double)Eq * FIX_INV) * invD;  // in [0, 1]: the bin's events are part of its risk set
     const double a = r * invm;
     int L = m;
@@ -497,7 +498,7 @@ __device__ __noinline__ BinTerms bin_terms(long long Dq, long long Eq, int m, in
         }
         T += log_f64(prod);
     }
-    o.T = T; o.G = sg * invD; o.F = sf * invD;
+    o.T = empty ? 0.0 : T; o.G = empty ? 0.0 : sg * invD; o.F = empty ? 0.0 : sf * invD;
     return o;
 }
 
@@ -731,6 +732,43 @@ __device__ __forceinline__ unsigned long long wait_flagged(const unsigned long l
     for (int it = 0; !(v & SLOT_FLAG) && it < SLOT_SPIN_MAX; ++it) v = ld_slot(p);
     return v & ~SLOT_FLAG;
 }
+// Look-back with all of a lane's loads in flight together: word `w` of the slots k0 + lane + 32 j (j < LB_MAX) that
+// lie below kend, each re-read until published (rare: the words are usually there when the reader arrives; issued one
+// after the other the round trips added up to 3 us for the blocks that need all 128 words).
+constexpr int LB_MAX = B200SURV_COX_MAX_BINS / 32 / 32;  // 8
+template <bool FLAGGED>
+__device__ __forceinline__ bool slot_ready(unsigned long long v) { return FLAGGED ? (v & SLOT_FLAG) != 0 : v != SLOT_EMPTY; }
+// Control flow stays WARP-UNIFORM (predicated loads, a vote decides whether to go round again): a warp that diverges
+// here keeps taking the slow path of every later shuffle (WARPSYNC.COLLECTIVE, ~250 ns each; measured).
+template <bool FLAGGED>
+__device__ __forceinline__ void lookback_words(const TailSlot *slots, int w, int k0, int kend, int lane,
+                                               unsigned long long (&v)[LB_MAX]) {
+    const int nj = (kend - k0 + 31) >> 5;  // uniform
+#pragma unroll
+    for (int j = 0; j < LB_MAX; ++j) {
+        const int k = k0 + lane + 32 * j;
+        v[j] = FLAGGED ? SLOT_FLAG : 0ull;
+        if (j < nj && k < kend) v[j] = ld_slot(reinterpret_cast<const unsigned long long *>(slots + k) + w);
+    }
+    for (int it = 0; it < SLOT_SPIN_MAX; ++it) {
+        bool pending = false;
+#pragma unroll
+        for (int j = 0; j < LB_MAX; ++j) {
+            const int k = k0 + lane + 32 * j;
+            if (j < nj && k < kend && !slot_ready<FLAGGED>(v[j])) {
+                v[j] = ld_slot(reinterpret_cast<const unsigned long long *>(slots + k) + w);
+                pending |= !slot_ready<FLAGGED>(v[j]);
+            }
+        }
+        if (!__any_sync(FULL, pending)) break;
+    }
+#pragma unroll
+    for (int j = 0; j < LB_MAX; ++j) {
+        const int k = k0 + lane + 32 * j;
+        if (FLAGGED) v[j] &= ~SLOT_FLAG;
+        if (!(j < nj && k < kend)) v[j] = 0ull;
+    }
+}
 __device__ __forceinline__ double wait_double(const unsigned long long *p) {
     unsigned long long v = ld_slot(p);
     for (int it = 0; v == SLOT_EMPTY && it < SLOT_SPIN_MAX; ++it) v = ld_slot(p);
@@ -820,6 +858,8 @@ __device__ __noinline__ void tail_block(const TailArgs &a, int blk, int lane, lo
     TailSlot *slots = a.slots;
     const int nblk = a.nb >> 5;
     const bool tr = a.trace != nullptr && blk == 0 && lane == 0;
+#define BSTAMP(i) do { if (a.trace != nullptr) { if (lane == 0) a.trace[32 + 8 * blk + (i)] = global_timer_ns(); __syncwarp(); } } while (0)
+    BSTAMP(0);
     // ---- D: suffix sums (integers).  Publish the block total, look back over the later blocks.
     const long long sfx = suffix_scan(s, lane);
     const unsigned ne = __reduce_add_sync(FULL, (unsigned)m), nt = __reduce_add_sync(FULL, m > 0 ? 1u : 0u);
@@ -827,10 +867,13 @@ __device__ __noinline__ void tail_block(const TailArgs &a, int blk, int lane, lo
         st_slot(&slots[blk].A, (unsigned long long)sfx | SLOT_FLAG);
         st_slot(&slots[blk].C, ((unsigned long long)ne << 32) | nt | SLOT_FLAG);
     }
+    unsigned long long v[LB_MAX];
+    lookback_words<true>(slots, 0, blk + 1, nblk, lane, v);
     long long off = 0;
-    for (int k = blk + 1 + lane; k < nblk; k += 32) off += (long long)wait_flagged(&slots[k].A);
-    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < LB_MAX; ++j) off += (long long)v[j];
     off = warp_sum(off);
+    BSTAMP(1);
     if (tr) a.trace[7] = global_timer_ns();
     // ---- per-bin terms, level-1 scans, publish the block totals
     const BinTerms bt = bin_terms(off + sfx, e, m, a.efron);
@@ -840,23 +883,25 @@ __device__ __noinline__ void tail_block(const TailArgs &a, int blk, int lane, lo
         st_slot(&slots[blk].G, (unsigned long long)__double_as_longlong(gi));
         st_slot(&slots[blk].T, (unsigned long long)__double_as_longlong(ti));
     }
+    BSTAMP(2);
     if (tr) a.trace[8] = global_timer_ns();
     // ---- P: look back over the earlier blocks (levels 2 and 3 of the canonical tree)
     const int sblk = blk >> 5, pos = blk & 31;
-    double run_g = 0.0;
-    for (int s2 = 0; s2 < sblk; ++s2) {
-        const double v = wait_double(&slots[32 * s2 + lane].G);
-        __syncwarp();
-        run_g += __shfl_sync(FULL, hs_scan(v, lane), 31);
+    lookback_words<false>(slots, 2, 0, blk, lane, v);  // G of the blocks [0, blk): lane l holds blocks l, l + 32, ...
+    double run_g = 0.0, ex = 0.0;
+#pragma unroll
+    for (int j = 0; j < LB_MAX; ++j) {
+        if (j <= sblk) {  // (zero from this block on: the inclusive scan at a lane only depends on the lanes before it)
+            const double ig = hs_scan(__longlong_as_double((long long)v[j]), lane);
+            if (j < sblk) run_g += __shfl_sync(FULL, ig, 31);
+            else ex = __shfl_sync(FULL, ig, pos > 0 ? pos - 1 : 0);
+        }
     }
-    double vg = 0.0;  // (zero from this block on: the inclusive scan at a lane only depends on the lanes before it)
-    if (lane < pos) vg = wait_double(&slots[32 * sblk + lane].G);
-    __syncwarp();
-    const double ig = hs_scan(vg, lane);
-    const double ex = __shfl_sync(FULL, ig, pos > 0 ? pos - 1 : 0);
     const double P = (run_g + (pos > 0 ? ex : 0.0)) + gi;
     a.table[32 * blk + lane] = make_float2((float)P, (float)bt.F);
+    BSTAMP(3);
     if (tr) a.trace[9] = global_timer_ns();
+#undef BSTAMP
 }
 
 // Loss and header, by a warp that owns no block: waits for the T totals and the event counts of all blocks, forms the
@@ -893,21 +938,18 @@ __device__ __noinline__ void tail_header(const TailArgs &a, int lane) {
         h.n_bad_time = warp_sum(w3);
         h.max_eta = a.peer_timeout ? 0.f : warp_max(mx);
     }
+    unsigned long long vc[LB_MAX], vt[LB_MAX];
+    lookback_words<true>(slots, 1, 0, nblk, lane, vc);
+    lookback_words<false>(slots, 3, 0, nblk, lane, vt);
     long long cnt_e = 0, cnt_t = 0;
-    for (int k = lane; k < nblk; k += 32) {
-        const unsigned long long c = wait_flagged(&slots[k].C);
-        cnt_e += (long long)(c >> 32); cnt_t += (long long)(c & 0xffffffffull);
-    }
-    __syncwarp();
-    cnt_e = warp_sum(cnt_e); cnt_t = warp_sum(cnt_t);
     double run_t = 0.0;
-    for (int s2 = 0; 32 * s2 < nblk; ++s2) {
-        const int k = 32 * s2 + lane;
-        double v = 0.0;
-        if (k < nblk) v = wait_double(&slots[k].T);
-        __syncwarp();
-        run_t += __shfl_sync(FULL, hs_scan(v, lane), min(31, nblk - 1 - 32 * s2));
+#pragma unroll
+    for (int j = 0; j < LB_MAX; ++j) {
+        cnt_e += (long long)(vc[j] >> 32); cnt_t += (long long)(vc[j] & 0xffffffffull);
+        if (32 * j < nblk)
+            run_t += __shfl_sync(FULL, hs_scan(__longlong_as_double((long long)vt[j]), lane), min(31, nblk - 1 - 32 * j));
     }
+    cnt_e = warp_sum(cnt_e); cnt_t = warp_sum(cnt_t);
     h.n_events = cnt_e; h.n_times = cnt_t; h.T = run_t; h.peer_timeout = a.peer_timeout;
     if (lane == 0) {
         write_header(h, a.efron, a.reduction, a.shift, a.nb, a.hdr, a.out_loss);
@@ -1185,7 +1227,7 @@ BinnedLayout binned_layout(int64_t n, int64_t n_seg, int nb) {
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     L.off_status = take(sizeof(int));
-    L.off_trace = take(16 * sizeof(long long));
+    L.off_trace = take((32 + 8 * 256) * sizeof(long long));
     L.off_slots = take((size_t)(nb / 32) * sizeof(TailSlot));
     L.off_partial = take((size_t)n_seg * L.nctas * PARTIAL_BYTES_PER_BIN * nb);
     L.off_recs = take((size_t)n_seg * L.nctas * sizeof(CtaRec));

@@ -69,18 +69,14 @@ class Variant:
                 out += f"   => SM clock {(cy[9] - cy[0]) / (tr[9] - tr[0]) * 1e3:.0f} MHz"
         if os.environ.get("BLOCK_TRACE"):
             bt = self.ws[off + 8 * 32:off + 8 * (32 + 8 * 128)].view(torch.int64).cpu().view(128, 8)
-            rel = (bt[:, :6] - tr[0]).double() / 1e3
-            out += "\n   per-block stamps (us): entry / wait1 / A summed / G published / wait2 / table"
+            rel = (bt[:, :4] - tr[0]).double() / 1e3
+            out += "\n   per-block stamps (us): entry / A look-back done / G published / table written"
             for nm, fn in (("min", rel.min(0).values), ("median", rel.median(0).values), ("max", rel.max(0).values)):
                 out += f"\n      {nm:6s} " + " ".join(f"{x:7.1f}" for x in fn.tolist())
-            relx = (bt - tr[0]).double() / 1e3
-            out += "\n      bin_terms per block (us): " + " ".join(f"{x:.1f}" for x in (relx[:, 6] - relx[:, 2]).tolist())
-            out += "\n      hs_scans per block (us): " + " ".join(f"{x:.1f}" for x in (relx[:, 7] - relx[:, 6]).tolist())
-            out += "\n      publish per block (us): " + " ".join(f"{x:.1f}" for x in (relx[:, 3] - relx[:, 7]).tolist())
-            lt = self.ws[off + 8 * (32 + 8 * 256):off + 8 * (32 + 8 * 256 + 32 * 128)].view(torch.int64).cpu().view(128, 32)
-            for b in (0, 1, 21, 30, 64, 125):
-                out += f"\n      bin_terms cycles per lane, block {b}: " + " ".join(str(int(x)) for x in lt[b].tolist())
-            out += "\n      slowest G-publishers: " + ", ".join(f"blk {int(i)} {rel[int(i), 3]:.1f}" for i in rel[:, 3].argsort(descending=True)[:6])
+            out += "\n      entry per block: " + " ".join(f"{x:.1f}" for x in rel[:, 0].tolist())
+            out += "\n      lb1   per block: " + " ".join(f"{x:.1f}" for x in rel[:, 1].tolist())
+            out += "\n      terms per block: " + " ".join(f"{x:.1f}" for x in (rel[:, 2] - rel[:, 1]).tolist())
+            out += "\n      lb2   per block: " + " ".join(f"{x:.1f}" for x in (rel[:, 3] - rel[:, 2]).tolist())
         return out
 
 
