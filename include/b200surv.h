@@ -141,17 +141,18 @@ int32_t b200surv_cox_binned_finalize(const int64_t *bins_sum, const float *bins_
  * NCCL call on the data path.  Every rank of the box allocates one peer buffer of
  * b200surv_cox_peer_buffer_bytes(nbins) bytes, zero-filled once, that all ranks can address (CUDA IPC / VMM
  * fabric handles / torch symmetric memory); peer_bufs[r] (HOST array of `world` device pointers, 256-byte
- * aligned) is rank r's buffer as mapped into THIS process.  One cooperative launch per rank: pass 1 ->
- * per-bin int64 sums into this rank's slot -> flag to every peer, wait for every peer's flag (2 s time-out
- * -> B200SURV_COXF_PEER_TIMEOUT, loss NaN) -> each CTA pulls its slice of bins from all peers and adds them
- * -> scan, Efron terms, loss, header and (P,F) table exactly as b200surv_cox_fwd.  Integer sums: every rank
- * obtains the bit-identical loss for any sharding.  epoch: 1, 2, 3, ... the same sequence on every rank
- * (slots are double-buffered on its parity); n, log_hz, time, event are the rank-local rows.  Then
- * b200surv_cox_bwd(mode BINNED) on the local rows. */
+ * aligned) is rank r's buffer as mapped into THIS process.  One cooperative launch per rank: pass 1 -> per-bin
+ * int64 sums -> the warp that owns a 32-bin block PUSHES its sums into every peer's buffer (plain remote stores,
+ * each 64-bit word tagged with epoch & 3 in its top bits: a word is its own "arrived" mark, so there is no flag, no
+ * fence and no extra barrier), polls its own buffer until every source's words carry the tag (2 s time-out ->
+ * B200SURV_COXF_PEER_TIMEOUT, loss NaN) and adds them -> the O(nbins) tail, loss, header and (P,F) table exactly as
+ * b200surv_cox_fwd.  Integer sums: every rank obtains the bit-identical loss for any sharding.  epoch: 1, 2, 3, ...
+ * the same sequence on every rank (slots are double-buffered on its parity); n, log_hz, time, event are the
+ * rank-local rows.  Then b200surv_cox_bwd(mode BINNED) on the local rows. */
 size_t b200surv_cox_peer_buffer_bytes(int32_t nbins);
 /* Diagnostics: with B200SURV_PEER_TRACE set in the environment, b200surv_cox_binned_fwd_peer leaves 11 int64
- * %globaltimer stamps (ns; kernel start, pass 1, reduce, flag sent, peers seen, pulled, Efron terms, end) at this
- * byte offset of the workspace. */
+ * %globaltimer stamps (ns; kernel start, pass 1, grid barrier, reduce, -, -, peers' sums added, look-back A, terms,
+ * look-back G, header) at this byte offset of the workspace. */
 size_t b200surv_cox_peer_trace_offset(int64_t n, int32_t nbins);
 /* Peer-buffer plumbing for callers without their own symmetric allocator: alloc (cudaMalloc on the current
  * device, zero-filled) returns the pointer and a 64-byte CUDA IPC handle to hand to the other ranks of the

@@ -777,18 +777,22 @@ __device__ __forceinline__ double wait_double(const unsigned long long *p) {
 
 // ---- multi-GPU exchange through peer memory (NVLink / NVSwitch), fused into the cooperative forward.
 // Every rank owns one "peer buffer" that all ranks of the box have mapped (symmetric allocation):
-//   [ flags: PEER_MAX_WORLD x 128 B, slot r is written by rank r ]
-//   [ slot 0 | slot 1 ]   each: int64 bins[3 nb + 4], float max[2]     (slot = epoch & 1)
-// Step k: a rank writes its own per-bin sums into its slot k&1, publishes flag[rank] = k in every peer's
-// buffer (release, system scope), waits until its own flags show k for every peer, then every block warp pulls
-// its 32 bins from every peer ((world-1) * 24 nb bytes per GPU over NVLink in total).  Integer sums, so every
-// rank obtains bit-identical totals.  Double buffering is enough: a rank rewrites slot k&1 in step k+2, after it
-// passed the barrier of step k+1, which every peer only signals once its step-k kernel (the one reading this
-// slot) has finished.
+//   [ slot 0 | slot 1 ]   slot = epoch & 1;  each slot: for every source rank r < PEER_MAX_WORLD
+//                         int64 words[3][nb] (S_cens, S_event, m of rank r's rows) and 8 scalar words
+// PUSH, no barrier, no flag, no fence: in step k the warp that owns a 32-bin block stores its rank-local sums
+// straight into every peer's buffer (region of source = this rank), each 64-bit word carrying the step's 2-bit tag
+// (k & 3, never 0 on first use) in its top bits; then it polls the same block in its OWN buffer until the words of
+// all sources show the tag, and adds them.  A word is its own "arrived" mark, so nothing has to be ordered against
+// anything.  Integer sums: every rank obtains bit-identical totals.  Double buffering is enough: a rank rewrites
+// slot k&1 in step k+2, after it has received every peer's step-k+1 words, which a peer only sends from its
+// step-k+1 kernel, i.e. after its step-k kernel (the reader of this slot) has finished.
 constexpr int PEER_MAX_WORLD = 16;
-constexpr int PEER_FLAG_STRIDE = 32;  // unsigned words (128 B)
-constexpr size_t PEER_FLAGS_BYTES = (size_t)PEER_MAX_WORLD * PEER_FLAG_STRIDE * sizeof(unsigned);
+constexpr int PEER_SCALARS = 8;  // sum of event log_hz, NOT_BINNABLE, ceil(sum w), BAD_TIME, max log_hz (float bits), 3 spare
+constexpr unsigned long long PEER_VAL_MASK = (1ull << 62) - 1;
 constexpr long long PEER_SPIN_LIMIT_NS = 2000000000ll;  // 2 s: a missing peer must not hang the GPU
+
+__host__ __device__ inline size_t peer_src_words(int nb) { return 3 * (size_t)nb + PEER_SCALARS; }
+__host__ __device__ inline size_t peer_slot_bytes(int nb) { return PEER_MAX_WORLD * peer_src_words(nb) * sizeof(long long); }
 
 struct PeerArgs {
     int world, rank;
@@ -797,27 +801,13 @@ struct PeerArgs {
     unsigned char *buf[PEER_MAX_WORLD];
 };
 
-__host__ __device__ inline size_t peer_slot_bytes(int nb) {
-    return ((3 * (size_t)nb + 4) * sizeof(long long) + 2 * sizeof(float) + 255) / 256 * 256;
-}
-
-__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ long long ld_relaxed_sys_s64(const long long *p) {
-    long long v;
-    asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ld_relaxed_sys_f32(const float *p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ long long global_timer_ns() {
     long long v;
@@ -844,10 +834,53 @@ struct TailArgs {
     const CtaRec *recs;  // single GPU: the header scalars come from the CTA records
     int nparts;
     const PeerArgs *peer;  // multi GPU: from the scalar words of every peer's slot
-    size_t peer_slot_off;
     int peer_timeout;
     long long *trace;
 };
+
+// Multi-GPU exchange of `nw` (<= 4) words per lane: store them, tagged, into every peer's buffer at word offset `off`
+// of this rank's source region, then poll the same words of every source in this rank's own buffer and add them up
+// (this rank's own contribution comes from the registers).  Warp-uniform control flow; returns false on time-out.
+__device__ __forceinline__ bool peer_push_sum(const PeerArgs &pa, int nb, const size_t (&off)[4], int nw, bool active,
+                                              long long (&val)[4]) {
+    const unsigned long long tag = (unsigned long long)(pa.epoch & 3u) << 62;
+    const size_t slot_words = (size_t)(pa.epoch & 1u) * PEER_MAX_WORLD * peer_src_words(nb);
+    const size_t src_words = peer_src_words(nb);
+    if (active) {
+        for (int p = 0; p < pa.world; ++p) {
+            if (p == pa.rank) continue;
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(pa.buf[p]) + slot_words + (size_t)pa.rank * src_words;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < nw) st_relaxed_sys_u64(dst + off[i], ((unsigned long long)val[i] & PEER_VAL_MASK) | tag);
+        }
+    }
+    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(pa.buf[pa.rank]) + slot_words;
+    const long long t0 = global_timer_ns();
+    bool ok = true;
+    for (int p = 0; p < pa.world; ++p) {  // (uniform trip count; the polls of one source are in flight together)
+        if (p == pa.rank) continue;
+        const unsigned long long *src = mine + (size_t)p * src_words;
+        unsigned long long w[4] = {tag, tag, tag, tag};
+        for (;;) {
+            bool pending = false;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (active && i < nw) { w[i] = ld_relaxed_sys_u64(src + off[i]); pending |= (w[i] >> 62) != (tag >> 62); }
+            if (!__any_sync(FULL, pending)) break;
+            if (global_timer_ns() - t0 > PEER_SPIN_LIMIT_NS) { ok = false; break; }
+        }
+        ok = __all_sync(FULL, ok);
+        if (!ok) break;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (active && i < nw) {  // 62-bit two's complement -> 64 bits
+                const long long x = (long long)(w[i] << 2) >> 2;
+                val[i] += x;
+            }
+    }
+    return ok;
+}
 
 // The tail of one 32-bin block, run by one warp (lane = bin).  s = S_cens + S_event, e = S_event (fixed point),
 // m = event count of the lane's bin.  Data flow, no barrier: the block waits for the A words of the later blocks and
@@ -910,7 +943,7 @@ __device__ __noinline__ void tail_header(const TailArgs &a, int lane) {
     TailSlot *slots = a.slots;
     const int nblk = a.nb >> 5;
     HeaderIn h;
-    if (a.peer == nullptr) {
+    {  // this rank's scalar words, from its CTA records
         double se = 0.0, sw = 0.0;
         float mx = -INFINITY;
         unsigned fl = 0;
@@ -922,21 +955,45 @@ __device__ __noinline__ void tail_header(const TailArgs &a, int lane) {
         se = warp_sum(se); sw = warp_sum(sw); mx = warp_max(mx); fl = warp_or(fl);
         h.sum_ev_eta_q = __double2ll_rn(se * ETA_SCALE);
         h.n_not_binnable = (fl & B200SURV_COXF_NOT_BINNABLE) ? 1 : 0;
-        h.sum_w_ceil = (long long)fmin(ceil(sw), 9.0e18);
+        h.sum_w_ceil = (long long)fmin(ceil(sw), 1.0e18);  // (fits the 62-bit words of the multi-GPU exchange)
         h.n_bad_time = (fl & B200SURV_COXF_BAD_TIME) ? 1 : 0;
         h.max_eta = mx;
-    } else {
-        long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-        float mx = -INFINITY;
-        if (lane < a.peer->world && !a.peer_timeout) {
-            const long long *ps = reinterpret_cast<const long long *>(a.peer->buf[lane] + a.peer_slot_off) + 3 * (size_t)a.nb;
-            w0 = ld_relaxed_sys_s64(ps); w1 = ld_relaxed_sys_s64(ps + 1); w2 = ld_relaxed_sys_s64(ps + 2);
-            w3 = ld_relaxed_sys_s64(ps + 3);
-            mx = ld_relaxed_sys_f32(reinterpret_cast<const float *>(ps + 4));
+    }
+    int peer_timeout = a.peer_timeout;
+    if (a.peer != nullptr) {  // add the other ranks' scalar words (lanes 0..3), maximum of max log_hz over the ranks
+        long long val[4] = {0, 0, 0, 0};
+        if (lane == 0) val[0] = h.sum_ev_eta_q;
+        if (lane == 1) val[0] = h.n_not_binnable;
+        if (lane == 2) val[0] = h.sum_w_ceil;
+        if (lane == 3) val[0] = h.n_bad_time;
+        const size_t off[4] = {3 * (size_t)a.nb + (size_t)(lane < 4 ? lane : 0), 0, 0, 0};
+        if (!peer_push_sum(*a.peer, a.nb, off, 1, lane < 4, val)) peer_timeout = 1;
+        h.sum_ev_eta_q = __shfl_sync(FULL, val[0], 0); h.n_not_binnable = __shfl_sync(FULL, val[0], 1);
+        h.sum_w_ceil = __shfl_sync(FULL, val[0], 2); h.n_bad_time = __shfl_sync(FULL, val[0], 3);
+        // the maximum: one word per source rank, lane p reads source p
+        const unsigned long long tag = (unsigned long long)(a.peer->epoch & 3u) << 62;
+        const size_t slot_words = (size_t)(a.peer->epoch & 1u) * PEER_MAX_WORLD * peer_src_words(a.nb);
+        const size_t word = 3 * (size_t)a.nb + 4;
+        if (lane < a.peer->world && lane != a.peer->rank)
+            st_relaxed_sys_u64(reinterpret_cast<unsigned long long *>(a.peer->buf[lane]) + slot_words +
+                                   (size_t)a.peer->rank * peer_src_words(a.nb) + word,
+                               (unsigned long long)__float_as_uint(h.max_eta) | tag);
+        float mx = h.max_eta;
+        const long long t0 = global_timer_ns();
+        for (;;) {
+            bool pending = false;
+            if (lane < a.peer->world && lane != a.peer->rank) {
+                const unsigned long long w = ld_relaxed_sys_u64(reinterpret_cast<const unsigned long long *>(a.peer->buf[a.peer->rank]) +
+                                                                slot_words + (size_t)lane * peer_src_words(a.nb) + word);
+                pending = (w >> 62) != (tag >> 62);
+                if (!pending) mx = __uint_as_float((unsigned)w);
+            }
+            if (!__any_sync(FULL, pending)) break;
+            if (global_timer_ns() - t0 > PEER_SPIN_LIMIT_NS) { peer_timeout = 1; break; }
         }
-        h.sum_ev_eta_q = warp_sum(w0); h.n_not_binnable = warp_sum(w1); h.sum_w_ceil = warp_sum(w2);
-        h.n_bad_time = warp_sum(w3);
-        h.max_eta = a.peer_timeout ? 0.f : warp_max(mx);
+        peer_timeout = __any_sync(FULL, peer_timeout != 0) ? 1 : 0;
+        h.max_eta = peer_timeout ? 0.f : warp_max(mx);
+        if (peer_timeout) { h.sum_ev_eta_q = 0; h.n_not_binnable = 0; h.sum_w_ceil = 0; h.n_bad_time = 0; }
     }
     unsigned long long vc[LB_MAX], vt[LB_MAX];
     lookback_words<true>(slots, 1, 0, nblk, lane, vc);
@@ -950,7 +1007,8 @@ __device__ __noinline__ void tail_header(const TailArgs &a, int lane) {
             run_t += __shfl_sync(FULL, hs_scan(__longlong_as_double((long long)vt[j]), lane), min(31, nblk - 1 - 32 * j));
     }
     cnt_e = warp_sum(cnt_e); cnt_t = warp_sum(cnt_t);
-    h.n_events = cnt_e; h.n_times = cnt_t; h.T = run_t; h.peer_timeout = a.peer_timeout;
+    h.n_events = cnt_e; h.n_times = cnt_t; h.T = run_t;
+    h.peer_timeout = (peer_timeout || (a.peer != nullptr && __ldcg(a.peer->status) != 0)) ? 1 : 0;
     if (lane == 0) {
         write_header(h, a.efron, a.reduction, a.shift, a.nb, a.hdr, a.out_loss);
         if (a.trace != nullptr) a.trace[10] = global_timer_ns();
@@ -1036,71 +1094,19 @@ cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__
     TRACE(3);
     const bool has_blk = warp < bpc && blk0 + warp < nblk;
     const int blk = blk0 + warp;
-    const size_t slot_off = PEER ? PEER_FLAGS_BYTES + (size_t)(pa.epoch & 1u) * peer_slot_bytes(nb) : 0;
     int peer_timeout = 0;
     if constexpr (PEER) {
-        // ---- publish this rank's sums, wait for every peer, pull and add their sums for this warp's block
-        __shared__ int s_timeout;
-        long long *own = reinterpret_cast<long long *>(pa.buf[pa.rank] + slot_off);
+        // ---- push this block's rank-local sums to every peer, wait for theirs, add (no barrier: see PeerArgs)
         if (has_blk) {
-            const int b = 32 * blk + lane;
-            own[b] = my_c; own[nb + b] = my_e; own[2 * (size_t)nb + b] = my_m;
-        }
-        if (cta == G - 1 && warp == P1_THREADS / 32 - 2) {  // the four scalar words and the maximum of this rank
-            double se = 0.0, sw = 0.0;
-            float mx = -INFINITY;
-            unsigned fl = 0;
-            for (int c = lane; c < nparts; c += 32) {
-                const CtaRec *rp = recs + c;
-                se += __ldcg(&rp->sum_ev_eta); sw += __ldcg(&rp->sum_w); mx = fmaxf(mx, __ldcg(&rp->max_eta));
-                fl |= __ldcg(&rp->flags);
+            const size_t b = 32 * (size_t)blk + lane;
+            const size_t off[4] = {b, (size_t)nb + b, 2 * (size_t)nb + b, 0};
+            long long val[4] = {my_c, my_e, (long long)my_m, 0};
+            if (!peer_push_sum(pa, nb, off, 3, true, val)) {  // a peer never arrived: leave an empty cohort behind
+                peer_timeout = 1;
+                val[0] = 0; val[1] = 0; val[2] = 0;
+                if (lane == 0) atomicExch(pa.status, 1);
             }
-            se = warp_sum(se); sw = warp_sum(sw); mx = warp_max(mx); fl = warp_or(fl);
-            if (lane == 0) {
-                own[3 * (size_t)nb + 0] = __double2ll_rn(se * ETA_SCALE);
-                own[3 * (size_t)nb + 1] = (fl & B200SURV_COXF_NOT_BINNABLE) ? 1 : 0;
-                own[3 * (size_t)nb + 2] = (long long)fmin(ceil(sw), 9.0e18);
-                own[3 * (size_t)nb + 3] = (fl & B200SURV_COXF_BAD_TIME) ? 1 : 0;
-                float *bmax = reinterpret_cast<float *>(own + 3 * (size_t)nb + 4);
-                bmax[0] = mx; bmax[1] = -1.f;
-            }
-        }
-        if (t == 0) s_timeout = 0;
-        grid.sync();  // the whole slot is written
-        TRACE(4);
-        if (cta == 0 && t < pa.world) {
-            __threadfence_system();
-            st_release_sys_u32(reinterpret_cast<unsigned *>(pa.buf[t]) + pa.rank * PEER_FLAG_STRIDE, pa.epoch);
-        }
-        TRACE(5);
-        if (t < pa.world) {
-            const unsigned *f = reinterpret_cast<const unsigned *>(pa.buf[pa.rank]) + t * PEER_FLAG_STRIDE;
-            const long long t0 = global_timer_ns();
-            while ((int)(ld_acquire_sys_u32(f) - pa.epoch) < 0) {
-                if (global_timer_ns() - t0 > PEER_SPIN_LIMIT_NS) { s_timeout = 1; break; }
-                __nanosleep(64);
-            }
-        }
-        __syncthreads();
-        peer_timeout = s_timeout;
-        if (peer_timeout && t == 0) atomicExch(pa.status, 1);
-        if (has_blk) {
-            my_c = 0; my_e = 0;
-            long long mm = 0;  // a peer that never arrived leaves an empty cohort behind (no stale sums)
-            if (!peer_timeout) {
-                const size_t b = 32 * (size_t)blk + lane;
-                long long vc[PEER_MAX_WORLD], ve[PEER_MAX_WORLD], vm[PEER_MAX_WORLD];
-#pragma unroll
-                for (int p = 0; p < PEER_MAX_WORLD; ++p) {  // all peers' loads in flight together
-                    const long long *ps = reinterpret_cast<const long long *>(pa.buf[p < pa.world ? p : 0] + slot_off);
-                    vc[p] = p < pa.world ? ld_relaxed_sys_s64(ps + b) : 0ll;
-                    ve[p] = p < pa.world ? ld_relaxed_sys_s64(ps + nb + b) : 0ll;
-                    vm[p] = p < pa.world ? ld_relaxed_sys_s64(ps + 2 * (size_t)nb + b) : 0ll;
-                }
-#pragma unroll
-                for (int p = 0; p < PEER_MAX_WORLD; ++p) { my_c += vc[p]; my_e += ve[p]; mm += vm[p]; }
-            }
-            my_m = (int)mm;
+            my_c = val[0]; my_e = val[1]; my_m = (int)val[2];
         }
         TRACE(6);
     }
@@ -1116,7 +1122,7 @@ cox_binned_fwd_fused(const float *__restrict__ log_hz, const float *__restrict__
         ta.hdr = reinterpret_cast<b200surv_cox_header *>(fa.state);
         ta.out_loss = fa.out_loss;
         ta.recs = recs; ta.nparts = nparts;
-        ta.peer = PEER ? &pa : nullptr; ta.peer_slot_off = slot_off; ta.peer_timeout = peer_timeout;
+        ta.peer = PEER ? &pa : nullptr; ta.peer_timeout = peer_timeout;
         ta.trace = fa.trace;
         if (has_blk) tail_block(ta, blk, lane, my_c + my_e, my_e, my_m);
         else tail_header(ta, lane);
@@ -1389,7 +1395,7 @@ int32_t cox_binned_fwd(const float *log_hz, const float *time, const uint8_t *ev
     return launch_finish(bins, bins_max, n_seg, ties, reduction, nb, shift, out_loss, state, L, w8, st);
 }
 
-size_t cox_binned_peer_buffer_bytes(int nb) { return PEER_FLAGS_BYTES + 2 * peer_slot_bytes(nb); }
+size_t cox_binned_peer_buffer_bytes(int nb) { return 2 * peer_slot_bytes(nb); }
 size_t cox_binned_peer_trace_offset(int64_t n, int nb) { return binned_layout(n, 1, nb).off_trace; }
 
 int32_t cox_binned_fwd_peer(const float *log_hz, const float *time, const uint8_t *event, int64_t n, int ties,
