@@ -44,53 +44,79 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons during the timed region, through NVML (a thread polling every ~0.5 ms: the timed
+    region of the default run is a few milliseconds, far shorter than nvidia-smi's sampling period) plus one
+    guaranteed sample right before and right after it; falls back to one `nvidia-smi` query when NVML is missing."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.samples, self.bits, self.stop_flag, self.th, self.h, self.nv = gpu_index, [], 0, False, None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu_index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip() != ""]
+            if i < len(ids) and ids[i].strip().isdigit():
+                return int(ids[i])
+        return i
+
+    def sample(self):
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            try:
+                self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self.stop_flag:
+            self.sample()
+            time.sleep(0.0005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+        self.sample()
+        if self.nv is not None:
+            self.th = threading.Thread(target=self._run, daemon=True)
             self.th.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        self.stop_flag = True
+        if self.th is not None:
+            self.th.join(timeout=2)
+        self.sample()
+        if self.nv is None or not self.samples:
+            return self._smi_once()
+        sm = sorted(self.samples)
+        reasons = sorted(k for k, bit in self.REASONS.items() if self.bits & bit)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                "source": "NVML, polled during the timed region"}
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc.wait(timeout=2)
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+            f = [x.strip() for x in out.split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]),
+                    "reasons": sorted(n for n, v in zip(names, f[2:]) if v.lower().startswith("active")), "samples": 1,
+                    "source": "nvidia-smi, one query after the timed region"}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx = float(f[2])
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if f[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
 def cpu_port_rate(rows, steps=1):
@@ -319,19 +345,19 @@ def run_b200(args):
                         if op.exchange == "peer" else f"row-block shards x{world}, NCCL all-reduce of per-bin int64 sums"),
                        "l2": "no flush needed: each step streams 151 MB in + 67 MB out, larger than the 126 MB L2"},
             "loss": loss_val,
-            # dominant kernel of the step = the fused forward (57 % of the step in the ncu launch list,
-            # profiles/r1_v13_launches.csv).  `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of one launch
-            # from the ncu --set full capture of this command (profiles/r1_v13_ncu_full_cox.csv), valid for the
+            # dominant kernel of the step = the fused forward (58 % of the step in the ncu launch list,
+            # profiles/r1_v14_launches.csv).  `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of one launch
+            # from the ncu --set full capture of this command (profiles/r1_v14_ncu_full_cox.csv), valid for the
             # default 16,777,216-row workload only.
             "roofline": {"bound": "hbm",
                          "kernel": ("cox_binned_fwd_fused (9 B/row read: pass 1 + reduce + O(nbins) tail in one cooperative launch)"
                                     if fused else "cox_binned_pass1 + reduce + all-reduce + finish (9 B/row read)"),
                          "achieved": achieved_fwd, "peak": peak, "unit": "GB/s", "frac": achieved_fwd / peak,
-                         "traffic": (151.086592e6 + 3.994368e6) if (fused and n == N_ROWS) else None,
+                         "traffic": (151.133696e6 + 3.794688e6) if (fused and n == N_ROWS) else None,
                          "peak_source": peak_src, "ms": fwd_ms,
                          "bwd": {"kernel": "cox_binned_bwd (13 B/row: 9 read + 4 written)", "achieved": achieved_bwd,
                                  "frac": achieved_bwd / peak, "ms": bwd_ms,
-                                 "traffic": (151.044352e6 + 33.467392e6) if n == N_ROWS else None,
+                                 "traffic": (151.043328e6 + 33.323264e6) if n == N_ROWS else None,
                                  "traffic_note": "gradient stores still in L2 when the kernel ends are not in dram__bytes_write"},
                          "step": {"bytes_per_row": ALGO_BYTES_PER_ROW, "achieved": achieved_step,
                                   "frac": achieved_step / peak, "frac_of_8TBs": achieved_step / 8000.0}},
