@@ -12,13 +12,12 @@
 //   #(e_j < lo) and #(e_j <= hi) over upper-triangular tiles only.  Column tiles are staged in shared
 //   memory and broadcast; each thread keeps 8 rows in registers; per-thread 32-bit counters are
 //   reduced with warp shuffles into int64 atomics once per CTA.
-// The radix sort / prefix sum of the preprocessing are CUB (library) in this round.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-
+// The radix sort and the prefix sum of the preprocessing are hand-written (sortscan.cuh: stable LSD radix sort,
+// single-pass scan with decoupled look-back).
 #include <climits>
 
 #include "common.cuh"
+#include "sortscan.cuh"
 
 namespace b200surv {
 namespace {
@@ -271,6 +270,15 @@ __global__ void k_ci_final(const Acc1 *acc, long long *out) {
     }
 }
 
+struct LoadIsRow {
+    const int *isrow;
+    __device__ sortscan::Tup operator()(int64_t p) const { sortscan::Tup t; t.a = 0.0; t.b = 0.0; t.i = isrow[p]; return t; }
+};
+struct StoreRank {  // exclusive prefix = index of the row among the selected event rows
+    int *rank;
+    __device__ void operator()(int64_t p, const sortscan::Tup &inc, const sortscan::Tup &el) const { rank[p] = (int)(inc.i - el.i); }
+};
+
 struct CiLayout {
     size_t off_acc, off_keys, off_vals, off_keys_s, off_idx_s, off_est_s, off_isrow, off_rank, off_lo, off_hi,
         off_s, off_ge, off_cub, cub_bytes, total;
@@ -284,13 +292,8 @@ CiLayout ci_layout(int64_t n) {
     L.off_keys = take(N * 4); L.off_vals = take(N * 4); L.off_keys_s = take(N * 4); L.off_idx_s = take(N * 4);
     L.off_est_s = take(N * 4 + 16); L.off_isrow = take(N * 4); L.off_rank = take(N * 4);
     L.off_lo = take(N * 4); L.off_hi = take(N * 4); L.off_s = take(N * 4); L.off_ge = take(N * 4);
-    size_t mx = 0, b = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (uint32_t *)nullptr, (int)N);
-    mx = b > mx ? b : mx;
-    cub::DeviceScan::ExclusiveSum(nullptr, b, (int *)nullptr, (int *)nullptr, (int)N);
-    mx = b > mx ? b : mx;
-    L.cub_bytes = mx + 256;
+    const size_t tmp = sortscan::radix_sort_temp_bytes((int64_t)N), sc = sortscan::scan_state_bytes((int64_t)N);
+    L.cub_bytes = (tmp > sc ? tmp : sc) + 256;
     L.off_cub = take(L.cub_bytes);
     L.total = o;
     return L;
@@ -331,15 +334,20 @@ int32_t cindex_counts_launch(const float *est, const float *time, const uint8_t 
     float *r_lo = reinterpret_cast<float *>(w8 + L.off_lo), *r_hi = reinterpret_cast<float *>(w8 + L.off_hi);
     int *r_s = reinterpret_cast<int *>(w8 + L.off_s), *r_ge = reinterpret_cast<int *>(w8 + L.off_ge);
     void *cub_tmp = w8 + L.off_cub;
-    size_t cb = L.cub_bytes;
     int grid = (int)((n + 255) / 256);
     const int cap = 16 * num_sms();
     if (grid > cap) grid = cap;
-    k_ci_keys<<<grid, 256, 0, st>>>(time, event, n, keys, vals, acc);
-    B200_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys, keys_s, vals, idx_s, (int)n, 0, 32, st));
+    // keys are generated into (keys_s, idx_s): four ping-pong passes leave the sorted pairs there
+    k_ci_keys<<<grid, 256, 0, st>>>(time, event, n, keys_s, idx_s, acc);
+    {
+        const int32_t rc = sortscan::radix_sort_pairs(keys_s, idx_s, keys, vals, n, 32, cub_tmp, st);
+        if (rc) return rc;
+    }
     k_ci_flag<<<grid, 256, 0, st>>>(est, keys_s, idx_s, n, row_begin, row_end, est_s, isrow);
-    cb = L.cub_bytes;
-    B200_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cb, isrow, rank, (int)n, st));
+    {
+        const int32_t rc = sortscan::scan_lookback<sortscan::I_ADD, false>(n, LoadIsRow{isrow}, StoreRank{rank}, cub_tmp, st);
+        if (rc) return rc;
+    }
     k_ci_rows<<<grid, 256, 0, st>>>(keys_s, est_s, isrow, rank, n, tol, r_lo, r_hi, r_s, r_ge, shard, n_shards, acc);
     {
         // upper bound on selected rows known to the host: min(n, row_end - row_begin)

@@ -5,33 +5,19 @@
 //   D = sum_{q >= gs} w_q,  E, m = segmented sums over the group,  l = p - gs for event rows,
 //   a_p = 1/(D - (l/m)E), f_p = (l/m) a_p,  P = prefix sum of a up to ge-1,  F = segmented sum of f,
 //   grad = scale * (d - w (P - d F)).
-// The radix sort and the device-wide scans are CUB (CCCL header library shipped with CUDA 12.9) in
-// this round: library code, not a hand-written kernel -- the headline path is cox_binned.cu.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#include <thrust/iterator/reverse_iterator.h>
-
+// The radix sort and the three device-wide scans are hand-written (sortscan.cuh): a stable LSD radix sort on
+// (time, event) keys and single-pass scans with decoupled look-back --
+//   R1 (reverse): D = suffix sums of w, ge = end of the row's tie group (min-scan)
+//   F1 (forward): prefix sums of the event weights and of the event count, gs = start of the tie group (max-scan);
+//                 a group's E and m are differences of the prefix sums at its two ends
+//   F2 (forward): prefix sums of a and f (F of a group again as a difference)
 #include <climits>
 
 #include "common.cuh"
+#include "sortscan.cuh"
 
 namespace b200surv {
 namespace {
-
-struct EM {
-    double e;
-    int m;
-    int gs;
-};
-struct SumEM {
-    __host__ __device__ EM operator()(const EM &a, const EM &b) const { return EM{a.e + b.e, a.m + b.m, a.gs}; }
-};
-struct SumD {
-    __host__ __device__ double operator()(double a, double b) const { return a + b; }
-};
-struct MinI {
-    __host__ __device__ int operator()(int a, int b) const { return a < b ? a : b; }
-};
 
 struct Acc {  // device accumulators
     double sum_eta, sum_log;
@@ -78,30 +64,62 @@ k_make_keys(const float *__restrict__ log_hz, const float *__restrict__ time,
     }
 }
 
-// sorted rows: weights, group keys, scan inputs
+// sorted rows: weights
 __global__ void __launch_bounds__(256)
-k_gather(const float *__restrict__ log_hz, const uint32_t *__restrict__ keys_s,
-         const uint32_t *__restrict__ idx_s, int64_t n, const Acc *__restrict__ acc,
-         double *__restrict__ w, uint32_t *__restrict__ grp, EM *__restrict__ em,
-         int *__restrict__ tailv) {
+k_gather(const float *__restrict__ log_hz, const uint32_t *__restrict__ idx_s, int64_t n, const Acc *__restrict__ acc,
+         double *__restrict__ w) {
     const double c = (double)acc->max_eta;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t k = keys_s[p];
-        const int d = (k & 1u) ? 0 : 1;
-        const double wp = exp((double)log_hz[idx_s[p]] - c);
-        w[p] = wp;
-        grp[p] = k >> 1;
-        em[p] = EM{d ? wp : 0.0, d, (int)p};
-        const bool tail = (p == n - 1) || ((keys_s[p + 1] >> 1) != (k >> 1));
-        tailv[p] = tail ? (int)(p + 1) : INT_MAX;
-    }
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+        w[p] = exp((double)log_hz[idx_s[p]] - c);
 }
+
+// scan functors (see sortscan.cuh: Tup = {a, b: fp64 sums; i: integer with add / min / max})
+struct LoadR1 {   // a = w, i = p + 1 at the last row of a tie group
+    const double *w; const uint32_t *keys_s; int64_t n;
+    __device__ sortscan::Tup operator()(int64_t p) const {
+        sortscan::Tup t;
+        t.a = w[p]; t.b = 0.0;
+        const bool tail = (p == n - 1) || ((keys_s[p + 1] >> 1) != (keys_s[p] >> 1));
+        t.i = tail ? p + 1 : LLONG_MAX;
+        return t;
+    }
+};
+struct StoreR1 {
+    double *D; int *ge;
+    __device__ void operator()(int64_t p, const sortscan::Tup &inc, const sortscan::Tup &) const { D[p] = inc.a; ge[p] = (int)inc.i; }
+};
+struct LoadF1 {   // a = event weight, b = event indicator, i = p at the first row of a tie group
+    const double *w; const uint32_t *keys_s;
+    __device__ sortscan::Tup operator()(int64_t p) const {
+        sortscan::Tup t;
+        const uint32_t k = keys_s[p];
+        const bool d = !(k & 1u);
+        t.a = d ? w[p] : 0.0; t.b = d ? 1.0 : 0.0;
+        const bool head = (p == 0) || ((keys_s[p - 1] >> 1) != (k >> 1));
+        t.i = head ? p : -1;
+        return t;
+    }
+};
+struct StoreF1 {
+    double *prefE, *cntE; int *gs;
+    __device__ void operator()(int64_t p, const sortscan::Tup &inc, const sortscan::Tup &) const {
+        prefE[p] = inc.a; cntE[p] = inc.b; gs[p] = (int)inc.i;
+    }
+};
+struct LoadF2 {
+    const double *a, *f;
+    __device__ sortscan::Tup operator()(int64_t p) const { sortscan::Tup t; t.a = a[p]; t.b = f[p]; t.i = 0; return t; }
+};
+struct StoreF2 {
+    double *PA, *PF;
+    __device__ void operator()(int64_t p, const sortscan::Tup &inc, const sortscan::Tup &) const { PA[p] = inc.a; PF[p] = inc.b; }
+};
 
 __global__ void __launch_bounds__(256)
 k_terms(const float *__restrict__ log_hz, const uint32_t *__restrict__ keys_s,
         const uint32_t *__restrict__ idx_s, int64_t n, int ties, const double *__restrict__ Dpos,
-        const EM *__restrict__ em_s, const int *__restrict__ ge, Acc *acc, double *__restrict__ a,
-        double *__restrict__ f) {
+        const double *__restrict__ prefE, const double *__restrict__ cntE, const int *__restrict__ gsv,
+        const int *__restrict__ ge, Acc *acc, double *__restrict__ a, double *__restrict__ f) {
     __shared__ double red_d[32];
     __shared__ long long red_l[32];
     const double c = (double)acc->max_eta;
@@ -110,12 +128,16 @@ k_terms(const float *__restrict__ log_hz, const uint32_t *__restrict__ keys_s,
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
         double ap = 0.0, fp = 0.0;
         if (!(keys_s[p] & 1u)) {
-            const int gs = em_s[p].gs, gend = ge[p];
-            const EM tot = em_s[gend - 1];
+            const int gs = gsv[p], gend = ge[p];
             const double D = Dpos[gs];
             const int l = (int)p - gs;
             double den = D, frac = 0.0;
-            if (ties == B200SURV_TIES_EFRON) { frac = (double)l / (double)tot.m; den = D - frac * tot.e; }
+            if (ties == B200SURV_TIES_EFRON) {
+                const double E = prefE[gend - 1] - (gs > 0 ? prefE[gs - 1] : 0.0);
+                const double m = cntE[gend - 1] - (gs > 0 ? cntE[gs - 1] : 0.0);
+                frac = (double)l / m;
+                den = D - frac * E;
+            }
             ap = 1.0 / den;
             fp = frac / den;
             sum_log += log(den) + c;
@@ -154,14 +176,15 @@ __device__ __forceinline__ void loss_from_acc(const Acc *acc, int ties, int redu
 __global__ void __launch_bounds__(256)
 k_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ idx_s, int64_t n, int ties,
        int reduction, const double *__restrict__ w, const double *__restrict__ PA,
-       const double *__restrict__ PF, const int *__restrict__ ge, const Acc *__restrict__ acc,
+       const double *__restrict__ PF, const int *__restrict__ gsv, const int *__restrict__ ge, const Acc *__restrict__ acc,
        float *__restrict__ grad_unit, float *__restrict__ out_loss, b200surv_cox_header *hdr) {
     double loss, scale, pll;
     loss_from_acc(acc, ties, reduction, &loss, &scale, &pll);
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
         const double d = (keys_s[p] & 1u) ? 0.0 : 1.0;
-        const int gend = ge[p];
-        const double g = d - w[p] * (PA[gend - 1] - d * PF[gend - 1]);
+        const int gs = gsv[p], gend = ge[p];
+        const double F = PF[gend - 1] - (gs > 0 ? PF[gs - 1] : 0.0);
+        const double g = d - w[p] * (PA[gend - 1] - d * F);
         grad_unit[idx_s[p]] = (float)(scale * g);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -174,8 +197,8 @@ k_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ idx_s, 
 }
 
 struct SortedLayout {
-    size_t off_acc, off_keys, off_vals, off_keys_s, off_idx_s, off_w, off_grp, off_em, off_em_s, off_tail,
-        off_ge, off_D, off_a, off_f, off_PA, off_PF, off_cub, cub_bytes, total;
+    size_t off_acc, off_keys, off_vals, off_keys_s, off_idx_s, off_w, off_gs, off_ge, off_D, off_prefE, off_cntE, off_a,
+        off_f, off_PA, off_PF, off_tmp, total;
 };
 
 SortedLayout sorted_layout(int64_t n) {
@@ -185,29 +208,11 @@ SortedLayout sorted_layout(int64_t n) {
     const size_t N = (size_t)(n > 0 ? n : 1);
     L.off_acc = take(sizeof(Acc));
     L.off_keys = take(N * 4); L.off_vals = take(N * 4); L.off_keys_s = take(N * 4); L.off_idx_s = take(N * 4);
-    L.off_w = take(N * 8); L.off_grp = take(N * 4); L.off_em = take(N * sizeof(EM)); L.off_em_s = take(N * sizeof(EM));
-    L.off_tail = take(N * 4); L.off_ge = take(N * 4); L.off_D = take(N * 8);
+    L.off_w = take(N * 8); L.off_gs = take(N * 4); L.off_ge = take(N * 4); L.off_D = take(N * 8);
+    L.off_prefE = take(N * 8); L.off_cntE = take(N * 8);
     L.off_a = take(N * 8); L.off_f = take(N * 8); L.off_PA = take(N * 8); L.off_PF = take(N * 8);
-    // CUB temp storage: max over the calls made below (size queries launch nothing)
-    size_t mx = 0, b = 0;
-    const int ni = (int)N;
-    cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (uint32_t *)nullptr, ni);
-    mx = b > mx ? b : mx;
-    cub::DeviceScan::InclusiveScan(nullptr, b, thrust::make_reverse_iterator((double *)nullptr),
-                                   thrust::make_reverse_iterator((double *)nullptr), SumD(), ni);
-    mx = b > mx ? b : mx;
-    cub::DeviceScan::InclusiveScan(nullptr, b, thrust::make_reverse_iterator((int *)nullptr),
-                                   thrust::make_reverse_iterator((int *)nullptr), MinI(), ni);
-    mx = b > mx ? b : mx;
-    cub::DeviceScan::InclusiveScan(nullptr, b, (double *)nullptr, (double *)nullptr, SumD(), ni);
-    mx = b > mx ? b : mx;
-    cub::DeviceScan::InclusiveScanByKey(nullptr, b, (uint32_t *)nullptr, (EM *)nullptr, (EM *)nullptr, SumEM(), ni);
-    mx = b > mx ? b : mx;
-    cub::DeviceScan::InclusiveScanByKey(nullptr, b, (uint32_t *)nullptr, (double *)nullptr, (double *)nullptr, SumD(), ni);
-    mx = b > mx ? b : mx;
-    L.cub_bytes = mx + 256;
-    L.off_cub = take(L.cub_bytes);
+    size_t tmp = sortscan::radix_sort_temp_bytes((int64_t)N), sc = sortscan::scan_state_bytes((int64_t)N);
+    L.off_tmp = take(tmp > sc ? tmp : sc);
     L.total = o;
     return L;
 }
@@ -231,42 +236,34 @@ int32_t cox_sorted_fwd_launch(const float *log_hz, const float *time, const uint
     uint32_t *keys = reinterpret_cast<uint32_t *>(w8 + L.off_keys), *vals = reinterpret_cast<uint32_t *>(w8 + L.off_vals);
     uint32_t *keys_s = reinterpret_cast<uint32_t *>(w8 + L.off_keys_s), *idx_s = reinterpret_cast<uint32_t *>(w8 + L.off_idx_s);
     double *w = reinterpret_cast<double *>(w8 + L.off_w);
-    uint32_t *grp = reinterpret_cast<uint32_t *>(w8 + L.off_grp);
-    EM *em = reinterpret_cast<EM *>(w8 + L.off_em), *em_s = reinterpret_cast<EM *>(w8 + L.off_em_s);
-    int *tailv = reinterpret_cast<int *>(w8 + L.off_tail), *ge = reinterpret_cast<int *>(w8 + L.off_ge);
-    double *Dpos = reinterpret_cast<double *>(w8 + L.off_D), *a = reinterpret_cast<double *>(w8 + L.off_a),
+    int *gs = reinterpret_cast<int *>(w8 + L.off_gs), *ge = reinterpret_cast<int *>(w8 + L.off_ge);
+    double *Dpos = reinterpret_cast<double *>(w8 + L.off_D), *prefE = reinterpret_cast<double *>(w8 + L.off_prefE),
+           *cntE = reinterpret_cast<double *>(w8 + L.off_cntE), *a = reinterpret_cast<double *>(w8 + L.off_a),
            *f = reinterpret_cast<double *>(w8 + L.off_f), *PA = reinterpret_cast<double *>(w8 + L.off_PA),
            *PF = reinterpret_cast<double *>(w8 + L.off_PF);
-    void *cub_tmp = w8 + L.off_cub;
-    size_t cb = L.cub_bytes;
-    const int ni = (int)n;
+    void *tmp = w8 + L.off_tmp;
     int grid = (int)((n + 255) / 256);
     const int cap = 16 * num_sms();
     if (grid > cap) grid = cap;
 
     b200surv_cox_header *hdr = static_cast<b200surv_cox_header *>(state);
     float *grad_unit = reinterpret_cast<float *>(hdr + 1);
+    int32_t rc;
 
     k_init_acc<<<1, 32, 0, st>>>(acc);
-    k_make_keys<<<grid, 256, 0, st>>>(log_hz, time, event, n, keys, vals, acc);
-    B200_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys, keys_s, vals, idx_s, ni, 0, 32, st));
-    k_gather<<<grid, 256, 0, st>>>(log_hz, keys_s, idx_s, n, acc, w, grp, em, tailv);
-    cb = L.cub_bytes;
-    B200_CHECK_CUDA(cub::DeviceScan::InclusiveScan(cub_tmp, cb, thrust::make_reverse_iterator(w + n),
-                                                   thrust::make_reverse_iterator(Dpos + n), SumD(), ni, st));
-    cb = L.cub_bytes;
-    B200_CHECK_CUDA(cub::DeviceScan::InclusiveScan(cub_tmp, cb, thrust::make_reverse_iterator(tailv + n),
-                                                   thrust::make_reverse_iterator(ge + n), MinI(), ni, st));
-    cb = L.cub_bytes;
-    B200_CHECK_CUDA(cub::DeviceScan::InclusiveScanByKey(cub_tmp, cb, grp, em, em_s, SumEM(), ni,
-                                                        ::cuda::std::equal_to<>(), st));
-    k_terms<<<grid, 256, 0, st>>>(log_hz, keys_s, idx_s, n, ties, Dpos, em_s, ge, acc, a, f);
-    cb = L.cub_bytes;
-    B200_CHECK_CUDA(cub::DeviceScan::InclusiveScan(cub_tmp, cb, a, PA, SumD(), ni, st));
-    cb = L.cub_bytes;
-    B200_CHECK_CUDA(cub::DeviceScan::InclusiveScanByKey(cub_tmp, cb, grp, f, PF, SumD(), ni,
-                                                        ::cuda::std::equal_to<>(), st));
-    k_grad<<<grid, 256, 0, st>>>(keys_s, idx_s, n, ties, reduction, w, PA, PF, ge, acc, grad_unit, out_loss, hdr);
+    // keys are generated into (keys_s, idx_s): four ping-pong passes leave the sorted pairs there
+    k_make_keys<<<grid, 256, 0, st>>>(log_hz, time, event, n, keys_s, idx_s, acc);
+    rc = sortscan::radix_sort_pairs(keys_s, idx_s, keys, vals, n, 32, tmp, st);
+    if (rc) return rc;
+    k_gather<<<grid, 256, 0, st>>>(log_hz, idx_s, n, acc, w);
+    rc = sortscan::scan_lookback<sortscan::I_MIN, true>(n, LoadR1{w, keys_s, n}, StoreR1{Dpos, ge}, tmp, st);
+    if (rc) return rc;
+    rc = sortscan::scan_lookback<sortscan::I_MAX, false>(n, LoadF1{w, keys_s}, StoreF1{prefE, cntE, gs}, tmp, st);
+    if (rc) return rc;
+    k_terms<<<grid, 256, 0, st>>>(log_hz, keys_s, idx_s, n, ties, Dpos, prefE, cntE, gs, ge, acc, a, f);
+    rc = sortscan::scan_lookback<sortscan::I_ADD, false>(n, LoadF2{a, f}, StoreF2{PA, PF}, tmp, st);
+    if (rc) return rc;
+    k_grad<<<grid, 256, 0, st>>>(keys_s, idx_s, n, ties, reduction, w, PA, PF, gs, ge, acc, grad_unit, out_loss, hdr);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }

@@ -1,0 +1,321 @@
+// Hand-written device-wide primitives for the SORTED Cox path and the C-index preprocessing (sm_100a):
+//   * scan_lookback  -- single-pass inclusive scan with DECOUPLED LOOK-BACK over tiles of 2048 elements, forward or
+//                       reverse, of a small tuple (two fp64 sums + one integer with add / min / max).  Fence-free:
+//                       every 64-bit word a tile publishes (its aggregate, its inclusive prefix) is its own "valid"
+//                       mark (SCAN_EMPTY until written), so there is no status flag to order the payload against
+//                       (a gpu-scope fence costs microseconds on this part -- see DESIGN.md 3.1).  Tile ids are
+//                       handed out by an atomic counter, so a tile's predecessors are always running or done.
+//   * radix_sort_pairs -- stable LSD radix sort of (u32 key, u32 value) pairs, 8 bits per pass: per-tile digit
+//                       histograms, one exclusive scan of the (digit, tile) matrix (scan_lookback), stable scatter
+//                       with warp-level match ranking.
+// They replace cub::DeviceScan / cub::DeviceRadixSort in cox_sorted.cu and cindex.cu.
+#pragma once
+#include <climits>
+
+#include "common.cuh"
+
+namespace b200surv {
+namespace sortscan {
+
+// ------------------------------------------------------------------------------------------------ scan
+struct Tup {
+    double a, b;   // summed
+    long long i;   // combined with IOP
+};
+enum IntOp { I_ADD = 0, I_MIN = 1, I_MAX = 2 };
+
+template <int IOP>
+__device__ __forceinline__ Tup tup_identity() {
+    Tup t;
+    t.a = 0.0; t.b = 0.0;
+    t.i = IOP == I_ADD ? 0ll : (IOP == I_MIN ? LLONG_MAX : LLONG_MIN);
+    return t;
+}
+// `x` precedes `y` in scan order
+template <int IOP>
+__device__ __forceinline__ Tup tup_combine(const Tup &x, const Tup &y) {
+    Tup t;
+    t.a = x.a + y.a; t.b = x.b + y.b;
+    t.i = IOP == I_ADD ? x.i + y.i : (IOP == I_MIN ? (x.i < y.i ? x.i : y.i) : (x.i > y.i ? x.i : y.i));
+    return t;
+}
+__device__ __forceinline__ Tup tup_shfl_up(const Tup &v, int d) {
+    Tup t;
+    t.a = __shfl_up_sync(FULL, v.a, d); t.b = __shfl_up_sync(FULL, v.b, d); t.i = __shfl_up_sync(FULL, v.i, d);
+    return t;
+}
+__device__ __forceinline__ Tup tup_shfl(const Tup &v, int src) {
+    Tup t;
+    t.a = __shfl_sync(FULL, v.a, src); t.b = __shfl_sync(FULL, v.b, src); t.i = __shfl_sync(FULL, v.i, src);
+    return t;
+}
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2048
+constexpr unsigned long long SCAN_EMPTY = ~0ull;       // a NaN pattern / an integer no scan here produces
+constexpr int SCAN_SPIN_MAX = 1 << 24;
+
+// per launch: words[2][ntiles][3] (aggregate, inclusive) preset to SCAN_EMPTY, and a tile counter preset to 0
+struct ScanState {
+    unsigned long long *agg, *inc;
+    unsigned *counter;
+};
+inline size_t scan_state_bytes(int64_t n) {
+    const size_t ntiles = (size_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+    return align_up(2 * ntiles * 3 * sizeof(unsigned long long), 256) + 256;
+}
+inline ScanState scan_state_at(void *buf, int64_t n) {
+    const size_t ntiles = (size_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+    ScanState s;
+    s.agg = static_cast<unsigned long long *>(buf);
+    s.inc = s.agg + ntiles * 3;
+    s.counter = reinterpret_cast<unsigned *>(static_cast<unsigned char *>(buf) + align_up(2 * ntiles * 3 * sizeof(unsigned long long), 256));
+    return s;
+}
+static __global__ void k_scan_state_init(ScanState s, size_t words) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) s.agg[i] = SCAN_EMPTY;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *s.counter = 0;
+}
+
+__device__ __forceinline__ unsigned long long scan_ld(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void scan_st(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void scan_publish(unsigned long long *w, const Tup &t) {
+    scan_st(w, (unsigned long long)__double_as_longlong(t.a));
+    scan_st(w + 1, (unsigned long long)__double_as_longlong(t.b));
+    scan_st(w + 2, (unsigned long long)t.i);
+}
+// all three words valid?  (each word is published on its own; a tuple is usable once none is SCAN_EMPTY)
+__device__ __forceinline__ bool scan_try_read(const unsigned long long *w, Tup &t) {
+    const unsigned long long x = scan_ld(w), y = scan_ld(w + 1), z = scan_ld(w + 2);
+    t.a = __longlong_as_double((long long)x); t.b = __longlong_as_double((long long)y); t.i = (long long)z;
+    return x != SCAN_EMPTY && y != SCAN_EMPTY && z != SCAN_EMPTY;
+}
+
+// Inclusive scan of load(p), p the PHYSICAL index; scan order = ascending p, or descending p when REVERSE.
+// store(p, inclusive, element).  grid = number of tiles, SCAN_THREADS threads.
+template <int IOP, bool REVERSE, typename Load, typename Store>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_lookback(int64_t n, Load load, Store store, ScanState st) {
+    __shared__ Tup s_warp[SCAN_THREADS / 32];
+    __shared__ Tup s_prefix;
+    __shared__ unsigned s_tile;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) s_tile = atomicAdd(st.counter, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t base = tile * SCAN_TILE + (int64_t)t * SCAN_ITEMS;  // logical index of this thread's first item
+
+    Tup item[SCAN_ITEMS];
+    Tup run = tup_identity<IOP>();
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int64_t li = base + k;
+        item[k] = li < n ? load(REVERSE ? n - 1 - li : li) : tup_identity<IOP>();
+        run = tup_combine<IOP>(run, item[k]);
+    }
+    // block-wide exclusive scan of the thread aggregates
+    Tup inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Tup u = tup_shfl_up(inc, d);
+        if (lane >= d) inc = tup_combine<IOP>(u, inc);
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    Tup wpre = tup_identity<IOP>(), tile_agg = tup_identity<IOP>();
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        if (w < warp) wpre = tup_combine<IOP>(wpre, s_warp[w]);
+        tile_agg = tup_combine<IOP>(tile_agg, s_warp[w]);
+    }
+    Tup thread_excl = tup_shfl_up(inc, 1);
+    if (lane == 0) thread_excl = tup_identity<IOP>();
+    thread_excl = tup_combine<IOP>(wpre, thread_excl);
+
+    // ---- decoupled look-back (warp 0): publish the aggregate, find the prefix of all earlier tiles
+    if (warp == 0) {
+        if (lane == 0) {
+            if (tile == 0) scan_publish(st.inc, tile_agg);
+            else scan_publish(st.agg + 3 * tile, tile_agg);
+        }
+        Tup prefix = tup_identity<IOP>();
+        int64_t look = tile - 1;  // nearest tile not yet accounted for
+        for (int guard = 0; look >= 0 && guard < SCAN_SPIN_MAX; ++guard) {
+            // lane l examines tile look - l: 2 = inclusive prefix available, 1 = aggregate only, 0 = nothing yet
+            const int64_t q = look - lane;
+            Tup v = tup_identity<IOP>();
+            int state = 2;  // lanes beyond tile 0 behave like "inclusive = identity"
+            if (q >= 0) {
+                if (scan_try_read(st.inc + 3 * q, v)) state = 2;
+                else if (scan_try_read(st.agg + 3 * q, v)) state = 1;
+                else state = 0;
+            }
+            // the usable run: lanes 0 .. first lane with an inclusive prefix, provided none before it is empty
+            const unsigned m_inc = __ballot_sync(FULL, state == 2), m_none = __ballot_sync(FULL, state == 0);
+            const int first_inc = m_inc ? __ffs(m_inc) - 1 : 32, first_none = m_none ? __ffs(m_none) - 1 : 32;
+            const bool done = first_inc < first_none;                      // an inclusive prefix with no gap before it
+            const int take = done ? first_inc + 1 : first_none;            // lanes [0, take) are combined (<= 32)
+            // combine in scan order: farthest tile first
+            Tup acc = tup_identity<IOP>();
+            for (int l = take - 1; l >= 0; --l) acc = tup_combine<IOP>(acc, tup_shfl(v, l));
+            prefix = tup_combine<IOP>(acc, prefix);
+            if (done) break;
+            look -= take;  // go on behind the tiles taken (take == 0: poll the same, still empty tile again)
+        }
+        if (lane == 0) {
+            if (tile != 0) scan_publish(st.inc + 3 * tile, tup_combine<IOP>(prefix, tile_agg));
+            s_prefix = prefix;
+        }
+    }
+    __syncthreads();
+    Tup acc = tup_combine<IOP>(s_prefix, thread_excl);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int64_t li = base + k;
+        acc = tup_combine<IOP>(acc, item[k]);
+        if (li < n) store(REVERSE ? n - 1 - li : li, acc, item[k]);
+    }
+}
+
+template <int IOP, bool REVERSE, typename Load, typename Store>
+int32_t scan_lookback(int64_t n, Load load, Store store, void *state_buf, cudaStream_t st) {
+    if (n <= 0) return B200SURV_OK;
+    const size_t ntiles = (size_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+    const ScanState s = scan_state_at(state_buf, n);
+    const size_t words = 2 * ntiles * 3;
+    unsigned ig = (unsigned)((words + 255) / 256);
+    if (ig > 1184) ig = 1184;
+    k_scan_state_init<<<ig, 256, 0, st>>>(s, words);
+    k_scan_lookback<IOP, REVERSE, Load, Store><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(n, load, store, s);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ radix sort
+constexpr int RS_THREADS = 256;
+constexpr int RS_ROUNDS = 16;                       // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;     // 4096 keys per tile; warp w owns keys [512 w, 512 w + 512)
+constexpr int RS_RADIX = 256;
+
+// per-tile digit histogram, stored digit-major: hist[digit][tile]
+static __global__ void __launch_bounds__(RS_THREADS)
+k_rs_hist(const uint32_t *__restrict__ keys, int64_t n, int shift, int ntiles, int *__restrict__ hist) {
+    __shared__ int s_cnt[RS_RADIX];
+    const int tile = blockIdx.x;
+    s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)tile * RS_TILE;
+#pragma unroll 4
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const int64_t i = base + (int64_t)r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&s_cnt[(keys[i] >> shift) & (RS_RADIX - 1)], 1);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * ntiles + tile] = s_cnt[threadIdx.x];
+}
+
+// stable scatter: offs[digit][tile] = first output position of the tile's keys with that digit
+static __global__ void __launch_bounds__(RS_THREADS)
+k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t n, int shift, int ntiles,
+             const long long *__restrict__ offs, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+    __shared__ int s_cnt[RS_THREADS / 32][RS_RADIX];       // running count of each digit within each warp's chunk
+    __shared__ long long s_base[RS_THREADS / 32][RS_RADIX];
+    const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < (RS_THREADS / 32) * RS_RADIX; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)tile * RS_TILE + (int64_t)warp * (RS_TILE / (RS_THREADS / 32));
+    uint32_t k[RS_ROUNDS], v[RS_ROUNDS];
+    int rank[RS_ROUNDS];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const int64_t i = base + r * 32 + lane;
+        const bool in = i < n;
+        k[r] = in ? keys[i] : 0xffffffffu;
+        v[r] = in ? vals[i] : 0u;
+        const int d = in ? (int)((k[r] >> shift) & (RS_RADIX - 1)) : -1;
+        // lanes of this round holding the same digit; out-of-range lanes form their own group and are ignored
+        const unsigned peers = __match_any_sync(FULL, d);
+        const int before = in ? s_cnt[warp][d] : 0;
+        rank[r] = before + __popc(peers & lt);
+        __syncwarp();
+        if (in && (peers & lt) == 0) s_cnt[warp][d] = before + __popc(peers);  // the group's first lane updates the count
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // digit t: exclusive prefix over the warps on top of the tile's global offset
+        long long run = offs[(size_t)t * ntiles + tile];
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) { s_base[w][t] = run; run += s_cnt[w][t]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const int64_t i = base + r * 32 + lane;
+        if (i < n) {
+            const int d = (int)((k[r] >> shift) & (RS_RADIX - 1));
+            const long long dst = s_base[warp][d] + rank[r];
+            keys_out[dst] = k[r];
+            vals_out[dst] = v[r];
+        }
+    }
+}
+
+struct RsLayout {
+    size_t off_hist, off_offs, off_scan, total;
+    int ntiles;
+};
+inline RsLayout rs_layout(int64_t n) {
+    RsLayout L;
+    L.ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+    if (L.ntiles < 1) L.ntiles = 1;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    L.off_hist = take((size_t)RS_RADIX * L.ntiles * sizeof(int));
+    L.off_offs = take((size_t)RS_RADIX * L.ntiles * sizeof(long long));
+    L.off_scan = take(scan_state_bytes((int64_t)RS_RADIX * L.ntiles));
+    L.total = o;
+    return L;
+}
+inline size_t radix_sort_temp_bytes(int64_t n) { return rs_layout(n).total; }
+
+struct RsLoadHist {
+    const int *hist;
+    __device__ Tup operator()(int64_t p) const { Tup t; t.a = 0.0; t.b = 0.0; t.i = hist[p]; return t; }
+};
+struct RsStoreOffs {
+    long long *offs;
+    __device__ void operator()(int64_t p, const Tup &inc, const Tup &el) const { offs[p] = inc.i - el.i; }  // exclusive
+};
+
+// keys_in/vals_in are overwritten (ping-pong); the sorted pairs end up in keys_out/vals_out.  Bits [0, end_bit) of the
+// keys are sorted (end_bit a multiple of 8, an even number of passes).
+inline int32_t radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n,
+                                int end_bit, void *temp, cudaStream_t st) {
+    const RsLayout L = rs_layout(n);
+    unsigned char *t8 = static_cast<unsigned char *>(temp);
+    int *hist = reinterpret_cast<int *>(t8 + L.off_hist);
+    long long *offs = reinterpret_cast<long long *>(t8 + L.off_offs);
+    uint32_t *ka = keys_in, *va = vals_in, *kb = keys_out, *vb = vals_out;
+    for (int shift = 0; shift < end_bit; shift += 8) {
+        k_rs_hist<<<L.ntiles, RS_THREADS, 0, st>>>(ka, n, shift, L.ntiles, hist);
+        const int32_t rc = scan_lookback<I_ADD, false>((int64_t)RS_RADIX * L.ntiles, RsLoadHist{hist}, RsStoreOffs{offs},
+                                                       t8 + L.off_scan, st);
+        if (rc) return rc;
+        k_rs_scatter<<<L.ntiles, RS_THREADS, 0, st>>>(ka, va, n, shift, L.ntiles, offs, kb, vb);
+        uint32_t *tk = ka; ka = kb; kb = tk;
+        uint32_t *tv = va; va = vb; vb = tv;
+    }
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;  // after an even number of passes the result is back in keys_in/vals_in: see the callers
+}
+
+}  // namespace sortscan
+}  // namespace b200surv
