@@ -326,6 +326,39 @@ def run_b200(args):
     head_ms = timed_head(lambda: graphed.step(*fresh), reps=20)
     head_flop_per_row = 11_396_224          # fwd 5,507,136 + bwd 5,889,088
 
+    # ---- CV sweep share of one GPU (BASELINE.json configs[4]): 32 replicas x one fold of 100k patients, packed back to
+    # back: segmented Cox fwd+bwd (one call) + one C-index per replica.  Replicas are independent: no collective.
+    sw_rep, sw_rows = 32, 100_000
+    slh, sev, st_ = synth.cohort(sw_rep * sw_rows, 1000 + rank)
+    sx, se_, stt = slh.to(dev), sev.to(dev), st_.to(dev)
+    soff = torch.arange(0, sw_rep + 1, dtype=torch.int64) * sw_rows
+    soff_d = soff.to(dev)
+    sones = torch.ones(sw_rep, dtype=torch.float32, device=dev)
+
+    def sweep_cox():
+        loss, state = gcox.cox_fwd_raw(sx, stt, se_, soff_d, sw_rep, L.TIES["efron"], L.REDUCE_MEAN_TERMS, L.COX_BINNED, 4096)
+        return loss, gcox.cox_bwd_raw(sones, state, sx, stt, se_, soff_d, sw_rep, L.COX_BINNED, 4096)
+
+    def sweep_ci():
+        return gci.cindex_counts_cohorts(sx, se_, stt, soff)
+
+    def timed_ms(fn, reps=5):
+        for _ in range(2):
+            fn()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record()
+        barrier()
+        tt_ = torch.tensor([a0.elapsed_time(a1) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+        return float(tt_.item())
+
+    sweep_cox_ms, sweep_ci_ms = timed_ms(sweep_cox), timed_ms(sweep_ci)
+
     if rank == 0:
         peak, peak_src = load_peaks()
         achieved_bwd = BWD_BYTES_PER_ROW * n / (bwd_ms * 1e-3) / 1e9
@@ -370,6 +403,12 @@ def run_b200(args):
             "extra": {"cindex_1m": {"n": cn, "ms": ci_ms, "patients_per_s": cn / (ci_ms * 1e-3),
                                     "ordered_pairs_per_s": sum(counts) / (ci_ms * 1e-3), "counts": counts,
                                     "n_gpus": world, "scaling": "strong (rows sharded, int64 all-reduce)"},
+                      "cv_sweep": {"replicas_per_gpu": sw_rep, "rows_per_replica": sw_rows, "n_gpus": world,
+                                   "cox_fwd_bwd_ms": sweep_cox_ms, "cindex_ms": sweep_ci_ms,
+                                   "replica_evals_per_s": world * sw_rep / ((sweep_cox_ms + sweep_ci_ms) * 1e-3),
+                                   "note": "32 replicas x 100k patients per GPU packed back to back: segmented Cox "
+                                           "fwd+bwd (one call) + one C-index per replica; independent replicas, no "
+                                           "collective (weak scaling)"},
                       "head_b4096": {"rows": hb, "ms_fwd_bwd": head_ms, "rows_per_s": hb / (head_ms * 1e-3),
                                      "tflops": hb * head_flop_per_row / (head_ms * 1e-3) / 1e12,
                                      "dtype": "bf16 operands, fp32 accumulate (tcgen05)", "dropout_p": 0.3,
