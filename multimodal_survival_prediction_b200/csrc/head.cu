@@ -42,15 +42,26 @@ __device__ __forceinline__ bool keep_elem(uint64_t seed, uint32_t layer, uint64_
     return rng32(seed, layer, idx) >= thresh;  // P(drop) = thresh / 2^32
 }
 
+// row = i / N without a 64-bit division where the flat index fits 32 bits (it does up to millions of rows)
+__device__ __forceinline__ int64_t row_of(int64_t i, int N) {
+    return i < 0x7fffffffll ? (int64_t)((unsigned)i / (unsigned)N) : i / N;
+}
+
 // ---------------------------------------------------------------- casts
+// dst[r][0..Cp) = bf16(src[r][0..C)), zero padded; grid (column chunks, row groups): no per-element division
 __global__ void k_cast_pad(const float *__restrict__ src, int64_t lds, bf16 *__restrict__ dst, int64_t ldd, int64_t R,
                            int C, int Cp) {
-    const int64_t total = R * Cp;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / Cp;
-        const int c = (int)(i - r * Cp);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cp) return;
+    for (int64_t r = blockIdx.y; r < R; r += gridDim.y)
         dst[r * ldd + c] = __float2bfloat16_rn(c < C ? src[r * lds + c] : 0.f);
-    }
+}
+static void cast_pad(const float *src, int64_t lds, bf16 *dst, int64_t ldd, int64_t R, int C, int Cp, cudaStream_t st) {
+    const unsigned gx = (unsigned)((Cp + 255) / 256);
+    int64_t gy = R < 65535 ? R : 65535;
+    const int64_t cap = (int64_t)32 * num_sms() / gx + 1;  // ~32 CTAs per SM are plenty
+    if (gy > cap) gy = cap;
+    k_cast_pad<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(src, lds, dst, ldd, R, C, Cp);
 }
 
 // ---------------------------------------------------------------- column reductions (deterministic)
@@ -100,27 +111,39 @@ k_colreduce(const float *__restrict__ a, int64_t lda, const float *__restrict__ 
         partial[((size_t)slice * 2 + 1) * N + n] = v1;
     }
 }
-// sums the slices: out0[n], out1[n] (float, nullable), scaled
-__global__ void k_colreduce_final(const double *__restrict__ partial, int nslices, int N, float scale, float *out0,
-                                  float *out1) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+// sums the slices: out0[n], out1[n] (float, nullable), scaled.  One WARP per column, lanes over the slices in a fixed
+// order (deterministic); launched with colfinal_grid(N) blocks of 256 threads.
+__device__ __forceinline__ void slice_sums(const double *__restrict__ partial, int nslices, int N, int n, int lane,
+                                           double &v0, double &v1) {
+    v0 = 0.0; v1 = 0.0;
+    for (int k = lane; k < nslices; k += 32) { v0 += partial[((size_t)k * 2 + 0) * N + n]; v1 += partial[((size_t)k * 2 + 1) * N + n]; }
+    v0 = warp_sum(v0); v1 = warp_sum(v1);
+}
+inline unsigned colfinal_grid(int N) { return (unsigned)((N + 7) / 8); }
+__global__ void __launch_bounds__(256)
+k_colreduce_final(const double *__restrict__ partial, int nslices, int N, float scale, float *out0, float *out1) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
-    double v0 = 0.0, v1 = 0.0;
-    for (int k = 0; k < nslices; ++k) { v0 += partial[((size_t)k * 2 + 0) * N + n]; v1 += partial[((size_t)k * 2 + 1) * N + n]; }
-    if (out0) out0[n] = (float)(v0 * scale);
-    if (out1) out1[n] = (float)(v1 * scale);
+    double v0, v1;
+    slice_sums(partial, nslices, N, n, lane, v0, v1);
+    if (lane == 0) {
+        if (out0) out0[n] = (float)(v0 * scale);
+        if (out1) out1[n] = (float)(v1 * scale);
+    }
 }
 
 // ---------------------------------------------------------------- BatchNorm1d
 // train: mu, rstd from the batch; running <- 0.9 running + 0.1 (mu, unbiased var).  eval: from running stats.
-__global__ void k_bn_finalize(const double *__restrict__ partial, int nslices, int64_t B, int N, int training,
-                              float *__restrict__ run_mean, float *__restrict__ run_var, float *__restrict__ mu,
-                              float *__restrict__ rstd) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+k_bn_finalize(const double *__restrict__ partial, int nslices, int64_t B, int N, int training,
+              float *__restrict__ run_mean, float *__restrict__ run_var, float *__restrict__ mu,
+              float *__restrict__ rstd) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
     if (training) {
-        double s = 0.0, ss = 0.0;
-        for (int k = 0; k < nslices; ++k) { s += partial[((size_t)k * 2 + 0) * N + n]; ss += partial[((size_t)k * 2 + 1) * N + n]; }
+        double s, ss;
+        slice_sums(partial, nslices, N, n, lane, s, ss);
+        if (lane != 0) return;
         const double m = s / (double)B;
         double var = ss / (double)B - m * m;
         if (var < 0.0) var = 0.0;
@@ -131,7 +154,7 @@ __global__ void k_bn_finalize(const double *__restrict__ partial, int nslices, i
             run_mean[n] = (1.f - BN_MOM) * run_mean[n] + BN_MOM * (float)m;
             run_var[n] = (1.f - BN_MOM) * run_var[n] + BN_MOM * (float)unb;
         }
-    } else {
+    } else if (lane == 0) {
         mu[n] = run_mean[n];
         rstd[n] = rsqrtf(run_var[n] + BN_EPS);
     }
@@ -145,7 +168,7 @@ __global__ void k_bn_apply(const float *__restrict__ x, int64_t ldx, const float
     if (seed_dev != nullptr) seed = *seed_dev;  // (CUDA-graph replays: the seed lives in device memory)
     const int64_t total = B * N;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / N;
+        const int64_t r = row_of(i, N);
         const int n = (int)(i - r * N);
         float v = (x[r * ldx + n] - mu[n]) * rstd[n] * gamma[n] + beta[n];
         v = fmaxf(v, 0.f);
@@ -164,7 +187,7 @@ __global__ void k_bn_bwd_dy(const float *__restrict__ dA, int64_t ldd, const flo
     if (seed_dev != nullptr) seed = *seed_dev;
     const int64_t total = B * N;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / N;
+        const int64_t r = row_of(i, N);
         const int n = (int)(i - r * N);
         const float v = (x[r * ldx + n] - mu[n]) * rstd[n] * gamma[n] + beta[n];
         float g = dA[r * ldd + n];
@@ -182,7 +205,7 @@ __global__ void k_bn_bwd_dx(const float *__restrict__ dy, const float *__restric
     const int64_t total = B * N;
     const float invB = 1.f / (float)B;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / N;
+        const int64_t r = row_of(i, N);
         const int n = (int)(i - r * N);
         float v = dy[i];
         if (training) {
@@ -207,7 +230,7 @@ __global__ void k_gate_prep(const float *__restrict__ ct, const float *__restric
                             int64_t B, float *__restrict__ feat, bf16 *__restrict__ z, bf16 *__restrict__ fused) {
     const int64_t total = B * GZP;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = i / GZP;
+        const int64_t b = row_of(i, GZP);
         const int j = (int)(i - b * GZP);
         float v = 0.f;
         if (j < FEAT) {
@@ -282,7 +305,7 @@ __global__ void k_gate_prep_bwd(const float *__restrict__ dfeat, const float *__
                                 bf16 *__restrict__ dR, float *__restrict__ dC) {
     const int64_t total = B * FEAT;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = i / FEAT;
+        const int64_t b = row_of(i, FEAT);
         const int j = (int)(i - b * FEAT);
         float v = dfeat[i] + (dz ? dz[b * lddz + j] : 0.f);
         if (j < CT) {
@@ -316,7 +339,7 @@ __global__ void k_cox_head_bwd(const float *__restrict__ dhz, const float *__res
                                int64_t B, bf16 *__restrict__ df2) {
     const int64_t total = B * F2N;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = i / F2N;
+        const int64_t b = row_of(i, F2N);
         const int j = (int)(i - b * F2N);
         df2[i] = __float2bfloat16_rn(f2[i] > 0.f ? dhz[b] * w[j] : 0.f);
     }
@@ -407,12 +430,12 @@ void rowscale_sum(const float *a, int64_t lda, const float *s, int64_t s_stride,
                   float *out0, float *out1, cudaStream_t st) {
     const int nsl = nslices_for(B);
     colreduce<2>(a, lda, nullptr, 0, nullptr, nullptr, s, s_stride, B, N, partial, nsl, st);
-    k_colreduce_final<<<(N + 255) / 256, 256, 0, st>>>(partial, nsl, N, 1.f, out0, out1);
+    k_colreduce_final<<<colfinal_grid(N), 256, 0, st>>>(partial, nsl, N, 1.f, out0, out1);
 }
 void col_sum(const float *a, int64_t lda, int64_t B, int N, double *partial, float *out0, cudaStream_t st) {
     const int nsl = nslices_for(B);
     colreduce<3>(a, lda, nullptr, 0, nullptr, nullptr, nullptr, 0, B, N, partial, nsl, st);
-    k_colreduce_final<<<(N + 255) / 256, 256, 0, st>>>(partial, nsl, N, 1.f, out0, nullptr);
+    k_colreduce_final<<<colfinal_grid(N), 256, 0, st>>>(partial, nsl, N, 1.f, out0, nullptr);
 }
 void col_sum_bf16(const bf16 *a, int64_t B, int N, float *tmp, double *partial, float *out0, cudaStream_t st) {
     k_bf16_to_f32<<<gs(B * N), 256, 0, st>>>(a, tmp, B * N);
@@ -492,18 +515,18 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
     int32_t rc;
 
     // bf16 operand copies (K padded to a multiple of 8 for the TMA row pitch)
-    k_cast_pad<<<gs(B * Kp), 256, 0, st>>>(rna, rna_dim, s.xb, Kp, B, rna_dim, Kp);
-    k_cast_pad<<<gs((int64_t)H1 * Kp), 256, 0, st>>>(p->rna0_w, rna_dim, s.w1b, Kp, H1, rna_dim, Kp);
-    k_cast_pad<<<gs(R1 * H1), 256, 0, st>>>(p->rna4_w, H1, s.w2b, H1, R1, H1, H1);
-    if (gated) k_cast_pad<<<gs(GH * GZP), 256, 0, st>>>(p->gate0_w, GZ, s.wg1b, GZP, GH, GZ, GZP);
-    k_cast_pad<<<gs(H2 * FEAT), 256, 0, st>>>(p->fus0_w, FEAT, s.wf1b, FEAT, H2, FEAT, FEAT);
-    k_cast_pad<<<gs(F2N * H2), 256, 0, st>>>(p->fus4_w, H2, s.wf2b, H2, F2N, H2, H2);
+    cast_pad(rna, rna_dim, s.xb, Kp, B, rna_dim, Kp, st);
+    cast_pad(p->rna0_w, rna_dim, s.w1b, Kp, H1, rna_dim, Kp, st);
+    cast_pad(p->rna4_w, H1, s.w2b, H1, R1, H1, H1, st);
+    if (gated) cast_pad(p->gate0_w, GZ, s.wg1b, GZP, GH, GZ, GZP, st);
+    cast_pad(p->fus0_w, FEAT, s.wf1b, FEAT, H2, FEAT, FEAT, st);
+    cast_pad(p->fus4_w, H2, s.wf2b, H2, F2N, H2, H2, st);
 
     // rna encoder: Linear(rna_dim, 512) -> BN -> ReLU -> Dropout -> Linear(512, 128) -> ReLU
     rc = gemm_bf16(s.xb, Kp, 0, s.w1b, Kp, 0, (int)B, H1, rna_dim, s.h1, H1, nullptr, 0, p->rna0_b, 0, nullptr, st);
     if (rc) return rc;
     if (training) colreduce<0>(s.h1, H1, nullptr, 0, nullptr, nullptr, nullptr, 0, B, H1, w.partial, nsl, st);
-    k_bn_finalize<<<(H1 + 255) / 256, 256, 0, st>>>(w.partial, nsl, B, H1, training, p->bn1_rm, p->bn1_rv, s.mu1, s.rstd1);
+    k_bn_finalize<<<colfinal_grid(H1), 256, 0, st>>>(w.partial, nsl, B, H1, training, p->bn1_rm, p->bn1_rv, s.mu1, s.rstd1);
     k_bn_apply<<<gs(B * H1), 256, 0, st>>>(s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh, inv_keep, seed, seed_dev, 1,
                                            s.a1, H1, keep1);
     rc = gemm_bf16(s.a1, H1, 0, s.w2b, H1, 0, (int)B, R1, H1, s.r, R1, nullptr, 0, p->rna4_b, 1, nullptr, st);
@@ -522,7 +545,7 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
     rc = gemm_bf16(s.fused, FEAT, 0, s.wf1b, FEAT, 0, (int)B, H2, FEAT, s.h2, H2, nullptr, 0, p->fus0_b, 0, nullptr, st);
     if (rc) return rc;
     if (training) colreduce<0>(s.h2, H2, nullptr, 0, nullptr, nullptr, nullptr, 0, B, H2, w.partial, nsl, st);
-    k_bn_finalize<<<(H2 + 255) / 256, 256, 0, st>>>(w.partial, nsl, B, H2, training, p->bn2_rm, p->bn2_rv, s.mu2, s.rstd2);
+    k_bn_finalize<<<colfinal_grid(H2), 256, 0, st>>>(w.partial, nsl, B, H2, training, p->bn2_rm, p->bn2_rv, s.mu2, s.rstd2);
     k_bn_apply<<<gs(B * H2), 256, 0, st>>>(s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh, inv_keep, seed, seed_dev, 2,
                                            s.a2, H2, keep2);
     rc = gemm_bf16(s.a2, H2, 0, s.wf2b, H2, 0, (int)B, F2N, H2, s.f2, F2N, nullptr, 0, p->fus4_b, 1, nullptr, st);
@@ -567,7 +590,7 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     k_bn_bwd_dy<<<gs(B * H2), 256, 0, st>>>(w.t0, H2, s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh, inv_keep,
                                             seed, seed_dev, 2, w.t1);                                       // t1 = dy
     colreduce<1>(w.t1, H2, s.h2, H2, s.mu2, s.rstd2, nullptr, 0, B, H2, w.partial, nsl, st);
-    k_colreduce_final<<<(H2 + 255) / 256, 256, 0, st>>>(w.partial, nsl, H2, 1.f, g->bn2_b, g->bn2_w);  // dbeta, dgamma
+    k_colreduce_final<<<colfinal_grid(H2), 256, 0, st>>>(w.partial, nsl, H2, 1.f, g->bn2_b, g->bn2_w);  // dbeta, dgamma
     k_bn_bwd_dx<<<gs(B * H2), 256, 0, st>>>(w.t1, s.h2, H2, s.mu2, s.rstd2, p->bn2_w, g->bn2_b, g->bn2_w, B, H2, training,
                                             w.b1, H2);                                            // b1 = dH2
     k_bn_bias_grad<<<(H2 + 255) / 256, 256, 0, st>>>(g->bn2_b, p->bn2_w, s.rstd2, H2, training, g->fus0_b);
@@ -608,7 +631,7 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     k_bn_bwd_dy<<<gs(B * H1), 256, 0, st>>>(w.t0, H1, s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh, inv_keep,
                                             seed, seed_dev, 1, w.t1);
     colreduce<1>(w.t1, H1, s.h1, H1, s.mu1, s.rstd1, nullptr, 0, B, H1, w.partial, nsl, st);
-    k_colreduce_final<<<(H1 + 255) / 256, 256, 0, st>>>(w.partial, nsl, H1, 1.f, g->bn1_b, g->bn1_w);
+    k_colreduce_final<<<colfinal_grid(H1), 256, 0, st>>>(w.partial, nsl, H1, 1.f, g->bn1_b, g->bn1_w);
     k_bn_bwd_dx<<<gs(B * H1), 256, 0, st>>>(w.t1, s.h1, H1, s.mu1, s.rstd1, p->bn1_w, g->bn1_b, g->bn1_w, B, H1, training,
                                             w.b0, H1);                             // b0 = dH1
     k_bn_bias_grad<<<(H1 + 255) / 256, 256, 0, st>>>(g->bn1_b, p->bn1_w, s.rstd1, H1, training, g->rna0_b);
