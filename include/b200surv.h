@@ -272,6 +272,15 @@ int32_t b200surv_head_bwd(const b200surv_head_params *params, const b200surv_hea
                           size_t saved_bytes, void *workspace, size_t workspace_bytes,
                           b200surv_stream_t stream);
 
+/* ---- test hooks: the hand-written sort / scan primitives behind the SORTED Cox path and the C-index ---------- */
+/* stable LSD radix sort of (u32 key, u32 value) pairs, in place (keys_tmp / vals_tmp: ping-pong buffers);
+ * inclusive scan of (a, 2a, i), i combined by iop (0 add, 1 min, 2 max), ascending or descending index order. */
+size_t b200surv_debug_sortscan_temp_bytes(int64_t n);
+int32_t b200surv_debug_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
+                                  void *temp, b200surv_stream_t stream);
+int32_t b200surv_debug_scan(const double *a, const int64_t *i, int64_t n, int32_t iop, int32_t reverse, double *out_a,
+                            double *out_b, int64_t *out_i, void *temp, b200surv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -370,4 +370,36 @@ int32_t cindex_counts_launch(const float *est, const float *time, const uint8_t 
     return B200SURV_OK;
 }
 
+// ---- test hooks for the primitives of sortscan.cuh (tests/test_sortscan_gpu.py)
+size_t debug_sortscan_temp_bytes(int64_t n) {
+    const size_t a = sortscan::radix_sort_temp_bytes(n), b = sortscan::scan_state_bytes(n);
+    return (a > b ? a : b) + 256;
+}
+int32_t debug_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, int64_t n, void *temp,
+                         cudaStream_t st) {
+    return sortscan::radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 32, temp, st);  // sorted pairs end up in keys/vals
+}
+namespace {
+struct DbgLoad {
+    const double *a; const long long *i;
+    __device__ sortscan::Tup operator()(int64_t p) const { sortscan::Tup t; t.a = a[p]; t.b = 2.0 * a[p]; t.i = i[p]; return t; }
+};
+struct DbgStore {
+    double *a, *b; long long *i;
+    __device__ void operator()(int64_t p, const sortscan::Tup &inc, const sortscan::Tup &) const { a[p] = inc.a; b[p] = inc.b; i[p] = inc.i; }
+};
+}  // namespace
+// inclusive scan of (a, 2a, i) with i combined by iop (0 add, 1 min, 2 max), forward or reverse
+int32_t debug_scan(const double *a, const long long *i, int64_t n, int iop, int reverse, double *out_a, double *out_b,
+                   long long *out_i, void *temp, cudaStream_t st) {
+    const DbgLoad ld{a, i};
+    const DbgStore sto{out_a, out_b, out_i};
+    if (iop == 0) return reverse ? sortscan::scan_lookback<sortscan::I_ADD, true>(n, ld, sto, temp, st)
+                                 : sortscan::scan_lookback<sortscan::I_ADD, false>(n, ld, sto, temp, st);
+    if (iop == 1) return reverse ? sortscan::scan_lookback<sortscan::I_MIN, true>(n, ld, sto, temp, st)
+                                 : sortscan::scan_lookback<sortscan::I_MIN, false>(n, ld, sto, temp, st);
+    return reverse ? sortscan::scan_lookback<sortscan::I_MAX, true>(n, ld, sto, temp, st)
+                   : sortscan::scan_lookback<sortscan::I_MAX, false>(n, ld, sto, temp, st);
+}
+
 }  // namespace b200surv

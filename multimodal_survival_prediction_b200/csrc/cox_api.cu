@@ -29,6 +29,9 @@ int32_t cox_sorted_fwd_launch(const float *, const float *, const uint8_t *, int
 size_t cindex_workspace_bytes(int64_t n, int algo);
 int32_t cindex_counts_launch(const float *, const float *, const uint8_t *, int64_t, int64_t, int64_t, float, int, int,
                              int, int64_t *, void *, size_t, cudaStream_t);
+size_t debug_sortscan_temp_bytes(int64_t n);
+int32_t debug_sort_pairs(uint32_t *, uint32_t *, uint32_t *, uint32_t *, int64_t, void *, cudaStream_t);
+int32_t debug_scan(const double *, const long long *, int64_t, int, int, double *, double *, long long *, void *, cudaStream_t);
 }  // namespace b200surv
 
 using namespace b200surv;
@@ -180,6 +183,20 @@ int32_t b200surv_cindex_counts_cohorts(const float *estimate, const float *time,
         if (rc != B200SURV_OK) return rc;
     }
     return B200SURV_OK;
+}
+
+/* test hooks for the sort / scan primitives (csrc/sortscan.cuh) */
+size_t b200surv_debug_sortscan_temp_bytes(int64_t n) { return debug_sortscan_temp_bytes(n); }
+int32_t b200surv_debug_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, int64_t n,
+                                  void *temp, b200surv_stream_t stream) {
+    B200_REQUIRE(keys && vals && keys_tmp && vals_tmp && temp && n >= 1, "arguments");
+    return debug_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, temp, as_stream(stream));
+}
+int32_t b200surv_debug_scan(const double *a, const int64_t *i, int64_t n, int32_t iop, int32_t reverse, double *out_a,
+                            double *out_b, int64_t *out_i, void *temp, b200surv_stream_t stream) {
+    B200_REQUIRE(a && i && out_a && out_b && out_i && temp && n >= 1 && iop >= 0 && iop <= 2, "arguments");
+    return debug_scan(a, reinterpret_cast<const long long *>(i), n, iop, reverse, out_a, out_b,
+                      reinterpret_cast<long long *>(out_i), temp, as_stream(stream));
 }
 
 }  // extern "C"
