@@ -197,8 +197,9 @@ int32_t b200surv_cindex_counts_shard(const float *estimate, const float *time, c
 /* Many independent cohorts packed back to back (the CV sweep evaluates one C-index per fold and replica,
  * partial_modality_training.py:438-485 called per fold): cohort c is rows
  * [cohort_offsets_host[c], cohort_offsets_host[c+1]) -- a HOST array of n_cohorts+1 offsets -- and
- * out_counts is device int64[n_cohorts][6] (ADDED to).  Stream-ordered launches, one per cohort, sharing a
- * workspace sized for the largest cohort (b200surv_cindex_workspace_bytes(n_max, 1, algo)). */
+ * out_counts is device int64[n_cohorts][6] (ADDED to).  One chain of launches per cohort; a workspace of k x
+ * b200surv_cindex_workspace_bytes(n_max, 1, algo) bytes (rounded up to 256; k <= 8) lets k chains run at a time on
+ * internal streams forked from and joined to `stream` with events (k = 1: one after the other on `stream`). */
 int32_t b200surv_cindex_counts_cohorts(const float *estimate, const float *time, const uint8_t *event,
                                        const int64_t *cohort_offsets_host, int64_t n_cohorts,
                                        float tied_tol, int32_t algo, int64_t *out_counts, void *workspace,

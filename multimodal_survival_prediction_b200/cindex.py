@@ -73,8 +73,8 @@ def cindex_counts_cohorts(estimate, event, time, offsets, tied_tol=1e-8, algo=1)
         raise ValueError("offsets must run from 0 to n, non-decreasing, with at least one cohort")
     out = torch.zeros(nc, 6, dtype=torch.int64, device=dev)
     n_max = max(b - a for a, b in zip(offs, offs[1:]))
-    wb = lib.b200surv_cindex_workspace_bytes(n_max, 1, algo)
-    ws = torch.empty(max(wb, 256), dtype=torch.uint8, device=dev)
+    wb = (lib.b200surv_cindex_workspace_bytes(n_max, 1, algo) + 255) // 256 * 256
+    ws = torch.empty(max(wb, 256) * min(8, nc), dtype=torch.uint8, device=dev)   # room for 8 cohorts in flight
     host = (ctypes.c_int64 * (nc + 1))(*offs)
     rc = lib.b200surv_cindex_counts_cohorts(L.ptr(estimate), L.ptr(time), L.ptr(event), host, nc,
                                             ctypes.c_float(tied_tol), algo, L.ptr(out), L.ptr(ws), ws.numel(),

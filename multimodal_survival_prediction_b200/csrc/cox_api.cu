@@ -36,6 +36,29 @@ int32_t debug_scan(const double *, const long long *, int64_t, int, int, double 
 
 using namespace b200surv;
 
+namespace {
+// internal streams of b200surv_cindex_counts_cohorts, created once per device on first use
+constexpr int COHORT_LANES = 8;
+struct CohortLanes {
+    cudaStream_t s[COHORT_LANES];
+    cudaEvent_t done[COHORT_LANES], fork;
+};
+CohortLanes *cohort_lanes() {
+    static CohortLanes pool[64];
+    static int state[64];  // 0 = not tried, 1 = ready, -1 = failed
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (state[dev] == 0) {
+        bool ok = cudaEventCreateWithFlags(&pool[dev].fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int j = 0; ok && j < COHORT_LANES; ++j)
+            ok = cudaStreamCreateWithFlags(&pool[dev].s[j], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&pool[dev].done[j], cudaEventDisableTiming) == cudaSuccess;
+        state[dev] = ok ? 1 : -1;
+    }
+    return state[dev] == 1 ? &pool[dev] : nullptr;
+}
+}  // namespace
+
 extern "C" {
 
 size_t b200surv_cox_state_bytes(int64_t n, int64_t n_seg, int32_t mode, int32_t nbins) {
@@ -174,13 +197,41 @@ int32_t b200surv_cindex_counts_cohorts(const float *estimate, const float *time,
     B200_REQUIRE(estimate && time && event && out_counts && cohort_offsets_host, "null pointer");
     B200_REQUIRE(n_cohorts >= 1, "n_cohorts");
     B200_REQUIRE(algo == 0 || workspace != nullptr, "workspace");
-    for (int64_t c = 0; c < n_cohorts; ++c) {  // stream-ordered: the cohorts share the workspace
+    cudaStream_t user = as_stream(stream);
+    // A cohort is a chain of ~25 small launches; with a workspace that holds k >= 2 cohorts' scratch (k x
+    // b200surv_cindex_workspace_bytes(n_max, 1, algo), up to 8) the chains run k at a time on internal streams that
+    // fork from and join the caller's stream with events (so everything stays ordered on `stream`).
+    int64_t n_max = 0;
+    for (int64_t c = 0; c < n_cohorts; ++c) {
         const int64_t a = cohort_offsets_host[c], b = cohort_offsets_host[c + 1];
         B200_REQUIRE(a >= 0 && b >= a, "cohort_offsets_host must be non-decreasing");
+        if (b - a > n_max) n_max = b - a;
+    }
+    const size_t ws_one = align_up(cindex_workspace_bytes(n_max, algo), 256);
+    int k = (algo == 0 || ws_one == 0) ? 1 : (int)(workspace_bytes / ws_one);
+    if (k > COHORT_LANES) k = COHORT_LANES;
+    if (k > n_cohorts) k = (int)n_cohorts;
+    CohortLanes *lanes = k >= 2 ? cohort_lanes() : nullptr;
+    if (lanes == nullptr) k = 1;
+    if (k >= 2) {
+        B200_CHECK_CUDA(cudaEventRecord(lanes->fork, user));
+        for (int j = 0; j < k; ++j) B200_CHECK_CUDA(cudaStreamWaitEvent(lanes->s[j], lanes->fork, 0));
+    }
+    for (int64_t c = 0; c < n_cohorts; ++c) {
+        const int64_t a = cohort_offsets_host[c], b = cohort_offsets_host[c + 1];
         if (b == a) continue;
+        const int j = (int)(c % k);
         const int32_t rc = cindex_counts_launch(estimate + a, time + a, event + a, b - a, 0, b - a, tied_tol, algo, 0, 1,
-                                                out_counts + 6 * c, workspace, workspace_bytes, as_stream(stream));
+                                                out_counts + 6 * c,
+                                                k >= 2 ? static_cast<unsigned char *>(workspace) + (size_t)j * ws_one : workspace,
+                                                k >= 2 ? ws_one : workspace_bytes, k >= 2 ? lanes->s[j] : user);
         if (rc != B200SURV_OK) return rc;
+    }
+    if (k >= 2) {
+        for (int j = 0; j < k; ++j) {
+            B200_CHECK_CUDA(cudaEventRecord(lanes->done[j], lanes->s[j]));
+            B200_CHECK_CUDA(cudaStreamWaitEvent(user, lanes->done[j], 0));
+        }
     }
     return B200SURV_OK;
 }
