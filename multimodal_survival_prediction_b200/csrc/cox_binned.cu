@@ -858,26 +858,39 @@ __device__ __forceinline__ bool peer_push_sum(const PeerArgs &pa, int nb, const 
     const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(pa.buf[pa.rank]) + slot_words;
     const long long t0 = global_timer_ns();
     bool ok = true;
-    for (int p = 0; p < pa.world; ++p) {  // (uniform trip count; the polls of one source are in flight together)
-        if (p == pa.rank) continue;
-        const unsigned long long *src = mine + (size_t)p * src_words;
-        unsigned long long w[4] = {tag, tag, tag, tag};
+    // sources in groups of four, the polls of a group in flight together (one after the other, seven sources cost seven
+    // L2 round trips); uniform trip counts, a vote decides whether to go round again
+    for (int p0 = 0; p0 < pa.world && ok; p0 += 4) {
+        unsigned long long w[4][4];
         for (;;) {
             bool pending = false;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (active && i < nw) { w[i] = ld_relaxed_sys_u64(src + off[i]); pending |= (w[i] >> 62) != (tag >> 62); }
+            for (int q = 0; q < 4; ++q) {
+                const int p = p0 + q;
+                const bool src_ok = p < pa.world && p != pa.rank;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    w[q][i] = tag;
+                    if (src_ok && active && i < nw) {
+                        w[q][i] = ld_relaxed_sys_u64(mine + (size_t)p * src_words + off[i]);
+                        pending |= (w[q][i] >> 62) != (tag >> 62);
+                    }
+                }
+            }
             if (!__any_sync(FULL, pending)) break;
             if (global_timer_ns() - t0 > PEER_SPIN_LIMIT_NS) { ok = false; break; }
         }
         ok = __all_sync(FULL, ok);
         if (!ok) break;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (active && i < nw) {  // 62-bit two's complement -> 64 bits
-                const long long x = (long long)(w[i] << 2) >> 2;
-                val[i] += x;
+        for (int q = 0; q < 4; ++q) {
+            const int p = p0 + q;
+            if (p < pa.world && p != pa.rank && active) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < nw) val[i] += (long long)(w[q][i] << 2) >> 2;  // 62-bit two's complement -> 64 bits
             }
+        }
     }
     return ok;
 }
