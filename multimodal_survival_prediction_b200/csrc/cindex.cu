@@ -76,11 +76,10 @@ constexpr int CT_THREADS = 256;
 constexpr int CT_R = 8;                       // rows per thread
 constexpr int CT_ROWS = CT_THREADS * CT_R;    // 2048 rows per CTA
 constexpr int CT_TILE = 1024;                 // columns per shared-memory tile
-constexpr int CT_CHUNK_TILES = 8;             // column tiles per CTA, at most (fewer when there are few row tiles)
 
 struct Acc1 {
     unsigned long long conc_s, le_s, conc_t, le_t, tot_s, tot_t;
-    unsigned long long n_rows, pad;
+    unsigned long long n_rows, work;  // work: the counter the count kernel's CTAs pull their items from
 };
 
 __device__ __forceinline__ uint32_t time_key(float t, bool ev) {
@@ -166,57 +165,74 @@ k_ci_rows(const uint32_t *__restrict__ keys_s, const float *__restrict__ est_s,
     }
 }
 
-// grid: x = column chunk, y = row tile (of compacted selected event rows)
+// c += (a < b) / (a <= b) (ordered compares: false on NaN, like the C operators)
+__device__ __forceinline__ void inc_lt(unsigned &c, float a, float b) {
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(c) : "f"(a), "f"(b));
+}
+__device__ __forceinline__ void inc_le(unsigned &c, float a, float b) {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(c) : "f"(a), "f"(b));
+}
+
+// Persistent CTAs pull work items -- (row tile of this shard, column tile) pairs, 2048 rows x 1024 columns -- from an
+// atomic counter: the number of event rows is only known on the device, and with a fixed grid of multi-tile CTAs the
+// last, partly filled wave cost a 1/8 shard 1 ms of its 4 ms.
 __global__ void __launch_bounds__(CT_THREADS)
 k_ci_count(const float *__restrict__ est_s, int64_t n, const float *__restrict__ r_lo,
            const float *__restrict__ r_hi, const int *__restrict__ r_s, const int *__restrict__ r_ge,
-           int shard, int n_shards, int chunk_tiles, Acc1 *acc) {
+           int shard, int n_shards, Acc1 *acc) {
     __shared__ __align__(16) float s_e[CT_TILE];
     __shared__ int s_red[2][32];
     __shared__ long long red[32];
+    __shared__ unsigned long long s_item;
     const long long n_rows = (long long)acc->n_rows;
-    const long long k0 = ((long long)blockIdx.y * n_shards + shard) * CT_ROWS;  // row tile blockIdx.y of this shard
-    if (k0 >= n_rows) return;
-    const int chunk0 = blockIdx.x * (CT_TILE * chunk_tiles);
-    const int chunk1 = (int)min((long long)n, (long long)chunk0 + CT_TILE * chunk_tiles);
-
-    float lo[CT_R], hi[CT_R];
-    int rs[CT_R], rg[CT_R];
-    int mins = INT_MAX, maxge = 0;
-#pragma unroll
-    for (int u = 0; u < CT_R; ++u) {
-        const long long k = k0 + threadIdx.x + (long long)u * CT_THREADS;
-        if (k < n_rows) {
-            lo[u] = r_lo[k]; hi[u] = r_hi[k]; rs[u] = r_s[k]; rg[u] = r_ge[k];
-            mins = min(mins, rs[u]); maxge = max(maxge, rg[u]);
-        } else {  // padding row: empty comparable range, NaN thresholds never compare true
-            lo[u] = __int_as_float(0x7fc00000); hi[u] = lo[u]; rs[u] = INT_MAX; rg[u] = INT_MAX;
-        }
-    }
-    // CTA-wide min(s) and max(ge) decide, per column tile, between skip / fast / general
-    {
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mins = min(mins, __shfl_xor_sync(FULL, mins, o));
-            maxge = max(maxge, __shfl_xor_sync(FULL, maxge, o));
-        }
-        if (lane == 0) { s_red[0][wid] = mins; s_red[1][wid] = maxge; }
+    const long long tiles_all = (n_rows + CT_ROWS - 1) / CT_ROWS;
+    const long long my_tiles = tiles_all > shard ? (tiles_all - shard + n_shards - 1) / n_shards : 0;
+    const long long col_tiles = (n + CT_TILE - 1) / CT_TILE;
+    const unsigned long long total = (unsigned long long)(my_tiles * col_tiles);
+    long long a = 0, b = 0, c = 0, d = 0;  // this CTA's strict conc / le and same-time conc / le counts
+    for (;;) {
+        __syncthreads();  // (s_item, s_e and s_red of the previous item are no longer read)
+        if (threadIdx.x == 0) s_item = atomicAdd(&acc->work, 1ull);
         __syncthreads();
-        mins = INT_MAX; maxge = 0;
-        for (int w = 0; w < CT_THREADS / 32; ++w) { mins = min(mins, s_red[0][w]); maxge = max(maxge, s_red[1][w]); }
-    }
-    if (chunk1 <= mins) return;  // whole chunk precedes every row's comparable range
+        const unsigned long long item = s_item;
+        if (item >= total) break;
+        const long long ty = (long long)(item / (unsigned long long)col_tiles);
+        const int c0 = (int)(item - (unsigned long long)ty * (unsigned long long)col_tiles) * CT_TILE;
+        const int c1 = (int)min((long long)n, (long long)c0 + CT_TILE);
+        const long long k0 = (ty * n_shards + shard) * CT_ROWS;  // row tile ty of this shard
 
-    unsigned cs[CT_R], ls[CT_R];      // strict: #(e_j < lo), #(e_j <= hi)
-    unsigned long long conc_t = 0, le_t = 0;  // same-time (rare, general path only)
+        float lo[CT_R], hi[CT_R];
+        int rs[CT_R], rg[CT_R];
+        int mins = INT_MAX, maxge = 0;
 #pragma unroll
-    for (int u = 0; u < CT_R; ++u) { cs[u] = 0; ls[u] = 0; }
+        for (int u = 0; u < CT_R; ++u) {
+            const long long k = k0 + threadIdx.x + (long long)u * CT_THREADS;
+            if (k < n_rows) {
+                lo[u] = r_lo[k]; hi[u] = r_hi[k]; rs[u] = r_s[k]; rg[u] = r_ge[k];
+                mins = min(mins, rs[u]); maxge = max(maxge, rg[u]);
+            } else {  // padding row: empty comparable range, NaN thresholds never compare true
+                lo[u] = __int_as_float(0x7fc00000); hi[u] = lo[u]; rs[u] = INT_MAX; rg[u] = INT_MAX;
+            }
+        }
+        // CTA-wide min(s) and max(ge) decide between skip / fast / general
+        {
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mins = min(mins, __shfl_xor_sync(FULL, mins, o));
+                maxge = max(maxge, __shfl_xor_sync(FULL, maxge, o));
+            }
+            if (lane == 0) { s_red[0][wid] = mins; s_red[1][wid] = maxge; }
+            __syncthreads();
+            mins = INT_MAX; maxge = 0;
+            for (int w = 0; w < CT_THREADS / 32; ++w) { mins = min(mins, s_red[0][w]); maxge = max(maxge, s_red[1][w]); }
+        }
+        if (c1 <= mins) continue;  // the whole column tile precedes every row's comparable range
 
-    for (int c0 = chunk0; c0 < chunk1; c0 += CT_TILE) {
-        const int c1 = min(c0 + CT_TILE, chunk1);
-        if (c1 <= mins) continue;
-        __syncthreads();
+        unsigned cs[CT_R], ls[CT_R];      // strict: #(e_j < lo), #(e_j <= hi)
+        unsigned long long conc_t = 0, le_t = 0;  // same-time (rare, general path only)
+#pragma unroll
+        for (int u = 0; u < CT_R; ++u) { cs[u] = 0; ls[u] = 0; }
         for (int q = threadIdx.x; q < CT_TILE; q += CT_THREADS) s_e[q] = (c0 + q < n) ? est_s[c0 + q] : 0.f;
         __syncthreads();
         if (c0 >= maxge && c1 - c0 == CT_TILE) {
@@ -226,8 +242,10 @@ k_ci_count(const float *__restrict__ est_s, int64_t n, const float *__restrict__
                 const float4 e4 = *reinterpret_cast<const float4 *>(s_e + q);
 #pragma unroll
                 for (int u = 0; u < CT_R; ++u) {
-                    cs[u] += (e4.x < lo[u]) + (e4.y < lo[u]) + (e4.z < lo[u]) + (e4.w < lo[u]);
-                    ls[u] += (e4.x <= hi[u]) + (e4.y <= hi[u]) + (e4.z <= hi[u]) + (e4.w <= hi[u]);
+                    // compare + predicated increment (2 instructions per comparison; `count += (a < b)` compiles to
+                    // ~2.5: predicate, select, add)
+                    inc_lt(cs[u], e4.x, lo[u]); inc_lt(cs[u], e4.y, lo[u]); inc_lt(cs[u], e4.z, lo[u]); inc_lt(cs[u], e4.w, lo[u]);
+                    inc_le(ls[u], e4.x, hi[u]); inc_le(ls[u], e4.y, hi[u]); inc_le(ls[u], e4.z, hi[u]); inc_le(ls[u], e4.w, hi[u]);
                 }
             }
         } else {
@@ -243,14 +261,14 @@ k_ci_count(const float *__restrict__ est_s, int64_t n, const float *__restrict__
                 }
             }
         }
-    }
-    long long a = 0, b = 0;
 #pragma unroll
-    for (int u = 0; u < CT_R; ++u) { a += cs[u]; b += ls[u]; }
+        for (int u = 0; u < CT_R; ++u) { a += cs[u]; b += ls[u]; }
+        c += (long long)conc_t; d += (long long)le_t;
+    }
     a = block_reduce<long long>(a, 0ll, OpAddLL(), red);
     b = block_reduce<long long>(b, 0ll, OpAddLL(), red);
-    const long long c = block_reduce<long long>((long long)conc_t, 0ll, OpAddLL(), red);
-    const long long d = block_reduce<long long>((long long)le_t, 0ll, OpAddLL(), red);
+    c = block_reduce<long long>(c, 0ll, OpAddLL(), red);
+    d = block_reduce<long long>(d, 0ll, OpAddLL(), red);
     if (threadIdx.x == 0) {
         if (a) atomicAdd(&acc->conc_s, (unsigned long long)a);
         if (b) atomicAdd(&acc->le_s, (unsigned long long)b);
@@ -349,22 +367,7 @@ int32_t cindex_counts_launch(const float *est, const float *time, const uint8_t 
         if (rc) return rc;
     }
     k_ci_rows<<<grid, 256, 0, st>>>(keys_s, est_s, isrow, rank, n, tol, r_lo, r_hi, r_s, r_ge, shard, n_shards, acc);
-    {
-        // upper bound on selected rows known to the host: min(n, row_end - row_begin)
-        const int64_t max_rows = row_end - row_begin;
-        const int64_t tiles = (max_rows + CT_ROWS - 1) / CT_ROWS;
-        const unsigned gy = (unsigned)((tiles + n_shards - 1) / n_shards);
-        // column tiles per CTA: enough CTAs (about half of the grid is above the diagonal and does the work) for
-        // ~8 waves of 8 CTAs per SM, or the last, partly filled wave costs milliseconds (measured: a 1/8 shard took
-        // 7.1 ms with 8 tiles per CTA against 4.8 ms of work)
-        const int64_t col_tiles = (n + CT_TILE - 1) / CT_TILE;
-        int64_t ct = (int64_t)gy * col_tiles / 2 / (64 * (int64_t)num_sms());
-        if (ct < 1) ct = 1;
-        if (ct > CT_CHUNK_TILES) ct = CT_CHUNK_TILES;
-        const unsigned gx = (unsigned)((col_tiles + ct - 1) / ct);
-        B200_REQUIRE(gy <= 65535, "too many row tiles");
-        k_ci_count<<<dim3(gx, gy), CT_THREADS, 0, st>>>(est_s, n, r_lo, r_hi, r_s, r_ge, shard, n_shards, (int)ct, acc);
-    }
+    k_ci_count<<<8 * num_sms(), CT_THREADS, 0, st>>>(est_s, n, r_lo, r_hi, r_s, r_ge, shard, n_shards, acc);
     k_ci_final<<<1, 32, 0, st>>>(acc, reinterpret_cast<long long *>(out));
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
