@@ -132,3 +132,35 @@ def test_tile_shards_partition_the_pairs(n_shards):
         assert (part >= 0).all()
         acc += part
     assert torch.equal(acc, full), (acc.tolist(), full.tolist())
+
+
+@pytest.mark.parametrize("n", [1, 2, 37, 2048, 5000])
+def test_tile_shards_on_small_cohorts_including_empty_shards(n):
+    """Fewer row tiles than shards: the surplus shards count nothing, the sum is still exact."""
+    from multimodal_survival_prediction_b200 import synth
+    from multimodal_survival_prediction_b200.cindex import cindex_counts, cindex_counts_shard
+    lh, ev, t = synth.cohort(n, 33, risk_tie_frac=0.2)
+    t = torch.clamp(torch.floor(t / 200.0), 1, 40)          # many same-time pairs
+    x, e, tt = lh.cuda(), ev.cuda(), t.cuda()
+    full = cindex_counts(x, e, tt, 1e-8).cpu()
+    ref = oci.counts_fast(lh.numpy(), ev.numpy(), t.numpy())
+    assert full.tolist() == list(ref)
+    acc = torch.zeros(6, dtype=torch.int64)
+    for s in range(8):
+        acc += cindex_counts_shard(x, e, tt, s, 8, 1e-8).cpu()
+    assert torch.equal(acc, full)
+
+
+def test_cohorts_in_flight_match_one_by_one():
+    """b200surv_cindex_counts_cohorts with room for eight cohorts in flight (internal streams) equals per-cohort calls."""
+    from multimodal_survival_prediction_b200 import synth
+    from multimodal_survival_prediction_b200.cindex import cindex_counts, cindex_counts_cohorts
+    lens = [3001, 1, 777, 20_000, 2, 4096, 9999, 12, 5000, 64, 8191]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    lh, ev, t = synth.cohort(int(off[-1]), 17, risk_tie_frac=0.1)
+    x, e, tt = lh.cuda(), ev.cuda(), t.cuda()
+    out = cindex_counts_cohorts(x, e, tt, off.tolist()).cpu()
+    for c in range(len(lens)):
+        a, b = int(off[c]), int(off[c + 1])
+        one = cindex_counts(x[a:b].contiguous(), e[a:b].contiguous(), tt[a:b].contiguous(), 1e-8).cpu()
+        assert torch.equal(out[c], one), c
