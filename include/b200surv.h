@@ -273,6 +273,13 @@ int32_t b200surv_head_bwd(const b200surv_head_params *params, const b200surv_hea
                           size_t saved_bytes, void *workspace, size_t workspace_bytes,
                           b200surv_stream_t stream);
 
+/* Gate-entropy regulariser of the gated head (partial_modality_training.py:322-331, weighted 0.01 in the training
+ * step :418-422): out_loss[0] = mean_b sum_k g log(g + eps) over gate [B][3]; backward d_gate [B][3] =
+ * grad_out[0] * (log(g + eps) + g / (g + eps)) / B.  One launch each instead of eight small framework kernels. */
+int32_t b200surv_gate_entropy_fwd(const float *gate, int64_t B, float eps, float *out_loss, b200surv_stream_t stream);
+int32_t b200surv_gate_entropy_bwd(const float *gate, const float *grad_out, int64_t B, float eps, float *d_gate,
+                                  b200surv_stream_t stream);
+
 /* ---- test hooks: the hand-written sort / scan primitives behind the SORTED Cox path and the C-index ---------- */
 /* stable LSD radix sort of (u32 key, u32 value) pairs, in place (keys_tmp / vals_tmp: ping-pong buffers);
  * inclusive scan of (a, 2a, i), i combined by iop (0 add, 1 min, 2 max), ascending or descending index order. */

@@ -70,6 +70,8 @@ SIGNATURES = {
     "b200surv_cindex_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "b200surv_cindex_counts_cohorts": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int32,
                                                  c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200surv_gate_entropy_fwd": (c_int32, [c_void_p, c_int64, c_float, c_void_p, c_void_p]),
+    "b200surv_gate_entropy_bwd": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p]),
     "b200surv_debug_sortscan_temp_bytes": (c_size_t, [c_int64]),
     "b200surv_debug_sort_pairs": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "b200surv_debug_scan": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,

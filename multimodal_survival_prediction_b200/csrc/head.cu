@@ -462,6 +462,30 @@ int32_t gemm_wgrad(const void *a, int64_t lda, const void *b, int64_t ldb, int M
     return B200SURV_OK;
 }
 
+// ---------------------------------------------------------------- gate-entropy regulariser
+// partial_modality_training.py:322-331: loss = -mean_b( -sum_k g log(g + eps) ) = mean_b sum_k g log(g + eps).
+// One CTA (the value is one scalar; 3 B elements), fixed summation order: deterministic.
+__global__ void __launch_bounds__(1024)
+k_gate_entropy_fwd(const float *__restrict__ gate, int64_t B, float eps, float *__restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < 3 * B; i += blockDim.x) {
+        const float g = gate[i];
+        s += (double)(g * logf(g + eps));
+    }
+    s = block_reduce<double>(s, 0.0, OpAddD(), red);
+    if (threadIdx.x == 0) out[0] = (float)(s / (double)B);
+}
+// d loss / d g = (log(g + eps) + g / (g + eps)) / B
+__global__ void k_gate_entropy_bwd(const float *__restrict__ gate, const float *__restrict__ grad_out, int64_t B, float eps,
+                                   float *__restrict__ d_gate) {
+    const float k = grad_out[0] / (float)B;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * B; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = gate[i], ge = g + eps;
+        d_gate[i] = k * (logf(ge) + g / ge);
+    }
+}
+
 uint32_t drop_thresh(float p) {
     if (p <= 0.f) return 0;
     double t = (double)p * 4294967296.0;
@@ -638,6 +662,20 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     // ---- rna_encoder.0: dW1 [512][rna_dim] = dH1^T x  (the big one; x is an input, no dx)
     rc = gemm_wgrad(w.b0, H1, s.xb, Kp, H1, rna_dim, (int)B, g->rna0_w, rna_dim, w.splitk, st);
     if (rc) return rc;
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_gate_entropy_fwd(const float *gate, int64_t B, float eps, float *out_loss, b200surv_stream_t stream) {
+    B200_REQUIRE(gate && out_loss && B >= 1, "arguments");
+    k_gate_entropy_fwd<<<1, 1024, 0, as_stream(stream)>>>(gate, B, eps, out_loss);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+int32_t b200surv_gate_entropy_bwd(const float *gate, const float *grad_out, int64_t B, float eps, float *d_gate,
+                                  b200surv_stream_t stream) {
+    B200_REQUIRE(gate && grad_out && d_gate && B >= 1, "arguments");
+    k_gate_entropy_bwd<<<gs(3 * B), 256, 0, as_stream(stream)>>>(gate, grad_out, B, eps, d_gate);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }

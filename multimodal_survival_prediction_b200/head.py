@@ -260,6 +260,37 @@ class GraphedHeadStep:
         return self.replay()
 
 
+class _GateEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate, eps):
+        dev = gate.device
+        lib = L.load()
+        g = _f32c(gate, dev)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.b200surv_gate_entropy_fwd(L.ptr(g), g.shape[0], ctypes.c_float(eps), L.ptr(out), L.stream_ptr(dev)),
+                    "b200surv_gate_entropy_fwd")
+        ctx.save_for_backward(g)
+        ctx.meta = (float(eps), gate.dtype)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (g,) = ctx.saved_tensors
+        eps, dtype = ctx.meta
+        dev = g.device
+        go = _f32c(grad_out.reshape(1), dev)
+        dg = torch.empty_like(g)
+        with torch.cuda.device(dev):
+            L.check(L.load().b200surv_gate_entropy_bwd(L.ptr(g), L.ptr(go), g.shape[0], ctypes.c_float(eps), L.ptr(dg),
+                                                       L.stream_ptr(dev)), "b200surv_gate_entropy_bwd")
+        return (dg if dtype is torch.float32 else dg.to(dtype)), None
+
+
 def gate_entropy_loss(gate_weights, eps=1e-8):
-    """partial_modality_training.py:322-331 (plain autograd; its gradient enters the head through d_gate)."""
+    """partial_modality_training.py:322-331: mean over the batch of sum_k g log(g + eps) (the negative gate entropy;
+    its gradient enters the head through d_gate).  One fused kernel each way for CUDA (B, 3) inputs; the reference's
+    expression otherwise."""
+    if gate_weights.is_cuda and gate_weights.dim() == 2 and gate_weights.shape[1] == 3 and gate_weights.shape[0] >= 1:
+        return _GateEntropy.apply(gate_weights, eps)
     return -(-(gate_weights * torch.log(gate_weights + eps)).sum(dim=1)).mean()

@@ -234,3 +234,19 @@ def test_graphed_step_matches_eager_and_redraws_dropout():
     m3.load_state_dict(before)
     b = g3.replay()[1][0].clone()
     assert not torch.equal(a, b)
+
+
+def test_gate_entropy_loss_matches_the_reference_expression():
+    """SURVEY 8f #1: fused gate-entropy regulariser == partial_modality_training.py:322-331 (value and gradient)."""
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(1)
+    for B in (1, 7, 4096, 100_003):
+        g = torch.softmax(torch.randn(B, 3, device=dev) * 3, dim=1).requires_grad_(True)
+        g2 = g.detach().clone().requires_grad_(True)
+        eps = 1e-8
+        ours = ghead.gate_entropy_loss(g, eps)
+        ref = -(-(g2 * torch.log(g2 + eps)).sum(dim=1)).mean()
+        (2.5 * ours).backward()
+        (2.5 * ref).backward()
+        assert abs(float(ours) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref))), (B, float(ours), float(ref))
+        assert float((g.grad - g2.grad).abs().max()) <= 1e-5 * float(g2.grad.abs().max()) + 1e-9, B
