@@ -280,6 +280,19 @@ int32_t b200surv_gate_entropy_fwd(const float *gate, int64_t B, float eps, float
 int32_t b200surv_gate_entropy_bwd(const float *gate, const float *grad_out, int64_t B, float eps, float *d_gate,
                                   b200surv_stream_t stream);
 
+/* Fused clip_grad_norm_(max_norm) + Adam / AdamW step over a list of fp32 tensors -- the end of the reference's
+ * training step (partial_modality_training.py:427-428 with optim.Adam(lr, weight_decay=1e-4) :536; simple_fusion.py
+ * :273-274 with optim.AdamW :391).  params / grads / exp_avg / exp_avg_sq: HOST arrays of n_tensors device pointers,
+ * numel_host their element counts; max_norm <= 0 disables clipping; adamw != 0: decoupled weight decay; step = 1, 2,
+ * ... (bias correction); out_total_norm (device, nullable) receives the gradient norm before clipping.  Same update
+ * as torch.optim.Adam / AdamW (no amsgrad), deterministic. */
+size_t b200surv_clip_adam_workspace_bytes(const int64_t *numel_host, int32_t n_tensors);
+int32_t b200surv_clip_adam_step(float *const *params, const float *const *grads, float *const *exp_avg,
+                                float *const *exp_avg_sq, const int64_t *numel_host, int32_t n_tensors, float max_norm,
+                                float lr, float beta1, float beta2, float eps, float weight_decay, int32_t adamw,
+                                int64_t step, float *out_total_norm, void *workspace, size_t workspace_bytes,
+                                b200surv_stream_t stream);
+
 /* ---- test hooks: the hand-written sort / scan primitives behind the SORTED Cox path and the C-index ---------- */
 /* stable LSD radix sort of (u32 key, u32 value) pairs, in place (keys_tmp / vals_tmp: ping-pong buffers);
  * inclusive scan of (a, 2a, i), i combined by iop (0 add, 1 min, 2 max), ascending or descending index order. */
