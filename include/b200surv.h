@@ -273,6 +273,19 @@ int32_t b200surv_head_bwd(const b200surv_head_params *params, const b200surv_hea
                           size_t saved_bytes, void *workspace, size_t workspace_bytes,
                           b200surv_stream_t stream);
 
+/* Labelled-row compaction (partial_modality_training.py:401-408: hazard[mask], label[mask, 0], label[mask, 1] with
+ * mask = has_survival): keeps the rows with has_survival[b] != 0 in order.  label is [B][2] = (time, event as 0/1
+ * float).  Outputs sized for B rows: out_hazard, out_time, out_event (0/1 bytes = torch.bool storage), out_index
+ * (source row of every kept row, for the backward scatter), out_counts[2] = {rows kept, events kept} (device; the
+ * caller reads them to size the loss call and to apply the reference's skip rule n >= 2 && events > 0).
+ * b200surv_scatter_rows: out_grad[B] = 0, out_grad[index[q]] = grad_sel[q] (the backward of the selection). */
+size_t b200surv_compact_workspace_bytes(int64_t B);
+int32_t b200surv_compact_labelled(const float *hazard, const float *label, const uint8_t *has_survival, int64_t B,
+                                  float *out_hazard, float *out_time, uint8_t *out_event, int32_t *out_index,
+                                  int64_t *out_counts, void *workspace, size_t workspace_bytes, b200surv_stream_t stream);
+int32_t b200surv_scatter_rows(const float *grad_sel, const int32_t *index, int64_t n_sel, int64_t B, float *out_grad,
+                              b200surv_stream_t stream);
+
 /* Gate-entropy regulariser of the gated head (partial_modality_training.py:322-331, weighted 0.01 in the training
  * step :418-422): out_loss[0] = mean_b sum_k g log(g + eps) over gate [B][3]; backward d_gate [B][3] =
  * grad_out[0] * (log(g + eps) + g / (g + eps)) / B.  One launch each instead of eight small framework kernels. */

@@ -70,6 +70,10 @@ SIGNATURES = {
     "b200surv_cindex_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "b200surv_cindex_counts_cohorts": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int32,
                                                  c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200surv_compact_workspace_bytes": (c_size_t, [c_int64]),
+    "b200surv_compact_labelled": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200surv_scatter_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "b200surv_clip_adam_workspace_bytes": (c_size_t, [c_void_p, c_int32]),
     "b200surv_clip_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float, c_float, c_float,
                                           c_float, c_float, c_float, c_int32, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
