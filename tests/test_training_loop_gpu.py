@@ -14,7 +14,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_style_training_loop_learns():
+@pytest.mark.parametrize("fused_step", [False, True])
+def test_reference_style_training_loop_learns(fused_step):
+    """fused_step: the labelled-row selection and clip + Adam also come from this package (select_labelled, ClipAdam)."""
     sys.path.insert(0, os.path.join(ROOT, "shim"))
     try:
         from torchsurv.loss.cox import neg_partial_log_likelihood        # resolves to the B200 operators
@@ -39,7 +41,11 @@ def test_reference_style_training_loop_learns():
     label = torch.stack([time, event.float()], 1)
 
     model = ghead.PartialModalityNet().to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    from multimodal_survival_prediction_b200.compact import select_labelled
+    from multimodal_survival_prediction_b200.optim import ClipAdam
+    params = [p for n_, p in model.named_parameters() if not n_.startswith("ct_encoder")]
+    opt = (ClipAdam(params, lr=1e-3, weight_decay=1e-4, max_norm=1.0) if fused_step
+           else torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4))
 
     def cox_loss(hazard, ev, tm):                                         # partial_modality_training.py:285-288
         return neg_partial_log_likelihood(hazard, ev.bool(), tm)
@@ -54,13 +60,18 @@ def test_reference_style_training_loop_learns():
             lab, surv = label[sl].to(dev), has_survival[sl].to(dev)
             with torch.set_grad_enabled(train):
                 hazard, gate = model.forward_features(c, r, cl, m)
-                hs, ts, es = hazard[surv], lab[surv, 0], lab[surv, 1]
-                c_loss = cox_loss(hs, es, ts) if hs.shape[0] >= 2 and es.sum() > 0 else torch.tensor(0.0, device=dev)
+                if fused_step:
+                    hs, ts, es, n_ev = select_labelled(hazard, lab, surv)
+                else:
+                    hs, ts, es = hazard[surv], lab[surv, 0], lab[surv, 1]
+                    n_ev = int(es.sum())
+                c_loss = cox_loss(hs, es, ts) if hs.shape[0] >= 2 and n_ev > 0 else torch.tensor(0.0, device=dev)
                 loss = c_loss + 0.01 * ghead.gate_entropy_loss(gate)
             if train:
                 opt.zero_grad()
                 loss.backward()
-                torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+                if not fused_step:
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
                 opt.step()
             tot += float(c_loss.detach()); nb += 1
             hz_all.append(hs.detach().cpu()); ev_all.append(es.detach().cpu()); t_all.append(ts.detach().cpu())
