@@ -289,8 +289,9 @@ class _GateEntropy(torch.autograd.Function):
 
 def gate_entropy_loss(gate_weights, eps=1e-8):
     """partial_modality_training.py:322-331: mean over the batch of sum_k g log(g + eps) (the negative gate entropy;
-    its gradient enters the head through d_gate).  One fused kernel each way for CUDA (B, 3) inputs; the reference's
-    expression otherwise."""
-    if gate_weights.is_cuda and gate_weights.dim() == 2 and gate_weights.shape[1] == 3 and gate_weights.shape[0] >= 1:
+    its gradient enters the head through d_gate).  One fused kernel each way for the head's (B, 3) gate weights."""
+    if not gate_weights.is_cuda:
+        raise L.B200SurvError("gate_entropy_loss has no CPU path: the gate weights come from the CUDA head")
+    if gate_weights.dim() == 2 and gate_weights.shape[1] == 3 and gate_weights.shape[0] >= 1:
         return _GateEntropy.apply(gate_weights, eps)
-    return -(-(gate_weights * torch.log(gate_weights + eps)).sum(dim=1)).mean()
+    return -(-(gate_weights * torch.log(gate_weights + eps)).sum(dim=1)).mean()   # other widths: the reference's expression
