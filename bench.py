@@ -5,13 +5,15 @@
 
 Workload at N=1: Efron ties, 16,777,216 synthetic patients (integer days 1..4000 => heavy ties,
 ~30 % events, log_hz ~ N(0,1), seed 1234) resident in HBM; one step = forward + backward through the
-C ABI (b200surv_cox_binned_partial/finalize + b200surv_cox_bwd).  At N>1 (torchrun, one rank per
-GPU) each rank holds 16,777,216 rows of an N x 16M-row cohort: per-bin aggregates are all-reduced
-over NCCL each step (weak scaling; value = all rows / max-over-ranks time).
+C ABI (b200surv_cox_fwd: one cooperative launch; b200surv_cox_bwd: one launch).  At N>1 (torchrun, one rank per
+GPU) each rank holds 16,777,216 rows of an N x 16M-row cohort: the per-bin int64 sums are exchanged INSIDE the forward
+kernel over NVLink peer memory (b200surv_cox_binned_fwd_peer; --exchange nccl: partial / all-reduce / finalize)
+each step (weak scaling; value = all rows / max-over-ranks time).
 
 Extra measurements on the same JSON line: `e2e` (public Python API, pinned host inputs, H2D + D2H in
 the timed region), `roofline` (dominant kernel, CUDA events), `cpu_baseline` (oracle port on the
-host cores), `extra.cindex_1m` (C-index on 1M patients, row-sharded over the N ranks).
+host cores), `extra.cindex_1m` (C-index on 1M patients, tile-sharded over the N ranks), `extra.head_b4096` (gated
+fusion head fwd+bwd, B = 4096), `extra.cv_sweep` (one GPU's share of the 5-fold CV sweep).
 `--impl reference` times the CPU port of the reference's loss (oracle/cox_torch.py) instead.
 """
 from __future__ import annotations
