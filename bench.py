@@ -361,6 +361,23 @@ def run_b200(args):
 
     sweep_cox_ms, sweep_ci_ms = timed_ms(sweep_cox), timed_ms(sweep_ci)
 
+    # ---- CPU baseline of the C-index (rank 0, N=1 only; bounded samples): the oracle's C brute force -- the same
+    # O(n^2) pair rule as the GPU kernel and the reference's fallback (simple_fusion.py:59-73), all host cores (OpenMP)
+    ci_cpu = None
+    if rank == 0 and world == 1:
+        try:
+            from oracle import cindex as oci
+            m = 40_000
+            t0 = time.perf_counter()
+            cb = oci.counts_brute(clh[:m].numpy(), cev[:m].numpy(), ct[:m].numpy())
+            dt_b = time.perf_counter() - t0
+            ci_cpu = {"kind": "port", "cores": os.cpu_count(),
+                      "sample": f"first {m} of the 1,048,576 patients, brute-force C with OpenMP (oracle/cindex_oracle.c)",
+                      "ordered_pairs_per_s": float(sum(int(v) for v in cb)) / dt_b, "seconds": dt_b,
+                      "extrapolated_ms_at_1m": dt_b * (cn / m) ** 2 * 1e3}
+        except Exception as ex:  # noqa: BLE001 -- the baseline is optional, the bench line is not
+            ci_cpu = {"unavailable": repr(ex)}
+
     if rank == 0:
         peak, peak_src = load_peaks()
         achieved_bwd = BWD_BYTES_PER_ROW * n / (bwd_ms * 1e-3) / 1e9
@@ -404,7 +421,8 @@ def run_b200(args):
             "clocks": clocks,
             "extra": {"cindex_1m": {"n": cn, "ms": ci_ms, "patients_per_s": cn / (ci_ms * 1e-3),
                                     "ordered_pairs_per_s": sum(counts) / (ci_ms * 1e-3), "counts": counts,
-                                    "n_gpus": world, "scaling": "strong (rows sharded, int64 all-reduce)"},
+                                    "n_gpus": world, "scaling": "strong (row tiles sharded, int64 all-reduce)",
+                                    "cpu_baseline": ci_cpu},
                       "cv_sweep": {"replicas_per_gpu": sw_rep, "rows_per_replica": sw_rows, "n_gpus": world,
                                    "cox_fwd_bwd_ms": sweep_cox_ms, "cindex_ms": sweep_ci_ms,
                                    "replica_evals_per_s": world * sw_rep / ((sweep_cox_ms + sweep_ci_ms) * 1e-3),
