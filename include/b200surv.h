@@ -306,6 +306,52 @@ int32_t b200surv_clip_adam_step(float *const *params, const float *const *grads,
                                 int64_t step, float *out_total_norm, void *workspace, size_t workspace_bytes,
                                 b200surv_stream_t stream);
 
+/* ---- CT encoder feeding the head --------------------------------------------------------- */
+/* The reference's non-MONAI CT branch (partial_modality_training.py:179-190): three Conv3d(k 3, stride 2, pad 1) +
+ * BatchNorm3d + ReLU stages (1 -> 32 -> 64 -> 128 channels) and AdaptiveAvgPool3d(1), as primitives the host layer
+ * (ctenc.py) strings together.  Activations are CHANNELS-LAST: rows = (sample, z, y, x) of a stage's output grid,
+ * columns = channels; an input grid D x H x W gives an output grid ((D-1)/2+1) x ((H-1)/2+1) x ((W-1)/2+1).
+ *   conv_first_fwd  : x fp32 [B][D][H][W] (one input channel), w fp32 [Cout][27] (torch (Cout,1,3,3,3)), bias ->
+ *                     h fp32 [B*Do*Ho*Wo][Cout]                                       (direct kernel, K = 27)
+ *   conv_first_wgrad: dw fp32 [Cout][27] = sum_rows dx[row][c] * patch(row)[tap]        (dx bf16 [rows][Cout])
+ *   im2col / col2im : a bf16 [Bc*D*H*W][C] -> col bf16 [Bc*Do*Ho*Wo][27*C] (column = tap*C + c; the conv is then
+ *                     b200surv_gemm_bf16(col, W_packed)); dcol bf16 -> da fp32 [Bc*D*H*W][C] by gathering (no atomics)
+ *   weight_pack     : w fp32 (Cout,Cin,3,3,3) -> bf16 [Cout][27*Cin] tap-major; weight_unpack: the sum of `slices`
+ *                     fp32 [Cout][27*Cin] gradient slices -> dw fp32 (Cout,Cin,3,3,3)
+ *   bn_stats        : training: mu, rstd of the columns of x [R][C] (biased variance, eps 1e-5) and running <- 0.9
+ *                     running + 0.1 (mu, unbiased variance) like nn.BatchNorm3d; eval: mu, rstd from the running stats
+ *   bn_relu         : y bf16 = relu((x - mu) rstd gamma + beta);   bn_relu_pool: feat fp32 [B][C] = mean over the V
+ *                     voxels of a sample of the same (stage 3 + AdaptiveAvgPool3d(1));  pool_bwd: dA[r][c] = dfeat[b][c]/V
+ *   bn_bwd          : dy = [bn(x) > 0] dA; dgamma = sum dy xhat, dbeta = sum dy, dx bf16 = gamma rstd (dy - dbeta/R -
+ *                     xhat dgamma/R) (training) or gamma rstd dy (eval); dbias = sum_rows dx (gradient of the conv bias)
+ * C must be a power of two in [8, 256] for the bn_* calls and a multiple of 8 for im2col / col2im.  Every reduction
+ * sums in a fixed order (deterministic).  workspace: b200surv_ct_workspace_bytes() bytes. */
+size_t b200surv_ct_workspace_bytes(void);
+int32_t b200surv_ct_conv_first_fwd(const float *x, const float *w, const float *bias, int64_t B, int32_t D, int32_t H,
+                                   int32_t W, int32_t Cout, float *h, b200surv_stream_t stream);
+int32_t b200surv_ct_conv_first_wgrad(const float *x, const void *dx_bf16, int64_t B, int32_t D, int32_t H, int32_t W,
+                                     int32_t Cout, float *dw, void *workspace, size_t workspace_bytes,
+                                     b200surv_stream_t stream);
+int32_t b200surv_ct_im2col(const void *a_bf16, int64_t Bc, int32_t D, int32_t H, int32_t W, int32_t C, void *col_bf16,
+                           b200surv_stream_t stream);
+int32_t b200surv_ct_col2im(const void *dcol_bf16, int64_t Bc, int32_t D, int32_t H, int32_t W, int32_t C, float *da,
+                           b200surv_stream_t stream);
+int32_t b200surv_ct_weight_pack(const float *w, int32_t Cout, int32_t Cin, void *wr_bf16, b200surv_stream_t stream);
+int32_t b200surv_ct_weight_unpack(const float *dwr_slices, int32_t slices, int32_t Cout, int32_t Cin, float *dw,
+                                  b200surv_stream_t stream);
+int32_t b200surv_ct_bn_stats(const float *x, int64_t R, int32_t C, int32_t training, float *run_mean, float *run_var,
+                             float *mu, float *rstd, void *workspace, size_t workspace_bytes, b200surv_stream_t stream);
+int32_t b200surv_ct_bn_relu(const float *x, const float *mu, const float *rstd, const float *gamma, const float *beta,
+                            int64_t R, int32_t C, void *y_bf16, b200surv_stream_t stream);
+int32_t b200surv_ct_bn_relu_pool(const float *x, const float *mu, const float *rstd, const float *gamma,
+                                 const float *beta, int64_t B, int32_t V, int32_t C, float *feat,
+                                 b200surv_stream_t stream);
+int32_t b200surv_ct_pool_bwd(const float *dfeat, int64_t B, int32_t V, int32_t C, float *dA, b200surv_stream_t stream);
+int32_t b200surv_ct_bn_bwd(const float *x, const float *dA, const float *mu, const float *rstd, const float *gamma,
+                           const float *beta, int64_t R, int32_t C, int32_t training, void *dx_bf16, float *dgamma,
+                           float *dbeta, float *dbias, void *workspace, size_t workspace_bytes,
+                           b200surv_stream_t stream);
+
 /* ---- test hooks: the hand-written sort / scan primitives behind the SORTED Cox path and the C-index ---------- */
 /* stable LSD radix sort of (u32 key, u32 value) pairs, in place (keys_tmp / vals_tmp: ping-pong buffers);
  * inclusive scan of (a, 2a, i), i combined by iop (0 add, 1 min, 2 max), ascending or descending index order. */

@@ -5,8 +5,8 @@ C ABI in include/b200surv.h.  Importing the package does not need a GPU; calling
 from . import _lib
 from ._lib import B200SurvError
 from .cindex import ConcordanceIndex, cindex_counts, cindex_from_counts
-from .compact import select_labelled
+from .compact import ValidationCohort, select_labelled
 from .cox import neg_partial_log_likelihood, neg_partial_log_likelihood_segmented
 
 __all__ = ["B200SurvError", "ConcordanceIndex", "cindex_counts", "cindex_from_counts",
-           "neg_partial_log_likelihood", "neg_partial_log_likelihood_segmented", "select_labelled"]
+           "neg_partial_log_likelihood", "neg_partial_log_likelihood_segmented", "select_labelled", "ValidationCohort"]

@@ -79,6 +79,22 @@ SIGNATURES = {
                                           c_float, c_float, c_float, c_int32, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200surv_gate_entropy_fwd": (c_int32, [c_void_p, c_int64, c_float, c_void_p, c_void_p]),
     "b200surv_gate_entropy_bwd": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p]),
+    "b200surv_ct_workspace_bytes": (c_size_t, []),
+    "b200surv_ct_conv_first_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                             c_void_p, c_void_p]),
+    "b200surv_ct_conv_first_wgrad": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                               c_void_p, c_size_t, c_void_p]),
+    "b200surv_ct_im2col": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200surv_ct_col2im": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200surv_ct_weight_pack": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200surv_ct_weight_unpack": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200surv_ct_bn_stats": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_void_p]),
+    "b200surv_ct_bn_relu": (c_int32, [c_void_p] * 5 + [c_int64, c_int32, c_void_p, c_void_p]),
+    "b200surv_ct_bn_relu_pool": (c_int32, [c_void_p] * 5 + [c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200surv_ct_pool_bwd": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200surv_ct_bn_bwd": (c_int32, [c_void_p] * 6 + [c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                     c_void_p, c_size_t, c_void_p]),
     "b200surv_debug_sortscan_temp_bytes": (c_size_t, [c_int64]),
     "b200surv_debug_sort_pairs": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "b200surv_debug_scan": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,

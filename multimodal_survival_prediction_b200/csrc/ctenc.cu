@@ -1,0 +1,542 @@
+// CT encoder feeding the fusion head: the reference's non-MONAI branch,
+// scripts/training/partial_modality_training.py:179-190
+//     Conv3d(1,32,3,s2,p1) BN3d ReLU  Conv3d(32,64,3,s2,p1) BN3d ReLU  Conv3d(64,128,3,s2,p1) BN3d ReLU  AdaptiveAvgPool3d(1)
+// as B200 primitives behind the C ABI; the host layer (ctenc.py) strings them together.
+//
+// Layout: activations are CHANNELS-LAST, rows = (sample, z, y, x) of a layer's output grid, columns = channels, so that
+//   * BatchNorm3d is a per-column normalisation of an [R][C] matrix (R = B * voxels),
+//   * the 3x3x3 stride-2 convolutions with Cin >= 32 are GEMMs [R][27 Cin] x [27 Cin][Cout] on the tcgen05 kernel of
+//     gemm_tc.cu: the patch matrix ("col", tap-major: column = tap * Cin + c, so every tap is one contiguous Cin-vector
+//     of the source voxel) is written by k_im2col for a CHUNK of samples sized to stay in the 126 MB L2 between the
+//     im2col store and the GEMM's TMA loads,
+//   * the first convolution (Cin = 1, K = 27: too thin for the tensor pipe) is a direct CUDA-core kernel.
+// Backward: BN/ReLU backward in two streaming passes (column sums, then dx as bf16), weight gradients = dx^T col on the
+// GEMM (both operands MN-major), input gradients = dx W on the GEMM followed by a GATHER col2im (every input voxel pulls
+// its <= 8 (tap, output voxel) contributions: no atomics, deterministic).  Every reduction sums in a fixed order.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace b200surv {
+namespace {
+
+using bf16 = __nv_bfloat16;
+constexpr float BN_EPS = 1e-5f, BN_MOM = 0.1f;
+
+struct Grid3 {            // input grid of one stride-2 convolution and its output grid
+    int D, H, W, Do, Ho, Wo;
+};
+inline int out_dim(int d) { return (d - 1) / 2 + 1; }   // floor((d + 2*1 - 3) / 2) + 1
+inline Grid3 make_grid(int D, int H, int W) { return Grid3{D, H, W, out_dim(D), out_dim(H), out_dim(W)}; }
+
+inline unsigned blocks_for(int64_t items, int per_block, int max_per_sm) {
+    int64_t g = (items + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)max_per_sm * num_sms();
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+// ---------------------------------------------------------------- first convolution (Cin = 1), direct
+// x fp32 [B][D][H][W]; w fp32 [Cout][27] (torch (Cout,1,3,3,3)); h fp32 [B*Do*Ho*Wo][Cout].  One thread = one output
+// voxel x 8 channels (Cout/8 neighbouring threads share the voxel and write 32 contiguous bytes each).
+__global__ void __launch_bounds__(256)
+k_conv_first_fwd(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, int64_t B,
+                 Grid3 g, int Cout, float *__restrict__ h) {
+    extern __shared__ float sw[];           // [27][Cout] then bias[Cout]
+    for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) { const int c = i % Cout, t = i / Cout; sw[i] = w[c * 27 + t]; }
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int groups = Cout / 8;
+    const int64_t vox = (int64_t)g.Do * g.Ho * g.Wo, total = B * vox * groups;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % groups);
+        const int64_t r = i / groups;
+        const int64_t b = r / vox;
+        int v = (int)(r - b * vox);
+        const int xo = v % g.Wo; v /= g.Wo;
+        const int yo = v % g.Ho, zo = v / g.Ho;
+        const float *xb = x + b * (int64_t)g.D * g.H * g.W;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = sw[27 * Cout + cg * 8 + j];
+#pragma unroll
+        for (int kz = 0; kz < 3; ++kz) {
+            const int z = 2 * zo - 1 + kz;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int y = 2 * yo - 1 + ky;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = 2 * xo - 1 + kx;
+                    const bool in = z >= 0 && z < g.D && y >= 0 && y < g.H && xx >= 0 && xx < g.W;
+                    const float xv = in ? __ldg(xb + ((int64_t)z * g.H + y) * g.W + xx) : 0.f;
+                    const float4 w0 = *reinterpret_cast<const float4 *>(sw + (kz * 9 + ky * 3 + kx) * Cout + cg * 8);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(sw + (kz * 9 + ky * 3 + kx) * Cout + cg * 8 + 4);
+                    acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
+                    acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+                }
+            }
+        }
+        float4 *o = reinterpret_cast<float4 *>(h + r * Cout + cg * 8);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
+
+// weight gradient of the first convolution: dw[c][tap] = sum_r dx[r][c] * patch_r[tap].  Thread = (row lane, channel);
+// 27 accumulators per thread; the patch values are warp-uniform (broadcast loads).  partial[cta][Cout][27] (fp32) is
+// summed in CTA order by k_conv_first_wgrad_final.
+__global__ void __launch_bounds__(256)
+k_conv_first_wgrad(const float *__restrict__ x, const bf16 *__restrict__ dx, int64_t B, Grid3 g, int Cout,
+                   float *__restrict__ partial) {
+    extern __shared__ float red[];          // [256][27]
+    const int c = threadIdx.x % Cout, lane_r = threadIdx.x / Cout, lanes = blockDim.x / Cout;
+    const int64_t vox = (int64_t)g.Do * g.Ho * g.Wo, R = B * vox;
+    const int64_t per = (R + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(R, r0 + per);
+    float acc[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+    for (int64_t r = r0 + lane_r; r < r1; r += lanes) {
+        const float d = __bfloat162float(dx[r * Cout + c]);
+        const int64_t b = r / vox;
+        int v = (int)(r - b * vox);
+        const int xo = v % g.Wo; v /= g.Wo;
+        const int yo = v % g.Ho, zo = v / g.Ho;
+        const float *xb = x + b * (int64_t)g.D * g.H * g.W;
+#pragma unroll
+        for (int kz = 0; kz < 3; ++kz) {
+            const int z = 2 * zo - 1 + kz;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int y = 2 * yo - 1 + ky;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = 2 * xo - 1 + kx;
+                    const bool in = z >= 0 && z < g.D && y >= 0 && y < g.H && xx >= 0 && xx < g.W;
+                    const float xv = in ? __ldg(xb + ((int64_t)z * g.H + y) * g.W + xx) : 0.f;
+                    acc[kz * 9 + ky * 3 + kx] += d * xv;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 27; ++t) red[threadIdx.x * 27 + t] = acc[t];
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) {
+        const int cc = i / 27, t = i % 27;
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[(l * Cout + cc) * 27 + t];
+        partial[(size_t)blockIdx.x * Cout * 27 + i] = s;
+    }
+}
+__global__ void k_sum_slices(const float *__restrict__ part, int slices, int64_t elems, float *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < slices; ++k) s += part[(size_t)k * elems + i];
+        out[i] = (float)s;
+    }
+}
+
+// ---------------------------------------------------------------- im2col / col2im (stride 2, pad 1, 3x3x3)
+// a bf16 [Bc*D*H*W][C] -> col bf16 [Bc*Do*Ho*Wo][27*C], column = tap*C + c.  One thread = 8 channels (16 bytes).
+__global__ void __launch_bounds__(256)
+k_im2col(const bf16 *__restrict__ a, int64_t Bc, Grid3 g, int C, bf16 *__restrict__ col) {
+    const int cv = C / 8;
+    const int64_t vox = (int64_t)g.Do * g.Ho * g.Wo, total = Bc * vox * 27 * cv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cv);
+        int64_t q = i / cv;
+        const int tap = (int)(q % 27);
+        const int64_t r = q / 27;
+        const int64_t b = r / vox;
+        int v = (int)(r - b * vox);
+        const int xo = v % g.Wo; v /= g.Wo;
+        const int yo = v % g.Ho, zo = v / g.Ho;
+        const int kz = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
+        const int z = 2 * zo - 1 + kz, y = 2 * yo - 1 + ky, xx = 2 * xo - 1 + kx;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (z >= 0 && z < g.D && y >= 0 && y < g.H && xx >= 0 && xx < g.W)
+            val = __ldg(reinterpret_cast<const uint4 *>(a + (((b * g.D + z) * g.H + y) * (int64_t)g.W + xx) * C) + c8);
+        reinterpret_cast<uint4 *>(col)[i] = val;      // i == (r*27 + tap)*cv + c8
+    }
+}
+__device__ __forceinline__ void add_bf16x8(float *acc, uint4 v) {
+    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(p[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+}
+// dcol bf16 [Bc*Do*Ho*Wo][27*C] -> da fp32 [Bc*D*H*W][C]: input voxel (z,y,x) receives tap (kz,ky,kx) of output voxel
+// ((z+1-kz)/2, ...) whenever that is an integer inside the output grid.
+__global__ void __launch_bounds__(256)
+k_col2im(const bf16 *__restrict__ dcol, int64_t Bc, Grid3 g, int C, float *__restrict__ da) {
+    const int cv = C / 8;
+    const int64_t vin = (int64_t)g.D * g.H * g.W, vox = (int64_t)g.Do * g.Ho * g.Wo, total = Bc * vin * cv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cv);
+        const int64_t p = i / cv;
+        const int64_t b = p / vin;
+        int v = (int)(p - b * vin);
+        const int xx = v % g.W; v /= g.W;
+        const int y = v % g.H, z = v / g.H;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int kz = (z + 1) & 1; kz < 3; kz += 2) {
+            const int zo = (z + 1 - kz) / 2;
+            if (z + 1 - kz < 0 || zo >= g.Do) continue;
+            for (int ky = (y + 1) & 1; ky < 3; ky += 2) {
+                const int yo = (y + 1 - ky) / 2;
+                if (y + 1 - ky < 0 || yo >= g.Ho) continue;
+                for (int kx = (xx + 1) & 1; kx < 3; kx += 2) {
+                    const int xo = (xx + 1 - kx) / 2;
+                    if (xx + 1 - kx < 0 || xo >= g.Wo) continue;
+                    const int64_t r = b * vox + ((int64_t)zo * g.Ho + yo) * g.Wo + xo;
+                    const int tap = kz * 9 + ky * 3 + kx;
+                    add_bf16x8(acc, __ldg(reinterpret_cast<const uint4 *>(dcol + (r * 27 + tap) * C) + c8));
+                }
+            }
+        }
+        float4 *o = reinterpret_cast<float4 *>(da + p * C + c8 * 8);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
+
+// ---------------------------------------------------------------- weights: torch (Cout,Cin,3,3,3) <-> tap-major
+__global__ void k_weight_pack(const float *__restrict__ w, int Cout, int Cin, bf16 *__restrict__ wr) {
+    const int total = Cout * Cin * 27;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % Cin, tap = (i / Cin) % 27, o = i / (27 * Cin);       // i indexes wr
+        wr[i] = __float2bfloat16_rn(w[((size_t)o * Cin + c) * 27 + tap]);
+    }
+}
+__global__ void k_weight_unpack(const float *__restrict__ dwr, int slices, int Cout, int Cin, float *__restrict__ dw) {
+    const int total = Cout * Cin * 27;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tap = i % 27, c = (i / 27) % Cin, o = i / (27 * Cin);        // i indexes dw
+        double s = 0.0;
+        for (int k = 0; k < slices; ++k) s += dwr[(size_t)k * total + ((size_t)o * 27 + tap) * Cin + c];
+        dw[i] = (float)s;
+    }
+}
+
+// ---------------------------------------------------------------- BatchNorm3d on [R][C] (channels-last), C | 1024
+// Column sums of an [R][C] fp32 matrix read as float4: thread t always sees channels (4t) % C .. +3.
+// MODE 0: (sum x, sum x^2).  MODE 1: dy = [bn(x) > 0] * dA -> (sum dy, sum dy * xhat).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_bn_colsums(const float *__restrict__ x, const float *__restrict__ dA, const float *__restrict__ mu,
+             const float *__restrict__ rstd, const float *__restrict__ gamma, const float *__restrict__ beta, int64_t R,
+             int C, double *__restrict__ partial) {
+    __shared__ double sh[256][8];
+    const int t = threadIdx.x, c0 = (4 * t) % C;
+    const int64_t nvec = R * C / 4;
+    const int64_t per = ((nvec + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;     // keeps t <-> channel fixed
+    const int64_t v0 = (int64_t)blockIdx.x * per, v1 = min(nvec, v0 + per);
+    float m[4] = {0, 0, 0, 0}, rs[4] = {0, 0, 0, 0}, ga[4] = {0, 0, 0, 0}, be[4] = {0, 0, 0, 0};
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { m[j] = mu[c0 + j]; rs[j] = rstd[c0 + j]; ga[j] = gamma[c0 + j]; be[j] = beta[c0 + j]; }
+    }
+    double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+    int64_t v = v0 + t;
+    while (v < v1) {
+        float f0[4] = {0, 0, 0, 0}, f1[4] = {0, 0, 0, 0};
+        for (int it = 0; it < 16 && v < v1; ++it, v += 256) {      // short fp32 runs, folded into fp64
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(x) + v);
+            const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+            if (MODE == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { f0[j] += xa[j]; f1[j] += xa[j] * xa[j]; }
+            } else {
+                const float4 dv = __ldg(reinterpret_cast<const float4 *>(dA) + v);
+                const float da[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float xh = (xa[j] - m[j]) * rs[j];
+                    const float dy = (xh * ga[j] + be[j] > 0.f) ? da[j] : 0.f;
+                    f0[j] += dy; f1[j] += dy * xh;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s0[j] += f0[j]; s1[j] += f1[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sh[t][j] = s0[j]; sh[t][4 + j] = s1[j]; }
+    __syncthreads();
+    if (t < C) {
+        const int q = C / 4;                  // threads t' = t/4 + k*q hold channel t
+        double a0 = 0.0, a1 = 0.0;
+        for (int k = 0; k < 256 / q; ++k) { a0 += sh[t / 4 + k * q][t % 4]; a1 += sh[t / 4 + k * q][4 + t % 4]; }
+        partial[((size_t)blockIdx.x * 2 + 0) * C + t] = a0;
+        partial[((size_t)blockIdx.x * 2 + 1) * C + t] = a1;
+    }
+}
+__global__ void k_bn_finalize(const double *__restrict__ partial, int nparts, int64_t R, int C, int training,
+                              float *__restrict__ run_mean, float *__restrict__ run_var, float *__restrict__ mu,
+                              float *__restrict__ rstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (!training) { mu[c] = run_mean[c]; rstd[c] = rsqrtf(run_var[c] + BN_EPS); return; }
+    double s = 0.0, ss = 0.0;
+    for (int k = 0; k < nparts; ++k) { s += partial[((size_t)k * 2 + 0) * C + c]; ss += partial[((size_t)k * 2 + 1) * C + c]; }
+    const double mean = s / (double)R;
+    double var = ss / (double)R - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mu[c] = (float)mean;
+    rstd[c] = (float)(1.0 / sqrt(var + (double)BN_EPS));
+    if (run_mean) {
+        const double unb = R > 1 ? var * ((double)R / (double)(R - 1)) : var;
+        run_mean[c] = (1.f - BN_MOM) * run_mean[c] + BN_MOM * (float)mean;
+        run_var[c] = (1.f - BN_MOM) * run_var[c] + BN_MOM * (float)unb;
+    }
+}
+// sums of the backward pass: sdy, sdyx (kept for k_bn_dx), dgamma = sdyx, dbeta = sdy, conv-bias gradient
+// = sum_r dx = (train ? 0 : gamma rstd sdy)
+__global__ void k_bn_bwd_finalize(const double *__restrict__ partial, int nparts, int C, int training,
+                                  const float *__restrict__ gamma, const float *__restrict__ rstd,
+                                  float *__restrict__ sums, float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                  float *__restrict__ dbias) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, sx = 0.0;
+    for (int k = 0; k < nparts; ++k) { s += partial[((size_t)k * 2 + 0) * C + c]; sx += partial[((size_t)k * 2 + 1) * C + c]; }
+    sums[c] = (float)s; sums[C + c] = (float)sx;
+    if (dgamma) dgamma[c] = (float)sx;
+    if (dbeta) dbeta[c] = (float)s;
+    if (dbias) dbias[c] = training ? 0.f : gamma[c] * rstd[c] * (float)s;
+}
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 r;
+    r.x = *reinterpret_cast<unsigned *>(&lo); r.y = *reinterpret_cast<unsigned *>(&hi);
+    return r;
+}
+// y bf16 = relu(bn(x))
+__global__ void __launch_bounds__(256)
+k_bn_relu(const float *__restrict__ x, const float *__restrict__ mu, const float *__restrict__ rstd,
+          const float *__restrict__ gamma, const float *__restrict__ beta, int64_t R, int C, bf16 *__restrict__ y) {
+    const int64_t nvec = R * C / 4;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)((4 * v) % C);
+        const float4 xv = __ldg(reinterpret_cast<const float4 *>(x) + v);
+        const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            o[j] = fmaxf((xa[j] - mu[c0 + j]) * rstd[c0 + j] * gamma[c0 + j] + beta[c0 + j], 0.f);
+        reinterpret_cast<uint2 *>(y)[v] = pack_bf16x4(o[0], o[1], o[2], o[3]);
+    }
+}
+// feat[b][c] = mean_v relu(bn(x[b*V + v][c]))   (BN + ReLU + AdaptiveAvgPool3d(1) of the last stage)
+__global__ void __launch_bounds__(256)
+k_bn_relu_pool(const float *__restrict__ x, const float *__restrict__ mu, const float *__restrict__ rstd,
+               const float *__restrict__ gamma, const float *__restrict__ beta, int64_t B, int V, int C,
+               float *__restrict__ feat) {
+    const int64_t total = B * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t b = i / C;
+        const float m = mu[c], sc = rstd[c] * gamma[c], be = beta[c];
+        float s = 0.f;
+        for (int v = 0; v < V; ++v) s += fmaxf((x[(b * V + v) * C + c] - m) * sc + be, 0.f);
+        feat[i] = s / (float)V;
+    }
+}
+__global__ void k_pool_bwd(const float *__restrict__ dfeat, int64_t B, int V, int C, float *__restrict__ dA) {
+    const int64_t total = B * V * C;
+    const float inv = 1.f / (float)V;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t b = i / ((int64_t)V * C);
+        dA[i] = dfeat[b * C + c] * inv;
+    }
+}
+// dx bf16 = gamma rstd (dy - sdy/R - xhat sdyx/R) in training, gamma rstd dy in eval; dy = [bn(x) > 0] dA
+__global__ void __launch_bounds__(256)
+k_bn_dx(const float *__restrict__ x, const float *__restrict__ dA, const float *__restrict__ mu,
+        const float *__restrict__ rstd, const float *__restrict__ gamma, const float *__restrict__ beta,
+        const float *__restrict__ sums, int64_t R, int C, int training, bf16 *__restrict__ dx) {
+    const int64_t nvec = R * C / 4;
+    const float invR = 1.f / (float)R;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)((4 * v) % C);
+        const float4 xv = __ldg(reinterpret_cast<const float4 *>(x) + v);
+        const float4 dv = __ldg(reinterpret_cast<const float4 *>(dA) + v);
+        const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j;
+            const float xh = (xa[j] - mu[c]) * rstd[c];
+            float d = (xh * gamma[c] + beta[c] > 0.f) ? da[j] : 0.f;
+            if (training) d = d - sums[c] * invR - xh * sums[C + c] * invR;
+            o[j] = d * gamma[c] * rstd[c];
+        }
+        reinterpret_cast<uint2 *>(dx)[v] = pack_bf16x4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+inline bool pow2_channels(int C) { return C >= 8 && C <= 256 && (C & (C - 1)) == 0; }
+constexpr int BN_PARTS_PER_SM = 4;
+inline int bn_parts(int64_t R, int C) {
+    int64_t p = (R * C / 4 + 4095) / 4096;
+    const int64_t cap = (int64_t)BN_PARTS_PER_SM * num_sms();
+    if (p > cap) p = cap;
+    if (p < 1) p = 1;
+    return (int)p;
+}
+
+}  // namespace
+}  // namespace b200surv
+
+using namespace b200surv;
+
+extern "C" {
+
+int32_t b200surv_ct_conv_first_fwd(const float *x, const float *w, const float *bias, int64_t B, int32_t D, int32_t H,
+                                   int32_t W, int32_t Cout, float *h, b200surv_stream_t stream) {
+    B200_REQUIRE(x && w && h, "null pointer");
+    B200_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1, "shape");
+    B200_REQUIRE(Cout >= 8 && Cout % 8 == 0 && Cout <= 256, "Cout must be a multiple of 8, <= 256");
+    const Grid3 g = make_grid(D, H, W);
+    const int64_t total = B * (int64_t)g.Do * g.Ho * g.Wo * (Cout / 8);
+    k_conv_first_fwd<<<blocks_for(total, 256, 16), 256, (size_t)28 * Cout * sizeof(float), as_stream(stream)>>>(
+        x, w, bias, B, g, Cout, h);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+size_t b200surv_ct_workspace_bytes(void) {
+    // the larger of: BN column-sum partials [parts][2][256] fp64; first-conv weight-gradient partials [ctas][256*27] fp32
+    const size_t bn = (size_t)BN_PARTS_PER_SM * num_sms() * 2 * 256 * sizeof(double) + 2 * 256 * sizeof(float);
+    const size_t wg = (size_t)2 * num_sms() * 256 * 27 * sizeof(float);
+    return align_up(bn > wg ? bn : wg, 256);
+}
+
+int32_t b200surv_ct_conv_first_wgrad(const float *x, const void *dx_bf16, int64_t B, int32_t D, int32_t H, int32_t W,
+                                     int32_t Cout, float *dw, void *workspace, size_t workspace_bytes,
+                                     b200surv_stream_t stream) {
+    B200_REQUIRE(x && dx_bf16 && dw && workspace, "null pointer");
+    B200_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1, "shape");
+    B200_REQUIRE(Cout >= 8 && 256 % Cout == 0, "Cout must divide 256");
+    if (workspace_bytes < b200surv_ct_workspace_bytes()) { set_error("ct: workspace too small"); return B200SURV_WORKSPACE_TOO_SMALL; }
+    const Grid3 g = make_grid(D, H, W);
+    const int64_t R = B * (int64_t)g.Do * g.Ho * g.Wo;
+    const int lanes = 256 / Cout;
+    int ctas = 2 * num_sms();
+    if ((int64_t)ctas * lanes > R) ctas = (int)((R + lanes - 1) / lanes);
+    float *partial = static_cast<float *>(workspace);
+    cudaStream_t st = as_stream(stream);
+    k_conv_first_wgrad<<<ctas, 256, (size_t)256 * 27 * sizeof(float), st>>>(x, static_cast<const bf16 *>(dx_bf16), B, g, Cout, partial);
+    k_sum_slices<<<(Cout * 27 + 255) / 256, 256, 0, st>>>(partial, ctas, (int64_t)Cout * 27, dw);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_ct_im2col(const void *a_bf16, int64_t Bc, int32_t D, int32_t H, int32_t W, int32_t C, void *col_bf16,
+                           b200surv_stream_t stream) {
+    B200_REQUIRE(a_bf16 && col_bf16, "null pointer");
+    B200_REQUIRE(Bc >= 1 && D >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "shape (C multiple of 8)");
+    const Grid3 g = make_grid(D, H, W);
+    const int64_t total = Bc * (int64_t)g.Do * g.Ho * g.Wo * 27 * (C / 8);
+    k_im2col<<<blocks_for(total, 256 * 4, 16), 256, 0, as_stream(stream)>>>(static_cast<const bf16 *>(a_bf16), Bc, g, C,
+                                                                        static_cast<bf16 *>(col_bf16));
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_ct_col2im(const void *dcol_bf16, int64_t Bc, int32_t D, int32_t H, int32_t W, int32_t C, float *da,
+                           b200surv_stream_t stream) {
+    B200_REQUIRE(dcol_bf16 && da, "null pointer");
+    B200_REQUIRE(Bc >= 1 && D >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "shape (C multiple of 8)");
+    const Grid3 g = make_grid(D, H, W);
+    const int64_t total = Bc * (int64_t)D * H * W * (C / 8);
+    k_col2im<<<blocks_for(total, 256 * 2, 16), 256, 0, as_stream(stream)>>>(static_cast<const bf16 *>(dcol_bf16), Bc, g, C, da);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_ct_weight_pack(const float *w, int32_t Cout, int32_t Cin, void *wr_bf16, b200surv_stream_t stream) {
+    B200_REQUIRE(w && wr_bf16 && Cout >= 1 && Cin >= 1, "arguments");
+    k_weight_pack<<<(Cout * Cin * 27 + 255) / 256, 256, 0, as_stream(stream)>>>(w, Cout, Cin, static_cast<bf16 *>(wr_bf16));
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_ct_weight_unpack(const float *dwr_slices, int32_t slices, int32_t Cout, int32_t Cin, float *dw,
+                                  b200surv_stream_t stream) {
+    B200_REQUIRE(dwr_slices && dw && slices >= 1 && Cout >= 1 && Cin >= 1, "arguments");
+    k_weight_unpack<<<(Cout * Cin * 27 + 255) / 256, 256, 0, as_stream(stream)>>>(dwr_slices, slices, Cout, Cin, dw);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_ct_bn_stats(const float *x, int64_t R, int32_t C, int32_t training, float *run_mean, float *run_var,
+                             float *mu, float *rstd, void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
+    B200_REQUIRE(x && mu && rstd && workspace, "null pointer");
+    B200_REQUIRE(R >= 1 && pow2_channels(C), "C must be a power of two in [8, 256]");
+    B200_REQUIRE(training || (run_mean && run_var), "eval mode needs the running statistics");
+    if (workspace_bytes < b200surv_ct_workspace_bytes()) { set_error("ct: workspace too small"); return B200SURV_WORKSPACE_TOO_SMALL; }
+    cudaStream_t st = as_stream(stream);
+    double *partial = static_cast<double *>(workspace);
+    const int parts = bn_parts(R, C);
+    if (training)
+        k_bn_colsums<0><<<parts, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, nullptr, R, C, partial);
+    k_bn_finalize<<<1, 256, 0, st>>>(partial, parts, R, C, training, run_mean, run_var, mu, rstd);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_ct_bn_relu(const float *x, const float *mu, const float *rstd, const float *gamma, const float *beta,
+                            int64_t R, int32_t C, void *y_bf16, b200surv_stream_t stream) {
+    B200_REQUIRE(x && mu && rstd && gamma && beta && y_bf16, "null pointer");
+    B200_REQUIRE(R >= 1 && pow2_channels(C), "C must be a power of two in [8, 256]");
+    k_bn_relu<<<blocks_for(R * C / 4, 256 * 4, 16), 256, 0, as_stream(stream)>>>(x, mu, rstd, gamma, beta, R, C,
+                                                                             static_cast<bf16 *>(y_bf16));
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_ct_bn_relu_pool(const float *x, const float *mu, const float *rstd, const float *gamma,
+                                 const float *beta, int64_t B, int32_t V, int32_t C, float *feat,
+                                 b200surv_stream_t stream) {
+    B200_REQUIRE(x && mu && rstd && gamma && beta && feat, "null pointer");
+    B200_REQUIRE(B >= 1 && V >= 1 && C >= 1, "shape");
+    k_bn_relu_pool<<<blocks_for(B * C, 256, 16), 256, 0, as_stream(stream)>>>(x, mu, rstd, gamma, beta, B, V, C, feat);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_ct_pool_bwd(const float *dfeat, int64_t B, int32_t V, int32_t C, float *dA, b200surv_stream_t stream) {
+    B200_REQUIRE(dfeat && dA && B >= 1 && V >= 1 && C >= 1, "arguments");
+    k_pool_bwd<<<blocks_for(B * V * C, 256 * 4, 16), 256, 0, as_stream(stream)>>>(dfeat, B, V, C, dA);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_ct_bn_bwd(const float *x, const float *dA, const float *mu, const float *rstd, const float *gamma,
+                           const float *beta, int64_t R, int32_t C, int32_t training, void *dx_bf16, float *dgamma,
+                           float *dbeta, float *dbias, void *workspace, size_t workspace_bytes,
+                           b200surv_stream_t stream) {
+    B200_REQUIRE(x && dA && mu && rstd && gamma && beta && dx_bf16 && workspace, "null pointer");
+    B200_REQUIRE(R >= 1 && pow2_channels(C), "C must be a power of two in [8, 256]");
+    if (workspace_bytes < b200surv_ct_workspace_bytes()) { set_error("ct: workspace too small"); return B200SURV_WORKSPACE_TOO_SMALL; }
+    cudaStream_t st = as_stream(stream);
+    double *partial = static_cast<double *>(workspace);
+    const int parts = bn_parts(R, C);
+    // the 2 C fp32 column sums live behind the partials (b200surv_ct_workspace_bytes() reserves them)
+    float *sums = reinterpret_cast<float *>(partial + (size_t)parts * 2 * C);
+    B200_REQUIRE((size_t)parts * 2 * C * sizeof(double) + 2 * C * sizeof(float) <= workspace_bytes, "workspace layout");
+    k_bn_colsums<1><<<parts, 256, 0, st>>>(x, dA, mu, rstd, gamma, beta, R, C, partial);
+    k_bn_bwd_finalize<<<1, 256, 0, st>>>(partial, parts, C, training, gamma, rstd, sums, dgamma, dbeta, dbias);
+    k_bn_dx<<<blocks_for(R * C / 4, 256 * 4, 16), 256, 0, st>>>(x, dA, mu, rstd, gamma, beta, sums, R, C, training,
+                                                               static_cast<bf16 *>(dx_bf16));
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+"""CT encoder against the reference's nn.Sequential CNN branch,
+scripts/training/partial_modality_training.py:179-190, run by PyTorch/cuDNN in fp32 on the same device."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from multimodal_survival_prediction_b200.ctenc import CTEncoderCNN
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL = 2e-2      # bf16 GEMM operands, fp32 accumulation (BASELINE.json: 2e-2 on the bf16 path)
+GRAD_TOL = 3e-2     # per-tensor relative Frobenius error against the reference with bf16-rounded conv operands
+GRAD_TOL_FP32 = 0.15  # ... and against the full-precision reference: in training mode BatchNorm's backward projects
+#                       out most of dy, which amplifies the bf16 operand rounding to 5-9 % per tensor -- the matched
+#                       reference shows the same 5-9 % against fp32 (scratch/ctenc_diag.py), eval mode stays < 1 %
+
+
+def _reference_cnn():
+    return nn.Sequential(                                   # partial_modality_training.py:179-190
+        nn.Conv3d(1, 32, 3, stride=2, padding=1), nn.BatchNorm3d(32), nn.ReLU(),
+        nn.Conv3d(32, 64, 3, stride=2, padding=1), nn.BatchNorm3d(64), nn.ReLU(),
+        nn.Conv3d(64, 128, 3, stride=2, padding=1), nn.BatchNorm3d(128), nn.ReLU(),
+        nn.AdaptiveAvgPool3d(1),
+    )
+
+
+class _RoundBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _matched(seq, ct):
+    """The reference CNN with the operands of convolutions 2 and 3 rounded to bf16 (straight-through): the arithmetic
+    of the tensor-core path, evaluated by PyTorch."""
+    x = ct
+    for i in (0, 3, 6):
+        conv, bn = seq[i], seq[i + 1]
+        x = conv(x) if i == 0 else F.conv3d(_RoundBf16.apply(x), _RoundBf16.apply(conv.weight), conv.bias, stride=2, padding=1)
+        x = F.relu(bn(x))
+    return seq[9](x)
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("shape,training", [((3, 1, 16, 16, 8), True), ((2, 1, 15, 13, 9), True), ((4, 1, 64, 64, 32), True),
+                                            ((4, 1, 64, 64, 32), False), ((40, 1, 32, 32, 16), True)])
+def test_ct_encoder_matches_torch_cnn(shape, training):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(shape[0] * 1000 + shape[2])
+    ref = _reference_cnn().to(dev)
+    with torch.no_grad():                                   # non-trivial BatchNorm parameters and running statistics
+        for m in ref:
+            if isinstance(m, nn.BatchNorm3d):
+                m.weight.uniform_(0.5, 1.5); m.bias.uniform_(-0.3, 0.3)
+                m.running_mean.uniform_(-0.2, 0.2); m.running_var.uniform_(0.5, 1.5)
+    refm = copy.deepcopy(ref)
+    ours = CTEncoderCNN().to(dev)
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    ours.load_state_dict(copy.deepcopy(ref.state_dict()))   # a reference .pth loads as is
+    ref.train(training); ours.train(training); refm.train(training)
+    ct = torch.rand(shape, device=dev)
+    ct[0].zero_()                                           # a patient without imaging: zero volume (:89)
+    w = torch.randn(shape[0], 128, 1, 1, 1, device=dev)
+    y_ref = ref(ct); (y_ref * w).sum().backward()
+    (_matched(refm, ct) * w).sum().backward()
+    y = ours(ct); (y * w).sum().backward()
+    assert y.shape == y_ref.shape and y.dtype == y_ref.dtype
+    assert float((y - y_ref).abs().max()) <= OUT_TOL * max(1.0, float(y_ref.abs().max())), "features"
+    for (k, a), (_, b) in zip(ours.state_dict().items(), ref.state_dict().items()):
+        if "running" in k:
+            assert _rel(a, b) <= 1e-3, k
+        if "num_batches" in k:
+            assert int(a) == int(b), k
+    live = [k for k, pb in ref.named_parameters() if not (training and k in ("0.bias", "3.bias", "6.bias"))]
+    ga, gf, gm = (dict((k, p.grad) for k, p in m.named_parameters()) for m in (ours, ref, refm))
+    errs = {k: (_rel(ga[k], gm[k]), _rel(ga[k], gf[k])) for k in live}
+    assert max(e[0] for e in errs.values()) <= GRAD_TOL and max(e[1] for e in errs.values()) <= GRAD_TOL_FP32, errs
+    if training:
+        for i in (0, 3, 6):                                 # BatchNorm cancels the bias: exactly zero here
+            assert float(ours[i].bias.grad.abs().max()) == 0.0
+
+
+def test_ct_encoder_rejects_cpu_and_bad_shapes():
+    enc = CTEncoderCNN()
+    from multimodal_survival_prediction_b200 import B200SurvError
+    with pytest.raises(B200SurvError):
+        enc(torch.zeros(2, 1, 8, 8, 8))
+    with pytest.raises(ValueError):
+        enc.cuda()(torch.zeros(2, 2, 8, 8, 8, device="cuda"))
