@@ -7,8 +7,9 @@ scripts/training/final_multimodal.py:59-150: same constructor arguments, forward
 types and ``state_dict`` keys/shapes (so ``.pth`` files interchange).  The sub-modules exist as
 parameter containers; everything from the 128-d CT feature onward runs in libb200surv.so
 (csrc/head.cu + csrc/gemm_tc.cu: tcgen05/TMEM GEMMs, fused BatchNorm/dropout/gate kernels) through
-``b200surv_head_fwd`` / ``b200surv_head_bwd``.  The CT encoder stays a PyTorch/cuDNN sub-module
-(outside the head).  There is no CPU path.
+``b200surv_head_fwd`` / ``b200surv_head_bwd``.  The CT encoder (the reference's CNN branch) is
+``ctenc.CTEncoderCNN`` on the ``b200surv_ct_*`` primitives; the MONAI DenseNet121 branch is out of scope.  There is no
+CPU path.
 """
 from __future__ import annotations
 
@@ -155,13 +156,10 @@ def fused_head(module, ct_feat, rna, clinical, mask=None, want_masks=False, seed
 
 
 def _ct_cnn():
-    # the reference's non-MONAI CT encoder (partial_modality_training.py:179-190): a PyTorch/cuDNN sub-module
-    return nn.Sequential(
-        nn.Conv3d(1, 32, 3, stride=2, padding=1), nn.BatchNorm3d(32), nn.ReLU(),
-        nn.Conv3d(32, 64, 3, stride=2, padding=1), nn.BatchNorm3d(64), nn.ReLU(),
-        nn.Conv3d(64, 128, 3, stride=2, padding=1), nn.BatchNorm3d(128), nn.ReLU(),
-        nn.AdaptiveAvgPool3d(1),
-    )
+    # the reference's non-MONAI CT encoder (partial_modality_training.py:179-190) on the b200surv_ct_* primitives:
+    # same sub-modules and state_dict keys as the reference's nn.Sequential (ctenc.py)
+    from .ctenc import CTEncoderCNN
+    return CTEncoderCNN()
 
 
 class _HeadBase(nn.Module):

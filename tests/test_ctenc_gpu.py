@@ -99,3 +99,32 @@ def test_ct_encoder_rejects_cpu_and_bad_shapes():
         enc(torch.zeros(2, 1, 8, 8, 8))
     with pytest.raises(ValueError):
         enc.cuda()(torch.zeros(2, 2, 8, 8, 8, device="cuda"))
+
+
+def test_full_model_step_with_ct_volumes():
+    """PartialModalityNet.forward(ct, rna, clinical, mask) (partial_modality_training.py:234-277) with CT volumes:
+    the gradient of a Cox loss reaches the CT encoder through the fused head; reference = the same head fed by the
+    torch CNN (bf16-matched) with the same weights."""
+    from multimodal_survival_prediction_b200 import head as ghead, neg_partial_log_likelihood, synth
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(1)
+    B = 8
+    m = ghead.PartialModalityNet().to(dev).train()
+    m.rna_encoder[3].p = 0.0; m.fusion[3].p = 0.0            # dropout off: two passes must see the same network
+    cnn = _reference_cnn().to(dev).train()
+    cnn.load_state_dict(copy.deepcopy(m.ct_encoder.state_dict()))
+    before = copy.deepcopy(m.state_dict())
+    _, rna, clin, mask = [t.to(dev) for t in synth.modality_batch(B, seed=3)]
+    ct = torch.rand(B, 1, 64, 64, 32, device=dev) * mask[:, 0].view(B, 1, 1, 1, 1)      # no imaging -> zero volume
+    time = torch.arange(1, B + 1, device=dev).float()
+    event = torch.tensor([1, 0, 1, 1, 0, 1, 0, 1], device=dev).bool()
+    hz, gate = m(ct, rna, clin, mask)
+    neg_partial_log_likelihood(hz, event, time).backward()
+    g_ours = {k: p.grad.clone() for k, p in m.ct_encoder.named_parameters()}
+    m.load_state_dict(before); m.zero_grad()
+    hz2, _ = m.forward_features(_matched(cnn, ct).view(B, -1), rna, clin, mask)
+    neg_partial_log_likelihood(hz2, event, time).backward()
+    assert float((hz - hz2).abs().max()) <= OUT_TOL * max(1.0, float(hz2.abs().max()))
+    errs = {k: _rel(g_ours[k], p.grad) for k, p in cnn.named_parameters() if k not in ("0.bias", "3.bias", "6.bias")}
+    assert all(float(g.abs().max()) > 0 for k, g in g_ours.items() if k in errs)
+    assert max(errs.values()) <= 2 * GRAD_TOL, errs           # two bf16 heads in front of the comparison
