@@ -221,6 +221,13 @@ int32_t b200surv_gemm_bf16(const void *a, int64_t lda, int32_t a_mn, const void 
                            void *c_bf16, int64_t ldc_bf16, const float *bias, int32_t relu,
                            b200surv_stream_t stream);
 
+/* Split-K variant for outputs with few tiles and a long K (weight gradients): writes
+ * b200surv_gemm_splitk_slices(M, N, K) (1..32) fp32 slices [M][ldc] back to back into `slices`; the caller sums them
+ * in slice order (deterministic).  Same operand conventions as b200surv_gemm_bf16. */
+int32_t b200surv_gemm_splitk_slices(int32_t M, int32_t N, int32_t K);
+int32_t b200surv_gemm_bf16_splitk(const void *a, int64_t lda, int32_t a_mn, const void *b, int64_t ldb, int32_t b_mn,
+                                  int32_t M, int32_t N, int32_t K, float *slices, int64_t ldc, b200surv_stream_t stream);
+
 /* ---- fusion head: forward / backward -------------------------------------------------------- */
 /* Parameters of the head, fp32 row-major [out][in], one pointer per reference state_dict entry
  * (PartialModalityNet: partial_modality_training.py:193-232; MultiModalSurvivalNet:

@@ -61,6 +61,9 @@ SIGNATURES = {
                                                c_int32, c_int32, ctypes.c_uint32, c_void_p]),
     "b200surv_gemm_bf16": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                      c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
+    "b200surv_gemm_splitk_slices": (c_int32, [c_int32, c_int32, c_int32]),
+    "b200surv_gemm_bf16_splitk": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                            c_void_p, c_int64, c_void_p]),
     "b200surv_head_saved_bytes": (c_size_t, [c_int64, c_int32]),
     "b200surv_head_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "b200surv_head_fwd": (c_int32, [c_void_p] * 5 + [c_int64, c_int32, c_int32, c_float, ctypes.c_uint64] +

@@ -84,58 +84,84 @@ k_conv_first_fwd(const float *__restrict__ x, const float *__restrict__ w, const
     }
 }
 
-// weight gradient of the first convolution: dw[c][tap] = sum_r dx[r][c] * patch_r[tap].  Thread = (row lane, channel);
-// 27 accumulators per thread; the patch values are warp-uniform (broadcast loads).  partial[cta][Cout][27] (fp32) is
-// summed in CTA order by k_conv_first_wgrad_final.
-__global__ void __launch_bounds__(256)
+// weight gradient of the first convolution: dw[c][tap] = sum_r dx[r][c] * patch_r[tap].  Thread = (row lane, channel):
+// a warp owns a contiguous run of output rows (voxel coordinates advance incrementally: no division in the loop) and
+// its lanes the channels, so the 27 patch values are warp-uniform broadcast loads; 27 accumulators per thread.
+// partial[cta][Cout][27] (fp32) is summed in CTA order by k_sum_slices.
+constexpr int WG_THREADS = 1024;
+__global__ void __launch_bounds__(WG_THREADS, 1)
 k_conv_first_wgrad(const float *__restrict__ x, const bf16 *__restrict__ dx, int64_t B, Grid3 g, int Cout,
                    float *__restrict__ partial) {
-    extern __shared__ float red[];          // [256][27]
-    const int c = threadIdx.x % Cout, lane_r = threadIdx.x / Cout, lanes = blockDim.x / Cout;
+    __shared__ float red[WG_THREADS * 9];
+    const int c = threadIdx.x % Cout, lane_r = threadIdx.x / Cout, lanes = WG_THREADS / Cout;
     const int64_t vox = (int64_t)g.Do * g.Ho * g.Wo, R = B * vox;
-    const int64_t per = (R + gridDim.x - 1) / gridDim.x;
-    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(R, r0 + per);
+    const int64_t per = (R + (int64_t)gridDim.x * lanes - 1) / ((int64_t)gridDim.x * lanes);
+    const int64_t r0 = ((int64_t)blockIdx.x * lanes + lane_r) * per, r1 = min(R, r0 + per);
     float acc[27];
 #pragma unroll
     for (int t = 0; t < 27; ++t) acc[t] = 0.f;
-    for (int64_t r = r0 + lane_r; r < r1; r += lanes) {
-        const float d = __bfloat162float(dx[r * Cout + c]);
-        const int64_t b = r / vox;
-        int v = (int)(r - b * vox);
-        const int xo = v % g.Wo; v /= g.Wo;
-        const int yo = v % g.Ho, zo = v / g.Ho;
-        const float *xb = x + b * (int64_t)g.D * g.H * g.W;
+    if (r0 < r1) {
+        int64_t b = r0 / vox;
+        int v = (int)(r0 - b * vox);
+        int xo = v % g.Wo; v /= g.Wo;
+        int yo = v % g.Ho, zo = v / g.Ho;
+        const int64_t plane = (int64_t)g.H * g.W;
+        const float *xb = x + b * g.D * plane;
+        for (int64_t r = r0; r < r1; ++r) {
+            const float d = __bfloat162float(dx[r * Cout + c]);
+            const float *x0 = xb + (int64_t)(2 * zo - 1) * plane + (int64_t)(2 * yo - 1) * g.W + (2 * xo - 1);
 #pragma unroll
-        for (int kz = 0; kz < 3; ++kz) {
-            const int z = 2 * zo - 1 + kz;
+            for (int kz = 0; kz < 3; ++kz) {
+                const bool inz = (unsigned)(2 * zo - 1 + kz) < (unsigned)g.D;
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int y = 2 * yo - 1 + ky;
+                for (int ky = 0; ky < 3; ++ky) {
+                    const bool iny = inz && (unsigned)(2 * yo - 1 + ky) < (unsigned)g.H;
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int xx = 2 * xo - 1 + kx;
-                    const bool in = z >= 0 && z < g.D && y >= 0 && y < g.H && xx >= 0 && xx < g.W;
-                    const float xv = in ? __ldg(xb + ((int64_t)z * g.H + y) * g.W + xx) : 0.f;
-                    acc[kz * 9 + ky * 3 + kx] += d * xv;
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const bool in = iny && (unsigned)(2 * xo - 1 + kx) < (unsigned)g.W;
+                        const float xv = in ? __ldg(x0 + kz * plane + ky * g.W + kx) : 0.f;
+                        acc[kz * 9 + ky * 3 + kx] += d * xv;
+                    }
+                }
+            }
+            if (++xo == g.Wo) {
+                xo = 0;
+                if (++yo == g.Ho) {
+                    yo = 0;
+                    if (++zo == g.Do) { zo = 0; xb += g.D * plane; }
                 }
             }
         }
     }
 #pragma unroll
-    for (int t = 0; t < 27; ++t) red[threadIdx.x * 27 + t] = acc[t];
-    __syncthreads();
-    for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) {
-        const int cc = i / 27, t = i % 27;
-        float s = 0.f;
-        for (int l = 0; l < lanes; ++l) s += red[(l * Cout + cc) * 27 + t];
-        partial[(size_t)blockIdx.x * Cout * 27 + i] = s;
+    for (int round = 0; round < 3; ++round) {       // nine taps at a time through 36 KB of shared memory
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 9; ++t) red[threadIdx.x * 9 + t] = acc[round * 9 + t];
+        __syncthreads();
+        for (int i = threadIdx.x; i < Cout * 9; i += WG_THREADS) {
+            const int cc = i / 9, t = i % 9;
+            float sum = 0.f;
+            for (int l = 0; l < lanes; ++l) sum += red[(l * Cout + cc) * 9 + t];
+            partial[(size_t)blockIdx.x * Cout * 27 + cc * 27 + round * 9 + t] = sum;
+        }
     }
 }
-__global__ void k_sum_slices(const float *__restrict__ part, int slices, int64_t elems, float *__restrict__ out) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (int64_t)gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (int k = 0; k < slices; ++k) s += part[(size_t)k * elems + i];
-        out[i] = (float)s;
+// out[i] = sum over the slices, in a fixed order: 32 elements x 8 slice lanes per CTA
+__global__ void __launch_bounds__(256)
+k_sum_slices(const float *__restrict__ part, int slices, int64_t elems, float *__restrict__ out) {
+    __shared__ double sh[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + tx;
+    double sum = 0.0;
+    if (i < elems)
+        for (int k = ty; k < slices; k += 8) sum += part[(size_t)k * elems + i];
+    sh[ty][tx] = sum;
+    __syncthreads();
+    if (ty == 0 && i < elems) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) sum += sh[k][tx];
+        out[i] = (float)sum;
     }
 }
 
@@ -275,14 +301,26 @@ k_bn_colsums(const float *__restrict__ x, const float *__restrict__ dA, const fl
         partial[((size_t)blockIdx.x * 2 + 1) * C + t] = a1;
     }
 }
-__global__ void k_bn_finalize(const double *__restrict__ partial, int nparts, int64_t R, int C, int training,
-                              float *__restrict__ run_mean, float *__restrict__ run_var, float *__restrict__ mu,
-                              float *__restrict__ rstd) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one WARP per channel, lanes over the partials in a fixed order (deterministic); grid = C / 8 blocks of 256 threads
+__device__ __forceinline__ void part_sums(const double *__restrict__ partial, int nparts, int C, int c, int lane,
+                                          double &s0, double &s1) {
+    s0 = 0.0; s1 = 0.0;
+    for (int k = lane; k < nparts; k += 32) { s0 += partial[((size_t)k * 2 + 0) * C + c]; s1 += partial[((size_t)k * 2 + 1) * C + c]; }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+}
+__global__ void __launch_bounds__(256)
+k_bn_finalize(const double *__restrict__ partial, int nparts, int64_t R, int C, int training,
+              float *__restrict__ run_mean, float *__restrict__ run_var, float *__restrict__ mu,
+              float *__restrict__ rstd) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
-    if (!training) { mu[c] = run_mean[c]; rstd[c] = rsqrtf(run_var[c] + BN_EPS); return; }
-    double s = 0.0, ss = 0.0;
-    for (int k = 0; k < nparts; ++k) { s += partial[((size_t)k * 2 + 0) * C + c]; ss += partial[((size_t)k * 2 + 1) * C + c]; }
+    if (!training) {
+        if (lane == 0) { mu[c] = run_mean[c]; rstd[c] = rsqrtf(run_var[c] + BN_EPS); }
+        return;
+    }
+    double s, ss;
+    part_sums(partial, nparts, C, c, lane, s, ss);
+    if (lane != 0) return;
     const double mean = s / (double)R;
     double var = ss / (double)R - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -296,14 +334,15 @@ __global__ void k_bn_finalize(const double *__restrict__ partial, int nparts, in
 }
 // sums of the backward pass: sdy, sdyx (kept for k_bn_dx), dgamma = sdyx, dbeta = sdy, conv-bias gradient
 // = sum_r dx = (train ? 0 : gamma rstd sdy)
-__global__ void k_bn_bwd_finalize(const double *__restrict__ partial, int nparts, int C, int training,
-                                  const float *__restrict__ gamma, const float *__restrict__ rstd,
-                                  float *__restrict__ sums, float *__restrict__ dgamma, float *__restrict__ dbeta,
-                                  float *__restrict__ dbias) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+k_bn_bwd_finalize(const double *__restrict__ partial, int nparts, int C, int training, const float *__restrict__ gamma,
+                  const float *__restrict__ rstd, float *__restrict__ sums, float *__restrict__ dgamma,
+                  float *__restrict__ dbeta, float *__restrict__ dbias) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
-    double s = 0.0, sx = 0.0;
-    for (int k = 0; k < nparts; ++k) { s += partial[((size_t)k * 2 + 0) * C + c]; sx += partial[((size_t)k * 2 + 1) * C + c]; }
+    double s, sx;
+    part_sums(partial, nparts, C, c, lane, s, sx);
+    if (lane != 0) return;
     sums[c] = (float)s; sums[C + c] = (float)sx;
     if (dgamma) dgamma[c] = (float)sx;
     if (dbeta) dbeta[c] = (float)s;
@@ -422,17 +461,17 @@ int32_t b200surv_ct_conv_first_wgrad(const float *x, const void *dx_bf16, int64_
                                      b200surv_stream_t stream) {
     B200_REQUIRE(x && dx_bf16 && dw && workspace, "null pointer");
     B200_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1, "shape");
-    B200_REQUIRE(Cout >= 8 && 256 % Cout == 0, "Cout must divide 256");
+    B200_REQUIRE(Cout >= 8 && Cout <= 256 && WG_THREADS % Cout == 0, "Cout must be a power of two in [8, 256]");
     if (workspace_bytes < b200surv_ct_workspace_bytes()) { set_error("ct: workspace too small"); return B200SURV_WORKSPACE_TOO_SMALL; }
     const Grid3 g = make_grid(D, H, W);
     const int64_t R = B * (int64_t)g.Do * g.Ho * g.Wo;
-    const int lanes = 256 / Cout;
-    int ctas = 2 * num_sms();
+    const int lanes = WG_THREADS / Cout;
+    int ctas = num_sms();       // 64 registers x 1024 threads: one CTA per SM
     if ((int64_t)ctas * lanes > R) ctas = (int)((R + lanes - 1) / lanes);
     float *partial = static_cast<float *>(workspace);
     cudaStream_t st = as_stream(stream);
-    k_conv_first_wgrad<<<ctas, 256, (size_t)256 * 27 * sizeof(float), st>>>(x, static_cast<const bf16 *>(dx_bf16), B, g, Cout, partial);
-    k_sum_slices<<<(Cout * 27 + 255) / 256, 256, 0, st>>>(partial, ctas, (int64_t)Cout * 27, dw);
+    k_conv_first_wgrad<<<ctas, WG_THREADS, 0, st>>>(x, static_cast<const bf16 *>(dx_bf16), B, g, Cout, partial);
+    k_sum_slices<<<(Cout * 27 + 31) / 32, 256, 0, st>>>(partial, ctas, (int64_t)Cout * 27, dw);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -486,7 +525,7 @@ int32_t b200surv_ct_bn_stats(const float *x, int64_t R, int32_t C, int32_t train
     const int parts = bn_parts(R, C);
     if (training)
         k_bn_colsums<0><<<parts, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, nullptr, R, C, partial);
-    k_bn_finalize<<<1, 256, 0, st>>>(partial, parts, R, C, training, run_mean, run_var, mu, rstd);
+    k_bn_finalize<<<(C + 7) / 8, 256, 0, st>>>(partial, parts, R, C, training, run_mean, run_var, mu, rstd);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -532,7 +571,7 @@ int32_t b200surv_ct_bn_bwd(const float *x, const float *dA, const float *mu, con
     float *sums = reinterpret_cast<float *>(partial + (size_t)parts * 2 * C);
     B200_REQUIRE((size_t)parts * 2 * C * sizeof(double) + 2 * C * sizeof(float) <= workspace_bytes, "workspace layout");
     k_bn_colsums<1><<<parts, 256, 0, st>>>(x, dA, mu, rstd, gamma, beta, R, C, partial);
-    k_bn_bwd_finalize<<<1, 256, 0, st>>>(partial, parts, C, training, gamma, rstd, sums, dgamma, dbeta, dbias);
+    k_bn_bwd_finalize<<<(C + 7) / 8, 256, 0, st>>>(partial, parts, C, training, gamma, rstd, sums, dgamma, dbeta, dbias);
     k_bn_dx<<<blocks_for(R * C / 4, 256 * 4, 16), 256, 0, st>>>(x, dA, mu, rstd, gamma, beta, sums, R, C, training,
                                                                static_cast<bf16 *>(dx_bf16));
     B200_CHECK_CUDA(cudaGetLastError());

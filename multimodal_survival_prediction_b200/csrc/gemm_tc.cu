@@ -360,3 +360,16 @@ extern "C" int32_t b200surv_gemm_bf16(const void *a, int64_t lda, int32_t a_mn, 
     return b200surv::gemm_bf16(a, lda, a_mn, b, ldb, b_mn, M, N, K, c, ldc, c_bf16, ldc_bf16, bias, relu, nullptr,
                                b200surv::as_stream(stream));
 }
+
+// Split-K variant for outputs with few tiles and a long K (weight gradients): writes b200surv_gemm_splitk_slices(M, N, K)
+// fp32 slices [M][ldc] back to back into `slices`; the caller sums them in slice order (deterministic).
+extern "C" int32_t b200surv_gemm_splitk_slices(int32_t M, int32_t N, int32_t K) {
+    if (M < 1 || N < 1 || K < 1) return 0;
+    return b200surv::splitk_slices(M, N, K, nullptr);
+}
+extern "C" int32_t b200surv_gemm_bf16_splitk(const void *a, int64_t lda, int32_t a_mn, const void *b, int64_t ldb,
+                                             int32_t b_mn, int32_t M, int32_t N, int32_t K, float *slices, int64_t ldc,
+                                             b200surv_stream_t stream) {
+    return b200surv::gemm_bf16(a, lda, a_mn, b, ldb, b_mn, M, N, K, slices, ldc, nullptr, 0, nullptr, 0, slices,
+                               b200surv::as_stream(stream));
+}

@@ -132,7 +132,10 @@ class _CTEncFn(torch.autograd.Function):
                     a_prev, wr = acts[s - 1], wrs[s]
                     col = torch.empty(sg.chunk * sg.vox, sg.K, dtype=torch.bfloat16, device=dev)
                     dcol = torch.empty(sg.chunk * sg.vox, sg.K, dtype=torch.bfloat16, device=dev)
-                    dwr = torch.empty(sg.nchunks, sg.Cout, sg.K, dtype=torch.float32, device=dev)
+                    nsl = [lib.b200surv_gemm_splitk_slices(sg.Cout, sg.K, min(sg.chunk, B - b0) * sg.vox)
+                           for b0 in range(0, B, sg.chunk)]        # split-K slices every chunk's weight gradient writes
+                    dwr = torch.empty(sum(nsl), sg.Cout, sg.K, dtype=torch.float32, device=dev)
+                    sl0 = 0
                     dA_prev = torch.empty(B * sg.vin, sg.Cin, dtype=torch.float32, device=dev)
                     for k, b0 in enumerate(range(0, B, sg.chunk)):
                         bc = min(sg.chunk, B - b0)
@@ -141,12 +144,14 @@ class _CTEncFn(torch.autograd.Function):
                         L.check(lib.b200surv_ct_im2col(L.ptr(a_prev[b0 * sg.vin:]), bc, sg.D, sg.H, sg.W, sg.Cin, L.ptr(col), st),
                                 "b200surv_ct_im2col")
                         # dW (tap-major) = dx^T col : both operands read as stored (MN-major)
-                        _gemm(lib, dev, dxc, sg.Cout, 1, col, sg.K, 1, sg.Cout, sg.K, rows, c=dwr[k], ldc=sg.K)
+                        L.check(lib.b200surv_gemm_bf16_splitk(L.ptr(dxc), sg.Cout, 1, L.ptr(col), sg.K, 1, sg.Cout, sg.K, rows,
+                                                              L.ptr(dwr[sl0:]), sg.K, st), "b200surv_gemm_bf16_splitk")
+                        sl0 += nsl[k]
                         # dcol = dx W, then every input voxel gathers its taps
                         _gemm(lib, dev, dxc, sg.Cout, 0, wr, sg.K, 1, rows, sg.K, sg.Cout, c_bf16=dcol, ldc_bf16=sg.K)
                         L.check(lib.b200surv_ct_col2im(L.ptr(dcol), bc, sg.D, sg.H, sg.W, sg.Cin, L.ptr(dA_prev[b0 * sg.vin:]), st),
                                 "b200surv_ct_col2im")
-                    L.check(lib.b200surv_ct_weight_unpack(L.ptr(dwr), sg.nchunks, sg.Cout, sg.Cin, L.ptr(dw), st),
+                    L.check(lib.b200surv_ct_weight_unpack(L.ptr(dwr), sum(nsl), sg.Cout, sg.Cin, L.ptr(dw), st),
                             "b200surv_ct_weight_unpack")
                     dA = dA_prev
                 for j, g in enumerate((dw, dbias, dgamma, dbeta)):
