@@ -324,7 +324,7 @@ int32_t b200surv_clip_adam_step(float *const *params, const float *const *grads,
  *   im2col / col2im : a bf16 [Bc*D*H*W][C] -> col bf16 [Bc*Do*Ho*Wo][27*C] (column = tap*C + c; the conv is then
  *                     b200surv_gemm_bf16(col, W_packed)); dcol bf16 -> da fp32 [Bc*D*H*W][C] by gathering (no atomics)
  *   weight_pack     : w fp32 (Cout,Cin,3,3,3) -> bf16 [Cout][27*Cin] tap-major; weight_unpack: the sum of `slices`
- *                     fp32 [Cout][27*Cin] gradient slices -> dw fp32 (Cout,Cin,3,3,3)
+ *                     fp32 [Cout][27*Cin] gradient slices -> dw fp32 (Cout,Cin,3,3,3), added to dw when accumulate != 0
  *   bn_stats        : training: mu, rstd of the columns of x [R][C] (biased variance, eps 1e-5) and running <- 0.9
  *                     running + 0.1 (mu, unbiased variance) like nn.BatchNorm3d; eval: mu, rstd from the running stats
  *   bn_relu         : y bf16 = relu((x - mu) rstd gamma + beta);   bn_relu_pool: feat fp32 [B][C] = mean over the V
@@ -344,8 +344,8 @@ int32_t b200surv_ct_im2col(const void *a_bf16, int64_t Bc, int32_t D, int32_t H,
 int32_t b200surv_ct_col2im(const void *dcol_bf16, int64_t Bc, int32_t D, int32_t H, int32_t W, int32_t C, float *da,
                            b200surv_stream_t stream);
 int32_t b200surv_ct_weight_pack(const float *w, int32_t Cout, int32_t Cin, void *wr_bf16, b200surv_stream_t stream);
-int32_t b200surv_ct_weight_unpack(const float *dwr_slices, int32_t slices, int32_t Cout, int32_t Cin, float *dw,
-                                  b200surv_stream_t stream);
+int32_t b200surv_ct_weight_unpack(const float *dwr_slices, int32_t slices, int32_t Cout, int32_t Cin, int32_t accumulate,
+                                  float *dw, b200surv_stream_t stream);
 int32_t b200surv_ct_bn_stats(const float *x, int64_t R, int32_t C, int32_t training, float *run_mean, float *run_var,
                              float *mu, float *rstd, void *workspace, size_t workspace_bytes, b200surv_stream_t stream);
 int32_t b200surv_ct_bn_relu(const float *x, const float *mu, const float *rstd, const float *gamma, const float *beta,
@@ -358,6 +358,27 @@ int32_t b200surv_ct_bn_bwd(const float *x, const float *dA, const float *mu, con
                            const float *beta, int64_t R, int32_t C, int32_t training, void *dx_bf16, float *dgamma,
                            float *dbeta, float *dbias, void *workspace, size_t workspace_bytes,
                            b200surv_stream_t stream);
+
+/* The whole encoder (fixed architecture 1 -> 32 -> 64 -> 128 channels) in one call each way: ct fp32 [B][D][H][W],
+ * feat / d_feat fp32 [B][128].  Parameters as in the reference state_dict (w[s] (Cout,Cin,3,3,3), b[s], gamma[s] =
+ * BatchNorm weight, beta[s] = BatchNorm bias, running statistics updated in training); grads: one buffer per
+ * parameter, overwritten.  `saved` (b200surv_ct_encoder_saved_bytes) carries the forward's activations to the
+ * backward; `workspace` (b200surv_ct_encoder_workspace_bytes) is scratch.  No allocation, no synchronisation. */
+typedef struct {
+    const float *w[3], *b[3], *gamma[3], *beta[3];
+    float *run_mean[3], *run_var[3];
+} b200surv_ct_params;
+typedef struct {
+    float *w[3], *b[3], *gamma[3], *beta[3];
+} b200surv_ct_grads;
+size_t b200surv_ct_encoder_saved_bytes(int64_t B, int32_t D, int32_t H, int32_t W);
+size_t b200surv_ct_encoder_workspace_bytes(int64_t B, int32_t D, int32_t H, int32_t W);
+int32_t b200surv_ct_encoder_fwd(const float *ct, const b200surv_ct_params *p, int64_t B, int32_t D, int32_t H, int32_t W,
+                                int32_t training, float *feat, void *saved, size_t saved_bytes, void *workspace,
+                                size_t workspace_bytes, b200surv_stream_t stream);
+int32_t b200surv_ct_encoder_bwd(const float *ct, const b200surv_ct_params *p, const float *d_feat, int64_t B, int32_t D,
+                                int32_t H, int32_t W, int32_t training, const b200surv_ct_grads *grads, const void *saved,
+                                size_t saved_bytes, void *workspace, size_t workspace_bytes, b200surv_stream_t stream);
 
 /* ---- test hooks: the hand-written sort / scan primitives behind the SORTED Cox path and the C-index ---------- */
 /* stable LSD radix sort of (u32 key, u32 value) pairs, in place (keys_tmp / vals_tmp: ping-pong buffers);

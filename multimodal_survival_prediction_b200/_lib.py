@@ -90,7 +90,13 @@ SIGNATURES = {
     "b200surv_ct_im2col": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b200surv_ct_col2im": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b200surv_ct_weight_pack": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
-    "b200surv_ct_weight_unpack": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200surv_ct_weight_unpack": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200surv_ct_encoder_saved_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
+    "b200surv_ct_encoder_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
+    "b200surv_ct_encoder_fwd": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                          c_size_t, c_void_p, c_size_t, c_void_p]),
+    "b200surv_ct_encoder_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                          c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "b200surv_ct_bn_stats": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
     "b200surv_ct_bn_relu": (c_int32, [c_void_p] * 5 + [c_int64, c_int32, c_void_p, c_void_p]),

@@ -18,6 +18,11 @@
 #include "common.cuh"
 
 namespace b200surv {
+// gemm_tc.cu
+int32_t gemm_bf16(const void *a, int64_t lda, int a_mn, const void *b, int64_t ldb, int b_mn, int M, int N, int K,
+                  float *c, int64_t ldc, void *c_bf16, int64_t ldc_bf16, const float *bias, int relu, float *splitk_ws,
+                  cudaStream_t st);
+int splitk_slices(int M, int N, int K, int *kb_per);
 namespace {
 
 using bf16 = __nv_bfloat16;
@@ -238,11 +243,12 @@ __global__ void k_weight_pack(const float *__restrict__ w, int Cout, int Cin, bf
         wr[i] = __float2bfloat16_rn(w[((size_t)o * Cin + c) * 27 + tap]);
     }
 }
-__global__ void k_weight_unpack(const float *__restrict__ dwr, int slices, int Cout, int Cin, float *__restrict__ dw) {
+__global__ void k_weight_unpack(const float *__restrict__ dwr, int slices, int Cout, int Cin, int accumulate,
+                                float *__restrict__ dw) {
     const int total = Cout * Cin * 27;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int tap = i % 27, c = (i / 27) % Cin, o = i / (27 * Cin);        // i indexes dw
-        double s = 0.0;
+        double s = accumulate ? (double)dw[i] : 0.0;
         for (int k = 0; k < slices; ++k) s += dwr[(size_t)k * total + ((size_t)o * 27 + tap) * Cin + c];
         dw[i] = (float)s;
     }
@@ -506,10 +512,10 @@ int32_t b200surv_ct_weight_pack(const float *w, int32_t Cout, int32_t Cin, void 
     return B200SURV_OK;
 }
 
-int32_t b200surv_ct_weight_unpack(const float *dwr_slices, int32_t slices, int32_t Cout, int32_t Cin, float *dw,
-                                  b200surv_stream_t stream) {
+int32_t b200surv_ct_weight_unpack(const float *dwr_slices, int32_t slices, int32_t Cout, int32_t Cin, int32_t accumulate,
+                                  float *dw, b200surv_stream_t stream) {
     B200_REQUIRE(dwr_slices && dw && slices >= 1 && Cout >= 1 && Cin >= 1, "arguments");
-    k_weight_unpack<<<(Cout * Cin * 27 + 255) / 256, 256, 0, as_stream(stream)>>>(dwr_slices, slices, Cout, Cin, dw);
+    k_weight_unpack<<<(Cout * Cin * 27 + 255) / 256, 256, 0, as_stream(stream)>>>(dwr_slices, slices, Cout, Cin, accumulate, dw);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -575,6 +581,172 @@ int32_t b200surv_ct_bn_bwd(const float *x, const float *dA, const float *mu, con
     k_bn_dx<<<blocks_for(R * C / 4, 256 * 4, 16), 256, 0, st>>>(x, dA, mu, rstd, gamma, beta, sums, R, C, training,
                                                                static_cast<bf16 *>(dx_bf16));
     B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+
+// ---------------------------------------------------------------- the whole encoder in one call each way
+// (the reference's fixed architecture 1 -> 32 -> 64 -> 128; ~35 launches forward, ~45 backward, no host work between)
+}  // extern "C"
+namespace {
+constexpr size_t COL_BYTES_IN_L2 = (size_t)64 << 20;   // patch-matrix bytes per chunk of samples: half of the 126 MB L2
+struct CtGeom {
+    int64_t B;
+    Grid3 g[3];
+    int Cin[3], Cout[3], K[3];
+    int64_t vin[3], vox[3], R[3], chunk[3];
+};
+CtGeom ct_geom(int64_t B, int D, int H, int W) {
+    CtGeom q;
+    q.B = B;
+    const int ch[4] = {1, 32, 64, 128};
+    int d[3] = {D, H, W};
+    for (int s = 0; s < 3; ++s) {
+        q.g[s] = make_grid(d[0], d[1], d[2]);
+        q.Cin[s] = ch[s]; q.Cout[s] = ch[s + 1]; q.K[s] = 27 * ch[s];
+        q.vin[s] = (int64_t)d[0] * d[1] * d[2];
+        q.vox[s] = (int64_t)q.g[s].Do * q.g[s].Ho * q.g[s].Wo;
+        q.R[s] = B * q.vox[s];
+        int64_t c = (int64_t)(COL_BYTES_IN_L2 / ((size_t)q.vox[s] * q.K[s] * 2));
+        q.chunk[s] = c < 1 ? 1 : (c > B ? B : c);
+        d[0] = q.g[s].Do; d[1] = q.g[s].Ho; d[2] = q.g[s].Wo;
+    }
+    return q;
+}
+struct Carve {
+    unsigned char *base; size_t off;
+    template <typename T> T *take(size_t n) {
+        T *p = reinterpret_cast<T *>(base + off);
+        off = align_up(off + n * sizeof(T), 256);
+        return p;
+    }
+};
+struct CtSaved { float *h[3]; bf16 *a[2]; float *mu[3], *rstd[3]; bf16 *wr[3]; };
+CtSaved carve_ct_saved(void *buf, const CtGeom &q, size_t *bytes) {
+    Carve c{static_cast<unsigned char *>(buf), 0};
+    CtSaved v;
+    for (int s = 0; s < 3; ++s) {
+        v.h[s] = c.take<float>((size_t)q.R[s] * q.Cout[s]);
+        if (s < 2) v.a[s] = c.take<bf16>((size_t)q.R[s] * q.Cout[s]);
+        v.mu[s] = c.take<float>(q.Cout[s]); v.rstd[s] = c.take<float>(q.Cout[s]);
+        v.wr[s] = s ? c.take<bf16>((size_t)q.Cout[s] * q.K[s]) : nullptr;
+    }
+    *bytes = c.off;
+    return v;
+}
+struct CtScratch { void *ctws; bf16 *col, *dcol, *dx; float *dA_a, *dA_b, *dwr; };
+CtScratch carve_ct_scratch(void *buf, const CtGeom &q, size_t *bytes) {
+    Carve c{static_cast<unsigned char *>(buf), 0};
+    CtScratch w;
+    w.ctws = c.take<unsigned char>(b200surv_ct_workspace_bytes());
+    size_t col = 0, dx = 0, dwr = 0;
+    for (int s = 0; s < 3; ++s) {
+        if (s) { col = max(col, (size_t)q.chunk[s] * q.vox[s] * q.K[s]); dwr = max(dwr, (size_t)32 * q.Cout[s] * q.K[s]); }
+        dx = max(dx, (size_t)q.R[s] * q.Cout[s]);
+    }
+    w.col = c.take<bf16>(col); w.dcol = c.take<bf16>(col); w.dx = c.take<bf16>(dx);
+    w.dA_a = c.take<float>(max((size_t)q.R[2] * q.Cout[2], (size_t)q.R[0] * q.Cout[0]));
+    w.dA_b = c.take<float>((size_t)q.R[1] * q.Cout[1]);
+    w.dwr = c.take<float>(dwr);
+    *bytes = c.off;
+    return w;
+}
+#define CT_TRY(expr) do { const int32_t _rc = (expr); if (_rc != B200SURV_OK) return _rc; } while (0)
+}  // namespace
+extern "C" {
+
+size_t b200surv_ct_encoder_saved_bytes(int64_t B, int32_t D, int32_t H, int32_t W) {
+    if (B < 1 || D < 1 || H < 1 || W < 1) return 0;
+    size_t n; carve_ct_saved(nullptr, ct_geom(B, D, H, W), &n); return n;
+}
+size_t b200surv_ct_encoder_workspace_bytes(int64_t B, int32_t D, int32_t H, int32_t W) {
+    if (B < 1 || D < 1 || H < 1 || W < 1) return 0;
+    size_t n; carve_ct_scratch(nullptr, ct_geom(B, D, H, W), &n); return n;
+}
+
+int32_t b200surv_ct_encoder_fwd(const float *ct, const b200surv_ct_params *p, int64_t B, int32_t D, int32_t H, int32_t W,
+                                int32_t training, float *feat, void *saved, size_t saved_bytes, void *workspace,
+                                size_t workspace_bytes, b200surv_stream_t stream) {
+    B200_REQUIRE(ct && p && feat && saved && workspace, "null pointer");
+    B200_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1, "shape");
+    for (int s = 0; s < 3; ++s)
+        B200_REQUIRE(p->w[s] && p->gamma[s] && p->beta[s] && p->run_mean[s] && p->run_var[s], "null parameter");
+    const CtGeom q = ct_geom(B, D, H, W);
+    B200_REQUIRE(q.R[0] * 32 < ((int64_t)1 << 40) && q.chunk[1] * q.vox[1] < ((int64_t)1 << 31), "volume too large");
+    size_t need;
+    const CtSaved v = carve_ct_saved(saved, q, &need);
+    if (saved_bytes < need) { set_error("ct encoder: saved buffer too small"); return B200SURV_WORKSPACE_TOO_SMALL; }
+    const CtScratch w = carve_ct_scratch(workspace, q, &need);
+    if (workspace_bytes < need) { set_error("ct encoder: workspace too small"); return B200SURV_WORKSPACE_TOO_SMALL; }
+    cudaStream_t st = as_stream(stream);
+    const size_t ctws = b200surv_ct_workspace_bytes();
+    for (int s = 0; s < 3; ++s) {
+        const Grid3 &g = q.g[s];
+        if (s == 0) {
+            CT_TRY(b200surv_ct_conv_first_fwd(ct, p->w[0], p->b[0], B, g.D, g.H, g.W, q.Cout[0], v.h[0], stream));
+        } else {
+            CT_TRY(b200surv_ct_weight_pack(p->w[s], q.Cout[s], q.Cin[s], v.wr[s], stream));
+            for (int64_t b0 = 0; b0 < B; b0 += q.chunk[s]) {
+                const int64_t bc = min(q.chunk[s], B - b0);
+                CT_TRY(b200surv_ct_im2col(v.a[s - 1] + b0 * q.vin[s] * q.Cin[s], bc, g.D, g.H, g.W, q.Cin[s], w.col, stream));
+                CT_TRY(gemm_bf16(w.col, q.K[s], 0, v.wr[s], q.K[s], 0, (int)(bc * q.vox[s]), q.Cout[s], q.K[s],
+                                 v.h[s] + b0 * q.vox[s] * q.Cout[s], q.Cout[s], nullptr, 0, p->b[s], 0, nullptr, st));
+            }
+        }
+        CT_TRY(b200surv_ct_bn_stats(v.h[s], q.R[s], q.Cout[s], training, p->run_mean[s], p->run_var[s], v.mu[s], v.rstd[s],
+                                    w.ctws, ctws, stream));
+        if (s < 2)
+            CT_TRY(b200surv_ct_bn_relu(v.h[s], v.mu[s], v.rstd[s], p->gamma[s], p->beta[s], q.R[s], q.Cout[s], v.a[s], stream));
+        else
+            CT_TRY(b200surv_ct_bn_relu_pool(v.h[s], v.mu[s], v.rstd[s], p->gamma[s], p->beta[s], B, (int)q.vox[s], q.Cout[s],
+                                            feat, stream));
+    }
+    return B200SURV_OK;
+}
+
+int32_t b200surv_ct_encoder_bwd(const float *ct, const b200surv_ct_params *p, const float *d_feat, int64_t B, int32_t D,
+                                int32_t H, int32_t W, int32_t training, const b200surv_ct_grads *grads, const void *saved,
+                                size_t saved_bytes, void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
+    B200_REQUIRE(ct && p && d_feat && grads && saved && workspace, "null pointer");
+    B200_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1, "shape");
+    for (int s = 0; s < 3; ++s)
+        B200_REQUIRE(p->gamma[s] && p->beta[s] && grads->w[s] && grads->b[s] && grads->gamma[s] && grads->beta[s], "null parameter");
+    const CtGeom q = ct_geom(B, D, H, W);
+    size_t need;
+    const CtSaved v = carve_ct_saved(const_cast<void *>(saved), q, &need);
+    if (saved_bytes < need) { set_error("ct encoder: saved buffer too small"); return B200SURV_WORKSPACE_TOO_SMALL; }
+    const CtScratch w = carve_ct_scratch(workspace, q, &need);
+    if (workspace_bytes < need) { set_error("ct encoder: workspace too small"); return B200SURV_WORKSPACE_TOO_SMALL; }
+    cudaStream_t st = as_stream(stream);
+    const size_t ctws = b200surv_ct_workspace_bytes();
+    float *dA = w.dA_a;
+    CT_TRY(b200surv_ct_pool_bwd(d_feat, B, (int)q.vox[2], q.Cout[2], dA, stream));
+    for (int s = 2; s >= 0; --s) {
+        const Grid3 &g = q.g[s];
+        CT_TRY(b200surv_ct_bn_bwd(v.h[s], dA, v.mu[s], v.rstd[s], p->gamma[s], p->beta[s], q.R[s], q.Cout[s], training, w.dx,
+                                  grads->gamma[s], grads->beta[s], grads->b[s], w.ctws, ctws, stream));
+        if (s == 0) {
+            CT_TRY(b200surv_ct_conv_first_wgrad(ct, w.dx, B, g.D, g.H, g.W, q.Cout[0], grads->w[0], w.ctws, ctws, stream));
+            break;
+        }
+        float *dA_prev = (s == 2) ? w.dA_b : w.dA_a;
+        for (int64_t b0 = 0; b0 < B; b0 += q.chunk[s]) {
+            const int64_t bc = min(q.chunk[s], B - b0);
+            const int rows = (int)(bc * q.vox[s]);
+            const bf16 *dxc = w.dx + b0 * q.vox[s] * q.Cout[s];
+            CT_TRY(b200surv_ct_im2col(v.a[s - 1] + b0 * q.vin[s] * q.Cin[s], bc, g.D, g.H, g.W, q.Cin[s], w.col, stream));
+            // dW (tap-major) = dx^T col, both operands as stored (MN-major), split along K over the SMs
+            const int nsl = splitk_slices(q.Cout[s], q.K[s], rows, nullptr);
+            CT_TRY(gemm_bf16(dxc, q.Cout[s], 1, w.col, q.K[s], 1, q.Cout[s], q.K[s], rows, w.dwr, q.K[s], nullptr, 0, nullptr, 0,
+                             w.dwr, st));
+            CT_TRY(b200surv_ct_weight_unpack(w.dwr, nsl, q.Cout[s], q.Cin[s], b0 > 0, grads->w[s], stream));
+            // dcol = dx W; every input voxel then gathers its taps
+            CT_TRY(gemm_bf16(dxc, q.Cout[s], 0, v.wr[s], q.K[s], 1, rows, q.K[s], q.Cout[s], nullptr, 0, w.dcol, q.K[s], nullptr,
+                             0, nullptr, st));
+            CT_TRY(b200surv_ct_col2im(w.dcol, bc, g.D, g.H, g.W, q.Cin[s], dA_prev + b0 * q.vin[s] * q.Cin[s], stream));
+        }
+        dA = dA_prev;
+    }
     return B200SURV_OK;
 }
 
