@@ -328,6 +328,32 @@ def run_b200(args):
     head_ms = timed_head(lambda: graphed.step(*fresh), reps=20)
     head_flop_per_row = 11_396_224          # fwd 5,507,136 + bwd 5,889,088
 
+    # ---- CT encoder feeding the head: the reference's 3-conv CNN on 64 x 64 x 32 volumes, fwd + bwd,
+    # at the reference's batch size (4, partial_modality_training.py:366) and at 64; PyTorch/cuDNN (bf16 autocast,
+    # channels_last_3d, TF32 allowed: its fastest setting here) on the same GPU beside it
+    import copy as _copy
+    ct_extra = {}
+    for cb in (4, 64):
+        enc = net.ct_encoder.train()
+        vol = torch.rand(cb, 1, 64, 64, 32, device=dev)
+        cudnn_enc = torch.nn.Sequential(*[_copy.deepcopy(m_) for m_ in enc]).to(dev).to(memory_format=torch.channels_last_3d).train()
+
+        def ct_step(enc=enc, vol=vol):
+            for prm in enc.parameters():
+                prm.grad = None
+            enc(vol).sum().backward()
+
+        def cudnn_step(m_=cudnn_enc, vol=vol):
+            for prm in m_.parameters():
+                prm.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y_ = m_(vol)
+            y_.float().sum().backward()
+
+        ct_extra[f"b{cb}"] = {"ms_fwd_bwd": timed_head(ct_step), "cudnn_bf16_channels_last_ms": timed_head(cudnn_step)}
+    ct_extra["note"] = ("Conv3d(1,32)/(32,64)/(64,128) k3 s2 p1 + BatchNorm3d + ReLU + AdaptiveAvgPool3d(1) on 64x64x32 volumes, "
+                        "training mode: direct first conv, im2col + tcgen05 GEMM for the other two (b200surv_ct_encoder_fwd/_bwd); per rank")
+
     # ---- CV sweep share of one GPU (BASELINE.json configs[4]): 32 replicas x one fold of 100k patients, packed back to
     # back: segmented Cox fwd+bwd (one call) + one C-index per replica.  Replicas are independent: no collective.
     sw_rep, sw_rows = 32, 100_000
@@ -429,6 +455,7 @@ def run_b200(args):
                                    "note": "32 replicas x 100k patients per GPU packed back to back: segmented Cox "
                                            "fwd+bwd (one call) + one C-index per replica; independent replicas, no "
                                            "collective (weak scaling)"},
+                      "ct_encoder": ct_extra,
                       "head_b4096": {"rows": hb, "ms_fwd_bwd": head_ms, "rows_per_s": hb / (head_ms * 1e-3),
                                      "tflops": hb * head_flop_per_row / (head_ms * 1e-3) / 1e12,
                                      "dtype": "bf16 operands, fp32 accumulate (tcgen05)", "dropout_p": 0.3,

@@ -376,19 +376,25 @@ k_bn_relu(const float *__restrict__ x, const float *__restrict__ mu, const float
         reinterpret_cast<uint2 *>(y)[v] = pack_bf16x4(o[0], o[1], o[2], o[3]);
     }
 }
-// feat[b][c] = mean_v relu(bn(x[b*V + v][c]))   (BN + ReLU + AdaptiveAvgPool3d(1) of the last stage)
-__global__ void __launch_bounds__(256)
+// feat[b][c] = mean_v relu(bn(x[b*V + v][c]))   (BN + ReLU + AdaptiveAvgPool3d(1) of the last stage).  One CTA per
+// sample: thread = (voxel lane, channel), 1024 / C voxel lanes, summed in a fixed order.
+__global__ void __launch_bounds__(1024)
 k_bn_relu_pool(const float *__restrict__ x, const float *__restrict__ mu, const float *__restrict__ rstd,
                const float *__restrict__ gamma, const float *__restrict__ beta, int64_t B, int V, int C,
                float *__restrict__ feat) {
-    const int64_t total = B * C;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const int64_t b = i / C;
-        const float m = mu[c], sc = rstd[c] * gamma[c], be = beta[c];
+    __shared__ float sh[1024];
+    const int c = threadIdx.x % C, lane_v = threadIdx.x / C, lanes = 1024 / C;
+    const float m = mu[c], sc = rstd[c] * gamma[c], be = beta[c];
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
         float s = 0.f;
-        for (int v = 0; v < V; ++v) s += fmaxf((x[(b * V + v) * C + c] - m) * sc + be, 0.f);
-        feat[i] = s / (float)V;
+        for (int v = lane_v; v < V; v += lanes) s += fmaxf((x[(b * V + v) * C + c] - m) * sc + be, 0.f);
+        __syncthreads();
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        if (lane_v == 0) {
+            for (int l = 1; l < lanes; ++l) s += sh[l * C + c];
+            feat[b * C + c] = s / (float)V;
+        }
     }
 }
 __global__ void k_pool_bwd(const float *__restrict__ dfeat, int64_t B, int V, int C, float *__restrict__ dA) {
@@ -428,7 +434,7 @@ k_bn_dx(const float *__restrict__ x, const float *__restrict__ dA, const float *
 inline bool pow2_channels(int C) { return C >= 8 && C <= 256 && (C & (C - 1)) == 0; }
 constexpr int BN_PARTS_PER_SM = 4;
 inline int bn_parts(int64_t R, int C) {
-    int64_t p = (R * C / 4 + 4095) / 4096;
+    int64_t p = (R * C / 4 + 1023) / 1024;      // >= 4 float4 per thread
     const int64_t cap = (int64_t)BN_PARTS_PER_SM * num_sms();
     if (p > cap) p = cap;
     if (p < 1) p = 1;
@@ -550,8 +556,8 @@ int32_t b200surv_ct_bn_relu_pool(const float *x, const float *mu, const float *r
                                  const float *beta, int64_t B, int32_t V, int32_t C, float *feat,
                                  b200surv_stream_t stream) {
     B200_REQUIRE(x && mu && rstd && gamma && beta && feat, "null pointer");
-    B200_REQUIRE(B >= 1 && V >= 1 && C >= 1, "shape");
-    k_bn_relu_pool<<<blocks_for(B * C, 256, 16), 256, 0, as_stream(stream)>>>(x, mu, rstd, gamma, beta, B, V, C, feat);
+    B200_REQUIRE(B >= 1 && V >= 1 && pow2_channels(C), "shape (C a power of two in [8, 256])");
+    k_bn_relu_pool<<<blocks_for(B, 1, 2), 1024, 0, as_stream(stream)>>>(x, mu, rstd, gamma, beta, B, V, C, feat);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
