@@ -213,7 +213,53 @@ def gen_head():
         np.savez_compressed(os.path.join(OUT, f"head_{tag}_manifest.npz"), **man)
 
 
+def gen_ct_encoder():
+    """The CT branch of the reference's PartialModalityNet (partial_modality_training.py:179-190, USE_MONAI=False) run
+    through the reference class itself: eval features, one training step of the whole model (dropout off) and the
+    gradients / running statistics of ct_encoder.*  (SURVEY.md 8f row 3)."""
+    rna_dim, B = 40, 6
+    cls, l1 = extract("partial_modality_training.py", "PartialModalityNet", (ast.ClassDef,))
+    print(f"  ct encoder: partial_modality_training.py:{l1}")
+    torch.manual_seed(123)
+    model = cls(rna_dim=rna_dim, clinical_dim=1).double()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm3d)):
+                m.weight.uniform_(0.5, 1.5); m.bias.uniform_(-0.2, 0.2)
+                m.running_mean.uniform_(-0.3, 0.3); m.running_var.uniform_(0.5, 1.5)
+    g = torch.Generator().manual_seed(11)
+    ct = torch.rand(B, 1, 24, 20, 12, generator=g).double()
+    ct[1].zero_()                                    # a patient without imaging (:89)
+    rna = torch.randn(B, rna_dim, generator=g).double()
+    clin = (0.3 + 0.6 * torch.rand(B, 1, generator=g)).double()
+    mask = torch.ones(B, 3).double(); mask[1, 0] = 0.0
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    out = {"ct": ct.numpy().astype(np.float32), "rna": rna.numpy(), "clinical": clin.numpy(), "mask": mask.numpy()}
+    for k, v in sd0.items():
+        out["sd0/" + k] = v.numpy().astype(np.float32) if v.dtype.is_floating_point else v.numpy()
+    model.eval()
+    with torch.no_grad():
+        out["eval/ct_feat"] = model.ct_encoder(ct).view(B, -1).numpy()
+        out["eval/hazard"] = model(ct, rna, clin, mask)[0].numpy()
+    model.train()
+    _set_dropout_p(model, 0.0)
+    hz, gate = model(ct, rna, clin, mask)
+    wsum = torch.linspace(0.5, 1.5, B, dtype=torch.float64)
+    (hz * wsum).sum().backward()
+    out["train/hazard"], out["train/hazard_weights"] = hz.detach().numpy(), wsum.numpy()
+    for k, p_ in model.named_parameters():
+        if k.startswith("ct_encoder"):
+            out["grad/" + k] = p_.grad.numpy().astype(np.float32)
+    for k, v in model.state_dict().items():
+        if k.startswith("ct_encoder") and ("running" in k or "num_batches" in k):
+            out["sd1/" + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "ct_encoder.npz"), **out)
+
+
 def main():
+    if "--only-ct" in sys.argv:
+        gen_ct_encoder()
+        return
     if not os.path.isdir(REF):
         sys.exit("reference not present: golden vectors can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
@@ -221,6 +267,7 @@ def main():
     gen_cox()
     gen_cindex()
     gen_head()
+    gen_ct_encoder()
     print("wrote", sorted(os.listdir(OUT)))
 
 

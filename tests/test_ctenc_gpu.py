@@ -4,10 +4,10 @@ import copy
 
 import pytest
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from multimodal_survival_prediction_b200.ctenc import CTEncoderCNN
+from oracle.ctenc import matched_forward as _matched, reference_cnn as _reference_cnn
 
 pytestmark = pytest.mark.gpu
 
@@ -16,36 +16,6 @@ GRAD_TOL = 3e-2     # per-tensor relative Frobenius error against the reference 
 GRAD_TOL_FP32 = 0.15  # ... and against the full-precision reference: in training mode BatchNorm's backward projects
 #                       out most of dy, which amplifies the bf16 operand rounding to 5-9 % per tensor -- the matched
 #                       reference shows the same 5-9 % against fp32 (scratch/ctenc_diag.py), eval mode stays < 1 %
-
-
-def _reference_cnn():
-    return nn.Sequential(                                   # partial_modality_training.py:179-190
-        nn.Conv3d(1, 32, 3, stride=2, padding=1), nn.BatchNorm3d(32), nn.ReLU(),
-        nn.Conv3d(32, 64, 3, stride=2, padding=1), nn.BatchNorm3d(64), nn.ReLU(),
-        nn.Conv3d(64, 128, 3, stride=2, padding=1), nn.BatchNorm3d(128), nn.ReLU(),
-        nn.AdaptiveAvgPool3d(1),
-    )
-
-
-class _RoundBf16(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x):
-        return x.bfloat16().float()
-
-    @staticmethod
-    def backward(ctx, g):
-        return g
-
-
-def _matched(seq, ct):
-    """The reference CNN with the operands of convolutions 2 and 3 rounded to bf16 (straight-through): the arithmetic
-    of the tensor-core path, evaluated by PyTorch."""
-    x = ct
-    for i in (0, 3, 6):
-        conv, bn = seq[i], seq[i + 1]
-        x = conv(x) if i == 0 else F.conv3d(_RoundBf16.apply(x), _RoundBf16.apply(conv.weight), conv.bias, stride=2, padding=1)
-        x = F.relu(bn(x))
-    return seq[9](x)
 
 
 def _rel(a, b):
@@ -128,3 +98,44 @@ def test_full_model_step_with_ct_volumes():
     errs = {k: _rel(g_ours[k], p.grad) for k, p in cnn.named_parameters() if k not in ("0.bias", "3.bias", "6.bias")}
     assert all(float(g.abs().max()) > 0 for k, g in g_ours.items() if k in errs)
     assert max(errs.values()) <= 2 * GRAD_TOL, errs           # two bf16 heads in front of the comparison
+
+
+def test_ct_encoder_matches_reference_class_golden():
+    """tests/golden/ct_encoder.npz: the reference's own PartialModalityNet (fp64, CPU) on 24 x 20 x 12 volumes -- CT
+    features in eval mode, then one training step of the whole model and the gradients / running statistics of
+    ct_encoder.* (oracle/gen_golden.py: gen_ct_encoder)."""
+    import os
+    import numpy as np
+    from multimodal_survival_prediction_b200 import head as ghead
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ct_encoder.npz"))
+    dev = torch.device("cuda", 0)
+    m = ghead.PartialModalityNet(rna_dim=40).to(dev)
+    sd0 = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd0/")}
+    m.load_state_dict(sd0)                                   # the reference's state_dict loads key for key
+    ct, rna, clin, mask = (torch.from_numpy(g[k]).float().to(dev) for k in ("ct", "rna", "clinical", "mask"))
+    m.eval()
+    with torch.no_grad():
+        feat = m.ct_encoder(ct).view(ct.shape[0], -1)
+        hz = m(ct, rna, clin, mask)[0]
+    ref = torch.from_numpy(g["eval/ct_feat"]).float().to(dev)
+    assert float((feat - ref).abs().max()) <= OUT_TOL * max(1.0, float(ref.abs().max()))
+    assert float((hz.cpu() - torch.from_numpy(g["eval/hazard"]).float()).abs().max()) <= OUT_TOL
+    m.train()
+    m.rna_encoder[3].p = 0.0; m.fusion[3].p = 0.0
+    hz, _ = m(ct, rna, clin, mask)
+    assert float((hz.detach().cpu() - torch.from_numpy(g["train/hazard"]).float()).abs().max()) <= OUT_TOL
+    (hz * torch.from_numpy(g["train/hazard_weights"]).float().to(dev)).sum().backward()
+    errs = {}
+    for k, p in m.ct_encoder.named_parameters():
+        ref = torch.from_numpy(g["grad/ct_encoder." + k]).to(dev)
+        if k in ("0.bias", "3.bias", "6.bias"):              # cancelled by BatchNorm: ~1e-17 in the fp64 reference
+            assert float(p.grad.abs().max()) == 0.0 and float(ref.abs().max()) < 1e-9
+        else:
+            errs[k] = _rel(p.grad, ref)
+    # fp64 reference vs bf16 GEMM operands through two bf16 stages and the bf16 head: see GRAD_TOL_FP32 above
+    assert max(errs.values()) <= GRAD_TOL_FP32, errs
+    for k, v in m.ct_encoder.state_dict().items():
+        if "running" in k:
+            assert _rel(v, torch.from_numpy(g["sd1/ct_encoder." + k]).to(dev)) <= 5e-3, k
+        if "num_batches" in k:
+            assert int(v) == int(g["sd1/ct_encoder." + k]) == 1

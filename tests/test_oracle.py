@@ -207,3 +207,24 @@ def test_head_state_dict_manifest(golden):
         assert tuple(g[k]) == tuple(v.shape), k
     u = golden("head_ungated_manifest.npz")
     assert "gate.0.weight" not in u.files and tuple(u["fusion.0.weight"]) == (256, 288)
+
+
+def test_ct_encoder_restatement_matches_reference_class():
+    """oracle/ctenc.py (the CNN the GPU tests compare against) reproduces what the reference's own class computed:
+    tests/golden/ct_encoder.npz, eval features and training-step gradients of ct_encoder.* (fp64)."""
+    import os
+    from oracle.ctenc import reference_cnn
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ct_encoder.npz"))
+    cnn = reference_cnn().double()
+    cnn.load_state_dict({k[len("sd0/ct_encoder."):]: torch.from_numpy(g[k]).double() if g[k].dtype.kind == "f" else torch.from_numpy(g[k])
+                         for k in g.files if k.startswith("sd0/ct_encoder.")})
+    ct = torch.from_numpy(g["ct"]).double()
+    cnn.eval()
+    with torch.no_grad():
+        feat = cnn(ct).view(ct.shape[0], -1)
+    assert np.abs(feat.numpy() - g["eval/ct_feat"]).max() <= 1e-6      # the fixture stores the parameters as float32
+    cnn.train()
+    cnn(ct)
+    for k, v in cnn.state_dict().items():
+        if "running" in k:
+            assert np.abs(v.numpy() - g["sd1/ct_encoder." + k]).max() <= 1e-6, k
