@@ -152,6 +152,67 @@ k_conv_first_wgrad(const float *__restrict__ x, const bf16 *__restrict__ dx, int
         }
     }
 }
+// The reference's width (Cout = 32): lanes = the 27 taps, a warp = a contiguous run of output rows.  Per row one
+// (predicated) load of the lane's own tap and FOUR warp-uniform 16-byte loads of the row's 32 bf16 dx values, then 32
+// FMAs into per-channel accumulators: 5 loads per row and warp instead of 28.
+__global__ void __launch_bounds__(WG_THREADS, 1)
+k_conv_first_wgrad32(const float *__restrict__ x, const bf16 *__restrict__ dx, int64_t B, Grid3 g,
+                     float *__restrict__ partial) {
+    __shared__ float red[WG_THREADS * 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = WG_THREADS / 32;
+    const int tap = lane < 27 ? lane : 26;
+    const int kz = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
+    const int64_t vox = (int64_t)g.Do * g.Ho * g.Wo, R = B * vox;
+    const int64_t per = (R + (int64_t)gridDim.x * warps - 1) / ((int64_t)gridDim.x * warps);
+    const int64_t r0 = ((int64_t)blockIdx.x * warps + warp) * per, r1 = min(R, r0 + per);
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    if (r0 < r1) {
+        int64_t b = r0 / vox;
+        int v = (int)(r0 - b * vox);
+        int xo = v % g.Wo; v /= g.Wo;
+        int yo = v % g.Ho, zo = v / g.Ho;
+        const int64_t plane = (int64_t)g.H * g.W;
+        const float *xb = x + b * g.D * plane;
+        for (int64_t r = r0; r < r1; ++r) {
+            const int z = 2 * zo - 1 + kz, y = 2 * yo - 1 + ky, xx = 2 * xo - 1 + kx;
+            const bool in = (unsigned)z < (unsigned)g.D && (unsigned)y < (unsigned)g.H && (unsigned)xx < (unsigned)g.W;
+            const float xv = in ? __ldg(xb + z * plane + (int64_t)y * g.W + xx) : 0.f;
+            const uint4 *dr = reinterpret_cast<const uint4 *>(dx + r * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 u = __ldg(dr + q);
+                const unsigned w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[q * 8 + 2 * j] += xv * __uint_as_float(w4[j] << 16);
+                    acc[q * 8 + 2 * j + 1] += xv * __uint_as_float(w4[j] & 0xffff0000u);
+                }
+            }
+            if (++xo == g.Wo) {
+                xo = 0;
+                if (++yo == g.Ho) {
+                    yo = 0;
+                    if (++zo == g.Do) { zo = 0; xb += g.D * plane; }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int round = 0; round < 4; ++round) {       // eight channels at a time through 32 KB of shared memory
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) red[threadIdx.x * 8 + c] = acc[round * 8 + c];
+        __syncthreads();
+        for (int i = threadIdx.x; i < 27 * 8; i += WG_THREADS) {
+            const int t = i / 8, c = i % 8;
+            float sum = 0.f;
+            for (int w = 0; w < warps; ++w) sum += red[(w * 32 + t) * 8 + c];
+            partial[(size_t)blockIdx.x * 32 * 27 + (round * 8 + c) * 27 + t] = sum;
+        }
+    }
+}
 // out[i] = sum over the slices, in a fixed order: 32 elements x 8 slice lanes per CTA
 __global__ void __launch_bounds__(256)
 k_sum_slices(const float *__restrict__ part, int slices, int64_t elems, float *__restrict__ out) {
@@ -482,7 +543,13 @@ int32_t b200surv_ct_conv_first_wgrad(const float *x, const void *dx_bf16, int64_
     if ((int64_t)ctas * lanes > R) ctas = (int)((R + lanes - 1) / lanes);
     float *partial = static_cast<float *>(workspace);
     cudaStream_t st = as_stream(stream);
-    k_conv_first_wgrad<<<ctas, WG_THREADS, 0, st>>>(x, static_cast<const bf16 *>(dx_bf16), B, g, Cout, partial);
+    if (Cout == 32) {
+        ctas = num_sms();
+        if ((int64_t)ctas * (WG_THREADS / 32) > R) ctas = (int)((R + WG_THREADS / 32 - 1) / (WG_THREADS / 32));
+        k_conv_first_wgrad32<<<ctas, WG_THREADS, 0, st>>>(x, static_cast<const bf16 *>(dx_bf16), B, g, partial);
+    } else {
+        k_conv_first_wgrad<<<ctas, WG_THREADS, 0, st>>>(x, static_cast<const bf16 *>(dx_bf16), B, g, Cout, partial);
+    }
     k_sum_slices<<<(Cout * 27 + 31) / 32, 256, 0, st>>>(partial, ctas, (int64_t)Cout * 27, dw);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;

@@ -139,3 +139,33 @@ def test_ct_encoder_matches_reference_class_golden():
             assert _rel(v, torch.from_numpy(g["sd1/ct_encoder." + k]).to(dev)) <= 5e-3, k
         if "num_batches" in k:
             assert int(v) == int(g["sd1/ct_encoder." + k]) == 1
+
+
+@pytest.mark.parametrize("cout", [32, 64])
+def test_first_conv_primitives(cout):
+    """b200surv_ct_conv_first_fwd / _wgrad called directly (the width-32 and the generic weight-gradient kernels)
+    against F.conv3d and its weight gradient."""
+    import torch.nn.functional as F
+    from multimodal_survival_prediction_b200 import _lib as L
+    dev = torch.device("cuda", 0)
+    L.require_device(0)
+    lib = L.load()
+    torch.manual_seed(cout)
+    B, D, H, W = 3, 11, 16, 9
+    x = torch.rand(B, D, H, W, device=dev)
+    w = torch.randn(cout, 1, 3, 3, 3, device=dev) * 0.2
+    bias = torch.randn(cout, device=dev)
+    Do, Ho, Wo = (D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    R = B * Do * Ho * Wo
+    h = torch.empty(R, cout, device=dev)
+    st = L.stream_ptr(dev)
+    L.check(lib.b200surv_ct_conv_first_fwd(L.ptr(x), L.ptr(w), L.ptr(bias), B, D, H, W, cout, L.ptr(h), st), "fwd")
+    wref = w.clone().requires_grad_(True)
+    ref = F.conv3d(x.view(B, 1, D, H, W), wref, bias, stride=2, padding=1)           # (B, cout, Do, Ho, Wo)
+    assert torch.allclose(h.view(B, Do, Ho, Wo, cout).permute(0, 4, 1, 2, 3), ref, rtol=1e-5, atol=1e-5)
+    dy = torch.randn(R, cout, device=dev).bfloat16()
+    ref.backward(dy.float().view(B, Do, Ho, Wo, cout).permute(0, 4, 1, 2, 3))
+    dw = torch.empty(cout, 27, device=dev)
+    ws = torch.empty(lib.b200surv_ct_workspace_bytes(), dtype=torch.uint8, device=dev)
+    L.check(lib.b200surv_ct_conv_first_wgrad(L.ptr(x), L.ptr(dy), B, D, H, W, cout, L.ptr(dw), L.ptr(ws), ws.numel(), st), "wgrad")
+    assert _rel(dw.view_as(wref), wref.grad) <= 1e-5
