@@ -351,6 +351,44 @@ def run_b200(args):
             y_.float().sum().backward()
 
         ct_extra[f"b{cb}"] = {"ms_fwd_bwd": timed_head(ct_step), "cudnn_bf16_channels_last_ms": timed_head(cudnn_step)}
+    # ---- BASELINE.json configs[0]: one training step of the ungated net at the reference's batch size (4): CT volume +
+    # 5,005 genes + age from pinned host memory -> CT encoder -> head -> Cox loss -> backward -> clip + AdamW, all through
+    # the public modules; beside it the same step as a torch-CPU port on the host cores (rank 0, N=1 only)
+    from multimodal_survival_prediction_b200.optim import ClipAdam
+    c1 = ghead.MultiModalSurvivalNet().to(dev).train()
+    c1_opt = ClipAdam(c1.parameters(), lr=1e-4, weight_decay=1e-4, max_norm=1.0, adamw=True)      # simple_fusion.py:391
+    _, c1_rna, c1_clin, _ = synth.modality_batch(4, seed=SEED)
+    c1_host = [torch.rand(4, 1, 64, 64, 32).pin_memory(), c1_rna.pin_memory(), c1_clin.pin_memory()]
+    c1_ev = torch.tensor([1, 0, 1, 1]).bool().to(dev)
+    c1_t = torch.tensor([5.0, 3.0, 8.0, 1.0], device=dev)
+
+    def cfg1_step():
+        vol, rna_, clin_ = (x.to(dev, non_blocking=True) for x in c1_host)
+        c1_opt.zero_grad()
+        loss_ = gcox.neg_partial_log_likelihood(c1(vol, rna_, clin_), c1_ev, c1_t)
+        loss_.backward()
+        c1_opt.step()
+        return loss_
+
+    cfg1_ms = timed_head(cfg1_step, reps=20)
+    cfg1 = {"ms_per_step": cfg1_ms, "patients_per_s": 4 / (cfg1_ms * 1e-3), "h2d_bytes_per_step": sum(x.numel() * 4 for x in c1_host),
+            "note": "MultiModalSurvivalNet (CNN CT encoder + ungated head) + Cox loss + backward + fused clip/AdamW at batch 4, "
+                    "64x64x32 CT + 5005 genes + age copied from pinned host memory every step; per rank"}
+    if rank == 0 and world == 1:
+        try:
+            from oracle import model_torch
+            cm = model_torch.MultiModalNetCPU().train()
+            copt = torch.optim.AdamW(cm.parameters(), lr=1e-4, weight_decay=1e-4)
+            cargs = [x.clone() for x in c1_host] + [c1_ev.cpu(), c1_t.cpu()]
+            for _ in range(2):
+                model_torch.training_step(cm, copt, *cargs)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                model_torch.training_step(cm, copt, *cargs)
+            cfg1["cpu_port_ms_per_step"] = (time.perf_counter() - t0) / 10 * 1e3
+            cfg1["cpu_port"] = f"torch CPU fp32 port of the same step (oracle/model_torch.py), {torch.get_num_threads()} threads, 10 steps"
+        except Exception as ex:  # noqa: BLE001 -- the baseline is optional
+            cfg1["cpu_port"] = "unavailable: " + repr(ex)
     ct_extra["note"] = ("Conv3d(1,32)/(32,64)/(64,128) k3 s2 p1 + BatchNorm3d + ReLU + AdaptiveAvgPool3d(1) on 64x64x32 volumes, "
                         "training mode: direct first conv, im2col + tcgen05 GEMM for the other two (b200surv_ct_encoder_fwd/_bwd); per rank")
 
@@ -455,6 +493,7 @@ def run_b200(args):
                                    "note": "32 replicas x 100k patients per GPU packed back to back: segmented Cox "
                                            "fwd+bwd (one call) + one C-index per replica; independent replicas, no "
                                            "collective (weak scaling)"},
+                      "cfg1_batch4_step": cfg1,
                       "ct_encoder": ct_extra,
                       "head_b4096": {"rows": hb, "ms_fwd_bwd": head_ms, "rows_per_s": hb / (head_ms * 1e-3),
                                      "tflops": hb * head_flop_per_row / (head_ms * 1e-3) / 1e12,

@@ -228,3 +228,24 @@ def test_ct_encoder_restatement_matches_reference_class():
     for k, v in cnn.state_dict().items():
         if "running" in k:
             assert np.abs(v.numpy() - g["sd1/ct_encoder." + k]).max() <= 1e-6, k
+
+
+def test_cpu_model_port_has_the_reference_state_dict():
+    """oracle/model_torch.MultiModalNetCPU (bench.py's CPU leg of configs[0]) has exactly the keys and shapes of the
+    reference's MultiModalSurvivalNet (manifest written from the reference class by oracle/gen_golden.py), and one
+    training step of it runs and changes the parameters."""
+    import os
+    from oracle import model_torch
+    man = np.load(os.path.join(os.path.dirname(__file__), "golden", "head_ungated_manifest.npz"))
+    m = model_torch.MultiModalNetCPU()
+    sd = m.state_dict()
+    assert sorted(sd.keys()) == sorted(man.files)
+    for k in man.files:
+        assert tuple(sd[k].shape) == tuple(int(v) for v in man[k]), k
+    torch.manual_seed(0)
+    small = model_torch.MultiModalNetCPU(rna_dim=16).train()
+    opt = torch.optim.AdamW(small.parameters(), lr=1e-3)
+    w0 = small.cox_head.weight.detach().clone()
+    loss = model_torch.training_step(small, opt, torch.rand(4, 1, 16, 16, 8), torch.randn(4, 16), torch.rand(4, 1),
+                                     torch.tensor([1, 0, 1, 1]).bool(), torch.tensor([5.0, 3.0, 8.0, 1.0]))
+    assert np.isfinite(loss) and not torch.equal(w0, small.cox_head.weight.detach())
