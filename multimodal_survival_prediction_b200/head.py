@@ -258,6 +258,22 @@ class GraphedHeadStep:
         return self.replay()
 
 
+class GraphedModelStep(GraphedHeadStep):
+    """One training step of the WHOLE net from CT volumes -- CT encoder (ctenc.CTEncoderCNN), head, ``loss_fn(*outputs)``,
+    backward -- captured in ONE CUDA graph: the reference's step at batch 4 (partial_modality_training.py:382-435,
+    simple_fusion.py:255-275) is bound by the host when issued call by call (~200 launches).  Same contract as
+    GraphedHeadStep with ``ct`` = the (B,1,D,H,W) volumes; ``loss_fn`` must not synchronise (the Cox loss does not for
+    cohorts of <= 2048 rows; pass ``checks=False``)."""
+
+    def _eager(self):
+        self.seed += 1
+        ct_feat = self.module._ct_features(self.inputs[0])
+        outs = fused_head(self.module, ct_feat, *self.inputs[1:], seed=self.seed)
+        loss = self.loss_fn(*outs)
+        loss.backward()
+        return loss, outs
+
+
 class _GateEntropy(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gate, eps):

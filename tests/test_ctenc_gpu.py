@@ -169,3 +169,43 @@ def test_first_conv_primitives(cout):
     ws = torch.empty(lib.b200surv_ct_workspace_bytes(), dtype=torch.uint8, device=dev)
     L.check(lib.b200surv_ct_conv_first_wgrad(L.ptr(x), L.ptr(dy), B, D, H, W, cout, L.ptr(dw), L.ptr(ws), ws.numel(), st), "wgrad")
     assert _rel(dw.view_as(wref), wref.grad) <= 1e-5
+
+
+def test_graphed_model_step_matches_eager():
+    """head.GraphedModelStep (CT encoder + head + Cox loss + backward as one CUDA graph) reproduces the eager step bit
+    for bit (dropout off), also on a second batch copied into its static buffers."""
+    from multimodal_survival_prediction_b200 import head as ghead, neg_partial_log_likelihood, synth
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(2)
+    B = 4
+    m = ghead.MultiModalSurvivalNet().to(dev).train()
+    m.rna_encoder[3].p = 0.0; m.fusion[3].p = 0.0
+    before = copy.deepcopy(m.state_dict())
+    event = torch.tensor([1, 0, 1, 1], device=dev).bool()
+    time = torch.tensor([5.0, 3.0, 8.0, 1.0], device=dev)
+
+    def loss_fn(hazard, *_):
+        return neg_partial_log_likelihood(hazard, event, time, checks=False)
+
+    batches = []
+    for seed in (3, 4):
+        _, rna, clin, _ = [t.to(dev) for t in synth.modality_batch(B, seed=seed)]
+        batches.append((torch.rand(B, 1, 32, 32, 16, device=dev), rna, clin))
+    def eager_step(ct, rna, clin):                    # a function: no tensor of the autograd graph outlives the step
+        m.load_state_dict(before); m.zero_grad()      # (a live AccumulateGrad node of the default stream breaks capture)
+        loss = loss_fn(m(ct, rna, clin))
+        loss.backward()
+        return (loss.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters()}, copy.deepcopy(m.state_dict()))
+
+    eager = [eager_step(*b) for b in batches]         # every step from the same initial state
+    m.load_state_dict(before); m.zero_grad()
+    step = ghead.GraphedModelStep(m, batches[0][0], batches[0][1], batches[0][2], None, loss_fn)
+    for (ct, rna, clin), (loss_e, grads_e, sd_e) in zip(batches, eager):
+        m.load_state_dict(before)                     # warm-up and capture ran real steps
+        loss, _ = step.step(ct, rna, clin)
+        assert torch.equal(loss, loss_e)
+        for k, p in m.named_parameters():
+            assert torch.equal(p.grad, grads_e[k]), k
+        for k, v in m.state_dict().items():
+            if "running" in k:
+                assert torch.equal(v, sd_e[k]), k
