@@ -232,26 +232,32 @@ k_sum_slices(const float *__restrict__ part, int slices, int64_t elems, float *_
 }
 
 // ---------------------------------------------------------------- im2col / col2im (stride 2, pad 1, 3x3x3)
-// a bf16 [Bc*D*H*W][C] -> col bf16 [Bc*Do*Ho*Wo][27*C], column = tap*C + c.  One thread = 8 channels (16 bytes).
+// a bf16 [Bc*D*H*W][C] -> col bf16 [Bc*Do*Ho*Wo][27*C], column = tap*C + c.  A WARP copies one output row's 27*C
+// values as 16-byte vectors (lane j <-> vector j: fully coalesced stores; a tap's C channels are one contiguous run of
+// the source voxel), so the row's voxel coordinates are decomposed once per 27*C/8 vectors; CV = C/8 (0: run time).
+template <int CV>
 __global__ void __launch_bounds__(256)
 k_im2col(const bf16 *__restrict__ a, int64_t Bc, Grid3 g, int C, bf16 *__restrict__ col) {
-    const int cv = C / 8;
-    const int64_t vox = (int64_t)g.Do * g.Ho * g.Wo, total = Bc * vox * 27 * cv;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c8 = (int)(i % cv);
-        int64_t q = i / cv;
-        const int tap = (int)(q % 27);
-        const int64_t r = q / 27;
+    const int cv = CV ? CV : C / 8, nvec = 27 * cv;
+    const int lane = threadIdx.x & 31;
+    const int64_t vox = (int64_t)g.Do * g.Ho * g.Wo, rows = Bc * vox, vin = (int64_t)g.D * g.H * g.W;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
         const int64_t b = r / vox;
         int v = (int)(r - b * vox);
         const int xo = v % g.Wo; v /= g.Wo;
         const int yo = v % g.Ho, zo = v / g.Ho;
-        const int kz = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
-        const int z = 2 * zo - 1 + kz, y = 2 * yo - 1 + ky, xx = 2 * xo - 1 + kx;
-        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-        if (z >= 0 && z < g.D && y >= 0 && y < g.H && xx >= 0 && xx < g.W)
-            val = __ldg(reinterpret_cast<const uint4 *>(a + (((b * g.D + z) * g.H + y) * (int64_t)g.W + xx) * C) + c8);
-        reinterpret_cast<uint4 *>(col)[i] = val;      // i == (r*27 + tap)*cv + c8
+        const uint4 *src = reinterpret_cast<const uint4 *>(a + b * vin * C);
+        uint4 *dst = reinterpret_cast<uint4 *>(col + r * 27 * C);
+        for (int j = lane; j < nvec; j += 32) {
+            const int tap = j / cv, c8 = j - tap * cv;
+            const int kz = tap / 9, ky = (tap - kz * 9) / 3, kx = tap - kz * 9 - ky * 3;
+            const int z = 2 * zo - 1 + kz, y = 2 * yo - 1 + ky, xx = 2 * xo - 1 + kx;
+            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+            if ((unsigned)z < (unsigned)g.D && (unsigned)y < (unsigned)g.H && (unsigned)xx < (unsigned)g.W)
+                val = __ldg(src + (((int64_t)z * g.H + y) * g.W + xx) * cv + c8);
+            dst[j] = val;
+        }
     }
 }
 __device__ __forceinline__ void add_bf16x8(float *acc, uint4 v) {
@@ -560,9 +566,13 @@ int32_t b200surv_ct_im2col(const void *a_bf16, int64_t Bc, int32_t D, int32_t H,
     B200_REQUIRE(a_bf16 && col_bf16, "null pointer");
     B200_REQUIRE(Bc >= 1 && D >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "shape (C multiple of 8)");
     const Grid3 g = make_grid(D, H, W);
-    const int64_t total = Bc * (int64_t)g.Do * g.Ho * g.Wo * 27 * (C / 8);
-    k_im2col<<<blocks_for(total, 256 * 4, 16), 256, 0, as_stream(stream)>>>(static_cast<const bf16 *>(a_bf16), Bc, g, C,
-                                                                        static_cast<bf16 *>(col_bf16));
+    const int64_t rows = Bc * (int64_t)g.Do * g.Ho * g.Wo;       // one warp per row, 8 warps per CTA
+    const unsigned grid = blocks_for(rows, 8 * 4, 16);
+    const bf16 *ap = static_cast<const bf16 *>(a_bf16);
+    bf16 *cp = static_cast<bf16 *>(col_bf16);
+    if (C == 32) k_im2col<4><<<grid, 256, 0, as_stream(stream)>>>(ap, Bc, g, C, cp);
+    else if (C == 64) k_im2col<8><<<grid, 256, 0, as_stream(stream)>>>(ap, Bc, g, C, cp);
+    else k_im2col<0><<<grid, 256, 0, as_stream(stream)>>>(ap, Bc, g, C, cp);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }

@@ -209,3 +209,31 @@ def test_graphed_model_step_matches_eager():
         for k, v in m.state_dict().items():
             if "running" in k:
                 assert torch.equal(v, sd_e[k]), k
+
+
+@pytest.mark.parametrize("C", [8, 32, 64])
+def test_im2col_col2im_primitives(C):
+    """b200surv_ct_im2col against F.unfold-style patch extraction (tap-major columns) and b200surv_ct_col2im as its
+    exact adjoint: <im2col(a), d> == <a, col2im(d)>, checked element-wise against the autograd gradient."""
+    import torch.nn.functional as F
+    from multimodal_survival_prediction_b200 import _lib as L
+    dev = torch.device("cuda", 0)
+    L.require_device(0)
+    lib = L.load()
+    torch.manual_seed(C)
+    B, D, H, W = 2, 7, 10, 5
+    Do, Ho, Wo = (D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    a = torch.randn(B, D, H, W, C, device=dev).bfloat16()
+    col = torch.empty(B * Do * Ho * Wo, 27 * C, dtype=torch.bfloat16, device=dev)
+    st = L.stream_ptr(dev)
+    L.check(lib.b200surv_ct_im2col(L.ptr(a), B, D, H, W, C, L.ptr(col), st), "im2col")
+    af = a.float().requires_grad_(True)
+    pad = F.pad(af, (0, 0, 1, 1, 1, 1, 1, 1))                                    # pad W, H, D by 1 (channels last)
+    taps = [pad[:, kz:kz + 2 * Do:2, ky:ky + 2 * Ho:2, kx:kx + 2 * Wo:2, :] for kz in range(3) for ky in range(3) for kx in range(3)]
+    ref = torch.stack(taps, dim=4).reshape(B * Do * Ho * Wo, 27 * C)           # (b, zo, yo, xo, tap, c)
+    assert torch.equal(col.float(), ref.detach())
+    d = torch.randn_like(ref).bfloat16()
+    ref.backward(d.float())
+    da = torch.empty(B * D * H * W, C, device=dev)
+    L.check(lib.b200surv_ct_col2im(L.ptr(d), B, D, H, W, C, L.ptr(da), st), "col2im")
+    assert torch.allclose(da.view_as(af), af.grad, rtol=1e-5, atol=1e-5)
