@@ -111,6 +111,7 @@ struct Epilogue {
     int relu;
     int kb_per;             // split-K: k-blocks per grid.z slice (slice z writes c + z * split_stride)
     int64_t split_stride;
+    int staged;             // exactly one output, 16-byte aligned: rows are staged in shared memory and stored coalesced
 };
 
 // A_MN / B_MN: operand is stored [K][cols] (MN-major) instead of [rows][K] (K-major)
@@ -205,6 +206,55 @@ gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const int q = warp & 3;
         mbar_wait(smem_u32(bars + 2 * STAGES), 0);
         tcgen05_fence_after();
+        if (ep.staged) {
+            // Coalesced stores: lane = row after tcgen05.ld, so a direct store touches 32 rows per instruction (32 L1 tag
+            // cycles each; the wide dgrad outputs of the CT encoder were bound by exactly that).  Each warp stages its 32
+            // rows x 128 columns in the pipeline's shared memory (free: every MMA has retired) and stores whole rows.
+            const int ES = ep.c != nullptr ? 4 : 2, pitch = BN * ES + 16;
+            unsigned char *stg = tiles_a + (size_t)q * (32 * (BN * 4 + 16));
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+                const int col0 = tile_n * BN + c;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    if (ep.bias != nullptr && col0 + j < N) x += ep.bias[col0 + j];
+                    if (ep.relu) x = fmaxf(x, 0.f);
+                    f[j] = x;
+                }
+                if (ES == 4) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4 *>(stg + lane * pitch + (c + j) * 4) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]),
+                                       p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                        uint4 u;
+                        u.x = *reinterpret_cast<uint32_t *>(&p0); u.y = *reinterpret_cast<uint32_t *>(&p1);
+                        u.z = *reinterpret_cast<uint32_t *>(&p2); u.w = *reinterpret_cast<uint32_t *>(&p3);
+                        *reinterpret_cast<uint4 *>(stg + lane * pitch + (c + j) * 2) = u;
+                    }
+                }
+            }
+            __syncwarp();
+            const int lanes_per_row = BN * ES / 16, per_vec = 16 / ES;      // 32 (fp32) or 16 (bf16) lanes store one row
+            const int vec = lane % lanes_per_row, gcol = tile_n * BN + vec * per_vec;
+            for (int k = lane / lanes_per_row; k < 32; k += 32 / lanes_per_row) {
+                const int grow = tile_m * BM + q * 32 + k;
+                if (grow < M && gcol < N) {                                 // N is a multiple of per_vec: whole vector inside
+                    const uint4 u = *reinterpret_cast<const uint4 *>(stg + k * pitch + vec * 16);
+                    unsigned char *dst = ES == 4
+                        ? reinterpret_cast<unsigned char *>(ep.c + (int64_t)blockIdx.z * ep.split_stride + (int64_t)grow * ep.ldc + gcol)
+                        : reinterpret_cast<unsigned char *>(ep.c_bf16 + (int64_t)grow * ep.ldc_bf16 + gcol);
+                    *reinterpret_cast<uint4 *>(dst) = u;
+                }
+            }
+        } else {
         const int row = tile_m * BM + q * 32 + lane;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
@@ -247,6 +297,7 @@ gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                     }
                 }
             }
+        }
         }
     }
     tcgen05_fence_before();
@@ -346,6 +397,10 @@ int32_t gemm_bf16(const void *a, int64_t lda, int a_mn, const void *b, int64_t l
         splits = splitk_slices(M, N, K, &ep.kb_per);
         ep.c = splitk_ws; ep.split_stride = (int64_t)M * ldc;
     }
+    const bool only_f32 = ep.c != nullptr && ep.c_bf16 == nullptr, only_bf16 = ep.c == nullptr && ep.c_bf16 != nullptr;
+    ep.staged = (only_f32 && (N & 3) == 0 && (ldc & 3) == 0 && (ep.split_stride & 3) == 0 &&
+                 (reinterpret_cast<uintptr_t>(ep.c) & 15) == 0) ||
+                (only_bf16 && (N & 7) == 0 && (ldc_bf16 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.c_bf16) & 15) == 0);
     if (a_mn && b_mn) return launch<true, true>(ma, mb, M, N, K, ep, splits, st);
     if (a_mn && !b_mn) return launch<true, false>(ma, mb, M, N, K, ep, splits, st);
     if (!a_mn && b_mn) return launch<false, true>(ma, mb, M, N, K, ep, splits, st);
