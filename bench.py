@@ -13,7 +13,9 @@ each step (weak scaling; value = all rows / max-over-ranks time).
 Extra measurements on the same JSON line: `e2e` (public Python API, pinned host inputs, H2D + D2H in
 the timed region), `roofline` (dominant kernel, CUDA events), `cpu_baseline` (oracle port on the
 host cores), `extra.cindex_1m` (C-index on 1M patients, tile-sharded over the N ranks), `extra.head_b4096` (gated
-fusion head fwd+bwd, B = 4096), `extra.cv_sweep` (one GPU's share of the 5-fold CV sweep).
+fusion head fwd+bwd, B = 4096), `extra.cv_sweep` (one GPU's share of the 5-fold CV sweep), `extra.ct_encoder` (the CNN CT
+encoder fwd+bwd at B = 4 / 64 beside PyTorch/cuDNN on the same GPU), `extra.cfg1_batch4_step` (BASELINE.json configs[0]: one
+training step of the ungated net at batch 4 from host inputs, as one CUDA graph and call by call, CPU port beside it).
 `--impl reference` times the CPU port of the reference's loss (oracle/cox_torch.py) instead.
 """
 from __future__ import annotations

@@ -86,3 +86,21 @@ def test_shim_resolves_to_b200_kernels():
         sys.path.remove(os.path.join(ROOT, "shim"))
         for m in [m for m in sys.modules if m.startswith("torchsurv")]:
             del sys.modules[m]
+
+
+def test_ct_encoder_and_validation_cohort_have_no_cpu_path():
+    """The 8f widenings fail loudly without a B200, like the rest of the package; sizes are computable on the host."""
+    import torch
+    from multimodal_survival_prediction_b200 import B200SurvError, ValidationCohort, _lib as L
+    from multimodal_survival_prediction_b200.ctenc import CTEncoderCNN
+    lib = L.load()
+    assert lib.b200surv_ct_encoder_saved_bytes(4, 64, 64, 32) > 4 * 16384 * 32 * 4      # at least the stage-1 activations
+    assert lib.b200surv_ct_encoder_workspace_bytes(4, 64, 64, 32) > 0
+    assert lib.b200surv_ct_encoder_saved_bytes(0, 64, 64, 32) == 0
+    assert 1 <= lib.b200surv_gemm_splitk_slices(64, 864, 32768) <= 32
+    enc = CTEncoderCNN()
+    assert [k for k in enc.state_dict()][:2] == ["0.weight", "0.bias"] and enc[0].weight.shape == (32, 1, 3, 3, 3)
+    with pytest.raises(B200SurvError):
+        enc(torch.zeros(2, 1, 8, 8, 8))
+    with pytest.raises(B200SurvError):
+        ValidationCohort(capacity=8, device="cpu")
