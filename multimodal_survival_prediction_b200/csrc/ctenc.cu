@@ -45,6 +45,8 @@ inline unsigned blocks_for(int64_t items, int per_block, int max_per_sm) {
 // ---------------------------------------------------------------- first convolution (Cin = 1), direct
 // x fp32 [B][D][H][W]; w fp32 [Cout][27] (torch (Cout,1,3,3,3)); h fp32 [B*Do*Ho*Wo][Cout].  One thread = one output
 // voxel x 8 channels (Cout/8 neighbouring threads share the voxel and write 32 contiguous bytes each).
+// IDX: uint32_t when every index fits (64-bit divisions cost ~100 instructions each), else int64_t
+template <typename IDX>
 __global__ void __launch_bounds__(256)
 k_conv_first_fwd(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, int64_t B,
                  Grid3 g, int Cout, float *__restrict__ h) {
@@ -52,16 +54,16 @@ k_conv_first_fwd(const float *__restrict__ x, const float *__restrict__ w, const
     for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) { const int c = i % Cout, t = i / Cout; sw[i] = w[c * 27 + t]; }
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
     __syncthreads();
-    const int groups = Cout / 8;
-    const int64_t vox = (int64_t)g.Do * g.Ho * g.Wo, total = B * vox * groups;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const IDX groups = (IDX)(Cout / 8);
+    const IDX vox = (IDX)g.Do * g.Ho * g.Wo, total = (IDX)B * vox * groups;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
         const int cg = (int)(i % groups);
-        const int64_t r = i / groups;
-        const int64_t b = r / vox;
+        const IDX r = i / groups;
+        const IDX b = r / vox;
         int v = (int)(r - b * vox);
         const int xo = v % g.Wo; v /= g.Wo;
         const int yo = v % g.Ho, zo = v / g.Ho;
-        const float *xb = x + b * (int64_t)g.D * g.H * g.W;
+        const float *xb = x + (int64_t)b * g.D * g.H * g.W;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = sw[27 * Cout + cg * 8 + j];
@@ -83,7 +85,7 @@ k_conv_first_fwd(const float *__restrict__ x, const float *__restrict__ w, const
                 }
             }
         }
-        float4 *o = reinterpret_cast<float4 *>(h + r * Cout + cg * 8);
+        float4 *o = reinterpret_cast<float4 *>(h + (int64_t)r * Cout + cg * 8);
         o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
         o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
@@ -267,14 +269,16 @@ __device__ __forceinline__ void add_bf16x8(float *acc, uint4 v) {
 }
 // dcol bf16 [Bc*Do*Ho*Wo][27*C] -> da fp32 [Bc*D*H*W][C]: input voxel (z,y,x) receives tap (kz,ky,kx) of output voxel
 // ((z+1-kz)/2, ...) whenever that is an integer inside the output grid.
+template <typename IDX>
 __global__ void __launch_bounds__(256)
 k_col2im(const bf16 *__restrict__ dcol, int64_t Bc, Grid3 g, int C, float *__restrict__ da) {
-    const int cv = C / 8;
-    const int64_t vin = (int64_t)g.D * g.H * g.W, vox = (int64_t)g.Do * g.Ho * g.Wo, total = Bc * vin * cv;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const IDX cv = (IDX)(C / 8);
+    const IDX vin = (IDX)g.D * g.H * g.W, total = (IDX)Bc * vin * cv;
+    const int64_t vox = (int64_t)g.Do * g.Ho * g.Wo;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
         const int c8 = (int)(i % cv);
-        const int64_t p = i / cv;
-        const int64_t b = p / vin;
+        const IDX p = i / cv;
+        const IDX b = p / vin;
         int v = (int)(p - b * vin);
         const int xx = v % g.W; v /= g.W;
         const int y = v % g.H, z = v / g.H;
@@ -296,7 +300,7 @@ k_col2im(const bf16 *__restrict__ dcol, int64_t Bc, Grid3 g, int C, float *__res
                 }
             }
         }
-        float4 *o = reinterpret_cast<float4 *>(da + p * C + c8 * 8);
+        float4 *o = reinterpret_cast<float4 *>(da + (int64_t)p * C + c8 * 8);
         o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
         o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
@@ -433,7 +437,7 @@ k_bn_relu(const float *__restrict__ x, const float *__restrict__ mu, const float
           const float *__restrict__ gamma, const float *__restrict__ beta, int64_t R, int C, bf16 *__restrict__ y) {
     const int64_t nvec = R * C / 4;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
-        const int c0 = (int)((4 * v) % C);
+        const int c0 = (int)((4 * v) & (C - 1));      // C is a power of two
         const float4 xv = __ldg(reinterpret_cast<const float4 *>(x) + v);
         const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
         float o[4];
@@ -481,7 +485,7 @@ k_bn_dx(const float *__restrict__ x, const float *__restrict__ dA, const float *
     const int64_t nvec = R * C / 4;
     const float invR = 1.f / (float)R;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
-        const int c0 = (int)((4 * v) % C);
+        const int c0 = (int)((4 * v) & (C - 1));      // C is a power of two
         const float4 xv = __ldg(reinterpret_cast<const float4 *>(x) + v);
         const float4 dv = __ldg(reinterpret_cast<const float4 *>(dA) + v);
         const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
@@ -522,8 +526,12 @@ int32_t b200surv_ct_conv_first_fwd(const float *x, const float *w, const float *
     B200_REQUIRE(Cout >= 8 && Cout % 8 == 0 && Cout <= 256, "Cout must be a multiple of 8, <= 256");
     const Grid3 g = make_grid(D, H, W);
     const int64_t total = B * (int64_t)g.Do * g.Ho * g.Wo * (Cout / 8);
-    k_conv_first_fwd<<<blocks_for(total, 256, 16), 256, (size_t)28 * Cout * sizeof(float), as_stream(stream)>>>(
-        x, w, bias, B, g, Cout, h);
+    if (total < ((int64_t)1 << 30))
+        k_conv_first_fwd<uint32_t><<<blocks_for(total, 256, 16), 256, (size_t)28 * Cout * sizeof(float), as_stream(stream)>>>(
+            x, w, bias, B, g, Cout, h);
+    else
+        k_conv_first_fwd<int64_t><<<blocks_for(total, 256, 16), 256, (size_t)28 * Cout * sizeof(float), as_stream(stream)>>>(
+            x, w, bias, B, g, Cout, h);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -583,7 +591,10 @@ int32_t b200surv_ct_col2im(const void *dcol_bf16, int64_t Bc, int32_t D, int32_t
     B200_REQUIRE(Bc >= 1 && D >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "shape (C multiple of 8)");
     const Grid3 g = make_grid(D, H, W);
     const int64_t total = Bc * (int64_t)D * H * W * (C / 8);
-    k_col2im<<<blocks_for(total, 256 * 2, 16), 256, 0, as_stream(stream)>>>(static_cast<const bf16 *>(dcol_bf16), Bc, g, C, da);
+    if (total < ((int64_t)1 << 30))
+        k_col2im<uint32_t><<<blocks_for(total, 256 * 2, 16), 256, 0, as_stream(stream)>>>(static_cast<const bf16 *>(dcol_bf16), Bc, g, C, da);
+    else
+        k_col2im<int64_t><<<blocks_for(total, 256 * 2, 16), 256, 0, as_stream(stream)>>>(static_cast<const bf16 *>(dcol_bf16), Bc, g, C, da);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
