@@ -10,7 +10,13 @@ SURVEY.md section 6); the exact int64 counters stay available on the object.
 Unverifiable torchsurv conventions are explicit: ``convention="harrell"`` is
 (C + T/2)/(C + D + T) over strict pairs plus same-time event-vs-censored pairs with
 ``tied_tol=1e-8`` on |estimate difference|; ``convention="fallback"`` is the reference's in-repo rule
-(simple_fusion.py:59-73: strict pairs only, no credit for risk ties, 0.5 when nothing is comparable).
+(simple_fusion.py:59-73: strict pairs only, no credit for risk ties, 0.5 when nothing is comparable);
+``convention="lifelines"`` is the rule of ``lifelines.utils.concordance_index`` -- the reference's other
+fallback, ``concordance_index(time, -hazard, event)`` at partial_modality_training.py:313-319 and
+scripts/analysis/evaluate_model.py:41-45: the same comparable pairs as "harrell" (an event row against every
+later row and against the censored rows of its own time), risk ties by EXACT equality (``tied_tol`` is ignored:
+the counters are taken with tolerance 0), float64 result, ZeroDivisionError when nothing is comparable.
+``concordance_index_lifelines`` below keeps that function's signature (``shim/lifelines``).
 """
 from __future__ import annotations
 
@@ -93,7 +99,13 @@ def cindex_from_counts(counts, convention="harrell"):
     if convention == "fallback":
         den = c[0] + c[1] + c[2]
         return c[0] / den if den > 0 else 0.5
-    raise ValueError("convention must be 'harrell' or 'fallback'")
+    if convention == "lifelines":      # counters taken with tied_tol = 0; (correct + tied / 2) / pairs
+        C, D, T = c[0] + c[3], c[1] + c[4], c[2] + c[5]
+        den = C + D + T
+        if den == 0:
+            raise ZeroDivisionError("No admissable pairs in the dataset.")
+        return (C + T / 2) / den
+    raise ValueError("convention must be 'harrell', 'fallback' or 'lifelines'")
 
 
 class ConcordanceIndex:
@@ -134,11 +146,80 @@ class ConcordanceIndex:
         est = estimate.detach().to(device=dev, dtype=torch.float32).contiguous()
         t = time.detach().to(device=dev, dtype=torch.float32).contiguous()
         e = event.detach().to(device=dev).contiguous()
+        tol = 0.0 if self.convention == "lifelines" else self.tied_tol
         if est.numel() == 0:
             self.counts = [0] * 6
         else:
             with torch.cuda.device(dev):
-                self.counts = cindex_counts(est, e, t, self.tied_tol, algo=self.algo).cpu().tolist()
-        self.cindex = torch.tensor(cindex_from_counts(self.counts, self.convention), dtype=torch.float32,
-                                   device=src_dev)
+                self.counts = cindex_counts(est, e, t, tol, algo=self.algo).cpu().tolist()
+        # torchsurv returns float32; lifelines returns a float64 scalar
+        out_dtype = torch.float64 if self.convention == "lifelines" else torch.float32
+        self.cindex = torch.tensor(cindex_from_counts(self.counts, self.convention), dtype=out_dtype, device=src_dev)
         return self.cindex
+
+
+def _as_f32_exact(x, dev, what):
+    """Host array / Series / tensor -> fp32 device vector with the same order and equality pattern.
+
+    lifelines compares in float64.  fp32 input (the reference hands over ``hazard.cpu().numpy()``,
+    partial_modality_training.py:317) converts exactly.  float64 values that are not fp32-representable (risk scores
+    read back from a CSV, evaluate_model.py:41-45) are replaced by their dense ranks, which keeps every ``<`` and
+    ``==`` the pair counters evaluate (ranks are exact in fp32 up to 2^24 distinct values)."""
+    import numpy as np
+    if isinstance(x, torch.Tensor):
+        v = x.detach()
+    else:
+        a = np.asarray(x)
+        if a.dtype == object or a.dtype.kind not in "fiub":
+            a = a.astype(np.float64)
+        v = torch.from_numpy(np.ascontiguousarray(a))
+    v = v.reshape(-1) if v.dim() == 2 and 1 in v.shape else v
+    if v.dim() != 1:
+        raise ValueError(f"'{what}' should be one-dimensional")
+    v = v.to(dev)
+    if v.dtype in (torch.float32, torch.float16, torch.bfloat16, torch.bool, torch.uint8, torch.int8, torch.int16):
+        return v.to(torch.float32)
+    v64 = v.to(torch.float64)
+    if bool(torch.isnan(v64).any()):
+        raise ValueError("NaNs detected in inputs, please correct or drop.")
+    v32 = v64.to(torch.float32)
+    if bool((v32.to(torch.float64) == v64).all()):
+        return v32
+    uniq, inv = torch.unique(v64, sorted=True, return_inverse=True)
+    if uniq.numel() > (1 << 24):
+        raise L.B200SurvError(f"'{what}': more than 2^24 distinct float64 values that are not fp32-representable")
+    return inv.to(torch.float32)
+
+
+def concordance_index_lifelines(event_times, predicted_scores, event_observed=None) -> float:
+    """``lifelines.utils.concordance_index(event_times, predicted_scores, event_observed=None)`` on the B200.
+
+    The reference's call is ``concordance_index(time, -hazard, event)`` (partial_modality_training.py:313-319,
+    scripts/analysis/evaluate_model.py:41-45): ``predicted_scores`` are higher for LONGER survival, so the pair
+    counters run on ``estimate = -predicted_scores`` (negation is exact) with tolerance 0.  Returns a Python
+    float formed in float64, raises ``ZeroDivisionError`` when no pair is comparable and ``ValueError`` on NaNs or
+    mismatched lengths, like lifelines.  Infinite scores are rejected (lifelines would compare them as equal;
+    the fp32 pair predicate cannot)."""
+    if not torch.cuda.is_available():
+        raise L.B200SurvError("no CUDA device: the B200 survival kernels have no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for x in (event_times, predicted_scores, event_observed):
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            dev = x.device
+            break
+    with torch.cuda.device(dev):
+        t = _as_f32_exact(event_times, dev, "event_times")
+        s = _as_f32_exact(predicted_scores, dev, "predicted_scores")
+        if event_observed is None:
+            e = torch.ones(t.numel(), dtype=torch.bool, device=dev)
+        else:
+            e = _as_f32_exact(event_observed, dev, "event_observed") != 0
+        if not (t.numel() == s.numel() == e.numel()):
+            raise ValueError("Observed events must be 1-dimensional of same length as event times")
+        if bool(torch.isnan(t).any()) or bool(torch.isnan(s).any()):
+            raise ValueError("NaNs detected in inputs, please correct or drop.")
+        if bool(torch.isinf(s).any()):
+            raise ValueError("infinite predicted_scores are not supported")
+        counts = [0] * 6 if t.numel() == 0 else cindex_counts((-s).contiguous(), e.contiguous(), t.contiguous(),
+                                                              0.0).cpu().tolist()
+    return float(cindex_from_counts(counts, "lifelines"))
