@@ -78,8 +78,16 @@ const char *b200surv_last_error(void);
                                          >= 2^30): re-run with shift near max_log_hz (header)    */
 #define B200SURV_COXF_BAD_TIME 4u     /* NaN or negative time                                     */
 #define B200SURV_COXF_PEER_TIMEOUT 8u /* b200surv_cox_binned_fwd_peer: a peer rank never arrived   */
+#define B200SURV_COXF_LOW_PRECISION 16u /* BINNED: a row's weight exp(log_hz - shift) is below 2^-16, i.e.
+                                         under 2^12 quanta of the 36.28 fixed point (min(log_hz) - shift <
+                                         -11.09): a risk set made of such rows would lose precision or
+                                         round to zero.  Re-run with a larger shift if the spread allows,
+                                         else with SORTED (fp64).  The loss is poisoned with NaN.        */
 
-/* One header per segment at the start of the state buffer (device memory, 64 bytes each). */
+/* One 64-byte header per segment in the state buffer (device memory).  SMALL and SORTED: the n_seg headers are
+ * contiguous at the start of the buffer.  BINNED: segment s owns the slice [s * stride, (s + 1) * stride) with
+ * stride = b200surv_cox_state_bytes(n, 1, BINNED, nbins) = 64 + 8 * nbins; its header is the first 64 bytes of
+ * that slice, the (P, F) table follows. */
 typedef struct {
     uint32_t flags;        /* B200SURV_COXF_* */
     int32_t mode;
@@ -92,7 +100,8 @@ typedef struct {
     int64_t n_events;
     int64_t n_event_times; /* distinct times carrying at least one event */
     double pll;            /* partial log-likelihood before reduction */
-    int64_t reserved;
+    float min_log_hz;      /* BINNED only (else 0) */
+    int32_t reserved;
 } b200surv_cox_header;
 
 /* Bytes of caller-owned state (kept from fwd to bwd) and scratch workspace. */

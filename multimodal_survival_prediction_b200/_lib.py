@@ -15,7 +15,7 @@ REDUCE_MEAN_TERMS, REDUCE_SUM, REDUCE_MEAN_EVENTS = 0, 1, 2
 COX_SMALL, COX_BINNED, COX_SORTED = 1, 2, 3
 COX_SMALL_MAX = 2048
 COX_MAX_BINS = 8192
-COXF_NOT_BINNABLE, COXF_EXP_RANGE, COXF_BAD_TIME, COXF_PEER_TIMEOUT = 1, 2, 4, 8
+COXF_NOT_BINNABLE, COXF_EXP_RANGE, COXF_BAD_TIME, COXF_PEER_TIMEOUT, COXF_LOW_PRECISION = 1, 2, 4, 8, 16
 COX_HEADER_BYTES = 64
 
 
@@ -27,7 +27,7 @@ class CoxHeader(ctypes.Structure):
     _fields_ = [("flags", ctypes.c_uint32), ("mode", c_int32), ("loss", c_float), ("scale", c_float),
                 ("shift", c_float), ("max_log_hz", c_float), ("max_time", c_float), ("nbins", c_int32),
                 ("n_events", c_int64), ("n_event_times", c_int64), ("pll", ctypes.c_double),
-                ("reserved", c_int64)]
+                ("min_log_hz", c_float), ("reserved", c_int32)]
 
 
 assert ctypes.sizeof(CoxHeader) == COX_HEADER_BYTES
@@ -118,6 +118,20 @@ HEAD_TRAIN_SEED_DEV = 2
 
 _lib = None
 _arch_ok = set()
+CALLS: dict = {}            # entry point -> number of calls that went through check() in this process
+
+
+def _dump_calls():
+    path = os.environ.get("B200SURV_STATS_FILE")
+    if path:
+        import json
+        with open(path, "w") as fh:
+            json.dump({"calls": CALLS, "library": LIB_PATH, "loaded": _lib is not None}, fh)
+
+
+if os.environ.get("B200SURV_STATS_FILE"):      # the script harness reads this to show which entry points a run used
+    import atexit
+    atexit.register(_dump_calls)
 
 
 def load():
@@ -138,6 +152,7 @@ def load():
 
 
 def check(rc: int, what: str):
+    CALLS[what] = CALLS.get(what, 0) + 1
     if rc != OK:
         msg = load().b200surv_last_error()
         raise B200SurvError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")

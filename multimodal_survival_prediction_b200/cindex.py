@@ -151,7 +151,15 @@ class ConcordanceIndex:
             self.counts = [0] * 6
         else:
             with torch.cuda.device(dev):
-                self.counts = cindex_counts(est, e, t, tol, algo=self.algo).cpu().tolist()
+                counts = cindex_counts(est, e, t, tol, algo=self.algo)
+                if self.checks:     # negative / NaN times: the check rides on the counters' device->host copy (one sync)
+                    bad = torch.logical_not(t >= 0).any().to(torch.int64).reshape(1)
+                    host = torch.cat([counts, bad]).cpu().tolist()
+                    if host[6]:
+                        raise ValueError("Input 'time' should be non-negative and free of NaN")
+                    self.counts = host[:6]
+                else:
+                    self.counts = counts.cpu().tolist()
         # torchsurv returns float32; lifelines returns a float64 scalar
         out_dtype = torch.float64 if self.convention == "lifelines" else torch.float32
         self.cindex = torch.tensor(cindex_from_counts(self.counts, self.convention), dtype=out_dtype, device=src_dev)

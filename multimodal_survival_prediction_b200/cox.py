@@ -74,9 +74,16 @@ def _device_for(*tensors):
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def read_headers(state: torch.Tensor, n_seg: int):
-    """Device->host copy of the per-segment headers (synchronises the stream)."""
-    raw = state[: n_seg * L.COX_HEADER_BYTES].cpu().numpy().tobytes()
+def read_headers(state: torch.Tensor, n_seg: int, mode: int = L.COX_SMALL):
+    """Device->host copy of the per-segment headers (synchronises the stream).
+
+    SMALL / SORTED keep the n_seg headers contiguous at the start of ``state``; BINNED interleaves them with the
+    (P, F) tables: segment s's header starts at ``s * state.numel() // n_seg`` (include/b200surv.h)."""
+    if mode == L.COX_BINNED and n_seg > 1:
+        stride = state.numel() // n_seg
+        raw = state.view(n_seg, stride)[:, : L.COX_HEADER_BYTES].contiguous().cpu().numpy().tobytes()
+    else:
+        raw = state[: n_seg * L.COX_HEADER_BYTES].cpu().numpy().tobytes()
     return [L.CoxHeader.from_buffer_copy(raw, i * L.COX_HEADER_BYTES) for i in range(n_seg)]
 
 
@@ -110,9 +117,12 @@ def cox_bwd_raw(grad_out, state, log_hz, time, event, seg_offsets, n_seg, mode, 
     return out
 
 
-def _plan_and_run(log_hz, time, event, seg_offsets, n_seg, max_seg, ties, reduction, mode, nbins):
-    """Mode policy.  Explicit modes never synchronise; "auto" reads the 64-byte header back once
-    (torchsurv itself synchronises on event.sum() and torch.unique)."""
+LOWP_MIN = -11.090354888959125      # -16 ln 2: B200SURV_COXF_LOW_PRECISION threshold on min(log_hz) - shift
+
+
+def _plan_and_run(log_hz, time, event, seg_offsets, n_seg, max_seg, ties, reduction, mode, nbins, checks=True):
+    """Mode policy.  Explicit modes never synchronise (unless ``checks`` asks for the SMALL header); "auto" reads the
+    64-byte headers back once (torchsurv itself synchronises on event.sum() and torch.unique)."""
     n = log_hz.numel()
     if mode != 0:
         nb = nbins or DEFAULT_NBINS
@@ -120,13 +130,16 @@ def _plan_and_run(log_hz, time, event, seg_offsets, n_seg, max_seg, ties, reduct
         return loss, state, mode, nb
     if max_seg <= L.COX_SMALL_MAX:
         loss, state = cox_fwd_raw(log_hz, time, event, seg_offsets, n_seg, ties, reduction, L.COX_SMALL, 0)
+        if checks:      # like the larger cohorts: bad times raise instead of returning a silent NaN
+            if any(h.flags & L.COXF_BAD_TIME for h in read_headers(state, n_seg, L.COX_SMALL)):
+                raise ValueError("Input 'time' should be non-negative and free of NaN")
         return loss, state, L.COX_SMALL, 0
     nb = nbins or DEFAULT_NBINS
     shift = 0.0
     for _attempt in range(4):
         loss, state = cox_fwd_raw(log_hz, time, event, seg_offsets, n_seg, ties, reduction, L.COX_BINNED, nb,
                                   shift)
-        hdrs = read_headers(state, n_seg)
+        hdrs = read_headers(state, n_seg, L.COX_BINNED)
         flags = 0
         for h in hdrs:
             flags |= h.flags
@@ -139,10 +152,14 @@ def _plan_and_run(log_hz, time, event, seg_offsets, n_seg, max_seg, ties, reduct
                 nb = L.COX_MAX_BINS
                 continue
             break
-        if flags & L.COXF_EXP_RANGE:
+        if flags & (L.COXF_EXP_RANGE | L.COXF_LOW_PRECISION):
             # largest weight 2^k with n * 2^k <= 2^29: full fixed-point precision without overflow
             k = min(28, max(0, 29 - max(1, (n - 1).bit_length())))
-            shift = max(h.max_log_hz for h in hdrs) - k * 0.6931471805599453
+            new_shift = max(h.max_log_hz for h in hdrs) - k * 0.6931471805599453
+            lo = min(h.min_log_hz for h in hdrs)
+            if not (lo - new_shift >= LOWP_MIN) or new_shift == shift:
+                break       # the spread of log_hz does not fit the fixed point at any shift: fp64 path
+            shift = new_shift
             continue
     if n_seg != 1:
         raise L.B200SurvError("segmented cohorts larger than 2048 rows need integer day counts < 8192 "
@@ -153,14 +170,15 @@ def _plan_and_run(log_hz, time, event, seg_offsets, n_seg, max_seg, ties, reduct
 
 class _CoxNLL(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, log_hz, event, time, seg_offsets, n_seg, max_seg, ties, reduction, mode, nbins):
+    def forward(ctx, log_hz, event, time, seg_offsets, n_seg, max_seg, ties, reduction, mode, nbins, checks=True):
         dev = _device_for(log_hz, time, event)
         x = log_hz.detach().reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
         t = time.detach().to(device=dev, dtype=torch.float32).contiguous()
         e = event.detach().to(device=dev).contiguous()
         so = None if seg_offsets is None else seg_offsets.to(device=dev, dtype=torch.int64).contiguous()
         with torch.cuda.device(dev):
-            loss, state, used_mode, nb = _plan_and_run(x, t, e, so, n_seg, max_seg, ties, reduction, mode, nbins)
+            loss, state, used_mode, nb = _plan_and_run(x, t, e, so, n_seg, max_seg, ties, reduction, mode, nbins,
+                                                       checks)
         ctx.save_for_backward(x, t, e, state, so if so is not None else torch.empty(0, device=dev))
         ctx.meta = (n_seg, used_mode, nb, log_hz.shape, log_hz.dtype, log_hz.device, so is not None)
         return loss.to(log_hz.device)
@@ -173,7 +191,7 @@ class _CoxNLL(torch.autograd.Function):
         with torch.cuda.device(x.device):
             grad = cox_bwd_raw(g, state, x, t, e, so if has_so else None, n_seg, mode, nb)
         grad = grad.reshape(shape).to(device=src_dev, dtype=dtype)
-        return grad, None, None, None, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None, None, None, None
 
 
 def neg_partial_log_likelihood(log_hz, event, time, ties_method="efron", reduction="mean", checks=True, *,
@@ -190,7 +208,7 @@ def neg_partial_log_likelihood(log_hz, event, time, ties_method="efron", reducti
         return log_hz.sum() * 0.0
     ties = _ties_code(ties_method)
     red = _reduction_code(ties_method, reduction, efron_mean_over)
-    loss = _CoxNLL.apply(log_hz, event, time, None, 1, n, ties, red, _MODES[mode], nbins)
+    loss = _CoxNLL.apply(log_hz, event, time, None, 1, n, ties, red, _MODES[mode], nbins, bool(checks))
     return loss.reshape(())
 
 
@@ -212,4 +230,5 @@ def neg_partial_log_likelihood_segmented(log_hz, event, time, seg_offsets, ties_
         raise ValueError("empty segments are not allowed")
     ties = _ties_code(ties_method)
     red = _reduction_code(ties_method, reduction, efron_mean_over)
-    return _CoxNLL.apply(log_hz, event, time, so_host, n_seg, int(lens.max()), ties, red, _MODES[mode], nbins)
+    return _CoxNLL.apply(log_hz, event, time, so_host, n_seg, int(lens.max()), ties, red, _MODES[mode], nbins,
+                         bool(checks))

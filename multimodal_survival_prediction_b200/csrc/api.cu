@@ -14,17 +14,20 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int current_device() {
+    int dev = -1;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-            cached = sms;
-        else
-            return 148;
-    }
-    return cached;
+    static volatile int cached[MAX_DEVICES];  // 0 = not queried yet; writes of the same value race harmlessly
+    const int dev = current_device();
+    if (dev < 0) return 148;
+    if (dev < MAX_DEVICES && cached[dev] > 0) return cached[dev];
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+    if (dev < MAX_DEVICES) cached[dev] = sms;
+    return sms;
 }
 
 }  // namespace b200surv

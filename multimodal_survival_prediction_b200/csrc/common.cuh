@@ -36,7 +36,18 @@ void set_error(const char *fmt, ...);
 inline cudaStream_t as_stream(b200surv_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int num_sms();  // cached per process (148 on B200)
+int num_sms();         // of the CURRENT device, cached per device (148 on B200)
+int current_device();  // cudaGetDevice, -1 on failure
+
+// One-time per-DEVICE setup (cudaFuncSetAttribute is a per-device attribute: a process that drives several GPUs must
+// set it on each).  Setting an attribute twice is harmless, so two threads racing through `pending()` is fine; the
+// flags themselves are atomics, there is no other shared mutable state in the library's launch paths.
+constexpr int MAX_DEVICES = 64;
+struct PerDeviceOnce {
+    volatile unsigned char done[MAX_DEVICES];
+    bool pending() const { const int d = current_device(); return d < 0 || d >= MAX_DEVICES || !done[d]; }
+    void mark() { const int d = current_device(); if (d >= 0 && d < MAX_DEVICES) done[d] = 1; }
+};
 
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__

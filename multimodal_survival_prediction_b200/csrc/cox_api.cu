@@ -1,4 +1,6 @@
 // extern "C" entry points for the Cox loss and the C-index (declared in include/b200surv.h).
+#include <mutex>
+
 #include "common.cuh"
 
 namespace b200surv {
@@ -46,8 +48,10 @@ struct CohortLanes {
 CohortLanes *cohort_lanes() {
     static CohortLanes pool[64];
     static int state[64];  // 0 = not tried, 1 = ready, -1 = failed
+    static std::mutex mu;  // lazily built once per device; two host threads may arrive together
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
     if (state[dev] == 0) {
         bool ok = cudaEventCreateWithFlags(&pool[dev].fork, cudaEventDisableTiming) == cudaSuccess;
         for (int j = 0; ok && j < COHORT_LANES; ++j)

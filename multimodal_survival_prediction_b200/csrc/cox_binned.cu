@@ -51,12 +51,15 @@ constexpr double ETA_INV = 1.0 / 16777216.0;
 // shift is suitable when -8 <= max(log_hz) - shift <= 20 and the sum of weights stays below 2^30
 constexpr float SHIFT_HI = 20.f, SHIFT_LO = -8.f;
 constexpr double SUMW_LIMIT = 1073741824.0;      // 2^30
+// a weight below 2^12 quanta (2^-16) carries a rounding error above 1e-4 of itself, and below half a quantum it is
+// zero: min(log_hz) - shift < -16 ln 2 raises LOW_PRECISION (a late risk set made of such rows would be wrong)
+constexpr float LOWP_MIN = -11.090354888959125f;
 
 struct CtaRec {
     double sum_ev_eta;  // sum of log_hz over this CTA's event rows
     double sum_w;       // sum of weights (overflow guard)
-    float max_eta;
-    unsigned flags;
+    float max_eta, min_eta;
+    unsigned flags, pad;
 };
 
 struct SegRange {
@@ -89,7 +92,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 
 // ================================================================ K1: pass 1
 struct P1Acc {
-    float se, mx, sw;  // sum of the event rows' log_hz, max log_hz, sum of the weights (overflow guard)
+    float se, mx, mn, sw;  // sum of the event rows' log_hz, max / min log_hz, sum of the weights (overflow guard)
     bool notbin;   // a row was not an integer in [0, nbins) (also raised by NaN / negative times)
     bool badt;     // NaN or negative time: only looked for once notbin is up (cold path, see p1_bad_times)
 };
@@ -108,6 +111,7 @@ __device__ __forceinline__ P1Row p1_prep(float eta, float t, bool ev, float c2, 
     const float wq = ex2_approx(fmaf(eta, LOG2E, c2));
     const unsigned long long q = __float2ull_rn(wq);
     acc.mx = fmaxf(acc.mx, eta);
+    acc.mn = fminf(acc.mn, eta);
     acc.sw += wq;
     acc.se += ev ? eta : 0.f;
     int bin = __float2int_rz(t);
@@ -183,10 +187,11 @@ __device__ __forceinline__ void pass1_flush(const unsigned *h, const P1Acc &acc,
     const double sw = block_reduce<double>(sw_d * FIX_INV, 0.0, OpAddD(), red_d);
     const double se = block_reduce<double>(se_d, 0.0, OpAddD(), red_d);
     const float mx = block_reduce<float>(acc.mx, -INFINITY, OpMaxF(), red_f);
+    const float mn = -block_reduce<float>(-acc.mn, -INFINITY, OpMaxF(), red_f);
     const unsigned fl = block_reduce<unsigned>(flags, 0u, OpOrU(), red_u);
     if (threadIdx.x == 0) {
         CtaRec rec;
-        rec.sum_ev_eta = se; rec.sum_w = sw; rec.max_eta = mx; rec.flags = fl;
+        rec.sum_ev_eta = se; rec.sum_w = sw; rec.max_eta = mx; rec.min_eta = mn; rec.flags = fl; rec.pad = 0;
         recs[(size_t)seg * nctas + cta] = rec;
     }
 }
@@ -207,7 +212,7 @@ __device__ __forceinline__ void pass1_body(const float *__restrict__ log_hz, con
     const float c2 = (float)FIX_BITS - shift * LOG2E;
     const unsigned nbu = (unsigned)nb;
     const uint32_t h_addr = (uint32_t)__cvta_generic_to_shared(h);
-    P1Acc acc{0.f, -INFINITY, 0.f, false, false};
+    P1Acc acc{0.f, -INFINITY, INFINITY, 0.f, false, false};
     double se_d = 0.0, sw_d = 0.0;  // per-thread fp32 partials are folded into fp64 every iteration
 
     // 128-bit groups, two per thread per iteration (all six loads issued before any use)
@@ -283,7 +288,7 @@ __device__ __forceinline__ void pass1_body_tma(const float *__restrict__ log_hz,
     const float c2 = (float)FIX_BITS - shift * LOG2E;
     const unsigned nbu = (unsigned)nb;
     const uint32_t h_addr = smem_addr_u32(h);
-    P1Acc acc{0.f, -INFINITY, 0.f, false, false};
+    P1Acc acc{0.f, -INFINITY, INFINITY, 0.f, false, false};
     double se_d = 0.0, sw_d = 0.0;
     const int64_t ntiles = n / TMA_TILE;  // full tiles; the remainder goes through direct loads below
     if (warp == P1_THREADS / 32 - 1) {
@@ -362,7 +367,7 @@ __device__ __forceinline__ void pass1_body_ring(const float *__restrict__ log_hz
     const uint32_t h_addr = smem_addr_u32(h);
     const uint32_t ring = smem_addr_u32(smem_raw + tma_hist_bytes(nb));
     const uint32_t my_e = ring + 16u * t, my_t = ring + 16u * P1_THREADS + 16u * t, my_v = ring + 32u * P1_THREADS + 4u * t;
-    P1Acc acc{0.f, -INFINITY, 0.f, false, false};
+    P1Acc acc{0.f, -INFINITY, INFINITY, 0.f, false, false};
     double se_d = 0.0, sw_d = 0.0;
     const int64_t ngroups = n >> 2, stride = (int64_t)nctas * P1_THREADS;
     const int64_t g0 = (int64_t)cta * P1_THREADS + t;
@@ -564,20 +569,20 @@ cox_binned_reduce(const unsigned char *__restrict__ partial, const CtaRec *__res
     }
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         double se = 0.0, sw = 0.0;
-        float mx = -INFINITY;
+        float mx = -INFINITY, nmn = -INFINITY;
         unsigned fl = 0;
         for (int c = threadIdx.x; c < nctas; c += 32) {
             const CtaRec r = recs[(size_t)seg * nctas + c];
-            se += r.sum_ev_eta; sw += r.sum_w; mx = fmaxf(mx, r.max_eta); fl |= r.flags;
+            se += r.sum_ev_eta; sw += r.sum_w; mx = fmaxf(mx, r.max_eta); nmn = fmaxf(nmn, -r.min_eta); fl |= r.flags;
         }
-        se = warp_sum(se); sw = warp_sum(sw); mx = warp_max(mx); fl = warp_or(fl);
+        se = warp_sum(se); sw = warp_sum(sw); mx = warp_max(mx); nmn = warp_max(nmn); fl = warp_or(fl);
         if (threadIdx.x == 0) {
             bs[3 * (size_t)nb + 0] = __double2ll_rn(se * ETA_SCALE);
             bs[3 * (size_t)nb + 1] = (fl & B200SURV_COXF_NOT_BINNABLE) ? 1 : 0;
             bs[3 * (size_t)nb + 2] = (long long)fmin(ceil(sw), 9.0e18);
             bs[3 * (size_t)nb + 3] = (fl & B200SURV_COXF_BAD_TIME) ? 1 : 0;
             bins_max[2 * seg + 0] = mx;
-            bins_max[2 * seg + 1] = -1.f;  // reserved
+            bins_max[2 * seg + 1] = nmn;  // MINUS the smallest log_hz (so that a MAX all-reduce combines both words)
         }
     }
 }
@@ -590,7 +595,7 @@ __host__ __device__ inline size_t seg_state_stride(int nb) {
 
 struct HeaderIn {
     long long sum_ev_eta_q, n_not_binnable, sum_w_ceil, n_bad_time;  // the four scalar words of the per-bin sums
-    float max_eta;
+    float max_eta, min_eta;
     long long n_events, n_times;
     double T;  // sum over the bins of m log D + sum_l log x_l
     int peer_timeout;
@@ -609,13 +614,14 @@ __device__ __forceinline__ void write_header(const HeaderIn &h, int efron, int r
     if (!(mx - shift <= SHIFT_HI) || !(mx - shift >= SHIFT_LO) || (double)h.sum_w_ceil >= SUMW_LIMIT)
         flags |= B200SURV_COXF_EXP_RANGE;
     if (h.peer_timeout) flags |= B200SURV_COXF_PEER_TIMEOUT;
+    if (h.min_eta - shift < LOWP_MIN) flags |= B200SURV_COXF_LOW_PRECISION;
     float loss = 0.f, scale = 0.f;
     if (h.n_events > 0) { loss = (float)(-pll / norm); scale = (float)(-1.0 / norm); }
     if (flags) { loss = __int_as_float(0x7fc00000); scale = loss; }
     hdr->flags = flags; hdr->mode = B200SURV_COX_BINNED; hdr->loss = loss; hdr->scale = scale;
     hdr->shift = shift; hdr->max_log_hz = mx; hdr->max_time = -1.f;
     hdr->nbins = nb; hdr->n_events = h.n_events; hdr->n_event_times = h.n_times; hdr->pll = pll;
-    hdr->reserved = 0;
+    hdr->min_log_hz = h.min_eta; hdr->reserved = 0;
     *out_loss = loss;
 }
 
@@ -696,7 +702,7 @@ cox_binned_finish(const long long *__restrict__ bins, const float *__restrict__ 
         HeaderIn h;
         h.sum_ev_eta_q = bs[3 * (size_t)nb]; h.n_not_binnable = bs[3 * (size_t)nb + 1];
         h.sum_w_ceil = bs[3 * (size_t)nb + 2]; h.n_bad_time = bs[3 * (size_t)nb + 3];
-        h.max_eta = bins_max[2 * seg];
+        h.max_eta = bins_max[2 * seg]; h.min_eta = -bins_max[2 * seg + 1];
         h.n_events = s_ne; h.n_times = s_nt; h.T = run_t; h.peer_timeout = 0;
         write_header(h, efron ? 1 : 0, reduction, shift, nb, reinterpret_cast<b200surv_cox_header *>(seg_state),
                      out_loss + seg);
@@ -958,19 +964,20 @@ __device__ __noinline__ void tail_header(const TailArgs &a, int lane) {
     HeaderIn h;
     {  // this rank's scalar words, from its CTA records
         double se = 0.0, sw = 0.0;
-        float mx = -INFINITY;
+        float mx = -INFINITY, nmn = -INFINITY;
         unsigned fl = 0;
         for (int c = lane; c < a.nparts; c += 32) {
             const CtaRec *rp = a.recs + c;
             se += __ldcg(&rp->sum_ev_eta); sw += __ldcg(&rp->sum_w); mx = fmaxf(mx, __ldcg(&rp->max_eta));
+            nmn = fmaxf(nmn, -__ldcg(&rp->min_eta));
             fl |= __ldcg(&rp->flags);
         }
-        se = warp_sum(se); sw = warp_sum(sw); mx = warp_max(mx); fl = warp_or(fl);
+        se = warp_sum(se); sw = warp_sum(sw); mx = warp_max(mx); nmn = warp_max(nmn); fl = warp_or(fl);
         h.sum_ev_eta_q = __double2ll_rn(se * ETA_SCALE);
         h.n_not_binnable = (fl & B200SURV_COXF_NOT_BINNABLE) ? 1 : 0;
         h.sum_w_ceil = (long long)fmin(ceil(sw), 1.0e18);  // (fits the 62-bit words of the multi-GPU exchange)
         h.n_bad_time = (fl & B200SURV_COXF_BAD_TIME) ? 1 : 0;
-        h.max_eta = mx;
+        h.max_eta = mx; h.min_eta = -nmn;
     }
     int peer_timeout = a.peer_timeout;
     if (a.peer != nullptr) {  // add the other ranks' scalar words (lanes 0..3), maximum of max log_hz over the ranks
@@ -990,8 +997,15 @@ __device__ __noinline__ void tail_header(const TailArgs &a, int lane) {
         if (lane < a.peer->world && lane != a.peer->rank)
             st_relaxed_sys_u64(reinterpret_cast<unsigned long long *>(a.peer->buf[lane]) + slot_words +
                                    (size_t)a.peer->rank * peer_src_words(a.nb) + word,
-                               (unsigned long long)__float_as_uint(h.max_eta) | tag);
-        float mx = h.max_eta;
+                               (unsigned long long)__float_as_uint(h.max_eta) |
+                                   ((unsigned long long)(__float_as_uint(-h.min_eta) >> 2) << 32) | tag);
+        // (-min travels with its two lowest mantissa bits dropped and is rounded towards a smaller minimum on arrival;
+        // this rank's own value goes through the same rounding, so that every rank ends up with the same word)
+        auto dec_nmn = [](unsigned field30) {
+            const unsigned hb = field30 << 2;
+            return __uint_as_float((hb & 0x80000000u) ? hb : (hb | 3u));
+        };
+        float mx = h.max_eta, nmn = dec_nmn(__float_as_uint(-h.min_eta) >> 2);
         const long long t0 = global_timer_ns();
         for (;;) {
             bool pending = false;
@@ -999,13 +1013,17 @@ __device__ __noinline__ void tail_header(const TailArgs &a, int lane) {
                 const unsigned long long w = ld_relaxed_sys_u64(reinterpret_cast<const unsigned long long *>(a.peer->buf[a.peer->rank]) +
                                                                 slot_words + (size_t)lane * peer_src_words(a.nb) + word);
                 pending = (w >> 62) != (tag >> 62);
-                if (!pending) mx = __uint_as_float((unsigned)w);
+                if (!pending) {
+                    mx = __uint_as_float((unsigned)w);
+                    nmn = fmaxf(nmn, dec_nmn((unsigned)((w >> 32) & 0x3fffffffu)));
+                }
             }
             if (!__any_sync(FULL, pending)) break;
             if (global_timer_ns() - t0 > PEER_SPIN_LIMIT_NS) { peer_timeout = 1; break; }
         }
         peer_timeout = __any_sync(FULL, peer_timeout != 0) ? 1 : 0;
         h.max_eta = peer_timeout ? 0.f : warp_max(mx);
+        h.min_eta = peer_timeout ? 0.f : -warp_max(nmn);
         if (peer_timeout) { h.sum_ev_eta_q = 0; h.n_not_binnable = 0; h.sum_w_ceil = 0; h.n_bad_time = 0; }
     }
     unsigned long long vc[LB_MAX], vt[LB_MAX];
@@ -1260,15 +1278,11 @@ BinnedLayout binned_layout(int64_t n, int64_t n_seg, int nb) {
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-bool coop_supported() {
-    static int cached = -1;
-    if (cached < 0) {
-        int dev = 0, v = 0;
-        cached = (cudaGetDevice(&dev) == cudaSuccess &&
-                  cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v &&
-                  num_sms() >= 16) ? 1 : 0;  // (the fused kernel wants bpc < 32 blocks of bins per CTA)
-    }
-    return cached == 1;
+bool coop_supported() {  // of the current device (not cached: one attribute query, microseconds)
+    const int dev = current_device();
+    int v = 0;
+    return dev >= 0 && cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v &&
+           num_sms() >= 16;  // (the fused kernel wants bpc < 32 blocks of bins per CTA)
 }
 
 int32_t check_common(int64_t n, int64_t n_seg, int nb) {
@@ -1284,11 +1298,11 @@ int32_t launch_pass1_reduce(const float *log_hz, const float *time, const uint8_
                             const BinnedLayout &L, unsigned char *w8, cudaStream_t st) {
     const int vec_ok = aligned16(log_hz) && aligned16(time) && ((reinterpret_cast<uintptr_t>(event) & 3) == 0);
     const size_t smem = (size_t)nb * PARTIAL_BYTES_PER_BIN;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.pending()) {
         B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(B200SURV_COX_MAX_BINS * PARTIAL_BYTES_PER_BIN)));
-        attr_done = true;
+        attr_once.mark();
     }
     unsigned char *partial = w8 + L.off_partial;
     CtaRec *recs = reinterpret_cast<CtaRec *>(w8 + L.off_recs);
@@ -1327,14 +1341,14 @@ int32_t launch_fused(const float *log_hz, const float *time, const uint8_t *even
     int p1_mode = (vec_ok && nb <= 4096 && n >= 4 * (int64_t)TMA_TILE) ? p1_env : 0;
     size_t smem = p1_mode == 2 ? ring_smem_bytes(nb) : p1_mode == 1 ? tma_smem_bytes(nb) : (size_t)nb * 24 + 16;
     if (smem < 20480) smem = 20480;  // the reduce step stages 32 x 32 x (8 + 8 + 4) bytes
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.pending()) {
         size_t mx = (size_t)B200SURV_COX_MAX_BINS * 24 + 16;
         if (tma_smem_bytes(4096) > mx) mx = tma_smem_bytes(4096);
         if (ring_smem_bytes(4096) > mx) mx = ring_smem_bytes(4096);
         B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
         B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_fwd_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-        attr_done = true;
+        attr_once.mark();
     }
     unsigned char *partial = w8 + L.off_partial;
     CtaRec *recs = reinterpret_cast<CtaRec *>(w8 + L.off_recs);
@@ -1447,11 +1461,11 @@ int32_t cox_binned_bwd_launch(const float *grad_out, const void *state, size_t s
     const int vec_ok = aligned16(log_hz) && aligned16(time) && aligned16(out_grad) &&
                        ((reinterpret_cast<uintptr_t>(event) & 3) == 0);
     const size_t smem = (size_t)nb * sizeof(float2);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.pending()) {
         B200_CHECK_CUDA(cudaFuncSetAttribute(cox_binned_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              B200SURV_COX_MAX_BINS * (int)sizeof(float2)));
-        attr_done = true;
+        attr_once.mark();
     }
     const int sms = num_sms();
     int64_t c;

@@ -51,7 +51,7 @@ cox_small_fwd(const float *__restrict__ log_hz, const float *__restrict__ time,
             hdr->flags = n > SM_MAX ? B200SURV_COXF_NOT_BINNABLE : 0; hdr->mode = B200SURV_COX_SMALL;
             hdr->loss = n > SM_MAX ? __int_as_float(0x7fc00000) : 0.f; hdr->scale = 0.f; hdr->shift = 0.f;
             hdr->max_log_hz = 0.f; hdr->max_time = 0.f; hdr->nbins = 0; hdr->n_events = 0;
-            hdr->n_event_times = 0; hdr->pll = 0.0; hdr->reserved = 0; out_loss[seg] = hdr->loss;
+            hdr->n_event_times = 0; hdr->pll = 0.0; hdr->min_log_hz = 0.f; hdr->reserved = 0; out_loss[seg] = hdr->loss;
         }
         return;
     }
@@ -231,7 +231,7 @@ cox_small_fwd(const float *__restrict__ log_hz, const float *__restrict__ time,
     if (tid == 0) {
         hdr->flags = flags; hdr->mode = B200SURV_COX_SMALL; hdr->loss = (float)loss; hdr->scale = (float)scale;
         hdr->shift = mx; hdr->max_log_hz = mx; hdr->max_time = mt; hdr->nbins = 0; hdr->n_events = n_ev;
-        hdr->n_event_times = n_times; hdr->pll = pll; hdr->reserved = 0;
+        hdr->n_event_times = n_times; hdr->pll = pll; hdr->min_log_hz = 0.f; hdr->reserved = 0;
         out_loss[seg] = (float)loss;
     }
 }
@@ -262,11 +262,11 @@ int32_t cox_small_fwd_launch(const float *log_hz, const float *time, const uint8
     B200_REQUIRE(reduction >= 0 && reduction <= 2, "reduction");
     const size_t need = (size_t)n_seg * sizeof(b200surv_cox_header) + (size_t)n * sizeof(float);
     if (state_bytes < need) { set_error("cox small: state buffer %zu < %zu", state_bytes, need); return B200SURV_WORKSPACE_TOO_SMALL; }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.pending()) {
         B200_CHECK_CUDA(cudaFuncSetAttribute(cox_small_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)cox_small_smem_bytes()));
-        attr_done = true;
+        attr_once.mark();
     }
     b200surv_cox_header *hdrs = static_cast<b200surv_cox_header *>(state);
     float *grad_unit = reinterpret_cast<float *>(hdrs + n_seg);

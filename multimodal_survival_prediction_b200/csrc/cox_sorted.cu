@@ -191,7 +191,7 @@ k_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ idx_s, 
         hdr->flags = acc->flags; hdr->mode = B200SURV_COX_SORTED; hdr->loss = (float)loss;
         hdr->scale = (float)scale; hdr->shift = acc->max_eta; hdr->max_log_hz = acc->max_eta;
         hdr->max_time = acc->max_time; hdr->nbins = 0; hdr->n_events = (int64_t)acc->n_ev;
-        hdr->n_event_times = (int64_t)acc->n_times; hdr->pll = pll; hdr->reserved = 0;
+        hdr->n_event_times = (int64_t)acc->n_times; hdr->pll = pll; hdr->min_log_hz = 0.f; hdr->reserved = 0;
         out_loss[0] = (float)loss;
     }
 }

@@ -345,11 +345,11 @@ int32_t make_map(CUtensorMap *map, const void *ptr, int64_t inner, int64_t outer
 template <bool A_MN, bool B_MN>
 int32_t launch(const CUtensorMap &ma, const CUtensorMap &mb, int M, int N, int K, const Epilogue &ep, int splits,
                cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.pending()) {
         B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)GEMM_SMEM));
-        attr_done = true;
+        attr_once.mark();
     }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
     gemm_bf16_tc<A_MN, B_MN><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ma, mb, M, N, K, ep);

@@ -306,6 +306,7 @@ def gate_entropy_loss(gate_weights, eps=1e-8):
     its gradient enters the head through d_gate).  One fused kernel each way for the head's (B, 3) gate weights."""
     if not gate_weights.is_cuda:
         raise L.B200SurvError("gate_entropy_loss has no CPU path: the gate weights come from the CUDA head")
-    if gate_weights.dim() == 2 and gate_weights.shape[1] == 3 and gate_weights.shape[0] >= 1:
-        return _GateEntropy.apply(gate_weights, eps)
-    return -(-(gate_weights * torch.log(gate_weights + eps)).sum(dim=1)).mean()   # other widths: the reference's expression
+    if not (gate_weights.dim() == 2 and gate_weights.shape[1] == 3 and gate_weights.shape[0] >= 1):
+        raise ValueError(f"gate_entropy_loss expects the head's (B, 3) gate weights, got {tuple(gate_weights.shape)} "
+                         "(no eager path: the reference's gate has three modalities)")
+    return _GateEntropy.apply(gate_weights, eps)

@@ -6,4 +6,11 @@ The scripts do ``from torchsurv.loss.cox import neg_partial_log_likelihood`` and
 (``PYTHONPATH=<repo>/shim:<repo>``) and those imports resolve to
 multimodal_survival_prediction_b200.  This is NOT torchsurv: only the two entry points the
 reference uses exist."""
+import os as _os
+
+if _os.environ.get("B200SURV_NO_TORCHSURV_SHIM"):
+    # lets a harness drive the reference scripts down their OTHER branch (in-repo loss + lifelines C-index,
+    # partial_modality_training.py:295-319) with only the lifelines shim active
+    raise ImportError("torchsurv shim disabled by B200SURV_NO_TORCHSURV_SHIM")
+
 __version__ = "0.0+b200surv"

@@ -164,3 +164,15 @@ def test_cohorts_in_flight_match_one_by_one():
         a, b = int(off[c]), int(off[c + 1])
         one = cindex_counts(x[a:b].contiguous(), e[a:b].contiguous(), tt[a:b].contiguous(), 1e-8).cpu()
         assert torch.equal(out[c], one), c
+
+
+def test_negative_and_nan_times_raise():
+    """algo 1's sort key would alias a negative time with its absolute value; torchsurv rejects such input."""
+    lh, ev, t = synth.cohort(500, 3)
+    for bad in (-1.0, float("nan")):
+        t2 = t.clone(); t2[11] = bad
+        with pytest.raises(ValueError):
+            pkg.ConcordanceIndex()(lh, ev, t2)
+        with pytest.raises(ValueError):
+            pkg.ConcordanceIndex()(lh.cuda(), ev.cuda(), t2.cuda())
+    assert 0.0 <= pkg.ConcordanceIndex()(lh, ev, t).item() <= 1.0

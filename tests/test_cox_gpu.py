@@ -209,3 +209,72 @@ def test_full_size_16m_properties_and_oracle():
     ref_l, ref_g = ocox.cox_nll(lh.numpy().astype(np.float64), ev.numpy(), t.numpy(), "efron", "sum")
     assert abs(float(loss) - ref_l) <= LOSS_RTOL * abs(ref_l)
     assert np.abs(x.grad.cpu().numpy() - ref_g).max() <= GRAD_RTOL * np.abs(ref_g).max()
+
+
+def test_segmented_auto_mode_reads_every_segments_header():
+    """BINNED interleaves the per-segment headers with the (P,F) tables; auto mode must read the header of
+    EVERY segment (cohorts > 2048 rows, the CV-sweep case), including one that needs the EXP_RANGE retry and, in a
+    second cohort set, one with a negative time."""
+    lens = [5001, 3000, 12_345, 4096]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    lh, ev, t = synth.cohort(int(off[-1]), 31)
+    t = torch.clamp(torch.floor(t / 40.0), 1, 4000)
+    lh = lh.clone()
+    lh[off[2]:off[3]] += 60.0                      # only the third cohort is out of the fixed-point range at shift 0
+    x = lh.cuda().requires_grad_(True)
+    losses = pkg.neg_partial_log_likelihood_segmented(x, ev.cuda(), t.cuda(), torch.tensor(off))      # mode="auto"
+    losses.sum().backward()
+    ref_l, ref_g = ocox.cox_nll_segmented(lh.numpy().astype(np.float64), ev.numpy(), t.numpy(), off)
+    np.testing.assert_allclose(losses.detach().cpu().numpy(), ref_l, rtol=LOSS_RTOL, atol=1e-6)
+    g = x.grad.cpu().numpy()
+    for s in range(len(lens)):
+        a, b = off[s], off[s + 1]
+        assert np.abs(g[a:b] - ref_g[a:b]).max() <= GRAD_RTOL * np.abs(ref_g[a:b]).max() + 2e-6, s
+    # the headers themselves, at their real (strided) positions
+    so = torch.tensor(off).cuda()
+    _, state = gcox.cox_fwd_raw(lh.cuda(), t.cuda(), ev.cuda(), so, len(lens), L.TIES["efron"], 0, L.COX_BINNED, 4096)
+    hdrs = gcox.read_headers(state, len(lens), L.COX_BINNED)
+    assert [h.mode for h in hdrs] == [L.COX_BINNED] * 4 and [h.nbins for h in hdrs] == [4096] * 4
+    assert [bool(h.flags & L.COXF_EXP_RANGE) for h in hdrs] == [False, False, True, False]
+    for s, h in enumerate(hdrs):
+        a, b = off[s], off[s + 1]
+        assert h.n_events == int(ev[a:b].sum()) and h.max_log_hz == float(lh[a:b].max()) and h.min_log_hz == float(lh[a:b].min())
+    t_bad = t.clone(); t_bad[off[3] + 5] = -2.0    # a bad time in the LAST cohort only
+    with pytest.raises(ValueError):
+        pkg.neg_partial_log_likelihood_segmented(lh.cuda(), ev.cuda(), t_bad.cuda(), torch.tensor(off))
+
+
+def test_wide_hazard_spread_leaves_the_fixed_point_path():
+    """BINNED quantises exp(log_hz - shift) to 2^-28; rows ~20 nats below the shift round to zero.  A late risk
+    set made only of such rows used to give log(0).  Now the header raises LOW_PRECISION (loss NaN in explicit binned
+    mode) and auto re-shifts or falls through to the fp64 SORTED path."""
+    n = 20_000
+    lh, ev, t = synth.cohort(n, 41)
+    lh = lh.clone()
+    late = t >= torch.quantile(t, 0.97)
+    lh[late] -= 32.0                               # the largest times only hold very low hazards
+    ev = ev.clone(); ev[late] = True
+    l, _ = run_gpu(lh.numpy(), ev.numpy(), t.numpy(), mode="binned")
+    assert np.isnan(l)
+    x = lh.cuda()
+    _, state = gcox.cox_fwd_raw(x, t.cuda(), ev.cuda(), None, 1, L.TIES["efron"], 0, L.COX_BINNED, 4096)
+    h = gcox.read_headers(state, 1, L.COX_BINNED)[0]
+    assert h.flags & L.COXF_LOW_PRECISION and h.min_log_hz == float(lh.min())
+    check(lh.numpy(), ev.numpy(), t.numpy())       # auto: spread of ~37 nats does not fit any shift -> SORTED
+    # a spread that fits after re-shifting stays BINNED: 14 nats below, n = 20k allows weights up to 2^14
+    lh2, ev2, t2 = synth.cohort(n, 42)
+    lh2 = lh2.clone(); lh2[t2 >= torch.quantile(t2, 0.97)] -= 14.0
+    check(lh2.numpy(), ev2.numpy(), t2.numpy())
+
+
+def test_small_cohort_bad_times_raise_like_large_ones():
+    lh, ev, t = synth.cohort(40, 6)
+    t[7] = float("nan")
+    with pytest.raises(ValueError):
+        run_gpu(lh.numpy(), ev.numpy(), t.numpy())
+    t[7] = -3.0
+    with pytest.raises(ValueError):
+        run_gpu(lh.numpy(), ev.numpy(), t.numpy())
+    # checks=False keeps the call asynchronous (CUDA-graph capture): the loss is NaN instead
+    x = lh.cuda()
+    assert torch.isnan(pkg.neg_partial_log_likelihood(x, ev.cuda(), t.cuda(), checks=False))

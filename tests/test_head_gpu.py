@@ -250,3 +250,5 @@ def test_gate_entropy_loss_matches_the_reference_expression():
         (2.5 * ref).backward()
         assert abs(float(ours) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref))), (B, float(ours), float(ref))
         assert float((g.grad - g2.grad).abs().max()) <= 1e-5 * float(g2.grad.abs().max()) + 1e-9, B
+    with pytest.raises(ValueError):      # no eager path for other gate widths
+        ghead.gate_entropy_loss(torch.softmax(torch.randn(5, 4, device=dev), dim=1))
