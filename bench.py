@@ -39,6 +39,20 @@ FWD_BYTES_PER_ROW = 9.0
 METRIC = "cox_nll_fwd_bwd_patients_per_sec"
 
 
+def load_traffic(kernel, rows):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed summary of an
+    `ncu --set full` capture of this command (profiles/ncu_traffic.json, written by scratch/ncu_traffic.py).  None when
+    the capture was taken at another row count."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))[kernel]
+        if int(d["rows"]) != int(rows):
+            return None, None
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), d.get("source")
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -123,11 +137,24 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone and may use the whole host."""
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        pass
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_port_rate(rows, steps=1):
-    """patients/s of the torch-CPU port (fp32, all host threads) on a bounded sample."""
+    """patients/s of the torch-CPU port (fp32, all host threads) on one pass over the workload."""
     import torch
     from multimodal_survival_prediction_b200 import synth
     from oracle import cox_torch
+    use_all_host_threads()
     lh, ev, t = synth.cohort(rows, SEED)
     cox_torch.cox_nll_fwd_bwd(lh[: 1 << 16], ev[: 1 << 16], t[: 1 << 16])  # warm the thread pool
     t0 = time.perf_counter()
@@ -141,10 +168,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rows = min(args.rows, 1 << 22)
+    rows = args.rows            # the full workload: same config as the GPU arm (1.5-2 s per step on 16 threads)
     import torch
     from multimodal_survival_prediction_b200 import synth
     from oracle import cox_torch
+    use_all_host_threads()
     lh, ev, t = synth.cohort(rows, SEED)
     for _ in range(max(args.warmup, 1)):
         cox_torch.cox_nll_fwd_bwd(lh[: 1 << 18], ev[: 1 << 18], t[: 1 << 18])
@@ -154,7 +182,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     val = rows / dt
     cores = torch.get_num_threads()
-    sample = f"{rows} rows of the 16,777,216-row workload per step (bounded sample), torch CPU fp32, {cores} threads"
+    sample = f"all {rows} rows of the workload per step, {args.steps} steps, torch CPU fp32, {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "patients/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -206,7 +234,7 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    hdr = gcox.read_headers(op.state, 1)[0]
+    hdr = gcox.read_headers(op.state, 1, L.COX_BINNED)[0]
     if hdr.flags != 0:
         raise SystemExit(f"binned precondition violated on synthetic data: flags={hdr.flags}")
 
@@ -215,11 +243,13 @@ def run_b200(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launches0 = L.load().b200surv_debug_launch_count()
     ev0.record()
     for i in range(args.steps):      # the headline loop: exactly K steps, nothing else on the stream
         op.forward(x, tt, e)
         op.backward(x, tt, e, grad)
     ev1.record()
+    gpu_launches = int(L.load().b200surv_debug_launch_count() - launches0)   # counted by the library at its launch sites
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     ms_step = ms_total / args.steps
@@ -244,11 +274,76 @@ def run_b200(args):
     value = world * n / (ms_step * 1e-3)
     loss_val = float(op.loss.item())
 
+    # ---- N > 1: (a) PARITY of the sharded path, where the driver can see it: all ranks shard the SAME 16,777,216-row cohort
+    # (contiguous row blocks), rank 0 also computes it on one GPU, every rank compares the loss bit for bit and the gradient
+    # of its rows element for element; (b) STRONG scaling: the same total rows over N ranks, timed like the headline loop.
+    parity, strong = None, None
+    if world > 1:
+        glh, gev, gt = synth.cohort(n, SEED)
+        a_, b_ = gdist.shard_bounds(n, rank, world)
+        sx, se, st_ = glh[a_:b_].to(dev), gev[a_:b_].to(dev), gt[a_:b_].to(dev)
+        sgrad = torch.empty(b_ - a_, dtype=torch.float32, device=dev)
+        sop = gdist.ShardedCoxBinned(b_ - a_, dev, nbins=4096, ties="efron", exchange=args.exchange)
+        for _ in range(3):
+            sop.forward(sx, st_, se)
+            sop.backward(sx, st_, se, sgrad)
+        barrier()
+        ref = torch.zeros(2, dtype=torch.float32, device=dev)          # rank 0: loss of the whole cohort on ONE GPU
+        full_grad = None
+        if rank == 0:
+            fx, fe, ft = glh.to(dev), gev.to(dev), gt.to(dev)
+            l1, state1 = gcox.cox_fwd_raw(fx, ft, fe, None, 1, L.TIES["efron"], L.REDUCE_MEAN_TERMS, L.COX_BINNED, 4096)
+            full_grad = gcox.cox_bwd_raw(torch.ones(1, device=dev), state1, fx, ft, fe, None, 1, L.COX_BINNED, 4096)
+            ref[0] = l1[0]
+        dist.broadcast(ref, 0)
+        loss_equal = bool(torch.equal(sop.loss.view(torch.int32), ref[:1].view(torch.int32)))
+        # gradients: every rank sends its shard to rank 0 (NCCL), which compares them with the single-GPU gradient
+        shards = [torch.empty(gdist.shard_bounds(n, r, world)[1] - gdist.shard_bounds(n, r, world)[0],
+                              dtype=torch.float32, device=dev) for r in range(world)] if rank == 0 else None
+        if rank == 0:
+            shards[0].copy_(sgrad)
+            for r in range(1, world):
+                dist.recv(shards[r], src=r)
+            grad_equal = bool(torch.equal(torch.cat(shards), full_grad))
+            max_abs = float((torch.cat(shards) - full_grad).abs().max())
+            del shards, full_grad, fx, fe, ft, state1
+        else:
+            dist.send(sgrad, dst=0)
+            grad_equal, max_abs = True, 0.0
+        ok = torch.tensor([int(loss_equal), int(grad_equal)], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        parity = {"loss_bit_equal": bool(ok[0].item()), "grad_equal": bool(ok[1].item()), "grad_max_abs_diff": max_abs,
+                  "rows_total": n, "exchange": sop.exchange,
+                  "what": "the same 16,777,216-row cohort row-sharded over the ranks vs one GPU (rank 0), fp32 loss bits and every gradient element"}
+        # strong scaling, timed on the device, max over ranks
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s0.record()
+        for _ in range(args.steps):
+            sop.forward(sx, st_, se)
+            sop.backward(sx, st_, se, sgrad)
+        s1.record()
+        barrier()
+        sms = torch.tensor([s0.elapsed_time(s1) / args.steps], device=dev)
+        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        strong = {"rows_total": n, "rows_per_gpu": b_ - a_, "ms_per_step": float(sms.item()),
+                  "value": n / (float(sms.item()) * 1e-3), "unit": "patients/s", "scaling": "strong"}
+        if sop.peers is not None:
+            barrier()
+            sop.peers.close()
+        del sop, sx, se, st_, sgrad, glh, gev, gt
+        if not (parity["loss_bit_equal"] and parity["grad_equal"]):
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "n_gpus": world, "parity_check": parity, "error": "sharded result differs from one GPU"}))
+            dist.destroy_process_group()
+            raise SystemExit(3)
+
     if args.skip_extras:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": "patients/s", "n_gpus": world,
                               "steps": args.steps, "ms_per_step": ms_step, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
                               "exchange": op.exchange if world > 1 else None, "loss": loss_val,
+                              "parity_check": parity, "strong_scaling": strong, "gpu_launches": gpu_launches,
                               "note": "--skip-extras: partial line, not a bench result"}))
         if world > 1:
             dist.destroy_process_group()
@@ -461,8 +556,10 @@ def run_b200(args):
         achieved_bwd = BWD_BYTES_PER_ROW * n / (bwd_ms * 1e-3) / 1e9
         achieved_fwd = FWD_BYTES_PER_ROW * n / (fwd_ms * 1e-3) / 1e9
         achieved_step = ALGO_BYTES_PER_ROW * n / (ms_step * 1e-3) / 1e9
-        cpu_rows = 1 << 22
+        cpu_rows = n
         cpu_val, cpu_dt, cores = cpu_port_rate(cpu_rows) if world == 1 else (None, None, None)
+        fwd_traffic, traffic_src = load_traffic("cox_binned_fwd_fused", n) if fused else (None, None)
+        bwd_traffic, _ = load_traffic("cox_binned_bwd", n)
         out = {
             "metric": METRIC, "value": value, "unit": "patients/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -473,30 +570,36 @@ def run_b200(args):
                        "parallelism": "single GPU" if world == 1 else
                        (f"row-block shards x{world}, per-bin int64 sums exchanged inside the forward kernel over NVLink peer memory"
                         if op.exchange == "peer" else f"row-block shards x{world}, NCCL all-reduce of per-bin int64 sums"),
-                       "l2": "no flush needed: each step streams 151 MB in + 67 MB out, larger than the 126 MB L2"},
+                       "l2": "inputs larger than L2, no flush: a step streams 151 MB in twice and 67 MB out against a 126 MB L2; the "
+                             "kernels are L2-aware on purpose (the backward pass walks the rows in reverse so that it starts on "
+                             "the forward pass's tail); ncu's cold-cache durations agree with the loop (profiles/)"},
             "loss": loss_val,
-            # dominant kernel of the step = the fused forward (58 % of the step in the ncu launch list,
-            # profiles/r1_v14_launches.csv).  `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of one launch
-            # from the ncu --set full capture of this command (profiles/r1_v14_ncu_full_cox.csv), valid for the
-            # default 16,777,216-row workload only.
-            "roofline": {"bound": "hbm",
-                         "kernel": ("cox_binned_fwd_fused (9 B/row read: pass 1 + reduce + O(nbins) tail in one cooperative launch)"
-                                    if fused else "cox_binned_pass1 + reduce + all-reduce + finish (9 B/row read)"),
-                         "achieved": achieved_fwd, "peak": peak, "unit": "GB/s", "frac": achieved_fwd / peak,
-                         "traffic": (151.133696e6 + 3.794688e6) if (fused and n == N_ROWS) else None,
-                         "peak_source": peak_src, "ms": fwd_ms,
+            # `roofline`: the STEP (forward kernel + backward kernel; 22 algorithmic bytes per row) is the
+            # headline fraction, as VERDICT r1 asked; `fwd` (the dominant kernel: ~58 % of the step in the ncu launch list
+            # under profiles/) and `bwd` sit beside it, each = its algorithmic bytes / its own CUDA-event time.
+            # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch, read from profiles/ncu_traffic.json (the
+            # summary of the committed `ncu --set full` capture of this command); null if that capture was taken at
+            # another row count.
+            "roofline": {"bound": "hbm", "scope": "step = forward kernel + backward kernel, 22 B/row",
+                         "achieved": achieved_step, "peak": peak, "unit": "GB/s", "frac": achieved_step / peak,
+                         "frac_of_8TBs": achieved_step / 8000.0, "peak_source": peak_src, "ms": ms_step,
+                         "traffic": (fwd_traffic + bwd_traffic) if (fwd_traffic and bwd_traffic) else None,
+                         "traffic_source": traffic_src,
+                         "fwd": {"kernel": ("cox_binned_fwd_fused (9 B/row read: pass 1 + reduce + O(nbins) tail in one cooperative launch)"
+                                            if fused else "cox_binned_pass1 + reduce + all-reduce + finish (9 B/row read)"),
+                                 "dominant": True, "achieved": achieved_fwd, "frac": achieved_fwd / peak, "ms": fwd_ms,
+                                 "traffic": fwd_traffic},
                          "bwd": {"kernel": "cox_binned_bwd (13 B/row: 9 read + 4 written)", "achieved": achieved_bwd,
-                                 "frac": achieved_bwd / peak, "ms": bwd_ms,
-                                 "traffic": (151.043328e6 + 33.323264e6) if n == N_ROWS else None,
-                                 "traffic_note": "gradient stores still in L2 when the kernel ends are not in dram__bytes_write"},
-                         "step": {"bytes_per_row": ALGO_BYTES_PER_ROW, "achieved": achieved_step,
-                                  "frac": achieved_step / peak, "frac_of_8TBs": achieved_step / 8000.0}},
+                                 "frac": achieved_bwd / peak, "ms": bwd_ms, "traffic": bwd_traffic,
+                                 "traffic_note": "gradient stores still in L2 when the kernel ends are not in dram__bytes_write"}},
             "e2e": {"value": e2e_val, "unit": "patients/s", "h2d_bytes_per_step": 9 * n, "d2h_bytes_per_step": 4,
                     "ms_per_step": float(e2e_t.item()) * 1e3, "api": "neg_partial_log_likelihood(log_hz, event, time) + backward, mode=auto"},
-            # per step at N=1: cox_binned_fwd_fused (cooperative) + cox_binned_bwd; at N>1 the forward is split
-            # around the all-reduce: pass1, reduce, scan, items_finish, then bwd
-            "gpu_launches": (2 if fused else 5) * args.steps,
+            # kernels launched by libb200surv inside the timed region on this rank, counted by the library itself
+            # (b200surv_debug_launch_count): per step cox_binned_fwd_fused (cooperative) + cox_binned_bwd; with
+            # --exchange nccl the forward is pass1 + reduce, the all-reduce, finish
+            "gpu_launches": gpu_launches,
             "clocks": clocks,
+            "parity_check": parity, "strong_scaling": strong,
             "extra": {"cindex_1m": {"n": cn, "ms": ci_ms, "patients_per_s": cn / (ci_ms * 1e-3),
                                     "ordered_pairs_per_s": sum(counts) / (ci_ms * 1e-3), "counts": counts,
                                     "n_gpus": world, "scaling": "strong (row tiles sharded, int64 all-reduce)",
@@ -520,7 +623,7 @@ def run_b200(args):
         }
         if cpu_val is not None:
             out["cpu_baseline"] = {"value": cpu_val, "unit": "patients/s", "cores": cores, "kind": "port",
-                                   "sample": f"{cpu_rows} rows of the same cohort, one fwd+bwd ({cpu_dt:.2f} s), torch CPU fp32 port (oracle/cox_torch.py)"}
+                                   "sample": f"all {cpu_rows} rows of the same cohort, one fwd+bwd ({cpu_dt:.2f} s), torch CPU fp32 port (oracle/cox_torch.py)"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

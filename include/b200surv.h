@@ -46,6 +46,9 @@ typedef enum {
 int32_t b200surv_version(void);                 /* 1000*major + minor */
 int32_t b200surv_arch_check(int32_t device);    /* OK iff the device is compute capability 10.x */
 const char *b200surv_last_error(void);
+/* Diagnostics: kernels launched so far by the Cox entry points of this process (BINNED, SMALL; SORTED counts its own
+ * launches, not those of its sort/scan primitives).  bench.py reports the difference over its timed region. */
+uint64_t b200surv_debug_launch_count(void);
 
 /* ---- Cox negative partial log-likelihood ------------------------------------------------- */
 /* ties: tie handling of the partial likelihood (replaces torchsurv's ties_method string). */

@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200surv_version": (c_int32, []),
     "b200surv_arch_check": (c_int32, [c_int32]),
     "b200surv_last_error": (c_char_p, []),
+    "b200surv_debug_launch_count": (ctypes.c_uint64, []),
     "b200surv_cox_state_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32]),
     "b200surv_cox_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32]),
     "b200surv_cox_bins_sum_count": (c_size_t, [c_int32]),

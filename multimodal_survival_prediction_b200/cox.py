@@ -87,17 +87,21 @@ def read_headers(state: torch.Tensor, n_seg: int, mode: int = L.COX_SMALL):
     return [L.CoxHeader.from_buffer_copy(raw, i * L.COX_HEADER_BYTES) for i in range(n_seg)]
 
 
-def cox_fwd_raw(log_hz, time, event, seg_offsets, n_seg, ties, reduction, mode, nbins, shift=0.0):
-    """One call of b200surv_cox_fwd on prepared device tensors.  Returns (loss[n_seg], state)."""
+def cox_fwd_raw(log_hz, time, event, seg_offsets, n_seg, ties, reduction, mode, nbins, shift=0.0, state=None,
+                loss=None):
+    """One call of b200surv_cox_fwd on prepared device tensors.  Returns (loss[n_seg], state); ``state`` / ``loss``
+    may be caller-provided views (re-running one cohort of a packed set in place)."""
     dev = log_hz.device
     L.require_device(dev.index)
     lib = L.load()
     n = log_hz.numel()
     sb = lib.b200surv_cox_state_bytes(n, n_seg, mode, nbins)
     wb = lib.b200surv_cox_workspace_bytes(n, n_seg, mode, nbins)
-    state = torch.empty(sb, dtype=torch.uint8, device=dev)
+    if state is None:
+        state = torch.empty(sb, dtype=torch.uint8, device=dev)
     ws = torch.empty(max(wb, 256), dtype=torch.uint8, device=dev)
-    loss = torch.empty(n_seg, dtype=torch.float32, device=dev)
+    if loss is None:
+        loss = torch.empty(n_seg, dtype=torch.float32, device=dev)
     rc = lib.b200surv_cox_fwd(L.ptr(log_hz), L.ptr(time), L.ptr(event), L.ptr(seg_offsets), n, n_seg, ties,
                               reduction, mode, nbins, ctypes.c_float(shift), L.ptr(loss), L.ptr(state), sb,
                               L.ptr(ws), ws.numel(), L.stream_ptr(dev))
@@ -118,6 +122,15 @@ def cox_bwd_raw(grad_out, state, log_hz, time, event, seg_offsets, n_seg, mode, 
 
 
 LOWP_MIN = -11.090354888959125      # -16 ln 2: B200SURV_COXF_LOW_PRECISION threshold on min(log_hz) - shift
+
+
+def _fit_shift(n, hi, lo):
+    """Exponent shift for the 36.28 fixed point of a cohort of n rows with log_hz in [lo, hi]: the largest weight is 2^k
+    with n * 2^k <= 2^29 (full precision without overflow).  None when the smallest weight would still fall below the
+    LOW_PRECISION floor: the spread does not fit at any shift."""
+    k = min(28, max(0, 29 - max(1, (n - 1).bit_length())))
+    shift = hi - k * 0.6931471805599453
+    return shift if lo - shift >= LOWP_MIN else None
 
 
 def _plan_and_run(log_hz, time, event, seg_offsets, n_seg, max_seg, ties, reduction, mode, nbins, checks=True):
@@ -153,11 +166,27 @@ def _plan_and_run(log_hz, time, event, seg_offsets, n_seg, max_seg, ties, reduct
                 continue
             break
         if flags & (L.COXF_EXP_RANGE | L.COXF_LOW_PRECISION):
-            # largest weight 2^k with n * 2^k <= 2^29: full fixed-point precision without overflow
-            k = min(28, max(0, 29 - max(1, (n - 1).bit_length())))
-            new_shift = max(h.max_log_hz for h in hdrs) - k * 0.6931471805599453
-            lo = min(h.min_log_hz for h in hdrs)
-            if not (lo - new_shift >= LOWP_MIN) or new_shift == shift:
+            if n_seg > 1:
+                # packed cohorts: each flagged cohort is re-run in place with ITS OWN shift (the state keeps one header
+                # and table per cohort, and the backward pass reads the shift from the cohort's header)
+                so_host = seg_offsets.cpu().tolist()
+                stride = state.numel() // n_seg
+                for s_, h in enumerate(hdrs):
+                    if not h.flags:
+                        continue
+                    a, b = so_host[s_], so_host[s_ + 1]
+                    sh = _fit_shift(b - a, h.max_log_hz, h.min_log_hz)
+                    if sh is None:
+                        raise L.B200SurvError(f"cohort {s_} of a packed set: the spread of log_hz "
+                                              f"[{h.min_log_hz}, {h.max_log_hz}] does not fit the fixed-point (BINNED) "
+                                              "path; pass it alone (the SORTED mode handles one cohort per call)")
+                    cox_fwd_raw(log_hz[a:b], time[a:b], event[a:b], None, 1, ties, reduction, L.COX_BINNED, nb, sh,
+                                state=state[s_ * stride:(s_ + 1) * stride], loss=loss[s_:s_ + 1])
+                if any(h.flags for h in read_headers(state, n_seg, L.COX_BINNED)):
+                    break
+                return loss, state, L.COX_BINNED, nb
+            new_shift = _fit_shift(n, max(h.max_log_hz for h in hdrs), min(h.min_log_hz for h in hdrs))
+            if new_shift is None or new_shift == shift:
                 break       # the spread of log_hz does not fit the fixed point at any shift: fp64 path
             shift = new_shift
             continue

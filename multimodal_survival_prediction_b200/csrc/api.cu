@@ -1,6 +1,8 @@
 // Library-level entry points of libb200surv: version, architecture gate, error string.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace b200surv {
@@ -13,6 +15,10 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int k) { g_launches.fetch_add((unsigned long long)k, std::memory_order_relaxed); }
+unsigned long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 
 int current_device() {
     int dev = -1;
@@ -37,6 +43,8 @@ extern "C" {
 int32_t b200surv_version(void) { return 1000 * 0 + 1; }
 
 const char *b200surv_last_error(void) { return b200surv::g_err; }
+
+uint64_t b200surv_debug_launch_count(void) { return b200surv::launches_so_far(); }
 
 int32_t b200surv_arch_check(int32_t device) {
     int major = 0, minor = 0;

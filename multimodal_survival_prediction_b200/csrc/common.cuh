@@ -38,6 +38,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int num_sms();         // of the CURRENT device, cached per device (148 on B200)
 int current_device();  // cudaGetDevice, -1 on failure
+void count_launches(int k);  // adds to the process-wide counter behind b200surv_debug_launch_count()
 
 // One-time per-DEVICE setup (cudaFuncSetAttribute is a per-device attribute: a process that drives several GPUs must
 // set it on each).  Setting an attribute twice is harmless, so two threads racing through `pending()` is fine; the

@@ -1311,6 +1311,7 @@ int32_t launch_pass1_reduce(const float *log_hz, const float *time, const uint8_
     cox_binned_reduce<<<dim3(nb / RED_BINS, (unsigned)n_seg), RED_THREADS, 0, st>>>(partial, recs, L.nctas, nb, bins,
                                                                                     bins_max);
     B200_CHECK_CUDA(cudaGetLastError());
+    count_launches(2);
     return B200SURV_OK;
 }
 
@@ -1321,6 +1322,7 @@ int32_t launch_finish(const long long *bins, const float *bins_max, int64_t n_se
         bins, bins_max, nb, ties, reduction, shift, reinterpret_cast<double *>(w8 + L.off_scr_g),
         reinterpret_cast<double *>(w8 + L.off_scr_f), out_loss, static_cast<unsigned char *>(state));
     B200_CHECK_CUDA(cudaGetLastError());
+    count_launches(1);
     return B200SURV_OK;
 }
 
@@ -1366,6 +1368,7 @@ int32_t launch_fused(const float *log_hz, const float *time, const uint8_t *even
     const void *fn = peer ? (const void *)cox_binned_fwd_fused<true> : (const void *)cox_binned_fwd_fused<false>;
     // the full grid always: CTAs beyond the pass-1 participants still own blocks of bins in the reduce step and the tail
     B200_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms()), dim3(P1_THREADS), args, smem, st));
+    count_launches(1);
     return B200SURV_OK;
 }
 
@@ -1476,6 +1479,7 @@ int32_t cox_binned_bwd_launch(const float *grad_out, const void *state, size_t s
     cox_binned_bwd<<<dim3((unsigned)c, (unsigned)n_seg), P2_THREADS, smem, st>>>(
         grad_out, static_cast<const unsigned char *>(state), log_hz, time, event, seg_off, n, nb, vec_ok, out_grad);
     B200_CHECK_CUDA(cudaGetLastError());
+    count_launches(1);
     return B200SURV_OK;
 }
 

@@ -273,6 +273,7 @@ int32_t cox_small_fwd_launch(const float *log_hz, const float *time, const uint8
     cox_small_fwd<<<(unsigned)n_seg, SM_THREADS, cox_small_smem_bytes(), st>>>(
         log_hz, time, event, seg_off, n, ties, reduction, out_loss, hdrs, grad_unit);
     B200_CHECK_CUDA(cudaGetLastError());
+    count_launches(1);
     return B200SURV_OK;
 }
 
@@ -288,6 +289,7 @@ int32_t cox_scale_grad_launch(const float *grad_out, const void *state, const in
     if (gx < 1) gx = 1;
     cox_scale_grad<<<dim3(gx, (unsigned)n_seg), 256, 0, st>>>(grad_out, grad_unit, seg_off, n, out_grad);
     B200_CHECK_CUDA(cudaGetLastError());
+    count_launches(1);
     return B200SURV_OK;
 }
 
