@@ -8,9 +8,12 @@
 // The radix sort and the three device-wide scans are hand-written (sortscan.cuh): a stable LSD radix sort on
 // (time, event) keys and single-pass scans with decoupled look-back --
 //   R1 (reverse): D = suffix sums of w, ge = end of the row's tie group (min-scan)
-//   F1 (forward): prefix sums of the event weights and of the event count, gs = start of the tie group (max-scan);
-//                 a group's E and m are differences of the prefix sums at its two ends
-//   F2 (forward): prefix sums of a and f (F of a group again as a difference)
+//   F1 (forward): SEGMENTED sums (restarting at every tie group) of the event weights and of the event count, gs =
+//                 start of the tie group (max-scan); a group's E and m are the values at its last row
+//   F2 (forward): prefix sums of a; segmented sums of f (F of a group = the value at its last row)
+// Group sums are segmented scans, not differences of global prefix sums: with log-hazards spread over tens of nats
+// (the cohorts BINNED hands over, COXF_LOW_PRECISION) a late group's weights are 1e-15 of the running total and a
+// difference would be pure rounding noise (negative Efron denominators, NaN).
 #include <climits>
 
 #include "common.cuh"
@@ -106,9 +109,11 @@ struct StoreF1 {
         prefE[p] = inc.a; cntE[p] = inc.b; gs[p] = (int)inc.i;
     }
 };
-struct LoadF2 {
-    const double *a, *f;
-    __device__ sortscan::Tup operator()(int64_t p) const { sortscan::Tup t; t.a = a[p]; t.b = f[p]; t.i = 0; return t; }
+struct LoadF2 {   // a = a_p (global prefix), b = f_p (segmented by tie group: head marker i = p)
+    const double *a, *f; const int *gs;
+    __device__ sortscan::Tup operator()(int64_t p) const {
+        sortscan::Tup t; t.a = a[p]; t.b = f[p]; t.i = gs[p] == (int)p ? p : -1; return t;
+    }
 };
 struct StoreF2 {
     double *PA, *PF;
@@ -133,8 +138,7 @@ k_terms(const float *__restrict__ log_hz, const uint32_t *__restrict__ keys_s,
             const int l = (int)p - gs;
             double den = D, frac = 0.0;
             if (ties == B200SURV_TIES_EFRON) {
-                const double E = prefE[gend - 1] - (gs > 0 ? prefE[gs - 1] : 0.0);
-                const double m = cntE[gend - 1] - (gs > 0 ? cntE[gs - 1] : 0.0);
+                const double E = prefE[gend - 1], m = cntE[gend - 1];   // segmented sums: the group's own terms only
                 frac = (double)l / m;
                 den = D - frac * E;
             }
@@ -183,7 +187,7 @@ k_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ idx_s, 
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
         const double d = (keys_s[p] & 1u) ? 0.0 : 1.0;
         const int gs = gsv[p], gend = ge[p];
-        const double F = PF[gend - 1] - (gs > 0 ? PF[gs - 1] : 0.0);
+        const double F = PF[gend - 1];
         const double g = d - w[p] * (PA[gend - 1] - d * F);
         grad_unit[idx_s[p]] = (float)(scale * g);
     }
@@ -258,10 +262,10 @@ int32_t cox_sorted_fwd_launch(const float *log_hz, const float *time, const uint
     k_gather<<<grid, 256, 0, st>>>(log_hz, idx_s, n, acc, w);
     rc = sortscan::scan_lookback<sortscan::I_MIN, true>(n, LoadR1{w, keys_s, n}, StoreR1{Dpos, ge}, tmp, st);
     if (rc) return rc;
-    rc = sortscan::scan_lookback<sortscan::I_MAX, false>(n, LoadF1{w, keys_s}, StoreF1{prefE, cntE, gs}, tmp, st);
+    rc = sortscan::scan_lookback<sortscan::I_MAX, false, true, true>(n, LoadF1{w, keys_s}, StoreF1{prefE, cntE, gs}, tmp, st);
     if (rc) return rc;
     k_terms<<<grid, 256, 0, st>>>(log_hz, keys_s, idx_s, n, ties, Dpos, prefE, cntE, gs, ge, acc, a, f);
-    rc = sortscan::scan_lookback<sortscan::I_ADD, false>(n, LoadF2{a, f}, StoreF2{PA, PF}, tmp, st);
+    rc = sortscan::scan_lookback<sortscan::I_MAX, false, false, true>(n, LoadF2{a, f, gs}, StoreF2{PA, PF}, tmp, st);
     if (rc) return rc;
     k_grad<<<grid, 256, 0, st>>>(keys_s, idx_s, n, ties, reduction, w, PA, PF, gs, ge, acc, grad_unit, out_loss, hdr);
     B200_CHECK_CUDA(cudaGetLastError());

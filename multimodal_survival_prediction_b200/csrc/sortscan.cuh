@@ -31,11 +31,18 @@ __device__ __forceinline__ Tup tup_identity() {
     t.i = IOP == I_ADD ? 0ll : (IOP == I_MIN ? LLONG_MAX : LLONG_MIN);
     return t;
 }
-// `x` precedes `y` in scan order
-template <int IOP>
+// `x` precedes `y` in scan order.  SEGA / SEGB turn the sum of a / b into a SEGMENTED sum that restarts at every
+// segment head: an element marks a head through its integer (I_MAX: i >= 0, e.g. its own index, -1 otherwise;
+// I_MIN: i != LLONG_MAX), so "y holds a head" is read off y.i and the operator stays associative
+// ((f1,v1)+(f2,v2) = (f1|f2, f2 ? v2 : v1+v2)).  Sums of a tie group formed this way involve only the group's own
+// terms -- differences of two global prefix sums cancel catastrophically when a group's weights are tiny.
+template <int IOP, bool SEGA = false, bool SEGB = false>
 __device__ __forceinline__ Tup tup_combine(const Tup &x, const Tup &y) {
+    static_assert(!(SEGA || SEGB) || IOP != I_ADD, "segmented sums need head markers (I_MIN / I_MAX)");
     Tup t;
-    t.a = x.a + y.a; t.b = x.b + y.b;
+    const bool head = IOP == I_MAX ? y.i >= 0 : (IOP == I_MIN ? y.i != LLONG_MAX : false);
+    t.a = (SEGA && head) ? y.a : x.a + y.a;
+    t.b = (SEGB && head) ? y.b : x.b + y.b;
     t.i = IOP == I_ADD ? x.i + y.i : (IOP == I_MIN ? (x.i < y.i ? x.i : y.i) : (x.i > y.i ? x.i : y.i));
     return t;
 }
@@ -100,7 +107,7 @@ __device__ __forceinline__ bool scan_try_read(const unsigned long long *w, Tup &
 
 // Inclusive scan of load(p), p the PHYSICAL index; scan order = ascending p, or descending p when REVERSE.
 // store(p, inclusive, element).  grid = number of tiles, SCAN_THREADS threads.
-template <int IOP, bool REVERSE, typename Load, typename Store>
+template <int IOP, bool REVERSE, bool SEGA, bool SEGB, typename Load, typename Store>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_lookback(int64_t n, Load load, Store store, ScanState st) {
     __shared__ Tup s_warp[SCAN_THREADS / 32];
@@ -118,26 +125,26 @@ k_scan_lookback(int64_t n, Load load, Store store, ScanState st) {
     for (int k = 0; k < SCAN_ITEMS; ++k) {
         const int64_t li = base + k;
         item[k] = li < n ? load(REVERSE ? n - 1 - li : li) : tup_identity<IOP>();
-        run = tup_combine<IOP>(run, item[k]);
+        run = tup_combine<IOP, SEGA, SEGB>(run, item[k]);
     }
     // block-wide exclusive scan of the thread aggregates
     Tup inc = run;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const Tup u = tup_shfl_up(inc, d);
-        if (lane >= d) inc = tup_combine<IOP>(u, inc);
+        if (lane >= d) inc = tup_combine<IOP, SEGA, SEGB>(u, inc);
     }
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     Tup wpre = tup_identity<IOP>(), tile_agg = tup_identity<IOP>();
 #pragma unroll
     for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-        if (w < warp) wpre = tup_combine<IOP>(wpre, s_warp[w]);
-        tile_agg = tup_combine<IOP>(tile_agg, s_warp[w]);
+        if (w < warp) wpre = tup_combine<IOP, SEGA, SEGB>(wpre, s_warp[w]);
+        tile_agg = tup_combine<IOP, SEGA, SEGB>(tile_agg, s_warp[w]);
     }
     Tup thread_excl = tup_shfl_up(inc, 1);
     if (lane == 0) thread_excl = tup_identity<IOP>();
-    thread_excl = tup_combine<IOP>(wpre, thread_excl);
+    thread_excl = tup_combine<IOP, SEGA, SEGB>(wpre, thread_excl);
 
     // ---- decoupled look-back (warp 0): publish the aggregate, find the prefix of all earlier tiles
     if (warp == 0) {
@@ -164,27 +171,27 @@ k_scan_lookback(int64_t n, Load load, Store store, ScanState st) {
             const int take = done ? first_inc + 1 : first_none;            // lanes [0, take) are combined (<= 32)
             // combine in scan order: farthest tile first
             Tup acc = tup_identity<IOP>();
-            for (int l = take - 1; l >= 0; --l) acc = tup_combine<IOP>(acc, tup_shfl(v, l));
-            prefix = tup_combine<IOP>(acc, prefix);
+            for (int l = take - 1; l >= 0; --l) acc = tup_combine<IOP, SEGA, SEGB>(acc, tup_shfl(v, l));
+            prefix = tup_combine<IOP, SEGA, SEGB>(acc, prefix);
             if (done) break;
             look -= take;  // go on behind the tiles taken (take == 0: poll the same, still empty tile again)
         }
         if (lane == 0) {
-            if (tile != 0) scan_publish(st.inc + 3 * tile, tup_combine<IOP>(prefix, tile_agg));
+            if (tile != 0) scan_publish(st.inc + 3 * tile, tup_combine<IOP, SEGA, SEGB>(prefix, tile_agg));
             s_prefix = prefix;
         }
     }
     __syncthreads();
-    Tup acc = tup_combine<IOP>(s_prefix, thread_excl);
+    Tup acc = tup_combine<IOP, SEGA, SEGB>(s_prefix, thread_excl);
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
         const int64_t li = base + k;
-        acc = tup_combine<IOP>(acc, item[k]);
+        acc = tup_combine<IOP, SEGA, SEGB>(acc, item[k]);
         if (li < n) store(REVERSE ? n - 1 - li : li, acc, item[k]);
     }
 }
 
-template <int IOP, bool REVERSE, typename Load, typename Store>
+template <int IOP, bool REVERSE, bool SEGA = false, bool SEGB = false, typename Load, typename Store>
 int32_t scan_lookback(int64_t n, Load load, Store store, void *state_buf, cudaStream_t st) {
     if (n <= 0) return B200SURV_OK;
     const size_t ntiles = (size_t)((n + SCAN_TILE - 1) / SCAN_TILE);
@@ -193,7 +200,7 @@ int32_t scan_lookback(int64_t n, Load load, Store store, void *state_buf, cudaSt
     unsigned ig = (unsigned)((words + 255) / 256);
     if (ig > 1184) ig = 1184;
     k_scan_state_init<<<ig, 256, 0, st>>>(s, words);
-    k_scan_lookback<IOP, REVERSE, Load, Store><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(n, load, store, s);
+    k_scan_lookback<IOP, REVERSE, SEGA, SEGB, Load, Store><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(n, load, store, s);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }

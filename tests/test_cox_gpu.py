@@ -261,10 +261,18 @@ def test_wide_hazard_spread_leaves_the_fixed_point_path():
     h = gcox.read_headers(state, 1, L.COX_BINNED)[0]
     assert h.flags & L.COXF_LOW_PRECISION and h.min_log_hz == float(lh.min())
     check(lh.numpy(), ev.numpy(), t.numpy())       # auto: spread of ~37 nats does not fit any shift -> SORTED
-    # a spread that fits after re-shifting stays BINNED: 14 nats below, n = 20k allows weights up to 2^14
+    # a spread that fits after re-shifting stays BINNED (12 nats below; n = 20k allows weights up to 2^14) ...
     lh2, ev2, t2 = synth.cohort(n, 42)
-    lh2 = lh2.clone(); lh2[t2 >= torch.quantile(t2, 0.97)] -= 14.0
+    late2 = t2 >= torch.quantile(t2, 0.97)
+    lh2 = lh2.clone(); lh2[late2] -= 12.0
     check(lh2.numpy(), ev2.numpy(), t2.numpy())
+    # ... and two more nats do not: SORTED again, whose tie-group sums must not be differences of running totals
+    lh2[late2] -= 2.0
+    check(lh2.numpy(), ev2.numpy(), t2.numpy())
+    for spread in (25.0, 60.0):                    # explicit SORTED mode on heavy ties + very wide spreads
+        lh3, ev3, t3 = synth.cohort(30_000, 43)
+        lh3 = lh3.clone(); lh3[t3 >= torch.quantile(t3, 0.9)] -= spread
+        check(lh3.numpy(), ev3.numpy(), t3.numpy(), mode="sorted")
 
 
 def test_small_cohort_bad_times_raise_like_large_ones():
