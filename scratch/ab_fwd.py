@@ -42,7 +42,7 @@ class Variant:
         self.loss = torch.empty(1, dtype=torch.float32, device=dev)
         self.one = torch.ones(1, dtype=torch.float32, device=dev)
         self.st = L.stream_ptr(dev)
-        self.t_f, self.t_fb = [], []
+        self.t_f, self.t_fb, self.t_b, self.seq = [], [], [], []
 
     def fwd(self):
         rc = self.lib.b200surv_cox_fwd(L.ptr(x), L.ptr(tt), L.ptr(e), None, n, 1, 2, 0, L.COX_BINNED, 4096,
@@ -108,11 +108,23 @@ for r in range(ROUNDS):
     for v in vs:
         v.t_f.append(timed(v.fwd, ITERS))
         v.t_fb.append(timed(lambda: (v.fwd(), v.bwd()), ITERS))
+        v.t_b.append(timed(v.bwd, ITERS))
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * ITERS + 1)]     # per-kernel times inside the sequence
+        evs[0].record()
+        for i in range(ITERS):
+            v.fwd(); evs[2 * i + 1].record(); v.bwd(); evs[2 * i + 2].record()
+        torch.cuda.synchronize()
+        fs = sorted(evs[2 * i].elapsed_time(evs[2 * i + 1]) * 1e3 for i in range(1, ITERS))
+        bs = sorted(evs[2 * i + 1].elapsed_time(evs[2 * i + 2]) * 1e3 for i in range(1, ITERS))
+        v.seq.append((fs[len(fs) // 2], bs[len(bs) // 2]))
     print(f"round {r}: clocks/power {clock()}  " + "  ".join(f"{os.path.basename(v.path)} f={v.t_f[-1]:.1f} fb={v.t_fb[-1]:.1f}" for v in vs), flush=True)
 for v in vs:
     v.fwd(); torch.cuda.synchronize()
     f, fb = sorted(v.t_f), sorted(v.t_fb)
-    print(f"{os.path.basename(v.path):24s} fwd median {f[len(f) // 2]:.1f} min {f[0]:.1f} us | fwd+bwd median {fb[len(fb) // 2]:.1f} min {fb[0]:.1f} us | loss {v.loss.item():.6f}")
+    b = sorted(v.t_b)
+    sf, sb_ = sorted(x[0] for x in v.seq), sorted(x[1] for x in v.seq)
+    print(f"{os.path.basename(v.path):24s} fwd median {f[len(f) // 2]:.1f} min {f[0]:.1f} us | fwd+bwd median {fb[len(fb) // 2]:.1f} min {fb[0]:.1f} us | "
+          f"bwd alone {b[len(b) // 2]:.1f} | in sequence (events between calls): fwd {sf[len(sf) // 2]:.1f} bwd {sb_[len(sb_) // 2]:.1f} | loss {v.loss.item():.6f}")
     tr = v.trace()
     if tr and os.environ.get("B200SURV_PEER_TRACE"):
         print("   trace: " + tr)
