@@ -233,6 +233,21 @@ int32_t b200surv_gemm_bf16(const void *a, int64_t lda, int32_t a_mn, const void 
                            void *c_bf16, int64_t ldc_bf16, const float *bias, int32_t relu,
                            b200surv_stream_t stream);
 
+/* The same GEMM with an explicit tile width and K split.  tile_n: 128 (what b200surv_gemm_bf16 uses), 192 or 256 columns
+ * per 128-row output tile: wide tiles move fewer bytes from L2 per flop (rna_encoder.0 forward is bound by exactly that
+ * at 128), 192 puts the rna_encoder.0 weight gradient (512 x 5005) on 108 CTAs = one wave of the 148 SMs; tile_n = 512
+ * selects CTA PAIRS on 256 x 256 tiles (tcgen05.mma.cta_group::2, 2-CTA clusters): twice the math per byte a CTA loads.
+ * splits >= 2:
+ * K is cut into `splits` slices whose fp32 results [M][ldc] are written back to back into `slices` (c is ignored, no
+ * bias / ReLU / bf16 copy); the caller sums them in slice order.  splits <= 1: like b200surv_gemm_bf16. */
+int32_t b200surv_gemm_bf16_ex(const void *a, int64_t lda, int32_t a_mn, const void *b, int64_t ldb, int32_t b_mn, int32_t M,
+                              int32_t N, int32_t K, float *c, int64_t ldc, void *c_bf16, int64_t ldc_bf16, const float *bias,
+                              int32_t relu, int32_t tile_n, int32_t splits, float *slices, b200surv_stream_t stream);
+
+/* Diagnostics: CTA (0,0,0) of the CTA-pair GEMM writes %globaltimer stamps (start, first MMA, last commit, epilogue begin /
+ * end, exit; from index 8 the arrival of the first 24 k-blocks) into buf (>= 32 int64 of device memory); NULL = off. */
+void b200surv_debug_gemm_trace(long long *buf);
+
 /* Split-K variant for outputs with few tiles and a long K (weight gradients): writes
  * b200surv_gemm_splitk_slices(M, N, K) (1..32) fp32 slices [M][ldc] back to back into `slices`; the caller sums them
  * in slice order (deterministic).  Same operand conventions as b200surv_gemm_bf16. */

@@ -62,6 +62,10 @@ SIGNATURES = {
                                                c_int32, c_int32, ctypes.c_uint32, c_void_p]),
     "b200surv_gemm_bf16": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                      c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
+    "b200surv_gemm_bf16_ex": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                        c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                        c_void_p]),
+    "b200surv_debug_gemm_trace": (None, [c_void_p]),
     "b200surv_gemm_splitk_slices": (c_int32, [c_int32, c_int32, c_int32]),
     "b200surv_gemm_bf16_splitk": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                             c_void_p, c_int64, c_void_p]),

@@ -10,7 +10,21 @@
 // (tcgen05 + TMEM + TMA, bf16 operands, fp32 accumulation); the kernels in this file are the fused
 // element-wise / reduction glue between the GEMMs (BatchNorm statistics and application, dropout with a
 // counter-based RNG that backward re-derives, mask/gate/softmax, the 128->1 Cox head).
+//
+// Launch structure (round 2; B = 4096: 16 launches forward, ~28 backward, was 21 + ~60):
+//   * rna_encoder.0 forward and its weight gradient run on CTA PAIRS (256 x 256 tiles, tcgen05 cta_group::2); the
+//     forward is split in two along K, and the kernel that forms the BatchNorm statistics also adds the two slices
+//     and the bias (k_bn_stats_combine);
+//   * every reduction over the batch (bias gradients, BatchNorm backward sums, the small gate / clinical / Cox-head
+//     weight gradients) is fused into the kernel that produces the summand: a thread (or warp) owns a column and walks
+//     a slice of rows, writes one fp64 partial per (row slice, column); one small kernel per group sums the slices in a
+//     fixed order -- deterministic, no atomics;
+//   * the four small weight-gradient GEMMs and the slice sums leave the critical path: they run on an internal side
+//     stream forked from / joined to the caller's stream with events (also under CUDA-graph capture), while the
+//     caller's stream carries the chain of input-gradient GEMMs.
 #include <cuda_bf16.h>
+
+#include <mutex>
 
 #include "common.cuh"
 
@@ -19,6 +33,9 @@ namespace b200surv {
 int32_t gemm_bf16(const void *a, int64_t lda, int a_mn, const void *b, int64_t ldb, int b_mn, int M, int N, int K,
                   float *c, int64_t ldc, void *c_bf16, int64_t ldc_bf16, const float *bias, int relu, float *splitk_ws,
                   cudaStream_t st);
+int32_t gemm_bf16_ex(const void *a, int64_t lda, int a_mn, const void *b, int64_t ldb, int b_mn, int M, int N, int K,
+                     float *c, int64_t ldc, void *c_bf16, int64_t ldc_bf16, const float *bias, int relu, float *splitk_ws,
+                     int tile_n, int force_splits, cudaStream_t st);
 int splitk_slices(int M, int N, int K, int *kb_per);
 
 namespace {
@@ -178,50 +195,6 @@ __global__ void k_bn_apply(const float *__restrict__ x, int64_t ldx, const float
         y[r * ldy + n] = __float2bfloat16_rn(v);
     }
 }
-// dy = dA * keep/(1-p) * [bn(x) > 0]
-__global__ void k_bn_bwd_dy(const float *__restrict__ dA, int64_t ldd, const float *__restrict__ x, int64_t ldx,
-                            const float *__restrict__ mu, const float *__restrict__ rstd,
-                            const float *__restrict__ gamma, const float *__restrict__ beta, int64_t B, int N,
-                            uint32_t thresh, float inv_keep, uint64_t seed, const uint64_t *__restrict__ seed_dev,
-                            uint32_t layer, float *__restrict__ dy) {
-    if (seed_dev != nullptr) seed = *seed_dev;
-    const int64_t total = B * N;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = row_of(i, N);
-        const int n = (int)(i - r * N);
-        const float v = (x[r * ldx + n] - mu[n]) * rstd[n] * gamma[n] + beta[n];
-        float g = dA[r * ldd + n];
-        if (thresh) g = keep_elem(seed, layer, (uint64_t)i, thresh) ? g * inv_keep : 0.f;
-        dy[i] = v > 0.f ? g : 0.f;
-    }
-}
-// dx (bf16) from dy, column sums sdy = sum dy, sdyx = sum dy*xhat:
-// train: dx = gamma*rstd*(dy - sdy/B - xhat*sdyx/B);  eval: dx = gamma*rstd*dy
-__global__ void k_bn_bwd_dx(const float *__restrict__ dy, const float *__restrict__ x, int64_t ldx,
-                            const float *__restrict__ mu, const float *__restrict__ rstd,
-                            const float *__restrict__ gamma, const float *__restrict__ sdy,
-                            const float *__restrict__ sdyx, int64_t B, int N, int training, bf16 *__restrict__ dx,
-                            int64_t lddx) {
-    const int64_t total = B * N;
-    const float invB = 1.f / (float)B;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = row_of(i, N);
-        const int n = (int)(i - r * N);
-        float v = dy[i];
-        if (training) {
-            const float xh = (x[r * ldx + n] - mu[n]) * rstd[n];
-            v = v - sdy[n] * invB - xh * sdyx[n] * invB;
-        }
-        dx[r * lddx + n] = __float2bfloat16_rn(v * gamma[n] * rstd[n]);
-    }
-}
-// bias gradient of the Linear feeding a BatchNorm: sum_rows dx = (train ? 0 : gamma*rstd*sdy)
-__global__ void k_bn_bias_grad(const float *__restrict__ sdy, const float *__restrict__ gamma,
-                               const float *__restrict__ rstd, int N, int training, float *__restrict__ db) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < N) db[n] = training ? 0.f : gamma[n] * rstd[n] * sdy[n];
-}
-
 // ---------------------------------------------------------------- mask / clinical encoder / gate
 // feat[b] = [ct*m0 (128) | R*m1 (128) | relu(clin*Wc+bc)*m2 (32)] (fp32); gated: z = bf16([feat | mask | 0 pad]);
 // ungated (mask == nullptr): no masking, fused = bf16(feat)
@@ -251,7 +224,8 @@ __global__ void k_gate_prep(const float *__restrict__ ct, const float *__restric
 // one warp per row: logits = zh Wg2^T + bg2, gate = softmax, fused = bf16(feat * gate[group])
 __global__ void __launch_bounds__(256)
 k_gate_apply(const float *__restrict__ zh, const float *__restrict__ wg2, const float *__restrict__ bg2,
-             const float *__restrict__ feat, int64_t B, float *__restrict__ gate, bf16 *__restrict__ fused) {
+             const float *__restrict__ feat, int64_t B, float *__restrict__ gate, float *__restrict__ gate_out,
+             bf16 *__restrict__ fused) {
     const int lane = threadIdx.x & 31;
     for (int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < B; b += (int64_t)gridDim.x * 8) {
         const float z0 = zh[b * GH + lane], z1 = zh[b * GH + 32 + lane];
@@ -263,65 +237,16 @@ k_gate_apply(const float *__restrict__ zh, const float *__restrict__ wg2, const 
         const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx);
         const float inv = 1.f / (e0 + e1 + e2);
         const float g0 = e0 * inv, g1 = e1 * inv, g2 = e2 * inv;
-        if (lane == 0) { gate[b * 3 + 0] = g0; gate[b * 3 + 1] = g1; gate[b * 3 + 2] = g2; }
+        if (lane == 0) {  // the saved copy (backward) and the caller's output
+            gate[b * 3 + 0] = g0; gate[b * 3 + 1] = g1; gate[b * 3 + 2] = g2;
+            gate_out[b * 3 + 0] = g0; gate_out[b * 3 + 1] = g1; gate_out[b * 3 + 2] = g2;
+        }
         for (int j = lane; j < FEAT; j += 32) {
             const float g = j < CT ? g0 : (j < CT + R1 ? g1 : g2);
             fused[b * FEAT + j] = __float2bfloat16_rn(feat[b * FEAT + j] * g);
         }
     }
 }
-// one warp per row.  in: dfused [B][288], feat, gate, zh, d_gate_ext (nullable).
-// out: dfeat = dfused * gate (fp32 [B][288]); dlogit [B][3]; dzh = bf16((dlogit Wg2) * [zh > 0]) [B][64]
-__global__ void __launch_bounds__(256)
-k_gate_apply_bwd(const float *__restrict__ dfused, const float *__restrict__ feat, const float *__restrict__ gate,
-                 const float *__restrict__ zh, const float *__restrict__ wg2, const float *__restrict__ d_gate_ext,
-                 int64_t B, float *__restrict__ dfeat, float *__restrict__ dlogit, bf16 *__restrict__ dzh) {
-    const int lane = threadIdx.x & 31;
-    for (int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < B; b += (int64_t)gridDim.x * 8) {
-        const float g0 = gate[b * 3], g1 = gate[b * 3 + 1], g2 = gate[b * 3 + 2];
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-        for (int j = lane; j < FEAT; j += 32) {
-            const float df = dfused[b * FEAT + j], f = feat[b * FEAT + j];
-            if (j < CT) { d0 += df * f; dfeat[b * FEAT + j] = df * g0; }
-            else if (j < CT + R1) { d1 += df * f; dfeat[b * FEAT + j] = df * g1; }
-            else { d2 += df * f; dfeat[b * FEAT + j] = df * g2; }
-        }
-        d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
-        if (d_gate_ext) { d0 += d_gate_ext[b * 3]; d1 += d_gate_ext[b * 3 + 1]; d2 += d_gate_ext[b * 3 + 2]; }
-        const float dot = g0 * d0 + g1 * d1 + g2 * d2;
-        const float dl0 = g0 * (d0 - dot), dl1 = g1 * (d1 - dot), dl2 = g2 * (d2 - dot);
-        if (lane == 0) { dlogit[b * 3] = dl0; dlogit[b * 3 + 1] = dl1; dlogit[b * 3 + 2] = dl2; }
-        for (int k = lane; k < GH; k += 32) {
-            const float v = dl0 * wg2[k] + dl1 * wg2[GH + k] + dl2 * wg2[2 * GH + k];
-            dzh[b * GH + k] = __float2bfloat16_rn(zh[b * GH + k] > 0.f ? v : 0.f);
-        }
-    }
-}
-// dtot = dfeat (+ dz[:, :288]); d_ct = dtot[0:128]*m0; dR = bf16(dtot[128:256]*m1*[R>0]); dC = dtot[256:288]*m2*[C>0]
-__global__ void k_gate_prep_bwd(const float *__restrict__ dfeat, const float *__restrict__ dz, int64_t lddz,
-                                const float *__restrict__ mask, const float *__restrict__ R,
-                                const float *__restrict__ clin, const float *__restrict__ wc,
-                                const float *__restrict__ bc, int64_t B, float *__restrict__ d_ct,
-                                bf16 *__restrict__ dR, float *__restrict__ dC) {
-    const int64_t total = B * FEAT;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = row_of(i, FEAT);
-        const int j = (int)(i - b * FEAT);
-        float v = dfeat[i] + (dz ? dz[b * lddz + j] : 0.f);
-        if (j < CT) {
-            if (d_ct) d_ct[b * CT + j] = v * (mask ? mask[b * 3] : 1.f);
-        } else if (j < CT + R1) {
-            const int k = j - CT;
-            v *= (mask ? mask[b * 3 + 1] : 1.f);
-            dR[b * R1 + k] = __float2bfloat16_rn(R[b * R1 + k] > 0.f ? v : 0.f);
-        } else {
-            const int k = j - CT - R1;
-            v *= (mask ? mask[b * 3 + 2] : 1.f);
-            dC[b * CL + k] = (clin[b] * wc[k] + bc[k] > 0.f) ? v : 0.f;
-        }
-    }
-}
-
 // ---------------------------------------------------------------- Cox head 128 -> 1
 __global__ void __launch_bounds__(256)
 k_cox_head(const float *__restrict__ f2, const float *__restrict__ w, const float *__restrict__ bias, int64_t B,
@@ -334,19 +259,259 @@ k_cox_head(const float *__restrict__ f2, const float *__restrict__ w, const floa
         if (lane == 0) hazard[b] = s + bias[0];
     }
 }
-// dF2r = bf16(dhz[b] * w[j] * [f2 > 0])
-__global__ void k_cox_head_bwd(const float *__restrict__ dhz, const float *__restrict__ f2, const float *__restrict__ w,
-                               int64_t B, bf16 *__restrict__ df2) {
-    const int64_t total = B * F2N;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = row_of(i, F2N);
-        const int j = (int)(i - b * F2N);
-        df2[i] = __float2bfloat16_rn(f2[i] > 0.f ? dhz[b] * w[j] : 0.f);
+// ---------------------------------------------------------------- fused reductions (round 2)
+// one launch for the bf16 copies of all weight matrices (K padded with zeros where the TMA row pitch needs it)
+struct CastSeg { const float *src; bf16 *dst; int lds, ldd, R, C, Cp; };
+struct CastSegs { CastSeg s[5]; int n; };
+__global__ void __launch_bounds__(256)
+k_cast_multi(const CastSegs segs) {
+    for (int k = 0; k < segs.n; ++k) {
+        const CastSeg g = segs.s[k];
+        const int64_t total = (int64_t)g.R * g.Cp;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int r = (int)((unsigned)i / (unsigned)g.Cp), c = (int)(i - (int64_t)r * g.Cp);
+            g.dst[(int64_t)r * g.ldd + c] = __float2bfloat16_rn(c < g.C ? g.src[(int64_t)r * g.lds + c] : 0.f);
+        }
     }
 }
-__global__ void k_bf16_to_f32(const bf16 *__restrict__ src, float *__restrict__ dst, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        dst[i] = __bfloat162float(src[i]);
+
+// h[r][n] = s0[r][n] + s1[r][n] + bias[n] (the two K slices of the split GEMM), and the BatchNorm partial sums
+// (sum h, sum h^2) per (row slice, column) in the layout of k_colreduce<0>.  grid (N / 32, nslices), 256 threads.
+__global__ void __launch_bounds__(256)
+k_bn_stats_combine(const float *__restrict__ s0, const float *__restrict__ s1, const float *__restrict__ bias, int64_t B, int N,
+                   int want_stats, float *__restrict__ h, double *__restrict__ partial) {
+    __shared__ double sh0[8][32], sh1[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx, slice = blockIdx.y, nslices = gridDim.y;
+    const int64_t rows_per = (B + nslices - 1) / nslices, r0 = slice * rows_per, r1 = min(B, r0 + rows_per);
+    double v0 = 0.0, v1 = 0.0;
+    if (n < N) {
+        const float bn = bias[n];
+        int64_t r = r0 + ty;
+        for (; r + 24 < r1; r += 32) {
+            float a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a[u] = s0[(r + 8 * u) * N + n]; b[u] = s1[(r + 8 * u) * N + n]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float x = (a[u] + b[u]) + bn;
+                h[(r + 8 * u) * N + n] = x;
+                v0 += x; v1 += (double)x * x;
+            }
+        }
+        for (; r < r1; r += 8) {
+            const float x = (s0[r * N + n] + s1[r * N + n]) + bn;
+            h[r * N + n] = x;
+            v0 += x; v1 += (double)x * x;
+        }
+    }
+    if (!want_stats) return;
+    sh0[ty][tx] = v0; sh1[ty][tx] = v1;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { v0 += sh0[k][tx]; v1 += sh1[k][tx]; }
+        partial[((size_t)slice * 2 + 0) * N + n] = v0;
+        partial[((size_t)slice * 2 + 1) * N + n] = v1;
+    }
+}
+
+// BatchNorm backward, pass 1: dy = dA * keep/(1-p) * [bn(x) > 0] formed on the fly (not stored), partial sums
+// (sum dy, sum dy * xhat) per (row slice, column).  grid (N / 32, nslices), 256 threads.
+__global__ void __launch_bounds__(256)
+k_bn_bwd_stats(const float *__restrict__ dA, int64_t ldd, const float *__restrict__ x, int64_t ldx, const float *__restrict__ mu,
+               const float *__restrict__ rstd, const float *__restrict__ gamma, const float *__restrict__ beta, int64_t B, int N,
+               uint32_t thresh, float inv_keep, uint64_t seed, const uint64_t *__restrict__ seed_dev, uint32_t layer,
+               double *__restrict__ partial) {
+    __shared__ double sh0[8][32], sh1[8][32];
+    if (seed_dev != nullptr) seed = *seed_dev;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx, slice = blockIdx.y, nslices = gridDim.y;
+    const int64_t rows_per = (B + nslices - 1) / nslices, r0 = slice * rows_per, r1 = min(B, r0 + rows_per);
+    double v0 = 0.0, v1 = 0.0;
+    if (n < N) {
+        const float m = mu[n], rs = rstd[n], ga = gamma[n], be = beta[n];
+        for (int64_t r = r0 + ty; r < r1; r += 8) {
+            const float xh = (x[r * ldx + n] - m) * rs;
+            float g = dA[r * ldd + n];
+            if (thresh) g = keep_elem(seed, layer, (uint64_t)(r * N + n), thresh) ? g * inv_keep : 0.f;
+            const float dy = (xh * ga + be > 0.f) ? g : 0.f;
+            v0 += dy; v1 += (double)dy * xh;
+        }
+    }
+    sh0[ty][tx] = v0; sh1[ty][tx] = v1;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { v0 += sh0[k][tx]; v1 += sh1[k][tx]; }
+        partial[((size_t)slice * 2 + 0) * N + n] = v0;
+        partial[((size_t)slice * 2 + 1) * N + n] = v1;
+    }
+}
+// pass 2: dbeta = sum dy, dgamma = sum dy * xhat (one warp per column, slices in a fixed order) and the bias gradient
+// of the Linear that feeds the BatchNorm: sum_rows dx = (train ? 0 : gamma * rstd * sum dy)
+__global__ void __launch_bounds__(256)
+k_bn_bwd_final(const double *__restrict__ partial, int nslices, int N, const float *__restrict__ gamma,
+               const float *__restrict__ rstd, int training, float *__restrict__ dbeta, float *__restrict__ dgamma,
+               float *__restrict__ dbias) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    double v0, v1;
+    slice_sums(partial, nslices, N, n, lane, v0, v1);
+    if (lane == 0) {
+        dbeta[n] = (float)v0; dgamma[n] = (float)v1;
+        dbias[n] = training ? 0.f : gamma[n] * rstd[n] * (float)v0;
+    }
+}
+// pass 3: dx (bf16) = gamma * rstd * (dy - sdy / B - xhat * sdyx / B) (train) or gamma * rstd * dy (eval), dy re-derived
+__global__ void k_bn_bwd_dx2(const float *__restrict__ dA, int64_t ldd, const float *__restrict__ x, int64_t ldx,
+                             const float *__restrict__ mu, const float *__restrict__ rstd, const float *__restrict__ gamma,
+                             const float *__restrict__ beta, const float *__restrict__ sdy, const float *__restrict__ sdyx,
+                             int64_t B, int N, int training, uint32_t thresh, float inv_keep, uint64_t seed,
+                             const uint64_t *__restrict__ seed_dev, uint32_t layer, bf16 *__restrict__ dx, int64_t lddx) {
+    if (seed_dev != nullptr) seed = *seed_dev;
+    const int64_t total = B * N;
+    const float invB = 1.f / (float)B;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = row_of(i, N);
+        const int n = (int)(i - r * N);
+        const float xh = (x[r * ldx + n] - mu[n]) * rstd[n];
+        float g = dA[r * ldd + n];
+        if (thresh) g = keep_elem(seed, layer, (uint64_t)i, thresh) ? g * inv_keep : 0.f;
+        float v = (xh * gamma[n] + beta[n] > 0.f) ? g : 0.f;
+        if (training) v = v - sdy[n] * invB - xh * sdyx[n] * invB;
+        dx[r * lddx + n] = __float2bfloat16_rn(v * gamma[n] * rstd[n]);
+    }
+}
+
+// Cox head backward, one launch: df2 = bf16(dhz[b] * w[j] * [f2 > 0]) and the partial sums per (row slice, column j) of
+//   [0] sum_b dhz[b] * f2[b][j]  (cox_head.weight)   [1] sum_b df2[b][j]  (fusion.4.bias: column sums of the SAME bf16
+//   values the GEMMs read)   [2][0] sum_b dhz[b]  (cox_head.bias).  grid (nslices), 128 threads: a thread owns column j.
+__global__ void __launch_bounds__(F2N)
+k_cox_bwd_fused(const float *__restrict__ dhz, const float *__restrict__ f2, const float *__restrict__ w, int64_t B,
+                bf16 *__restrict__ df2, double *__restrict__ partial) {
+    const int j = threadIdx.x, slice = blockIdx.x, nslices = gridDim.x;
+    const int64_t rows_per = (B + nslices - 1) / nslices, r0 = slice * rows_per, r1 = min(B, r0 + rows_per);
+    const float wj = w[j];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int64_t b = r0; b < r1; ++b) {
+        const float d = dhz[b], f = f2[b * F2N + j];
+        const bf16 q = __float2bfloat16_rn(f > 0.f ? d * wj : 0.f);
+        df2[b * F2N + j] = q;
+        a0 += (double)d * f; a1 += (double)__bfloat162float(q); a2 += d;
+    }
+    double *p = partial + (size_t)slice * (3 * F2N);
+    p[j] = a0; p[F2N + j] = a1;
+    if (j == 0) p[2 * F2N] = a2;
+}
+
+// sums the row slices of `ncols` columns (partial[slice][ncols], fp64) into up to four float outputs: segment s takes the
+// columns [c0[s], c0[s + 1]).  One warp per column, slices in a fixed order.
+struct SumSegs { float *out[4]; int c0[5]; int n; };
+__global__ void __launch_bounds__(256)
+k_sum_slices(const double *__restrict__ partial, int nslices, int ncols, const SumSegs segs) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= ncols) return;
+    double v = 0.0;
+    for (int k = lane; k < nslices; k += 32) v += partial[(size_t)k * ncols + c];
+    v = warp_sum(v);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (s < segs.n && c >= segs.c0[s] && c < segs.c0[s + 1]) segs.out[s][c - segs.c0[s]] = (float)v;
+    }
+}
+
+// Gate backward (softmax + scaling), one launch, one warp per row inside a row slice per CTA:
+//   dfeat = dfused * gate (fp32 [B][288]); dzh = bf16((dlogit Wg2) * [zh > 0]) [B][64]; partial sums per row slice of
+//   gate.2.weight [3][64] (sum_b dlogit[b][k] zh[b][c]), gate.2.bias [3], gate.0.bias [64] (column sums of dzh as bf16).
+// partial[slice][GP_COLS]: [0,192) gate2_w, [192,195) gate2_b, [195,259) gate0_b.  grid (nslices), 256 threads.
+constexpr int GP_COLS = 3 * GH + 3 + GH;
+__global__ void __launch_bounds__(256)
+k_gate_bwd_fused(const float *__restrict__ dfused, const float *__restrict__ feat, const float *__restrict__ gate,
+                 const float *__restrict__ zh, const float *__restrict__ wg2, const float *__restrict__ d_gate_ext, int64_t B,
+                 float *__restrict__ dfeat, bf16 *__restrict__ dzh, double *__restrict__ partial) {
+    __shared__ double sh[8][GP_COLS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, slice = blockIdx.x, nslices = gridDim.x;
+    const int64_t rows_per = (B + nslices - 1) / nslices, r0 = slice * rows_per, r1 = min(B, r0 + rows_per);
+    double aw[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}}, ab[3] = {0.0, 0.0, 0.0}, az[2] = {0.0, 0.0};
+    for (int64_t b = r0 + warp; b < r1; b += 8) {
+        const float g0 = gate[b * 3], g1 = gate[b * 3 + 1], g2 = gate[b * 3 + 2];
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        for (int j = lane; j < FEAT; j += 32) {
+            const float df = dfused[b * FEAT + j], f = feat[b * FEAT + j];
+            if (j < CT) { d0 += df * f; dfeat[b * FEAT + j] = df * g0; }
+            else if (j < CT + R1) { d1 += df * f; dfeat[b * FEAT + j] = df * g1; }
+            else { d2 += df * f; dfeat[b * FEAT + j] = df * g2; }
+        }
+        d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
+        if (d_gate_ext) { d0 += d_gate_ext[b * 3]; d1 += d_gate_ext[b * 3 + 1]; d2 += d_gate_ext[b * 3 + 2]; }
+        const float dot = g0 * d0 + g1 * d1 + g2 * d2;
+        const float dl[3] = {g0 * (d0 - dot), g1 * (d1 - dot), g2 * (d2 - dot)};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = lane + 32 * u;
+            const float z = zh[b * GH + k];
+            const float v = dl[0] * wg2[k] + dl[1] * wg2[GH + k] + dl[2] * wg2[2 * GH + k];
+            const bf16 q = __float2bfloat16_rn(z > 0.f ? v : 0.f);
+            dzh[b * GH + k] = q;
+            az[u] += (double)__bfloat162float(q);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) aw[c][u] += (double)dl[c] * z;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ab[c] += dl[c];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sh[warp][c * GH + lane + 32 * u] = aw[c][u];
+        sh[warp][3 * GH + 3 + lane + 32 * u] = az[u];
+    }
+    if (lane < 3) sh[warp][3 * GH + lane] = ab[lane];
+    __syncthreads();
+    for (int c = threadIdx.x; c < GP_COLS; c += blockDim.x) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += sh[k][c];
+        partial[(size_t)slice * GP_COLS + c] = v;
+    }
+}
+
+// Mask / clinical-encoder backward, one launch: dtot = dfeat (+ dz[:, :288]); d_ct = dtot[0:128] * m0;
+// dR = bf16(dtot[128:256] * m1 * [R > 0]); dC = dtot[256:288] * m2 * [C > 0] (not stored), and the partial sums per row slice
+// of rna_encoder.4.bias (column sums of dR as bf16) [128], clinical_encoder.0.weight [32] (sum_b dC clin[b]) and .bias [32].
+// partial[slice][PP_COLS].  grid (nslices), 288 threads: a thread owns column j of the 288.
+constexpr int PP_COLS = R1 + 2 * CL;
+__global__ void __launch_bounds__(FEAT)
+k_prep_bwd_fused(const float *__restrict__ dfeat, const float *__restrict__ dz, int64_t lddz, const float *__restrict__ mask,
+                 const float *__restrict__ R, const float *__restrict__ clin, const float *__restrict__ wc,
+                 const float *__restrict__ bc, int64_t B, float *__restrict__ d_ct, bf16 *__restrict__ dR,
+                 double *__restrict__ partial) {
+    const int j = threadIdx.x, slice = blockIdx.x, nslices = gridDim.x;
+    const int64_t rows_per = (B + nslices - 1) / nslices, r0 = slice * rows_per, r1 = min(B, r0 + rows_per);
+    const int grp = j < CT ? 0 : (j < CT + R1 ? 1 : 2);
+    const int k = grp == 0 ? j : (grp == 1 ? j - CT : j - CT - R1);
+    const float wck = grp == 2 ? wc[k] : 0.f, bck = grp == 2 ? bc[k] : 0.f;
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t b = r0; b < r1; ++b) {
+        float v = dfeat[b * FEAT + j] + (dz ? dz[b * lddz + j] : 0.f);
+        v *= mask ? mask[b * 3 + grp] : 1.f;
+        if (grp == 0) {
+            if (d_ct) d_ct[b * CT + k] = v;
+        } else if (grp == 1) {
+            const bf16 q = __float2bfloat16_rn(R[b * R1 + k] > 0.f ? v : 0.f);
+            dR[b * R1 + k] = q;
+            a0 += (double)__bfloat162float(q);
+        } else {
+            const float c = clin[b];
+            const float dc = (c * wck + bck > 0.f) ? v : 0.f;
+            a0 += (double)dc * c; a1 += dc;
+        }
+    }
+    double *p = partial + (size_t)slice * PP_COLS;
+    if (grp == 1) p[k] = a0;
+    if (grp == 2) { p[R1 + k] = a0; p[R1 + CL + k] = a1; }
 }
 
 // ---------------------------------------------------------------- host orchestration
@@ -400,24 +565,48 @@ Saved carve_saved(void *buf, int64_t B, int rna_dim, size_t *bytes) {
 
 // scratch used inside one call (the `workspace` buffer)
 struct Scratch {
-    double *partial;          // [RS_MAX][2][max N]
-    float *t0, *t1, *t2;      // [B][512] fp32 temporaries
-    bf16 *b0, *b1;            // [B][512] bf16 temporaries
-    float *v0, *v1;           // [max N] vectors
-    float *dlogit, *dC;       // [B][3], [B][32]
-    float *splitk;            // [32 slices][SPLITK_ELEMS] fp32 partial weight gradients
+    double *partial;                  // [RS_MAX][2][512]: BatchNorm sums (caller's stream)
+    double *p_cox, *p_gate, *p_prep;  // row-slice partials of the fused reductions (summed on the side stream)
+    float *t0, *t1;                   // [B][512] fp32 temporaries (caller's stream)
+    float *slices;                    // [2][B][512]: the two K slices of rna_encoder.0 forward
+    bf16 *df2, *dh2, *dzh, *dR, *dh1; // dY operands of the gradient GEMMs: one buffer each (the side stream reads them)
+    float *splitk;                    // [32 slices][SPLITK_ELEMS] fp32 partial weight gradients (side stream)
 };
 Scratch carve_scratch(void *buf, int64_t B, size_t *bytes) {
     Carver c{static_cast<unsigned char *>(buf), 0};
     Scratch s;
-    s.partial = c.take<double>((size_t)RS_MAX * 2 * 8192);
-    s.t0 = c.take<float>((size_t)B * H1); s.t1 = c.take<float>((size_t)B * H1); s.t2 = c.take<float>((size_t)B * H1);
-    s.b0 = c.take<bf16>((size_t)B * H1); s.b1 = c.take<bf16>((size_t)B * H1);
-    s.v0 = c.take<float>(8192); s.v1 = c.take<float>(8192);
-    s.dlogit = c.take<float>((size_t)B * 4); s.dC = c.take<float>((size_t)B * CL);
+    s.partial = c.take<double>((size_t)RS_MAX * 2 * H1);
+    s.p_cox = c.take<double>((size_t)RS_MAX * 3 * F2N);
+    s.p_gate = c.take<double>((size_t)RS_MAX * GP_COLS);
+    s.p_prep = c.take<double>((size_t)RS_MAX * PP_COLS);
+    s.t0 = c.take<float>((size_t)B * H1); s.t1 = c.take<float>((size_t)B * H1);
+    s.slices = c.take<float>((size_t)2 * B * H1);
+    s.df2 = c.take<bf16>((size_t)B * F2N); s.dh2 = c.take<bf16>((size_t)B * H2); s.dzh = c.take<bf16>((size_t)B * GH);
+    s.dR = c.take<bf16>((size_t)B * R1); s.dh1 = c.take<bf16>((size_t)B * H1);
     s.splitk = c.take<float>((size_t)32 * SPLITK_ELEMS);
     *bytes = c.off;
     return s;
+}
+
+// the side stream of the backward pass (small weight-gradient GEMMs, slice sums), created once per device
+struct HeadLanes {
+    cudaStream_t side;
+    cudaEvent_t fork, join;
+};
+HeadLanes *head_lanes() {
+    static HeadLanes pool[MAX_DEVICES];
+    static int state[MAX_DEVICES];  // 0 = not tried, 1 = ready, -1 = failed
+    static std::mutex mu;
+    const int dev = current_device();
+    if (dev < 0 || dev >= MAX_DEVICES) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (state[dev] == 0) {
+        const bool ok = cudaStreamCreateWithFlags(&pool[dev].side, cudaStreamNonBlocking) == cudaSuccess &&
+                        cudaEventCreateWithFlags(&pool[dev].fork, cudaEventDisableTiming) == cudaSuccess &&
+                        cudaEventCreateWithFlags(&pool[dev].join, cudaEventDisableTiming) == cudaSuccess;
+        state[dev] = ok ? 1 : -1;
+    }
+    return state[dev] == 1 ? &pool[dev] : nullptr;
 }
 
 template <int MODE>
@@ -425,23 +614,6 @@ void colreduce(const float *a, int64_t lda, const float *x, int64_t ldx, const f
                const float *s, int64_t s_stride, int64_t B, int N, double *partial, int nsl, cudaStream_t st) {
     k_colreduce<MODE><<<dim3((N + 31) / 32, nsl), 256, 0, st>>>(a, lda, x, ldx, mu, rstd, s, s_stride, B, N, partial);
 }
-// out0[n] = sum_b a[b][n] * s[b*s_stride]
-void rowscale_sum(const float *a, int64_t lda, const float *s, int64_t s_stride, int64_t B, int N, double *partial,
-                  float *out0, float *out1, cudaStream_t st) {
-    const int nsl = nslices_for(B);
-    colreduce<2>(a, lda, nullptr, 0, nullptr, nullptr, s, s_stride, B, N, partial, nsl, st);
-    k_colreduce_final<<<colfinal_grid(N), 256, 0, st>>>(partial, nsl, N, 1.f, out0, out1);
-}
-void col_sum(const float *a, int64_t lda, int64_t B, int N, double *partial, float *out0, cudaStream_t st) {
-    const int nsl = nslices_for(B);
-    colreduce<3>(a, lda, nullptr, 0, nullptr, nullptr, nullptr, 0, B, N, partial, nsl, st);
-    k_colreduce_final<<<colfinal_grid(N), 256, 0, st>>>(partial, nsl, N, 1.f, out0, nullptr);
-}
-void col_sum_bf16(const bf16 *a, int64_t B, int N, float *tmp, double *partial, float *out0, cudaStream_t st) {
-    k_bf16_to_f32<<<gs(B * N), 256, 0, st>>>(a, tmp, B * N);
-    col_sum(tmp, N, B, N, partial, out0, st);
-}
-
 // weight gradient dW[M][N] = A^T B over K = batch rows (both operands MN-major).  The small ones (one to six output
 // tiles for 64 k-blocks) are split along K over the SMs into fp32 slices and summed in a fixed order (deterministic).
 __global__ void k_splitk_sum(const float *__restrict__ part, int slices, int64_t elems, float *__restrict__ out) {
@@ -538,18 +710,37 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
     const int nsl = nslices_for(B);
     int32_t rc;
 
-    // bf16 operand copies (K padded to a multiple of 8 for the TMA row pitch)
+    // bf16 operand copies (K padded to a multiple of 8 for the TMA row pitch): the batch, then all weights in one launch
     cast_pad(rna, rna_dim, s.xb, Kp, B, rna_dim, Kp, st);
-    cast_pad(p->rna0_w, rna_dim, s.w1b, Kp, H1, rna_dim, Kp, st);
-    cast_pad(p->rna4_w, H1, s.w2b, H1, R1, H1, H1, st);
-    if (gated) cast_pad(p->gate0_w, GZ, s.wg1b, GZP, GH, GZ, GZP, st);
-    cast_pad(p->fus0_w, FEAT, s.wf1b, FEAT, H2, FEAT, FEAT, st);
-    cast_pad(p->fus4_w, H2, s.wf2b, H2, F2N, H2, H2, st);
+    {
+        CastSegs cs;
+        cs.n = 0;
+        auto add = [&](const float *src, int lds, bf16 *dst, int ldd, int R, int C, int Cp) {
+            cs.s[cs.n].src = src; cs.s[cs.n].dst = dst; cs.s[cs.n].lds = lds; cs.s[cs.n].ldd = ldd;
+            cs.s[cs.n].R = R; cs.s[cs.n].C = C; cs.s[cs.n].Cp = Cp; ++cs.n;
+        };
+        add(p->rna0_w, rna_dim, s.w1b, Kp, H1, rna_dim, Kp);
+        add(p->rna4_w, H1, s.w2b, H1, R1, H1, H1);
+        if (gated) add(p->gate0_w, GZ, s.wg1b, GZP, GH, GZ, GZP);
+        add(p->fus0_w, FEAT, s.wf1b, FEAT, H2, FEAT, FEAT);
+        add(p->fus4_w, H2, s.wf2b, H2, F2N, H2, H2);
+        k_cast_multi<<<gs((int64_t)H1 * Kp), 256, 0, st>>>(cs);
+    }
 
     // rna encoder: Linear(rna_dim, 512) -> BN -> ReLU -> Dropout -> Linear(512, 128) -> ReLU
-    rc = gemm_bf16(s.xb, Kp, 0, s.w1b, Kp, 0, (int)B, H1, rna_dim, s.h1, H1, nullptr, 0, p->rna0_b, 0, nullptr, st);
-    if (rc) return rc;
-    if (training) colreduce<0>(s.h1, H1, nullptr, 0, nullptr, nullptr, nullptr, 0, B, H1, w.partial, nsl, st);
+    // Large batches: CTA pairs on 256 x 256 tiles, K split in two (64 pairs x 2 = 128 CTAs); the BatchNorm statistics kernel
+    // adds the two slices and the bias.  Small batches: one 128-wide tile kernel writes h1 directly.
+    const bool pair1 = B >= 512 && rna_dim >= 2048;
+    if (pair1) {
+        rc = gemm_bf16_ex(s.xb, Kp, 0, s.w1b, Kp, 0, (int)B, H1, rna_dim, w.slices, H1, nullptr, 0, nullptr, 0, w.slices, 512, 2, st);
+        if (rc) return rc;
+        k_bn_stats_combine<<<dim3(H1 / 32, nsl), 256, 0, st>>>(w.slices, w.slices + (size_t)B * H1, p->rna0_b, B, H1, training ? 1 : 0,
+                                                               s.h1, w.partial);
+    } else {
+        rc = gemm_bf16(s.xb, Kp, 0, s.w1b, Kp, 0, (int)B, H1, rna_dim, s.h1, H1, nullptr, 0, p->rna0_b, 0, nullptr, st);
+        if (rc) return rc;
+        if (training) colreduce<0>(s.h1, H1, nullptr, 0, nullptr, nullptr, nullptr, 0, B, H1, w.partial, nsl, st);
+    }
     k_bn_finalize<<<colfinal_grid(H1), 256, 0, st>>>(w.partial, nsl, B, H1, training, p->bn1_rm, p->bn1_rv, s.mu1, s.rstd1);
     k_bn_apply<<<gs(B * H1), 256, 0, st>>>(s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh, inv_keep, seed, seed_dev, 1,
                                            s.a1, H1, keep1);
@@ -562,8 +753,7 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
     if (gated) {
         rc = gemm_bf16(s.z, GZP, 0, s.wg1b, GZP, 0, (int)B, GH, GZ, s.zh, GH, nullptr, 0, p->gate0_b, 1, nullptr, st);
         if (rc) return rc;
-        k_gate_apply<<<gs(B * 32), 256, 0, st>>>(s.zh, p->gate2_w, p->gate2_b, s.feat, B, s.gate, s.fused);
-        B200_CHECK_CUDA(cudaMemcpyAsync(gate, s.gate, (size_t)B * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        k_gate_apply<<<gs(B * 32), 256, 0, st>>>(s.zh, p->gate2_w, p->gate2_b, s.feat, B, s.gate, gate, s.fused);
     }
     // fusion: Linear(288, 256) -> BN -> ReLU -> Dropout -> Linear(256, 128) -> ReLU ; cox head
     rc = gemm_bf16(s.fused, FEAT, 0, s.wf1b, FEAT, 0, (int)B, H2, FEAT, s.h2, H2, nullptr, 0, p->fus0_b, 0, nullptr, st);
@@ -600,68 +790,95 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     const int nsl = nslices_for(B);
     int32_t rc;
 
-    // ---- cox head: dwcox = sum_b dhz[b] f2[b], dbcox = sum dhz; dF2 (ReLU-masked, bf16)
-    rowscale_sum(s.f2, F2N, d_hazard, 1, B, F2N, w.partial, g->cox_w, w.v1, st);
-    B200_CHECK_CUDA(cudaMemcpyAsync(g->cox_b, w.v1, sizeof(float), cudaMemcpyDeviceToDevice, st));
-    k_cox_head_bwd<<<gs(B * F2N), 256, 0, st>>>(d_hazard, s.f2, p->cox_w, B, w.b0);           // b0 = dF2 [B][128]
-    // ---- fusion.4: dW = dF2^T a2, db = colsum dF2, dA2 = dF2 Wf2
-    rc = gemm_wgrad(w.b0, F2N, s.a2, H2, F2N, H2, (int)B, g->fus4_w, H2, w.splitk, st);
+    // The caller's stream carries the chain of input-gradient GEMMs; the small weight-gradient GEMMs and the slice sums of
+    // the fused reductions run on the side stream, forked / joined with events (works under stream capture as well).
+    HeadLanes *lanes = head_lanes();
+    cudaStream_t sd = lanes ? lanes->side : st;
+    auto fork = [&]() -> int32_t {  // everything issued on `st` so far precedes what the side stream does next
+        if (!lanes) return B200SURV_OK;
+        B200_CHECK_CUDA(cudaEventRecord(lanes->fork, st));
+        B200_CHECK_CUDA(cudaStreamWaitEvent(sd, lanes->fork, 0));
+        return B200SURV_OK;
+    };
+    auto sums = [&](const double *partial, int ncols, SumSegs sg) {
+        k_sum_slices<<<(ncols + 7) / 8, 256, 0, sd>>>(partial, nsl, ncols, sg);
+    };
+
+    // ---- cox head: df2 (ReLU-masked, bf16) + partial sums of cox_head.weight / .bias and fusion.4.bias, one launch
+    k_cox_bwd_fused<<<nsl, F2N, 0, st>>>(d_hazard, s.f2, p->cox_w, B, w.df2, w.p_cox);
+    if ((rc = fork())) return rc;
+    {
+        SumSegs sg; sg.n = 3;
+        sg.out[0] = g->cox_w; sg.out[1] = g->fus4_b; sg.out[2] = g->cox_b; sg.out[3] = nullptr;
+        sg.c0[0] = 0; sg.c0[1] = F2N; sg.c0[2] = 2 * F2N; sg.c0[3] = 2 * F2N + 1; sg.c0[4] = 2 * F2N + 1;
+        sums(w.p_cox, 3 * F2N, sg);
+    }
+    // ---- fusion.4: dW = dF2^T a2 (side), dA2 = dF2 Wf2
+    rc = gemm_wgrad(w.df2, F2N, s.a2, H2, F2N, H2, (int)B, g->fus4_w, H2, w.splitk, sd);
     if (rc) return rc;
-    col_sum_bf16(w.b0, B, F2N, w.t2, w.partial, g->fus4_b, st);
-    rc = gemm_bf16(w.b0, F2N, 0, s.wf2b, H2, 1, (int)B, H2, F2N, w.t0, H2, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dA2 [B][256]
+    rc = gemm_bf16(w.df2, F2N, 0, s.wf2b, H2, 1, (int)B, H2, F2N, w.t0, H2, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dA2 [B][256]
     if (rc) return rc;
-    // ---- fusion.1-3 (BN, ReLU, Dropout) backward -> dH2 (bf16, b1)
-    k_bn_bwd_dy<<<gs(B * H2), 256, 0, st>>>(w.t0, H2, s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh, inv_keep,
-                                            seed, seed_dev, 2, w.t1);                                       // t1 = dy
-    colreduce<1>(w.t1, H2, s.h2, H2, s.mu2, s.rstd2, nullptr, 0, B, H2, w.partial, nsl, st);
-    k_colreduce_final<<<colfinal_grid(H2), 256, 0, st>>>(w.partial, nsl, H2, 1.f, g->bn2_b, g->bn2_w);  // dbeta, dgamma
-    k_bn_bwd_dx<<<gs(B * H2), 256, 0, st>>>(w.t1, s.h2, H2, s.mu2, s.rstd2, p->bn2_w, g->bn2_b, g->bn2_w, B, H2, training,
-                                            w.b1, H2);                                            // b1 = dH2
-    k_bn_bias_grad<<<(H2 + 255) / 256, 256, 0, st>>>(g->bn2_b, p->bn2_w, s.rstd2, H2, training, g->fus0_b);
-    // ---- fusion.0: dW = dH2^T fused, dfused = dH2 Wf1
-    rc = gemm_wgrad(w.b1, H2, s.fused, FEAT, H2, FEAT, (int)B, g->fus0_w, FEAT, w.splitk, st);
+    // ---- fusion.1-3 (BN, ReLU, Dropout) backward -> dH2 (bf16); fusion.0.bias with it
+    k_bn_bwd_stats<<<dim3(H2 / 32, nsl), 256, 0, st>>>(w.t0, H2, s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh, inv_keep,
+                                                       seed, seed_dev, 2, w.partial);
+    k_bn_bwd_final<<<colfinal_grid(H2), 256, 0, st>>>(w.partial, nsl, H2, p->bn2_w, s.rstd2, training, g->bn2_b, g->bn2_w, g->fus0_b);
+    k_bn_bwd_dx2<<<gs(B * H2), 256, 0, st>>>(w.t0, H2, s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, g->bn2_b, g->bn2_w, B, H2,
+                                             training, thresh, inv_keep, seed, seed_dev, 2, w.dh2, H2);
+    // ---- fusion.0: dW = dH2^T fused (side), dfused = dH2 Wf1
+    if ((rc = fork())) return rc;
+    rc = gemm_wgrad(w.dh2, H2, s.fused, FEAT, H2, FEAT, (int)B, g->fus0_w, FEAT, w.splitk, sd);
     if (rc) return rc;
-    rc = gemm_bf16(w.b1, H2, 0, s.wf1b, FEAT, 1, (int)B, FEAT, H2, w.t0, FEAT, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dfused
+    rc = gemm_bf16(w.dh2, H2, 0, s.wf1b, FEAT, 1, (int)B, FEAT, H2, w.t0, FEAT, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dfused
     if (rc) return rc;
     const float *dfeat = w.t0;
     const float *dz = nullptr;
     if (gated) {
-        // ---- gate: softmax / scaling backward, gate.2 and gate.0
-        k_gate_apply_bwd<<<gs(B * 32), 256, 0, st>>>(w.t0, s.feat, s.gate, s.zh, p->gate2_w, d_gate, B, w.t1, w.dlogit,
-                                                     w.b0);                       // t1 = dfeat, b0 = dzh [B][64]
-        for (int k = 0; k < 3; ++k)
-            rowscale_sum(s.zh, GH, w.dlogit + k, 3, B, GH, w.partial, g->gate2_w + k * GH, w.v0 + k, st);
-        B200_CHECK_CUDA(cudaMemcpyAsync(g->gate2_b, w.v0, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        rc = gemm_wgrad(w.b0, GH, s.z, GZP, GH, GZ, (int)B, g->gate0_w, GZ, w.splitk, st);
+        // ---- gate: softmax / scaling backward with the gate.2 gradients and gate.0.bias as partial sums; gate.0
+        k_gate_bwd_fused<<<nsl, 256, 0, st>>>(w.t0, s.feat, s.gate, s.zh, p->gate2_w, d_gate, B, w.t1, w.dzh, w.p_gate);
+        if ((rc = fork())) return rc;
+        {
+            SumSegs sg; sg.n = 3;
+            sg.out[0] = g->gate2_w; sg.out[1] = g->gate2_b; sg.out[2] = g->gate0_b; sg.out[3] = nullptr;
+            sg.c0[0] = 0; sg.c0[1] = 3 * GH; sg.c0[2] = 3 * GH + 3; sg.c0[3] = GP_COLS; sg.c0[4] = GP_COLS;
+            sums(w.p_gate, GP_COLS, sg);
+        }
+        rc = gemm_wgrad(w.dzh, GH, s.z, GZP, GH, GZ, (int)B, g->gate0_w, GZ, w.splitk, sd);
         if (rc) return rc;
-        col_sum_bf16(w.b0, B, GH, w.t2, w.partial, g->gate0_b, st);
-        rc = gemm_bf16(w.b0, GH, 0, s.wg1b, GZP, 1, (int)B, GZP, GH, w.t0, GZP, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dz
+        rc = gemm_bf16(w.dzh, GH, 0, s.wg1b, GZP, 1, (int)B, GZP, GH, w.t0, GZP, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dz
         if (rc) return rc;
         dfeat = w.t1;
         dz = w.t0;
     }
-    // ---- masks, clinical encoder
-    k_gate_prep_bwd<<<gs(B * FEAT), 256, 0, st>>>(dfeat, dz, GZP, mask, s.r, clinical, p->clin_w, p->clin_b, B, d_ct_feat,
-                                                  w.b1, w.dC);                    // b1 = dR [B][128]
-    rowscale_sum(w.dC, CL, clinical, 1, B, CL, w.partial, g->clin_w, nullptr, st);
-    col_sum(w.dC, CL, B, CL, w.partial, g->clin_b, st);
-    // ---- rna_encoder.4: dW = dR^T a1, db, dA1 = dR W2
-    rc = gemm_wgrad(w.b1, R1, s.a1, H1, R1, H1, (int)B, g->rna4_w, H1, w.splitk, st);
+    // ---- masks, clinical encoder (its two gradients and rna_encoder.4.bias as partial sums)
+    k_prep_bwd_fused<<<nsl, FEAT, 0, st>>>(dfeat, dz, GZP, mask, s.r, clinical, p->clin_w, p->clin_b, B, d_ct_feat, w.dR, w.p_prep);
+    if ((rc = fork())) return rc;
+    {
+        SumSegs sg; sg.n = 3;
+        sg.out[0] = g->rna4_b; sg.out[1] = g->clin_w; sg.out[2] = g->clin_b; sg.out[3] = nullptr;
+        sg.c0[0] = 0; sg.c0[1] = R1; sg.c0[2] = R1 + CL; sg.c0[3] = PP_COLS; sg.c0[4] = PP_COLS;
+        sums(w.p_prep, PP_COLS, sg);
+    }
+    // ---- rna_encoder.4: dW = dR^T a1 (side), dA1 = dR W2
+    rc = gemm_wgrad(w.dR, R1, s.a1, H1, R1, H1, (int)B, g->rna4_w, H1, w.splitk, sd);
     if (rc) return rc;
-    col_sum_bf16(w.b1, B, R1, w.t2, w.partial, g->rna4_b, st);
-    rc = gemm_bf16(w.b1, R1, 0, s.w2b, H1, 1, (int)B, H1, R1, w.t0, H1, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dA1 [B][512]
+    rc = gemm_bf16(w.dR, R1, 0, s.w2b, H1, 1, (int)B, H1, R1, w.t0, H1, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dA1 [B][512]
     if (rc) return rc;
-    // ---- rna_encoder.1-3 backward -> dH1 (bf16, b0)
-    k_bn_bwd_dy<<<gs(B * H1), 256, 0, st>>>(w.t0, H1, s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh, inv_keep,
-                                            seed, seed_dev, 1, w.t1);
-    colreduce<1>(w.t1, H1, s.h1, H1, s.mu1, s.rstd1, nullptr, 0, B, H1, w.partial, nsl, st);
-    k_colreduce_final<<<colfinal_grid(H1), 256, 0, st>>>(w.partial, nsl, H1, 1.f, g->bn1_b, g->bn1_w);
-    k_bn_bwd_dx<<<gs(B * H1), 256, 0, st>>>(w.t1, s.h1, H1, s.mu1, s.rstd1, p->bn1_w, g->bn1_b, g->bn1_w, B, H1, training,
-                                            w.b0, H1);                             // b0 = dH1
-    k_bn_bias_grad<<<(H1 + 255) / 256, 256, 0, st>>>(g->bn1_b, p->bn1_w, s.rstd1, H1, training, g->rna0_b);
-    // ---- rna_encoder.0: dW1 [512][rna_dim] = dH1^T x  (the big one; x is an input, no dx)
-    rc = gemm_wgrad(w.b0, H1, s.xb, Kp, H1, rna_dim, (int)B, g->rna0_w, rna_dim, w.splitk, st);
+    // ---- rna_encoder.1-3 backward -> dH1 (bf16); rna_encoder.0.bias with it
+    k_bn_bwd_stats<<<dim3(H1 / 32, nsl), 256, 0, st>>>(w.t0, H1, s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh, inv_keep,
+                                                       seed, seed_dev, 1, w.partial);
+    k_bn_bwd_final<<<colfinal_grid(H1), 256, 0, st>>>(w.partial, nsl, H1, p->bn1_w, s.rstd1, training, g->bn1_b, g->bn1_w, g->rna0_b);
+    k_bn_bwd_dx2<<<gs(B * H1), 256, 0, st>>>(w.t0, H1, s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, g->bn1_b, g->bn1_w, B, H1,
+                                             training, thresh, inv_keep, seed, seed_dev, 1, w.dh1, H1);
+    // ---- rna_encoder.0: dW1 [512][rna_dim] = dH1^T x  (the big one; x is an input, no dx): CTA pairs for large batches
+    if (B >= 512 && rna_dim >= 2048)
+        rc = gemm_bf16_ex(w.dh1, H1, 1, s.xb, Kp, 1, H1, rna_dim, (int)B, g->rna0_w, rna_dim, nullptr, 0, nullptr, 0, nullptr, 512, 0, st);
+    else
+        rc = gemm_wgrad(w.dh1, H1, s.xb, Kp, H1, rna_dim, (int)B, g->rna0_w, rna_dim, w.splitk, st);
     if (rc) return rc;
+    if (lanes) {  // join: the caller's stream continues after the side stream's work
+        B200_CHECK_CUDA(cudaEventRecord(lanes->join, sd));
+        B200_CHECK_CUDA(cudaStreamWaitEvent(st, lanes->join, 0));
+    }
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }

@@ -61,3 +61,42 @@ def test_gemm_epilogue_bias_relu_bf16():
     assert (c - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
     assert (cb[:, :N].float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
     assert torch.all(cb[:, N:] == 0)
+
+
+@pytest.mark.parametrize("tile_n", [192, 256, 512])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+def test_gemm_wide_tiles(tile_n, a_mn, b_mn):
+    """b200surv_gemm_bf16_ex: 128 x 192 and 128 x 256 tiles (TMEM accumulators of 256 columns) and, tile_n = 512, CTA pairs on
+    256 x 256 tiles (tcgen05.mma.cta_group::2); ragged shapes, epilogue."""
+    lib = L.load()
+    for i, (M, N, K) in enumerate([(128, 256, 64), (4096, 512, 5005), (512, 5005, 4096), (300, 200, 136), (129, 385, 65), (4, 512, 5005)]):
+        a = padded(K, M, 20 + i) if a_mn else padded(M, K, 20 + i)
+        b = padded(K, N, 70 + i) if b_mn else padded(N, K, 70 + i)
+        A = a.float().t() if a_mn else a.float()
+        Bm = b.float() if b_mn else b.float().t()
+        bias = torch.randn(N, device="cuda")
+        ref = torch.relu(A @ Bm + bias)
+        c = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+        cb = torch.zeros((M, (N + 7) // 8 * 8), dtype=torch.bfloat16, device="cuda")
+        for want_bf16 in (False, True):       # one output: staged, coalesced epilogue; two outputs: direct stores
+            rc = lib.b200surv_gemm_bf16_ex(L.ptr(a), a.stride(0), int(a_mn), L.ptr(b), b.stride(0), int(b_mn), M, N, K, L.ptr(c),
+                                           c.stride(0), L.ptr(cb) if want_bf16 else None, cb.stride(0) if want_bf16 else 0,
+                                           L.ptr(bias), 1, tile_n, 1, None, L.stream_ptr(a.device))
+            L.check(rc, "b200surv_gemm_bf16_ex")
+            scale = ref.abs().max().item() + 1e-6
+            assert (c - ref).abs().max().item() <= 2e-4 * scale, (M, N, K, tile_n, a_mn, b_mn, want_bf16)
+            if want_bf16:
+                assert (cb[:, :N].float() - ref).abs().max().item() <= 1e-2 * scale
+
+
+@pytest.mark.parametrize("tile_n,splits", [(256, 2), (128, 3), (192, 4), (512, 2)])
+def test_gemm_forced_k_split(tile_n, splits):
+    lib = L.load()
+    M, N, K = 4096, 512, 5005
+    a, b = padded(M, K, 5), padded(N, K, 6)
+    ref = a.float() @ b.float().t()
+    sl = torch.full((splits, M, N), float("nan"), dtype=torch.float32, device="cuda")
+    rc = lib.b200surv_gemm_bf16_ex(L.ptr(a), a.stride(0), 0, L.ptr(b), b.stride(0), 0, M, N, K, None, N, None, 0, None, 0,
+                                   tile_n, splits, L.ptr(sl), L.stream_ptr(a.device))
+    L.check(rc, "b200surv_gemm_bf16_ex")
+    assert (sl.sum(0) - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
