@@ -46,6 +46,7 @@ constexpr int GZ = FEAT + 3, GZP = 296;                                      // 
 constexpr int GH = 64, H2 = 256, F2N = 128;
 constexpr float BN_EPS = 1e-5f, BN_MOM = 0.1f;
 constexpr int RS_MAX = 128;  // row slices of the column reductions
+constexpr int FS_MAX = 512;  // row slices of the fused backward reductions (8 rows per slice at B = 4096)
 constexpr int SPLITK_ELEMS = 256 * 512;  // largest weight gradient that is split along K (all but rna_encoder.0)
 
 __device__ __forceinline__ uint32_t rng32(uint64_t seed, uint32_t layer, uint64_t idx) {  // splitmix64
@@ -176,23 +177,40 @@ k_bn_finalize(const double *__restrict__ partial, int nslices, int64_t B, int N,
         rstd[n] = rsqrtf(run_var[n] + BN_EPS);
     }
 }
-// y = dropout(relu(bn(x))) as bf16 (the next GEMM's A operand); optional keep-mask export for tests
+// y = dropout(relu(bn(x))) as bf16 (the next GEMM's A operand); optional keep-mask export for tests.
+// Four consecutive columns per thread (N, ldx, ldy multiples of 4): 16-byte loads, 8-byte stores.
 __global__ void k_bn_apply(const float *__restrict__ x, int64_t ldx, const float *__restrict__ mu,
                            const float *__restrict__ rstd, const float *__restrict__ gamma,
                            const float *__restrict__ beta, int64_t B, int N, uint32_t thresh, float inv_keep,
                            uint64_t seed, const uint64_t *__restrict__ seed_dev, uint32_t layer, bf16 *__restrict__ y,
                            int64_t ldy, uint8_t *__restrict__ keep_out) {
     if (seed_dev != nullptr) seed = *seed_dev;  // (CUDA-graph replays: the seed lives in device memory)
-    const int64_t total = B * N;
+    const int n4 = N >> 2;
+    const int64_t total = B * n4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = row_of(i, N);
-        const int n = (int)(i - r * N);
-        float v = (x[r * ldx + n] - mu[n]) * rstd[n] * gamma[n] + beta[n];
-        v = fmaxf(v, 0.f);
-        bool keep = true;
-        if (thresh) { keep = keep_elem(seed, layer, (uint64_t)i, thresh); v = keep ? v * inv_keep : 0.f; }
-        if (keep_out) keep_out[i] = keep ? 1 : 0;
-        y[r * ldy + n] = __float2bfloat16_rn(v);
+        const int64_t r = row_of(i, n4);
+        const int n = (int)(i - r * n4) << 2;
+        const float4 xv = *reinterpret_cast<const float4 *>(x + r * ldx + n);
+        // (the per-column vectors are read element-wise: caller-owned parameter pointers need not be 16-byte aligned)
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = fmaxf((xs[u] - mu[n + u]) * rstd[n + u] * gamma[n + u] + beta[n + u], 0.f);
+        uint8_t kp[4] = {1, 1, 1, 1};
+        if (thresh) {
+            const uint64_t e0 = (uint64_t)(r * N + n);  // element index r * N + column, as the backward kernels derive it
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool keep = keep_elem(seed, layer, e0 + u, thresh);
+                kp[u] = keep ? 1 : 0;
+                v[u] = keep ? v[u] * inv_keep : 0.f;
+            }
+        }
+        if (keep_out) *reinterpret_cast<uchar4 *>(keep_out + r * N + n) = make_uchar4(kp[0], kp[1], kp[2], kp[3]);
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 u2;
+        u2.x = *reinterpret_cast<uint32_t *>(&p0); u2.y = *reinterpret_cast<uint32_t *>(&p1);
+        *reinterpret_cast<uint2 *>(y + r * ldy + n) = u2;
     }
 }
 // ---------------------------------------------------------------- mask / clinical encoder / gate
@@ -261,17 +279,20 @@ k_cox_head(const float *__restrict__ f2, const float *__restrict__ w, const floa
 }
 // ---------------------------------------------------------------- fused reductions (round 2)
 // one launch for the bf16 copies of all weight matrices (K padded with zeros where the TMA row pitch needs it)
+// (segment k owns the blocks [b0[k], b0[k + 1]): all matrices are converted at the same time)
 struct CastSeg { const float *src; bf16 *dst; int lds, ldd, R, C, Cp; };
-struct CastSegs { CastSeg s[5]; int n; };
+struct CastSegs { CastSeg s[5]; int b0[6]; int n; };
 __global__ void __launch_bounds__(256)
 k_cast_multi(const CastSegs segs) {
-    for (int k = 0; k < segs.n; ++k) {
-        const CastSeg g = segs.s[k];
-        const int64_t total = (int64_t)g.R * g.Cp;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-            const int r = (int)((unsigned)i / (unsigned)g.Cp), c = (int)(i - (int64_t)r * g.Cp);
-            g.dst[(int64_t)r * g.ldd + c] = __float2bfloat16_rn(c < g.C ? g.src[(int64_t)r * g.lds + c] : 0.f);
-        }
+    int k = 0;
+#pragma unroll
+    for (int q = 1; q < 5; ++q) k += (q < segs.n && (int)blockIdx.x >= segs.b0[q]) ? 1 : 0;
+    const CastSeg g = segs.s[k];
+    const int nb = segs.b0[k + 1] - segs.b0[k], bx = blockIdx.x - segs.b0[k];
+    const int64_t total = (int64_t)g.R * g.Cp;
+    for (int64_t i = (int64_t)bx * blockDim.x + threadIdx.x; i < total; i += (int64_t)nb * blockDim.x) {
+        const int r = (int)((unsigned)i / (unsigned)g.Cp), c = (int)(i - (int64_t)r * g.Cp);
+        g.dst[(int64_t)r * g.ldd + c] = __float2bfloat16_rn(c < g.C ? g.src[(int64_t)r * g.lds + c] : 0.f);
     }
 }
 
@@ -331,12 +352,24 @@ k_bn_bwd_stats(const float *__restrict__ dA, int64_t ldd, const float *__restric
     double v0 = 0.0, v1 = 0.0;
     if (n < N) {
         const float m = mu[n], rs = rstd[n], ga = gamma[n], be = beta[n];
-        for (int64_t r = r0 + ty; r < r1; r += 8) {
-            const float xh = (x[r * ldx + n] - m) * rs;
-            float g = dA[r * ldd + n];
-            if (thresh) g = keep_elem(seed, layer, (uint64_t)(r * N + n), thresh) ? g * inv_keep : 0.f;
-            const float dy = (xh * ga + be > 0.f) ? g : 0.f;
-            v0 += dy; v1 += (double)dy * xh;
+        for (int64_t rb = r0 + ty; rb < r1; rb += 32) {  // four rows in flight per thread
+            float xv[4], gv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t r = rb + 8 * u;
+                xv[u] = r < r1 ? x[r * ldx + n] : 0.f; gv[u] = r < r1 ? dA[r * ldd + n] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t r = rb + 8 * u;
+                if (r < r1) {
+                    const float xh = (xv[u] - m) * rs;
+                    float g = gv[u];
+                    if (thresh) g = keep_elem(seed, layer, (uint64_t)(r * N + n), thresh) ? g * inv_keep : 0.f;
+                    const float dy = (xh * ga + be > 0.f) ? g : 0.f;
+                    v0 += dy; v1 += (double)dy * xh;
+                }
+            }
         }
     }
     sh0[ty][tx] = v0; sh1[ty][tx] = v1;
@@ -363,24 +396,44 @@ k_bn_bwd_final(const double *__restrict__ partial, int nslices, int N, const flo
         dbias[n] = training ? 0.f : gamma[n] * rstd[n] * (float)v0;
     }
 }
-// pass 3: dx (bf16) = gamma * rstd * (dy - sdy / B - xhat * sdyx / B) (train) or gamma * rstd * dy (eval), dy re-derived
+// pass 3: dx (bf16) = gamma * rstd * (dy - sdy / B - xhat * sdyx / B) (train) or gamma * rstd * dy (eval), dy re-derived.
+// Four consecutive columns per thread (N and the pitches are multiples of 4).
 __global__ void k_bn_bwd_dx2(const float *__restrict__ dA, int64_t ldd, const float *__restrict__ x, int64_t ldx,
                              const float *__restrict__ mu, const float *__restrict__ rstd, const float *__restrict__ gamma,
                              const float *__restrict__ beta, const float *__restrict__ sdy, const float *__restrict__ sdyx,
                              int64_t B, int N, int training, uint32_t thresh, float inv_keep, uint64_t seed,
                              const uint64_t *__restrict__ seed_dev, uint32_t layer, bf16 *__restrict__ dx, int64_t lddx) {
     if (seed_dev != nullptr) seed = *seed_dev;
-    const int64_t total = B * N;
+    const int n4 = N >> 2;
+    const int64_t total = B * n4;
     const float invB = 1.f / (float)B;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = row_of(i, N);
-        const int n = (int)(i - r * N);
-        const float xh = (x[r * ldx + n] - mu[n]) * rstd[n];
-        float g = dA[r * ldd + n];
-        if (thresh) g = keep_elem(seed, layer, (uint64_t)i, thresh) ? g * inv_keep : 0.f;
-        float v = (xh * gamma[n] + beta[n] > 0.f) ? g : 0.f;
-        if (training) v = v - sdy[n] * invB - xh * sdyx[n] * invB;
-        dx[r * lddx + n] = __float2bfloat16_rn(v * gamma[n] * rstd[n]);
+        const int64_t r = row_of(i, n4);
+        const int n = (int)(i - r * n4) << 2;
+        const float4 xv4 = *reinterpret_cast<const float4 *>(x + r * ldx + n), g4 = *reinterpret_cast<const float4 *>(dA + r * ldd + n);
+        // (the per-column vectors are read element-wise: the gradient vectors sit at arbitrary offsets of the caller's buffer)
+        const float xs[4] = {xv4.x, xv4.y, xv4.z, xv4.w}, gs_[4] = {g4.x, g4.y, g4.z, g4.w};
+        float ms[4], rs[4], ga[4], be[4], sd[4], sx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ms[u] = mu[n + u]; rs[u] = rstd[n + u]; ga[u] = gamma[n + u]; be[u] = beta[n + u];
+            sd[u] = sdy[n + u]; sx[u] = sdyx[n + u];
+        }
+        const uint64_t e0 = (uint64_t)(r * N + n);
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float xh = (xs[u] - ms[u]) * rs[u];
+            float g = gs_[u];
+            if (thresh) g = keep_elem(seed, layer, e0 + u, thresh) ? g * inv_keep : 0.f;
+            float v = (xh * ga[u] + be[u] > 0.f) ? g : 0.f;
+            if (training) v = v - sd[u] * invB - xh * sx[u] * invB;
+            o[u] = v * ga[u] * rs[u];
+        }
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+        uint2 u2;
+        u2.x = *reinterpret_cast<uint32_t *>(&p0); u2.y = *reinterpret_cast<uint32_t *>(&p1);
+        *reinterpret_cast<uint2 *>(dx + r * lddx + n) = u2;
     }
 }
 
@@ -394,11 +447,21 @@ k_cox_bwd_fused(const float *__restrict__ dhz, const float *__restrict__ f2, con
     const int64_t rows_per = (B + nslices - 1) / nslices, r0 = slice * rows_per, r1 = min(B, r0 + rows_per);
     const float wj = w[j];
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int64_t b = r0; b < r1; ++b) {
-        const float d = dhz[b], f = f2[b * F2N + j];
-        const bf16 q = __float2bfloat16_rn(f > 0.f ? d * wj : 0.f);
-        df2[b * F2N + j] = q;
-        a0 += (double)d * f; a1 += (double)__bfloat162float(q); a2 += d;
+    for (int64_t b0 = r0; b0 < r1; b0 += 8) {  // the loads of eight rows in flight together
+        float d[8], f[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool in = b0 + u < r1;
+            d[u] = in ? dhz[b0 + u] : 0.f; f[u] = in ? f2[(b0 + u) * F2N + j] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (b0 + u < r1) {
+                const bf16 q = __float2bfloat16_rn(f[u] > 0.f ? d[u] * wj : 0.f);
+                df2[(b0 + u) * F2N + j] = q;
+                a0 += (double)d[u] * f[u]; a1 += (double)__bfloat162float(q); a2 += d[u];
+            }
+        }
     }
     double *p = partial + (size_t)slice * (3 * F2N);
     p[j] = a0; p[F2N + j] = a1;
@@ -494,19 +557,31 @@ k_prep_bwd_fused(const float *__restrict__ dfeat, const float *__restrict__ dz, 
     const int k = grp == 0 ? j : (grp == 1 ? j - CT : j - CT - R1);
     const float wck = grp == 2 ? wc[k] : 0.f, bck = grp == 2 ? bc[k] : 0.f;
     double a0 = 0.0, a1 = 0.0;
-    for (int64_t b = r0; b < r1; ++b) {
-        float v = dfeat[b * FEAT + j] + (dz ? dz[b * lddz + j] : 0.f);
-        v *= mask ? mask[b * 3 + grp] : 1.f;
-        if (grp == 0) {
-            if (d_ct) d_ct[b * CT + k] = v;
-        } else if (grp == 1) {
-            const bf16 q = __float2bfloat16_rn(R[b * R1 + k] > 0.f ? v : 0.f);
-            dR[b * R1 + k] = q;
-            a0 += (double)__bfloat162float(q);
-        } else {
-            const float c = clin[b];
-            const float dc = (c * wck + bck > 0.f) ? v : 0.f;
-            a0 += (double)dc * c; a1 += dc;
+    for (int64_t b0 = r0; b0 < r1; b0 += 8) {  // the loads of eight rows in flight together
+        float v[8], aux[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int64_t b = b0 + u;
+            const bool in = b < r1;
+            v[u] = in ? dfeat[b * FEAT + j] + (dz ? dz[b * lddz + j] : 0.f) : 0.f;
+            v[u] *= (in && mask) ? mask[b * 3 + grp] : 1.f;
+            aux[u] = !in ? 0.f : (grp == 1 ? R[b * R1 + k] : (grp == 2 ? clin[b] : 0.f));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int64_t b = b0 + u;
+            if (b < r1) {
+                if (grp == 0) {
+                    if (d_ct) d_ct[b * CT + k] = v[u];
+                } else if (grp == 1) {
+                    const bf16 q = __float2bfloat16_rn(aux[u] > 0.f ? v[u] : 0.f);
+                    dR[b * R1 + k] = q;
+                    a0 += (double)__bfloat162float(q);
+                } else {
+                    const float dc = (aux[u] * wck + bck > 0.f) ? v[u] : 0.f;
+                    a0 += (double)dc * aux[u]; a1 += dc;
+                }
+            }
         }
     }
     double *p = partial + (size_t)slice * PP_COLS;
@@ -521,6 +596,7 @@ inline int gs(int64_t total) {  // grid for grid-stride element-wise kernels
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 inline int nslices_for(int64_t B) { int64_t s = (B + 31) / 32; return (int)(s < 1 ? 1 : (s > RS_MAX ? RS_MAX : s)); }
+inline int fslices_for(int64_t B) { int64_t s = (B + 7) / 8; return (int)(s < 1 ? 1 : (s > FS_MAX ? FS_MAX : s)); }
 
 struct Carver {
     unsigned char *base;
@@ -576,9 +652,9 @@ Scratch carve_scratch(void *buf, int64_t B, size_t *bytes) {
     Carver c{static_cast<unsigned char *>(buf), 0};
     Scratch s;
     s.partial = c.take<double>((size_t)RS_MAX * 2 * H1);
-    s.p_cox = c.take<double>((size_t)RS_MAX * 3 * F2N);
-    s.p_gate = c.take<double>((size_t)RS_MAX * GP_COLS);
-    s.p_prep = c.take<double>((size_t)RS_MAX * PP_COLS);
+    s.p_cox = c.take<double>((size_t)FS_MAX * 3 * F2N);
+    s.p_gate = c.take<double>((size_t)FS_MAX * GP_COLS);
+    s.p_prep = c.take<double>((size_t)FS_MAX * PP_COLS);
     s.t0 = c.take<float>((size_t)B * H1); s.t1 = c.take<float>((size_t)B * H1);
     s.slices = c.take<float>((size_t)2 * B * H1);
     s.df2 = c.take<bf16>((size_t)B * F2N); s.dh2 = c.take<bf16>((size_t)B * H2); s.dzh = c.take<bf16>((size_t)B * GH);
@@ -724,7 +800,12 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
         if (gated) add(p->gate0_w, GZ, s.wg1b, GZP, GH, GZ, GZP);
         add(p->fus0_w, FEAT, s.wf1b, FEAT, H2, FEAT, FEAT);
         add(p->fus4_w, H2, s.wf2b, H2, F2N, H2, H2);
-        k_cast_multi<<<gs((int64_t)H1 * Kp), 256, 0, st>>>(cs);
+        cs.b0[0] = 0;
+        for (int k = 0; k < cs.n; ++k) {  // ~4 elements per thread, at least one block per matrix
+            const int64_t blocks = ((int64_t)cs.s[k].R * cs.s[k].Cp + 1023) / 1024;
+            cs.b0[k + 1] = cs.b0[k] + (int)(blocks < 1 ? 1 : blocks);
+        }
+        k_cast_multi<<<cs.b0[cs.n], 256, 0, st>>>(cs);
     }
 
     // rna encoder: Linear(rna_dim, 512) -> BN -> ReLU -> Dropout -> Linear(512, 128) -> ReLU
@@ -800,12 +881,13 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
         B200_CHECK_CUDA(cudaStreamWaitEvent(sd, lanes->fork, 0));
         return B200SURV_OK;
     };
+    const int fsl = fslices_for(B);
     auto sums = [&](const double *partial, int ncols, SumSegs sg) {
-        k_sum_slices<<<(ncols + 7) / 8, 256, 0, sd>>>(partial, nsl, ncols, sg);
+        k_sum_slices<<<(ncols + 7) / 8, 256, 0, sd>>>(partial, fsl, ncols, sg);
     };
 
     // ---- cox head: df2 (ReLU-masked, bf16) + partial sums of cox_head.weight / .bias and fusion.4.bias, one launch
-    k_cox_bwd_fused<<<nsl, F2N, 0, st>>>(d_hazard, s.f2, p->cox_w, B, w.df2, w.p_cox);
+    k_cox_bwd_fused<<<fsl, F2N, 0, st>>>(d_hazard, s.f2, p->cox_w, B, w.df2, w.p_cox);
     if ((rc = fork())) return rc;
     {
         SumSegs sg; sg.n = 3;
@@ -834,7 +916,7 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     const float *dz = nullptr;
     if (gated) {
         // ---- gate: softmax / scaling backward with the gate.2 gradients and gate.0.bias as partial sums; gate.0
-        k_gate_bwd_fused<<<nsl, 256, 0, st>>>(w.t0, s.feat, s.gate, s.zh, p->gate2_w, d_gate, B, w.t1, w.dzh, w.p_gate);
+        k_gate_bwd_fused<<<fsl, 256, 0, st>>>(w.t0, s.feat, s.gate, s.zh, p->gate2_w, d_gate, B, w.t1, w.dzh, w.p_gate);
         if ((rc = fork())) return rc;
         {
             SumSegs sg; sg.n = 3;
@@ -850,7 +932,7 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
         dz = w.t0;
     }
     // ---- masks, clinical encoder (its two gradients and rna_encoder.4.bias as partial sums)
-    k_prep_bwd_fused<<<nsl, FEAT, 0, st>>>(dfeat, dz, GZP, mask, s.r, clinical, p->clin_w, p->clin_b, B, d_ct_feat, w.dR, w.p_prep);
+    k_prep_bwd_fused<<<fsl, FEAT, 0, st>>>(dfeat, dz, GZP, mask, s.r, clinical, p->clin_w, p->clin_b, B, d_ct_feat, w.dR, w.p_prep);
     if ((rc = fork())) return rc;
     {
         SumSegs sg; sg.n = 3;
