@@ -290,6 +290,12 @@ size_t b200surv_head_workspace_bytes(int64_t B, int32_t rna_dim); /* scratch of 
  * replay once the caller bumps that word between replays.
  * Outputs: hazard [B], gate [B][3]. */
 #define B200SURV_HEAD_TRAIN_SEED_DEV 2
+/* OR-ed into `training`: the bf16 copy of `rna` already sits in the saved buffer (b200surv_head_stage_rna wrote it), `rna`
+ * is not read.  A captured CUDA graph of the step then needs no copy of the 82 MB batch into a static input buffer: the
+ * caller converts every new batch straight into the graph's saved buffer before the replay. */
+#define B200SURV_HEAD_X_STAGED 4
+int32_t b200surv_head_stage_rna(const float *rna, int64_t B, int32_t rna_dim, void *saved, size_t saved_bytes,
+                                b200surv_stream_t stream);
 int32_t b200surv_head_fwd(const b200surv_head_params *params, const float *ct_feat, const float *rna,
                           const float *clinical, const float *mask, int64_t B, int32_t rna_dim,
                           int32_t training, float dropout_p, uint64_t seed, float *hazard, float *gate,

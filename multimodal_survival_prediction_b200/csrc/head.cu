@@ -277,6 +277,206 @@ k_cox_head(const float *__restrict__ f2, const float *__restrict__ w, const floa
         if (lane == 0) hazard[b] = s + bias[0];
     }
 }
+// ---------------------------------------------------------------- BatchNorm1d, column-block kernels (round 2)
+// A CTA owns BC = 128 consecutive columns: 32 column quads x 8 row lanes, 16-byte loads.  Two launches per direction
+// instead of three: the kernel that CONSUMES the statistics (apply / dx) sums the row-slice partials of its own 128
+// columns in its prologue (<= 32 slices, fixed order: deterministic) -- there is no separate finalize launch; the CTAs of
+// the first row group also write what has to be kept (mu, rstd, running statistics / dbeta, dgamma, bias gradient).
+constexpr int BC = 128, BS_MAX = 64, BR = 64;  // columns per CTA, row slices of the sums, rows per CTA of apply / dx
+inline int bn_slices(int64_t B) { int64_t s = (B + 63) / 64; return (int)(s < 1 ? 1 : (s > BS_MAX ? BS_MAX : s)); }
+
+// partial[slice][2][N] (fp64).  MODE 0: (sum a, sum a^2).  MODE 2: a = s0 + s1 + bias (the two K slices of the split
+// rna_encoder.0 GEMM), stored to h, then as MODE 0 (want_stats == 0: only the combination).  MODE 1: (sum dy, sum dy * xhat)
+// with dy = dA * keep/(1-p) * [bn(x) > 0] formed on the fly.  grid (N / 128, slices), 256 threads.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_bn_colstats(const float *__restrict__ a, const float *__restrict__ s1, const float *__restrict__ bias,
+              const float *__restrict__ x, const float *__restrict__ mu, const float *__restrict__ rstd,
+              const float *__restrict__ gamma, const float *__restrict__ beta, int64_t B, int N, uint32_t thresh, float inv_keep,
+              uint64_t seed, const uint64_t *__restrict__ seed_dev, uint32_t layer, int want_stats, float *__restrict__ h,
+              double *__restrict__ partial) {
+    __shared__ double sh[8][2][BC];
+    if (MODE == 1 && seed_dev != nullptr) seed = *seed_dev;
+    const int tq = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * BC + 4 * tq, slice = blockIdx.y, nslices = gridDim.y;
+    const int64_t rows_per = (B + nslices - 1) / nslices, r0 = slice * rows_per, r1 = min(B, r0 + rows_per);
+    double v0[4] = {0.0, 0.0, 0.0, 0.0}, v1[4] = {0.0, 0.0, 0.0, 0.0};
+    float cm[4] = {0.f, 0.f, 0.f, 0.f}, cr[4] = {0.f, 0.f, 0.f, 0.f}, cg[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (MODE == 2) cb[u] = bias[n + u];
+        if (MODE == 1) { cm[u] = mu[n + u]; cr[u] = rstd[n + u]; cg[u] = gamma[n + u]; cb[u] = beta[n + u]; }
+    }
+    for (int64_t rb = r0 + ty; rb < r1; rb += 32) {  // four rows in flight per thread
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t r = rb + 8 * q;
+            av[q] = make_float4(0.f, 0.f, 0.f, 0.f); bv[q] = av[q];
+            if (r < r1) {
+                av[q] = *reinterpret_cast<const float4 *>(a + r * N + n);
+                if (MODE == 2) bv[q] = *reinterpret_cast<const float4 *>(s1 + r * N + n);
+                if (MODE == 1) bv[q] = *reinterpret_cast<const float4 *>(x + r * N + n);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t r = rb + 8 * q;
+            if (r >= r1) continue;
+            const float aa[4] = {av[q].x, av[q].y, av[q].z, av[q].w}, bb[4] = {bv[q].x, bv[q].y, bv[q].z, bv[q].w};
+            float o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (MODE == 0) { v0[u] += aa[u]; v1[u] += (double)aa[u] * aa[u]; }
+                if (MODE == 2) { const float xx = (aa[u] + bb[u]) + cb[u]; o[u] = xx; v0[u] += xx; v1[u] += (double)xx * xx; }
+                if (MODE == 1) {
+                    const float xh = (bb[u] - cm[u]) * cr[u];
+                    float g = aa[u];
+                    if (thresh) g = keep_elem(seed, layer, (uint64_t)(r * N + n + u), thresh) ? g * inv_keep : 0.f;
+                    const float dy = (xh * cg[u] + cb[u] > 0.f) ? g : 0.f;
+                    v0[u] += dy; v1[u] += (double)dy * xh;
+                }
+            }
+            if (MODE == 2) *reinterpret_cast<float4 *>(h + r * N + n) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    if (MODE == 2 && !want_stats) return;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { sh[ty][0][4 * tq + u] = v0[u]; sh[ty][1][4 * tq + u] = v1[u]; }
+    __syncthreads();
+    {
+        const int c = threadIdx.x & (BC - 1), st = threadIdx.x >> 7;  // 256 threads = 128 columns x 2 sums
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += sh[k][st][c];
+        partial[((size_t)slice * 2 + st) * N + blockIdx.x * BC + c] = v;
+    }
+}
+
+// sums the row-slice partials of this CTA's 128 columns into shared memory: out[st][c], st = 0 / 1 (all threads call)
+__device__ __forceinline__ void bn_block_sums(const double *__restrict__ partial, int nslices, int N, double (*out)[BC]) {
+    const int c = threadIdx.x & (BC - 1), st = threadIdx.x >> 7;
+    double pv[BS_MAX];  // all loads in flight together (one L2 round trip), then summed in slice order
+#pragma unroll
+    for (int k = 0; k < BS_MAX; ++k) pv[k] = k < nslices ? __ldcg(partial + ((size_t)k * 2 + st) * N + blockIdx.x * BC + c) : 0.0;
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < BS_MAX; ++k) v += pv[k];
+    out[st][c] = v;
+    __syncthreads();
+}
+
+// y = dropout(relu(bn(x))) as bf16 (the next GEMM's A operand); optional keep-mask export for tests.
+// train: mu, rstd from the partial sums of k_bn_colstats; running <- 0.9 running + 0.1 (mu, unbiased var).  eval: from the
+// running statistics.  mu / rstd are kept for the backward pass.  grid (N / 128, ceil(B / 64)), 256 threads.
+__global__ void __launch_bounds__(256)
+k_bn_apply2(const float *__restrict__ x, const double *__restrict__ partial, int nslices, const float *__restrict__ gamma,
+            const float *__restrict__ beta, int64_t B, int N, int training, float *__restrict__ run_mean,
+            float *__restrict__ run_var, float *__restrict__ mu_out, float *__restrict__ rstd_out, uint32_t thresh,
+            float inv_keep, uint64_t seed, const uint64_t *__restrict__ seed_dev, uint32_t layer, bf16 *__restrict__ y,
+            uint8_t *__restrict__ keep_out) {
+    __shared__ double sums[2][BC];
+    __shared__ float s_mu[BC], s_rs[BC];
+    if (seed_dev != nullptr) seed = *seed_dev;  // (CUDA-graph replays: the seed lives in device memory)
+    const int cbase = blockIdx.x * BC;
+    if (training) {
+        bn_block_sums(partial, nslices, N, sums);
+        if (threadIdx.x < BC) {
+            const int c = threadIdx.x;
+            const double m = sums[0][c] / (double)B;
+            double var = sums[1][c] / (double)B - m * m;
+            if (var < 0.0) var = 0.0;
+            s_mu[c] = (float)m; s_rs[c] = (float)(1.0 / sqrt(var + (double)BN_EPS));
+            if (blockIdx.y == 0) {
+                mu_out[cbase + c] = s_mu[c]; rstd_out[cbase + c] = s_rs[c];
+                if (run_mean) {
+                    const double unb = var * ((double)B / (double)(B - 1));
+                    run_mean[cbase + c] = (1.f - BN_MOM) * run_mean[cbase + c] + BN_MOM * (float)m;
+                    run_var[cbase + c] = (1.f - BN_MOM) * run_var[cbase + c] + BN_MOM * (float)unb;
+                }
+            }
+        }
+    } else if (threadIdx.x < BC) {
+        const int c = threadIdx.x;
+        s_mu[c] = run_mean[cbase + c]; s_rs[c] = rsqrtf(run_var[cbase + c] + BN_EPS);
+        if (blockIdx.y == 0) { mu_out[cbase + c] = s_mu[c]; rstd_out[cbase + c] = s_rs[c]; }
+    }
+    __syncthreads();
+    const int tq = threadIdx.x & 31, ty = threadIdx.x >> 5, n = cbase + 4 * tq;
+    float m4[4], r4[4], g4[4], b4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { m4[u] = s_mu[4 * tq + u]; r4[u] = s_rs[4 * tq + u]; g4[u] = gamma[n + u]; b4[u] = beta[n + u]; }
+    const int64_t r0 = (int64_t)blockIdx.y * BR, r1 = min(B, r0 + BR);
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+        const float4 xv = *reinterpret_cast<const float4 *>(x + r * N + n);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        float v[4];
+        uint8_t kp[4] = {1, 1, 1, 1};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u] = fmaxf((xs[u] - m4[u]) * r4[u] * g4[u] + b4[u], 0.f);
+            if (thresh) {
+                const bool keep = keep_elem(seed, layer, (uint64_t)(r * N + n + u), thresh);
+                kp[u] = keep ? 1 : 0;
+                v[u] = keep ? v[u] * inv_keep : 0.f;
+            }
+        }
+        if (keep_out) *reinterpret_cast<uchar4 *>(keep_out + r * N + n) = make_uchar4(kp[0], kp[1], kp[2], kp[3]);
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 u2;
+        u2.x = *reinterpret_cast<uint32_t *>(&p0); u2.y = *reinterpret_cast<uint32_t *>(&p1);
+        *reinterpret_cast<uint2 *>(y + r * N + n) = u2;
+    }
+}
+
+// BatchNorm backward, second launch: sdy = sum dy, sdyx = sum dy * xhat from the partials (prologue); the CTAs of the first
+// row group write dbeta = sdy, dgamma = sdyx and the bias gradient of the Linear feeding the BatchNorm, sum_rows dx =
+// (train ? 0 : gamma * rstd * sdy); then dx (bf16) = gamma * rstd * (dy - sdy / B - xhat * sdyx / B) (train) or
+// gamma * rstd * dy (eval), dy re-derived.  grid (N / 128, ceil(B / 64)), 256 threads.
+__global__ void __launch_bounds__(256)
+k_bn_bwd_dx3(const float *__restrict__ dA, const float *__restrict__ x, const double *__restrict__ partial, int nslices,
+             const float *__restrict__ mu, const float *__restrict__ rstd, const float *__restrict__ gamma,
+             const float *__restrict__ beta, int64_t B, int N, int training, uint32_t thresh, float inv_keep, uint64_t seed,
+             const uint64_t *__restrict__ seed_dev, uint32_t layer, float *__restrict__ dbeta, float *__restrict__ dgamma,
+             float *__restrict__ dbias, bf16 *__restrict__ dx) {
+    __shared__ double sums[2][BC];
+    if (seed_dev != nullptr) seed = *seed_dev;
+    const int cbase = blockIdx.x * BC;
+    bn_block_sums(partial, nslices, N, sums);
+    if (blockIdx.y == 0 && threadIdx.x < BC) {
+        const int c = threadIdx.x;
+        dbeta[cbase + c] = (float)sums[0][c]; dgamma[cbase + c] = (float)sums[1][c];
+        dbias[cbase + c] = training ? 0.f : gamma[cbase + c] * rstd[cbase + c] * (float)sums[0][c];
+    }
+    const int tq = threadIdx.x & 31, ty = threadIdx.x >> 5, n = cbase + 4 * tq;
+    const float invB = 1.f / (float)B;
+    float m4[4], r4[4], g4[4], b4[4], sd[4], sx[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        m4[u] = mu[n + u]; r4[u] = rstd[n + u]; g4[u] = gamma[n + u]; b4[u] = beta[n + u];
+        sd[u] = (float)sums[0][4 * tq + u]; sx[u] = (float)sums[1][4 * tq + u];
+    }
+    const int64_t r0 = (int64_t)blockIdx.y * BR, r1 = min(B, r0 + BR);
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+        const float4 xv4 = *reinterpret_cast<const float4 *>(x + r * N + n), gv4 = *reinterpret_cast<const float4 *>(dA + r * N + n);
+        const float xs[4] = {xv4.x, xv4.y, xv4.z, xv4.w}, gs_[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float xh = (xs[u] - m4[u]) * r4[u];
+            float g = gs_[u];
+            if (thresh) g = keep_elem(seed, layer, (uint64_t)(r * N + n + u), thresh) ? g * inv_keep : 0.f;
+            float v = (xh * g4[u] + b4[u] > 0.f) ? g : 0.f;
+            if (training) v = v - sd[u] * invB - xh * sx[u] * invB;
+            o[u] = v * g4[u] * r4[u];
+        }
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+        uint2 u2;
+        u2.x = *reinterpret_cast<uint32_t *>(&p0); u2.y = *reinterpret_cast<uint32_t *>(&p1);
+        *reinterpret_cast<uint2 *>(dx + r * N + n) = u2;
+    }
+}
+
 // ---------------------------------------------------------------- fused reductions (round 2)
 // one launch for the bf16 copies of all weight matrices (K padded with zeros where the TMA row pitch needs it)
 // (segment k owns the blocks [b0[k], b0[k + 1]): all matrices are converted at the same time)
@@ -765,7 +965,9 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
                           const float *mask, int64_t B, int32_t rna_dim, int32_t training, float dropout_p,
                           uint64_t seed, float *hazard, float *gate, uint8_t *keep1, uint8_t *keep2, void *saved,
                           size_t saved_bytes, void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
-    B200_REQUIRE(p && ct_feat && rna && clinical && hazard && saved && workspace, "null pointer");
+    const bool x_staged = (training & B200SURV_HEAD_X_STAGED) != 0;
+    training &= ~B200SURV_HEAD_X_STAGED;
+    B200_REQUIRE(p && ct_feat && (rna || x_staged) && clinical && hazard && saved && workspace, "null pointer");
     B200_REQUIRE(B >= 1 && B < (int64_t)1 << 24, "batch size must be in [1, 2^24)");
     B200_REQUIRE(rna_dim >= 1 && rna_dim <= 65536, "rna_dim");
     B200_REQUIRE(!(training && B < 2), "Expected more than 1 value per channel when training (BatchNorm1d)");
@@ -783,11 +985,12 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
     // training == B200SURV_HEAD_TRAIN_SEED_DEV: `seed` is the address of a uint64 in device memory
     const uint64_t *seed_dev = training == B200SURV_HEAD_TRAIN_SEED_DEV ? reinterpret_cast<const uint64_t *>(static_cast<uintptr_t>(seed)) : nullptr;
     const float inv_keep = 1.f / (1.f - dropout_p);
-    const int nsl = nslices_for(B);
+    const int bsl = bn_slices(B);
     int32_t rc;
 
-    // bf16 operand copies (K padded to a multiple of 8 for the TMA row pitch): the batch, then all weights in one launch
-    cast_pad(rna, rna_dim, s.xb, Kp, B, rna_dim, Kp, st);
+    // bf16 operand copies (K padded to a multiple of 8 for the TMA row pitch): the batch (unless the caller staged it with
+    // b200surv_head_stage_rna), then all weights in one launch
+    if (!x_staged) cast_pad(rna, rna_dim, s.xb, Kp, B, rna_dim, Kp, st);
     {
         CastSegs cs;
         cs.n = 0;
@@ -815,16 +1018,19 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
     if (pair1) {
         rc = gemm_bf16_ex(s.xb, Kp, 0, s.w1b, Kp, 0, (int)B, H1, rna_dim, w.slices, H1, nullptr, 0, nullptr, 0, w.slices, 512, 2, st);
         if (rc) return rc;
-        k_bn_stats_combine<<<dim3(H1 / 32, nsl), 256, 0, st>>>(w.slices, w.slices + (size_t)B * H1, p->rna0_b, B, H1, training ? 1 : 0,
-                                                               s.h1, w.partial);
+        k_bn_colstats<2><<<dim3(H1 / BC, bsl), 256, 0, st>>>(w.slices, w.slices + (size_t)B * H1, p->rna0_b, nullptr, nullptr, nullptr,
+                                                             nullptr, nullptr, B, H1, 0, 0.f, 0, nullptr, 0, training ? 1 : 0, s.h1,
+                                                             w.partial);
     } else {
         rc = gemm_bf16(s.xb, Kp, 0, s.w1b, Kp, 0, (int)B, H1, rna_dim, s.h1, H1, nullptr, 0, p->rna0_b, 0, nullptr, st);
         if (rc) return rc;
-        if (training) colreduce<0>(s.h1, H1, nullptr, 0, nullptr, nullptr, nullptr, 0, B, H1, w.partial, nsl, st);
+        if (training)
+            k_bn_colstats<0><<<dim3(H1 / BC, bsl), 256, 0, st>>>(s.h1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B, H1,
+                                                                 0, 0.f, 0, nullptr, 0, 1, nullptr, w.partial);
     }
-    k_bn_finalize<<<colfinal_grid(H1), 256, 0, st>>>(w.partial, nsl, B, H1, training, p->bn1_rm, p->bn1_rv, s.mu1, s.rstd1);
-    k_bn_apply<<<gs(B * H1), 256, 0, st>>>(s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh, inv_keep, seed, seed_dev, 1,
-                                           s.a1, H1, keep1);
+    k_bn_apply2<<<dim3(H1 / BC, (unsigned)((B + BR - 1) / BR)), 256, 0, st>>>(s.h1, w.partial, bsl, p->bn1_w, p->bn1_b, B, H1, training,
+                                                                              p->bn1_rm, p->bn1_rv, s.mu1, s.rstd1, thresh, inv_keep,
+                                                                              seed, seed_dev, 1, s.a1, keep1);
     rc = gemm_bf16(s.a1, H1, 0, s.w2b, H1, 0, (int)B, R1, H1, s.r, R1, nullptr, 0, p->rna4_b, 1, nullptr, st);
     if (rc) return rc;
 
@@ -839,13 +1045,26 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
     // fusion: Linear(288, 256) -> BN -> ReLU -> Dropout -> Linear(256, 128) -> ReLU ; cox head
     rc = gemm_bf16(s.fused, FEAT, 0, s.wf1b, FEAT, 0, (int)B, H2, FEAT, s.h2, H2, nullptr, 0, p->fus0_b, 0, nullptr, st);
     if (rc) return rc;
-    if (training) colreduce<0>(s.h2, H2, nullptr, 0, nullptr, nullptr, nullptr, 0, B, H2, w.partial, nsl, st);
-    k_bn_finalize<<<colfinal_grid(H2), 256, 0, st>>>(w.partial, nsl, B, H2, training, p->bn2_rm, p->bn2_rv, s.mu2, s.rstd2);
-    k_bn_apply<<<gs(B * H2), 256, 0, st>>>(s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh, inv_keep, seed, seed_dev, 2,
-                                           s.a2, H2, keep2);
+    if (training)
+        k_bn_colstats<0><<<dim3(H2 / BC, bsl), 256, 0, st>>>(s.h2, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B, H2, 0,
+                                                             0.f, 0, nullptr, 0, 1, nullptr, w.partial);
+    k_bn_apply2<<<dim3(H2 / BC, (unsigned)((B + BR - 1) / BR)), 256, 0, st>>>(s.h2, w.partial, bsl, p->bn2_w, p->bn2_b, B, H2, training,
+                                                                              p->bn2_rm, p->bn2_rv, s.mu2, s.rstd2, thresh, inv_keep,
+                                                                              seed, seed_dev, 2, s.a2, keep2);
     rc = gemm_bf16(s.a2, H2, 0, s.wf2b, H2, 0, (int)B, F2N, H2, s.f2, F2N, nullptr, 0, p->fus4_b, 1, nullptr, st);
     if (rc) return rc;
     k_cox_head<<<gs(B * 32), 256, 0, st>>>(s.f2, p->cox_w, p->cox_b, B, hazard);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_head_stage_rna(const float *rna, int64_t B, int32_t rna_dim, void *saved, size_t saved_bytes,
+                                b200surv_stream_t stream) {
+    B200_REQUIRE(rna && saved && B >= 1 && rna_dim >= 1, "arguments");
+    size_t need = 0;
+    const Saved s = carve_saved(saved, B, rna_dim, &need);
+    if (saved_bytes < need) { set_error("head stage: saved buffer %zu < %zu", saved_bytes, need); return B200SURV_WORKSPACE_TOO_SMALL; }
+    cast_pad(rna, rna_dim, s.xb, kpad(rna_dim), B, rna_dim, kpad(rna_dim), as_stream(stream));
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -856,6 +1075,7 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
                           size_t saved_bytes, void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
     B200_REQUIRE(p && g && d_hazard && clinical && saved && workspace, "null pointer");
     B200_REQUIRE(B >= 1 && rna_dim >= 1, "B, rna_dim");
+    training &= ~B200SURV_HEAD_X_STAGED;
     const bool gated = mask != nullptr;
     size_t need = 0;
     const Saved s = carve_saved(const_cast<void *>(saved), B, rna_dim, &need);
@@ -868,7 +1088,7 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     // training == B200SURV_HEAD_TRAIN_SEED_DEV: `seed` is the address of a uint64 in device memory
     const uint64_t *seed_dev = training == B200SURV_HEAD_TRAIN_SEED_DEV ? reinterpret_cast<const uint64_t *>(static_cast<uintptr_t>(seed)) : nullptr;
     const float inv_keep = 1.f / (1.f - dropout_p);
-    const int nsl = nslices_for(B);
+    const int bsl = bn_slices(B);
     int32_t rc;
 
     // The caller's stream carries the chain of input-gradient GEMMs; the small weight-gradient GEMMs and the slice sums of
@@ -901,11 +1121,11 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     rc = gemm_bf16(w.df2, F2N, 0, s.wf2b, H2, 1, (int)B, H2, F2N, w.t0, H2, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dA2 [B][256]
     if (rc) return rc;
     // ---- fusion.1-3 (BN, ReLU, Dropout) backward -> dH2 (bf16); fusion.0.bias with it
-    k_bn_bwd_stats<<<dim3(H2 / 32, nsl), 256, 0, st>>>(w.t0, H2, s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh, inv_keep,
-                                                       seed, seed_dev, 2, w.partial);
-    k_bn_bwd_final<<<colfinal_grid(H2), 256, 0, st>>>(w.partial, nsl, H2, p->bn2_w, s.rstd2, training, g->bn2_b, g->bn2_w, g->fus0_b);
-    k_bn_bwd_dx2<<<gs(B * H2), 256, 0, st>>>(w.t0, H2, s.h2, H2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, g->bn2_b, g->bn2_w, B, H2,
-                                             training, thresh, inv_keep, seed, seed_dev, 2, w.dh2, H2);
+    k_bn_colstats<1><<<dim3(H2 / BC, bsl), 256, 0, st>>>(w.t0, nullptr, nullptr, s.h2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh,
+                                                         inv_keep, seed, seed_dev, 2, 1, nullptr, w.partial);
+    k_bn_bwd_dx3<<<dim3(H2 / BC, (unsigned)((B + BR - 1) / BR)), 256, 0, st>>>(w.t0, s.h2, w.partial, bsl, s.mu2, s.rstd2, p->bn2_w,
+                                                                               p->bn2_b, B, H2, training, thresh, inv_keep, seed,
+                                                                               seed_dev, 2, g->bn2_b, g->bn2_w, g->fus0_b, w.dh2);
     // ---- fusion.0: dW = dH2^T fused (side), dfused = dH2 Wf1
     if ((rc = fork())) return rc;
     rc = gemm_wgrad(w.dh2, H2, s.fused, FEAT, H2, FEAT, (int)B, g->fus0_w, FEAT, w.splitk, sd);
@@ -946,11 +1166,11 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     rc = gemm_bf16(w.dR, R1, 0, s.w2b, H1, 1, (int)B, H1, R1, w.t0, H1, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dA1 [B][512]
     if (rc) return rc;
     // ---- rna_encoder.1-3 backward -> dH1 (bf16); rna_encoder.0.bias with it
-    k_bn_bwd_stats<<<dim3(H1 / 32, nsl), 256, 0, st>>>(w.t0, H1, s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh, inv_keep,
-                                                       seed, seed_dev, 1, w.partial);
-    k_bn_bwd_final<<<colfinal_grid(H1), 256, 0, st>>>(w.partial, nsl, H1, p->bn1_w, s.rstd1, training, g->bn1_b, g->bn1_w, g->rna0_b);
-    k_bn_bwd_dx2<<<gs(B * H1), 256, 0, st>>>(w.t0, H1, s.h1, H1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, g->bn1_b, g->bn1_w, B, H1,
-                                             training, thresh, inv_keep, seed, seed_dev, 1, w.dh1, H1);
+    k_bn_colstats<1><<<dim3(H1 / BC, bsl), 256, 0, st>>>(w.t0, nullptr, nullptr, s.h1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh,
+                                                         inv_keep, seed, seed_dev, 1, 1, nullptr, w.partial);
+    k_bn_bwd_dx3<<<dim3(H1 / BC, (unsigned)((B + BR - 1) / BR)), 256, 0, st>>>(w.t0, s.h1, w.partial, bsl, s.mu1, s.rstd1, p->bn1_w,
+                                                                               p->bn1_b, B, H1, training, thresh, inv_keep, seed,
+                                                                               seed_dev, 1, g->bn1_b, g->bn1_w, g->rna0_b, w.dh1);
     // ---- rna_encoder.0: dW1 [512][rna_dim] = dH1^T x  (the big one; x is an input, no dx): CTA pairs for large batches
     if (B >= 512 && rna_dim >= 2048)
         rc = gemm_bf16_ex(w.dh1, H1, 1, s.xb, Kp, 1, H1, rna_dim, (int)B, g->rna0_w, rna_dim, nullptr, 0, nullptr, 0, nullptr, 512, 0, st);

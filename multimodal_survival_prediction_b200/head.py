@@ -51,10 +51,13 @@ def _f32c(t, dev):
 
 
 class _HeadFn(torch.autograd.Function):
-    """(ct_feat, rna, clinical, mask|None, training, dropout_p, seed, want_masks, *24 parameter tensors)."""
+    """(ct_feat, rna, clinical, mask|None, training, dropout_p, seed, want_masks, staged_saved|None, *24 parameter tensors).
+
+    staged_saved: a caller-owned ``saved`` buffer into which ``stage_rna`` has already written the bf16 copy of ``rna``
+    (B200SURV_HEAD_X_STAGED): the forward pass then does not read ``rna`` (CUDA-graph replays, GraphedHeadStep)."""
 
     @staticmethod
-    def forward(ctx, ct_feat, rna, clinical, mask, training, dropout_p, seed, want_masks, *params):
+    def forward(ctx, ct_feat, rna, clinical, mask, training, dropout_p, seed, want_masks, staged_saved, *params):
         dev = ct_feat.device
         if dev.type != "cuda":
             raise L.B200SurvError("the B200 fusion head has no CPU path: move the module and its inputs to CUDA")
@@ -70,7 +73,7 @@ class _HeadFn(torch.autograd.Function):
         ps = HeadParams(**{f: (t.data_ptr() if t is not None else None) for f, t in tens.items()})
         sb = lib.b200surv_head_saved_bytes(B, rna_dim)
         wb = lib.b200surv_head_workspace_bytes(B, rna_dim)
-        saved = torch.empty(sb, dtype=torch.uint8, device=dev)
+        saved = torch.empty(sb, dtype=torch.uint8, device=dev) if staged_saved is None else staged_saved
         ws = torch.empty(wb, dtype=torch.uint8, device=dev)
         hazard = torch.empty(B, dtype=torch.float32, device=dev)
         gate = torch.empty(B, 3, dtype=torch.float32, device=dev) if gated else None
@@ -79,6 +82,8 @@ class _HeadFn(torch.autograd.Function):
         if isinstance(seed, torch.Tensor):   # device-resident seed (CUDA-graph replays): pass its address
             ctx.seed_keep = seed
             training, seed = (L.HEAD_TRAIN_SEED_DEV if training else 0), seed.data_ptr()
+        if staged_saved is not None:
+            training = int(training) | L.HEAD_X_STAGED
         with torch.cuda.device(dev):
             rc = lib.b200surv_head_fwd(ctypes.byref(ps), L.ptr(ct_c), L.ptr(rna_c), L.ptr(clin_c), L.ptr(mask_c), B,
                                        rna_dim, int(training), ctypes.c_float(dropout_p), ctypes.c_uint64(seed),
@@ -118,7 +123,7 @@ class _HeadFn(torch.autograd.Function):
                                        ctypes.c_uint64(seed), L.ptr(d_ct), L.ptr(saved), saved.numel(), L.ptr(ws),
                                        ws.numel(), L.stream_ptr(dev))
         L.check(rc, "b200surv_head_bwd")
-        out = [d_ct, None, None, None, None, None, None, None]
+        out = [d_ct, None, None, None, None, None, None, None, None]
         for f, meta in zip(_P_FIELDS, pmeta):
             if f.endswith(("_rm", "_rv")) or meta is None:
                 out.append(None)
@@ -140,14 +145,29 @@ def _param_list(module):
             module.cox_head.weight, module.cox_head.bias]
 
 
-def fused_head(module, ct_feat, rna, clinical, mask=None, want_masks=False, seed=None):
+def head_saved_buffer(batch: int, rna_dim: int, device):
+    """A ``saved`` buffer for ``stage_rna`` / ``fused_head(..., staged_saved=...)``."""
+    return torch.empty(L.load().b200surv_head_saved_bytes(batch, rna_dim), dtype=torch.uint8, device=device)
+
+
+def stage_rna(rna, saved):
+    """bf16 copy of the batch ``rna`` (B, rna_dim) straight into ``saved`` (b200surv_head_stage_rna): what the forward pass
+    would do first, done by the caller instead so that a captured graph needs no static fp32 copy of the batch."""
+    dev = saved.device
+    x = _f32c(rna, dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().b200surv_head_stage_rna(L.ptr(x), x.shape[0], x.shape[1], L.ptr(saved), saved.numel(), L.stream_ptr(dev)),
+                "b200surv_head_stage_rna")
+
+
+def fused_head(module, ct_feat, rna, clinical, mask=None, want_masks=False, seed=None, staged_saved=None):
     """Run the head of ``module`` (a PartialModalityNet / MultiModalSurvivalNet from this file) on CUDA."""
     params = _param_list(module)
     training = module.training
     p_drop = float(module.rna_encoder[3].p) if training else 0.0
     if seed is None:
         seed = int(torch.empty((), dtype=torch.int64).random_().item()) & ((1 << 62) - 1) if (training and p_drop > 0) else 0
-    outs = _HeadFn.apply(ct_feat, rna, clinical, mask, training, p_drop, seed, want_masks, *params)
+    outs = _HeadFn.apply(ct_feat, rna, clinical, mask, training, p_drop, seed, want_masks, staged_saved, *params)
     if training:
         with torch.no_grad():
             module.rna_encoder[1].num_batches_tracked += 1
@@ -216,8 +236,9 @@ class GraphedHeadStep:
 
     The eager step is bound by the host (about a hundred kernel launches plus the autograd bookkeeping cost ~1 ms at
     B = 4096, three times the GPU work); a replay costs one launch.  Shapes are fixed at construction.  ``step(...)``
-    copies a batch into the static input buffers (or write into ``self.inputs`` yourself and call ``replay()``),
-    replays, and returns ``(loss, outputs)``; the gradients are left in ``param.grad`` (static tensors that every replay
+    copies a batch into the static input buffers -- the RNA matrix is converted to bf16 straight into the graph's saved
+    buffer instead (``stage_rna``; to drive ``replay()`` yourself, write ct / clinical / mask into ``self.inputs[0 / 2 / 3]``
+    and call ``stage_rna(rna, self.saved)``) --, replays, and returns ``(loss, outputs)``; the gradients are left in ``param.grad`` (static tensors that every replay
     overwrites -- step the optimizer before the next replay and do not set them to None).  The dropout seed lives in
     device memory and advances inside the graph, so every replay draws new masks (B200SURV_HEAD_TRAIN_SEED_DEV).
     """
@@ -226,6 +247,10 @@ class GraphedHeadStep:
         dev = ct_feat.device
         self.module, self.loss_fn = module, loss_fn
         self.inputs = [None if t is None else t.detach().clone() for t in (ct_feat, rna, clinical, mask)]
+        # the RNA batch (82 MB at B = 4096) is not copied into a static fp32 buffer: step() converts every new batch to bf16
+        # straight into the graph's saved buffer (stage_rna) and the captured forward starts from there
+        self.saved = head_saved_buffer(rna.shape[0], rna.shape[1], dev)
+        stage_rna(rna, self.saved)
         self.seed = torch.empty((), dtype=torch.int64, device=dev).random_()
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
@@ -242,7 +267,7 @@ class GraphedHeadStep:
 
     def _eager(self):
         self.seed += 1
-        outs = fused_head(self.module, *self.inputs, seed=self.seed)
+        outs = fused_head(self.module, *self.inputs, seed=self.seed, staged_saved=self.saved)
         loss = self.loss_fn(*outs)
         loss.backward()
         return loss, outs
@@ -252,8 +277,12 @@ class GraphedHeadStep:
         return self.loss, self.outputs
 
     def step(self, ct_feat, rna, clinical, mask=None):
-        for dst, src in zip(self.inputs, (ct_feat, rna, clinical, mask)):
-            if dst is not None and src is not dst:
+        for i, (dst, src) in enumerate(zip(self.inputs, (ct_feat, rna, clinical, mask))):
+            if dst is None or src is dst:
+                continue
+            if i == 1:
+                stage_rna(src, self.saved)      # fp32 -> bf16 into the saved buffer; self.inputs[1] is not read by the graph
+            else:
                 dst.copy_(src, non_blocking=True)
         return self.replay()
 
@@ -268,7 +297,7 @@ class GraphedModelStep(GraphedHeadStep):
     def _eager(self):
         self.seed += 1
         ct_feat = self.module._ct_features(self.inputs[0])
-        outs = fused_head(self.module, ct_feat, *self.inputs[1:], seed=self.seed)
+        outs = fused_head(self.module, ct_feat, *self.inputs[1:], seed=self.seed, staged_saved=self.saved)
         loss = self.loss_fn(*outs)
         loss.backward()
         return loss, outs
