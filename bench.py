@@ -403,7 +403,7 @@ def run_b200(args):
         for prm in net.parameters():
             prm.grad = None
         hz, gt = net.forward_features(hct, hrna, hclin, hmask)
-        ((hz * hw).sum() + 0.01 * ghead.gate_entropy_loss(gt)).backward()
+        (torch.dot(hz, hw) + 0.01 * ghead.gate_entropy_loss(gt)).backward()
 
     def timed_head(fn, reps=10):
         for _ in range(3):
@@ -420,7 +420,7 @@ def run_b200(args):
     head_eager_ms = timed_head(head_step)
     # the same step as ONE CUDA graph (head.GraphedHeadStep): the eager step is bound by the host (~100 launches)
     graphed = ghead.GraphedHeadStep(net, hct, hrna, hclin, hmask,
-                                    lambda hz, gt: (hz * hw).sum() + 0.01 * ghead.gate_entropy_loss(gt))
+                                    lambda hz, gt: torch.dot(hz, hw) + 0.01 * ghead.gate_entropy_loss(gt))
     fresh = [x.clone() for x in (hct, hrna, hclin, hmask)]       # a "new batch": copied into the static buffers each step
     head_ms = timed_head(lambda: graphed.step(*fresh), reps=20)
     head_flop_per_row = 11_396_224          # fwd 5,507,136 + bwd 5,889,088

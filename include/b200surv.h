@@ -294,6 +294,9 @@ size_t b200surv_head_workspace_bytes(int64_t B, int32_t rna_dim); /* scratch of 
  * is not read.  A captured CUDA graph of the step then needs no copy of the 82 MB batch into a static input buffer: the
  * caller converts every new batch straight into the graph's saved buffer before the replay. */
 #define B200SURV_HEAD_X_STAGED 4
+/* OR-ed into `training` together with B200SURV_HEAD_TRAIN_SEED_DEV (forward only): the forward pass adds 1 to the
+ * device-resident seed before anything reads it, so a replayed graph draws new dropout masks without a separate launch. */
+#define B200SURV_HEAD_SEED_ADVANCE 8
 int32_t b200surv_head_stage_rna(const float *rna, int64_t B, int32_t rna_dim, void *saved, size_t saved_bytes,
                                 b200surv_stream_t stream);
 int32_t b200surv_head_fwd(const b200surv_head_params *params, const float *ct_feat, const float *rna,

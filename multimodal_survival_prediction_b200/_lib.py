@@ -122,6 +122,7 @@ SIGNATURES = {
 
 HEAD_TRAIN_SEED_DEV = 2
 HEAD_X_STAGED = 4
+HEAD_SEED_ADVANCE = 8
 
 _lib = None
 _arch_ok = set()

@@ -71,8 +71,16 @@ __global__ void k_cast_pad(const float *__restrict__ src, int64_t lds, bf16 *__r
                            int C, int Cp) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= Cp) return;
-    for (int64_t r = blockIdx.y; r < R; r += gridDim.y)
-        dst[r * ldd + c] = __float2bfloat16_rn(c < C ? src[r * lds + c] : 0.f);
+    const int64_t step = gridDim.y;
+    int64_t r = blockIdx.y;
+    for (; r + 3 * step < R; r += 4 * step) {  // four rows in flight per thread
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = c < C ? src[(r + u * step) * lds + c] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dst[(r + u * step) * ldd + c] = __float2bfloat16_rn(v[u]);
+    }
+    for (; r < R; r += step) dst[r * ldd + c] = __float2bfloat16_rn(c < C ? src[r * lds + c] : 0.f);
 }
 static void cast_pad(const float *src, int64_t lds, bf16 *dst, int64_t ldd, int64_t R, int C, int Cp, cudaStream_t st) {
     const unsigned gx = (unsigned)((Cp + 255) / 256);
@@ -481,19 +489,26 @@ k_bn_bwd_dx3(const float *__restrict__ dA, const float *__restrict__ x, const do
 // one launch for the bf16 copies of all weight matrices (K padded with zeros where the TMA row pitch needs it)
 // (segment k owns the blocks [b0[k], b0[k + 1]): all matrices are converted at the same time)
 struct CastSeg { const float *src; bf16 *dst; int lds, ldd, R, C, Cp; };
+// A block converts CAST_ROWS rows x 256 columns of its matrix: thread = column, the rows' loads in flight together.
+constexpr int CAST_ROWS = 8;
 struct CastSegs { CastSeg s[5]; int b0[6]; int n; };
 __global__ void __launch_bounds__(256)
-k_cast_multi(const CastSegs segs) {
+k_cast_multi(const CastSegs segs, uint64_t *seed_advance) {
+    if (seed_advance != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *seed_advance += 1;  // (see B200SURV_HEAD_SEED_ADVANCE)
     int k = 0;
 #pragma unroll
     for (int q = 1; q < 5; ++q) k += (q < segs.n && (int)blockIdx.x >= segs.b0[q]) ? 1 : 0;
     const CastSeg g = segs.s[k];
-    const int nb = segs.b0[k + 1] - segs.b0[k], bx = blockIdx.x - segs.b0[k];
-    const int64_t total = (int64_t)g.R * g.Cp;
-    for (int64_t i = (int64_t)bx * blockDim.x + threadIdx.x; i < total; i += (int64_t)nb * blockDim.x) {
-        const int r = (int)((unsigned)i / (unsigned)g.Cp), c = (int)(i - (int64_t)r * g.Cp);
-        g.dst[(int64_t)r * g.ldd + c] = __float2bfloat16_rn(c < g.C ? g.src[(int64_t)r * g.lds + c] : 0.f);
-    }
+    const int bx = blockIdx.x - segs.b0[k], chunks = (g.Cp + 255) / 256;
+    const int rg = bx / chunks, c = (bx - rg * chunks) * 256 + threadIdx.x;
+    if (c >= g.Cp) return;
+    const int r0 = rg * CAST_ROWS;
+    float v[CAST_ROWS];
+#pragma unroll
+    for (int u = 0; u < CAST_ROWS; ++u) v[u] = (r0 + u < g.R && c < g.C) ? g.src[(int64_t)(r0 + u) * g.lds + c] : 0.f;
+#pragma unroll
+    for (int u = 0; u < CAST_ROWS; ++u)
+        if (r0 + u < g.R) g.dst[(int64_t)(r0 + u) * g.ldd + c] = __float2bfloat16_rn(v[u]);
 }
 
 // h[r][n] = s0[r][n] + s1[r][n] + bias[n] (the two K slices of the split GEMM), and the BatchNorm partial sums
@@ -965,8 +980,8 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
                           const float *mask, int64_t B, int32_t rna_dim, int32_t training, float dropout_p,
                           uint64_t seed, float *hazard, float *gate, uint8_t *keep1, uint8_t *keep2, void *saved,
                           size_t saved_bytes, void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
-    const bool x_staged = (training & B200SURV_HEAD_X_STAGED) != 0;
-    training &= ~B200SURV_HEAD_X_STAGED;
+    const bool x_staged = (training & B200SURV_HEAD_X_STAGED) != 0, seed_adv = (training & B200SURV_HEAD_SEED_ADVANCE) != 0;
+    training &= ~(B200SURV_HEAD_X_STAGED | B200SURV_HEAD_SEED_ADVANCE);
     B200_REQUIRE(p && ct_feat && (rna || x_staged) && clinical && hazard && saved && workspace, "null pointer");
     B200_REQUIRE(B >= 1 && B < (int64_t)1 << 24, "batch size must be in [1, 2^24)");
     B200_REQUIRE(rna_dim >= 1 && rna_dim <= 65536, "rna_dim");
@@ -1004,11 +1019,11 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
         add(p->fus0_w, FEAT, s.wf1b, FEAT, H2, FEAT, FEAT);
         add(p->fus4_w, H2, s.wf2b, H2, F2N, H2, H2);
         cs.b0[0] = 0;
-        for (int k = 0; k < cs.n; ++k) {  // ~4 elements per thread, at least one block per matrix
-            const int64_t blocks = ((int64_t)cs.s[k].R * cs.s[k].Cp + 1023) / 1024;
-            cs.b0[k + 1] = cs.b0[k] + (int)(blocks < 1 ? 1 : blocks);
-        }
-        k_cast_multi<<<cs.b0[cs.n], 256, 0, st>>>(cs);
+        for (int k = 0; k < cs.n; ++k)
+            cs.b0[k + 1] = cs.b0[k] + ((cs.s[k].R + CAST_ROWS - 1) / CAST_ROWS) * ((cs.s[k].Cp + 255) / 256);
+        // B200SURV_HEAD_SEED_ADVANCE: the device-resident dropout seed is bumped here, by the first kernel of the forward
+        // pass -- every later kernel of this forward / backward pair reads the new value
+        k_cast_multi<<<cs.b0[cs.n], 256, 0, st>>>(cs, (seed_adv && seed_dev) ? const_cast<uint64_t *>(seed_dev) : nullptr);
     }
 
     // rna encoder: Linear(rna_dim, 512) -> BN -> ReLU -> Dropout -> Linear(512, 128) -> ReLU
@@ -1075,7 +1090,7 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
                           size_t saved_bytes, void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
     B200_REQUIRE(p && g && d_hazard && clinical && saved && workspace, "null pointer");
     B200_REQUIRE(B >= 1 && rna_dim >= 1, "B, rna_dim");
-    training &= ~B200SURV_HEAD_X_STAGED;
+    training &= ~(B200SURV_HEAD_X_STAGED | B200SURV_HEAD_SEED_ADVANCE);
     const bool gated = mask != nullptr;
     size_t need = 0;
     const Saved s = carve_saved(const_cast<void *>(saved), B, rna_dim, &need);

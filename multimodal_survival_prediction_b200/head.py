@@ -82,6 +82,8 @@ class _HeadFn(torch.autograd.Function):
         if isinstance(seed, torch.Tensor):   # device-resident seed (CUDA-graph replays): pass its address
             ctx.seed_keep = seed
             training, seed = (L.HEAD_TRAIN_SEED_DEV if training else 0), seed.data_ptr()
+            if training and staged_saved is not None:   # graphed steps: the forward pass itself advances the seed
+                training |= L.HEAD_SEED_ADVANCE
         if staged_saved is not None:
             training = int(training) | L.HEAD_X_STAGED
         with torch.cuda.device(dev):
@@ -170,8 +172,7 @@ def fused_head(module, ct_feat, rna, clinical, mask=None, want_masks=False, seed
     outs = _HeadFn.apply(ct_feat, rna, clinical, mask, training, p_drop, seed, want_masks, staged_saved, *params)
     if training:
         with torch.no_grad():
-            module.rna_encoder[1].num_batches_tracked += 1
-            module.fusion[1].num_batches_tracked += 1
+            torch._foreach_add_([module.rna_encoder[1].num_batches_tracked, module.fusion[1].num_batches_tracked], 1)
     return outs
 
 
@@ -266,7 +267,7 @@ class GraphedHeadStep:
             self.loss, self.outputs = self._eager()
 
     def _eager(self):
-        self.seed += 1
+        # (the device-resident seed is advanced by the forward pass: B200SURV_HEAD_SEED_ADVANCE)
         outs = fused_head(self.module, *self.inputs, seed=self.seed, staged_saved=self.saved)
         loss = self.loss_fn(*outs)
         loss.backward()
@@ -295,7 +296,6 @@ class GraphedModelStep(GraphedHeadStep):
     cohorts of <= 2048 rows; pass ``checks=False``)."""
 
     def _eager(self):
-        self.seed += 1
         ct_feat = self.module._ct_features(self.inputs[0])
         outs = fused_head(self.module, ct_feat, *self.inputs[1:], seed=self.seed, staged_saved=self.saved)
         loss = self.loss_fn(*outs)

@@ -9,7 +9,7 @@ hb = int(os.environ.get("B", 4096))
 net = ghead.PartialModalityNet().to(dev).train()
 hct, hrna, hclin, hmask = [x.to(dev) for x in synth.modality_batch(hb, seed=1234)]
 hw = torch.randn(hb, device=dev) / hb ** 0.5
-g = ghead.GraphedHeadStep(net, hct, hrna, hclin, hmask, lambda hz, gt: (hz * hw).sum() + 0.01 * ghead.gate_entropy_loss(gt))
+g = ghead.GraphedHeadStep(net, hct, hrna, hclin, hmask, lambda hz, gt: torch.dot(hz, hw) + 0.01 * ghead.gate_entropy_loss(gt))
 fresh = [x.clone() for x in (hct, hrna, hclin, hmask)]
 reps = 3 if "--ncu" in sys.argv else 50
 for _ in range(3):
