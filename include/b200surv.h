@@ -67,7 +67,9 @@ uint64_t b200surv_debug_launch_count(void);
  *            (log_hz, time, event) = 22 algorithmic bytes per row for fwd+bwd.  Rows that violate
  *            the precondition raise B200SURV_COXF_NOT_BINNABLE in the header and poison the loss
  *            with NaN; the caller then re-runs with SORTED.
- *   SORTED : any non-negative float times; radix sort on (time, event) + segmented scans. */
+ *   SORTED : any non-negative float times, one cohort or packed cohorts; radix sort on (cohort, time, event) + single-pass
+ *            look-back scans whose sums restart per tie group / per cohort, fp64: also the path for log-hazards spread over
+ *            more nats than the fixed point of BINNED holds (B200SURV_COXF_LOW_PRECISION). */
 #define B200SURV_COX_SMALL 1
 #define B200SURV_COX_BINNED 2
 #define B200SURV_COX_SORTED 3

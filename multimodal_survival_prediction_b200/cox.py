@@ -171,18 +171,18 @@ def _plan_and_run(log_hz, time, event, seg_offsets, n_seg, max_seg, ties, reduct
                 # and table per cohort, and the backward pass reads the shift from the cohort's header)
                 so_host = seg_offsets.cpu().tolist()
                 stride = state.numel() // n_seg
+                refit = True
                 for s_, h in enumerate(hdrs):
                     if not h.flags:
                         continue
                     a, b = so_host[s_], so_host[s_ + 1]
                     sh = _fit_shift(b - a, h.max_log_hz, h.min_log_hz)
-                    if sh is None:
-                        raise L.B200SurvError(f"cohort {s_} of a packed set: the spread of log_hz "
-                                              f"[{h.min_log_hz}, {h.max_log_hz}] does not fit the fixed-point (BINNED) "
-                                              "path; pass it alone (the SORTED mode handles one cohort per call)")
+                    if sh is None:      # this cohort's spread fits no shift: the whole set goes to the fp64 path
+                        refit = False
+                        break
                     cox_fwd_raw(log_hz[a:b], time[a:b], event[a:b], None, 1, ties, reduction, L.COX_BINNED, nb, sh,
                                 state=state[s_ * stride:(s_ + 1) * stride], loss=loss[s_:s_ + 1])
-                if any(h.flags for h in read_headers(state, n_seg, L.COX_BINNED)):
+                if not refit or any(h.flags for h in read_headers(state, n_seg, L.COX_BINNED)):
                     break
                 return loss, state, L.COX_BINNED, nb
             new_shift = _fit_shift(n, max(h.max_log_hz for h in hdrs), min(h.min_log_hz for h in hdrs))
@@ -190,10 +190,10 @@ def _plan_and_run(log_hz, time, event, seg_offsets, n_seg, max_seg, ties, reduct
                 break       # the spread of log_hz does not fit the fixed point at any shift: fp64 path
             shift = new_shift
             continue
-    if n_seg != 1:
-        raise L.B200SurvError("segmented cohorts larger than 2048 rows need integer day counts < 8192 "
-                              "(BINNED mode); the SORTED mode handles one cohort per call")
-    loss, state = cox_fwd_raw(log_hz, time, event, None, 1, ties, reduction, L.COX_SORTED, 0)
+    # any non-negative float times, hazards of any spread, one cohort or packed cohorts: sort + scans in fp64
+    loss, state = cox_fwd_raw(log_hz, time, event, seg_offsets if n_seg > 1 else None, n_seg, ties, reduction, L.COX_SORTED, 0)
+    if checks and any(h.flags & L.COXF_BAD_TIME for h in read_headers(state, n_seg, L.COX_SORTED)):
+        raise ValueError("Input 'time' should be non-negative and free of NaN")
     return loss, state, L.COX_SORTED, 0
 
 

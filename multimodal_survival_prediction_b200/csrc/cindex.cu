@@ -358,7 +358,8 @@ int32_t cindex_counts_launch(const float *est, const float *time, const uint8_t 
     // keys are generated into (keys_s, idx_s): four ping-pong passes leave the sorted pairs there
     k_ci_keys<<<grid, 256, 0, st>>>(time, event, n, keys_s, idx_s, acc);
     {
-        const int32_t rc = sortscan::radix_sort_pairs(keys_s, idx_s, keys, vals, n, 32, cub_tmp, st);
+        int in_first = 1;  // four passes: the sorted pairs are back in (keys_s, idx_s)
+        const int32_t rc = sortscan::radix_sort_pairs2(keys_s, idx_s, keys, vals, n, 32, nullptr, 0, cub_tmp, st, &in_first);
         if (rc) return rc;
     }
     k_ci_flag<<<grid, 256, 0, st>>>(est, keys_s, idx_s, n, row_begin, row_end, est_s, isrow);
@@ -380,7 +381,8 @@ size_t debug_sortscan_temp_bytes(int64_t n) {
 }
 int32_t debug_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, int64_t n, void *temp,
                          cudaStream_t st) {
-    return sortscan::radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 32, temp, st);  // sorted pairs end up in keys/vals
+    int in_first = 1;
+    return sortscan::radix_sort_pairs2(keys, vals, keys_tmp, vals_tmp, n, 32, nullptr, 0, temp, st, &in_first);  // sorted pairs end up in keys/vals
 }
 namespace {
 struct DbgLoad {

@@ -24,9 +24,9 @@ int32_t cox_small_fwd_launch(const float *, const float *, const uint8_t *, cons
                              int, float *, void *, size_t, cudaStream_t);
 int32_t cox_scale_grad_launch(const float *, const void *, const int64_t *, int64_t, int64_t, float *, cudaStream_t);
 // cox_sorted.cu
-size_t cox_sorted_workspace_bytes(int64_t n);
-int32_t cox_sorted_fwd_launch(const float *, const float *, const uint8_t *, int64_t, int, int, float *, void *,
-                              size_t, void *, size_t, cudaStream_t);
+size_t cox_sorted_workspace_bytes(int64_t n, int64_t n_seg);
+int32_t cox_sorted_fwd_launch(const float *, const float *, const uint8_t *, const int64_t *, int64_t, int64_t, int, int, float *,
+                              void *, size_t, void *, size_t, cudaStream_t);
 // cindex.cu
 size_t cindex_workspace_bytes(int64_t n, int algo);
 int32_t cindex_counts_launch(const float *, const float *, const uint8_t *, int64_t, int64_t, int64_t, float, int, int,
@@ -74,7 +74,7 @@ size_t b200surv_cox_state_bytes(int64_t n, int64_t n_seg, int32_t mode, int32_t 
 size_t b200surv_cox_workspace_bytes(int64_t n, int64_t n_seg, int32_t mode, int32_t nbins) {
     if (n < 0 || n_seg < 1) return 0;
     if (mode == B200SURV_COX_BINNED) return cox_binned_workspace_bytes(n, n_seg, nbins);
-    if (mode == B200SURV_COX_SORTED) return cox_sorted_workspace_bytes(n);
+    if (mode == B200SURV_COX_SORTED) return cox_sorted_workspace_bytes(n, n_seg);
     return 256;
 }
 
@@ -100,8 +100,7 @@ int32_t b200surv_cox_fwd(const float *log_hz, const float *time, const uint8_t *
                                   state, state_bytes, workspace, workspace_bytes, st);
         case B200SURV_COX_SORTED:
             B200_REQUIRE(workspace != nullptr, "workspace");
-            if (n_seg != 1) { set_error("SORTED mode handles one cohort per call"); return B200SURV_UNSUPPORTED; }
-            return cox_sorted_fwd_launch(log_hz, time, event, n, ties, reduction, out_loss, state, state_bytes,
+            return cox_sorted_fwd_launch(log_hz, time, event, seg_offsets, n, n_seg, ties, reduction, out_loss, state, state_bytes,
                                          workspace, workspace_bytes, st);
         default:
             set_error("unknown cox mode %d", mode);

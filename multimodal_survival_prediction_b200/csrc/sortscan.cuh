@@ -324,5 +324,305 @@ inline int32_t radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *
     return B200SURV_OK;  // after an even number of passes the result is back in keys_in/vals_in: see the callers
 }
 
+// ------------------------------------------------------------------------------------------------ round 2
+// (1) seg_scan: the look-back scan over a richer tuple -- three fp64 sums, each restarting at "group heads", at "segment
+//     heads" or never, and a position combined with min / max.  Head flags travel in the integer, so the operator stays
+//     associative:  (f1, v1) + (f2, v2) = (f1 | f2, f2 ? v2 : v1 + v2).  The SORTED Cox path runs entirely on it: tie
+//     groups inside cohorts ("segments") packed back to back.
+// (2) radix_sort_pairs2: the LSD radix sort with a scatter that is staged through shared memory (a tile's keys are first
+//     put in digit order on chip, then written as runs: ~2 sectors per 16 keys instead of one sector per key) and a
+//     key source functor, so that extra passes can sort by a key looked up through the value (the cohort id of a row).
+struct Tup4 {
+    double a, b, c;
+    long long i;   // bits [0, 40): position + 1 (0 = none); bit 60: holds a group head; bit 61: holds a segment head
+};
+constexpr long long T4_POS = (1ll << 40) - 1, T4_GROUP = 1ll << 60, T4_SEG = 1ll << 61;
+enum PosOp { P_NONE = 0, P_MIN = 1, P_MAX = 2 };
+
+__device__ __forceinline__ Tup4 t4_identity() { Tup4 t; t.a = 0.0; t.b = 0.0; t.c = 0.0; t.i = 0; return t; }
+// `x` precedes `y` in scan order.  RA / RB / RC: 0 = plain sum, 1 = restarts at group heads, 2 = restarts at segment heads.
+template <int POP, int RA, int RB, int RC>
+__device__ __forceinline__ Tup4 t4_combine(const Tup4 &x, const Tup4 &y) {
+    Tup4 t;
+    const bool hg = (y.i & T4_GROUP) != 0, hs = (y.i & T4_SEG) != 0;
+    t.a = ((RA == 1 && hg) || (RA == 2 && hs)) ? y.a : x.a + y.a;
+    t.b = ((RB == 1 && hg) || (RB == 2 && hs)) ? y.b : x.b + y.b;
+    t.c = ((RC == 1 && hg) || (RC == 2 && hs)) ? y.c : x.c + y.c;
+    const long long px = x.i & T4_POS, py = y.i & T4_POS;
+    long long pos = 0;
+    if (POP == P_MIN) pos = px == 0 ? py : (py == 0 ? px : (px < py ? px : py));
+    if (POP == P_MAX) pos = px > py ? px : py;
+    t.i = pos | ((x.i | y.i) & (T4_GROUP | T4_SEG));
+    return t;
+}
+__device__ __forceinline__ Tup4 t4_shfl_up(const Tup4 &v, int d) {
+    Tup4 t;
+    t.a = __shfl_up_sync(FULL, v.a, d); t.b = __shfl_up_sync(FULL, v.b, d); t.c = __shfl_up_sync(FULL, v.c, d);
+    t.i = __shfl_up_sync(FULL, v.i, d);
+    return t;
+}
+__device__ __forceinline__ Tup4 t4_shfl(const Tup4 &v, int src) {
+    Tup4 t;
+    t.a = __shfl_sync(FULL, v.a, src); t.b = __shfl_sync(FULL, v.b, src); t.c = __shfl_sync(FULL, v.c, src);
+    t.i = __shfl_sync(FULL, v.i, src);
+    return t;
+}
+inline size_t seg_scan_state_bytes(int64_t n) {
+    const size_t ntiles = (size_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+    return align_up(2 * ntiles * 4 * sizeof(unsigned long long), 256) + 256;
+}
+__device__ __forceinline__ void t4_publish(unsigned long long *w, const Tup4 &t) {
+    scan_st(w, (unsigned long long)__double_as_longlong(t.a));
+    scan_st(w + 1, (unsigned long long)__double_as_longlong(t.b));
+    scan_st(w + 2, (unsigned long long)__double_as_longlong(t.c));
+    scan_st(w + 3, (unsigned long long)t.i);
+}
+__device__ __forceinline__ bool t4_try_read(const unsigned long long *w, Tup4 &t) {
+    const unsigned long long x = scan_ld(w), y = scan_ld(w + 1), z = scan_ld(w + 2), u = scan_ld(w + 3);
+    t.a = __longlong_as_double((long long)x); t.b = __longlong_as_double((long long)y);
+    t.c = __longlong_as_double((long long)z); t.i = (long long)u;
+    return x != SCAN_EMPTY && y != SCAN_EMPTY && z != SCAN_EMPTY && u != SCAN_EMPTY;
+}
+
+// Inclusive scan of load(p); scan order = ascending p, or descending p when REVERSE.  store(p, inclusive, element); after its
+// last element every thread calls store.finish() (block-wide reductions of per-thread state are allowed there: all threads
+// of the block arrive).  grid = number of tiles, SCAN_THREADS threads; state: words[2][ntiles][4] preset to SCAN_EMPTY and a
+// tile counter preset to 0 (k_scan_state_init over 8 * ntiles words).
+template <int POP, bool REVERSE, int RA, int RB, int RC, typename Load, typename Store>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_seg_scan(int64_t n, Load load, Store store, unsigned long long *agg, unsigned long long *inc_w, unsigned *counter) {
+    __shared__ Tup4 s_warp[SCAN_THREADS / 32];
+    __shared__ Tup4 s_prefix;
+    __shared__ unsigned s_tile;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t base = tile * SCAN_TILE + (int64_t)t * SCAN_ITEMS;
+    Tup4 item[SCAN_ITEMS];
+    Tup4 run = t4_identity();
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int64_t li = base + k;
+        item[k] = li < n ? load(REVERSE ? n - 1 - li : li) : t4_identity();
+        run = t4_combine<POP, RA, RB, RC>(run, item[k]);
+    }
+    Tup4 inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Tup4 u = t4_shfl_up(inc, d);
+        if (lane >= d) inc = t4_combine<POP, RA, RB, RC>(u, inc);
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    Tup4 wpre = t4_identity(), tile_agg = t4_identity();
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        if (w < warp) wpre = t4_combine<POP, RA, RB, RC>(wpre, s_warp[w]);
+        tile_agg = t4_combine<POP, RA, RB, RC>(tile_agg, s_warp[w]);
+    }
+    Tup4 thread_excl = t4_shfl_up(inc, 1);
+    if (lane == 0) thread_excl = t4_identity();
+    thread_excl = t4_combine<POP, RA, RB, RC>(wpre, thread_excl);
+    if (warp == 0) {  // decoupled look-back, as in k_scan_lookback
+        if (lane == 0) {
+            if (tile == 0) t4_publish(inc_w, tile_agg);
+            else t4_publish(agg + 4 * tile, tile_agg);
+        }
+        Tup4 prefix = t4_identity();
+        int64_t look = tile - 1;
+        for (int guard = 0; look >= 0 && guard < SCAN_SPIN_MAX; ++guard) {
+            const int64_t q = look - lane;
+            Tup4 v = t4_identity();
+            int state = 2;
+            if (q >= 0) {
+                if (t4_try_read(inc_w + 4 * q, v)) state = 2;
+                else if (t4_try_read(agg + 4 * q, v)) state = 1;
+                else state = 0;
+            }
+            const unsigned m_inc = __ballot_sync(FULL, state == 2), m_none = __ballot_sync(FULL, state == 0);
+            const int first_inc = m_inc ? __ffs(m_inc) - 1 : 32, first_none = m_none ? __ffs(m_none) - 1 : 32;
+            const bool done = first_inc < first_none;
+            const int take = done ? first_inc + 1 : first_none;
+            Tup4 acc = t4_identity();
+            for (int l = take - 1; l >= 0; --l) acc = t4_combine<POP, RA, RB, RC>(acc, t4_shfl(v, l));
+            prefix = t4_combine<POP, RA, RB, RC>(acc, prefix);
+            if (done) break;
+            look -= take;
+        }
+        if (lane == 0) {
+            if (tile != 0) t4_publish(inc_w + 4 * tile, t4_combine<POP, RA, RB, RC>(prefix, tile_agg));
+            s_prefix = prefix;
+        }
+    }
+    __syncthreads();
+    Tup4 acc = t4_combine<POP, RA, RB, RC>(s_prefix, thread_excl);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int64_t li = base + k;
+        acc = t4_combine<POP, RA, RB, RC>(acc, item[k]);
+        if (li < n) store(REVERSE ? n - 1 - li : li, acc, item[k]);
+    }
+    store.finish();
+}
+
+template <int POP, bool REVERSE, int RA, int RB, int RC, typename Load, typename Store>
+int32_t seg_scan(int64_t n, Load load, Store store, void *state_buf, cudaStream_t st) {
+    if (n <= 0) return B200SURV_OK;
+    const size_t ntiles = (size_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+    unsigned long long *agg = static_cast<unsigned long long *>(state_buf), *inc_w = agg + ntiles * 4;
+    unsigned *counter = reinterpret_cast<unsigned *>(static_cast<unsigned char *>(state_buf) +
+                                                     align_up(2 * ntiles * 4 * sizeof(unsigned long long), 256));
+    ScanState s;
+    s.agg = agg; s.inc = inc_w; s.counter = counter;
+    const size_t words = 2 * ntiles * 4;
+    unsigned ig = (unsigned)((words + 255) / 256);
+    if (ig > 1184) ig = 1184;
+    k_scan_state_init<<<ig, 256, 0, st>>>(s, words);
+    k_seg_scan<POP, REVERSE, RA, RB, RC, Load, Store><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(n, load, store, agg, inc_w, counter);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+// ---- radix sort, round 2
+struct KeyDirect {   // the sort key of element i is keys[i]
+    __device__ uint32_t operator()(const uint32_t *keys, const uint32_t *, int64_t i) const { return keys[i]; }
+};
+struct KeyViaValue { // the sort key of element i is table[vals[i]] (e.g. the cohort of a row)
+    const uint32_t *table;
+    __device__ uint32_t operator()(const uint32_t *, const uint32_t *vals, int64_t i) const { return table[vals[i]]; }
+};
+
+template <typename KeyOf>
+static __global__ void __launch_bounds__(RS_THREADS)
+k_rs_hist2(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, KeyOf keyof, int64_t n, int shift, int ntiles,
+           int *__restrict__ hist) {
+    __shared__ int s_cnt[RS_RADIX];
+    const int tile = blockIdx.x;
+    s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)tile * RS_TILE;
+#pragma unroll 4
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const int64_t i = base + (int64_t)r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&s_cnt[(keyof(keys, vals, i) >> shift) & (RS_RADIX - 1)], 1);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * ntiles + tile] = s_cnt[threadIdx.x];
+}
+
+// stable scatter staged through shared memory: rank every key inside the tile (warp-level match ranking, warps in order),
+// place the pairs in digit order on chip, then write each digit's run to its global position -- consecutive threads write
+// consecutive addresses inside a run.
+template <typename KeyOf>
+static __global__ void __launch_bounds__(RS_THREADS)
+k_rs_scatter2(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, KeyOf keyof, int64_t n, int shift, int ntiles,
+              const long long *__restrict__ offs, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+    __shared__ int s_cnt[RS_THREADS / 32][RS_RADIX];   // per warp: count of each digit, then its start inside the digit's run
+    __shared__ int s_start[RS_RADIX];                  // first staged position of each digit
+    __shared__ long long s_goff[RS_RADIX];             // global position of staged position 0 of each digit's run
+    __shared__ uint32_t s_k[RS_TILE], s_v[RS_TILE];
+    __shared__ unsigned char s_d[RS_TILE];
+    const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < (RS_THREADS / 32) * RS_RADIX; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t tbase = (int64_t)tile * RS_TILE;
+    const int64_t base = tbase + (int64_t)warp * (RS_TILE / (RS_THREADS / 32));
+    uint32_t k[RS_ROUNDS], v[RS_ROUNDS];
+    int rank[RS_ROUNDS], dg[RS_ROUNDS];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const int64_t i = base + r * 32 + lane;
+        const bool in = i < n;
+        k[r] = in ? keys[i] : 0xffffffffu;
+        v[r] = in ? vals[i] : 0u;
+        dg[r] = in ? (int)((keyof(keys, vals, i) >> shift) & (RS_RADIX - 1)) : -1;
+        const unsigned peers = __match_any_sync(FULL, dg[r]);
+        const int before = in ? s_cnt[warp][dg[r]] : 0;
+        rank[r] = before + __popc(peers & lt);
+        __syncwarp();
+        if (in && (peers & lt) == 0) s_cnt[warp][dg[r]] = before + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // digit t: total of the tile, per-warp starts inside the run
+        int run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) { const int c = s_cnt[w][t]; s_cnt[w][t] = run; run += c; }
+        // exclusive scan of the 256 digit totals (warp scans + 8 warp totals through s_start)
+        int incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += u; }
+        __shared__ int s_wt[RS_THREADS / 32];
+        if (lane == 31) s_wt[warp] = incl;
+        __syncthreads();
+        int wpre = 0;
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) wpre += (w < warp) ? s_wt[w] : 0;
+        const int start = wpre + incl - run;
+        s_start[t] = start;
+        s_goff[t] = offs[(size_t)t * ntiles + tile] - start;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        if (dg[r] >= 0) {
+            const int pos = s_start[dg[r]] + s_cnt[warp][dg[r]] + rank[r];
+            s_k[pos] = k[r]; s_v[pos] = v[r]; s_d[pos] = (unsigned char)dg[r];
+        }
+    }
+    __syncthreads();
+    const int64_t cnt = n - tbase < RS_TILE ? n - tbase : RS_TILE;
+    for (int p = t; p < cnt; p += RS_THREADS) {
+        const long long dst = s_goff[s_d[p]] + p;
+        keys_out[dst] = s_k[p];
+        vals_out[dst] = s_v[p];
+    }
+}
+
+// One 8-bit pass: histogram, scan of the (digit, tile) matrix, staged scatter.
+template <typename KeyOf>
+inline int32_t radix_pass2(const uint32_t *ka, const uint32_t *va, uint32_t *kb, uint32_t *vb, KeyOf keyof, int64_t n, int shift,
+                           void *temp, cudaStream_t st) {
+    const RsLayout L = rs_layout(n);
+    unsigned char *t8 = static_cast<unsigned char *>(temp);
+    int *hist = reinterpret_cast<int *>(t8 + L.off_hist);
+    long long *offs = reinterpret_cast<long long *>(t8 + L.off_offs);
+    k_rs_hist2<KeyOf><<<L.ntiles, RS_THREADS, 0, st>>>(ka, va, keyof, n, shift, L.ntiles, hist);
+    const int32_t rc = scan_lookback<I_ADD, false>((int64_t)RS_RADIX * L.ntiles, RsLoadHist{hist}, RsStoreOffs{offs},
+                                                   t8 + L.off_scan, st);
+    if (rc) return rc;
+    k_rs_scatter2<KeyOf><<<L.ntiles, RS_THREADS, 0, st>>>(ka, va, keyof, n, shift, L.ntiles, offs, kb, vb);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+// Stable sort of (key, value) pairs by keys[0, end_bit) and then -- if seg_table != nullptr -- by seg_table[value]
+// (seg_bits of it, a multiple of 8): pairs of one cohort end up contiguous, sorted by key inside the cohort.
+// keys_in / vals_in are overwritten (ping-pong); the result is in keys_in / vals_in when the TOTAL number of passes is
+// even, else in keys_out / vals_out: the function returns which through *in_first (1 = keys_in / vals_in).
+inline int32_t radix_sort_pairs2(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n, int end_bit,
+                                 const uint32_t *seg_table, int seg_bits, void *temp, cudaStream_t st, int *in_first) {
+    uint32_t *ka = keys_in, *va = vals_in, *kb = keys_out, *vb = vals_out;
+    int passes = 0;
+    for (int shift = 0; shift < end_bit; shift += 8, ++passes) {
+        const int32_t rc = radix_pass2(ka, va, kb, vb, KeyDirect{}, n, shift, temp, st);
+        if (rc) return rc;
+        uint32_t *tk = ka; ka = kb; kb = tk;
+        uint32_t *tv = va; va = vb; vb = tv;
+    }
+    if (seg_table != nullptr) {
+        for (int shift = 0; shift < seg_bits; shift += 8, ++passes) {
+            const int32_t rc = radix_pass2(ka, va, kb, vb, KeyViaValue{seg_table}, n, shift, temp, st);
+            if (rc) return rc;
+            uint32_t *tk = ka; ka = kb; kb = tk;
+            uint32_t *tv = va; va = vb; vb = tv;
+        }
+    }
+    *in_first = (passes % 2 == 0) ? 1 : 0;
+    return B200SURV_OK;
+}
+
 }  // namespace sortscan
 }  // namespace b200surv

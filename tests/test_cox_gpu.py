@@ -286,3 +286,43 @@ def test_small_cohort_bad_times_raise_like_large_ones():
     # checks=False keeps the call asynchronous (CUDA-graph capture): the loss is NaN instead
     x = lh.cuda()
     assert torch.isnan(pkg.neg_partial_log_likelihood(x, ev.cuda(), t.cuda(), checks=False))
+
+
+def test_sorted_mode_packed_cohorts_float_times_and_ties():
+    """SORTED with cohorts packed back to back (the CV-sweep shape with continuous times, which used to raise): ragged cohort
+    sizes around the 2048-row scan tiles and 4096-key sort tiles, float times, integer days with heavy ties, a cohort without
+    events, cohorts whose hazards sit at very different levels; explicit mode and mode="auto"."""
+    lens = [5001, 1, 4096, 2049, 12_345, 2, 30_000, 777]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    n = int(off[-1])
+    lh, ev, t = synth.cohort(n, 51, few_ties=True)
+    lh, ev, t = lh.clone(), ev.clone(), t.clone()
+    t[off[2]:off[3]] = torch.floor(t[off[2]:off[3]] / 50.0)          # one cohort with integer times and heavy ties
+    t[off[6]:off[7]] = torch.round(t[off[6]:off[7]] * 4) / 4          # quarter-day ties
+    ev[off[3]:off[4]] = False                                         # a cohort without events: loss 0, zero gradient
+    lh[off[4]:off[5]] += 40.0                                         # levels far apart: every cohort has its own shift
+    lh[off[6]:off[7]] -= 25.0
+    w = torch.linspace(0.5, 2.0, len(lens)).cuda()
+    for mode in ("sorted", "auto"):
+        x = lh.cuda().requires_grad_(True)
+        losses = pkg.neg_partial_log_likelihood_segmented(x, ev.cuda(), t.cuda(), torch.tensor(off), mode=mode)
+        (losses * w).sum().backward()
+        ref_l, ref_g = ocox.cox_nll_segmented(lh.numpy().astype(np.float64), ev.numpy(), t.numpy(), off)
+        np.testing.assert_allclose(losses.detach().cpu().numpy(), ref_l, rtol=LOSS_RTOL, atol=1e-6, err_msg=mode)
+        g = x.grad.cpu().numpy()
+        for s in range(len(lens)):
+            a, b = off[s], off[s + 1]
+            rg = ref_g[a:b] * float(w[s])
+            assert np.abs(g[a:b] - rg).max() <= GRAD_RTOL * max(np.abs(rg).max(), 1e-30) + 2e-6, (mode, s)
+    # breslow and "sum" through the same path
+    for ties, red in (("breslow", "mean"), ("efron", "sum")):
+        losses = pkg.neg_partial_log_likelihood_segmented(lh.cuda(), ev.cuda(), t.cuda(), torch.tensor(off), ties, red, mode="sorted")
+        ref_l, _ = ocox.cox_nll_segmented(lh.numpy().astype(np.float64), ev.numpy(), t.numpy(), off, ties_method=ties, reduction=red)
+        np.testing.assert_allclose(losses.cpu().numpy(), ref_l, rtol=LOSS_RTOL, atol=1e-6)
+    # many small cohorts (two sort passes on the cohort id: more than 256 cohorts)
+    lens2 = [37] * 300
+    off2 = np.concatenate([[0], np.cumsum(lens2)])
+    lh2, ev2, t2 = synth.cohort(int(off2[-1]), 52, few_ties=True)
+    losses = pkg.neg_partial_log_likelihood_segmented(lh2.cuda(), ev2.cuda(), t2.cuda(), torch.tensor(off2), mode="sorted")
+    ref_l, _ = ocox.cox_nll_segmented(lh2.numpy().astype(np.float64), ev2.numpy(), t2.numpy(), off2)
+    np.testing.assert_allclose(losses.cpu().numpy(), ref_l, rtol=LOSS_RTOL, atol=1e-6)
