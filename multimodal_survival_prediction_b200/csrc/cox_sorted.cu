@@ -13,7 +13,8 @@
 //   keys    (time bits, censored bit) and the row index; per-cohort max log_hz (the exponent shift), flags
 //   sort    stable LSD radix sort, 4 passes of 8 bits on the key (+ 1-2 passes on the cohort id for packed cohorts), each
 //           pass = per-tile histograms, one scan of the (digit, tile) matrix, a scatter staged through shared memory
-//   R1      reverse scan: gathers log_hz through the permutation, w = exp(log_hz - shift); D (restarts per cohort), the
+//   weights w = exp(log_hz - shift) gathered through the permutation (element-wise kernel: the gathers need occupancy)
+//   R1      reverse scan: D (restarts per cohort), the
 //           group-suffix sums of event weight / event count (restart per tie group: at a group's first row they are E and
 //           m), ge = end of the row's group
 //   F1      forward max-scan: gs = start of the row's group
@@ -172,16 +173,55 @@ __device__ __forceinline__ void finish_sums(SegAcc *acc, SegSums &v) {
     }
 }
 
-// ---- R1 (reverse): weights, D, group-suffix sums, group ends
+// ---- weights in sorted order (a plain element-wise kernel: the two dependent gathers and the fp64 exp need the occupancy
+// a 148-register scan kernel does not have -- fused into the scan's load they cost 240 us per 4M rows at 12 % warp
+// occupancy, ncu r2_segscan); per-cohort sum of the event rows' log_hz and event count ride along
+__global__ void __launch_bounds__(256)
+k_weights(const float *__restrict__ log_hz, const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ idx_s,
+          const int64_t *__restrict__ seg_off, int n_seg, int64_t n, SegAcc *acc, float *__restrict__ w) {
+    __shared__ double red_d[32];
+    __shared__ long long red_l[32];
+    double se = 0.0;
+    long long ne = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, n_round = (n + 31) / 32 * 32;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
+        const bool in = p < n;
+        const int s = in ? seg_of(seg_off, n_seg, p) : -1;
+        const float eta = in ? log_hz[idx_s[p]] : 0.f;
+        const bool d = in && !(keys_s[p] & 1u);
+        if (in) w[p] = (float)exp((double)eta - (double)acc[s].max_eta);
+        if (seg_off == nullptr) {
+            if (d) { se += (double)eta; ne += 1; }
+        } else {  // packed cohorts: one pair of atomics per warp and iteration when its 32 positions share a cohort
+            const int s0 = __shfl_sync(FULL, s, 0);
+            if (__all_sync(FULL, s == s0 || s < 0)) {
+                const double ws = warp_sum(d ? (double)eta : 0.0);
+                const long long wc = warp_sum(d ? 1ll : 0ll);
+                if ((threadIdx.x & 31) == 0 && s0 >= 0 && wc > 0) {
+                    atomicAdd(&acc[s0].sum_eta, ws); atomicAdd(&acc[s0].n_ev, (unsigned long long)wc);
+                }
+            } else if (d) {
+                atomicAdd(&acc[s].sum_eta, (double)eta); atomicAdd(&acc[s].n_ev, 1ull);
+            }
+        }
+    }
+    if (seg_off == nullptr) {
+        se = block_reduce<double>(se, 0.0, OpAddD(), red_d);
+        ne = block_reduce<long long>(ne, 0ll, OpAddLL(), red_l);
+        if (threadIdx.x == 0 && ne > 0) { atomicAdd(&acc->sum_eta, se); atomicAdd(&acc->n_ev, (unsigned long long)ne); }
+    }
+}
+
+// ---- R1 (reverse): D, group-suffix sums, group ends
 struct LoadR1 {
-    const float *log_hz; const uint32_t *keys_s, *idx_s; const int64_t *seg_off; int n_seg; int64_t n; const SegAcc *acc;
+    const float *w; const uint32_t *keys_s; const int64_t *seg_off; int n_seg; int64_t n;
     __device__ Tup4 operator()(int64_t p) const {
         Tup4 t;
         const uint32_t k = keys_s[p];
         const int s = seg_of(seg_off, n_seg, p);
         const bool seg_tail = seg_off ? (p + 1 == seg_off[s + 1]) : (p == n - 1);
         const bool tail = seg_tail || ((keys_s[p + 1] >> 1) != (k >> 1));
-        const double w = exp((double)log_hz[idx_s[p]] - (double)acc[s].max_eta);
+        const double w = (double)this->w[p];
         const double d = (k & 1u) ? 0.0 : 1.0;
         t.a = w; t.b = w * d; t.c = d;
         t.i = (tail ? ((p + 2) | sortscan::T4_GROUP) : 0) | (seg_tail ? sortscan::T4_SEG : 0);
@@ -189,15 +229,12 @@ struct LoadR1 {
     }
 };
 struct StoreR1 {
-    const float *log_hz; const uint32_t *idx_s; const int64_t *seg_off; int n_seg; SegAcc *acc;
-    float *w; double *D, *Esuf; int *msuf, *ge;
-    SegSums sums;
-    __device__ void operator()(int64_t p, const Tup4 &inc, const Tup4 &el) {
-        w[p] = (float)el.a; D[p] = inc.a; Esuf[p] = inc.b; msuf[p] = (int)(inc.c + 0.5);
+    double *D, *Esuf; int *msuf, *ge;
+    __device__ void operator()(int64_t p, const Tup4 &inc, const Tup4 &) {
+        D[p] = inc.a; Esuf[p] = inc.b; msuf[p] = (int)(inc.c + 0.5);
         ge[p] = (int)((inc.i & sortscan::T4_POS) - 1);
-        if (el.c != 0.0) add_sums<0>(acc, sums, seg_of(seg_off, n_seg, p), (double)log_hz[idx_s[p]], 1);
     }
-    __device__ void finish() { finish_sums<0>(acc, sums); }
+    __device__ void finish() {}
 };
 // ---- F1 (forward): group starts
 struct LoadF1 {
@@ -345,8 +382,8 @@ int32_t cox_sorted_fwd_launch(const float *log_hz, const float *time, const uint
     rc = sortscan::radix_sort_pairs2(keys_s, idx_s, keys, vals, n, 32, n_seg > 1 ? segid : nullptr, seg_bits, tmp, st, &in_first);
     if (rc) return rc;
     const uint32_t *ks = in_first ? keys_s : keys, *is = in_first ? idx_s : vals;
-    rc = sortscan::seg_scan<sortscan::P_MIN, true, 2, 1, 1>(
-        n, LoadR1{log_hz, ks, is, seg_off, nseg, n, acc}, StoreR1{log_hz, is, seg_off, nseg, acc, wv, Dv, Ev, mv, ge, {-1, 0.0, 0}}, tmp, st);
+    k_weights<<<grid, 256, 0, st>>>(log_hz, ks, is, seg_off, nseg, n, acc, wv);
+    rc = sortscan::seg_scan<sortscan::P_MIN, true, 2, 1, 1>(n, LoadR1{wv, ks, seg_off, nseg, n}, StoreR1{Dv, Ev, mv, ge}, tmp, st);
     if (rc) return rc;
     rc = sortscan::seg_scan<sortscan::P_MAX, false, 0, 0, 0>(n, LoadF1{ks, seg_off, nseg}, StoreF1{gs}, tmp, st);
     if (rc) return rc;

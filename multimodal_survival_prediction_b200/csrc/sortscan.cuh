@@ -169,10 +169,15 @@ k_scan_lookback(int64_t n, Load load, Store store, ScanState st) {
             const int first_inc = m_inc ? __ffs(m_inc) - 1 : 32, first_none = m_none ? __ffs(m_none) - 1 : 32;
             const bool done = first_inc < first_none;                      // an inclusive prefix with no gap before it
             const int take = done ? first_inc + 1 : first_none;            // lanes [0, take) are combined (<= 32)
-            // combine in scan order: farthest tile first
-            Tup acc = tup_identity<IOP>();
-            for (int l = take - 1; l >= 0; --l) acc = tup_combine<IOP, SEGA, SEGB>(acc, tup_shfl(v, l));
-            prefix = tup_combine<IOP, SEGA, SEGB>(acc, prefix);
+            // combine in scan order, farthest tile first: an ordered five-step tree (a serial chain of 32 shuffled
+            // combines used to be the cost of every look-back hop)
+            if (lane >= take) v = tup_identity<IOP>();
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const Tup u = tup_shfl(v, (lane + d) & 31);
+                if (lane + d < 32) v = tup_combine<IOP, SEGA, SEGB>(u, v);
+            }
+            prefix = tup_combine<IOP, SEGA, SEGB>(tup_shfl(v, 0), prefix);
             if (done) break;
             look -= take;  // go on behind the tiles taken (take == 0: poll the same, still empty tile again)
         }
@@ -389,7 +394,7 @@ __device__ __forceinline__ bool t4_try_read(const unsigned long long *w, Tup4 &t
 // of the block arrive).  grid = number of tiles, SCAN_THREADS threads; state: words[2][ntiles][4] preset to SCAN_EMPTY and a
 // tile counter preset to 0 (k_scan_state_init over 8 * ntiles words).
 template <int POP, bool REVERSE, int RA, int RB, int RC, typename Load, typename Store>
-__global__ void __launch_bounds__(SCAN_THREADS)
+__global__ void __launch_bounds__(SCAN_THREADS, 3)   // <= 85 registers: three tiles per SM (at 148 it was one, 12 % occupancy)
 k_seg_scan(int64_t n, Load load, Store store, unsigned long long *agg, unsigned long long *inc_w, unsigned *counter) {
     __shared__ Tup4 s_warp[SCAN_THREADS / 32];
     __shared__ Tup4 s_prefix;
@@ -424,7 +429,7 @@ k_seg_scan(int64_t n, Load load, Store store, unsigned long long *agg, unsigned 
     Tup4 thread_excl = t4_shfl_up(inc, 1);
     if (lane == 0) thread_excl = t4_identity();
     thread_excl = t4_combine<POP, RA, RB, RC>(wpre, thread_excl);
-    if (warp == 0) {  // decoupled look-back, as in k_scan_lookback
+    if (warp == 0) {  // decoupled look-back
         if (lane == 0) {
             if (tile == 0) t4_publish(inc_w, tile_agg);
             else t4_publish(agg + 4 * tile, tile_agg);
@@ -432,21 +437,30 @@ k_seg_scan(int64_t n, Load load, Store store, unsigned long long *agg, unsigned 
         Tup4 prefix = t4_identity();
         int64_t look = tile - 1;
         for (int guard = 0; look >= 0 && guard < SCAN_SPIN_MAX; ++guard) {
+            // lane l examines tile look - l: 2 = inclusive prefix available, 1 = aggregate only, 0 = nothing yet; the eight
+            // words of both records are requested together (one round trip per poll)
             const int64_t q = look - lane;
             Tup4 v = t4_identity();
-            int state = 2;
+            int state = 2;  // lanes beyond tile 0 behave like "inclusive = identity"
             if (q >= 0) {
-                if (t4_try_read(inc_w + 4 * q, v)) state = 2;
-                else if (t4_try_read(agg + 4 * q, v)) state = 1;
-                else state = 0;
+                Tup4 vi, va;
+                const bool hi = t4_try_read(inc_w + 4 * q, vi), ha = t4_try_read(agg + 4 * q, va);
+                state = hi ? 2 : (ha ? 1 : 0);
+                v = hi ? vi : va;
             }
             const unsigned m_inc = __ballot_sync(FULL, state == 2), m_none = __ballot_sync(FULL, state == 0);
             const int first_inc = m_inc ? __ffs(m_inc) - 1 : 32, first_none = m_none ? __ffs(m_none) - 1 : 32;
             const bool done = first_inc < first_none;
-            const int take = done ? first_inc + 1 : first_none;
-            Tup4 acc = t4_identity();
-            for (int l = take - 1; l >= 0; --l) acc = t4_combine<POP, RA, RB, RC>(acc, t4_shfl(v, l));
-            prefix = t4_combine<POP, RA, RB, RC>(acc, prefix);
+            const int take = done ? first_inc + 1 : first_none;  // lanes [0, take) are combined (<= 32)
+            // ordered tree reduction, farthest tile first: after step d lane i holds tiles (i + 2d - 1 .. i); five steps
+            // instead of a 32-step serial chain of shuffles (that chain WAS the cost of a look-back hop)
+            if (lane >= take) v = t4_identity();
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const Tup4 u = t4_shfl(v, (lane + d) & 31);
+                if (lane + d < 32) v = t4_combine<POP, RA, RB, RC>(u, v);
+            }
+            prefix = t4_combine<POP, RA, RB, RC>(t4_shfl(v, 0), prefix);
             if (done) break;
             look -= take;
         }
