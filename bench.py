@@ -194,6 +194,70 @@ def run_reference(args):
     }))
 
 
+def sorted_few_ties(n, dev, reps=5):
+    """Cox Efron fwd+bwd on a FEW-TIES cohort (continuous times, SURVEY.md 8d variant): the SORTED path -- radix sort on
+    time + look-back scans -- through b200surv_cox_fwd / _bwd with caller-owned buffers.  Returns (ms fwd, ms bwd, loss)."""
+    import ctypes
+    import torch
+    from multimodal_survival_prediction_b200 import _lib as L
+    from multimodal_survival_prediction_b200 import synth
+    lib = L.load()
+    lh, ev, t = synth.cohort(n, SEED, few_ties=True)
+    x, e, tt = lh.to(dev), ev.to(dev), t.to(dev)
+    sb = lib.b200surv_cox_state_bytes(n, 1, L.COX_SORTED, 0)
+    wb = lib.b200surv_cox_workspace_bytes(n, 1, L.COX_SORTED, 0)
+    state = torch.empty(sb, dtype=torch.uint8, device=dev)
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    one = torch.ones(1, dtype=torch.float32, device=dev)
+    grad = torch.empty(n, dtype=torch.float32, device=dev)
+    st = L.stream_ptr(dev)
+
+    def fwd():
+        L.check(lib.b200surv_cox_fwd(L.ptr(x), L.ptr(tt), L.ptr(e), None, n, 1, L.TIES["efron"], L.REDUCE_MEAN_TERMS, L.COX_SORTED, 0,
+                                     ctypes.c_float(0.0), L.ptr(loss), L.ptr(state), sb, L.ptr(ws), wb, st), "b200surv_cox_fwd")
+
+    def bwd():
+        L.check(lib.b200surv_cox_bwd(L.ptr(one), L.ptr(state), sb, L.ptr(x), L.ptr(tt), L.ptr(e), None, n, 1, L.COX_SORTED, 0,
+                                     L.ptr(grad), st), "b200surv_cox_bwd")
+
+    for _ in range(3):
+        fwd(); bwd()
+    torch.cuda.synchronize()
+    tf = tb = 0.0
+    for _ in range(reps):
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record(); fwd(); b.record(); bwd(); c.record()
+        torch.cuda.synchronize()
+        tf += a.elapsed_time(b); tb += b.elapsed_time(c)
+    return tf / reps, tb / reps, float(loss.item())
+
+
+def run_few_ties(args):
+    """--workload few_ties: the SORTED path as its own bench line (one GPU)."""
+    import torch
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    n = args.rows
+    sampler = ClockSampler(0)
+    sampler.start()
+    fwd_ms, bwd_ms, loss = sorted_few_ties(n, dev, reps=max(args.steps, 3))
+    clocks = sampler.stop()
+    peak, peak_src = load_peaks()
+    ms = fwd_ms + bwd_ms
+    achieved = ALGO_BYTES_PER_ROW * n / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": METRIC, "value": n / (ms * 1e-3), "unit": "patients/s", "n_gpus": 1, "steps": max(args.steps, 3), "warmup": 3,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 sums over f32 inputs",
+        "data": "synthetic",
+        "config": {"workload": "cox_nll_fwd_bwd_efron_16M_few_ties", "rows_per_gpu": n, "ties": "efron", "time": "Exp(1000), continuous",
+                   "event_rate": 0.30, "mode": "sorted", "l2": "inputs and scratch (68 B/row) far larger than L2"},
+        "loss": loss,
+        "roofline": {"bound": "hbm", "scope": "step = sort + scans + gradient scatter, 22 algorithmic B/row", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "traffic": None},
+        "clocks": clocks}))
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -534,6 +598,76 @@ def run_b200(args):
 
     sweep_cox_ms, sweep_ci_ms = timed_ms(sweep_cox), timed_ms(sweep_ci)
 
+    # ---- BASELINE.json configs[4] END TO END: 256 fusion-head replicas x 5 folds x 100k patients across 8 GPUs = 32 replicas
+    # per GPU (with N ranks: 32 x N replicas, i.e. the full sweep at N = 8).  Per fold the rank stages the fold's RNA matrix
+    # once (bf16, shared by its replicas), runs every replica's gated head forward on the fold's 100k rows (eval mode), then
+    # ONE segmented Cox fwd+bwd over the 32 packed hazard vectors and ONE C-index call over the 32 packed cohorts; at the end
+    # one all-gather of the replica-fold C-indices.  Replicas are independent: no other collective.
+    folds = 5
+    fold_nets = [ghead.PartialModalityNet().to(dev).eval() for _ in range(sw_rep)]
+    fold_saved = ghead.head_saved_buffer(sw_rows, 5005, dev)
+    g_ = torch.Generator(device=dev).manual_seed(4321 + rank)
+    fold_x = torch.randn(sw_rows, 5005, device=dev, generator=g_)
+    fold_ct = torch.relu(torch.randn(sw_rows, 128, device=dev, generator=g_))
+    fold_clin = 0.3 + 0.6 * torch.rand(sw_rows, 1, device=dev, generator=g_)
+    fold_mask = (torch.rand(sw_rows, 3, device=dev, generator=g_) < torch.tensor([142 / 608, 427 / 608, 587 / 608], device=dev)).float()
+    fold_labels = []
+    for f in range(folds):
+        _, fev, ft = synth.cohort(sw_rows, 1000 + f)
+        fold_labels.append((fev.to(dev).repeat(sw_rep), ft.to(dev).repeat(sw_rep)))
+    hz_packed = torch.empty(sw_rep * sw_rows, dtype=torch.float32, device=dev)
+
+    def full_sweep():
+        counts = []
+        losses = []
+        with torch.no_grad():
+            for f in range(folds):
+                # (synthetic: the same feature matrices stand for every fold; the labels differ per fold)
+                ghead.stage_rna(fold_x, fold_saved)
+                for r_, net_ in enumerate(fold_nets):
+                    hz_, _ = ghead.fused_head(net_, fold_ct, fold_x, fold_clin, fold_mask, staged_saved=fold_saved)
+                    hz_packed[r_ * sw_rows:(r_ + 1) * sw_rows].copy_(hz_)
+                fev_, ft_ = fold_labels[f]
+                loss_, state_ = gcox.cox_fwd_raw(hz_packed, ft_, fev_, soff_d, sw_rep, L.TIES["efron"], L.REDUCE_MEAN_TERMS, L.COX_BINNED, 4096)
+                gcox.cox_bwd_raw(sones, state_, hz_packed, ft_, fev_, soff_d, sw_rep, L.COX_BINNED, 4096)
+                losses.append(loss_)
+                counts.append(gci.cindex_counts_cohorts(hz_packed, fev_, ft_, soff))
+        return torch.stack(losses), torch.stack(counts)      # [folds][replicas], [folds][replicas][6]
+
+    full_sweep()
+    barrier()
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    w0.record()
+    sweep_losses, sweep_counts = full_sweep()
+    w1.record()
+    barrier()
+    sweep_wall = time.perf_counter() - t_wall0
+    sweep_ms = torch.tensor([w0.elapsed_time(w1)], device=dev)
+    if world > 1:
+        dist.all_reduce(sweep_ms, op=dist.ReduceOp.MAX)
+    sweep_ms = float(sweep_ms.item())
+    ci_local = torch.tensor([[gci.cindex_from_counts(c) for c in fold_c] for fold_c in sweep_counts.cpu().tolist()], dtype=torch.float64,
+                            device=dev)                       # [folds][replicas of this rank]
+    if world > 1:
+        gathered = [torch.empty_like(ci_local) for _ in range(world)]
+        dist.all_gather(gathered, ci_local)                   # the one collective of the sweep: N x 160 C-indices
+        ci_all = torch.cat(gathered, dim=1)
+    else:
+        ci_all = ci_local
+    sweep_full = {"replicas": sw_rep * world, "folds": folds, "rows_per_fold": sw_rows, "replica_folds": int(ci_all.numel()),
+                  "ms_gpu_max_over_ranks": sweep_ms, "wall_s_rank0": sweep_wall,
+                  "replica_folds_per_s": ci_all.numel() / (sweep_ms * 1e-3),
+                  "c_index_mean": float(ci_all.mean()), "c_index_min": float(ci_all.min()), "c_index_max": float(ci_all.max()),
+                  "loss_mean": float(sweep_losses.mean()),
+                  "note": "per replica-fold: gated head forward on 100k rows (eval; the fold's RNA matrix staged once in bf16), then per "
+                          "fold one segmented Cox fwd+bwd over the packed hazards and one packed C-index call; all-gather of the "
+                          "C-indices at the end; 32 replicas per GPU (256 at 8 GPUs = BASELINE.json configs[4])"}
+    del fold_nets, fold_saved, fold_x, fold_ct, fold_clin, fold_mask, fold_labels, hz_packed
+
+    # ---- the SORTED path on the few-ties variant of the headline cohort (continuous times), this rank's GPU
+    ft_fwd_ms, ft_bwd_ms, ft_loss = sorted_few_ties(n, dev, reps=3)
+
     # ---- CPU baseline of the C-index (rank 0, N=1 only; bounded samples): the oracle's C brute force -- the same
     # O(n^2) pair rule as the GPU kernel and the reference's fallback (simple_fusion.py:59-73), all host cores (OpenMP)
     ci_cpu = None
@@ -607,9 +741,15 @@ def run_b200(args):
                       "cv_sweep": {"replicas_per_gpu": sw_rep, "rows_per_replica": sw_rows, "n_gpus": world,
                                    "cox_fwd_bwd_ms": sweep_cox_ms, "cindex_ms": sweep_ci_ms,
                                    "replica_evals_per_s": world * sw_rep / ((sweep_cox_ms + sweep_ci_ms) * 1e-3),
+                                   "end_to_end": sweep_full,
                                    "note": "32 replicas x 100k patients per GPU packed back to back: segmented Cox "
                                            "fwd+bwd (one call) + one C-index per replica; independent replicas, no "
                                            "collective (weak scaling)"},
+                      "sorted_few_ties": {"rows": n, "ms_fwd": ft_fwd_ms, "ms_bwd": ft_bwd_ms, "loss": ft_loss,
+                                          "patients_per_s": n / ((ft_fwd_ms + ft_bwd_ms) * 1e-3),
+                                          "frac_of_hbm_peak_22B_per_row": ALGO_BYTES_PER_ROW * n / ((ft_fwd_ms + ft_bwd_ms) * 1e-3) / 1e9 / peak,
+                                          "note": "continuous times (no BINNED path): radix sort on time + look-back scans + gradient "
+                                                  "scatter (mode sorted); also `bench.py --workload few_ties`; per rank"},
                       "cfg1_batch4_step": cfg1,
                       "ct_encoder": ct_extra,
                       "head_b4096": {"rows": hb, "ms_fwd_bwd": head_ms, "rows_per_s": hb / (head_ms * 1e-3),
@@ -637,11 +777,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=N_ROWS, help="rows per GPU (default: the BASELINE 16,777,216)")
     ap.add_argument("--skip-extras", action="store_true", help="only the timed fwd+bwd loop (for ncu launch lists)")
+    ap.add_argument("--workload", default="heavy_ties", choices=["heavy_ties", "few_ties"],
+                    help="heavy_ties: the BASELINE configuration (integer days, BINNED path); few_ties: continuous times, SORTED path")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1: per-bin sums meet inside the kernel over NVLink peer memory, or through an NCCL all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "few_ties":
+        run_few_ties(args)
     else:
         run_b200(args)
 
