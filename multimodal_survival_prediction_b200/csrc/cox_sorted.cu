@@ -9,22 +9,17 @@
 //   D = sum_{q >= gs, same cohort} w_q;  E, m = the group's event weight / event count;  l = p - gs for event rows;
 //   a_p = 1 / (D - (l/m) E), f_p = (l/m) a_p;  P = sum of a over the cohort's rows up to ge - 1;  F = the group's sum of f;
 //   grad = scale * (d - w (P - d F)).
-// Launch sequence (all hand-written, csrc/sortscan.cuh):
+// Launch sequence (all hand-written):
 //   keys    (time bits, censored bit) and the row index; per-cohort max log_hz (the exponent shift), flags
-//   sort    stable LSD radix sort, 4 passes of 8 bits on the key (+ 1-2 passes on the cohort id for packed cohorts), each
-//           pass = per-tile histograms, one scan of the (digit, tile) matrix, a scatter staged through shared memory
-//   weights w = exp(log_hz - shift) gathered through the permutation (element-wise kernel: the gathers need occupancy)
-//   R1      reverse scan: D (restarts per cohort), the
-//           group-suffix sums of event weight / event count (restart per tie group: at a group's first row they are E and
-//           m), ge = end of the row's group
-//   F1      forward max-scan: gs = start of the row's group
-//   F2      forward scan: forms a_p, f_p on the fly from (D, E, m) at gs; P (restarts per cohort), F (per group); the
-//           per-cohort sums of log-denominators / event-time counts ride along (Store::finish)
-//   loss    one small kernel per call: loss, scale, header of every cohort
-//   grad    gradient of every row, scattered back through the permutation
-// Every group sum is a SEGMENTED scan of the group's own terms -- never a difference of two running totals: with hazards
+//   sort    stable LSD radix sort (csrc/sortscan.cuh), 4 passes of 8 bits on the key (+ 1-2 passes on the cohort id for
+//           packed cohorts)
+//   weights w = exp(log_hz - shift) gathered through the permutation, as fp32 in sorted order
+//   tiles   reduce-then-scan over tiles of 2048 sorted rows (see "tile kernels" below): three sweeps over (key, w) and two
+//           single-CTA scans over the per-tile records; the last sweep scatters the gradient through the permutation
+// Every group sum is a SEGMENTED sum of the group's own terms -- never a difference of two running totals: with hazards
 // spread over tens of nats a late group's weights are 1e-15 of the total and a difference would be rounding noise.
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "sortscan.cuh"
@@ -39,7 +34,7 @@ struct SegAcc {  // per cohort, device accumulators
     unsigned long long n_ev, n_times;
     float max_eta, max_time;
     unsigned flags, pad;
-    double scale;  // d loss / d pll, written by k_loss
+    double scale;  // d loss / d pll, written by k_tile_scan2
 };
 
 __device__ __forceinline__ uint32_t time_key(float t, bool ev) {
@@ -115,64 +110,6 @@ k_make_keys(const float *__restrict__ log_hz, const float *__restrict__ time, co
     }
 }
 
-// per-thread partial sums keyed by cohort, flushed with warp aggregation (Store::finish of the scans)
-struct SegSums {
-    int seg;
-    double s0;
-    long long c0;
-};
-template <int WHICH>  // 0: (sum_eta, n_ev)   1: (sum_log, n_times)
-__device__ __forceinline__ void flush_sums(SegAcc *acc, SegSums &v) {
-    if (v.seg < 0) return;
-    if (WHICH == 0) { atomicAdd(&acc[v.seg].sum_eta, v.s0); atomicAdd(&acc[v.seg].n_ev, (unsigned long long)v.c0); }
-    else { atomicAdd(&acc[v.seg].sum_log, v.s0); atomicAdd(&acc[v.seg].n_times, (unsigned long long)v.c0); }
-    v.s0 = 0.0; v.c0 = 0;
-}
-template <int WHICH>
-__device__ __forceinline__ void add_sums(SegAcc *acc, SegSums &v, int seg, double s, long long c) {
-    if (seg != v.seg) { flush_sums<WHICH>(acc, v); v.seg = seg; }
-    v.s0 += s; v.c0 += c;
-}
-// end of the kernel: all threads of the block arrive.  A block whose threads hold one cohort (or nothing) -- every block of
-// a single-cohort call, nearly every block otherwise -- adds ONCE (two atomics per block: 16 k per scan at 16.7M rows, where
-// per-warp atomics on one address would cost more than the scan); else per warp, else per lane.
-template <int WHICH>
-__device__ __forceinline__ void finish_sums(SegAcc *acc, SegSums &v) {
-    __shared__ int sh_seg;
-    __shared__ double sh_s[32];
-    __shared__ long long sh_c[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    if (threadIdx.x == 0) sh_seg = -1;
-    __syncthreads();
-    if (v.seg >= 0) atomicMax(&sh_seg, v.seg);
-    __syncthreads();
-    const int sb = sh_seg;
-    if (__syncthreads_and(v.seg == sb || v.seg < 0)) {
-        const double s = warp_sum(v.seg < 0 ? 0.0 : v.s0);
-        const long long c = warp_sum(v.seg < 0 ? 0ll : v.c0);
-        if (lane == 0) { sh_s[warp] = s; sh_c[warp] = c; }
-        __syncthreads();
-        if (threadIdx.x == 0 && sb >= 0) {
-            double ts = 0.0;
-            long long tc = 0;
-            for (int k = 0; k < nw; ++k) { ts += sh_s[k]; tc += sh_c[k]; }
-            v.seg = sb; v.s0 = ts; v.c0 = tc;
-            flush_sums<WHICH>(acc, v);
-        }
-        return;
-    }
-    int s0 = v.seg;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s0 = max(s0, __shfl_xor_sync(FULL, s0, o));  // the cohort of the lanes that hold one
-    if (__all_sync(FULL, v.seg == s0 || v.seg < 0)) {
-        const double s = warp_sum(v.seg < 0 ? 0.0 : v.s0);
-        const long long c = warp_sum(v.seg < 0 ? 0ll : v.c0);
-        if (lane == 0 && s0 >= 0) { v.seg = s0; v.s0 = s; v.c0 = c; flush_sums<WHICH>(acc, v); }
-    } else {
-        flush_sums<WHICH>(acc, v);
-    }
-}
-
 // ---- weights in sorted order (a plain element-wise kernel: the two dependent gathers and the fp64 exp need the occupancy
 // a 148-register scan kernel does not have -- fused into the scan's load they cost 240 us per 4M rows at 12 % warp
 // occupancy, ncu r2_segscan); per-cohort sum of the event rows' log_hz and event count ride along
@@ -212,115 +149,748 @@ k_weights(const float *__restrict__ log_hz, const uint32_t *__restrict__ keys_s,
     }
 }
 
-// ---- R1 (reverse): D, group-suffix sums, group ends
-struct LoadR1 {
-    const float *w; const uint32_t *keys_s; const int64_t *seg_off; int n_seg; int64_t n;
-    __device__ Tup4 operator()(int64_t p) const {
-        Tup4 t;
-        const uint32_t k = keys_s[p];
-        const int s = seg_of(seg_off, n_seg, p);
-        const bool seg_tail = seg_off ? (p + 1 == seg_off[s + 1]) : (p == n - 1);
-        const bool tail = seg_tail || ((keys_s[p + 1] >> 1) != (k >> 1));
-        const double w = (double)this->w[p];
-        const double d = (k & 1u) ? 0.0 : 1.0;
-        t.a = w; t.b = w * d; t.c = d;
-        t.i = (tail ? ((p + 2) | sortscan::T4_GROUP) : 0) | (seg_tail ? sortscan::T4_SEG : 0);
-        return t;
+// ------------------------------------------------------------------------------------------------ tile kernels
+// Risk-set sums, Efron terms, loss and gradient as REDUCE-THEN-SCAN over tiles of 2048 sorted rows: no look-back chain and
+// no per-row fp64 intermediate in HBM.  A tile never crosses a cohort.  Tie groups that cross tile boundaries are handled
+// through per-tile FRAGMENT records (rows before the tile's first group head / from its last head on) chained by the two
+// single-CTA tile scans:
+//   k_tile_w      per tile: total weight, the two fragments' (weight, event weight, event count, rows)          [reads 8 B/row]
+//   k_tile_scan1  over tiles: S = weight of the cohort's later tiles; R = (E, m) of the rows AFTER the tile that belong to
+//                 its last row's group; L = (W, E, m, rows) of the rows BEFORE the tile that belong to its first row's group
+//   k_tile_terms  per tile: every group's (D, E, m) -> a_p, f_p, log-denominators; tile sums and fragment sums   [8 B/row]
+//   k_tile_scan2  over tiles: C = sum of a over the cohort's earlier tiles; AR, FR / FL = the open groups' sums of a, f in
+//                 later / earlier tiles; per-cohort loss, scale and header (the old k_loss)
+//   k_tile_grad   per tile: terms again, P at each group's end, gradient scattered through the permutation  [12 B/row + scatter]
+// Inside a tile the work is three block-wide scans over a blocked arrangement (8 consecutive rows per thread): reverse
+// (suffix weight; group-suffix event weight / count restarting at group tails; nearest tail), forward max (group start),
+// forward (prefix of a; group-prefix of f restarting at heads); group values reach their rows through shared memory.
+// The same tile sequence can span several GPUs (time-range shards): the tile records are then all-gathered and every rank
+// runs the tile scans over the whole sequence (b200surv_cox_sorted_* phase entry points, dist.py).
+constexpr int TS_THREADS = 256, TS_ITEMS = 8, TS_TILE = TS_THREADS * TS_ITEMS;
+constexpr int TS_NW = TS_THREADS / 32;
+constexpr int TF_FIRST = 1, TF_LAST = 2;   // first / last tile of its cohort
+constexpr int TS_KN = TS_TILE + 2 + (TS_TILE + 2) / 32 + 2;   // skewed 4-byte array with a halo of two
+constexpr int TS_DN = TS_TILE + TS_TILE / 8;                  // skewed 8-byte array
+
+struct TileW {   // 64 bytes
+    double Wtot, Ef, Wl, El;
+    int mf, ml, rowsf, rowsl, nheads, flags, pad0, pad1;
+};
+struct TileC1 {  // 48 bytes
+    double S, RE, LW, LE;
+    int Rm, Lm, Lrows, pad;
+};
+struct TileA {   // 64 bytes
+    double sumA, sumL, Af, Ff, Al, Fl;
+    int n_times, n_ev, pad0, pad1;
+};
+struct TileC2 { double C, AR, FR, FL; };
+static_assert(sizeof(TileW) == 64 && sizeof(TileA) == 64 && sizeof(TileC1) == 48 && sizeof(TileC2) == 32, "tile records");
+
+struct TileGeo {
+    int64_t p0;
+    int rows, seg, flags;
+    bool valid;
+};
+// tile -> (cohort, first row, rows).  One cohort: tiles of the whole range; packed cohorts: tile_base[s] = number of tiles
+// of the cohorts before s (k_tile_base), every cohort starts a new tile.
+__device__ __forceinline__ TileGeo tile_geo(int64_t t, const int64_t *__restrict__ seg_off, const int64_t *__restrict__ tile_base,
+                                            int n_seg, int64_t n) {
+    TileGeo g;
+    if (seg_off == nullptr) {
+        const int64_t nt = (n + TS_TILE - 1) / TS_TILE;
+        g.valid = t < nt; g.p0 = t * TS_TILE; g.seg = 0;
+        g.rows = (int)(n - g.p0 < TS_TILE ? n - g.p0 : TS_TILE);
+        g.flags = (t == 0 ? TF_FIRST : 0) | (t == nt - 1 ? TF_LAST : 0);
+        return g;
+    }
+    g.valid = t < tile_base[n_seg];
+    int lo = 0, hi = n_seg - 1;
+    while (lo < hi) {  // largest s with tile_base[s] <= t (an empty cohort shares its base with the next one)
+        const int mid = (lo + hi + 1) >> 1;
+        if (tile_base[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    g.seg = lo;
+    const int64_t c1 = seg_off[lo + 1];
+    g.p0 = seg_off[lo] + (t - tile_base[lo]) * TS_TILE;
+    g.rows = g.valid ? (int)(c1 - g.p0 < TS_TILE ? c1 - g.p0 : TS_TILE) : 0;
+    g.flags = (t == tile_base[lo] ? TF_FIRST : 0) | (t + 1 == tile_base[lo + 1] ? TF_LAST : 0);
+    return g;
+}
+
+__global__ void __launch_bounds__(1024)
+k_tile_base(const int64_t *__restrict__ seg_off, int n_seg, int64_t *__restrict__ tile_base) {
+    __shared__ int64_t s_part[1024];
+    const int t = threadIdx.x, per = (n_seg + 1023) / 1024;
+    int64_t sum = 0;
+    for (int k = 0; k < per; ++k) {
+        const int s = t * per + k;
+        if (s < n_seg) sum += (seg_off[s + 1] - seg_off[s] + TS_TILE - 1) / TS_TILE;
+    }
+    s_part[t] = sum;
+    __syncthreads();
+    if (t == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < 1024; ++i) { const int64_t v = s_part[i]; s_part[i] = run; run += v; }
+    }
+    __syncthreads();
+    int64_t run = s_part[t];
+    for (int k = 0; k < per; ++k) {
+        const int s = t * per + k;
+        if (s < n_seg) { tile_base[s] = run; run += (seg_off[s + 1] - seg_off[s] + TS_TILE - 1) / TS_TILE; }
+        if (s == n_seg - 1) tile_base[n_seg] = run;
+    }
+}
+
+// ---- block-wide scans over a blocked arrangement.  T: identity(), combine(first, second) with `first` earlier in SCAN
+// order, shfl(lane).  REV: scan order = descending thread index.  Returns the combination of everything before this thread.
+template <typename T, bool REV>
+__device__ __forceinline__ T block_prefix(const T &agg, T *s_warp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T inc = agg;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const T u = inc.shfl((REV ? lane + d : lane - d) & 31);
+        if (REV ? (lane + d < 32) : (lane >= d)) inc = T::combine(u, inc);
+    }
+    __syncthreads();  // s_warp may still be read from the previous scan
+    if (lane == (REV ? 0 : 31)) s_warp[warp] = inc;
+    __syncthreads();
+    T pre = T::identity();
+#pragma unroll
+    for (int k = 0; k < TS_NW; ++k) {
+        const int w = REV ? TS_NW - 1 - k : k;
+        if (REV ? (w > warp) : (w < warp)) pre = T::combine(pre, s_warp[w]);
+    }
+    T ex = inc.shfl((REV ? lane + 1 : lane - 1) & 31);
+    if (lane == (REV ? 31 : 0)) ex = T::identity();
+    return T::combine(pre, ex);
+}
+
+struct RevT {   // reverse scan: W = suffix weight; E, m = group-suffix (restart at tails); tpos = nearest tail at or after
+    double W, E;
+    int m, tpos;
+    static __device__ __forceinline__ RevT identity() { RevT r; r.W = 0.0; r.E = 0.0; r.m = 0; r.tpos = INT_MAX; return r; }
+    // x: rows after y's rows (already accumulated in reverse order)
+    static __device__ __forceinline__ RevT combine(const RevT &x, const RevT &y) {
+        RevT r;
+        const bool yt = y.tpos != INT_MAX;
+        r.W = x.W + y.W; r.E = yt ? y.E : x.E + y.E; r.m = yt ? y.m : x.m + y.m; r.tpos = min(x.tpos, y.tpos);
+        return r;
+    }
+    __device__ __forceinline__ RevT shfl(int src) const {
+        RevT r;
+        r.W = __shfl_sync(FULL, W, src); r.E = __shfl_sync(FULL, E, src); r.m = __shfl_sync(FULL, m, src);
+        r.tpos = __shfl_sync(FULL, tpos, src);
+        return r;
     }
 };
-struct StoreR1 {
-    double *D, *Esuf; int *msuf, *ge;
-    __device__ void operator()(int64_t p, const Tup4 &inc, const Tup4 &) {
-        D[p] = inc.a; Esuf[p] = inc.b; msuf[p] = (int)(inc.c + 0.5);
-        ge[p] = (int)((inc.i & sortscan::T4_POS) - 1);
-    }
-    __device__ void finish() {}
+struct MaxT {   // forward max scan of head positions (-1: none)
+    int h;
+    static __device__ __forceinline__ MaxT identity() { MaxT r; r.h = -1; return r; }
+    static __device__ __forceinline__ MaxT combine(const MaxT &x, const MaxT &y) { MaxT r; r.h = max(x.h, y.h); return r; }
+    __device__ __forceinline__ MaxT shfl(int src) const { MaxT r; r.h = __shfl_sync(FULL, h, src); return r; }
 };
-// ---- F1 (forward): group starts
-struct LoadF1 {
-    const uint32_t *keys_s; const int64_t *seg_off; int n_seg;
-    __device__ Tup4 operator()(int64_t p) const {
-        Tup4 t = sortscan::t4_identity();
-        const int s = seg_of(seg_off, n_seg, p);
-        const bool seg_head = seg_off ? (p == seg_off[s]) : (p == 0);
-        const bool head = seg_head || ((keys_s[p - 1] >> 1) != (keys_s[p] >> 1));
-        t.i = (head ? ((p + 1) | sortscan::T4_GROUP) : 0) | (seg_head ? sortscan::T4_SEG : 0);
-        return t;
+struct FwdT {   // forward scan: A = prefix of a; F = group-prefix of f (restart at heads)
+    double A, F;
+    int head;
+    static __device__ __forceinline__ FwdT identity() { FwdT r; r.A = 0.0; r.F = 0.0; r.head = 0; return r; }
+    static __device__ __forceinline__ FwdT combine(const FwdT &x, const FwdT &y) {
+        FwdT r;
+        r.A = x.A + y.A; r.F = y.head ? y.F : x.F + y.F; r.head = x.head | y.head;
+        return r;
     }
-};
-struct StoreF1 {
-    int *gs;
-    __device__ void operator()(int64_t p, const Tup4 &inc, const Tup4 &) { gs[p] = (int)((inc.i & sortscan::T4_POS) - 1); }
-    __device__ void finish() {}
-};
-// ---- F2 (forward): a_p, f_p on the fly; P, F; per-cohort log-denominator sums and event-time counts
-struct LoadF2 {
-    const uint32_t *keys_s; const int *gs; const double *D, *Esuf; const int *msuf; const int64_t *seg_off; int n_seg; int efron;
-    __device__ Tup4 operator()(int64_t p) const {
-        Tup4 t = sortscan::t4_identity();
-        const int g0 = gs[p];
-        const int s = seg_of(seg_off, n_seg, p);
-        const bool seg_head = seg_off ? (p == seg_off[s]) : (p == 0);
-        t.i = (g0 == (int)p ? sortscan::T4_GROUP : 0) | (seg_head ? sortscan::T4_SEG : 0);
-        if (!(keys_s[p] & 1u)) {
-            double den = D[g0], frac = 0.0;
-            if (efron) { frac = (double)((int)p - g0) / (double)msuf[g0]; den -= frac * Esuf[g0]; }
-            t.a = 1.0 / den; t.b = frac / den;
-        }
-        return t;
+    __device__ __forceinline__ FwdT shfl(int src) const {
+        FwdT r;
+        r.A = __shfl_sync(FULL, A, src); r.F = __shfl_sync(FULL, F, src); r.head = __shfl_sync(FULL, head, src);
+        return r;
     }
-};
-struct StoreF2 {
-    const uint32_t *keys_s; const int *gs; const int64_t *seg_off; int n_seg; SegAcc *acc;
-    double *PA, *PF;
-    SegSums sums;
-    __device__ void operator()(int64_t p, const Tup4 &inc, const Tup4 &el) {
-        PA[p] = inc.a; PF[p] = inc.b;
-        if (!(keys_s[p] & 1u)) {  // event row: log(den) = -log(a_p); one event time per group (counted at its first row)
-            const int s = seg_of(seg_off, n_seg, p);
-            add_sums<1>(acc, sums, s, -log(el.a) + (double)acc[s].max_eta, gs[p] == (int)p ? 1 : 0);
-        }
-    }
-    __device__ void finish() { finish_sums<1>(acc, sums); }
 };
 
-__global__ void __launch_bounds__(256)
-k_loss(SegAcc *acc, int n_seg, int ties, int reduction, float *__restrict__ out_loss, b200surv_cox_header *__restrict__ hdrs) {
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_seg; s += gridDim.x * blockDim.x) {
-        SegAcc &a = acc[s];
-        const double pll = a.sum_eta - a.sum_log;
-        const double n_ev = (double)a.n_ev, n_times = (double)a.n_times;
+__device__ __forceinline__ int sk(int j) { return j + (j >> 3); }    // skewed index of an 8-byte array read with stride 8
+__device__ __forceinline__ int sk4(int j) { return j + (j >> 5); }   // ... of a 4-byte array
+
+// What a thread holds of its 8 rows after tile_load: weight and flags (bit 0 head, 1 tail, 2 event).
+struct TileRows {
+    float w[TS_ITEMS];
+    unsigned flg[TS_ITEMS];
+};
+constexpr unsigned RF_HEAD = 1, RF_TAIL = 2, RF_EV = 4;
+
+// keys and weights of the tile through shared memory (coalesced loads at any alignment), then the blocked rows' flags.
+// A tile's first row continues the previous tile's group unless it is a head: equal time bits across the edge.  Rows past
+// the end of a partial tile are neutral (weight 0, no flags).
+__device__ __forceinline__ void tile_load(const TileGeo &g, const uint32_t *__restrict__ keys_s, const float *__restrict__ w,
+                                          uint32_t *s_key /*[TS_KN]*/, float *s_w /*[TS_KN]*/, TileRows &R) {
+    const int t = threadIdx.x;
+    // s_key[1 + j] = key of row j; s_key[0] / s_key[rows + 1] = the neighbours across the tile edges.  All loads of a thread
+    // are issued before the first store (one memory latency per tile, not one per element).
+    uint32_t kk[TS_ITEMS + 1];
+    float ww[TS_ITEMS];
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS + 1; ++k) {
+        const int j = t + k * TS_THREADS;
+        const bool edge = (j == 0 && (g.flags & TF_FIRST)) || (j == g.rows + 1 && (g.flags & TF_LAST));
+        kk[k] = (j < g.rows + 2 && !edge) ? keys_s[g.p0 + j - 1] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        const int j = t + k * TS_THREADS;
+        ww[k] = j < g.rows ? w[g.p0 + j] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS + 1; ++k) {
+        const int j = t + k * TS_THREADS;
+        if (j < g.rows + 2) s_key[j + (j >> 5)] = kk[k];
+    }
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        const int j = t + k * TS_THREADS;
+        if (j < g.rows) s_w[j + (j >> 5)] = ww[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        const int j = t * TS_ITEMS + k;
+        if (j < g.rows) {
+            const int j0 = j, j1 = j + 1, j2 = j + 2;
+            const uint32_t kp = s_key[j0 + (j0 >> 5)], kc = s_key[j1 + (j1 >> 5)], kn = s_key[j2 + (j2 >> 5)];
+            R.w[k] = s_w[j + (j >> 5)];
+            const bool head = (j == 0 && (g.flags & TF_FIRST)) || (kp >> 1) != (kc >> 1);
+            const bool tail = (j == g.rows - 1 && (g.flags & TF_LAST)) || (kn >> 1) != (kc >> 1);
+            R.flg[k] = (head ? RF_HEAD : 0u) | (tail ? RF_TAIL : 0u) | ((kc & 1u) ? 0u : RF_EV);
+        } else {
+            R.w[k] = 0.f; R.flg[k] = 0u;
+        }
+    }
+}
+
+// 1 / x and log x of a positive normal double from fp32 seeds on the mantissa (x = m 2^e, m in [1, 2)): two Newton steps
+// give the reciprocal to fp64 rounding; the logarithm is e ln 2 + logf(m), absolute error < 1e-7 on terms of size ~10 that
+// are averaged over the events (the full fp64 routines were half of the instructions of these kernels)
+__device__ __forceinline__ double fast_rcp(double x) {
+    const int hi = __double2hiint(x);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    double r = (double)__frcp_rn((float)m);
+    r = r * (2.0 - m * r);
+    r = r * (2.0 - m * r);
+    return __hiloint2double(__double2hiint(r) - (e << 20), __double2loint(r));
+}
+__device__ __forceinline__ double fast_log(double x) {
+    const int hi = __double2hiint(x);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    return (double)e * 0.6931471805599453 + (double)logf((float)m);
+}
+
+// first sweep: the tile's total weight and its two fragments, as masked sums (no scan needed yet)
+__global__ void __launch_bounds__(TS_THREADS)
+k_tile_w(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, const int64_t *__restrict__ seg_off,
+         const int64_t *__restrict__ tile_base, int n_seg, int64_t n, TileW *__restrict__ tw) {
+    __shared__ uint32_t s_key[TS_KN];
+    __shared__ float s_w[TS_KN];
+    __shared__ int s_hf[TS_NW], s_hl[TS_NW], s_nh[TS_NW];
+    __shared__ double s_sum[5][TS_NW];
+    __shared__ int s_cnt[2][TS_NW];
+    const TileGeo g = tile_geo(blockIdx.x, seg_off, tile_base, n_seg, n);
+    if (!g.valid) return;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    TileRows R;
+    tile_load(g, keys_s, w, s_key, s_w, R);
+    int hf = INT_MAX, hl = -1, nh = 0;
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k)
+        if (R.flg[k] & RF_HEAD) { const int j = t * TS_ITEMS + k; hf = min(hf, j); hl = max(hl, j); ++nh; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        hf = min(hf, __shfl_xor_sync(FULL, hf, o)); hl = max(hl, __shfl_xor_sync(FULL, hl, o)); nh += __shfl_xor_sync(FULL, nh, o);
+    }
+    if (lane == 0) { s_hf[warp] = hf; s_hl[warp] = hl; s_nh[warp] = nh; }
+    __syncthreads();
+    int first = INT_MAX, last = -1, nheads = 0;
+#pragma unroll
+    for (int q = 0; q < TS_NW; ++q) { first = min(first, s_hf[q]); last = max(last, s_hl[q]); nheads += s_nh[q]; }
+    if (!nheads) { first = g.rows; last = 0; }   // no head: both fragments are the whole tile
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};     // Wtot, Ef, Wl, El
+    int mf = 0, ml = 0;
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        const int j = t * TS_ITEMS + k;
+        const double wk = (double)R.w[k], ek = (R.flg[k] & RF_EV) ? wk : 0.0;
+        const int dk = (R.flg[k] & RF_EV) ? 1 : 0;
+        v[0] += wk;
+        if (j < first) { v[1] += ek; mf += dk; }
+        if (j >= last) { v[2] += wk; v[3] += ek; ml += dk; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = warp_sum(v[i]);
+    mf = (int)warp_sum((long long)mf); ml = (int)warp_sum((long long)ml);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_sum[i][warp] = v[i];
+        s_cnt[0][warp] = mf; s_cnt[1][warp] = ml;
+    }
+    __syncthreads();
+    if (t == 0) {
+        double r[4] = {0.0, 0.0, 0.0, 0.0};
+        int cf = 0, cl = 0;
+        for (int q = 0; q < TS_NW; ++q) {
+            for (int i = 0; i < 4; ++i) r[i] += s_sum[i][q];
+            cf += s_cnt[0][q]; cl += s_cnt[1][q];
+        }
+        TileW o;
+        o.Wtot = r[0]; o.Ef = r[1]; o.Wl = r[2]; o.El = r[3]; o.mf = cf; o.ml = cl;
+        o.rowsf = first; o.rowsl = g.rows - last; o.nheads = nheads; o.flags = g.flags; o.pad0 = 0; o.pad1 = 0;
+        tw[blockIdx.x] = o;
+    }
+}
+
+// ---- the two scans over tiles (one CTA).  Chains of fragments are segmented sums: they restart at every tile that holds
+// a head; the sums over a cohort's tiles restart at the cohort's first / last tile.
+template <int N>
+struct SegN {
+    double v[N];
+    int flag;
+    static __device__ __forceinline__ SegN identity() { SegN r; for (int i = 0; i < N; ++i) r.v[i] = 0.0; r.flag = 0; return r; }
+    static __device__ __forceinline__ SegN pick(bool take, const SegN &x) {            // x or the identity, without a branch
+        SegN r;
+        for (int i = 0; i < N; ++i) r.v[i] = take ? x.v[i] : 0.0;
+        r.flag = take ? x.flag : 0;
+        return r;
+    }
+    static __device__ __forceinline__ SegN combine(const SegN &x, const SegN &y) {   // x before y in scan order
+        SegN r;
+        for (int i = 0; i < N; ++i) r.v[i] = y.flag ? y.v[i] : x.v[i] + y.v[i];
+        r.flag = x.flag | y.flag;
+        return r;
+    }
+};
+constexpr int SC_THREADS = 512;
+template <int N>
+__device__ __forceinline__ SegN<N> seg_shfl(const SegN<N> &v, int src) {
+    SegN<N> r;
+    for (int i = 0; i < N; ++i) r.v[i] = __shfl_sync(FULL, v.v[i], src);
+    r.flag = __shfl_sync(FULL, v.flag, src);
+    return r;
+}
+// One round of a tile scan: thread i holds the element at scan position i of the round; returns the EXCLUSIVE prefix inside
+// the round and leaves the round's total in s_warp[32] (valid after the call for every thread).
+template <int N>
+__device__ __forceinline__ SegN<N> round_prefix(const SegN<N> &e, SegN<N> *s_warp /*[33]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // branch-free steps (a lane without a partner combines with the identity): a shuffle inside divergent code takes the
+    // WARPSYNC.COLLECTIVE slow path on this part
+    __syncwarp();
+    SegN<N> inc = e;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const SegN<N> u = seg_shfl(inc, (lane - d) & 31);
+        inc = SegN<N>::combine(SegN<N>::pick(lane >= d, u), inc);
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        SegN<N> v = lane < SC_THREADS / 32 ? s_warp[lane] : SegN<N>::identity();
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const SegN<N> u = seg_shfl(v, (lane - d) & 31);
+            v = SegN<N>::combine(SegN<N>::pick(lane >= d, u), v);
+        }
+        s_warp[lane] = v;
+        if (lane == SC_THREADS / 32 - 1) s_warp[32] = v;   // the round's total (lanes beyond the warp count hold nothing)
+    }
+    __syncthreads();
+    const SegN<N> pre = warp ? s_warp[warp - 1] : SegN<N>::identity();
+    SegN<N> ex = seg_shfl(inc, (lane - 1) & 31);
+    if (lane == 0) ex = SegN<N>::identity();
+    return SegN<N>::combine(pre, ex);
+}
+
+// A round covers SC_THREADS * SC_ITEMS tiles: every thread folds SC_ITEMS consecutive tiles (in scan order) on its own, one
+// block-wide prefix per round joins the threads, a carry joins the rounds.  pos = position in scan order; a reverse scan
+// visits tile T - 1 - pos.
+constexpr int SC_ITEMS = 8, SC_ROUND = SC_THREADS * SC_ITEMS;
+
+// grid = 2: CTA 0 scans the tiles in reverse (S, R), CTA 1 forward (L)
+__global__ void __launch_bounds__(SC_THREADS)
+k_tile_scan1(const TileW *__restrict__ tw, int64_t n_tiles_max, const int64_t *__restrict__ tile_base, int n_seg,
+             TileC1 *__restrict__ c1) {
+    __shared__ SegN<1> bufS[33];
+    __shared__ SegN<2> bufR[33];
+    __shared__ SegN<4> bufL[33];
+    const int64_t T = tile_base ? tile_base[n_seg] : n_tiles_max;
+    const int64_t rounds = (T + SC_ROUND - 1) / SC_ROUND;
+    if (blockIdx.x == 0) {   // reverse: S (restart at a cohort's last tile), chain of first fragments (E, m)
+        SegN<1> carS = SegN<1>::identity();
+        SegN<2> carR = SegN<2>::identity();
+        for (int64_t r = 0; r < rounds; ++r) {
+            SegN<1> eS[SC_ITEMS];
+            SegN<2> eR[SC_ITEMS];
+            int last[SC_ITEMS];
+            SegN<1> aggS = SegN<1>::identity();
+            SegN<2> aggR = SegN<2>::identity();
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k);
+                eS[k] = SegN<1>::identity(); eR[k] = SegN<2>::identity(); last[k] = 0;
+                if (q >= 0) {
+                    const TileW *x = tw + q;
+                    const int rowsf = x->rowsf, fl = x->flags;
+                    eS[k].v[0] = x->Wtot; eS[k].flag = (fl & TF_LAST) ? 1 : 0;
+                    eR[k].v[0] = rowsf ? x->Ef : 0.0; eR[k].v[1] = rowsf ? (double)x->mf : 0.0; eR[k].flag = x->nheads > 0;
+                    last[k] = fl & TF_LAST;
+                }
+                aggS = SegN<1>::combine(aggS, eS[k]); aggR = SegN<2>::combine(aggR, eR[k]);
+            }
+            SegN<1> stS = SegN<1>::combine(carS, round_prefix<1>(aggS, bufS));
+            SegN<2> stR = SegN<2>::combine(carR, round_prefix<2>(aggR, bufR));
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k);
+                if (q >= 0) {
+                    TileC1 *o = c1 + q;
+                    o->S = last[k] ? 0.0 : stS.v[0];
+                    o->RE = last[k] ? 0.0 : stR.v[0];
+                    o->Rm = last[k] ? 0 : (int)(stR.v[1] + 0.5);
+                }
+                stS = SegN<1>::combine(stS, eS[k]); stR = SegN<2>::combine(stR, eR[k]);
+            }
+            carS = SegN<1>::combine(carS, bufS[32]); carR = SegN<2>::combine(carR, bufR[32]);
+        }
+    } else {                 // forward: chain of last fragments (W, E, m, rows)
+        SegN<4> carL = SegN<4>::identity();
+        for (int64_t r = 0; r < rounds; ++r) {
+            SegN<4> e[SC_ITEMS];
+            int open[SC_ITEMS];
+            SegN<4> agg = SegN<4>::identity();
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                const int64_t q = r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k;
+                e[k] = SegN<4>::identity(); open[k] = 0;
+                if (q < T) {
+                    const TileW *x = tw + q;
+                    e[k].v[0] = x->Wl; e[k].v[1] = x->El; e[k].v[2] = (double)x->ml; e[k].v[3] = (double)x->rowsl;
+                    e[k].flag = x->nheads > 0;
+                    open[k] = x->rowsf > 0 && !(x->flags & TF_FIRST);
+                }
+                agg = SegN<4>::combine(agg, e[k]);
+            }
+            SegN<4> st = SegN<4>::combine(carL, round_prefix<4>(agg, bufL));
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                const int64_t q = r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k;
+                if (q < T) {
+                    TileC1 *o = c1 + q;
+                    o->LW = open[k] ? st.v[0] : 0.0; o->LE = open[k] ? st.v[1] : 0.0;
+                    o->Lm = open[k] ? (int)(st.v[2] + 0.5) : 0; o->Lrows = open[k] ? (int)(st.v[3] + 0.5) : 0; o->pad = 0;
+                }
+                st = SegN<4>::combine(st, e[k]);
+            }
+            carL = SegN<4>::combine(carL, bufL[32]);
+        }
+    }
+}
+
+// ---- per-row terms of a tile (shared by k_tile_terms and k_tile_grad): reverse scan -> every head publishes its group's
+// (D, E, m) -> forward max scan (group starts) -> a_p, f_p of the event rows
+struct TileTerms {
+    double a[TS_ITEMS], f[TS_ITEMS];
+    int gs[TS_ITEMS];     // start of the row's group inside the tile, -1: the group began in an earlier tile
+    int tpos[TS_ITEMS];   // last row of the row's group inside the tile, INT_MAX: the group reaches past the tile
+};
+template <bool WITH_LOG>
+__device__ __forceinline__ void tile_terms(const TileGeo &g, const TileRows &R, const TileW &tw, const TileC1 &c, int efron,
+                                           double *s_D, double *s_E, int *s_m, RevT *s_rev, MaxT *s_max, TileTerms &X,
+                                           double &sum_log) {
+    const int t = threadIdx.x;
+    {   // reverse scan; the tables take the place of the staged keys / weights (block_prefix synchronises first)
+        RevT agg = RevT::identity();
+#pragma unroll
+        for (int k = TS_ITEMS - 1; k >= 0; --k) {
+            RevT e;
+            const double w = (double)R.w[k];
+            e.W = w; e.E = (R.flg[k] & RF_EV) ? w : 0.0; e.m = (R.flg[k] & RF_EV) ? 1 : 0;
+            e.tpos = (R.flg[k] & RF_TAIL) ? t * TS_ITEMS + k : INT_MAX;
+            agg = RevT::combine(agg, e);
+        }
+        RevT acc = block_prefix<RevT, true>(agg, s_rev);
+#pragma unroll
+        for (int k = TS_ITEMS - 1; k >= 0; --k) {
+            const int j = t * TS_ITEMS + k;
+            RevT e;
+            const double w = (double)R.w[k];
+            e.W = w; e.E = (R.flg[k] & RF_EV) ? w : 0.0; e.m = (R.flg[k] & RF_EV) ? 1 : 0;
+            e.tpos = (R.flg[k] & RF_TAIL) ? j : INT_MAX;
+            acc = RevT::combine(acc, e);
+            X.tpos[k] = acc.tpos;
+            if (R.flg[k] & RF_HEAD) {   // a group that reaches the tile's end continues in later tiles (R)
+                const bool open = acc.tpos == INT_MAX;
+                s_D[sk(j)] = c.S + acc.W;
+                s_E[sk(j)] = acc.E + (open ? c.RE : 0.0);
+                s_m[sk4(j)] = acc.m + (open ? c.Rm : 0);
+            }
+        }
+    }
+    {   // group starts
+        MaxT agg = MaxT::identity();
+#pragma unroll
+        for (int k = 0; k < TS_ITEMS; ++k) if (R.flg[k] & RF_HEAD) agg.h = t * TS_ITEMS + k;
+        MaxT acc = block_prefix<MaxT, false>(agg, s_max);   // its barriers also order the table writes before the reads
+#pragma unroll
+        for (int k = 0; k < TS_ITEMS; ++k) {
+            if (R.flg[k] & RF_HEAD) acc.h = t * TS_ITEMS + k;
+            X.gs[k] = acc.h;
+        }
+    }
+    // the group of the rows before the first head began in an earlier tile (L); it may also reach past this tile (R)
+    const double Df = c.S + tw.Wtot + c.LW, Ef = c.LE + tw.Ef + (tw.nheads ? 0.0 : c.RE);
+    const int mf = c.Lm + tw.mf + (tw.nheads ? 0 : c.Rm);
+    sum_log = 0.0;
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        X.a[k] = 0.0; X.f[k] = 0.0;
+        if (R.flg[k] & RF_EV) {
+            const int j = t * TS_ITEMS + k, h = X.gs[k];
+            const double D = h >= 0 ? s_D[sk(h)] : Df, E = h >= 0 ? s_E[sk(h)] : Ef;
+            const int m = h >= 0 ? s_m[sk4(h)] : mf, l = h >= 0 ? j - h : c.Lrows + j;
+            double den = D, frac = 0.0;
+            if (efron && l > 0) { frac = (double)l * fast_rcp((double)m); den -= frac * E; }
+            const double a = fast_rcp(den);
+            X.a[k] = a; X.f[k] = frac * a;
+            if (WITH_LOG) sum_log += fast_log(den);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TS_THREADS, 3)
+k_tile_terms(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, const int64_t *__restrict__ seg_off,
+             const int64_t *__restrict__ tile_base, int n_seg, int64_t n, const TileW *__restrict__ tws,
+             const TileC1 *__restrict__ c1, int efron, TileA *__restrict__ ta) {
+    // (keys, weights) are staged only until the rows sit in registers; the group tables then take their place
+    __shared__ double s_pool[2 * TS_DN + (TS_KN + 1) / 2];
+    double *s_D = s_pool, *s_E = s_pool + TS_DN;
+    int *s_m = reinterpret_cast<int *>(s_pool + 2 * TS_DN);
+    uint32_t *s_key = reinterpret_cast<uint32_t *>(s_pool);
+    float *s_w = reinterpret_cast<float *>(s_key + TS_KN);
+    __shared__ RevT s_rev[TS_NW];
+    __shared__ MaxT s_max[TS_NW];
+    __shared__ double s_red[6][TS_NW];
+    __shared__ int s_redi[2][TS_NW];
+    const TileGeo g = tile_geo(blockIdx.x, seg_off, tile_base, n_seg, n);
+    if (!g.valid) return;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const TileW tw = tws[blockIdx.x];
+    const TileC1 c = c1[blockIdx.x];
+    TileRows R;
+    tile_load(g, keys_s, w, s_key, s_w, R);
+    TileTerms X;
+    double sl;
+    tile_terms<true>(g, R, tw, c, efron, s_D, s_E, s_m, s_rev, s_max, X, sl);
+    const int last = tw.nheads ? g.rows - tw.rowsl : 0;   // first row of the last fragment
+    double v[6] = {0.0, sl, 0.0, 0.0, 0.0, 0.0};
+    int nt = 0, ne = 0;
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        const int j = t * TS_ITEMS + k;
+        v[0] += X.a[k];
+        if (j < tw.rowsf) { v[2] += X.a[k]; v[3] += X.f[k]; }
+        if (j >= last) { v[4] += X.a[k]; v[5] += X.f[k]; }
+        ne += (R.flg[k] & RF_EV) ? 1 : 0; nt += (R.flg[k] & (RF_EV | RF_HEAD)) == (RF_EV | RF_HEAD) ? 1 : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = warp_sum(v[i]);
+    nt = (int)warp_sum((long long)nt); ne = (int)warp_sum((long long)ne);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s_red[i][warp] = v[i];
+        s_redi[0][warp] = nt; s_redi[1][warp] = ne;
+    }
+    __syncthreads();
+    if (t == 0) {
+        double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        int rt = 0, re = 0;
+        for (int q = 0; q < TS_NW; ++q) {
+            for (int i = 0; i < 6; ++i) r[i] += s_red[i][q];
+            rt += s_redi[0][q]; re += s_redi[1][q];
+        }
+        TileA o;
+        o.sumA = r[0]; o.sumL = r[1]; o.Af = r[2]; o.Ff = r[3]; o.Al = r[4]; o.Fl = r[5]; o.n_times = rt; o.n_ev = re;
+        o.pad0 = 0; o.pad1 = 0;
+        ta[blockIdx.x] = o;
+    }
+}
+
+// second tile scan + per-cohort loss / scale / header.  grid = 2: CTA 0 reverse (AR, FR), CTA 1 forward (C, FL, loss).
+__global__ void __launch_bounds__(SC_THREADS)
+k_tile_scan2(const TileW *__restrict__ tw, const TileA *__restrict__ ta, int64_t n_tiles_max, const int64_t *__restrict__ tile_base,
+             const int64_t *__restrict__ seg_off, int n_seg, int64_t n, int ties, int reduction, SegAcc *acc,
+             TileC2 *__restrict__ c2, float *__restrict__ out_loss, b200surv_cox_header *__restrict__ hdrs) {
+    __shared__ SegN<2> buf[33];
+    __shared__ SegN<4> bufC[33];
+    __shared__ SegN<1> bufF[33];
+    const int64_t T = tile_base ? tile_base[n_seg] : n_tiles_max;
+    const int64_t rounds = (T + SC_ROUND - 1) / SC_ROUND;
+    const int t = threadIdx.x;
+    if (blockIdx.x == 0) {   // reverse: chain of first fragments (A, F)
+        SegN<2> car = SegN<2>::identity();
+        for (int64_t r = 0; r < rounds; ++r) {
+            SegN<2> e[SC_ITEMS];
+            int last[SC_ITEMS];
+            SegN<2> agg = SegN<2>::identity();
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)t * SC_ITEMS + k);
+                e[k] = SegN<2>::identity(); last[k] = 0;
+                if (q >= 0) {
+                    const TileW *x = tw + q; const TileA *y = ta + q;
+                    const int rowsf = x->rowsf;
+                    e[k].v[0] = rowsf ? y->Af : 0.0; e[k].v[1] = rowsf ? y->Ff : 0.0; e[k].flag = x->nheads > 0;
+                    last[k] = x->flags & TF_LAST;
+                }
+                agg = SegN<2>::combine(agg, e[k]);
+            }
+            SegN<2> st = SegN<2>::combine(car, round_prefix<2>(agg, buf));
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)t * SC_ITEMS + k);
+                if (q >= 0) { c2[q].AR = last[k] ? 0.0 : st.v[0]; c2[q].FR = last[k] ? 0.0 : st.v[1]; }
+                st = SegN<2>::combine(st, e[k]);
+            }
+            car = SegN<2>::combine(car, buf[32]);
+        }
+        return;
+    }
+    {   // forward: C and the cohort's loss sums (restart at a cohort's first tile); chain of last fragments (F)
+        SegN<4> carC = SegN<4>::identity();
+        SegN<1> carF = SegN<1>::identity();
+        for (int64_t r = 0; r < rounds; ++r) {
+            SegN<4> e[SC_ITEMS];
+            SegN<1> ef[SC_ITEMS];
+            int fl[SC_ITEMS];   // bit 0: first tile of a cohort, 1: last, 2: the first row continues an earlier tile's group
+            SegN<4> aggC = SegN<4>::identity();
+            SegN<1> aggF = SegN<1>::identity();
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                const int64_t q = r * SC_ROUND + (int64_t)t * SC_ITEMS + k;
+                e[k] = SegN<4>::identity(); ef[k] = SegN<1>::identity(); fl[k] = 0;
+                if (q < T) {
+                    const TileW *x = tw + q; const TileA *y = ta + q;
+                    const int xf = x->flags;
+                    e[k].v[0] = y->sumA; e[k].v[1] = y->sumL; e[k].v[2] = (double)y->n_times; e[k].v[3] = (double)y->n_ev;
+                    e[k].flag = (xf & TF_FIRST) ? 1 : 0;
+                    ef[k].v[0] = y->Fl; ef[k].flag = x->nheads > 0;
+                    fl[k] = (xf & (TF_FIRST | TF_LAST)) | ((x->rowsf > 0 && !(xf & TF_FIRST)) ? 4 : 0);
+                }
+                aggC = SegN<4>::combine(aggC, e[k]); aggF = SegN<1>::combine(aggF, ef[k]);
+            }
+            SegN<4> stC = SegN<4>::combine(carC, round_prefix<4>(aggC, bufC));
+            SegN<1> stF = SegN<1>::combine(carF, round_prefix<1>(aggF, bufF));
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                const int64_t q = r * SC_ROUND + (int64_t)t * SC_ITEMS + k;
+                if (q < T) {
+                    c2[q].C = (fl[k] & TF_FIRST) ? 0.0 : stC.v[0];
+                    c2[q].FL = (fl[k] & 4) ? stF.v[0] : 0.0;
+                }
+                stC = SegN<4>::combine(stC, e[k]); stF = SegN<1>::combine(stF, ef[k]);
+                if (q < T && (fl[k] & TF_LAST)) {   // the cohort's totals are complete: its sums of log-denominators / event times
+                    const TileGeo g = tile_geo(q, seg_off, tile_base, n_seg, n);
+                    acc[g.seg].sum_log = stC.v[1];
+                    acc[g.seg].n_times = (unsigned long long)(stC.v[2] + 0.5);
+                }
+            }
+            carC = SegN<4>::combine(carC, bufC[32]); carF = SegN<1>::combine(carF, bufF[32]);
+        }
+    }
+    __syncthreads();
+    for (int s = t; s < n_seg; s += SC_THREADS) {
+        SegAcc &A = acc[s];
+        // sum_log holds the logs of the SHIFTED denominators: log sum w e^{shift} = log sum w + shift
+        const double pll = A.sum_eta - (A.sum_log + (double)A.n_ev * (double)A.max_eta);
+        const double n_ev = (double)A.n_ev, n_times = (double)A.n_times;
         double norm = 1.0;
         if (reduction == B200SURV_REDUCE_MEAN_EVENTS) norm = n_ev;
         else if (reduction == B200SURV_REDUCE_MEAN_TERMS) norm = (ties == B200SURV_TIES_EFRON) ? n_times : n_ev;
-        double scale = a.n_ev > 0 ? -1.0 / norm : 0.0, loss = a.n_ev > 0 ? -pll / norm : 0.0;
-        if (a.flags) { loss = __longlong_as_double(0x7ff8000000000000ll); scale = loss; }
-        a.scale = scale;
+        double scale = A.n_ev > 0 ? -1.0 / norm : 0.0, loss = A.n_ev > 0 ? -pll / norm : 0.0;
+        if (A.flags) { loss = __longlong_as_double(0x7ff8000000000000ll); scale = loss; }
+        A.scale = scale;
         b200surv_cox_header *hdr = hdrs + s;
-        hdr->flags = a.flags; hdr->mode = B200SURV_COX_SORTED; hdr->loss = (float)loss; hdr->scale = (float)scale;
-        hdr->shift = a.max_eta; hdr->max_log_hz = a.max_eta; hdr->max_time = a.max_time; hdr->nbins = 0;
-        hdr->n_events = (int64_t)a.n_ev; hdr->n_event_times = (int64_t)a.n_times; hdr->pll = pll; hdr->min_log_hz = 0.f;
+        hdr->flags = A.flags; hdr->mode = B200SURV_COX_SORTED; hdr->loss = (float)loss; hdr->scale = (float)scale;
+        hdr->shift = A.max_eta; hdr->max_log_hz = A.max_eta; hdr->max_time = A.max_time; hdr->nbins = 0;
+        hdr->n_events = (int64_t)A.n_ev; hdr->n_event_times = (int64_t)A.n_times; hdr->pll = pll; hdr->min_log_hz = 0.f;
         hdr->reserved = 0;
         out_loss[s] = (float)loss;
     }
 }
 
 // the state keeps the UNSCALED per-row gradient d loss / d log_hz for grad_out = 1 (cox_scale_grad multiplies by grad_out)
-__global__ void __launch_bounds__(256)
-k_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ idx_s, int64_t n, const float *__restrict__ w,
-       const double *__restrict__ PA, const double *__restrict__ PF, const int *__restrict__ ge, const int64_t *__restrict__ seg_off,
-       int n_seg, const SegAcc *__restrict__ acc, float *__restrict__ grad_unit) {
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
-        const double d = (keys_s[p] & 1u) ? 0.0 : 1.0;
-        const int gend = ge[p];
-        const double g = d - (double)w[p] * (PA[gend - 1] - d * PF[gend - 1]);
-        grad_unit[idx_s[p]] = (float)(acc[seg_of(seg_off, n_seg, p)].scale * g);
+__global__ void __launch_bounds__(TS_THREADS, 3)
+k_tile_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ idx_s, const float *__restrict__ w,
+            const int64_t *__restrict__ seg_off, const int64_t *__restrict__ tile_base, int n_seg, int64_t n,
+            const TileW *__restrict__ tws, const TileC1 *__restrict__ c1, const TileC2 *__restrict__ c2, int efron,
+            const SegAcc *__restrict__ acc, float *__restrict__ grad_unit) {
+    __shared__ double s_pool[2 * TS_DN + (TS_KN + 1) / 2];
+    double *s_D = s_pool, *s_E = s_pool + TS_DN;
+    int *s_m = reinterpret_cast<int *>(s_pool + 2 * TS_DN);
+    uint32_t *s_key = reinterpret_cast<uint32_t *>(s_pool);
+    float *s_w = reinterpret_cast<float *>(s_key + TS_KN);
+    __shared__ RevT s_rev[TS_NW];
+    __shared__ MaxT s_max[TS_NW];
+    __shared__ FwdT s_fwd[TS_NW];
+    const TileGeo g = tile_geo(blockIdx.x, seg_off, tile_base, n_seg, n);
+    if (!g.valid) return;
+    const int t = threadIdx.x;
+    const TileW tw = tws[blockIdx.x];
+    const TileC1 c = c1[blockIdx.x];
+    const TileC2 cc = c2[blockIdx.x];
+    const double scale = acc[g.seg].scale;
+    TileRows R;
+    tile_load(g, keys_s, w, s_key, s_w, R);
+    TileTerms X;
+    double sl;
+    tile_terms<false>(g, R, tw, c, efron, s_D, s_E, s_m, s_rev, s_max, X, sl);
+    // forward: P (prefix of a inside the tile), group-prefix of f
+    FwdT agg = FwdT::identity();
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        FwdT e; e.A = X.a[k]; e.F = X.f[k]; e.head = (R.flg[k] & RF_HEAD) ? 1 : 0;
+        agg = FwdT::combine(agg, e);
+    }
+    FwdT run = block_prefix<FwdT, false>(agg, s_fwd);   // its barriers: every thread is done with the (D, E, m) tables
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        FwdT e; e.A = X.a[k]; e.F = X.f[k]; e.head = (R.flg[k] & RF_HEAD) ? 1 : 0;
+        run = FwdT::combine(run, e);
+        const int j = t * TS_ITEMS + k;
+        if (j < g.rows) { s_D[sk(j)] = run.A; s_E[sk(j)] = run.F; }   // (P, F) at every row
+    }
+    uint32_t ridx[TS_ITEMS];   // the rows' original positions
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        const int j = t * TS_ITEMS + k;
+        ridx[k] = j < g.rows ? idx_s[g.p0 + j] : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        const int j = t * TS_ITEMS + k;
+        if (j < g.rows) {
+            const bool open = X.tpos[k] == INT_MAX;             // the row's group reaches past the tile
+            const int e = open ? g.rows - 1 : X.tpos[k];        // its last row inside the tile
+            const double PQ = cc.C + s_D[sk(e)] + (open ? cc.AR : 0.0);
+            const double Fg = s_E[sk(e)] + (open ? cc.FR : 0.0) + (X.gs[k] < 0 ? cc.FL : 0.0);
+            const double d = (R.flg[k] & RF_EV) ? 1.0 : 0.0;
+            const double gr = d - (double)R.w[k] * (PQ - d * Fg);
+            grad_unit[ridx[k]] = (float)(scale * gr);
+        }
     }
 }
 
 struct SortedLayout {
-    size_t off_acc, off_keys, off_vals, off_keys_s, off_idx_s, off_segid, off_w, off_D, off_E, off_m, off_ge, off_gs, off_PA, off_PF,
-        off_tmp, total;
+    size_t off_acc, off_keys, off_vals, off_keys_s, off_idx_s, off_segid, off_w, off_tbase, off_tw, off_c1, off_ta, off_c2, off_tmp, total;
+    int64_t tiles_max;
 };
 
 SortedLayout sorted_layout(int64_t n, int64_t n_seg) {
@@ -328,13 +898,16 @@ SortedLayout sorted_layout(int64_t n, int64_t n_seg) {
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     const size_t N = (size_t)(n > 0 ? n : 1);
+    L.tiles_max = (int64_t)((N + TS_TILE - 1) / TS_TILE) + (n_seg > 1 ? n_seg : 0);   // every cohort starts a new tile
+    const size_t T = (size_t)L.tiles_max;
     L.off_acc = take((size_t)n_seg * sizeof(SegAcc));
     L.off_keys = take(N * 4 + 4); L.off_vals = take(N * 4); L.off_keys_s = take(N * 4 + 4); L.off_idx_s = take(N * 4);
     L.off_segid = take(n_seg > 1 ? N * 4 : 4);
-    L.off_w = take(N * 4); L.off_D = take(N * 8); L.off_E = take(N * 8); L.off_m = take(N * 4); L.off_ge = take(N * 4);
-    L.off_gs = take(N * 4); L.off_PA = take(N * 8); L.off_PF = take(N * 8);
-    size_t tmp = sortscan::radix_sort_temp_bytes((int64_t)N), sc = sortscan::seg_scan_state_bytes((int64_t)N);
-    L.off_tmp = take(tmp > sc ? tmp : sc);
+    L.off_w = take(N * 4);
+    L.off_tbase = take((size_t)(n_seg + 1) * 8);
+    L.off_tw = take(T * sizeof(TileW)); L.off_c1 = take(T * sizeof(TileC1)); L.off_ta = take(T * sizeof(TileA));
+    L.off_c2 = take(T * sizeof(TileC2));
+    L.off_tmp = take(sortscan::radix_sort_temp_bytes((int64_t)N));
     L.total = o;
     return L;
 }
@@ -361,40 +934,66 @@ int32_t cox_sorted_fwd_launch(const float *log_hz, const float *time, const uint
     uint32_t *keys_s = reinterpret_cast<uint32_t *>(w8 + L.off_keys_s), *idx_s = reinterpret_cast<uint32_t *>(w8 + L.off_idx_s);
     uint32_t *segid = reinterpret_cast<uint32_t *>(w8 + L.off_segid);
     float *wv = reinterpret_cast<float *>(w8 + L.off_w);
-    double *Dv = reinterpret_cast<double *>(w8 + L.off_D), *Ev = reinterpret_cast<double *>(w8 + L.off_E);
-    int *mv = reinterpret_cast<int *>(w8 + L.off_m), *ge = reinterpret_cast<int *>(w8 + L.off_ge), *gs = reinterpret_cast<int *>(w8 + L.off_gs);
-    double *PA = reinterpret_cast<double *>(w8 + L.off_PA), *PF = reinterpret_cast<double *>(w8 + L.off_PF);
+    int64_t *tbase = seg_off ? reinterpret_cast<int64_t *>(w8 + L.off_tbase) : nullptr;
+    TileW *tw = reinterpret_cast<TileW *>(w8 + L.off_tw);
+    TileC1 *c1 = reinterpret_cast<TileC1 *>(w8 + L.off_c1);
+    TileA *ta = reinterpret_cast<TileA *>(w8 + L.off_ta);
+    TileC2 *c2 = reinterpret_cast<TileC2 *>(w8 + L.off_c2);
     void *tmp = w8 + L.off_tmp;
     int grid = (int)((n + 255) / 256);
     const int cap = 16 * num_sms();
     if (grid > cap) grid = cap;
     const int nseg = (int)n_seg;
+    const unsigned tiles = (unsigned)L.tiles_max;
+    const int efron = ties == B200SURV_TIES_EFRON ? 1 : 0;
 
     b200surv_cox_header *hdrs = static_cast<b200surv_cox_header *>(state);
     float *grad_unit = reinterpret_cast<float *>(hdrs + n_seg);
     int32_t rc;
 
+    // B200SURV_SORTED_TRACE=1: per-phase device times of this call on stderr (events on the caller's stream; debugging aid)
+    static const bool trace = getenv("B200SURV_SORTED_TRACE") != nullptr;
+    cudaEvent_t ev[10];
+    int nev = 0;
+    auto mark = [&]() { if (trace && nev < 10) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], st); ++nev; } };
+    mark();
     k_init_acc<<<(nseg + 255) / 256, 256, 0, st>>>(acc, nseg);
     // keys are generated into (keys_s, idx_s); radix_sort_pairs2 reports which buffer pair holds the result
     k_make_keys<<<grid, 256, 0, st>>>(log_hz, time, event, seg_off, nseg, n, keys_s, idx_s, segid, acc);
+    mark();
     const int seg_bits = n_seg == 1 ? 0 : (n_seg <= 256 ? 8 : 16);
     int in_first = 1;
     rc = sortscan::radix_sort_pairs2(keys_s, idx_s, keys, vals, n, 32, n_seg > 1 ? segid : nullptr, seg_bits, tmp, st, &in_first);
     if (rc) return rc;
+    mark();
     const uint32_t *ks = in_first ? keys_s : keys, *is = in_first ? idx_s : vals;
     k_weights<<<grid, 256, 0, st>>>(log_hz, ks, is, seg_off, nseg, n, acc, wv);
-    rc = sortscan::seg_scan<sortscan::P_MIN, true, 2, 1, 1>(n, LoadR1{wv, ks, seg_off, nseg, n}, StoreR1{Dv, Ev, mv, ge}, tmp, st);
-    if (rc) return rc;
-    rc = sortscan::seg_scan<sortscan::P_MAX, false, 0, 0, 0>(n, LoadF1{ks, seg_off, nseg}, StoreF1{gs}, tmp, st);
-    if (rc) return rc;
-    rc = sortscan::seg_scan<sortscan::P_NONE, false, 2, 1, 0>(
-        n, LoadF2{ks, gs, Dv, Ev, mv, seg_off, nseg, ties == B200SURV_TIES_EFRON ? 1 : 0},
-        StoreF2{ks, gs, seg_off, nseg, acc, PA, PF, {-1, 0.0, 0}}, tmp, st);
-    if (rc) return rc;
-    k_loss<<<(nseg + 255) / 256, 256, 0, st>>>(acc, nseg, ties, reduction, out_loss, hdrs);
-    k_grad<<<grid, 256, 0, st>>>(ks, is, n, wv, PA, PF, ge, seg_off, nseg, acc, grad_unit);
+    mark();
+    if (seg_off) k_tile_base<<<1, 1024, 0, st>>>(seg_off, nseg, tbase);
+    k_tile_w<<<tiles, TS_THREADS, 0, st>>>(ks, wv, seg_off, tbase, nseg, n, tw);
+    mark();
+    k_tile_scan1<<<2, SC_THREADS, 0, st>>>(tw, L.tiles_max, tbase, nseg, c1);
+    mark();
+    k_tile_terms<<<tiles, TS_THREADS, 0, st>>>(ks, wv, seg_off, tbase, nseg, n, tw, c1, efron, ta);
+    mark();
+    k_tile_scan2<<<2, SC_THREADS, 0, st>>>(tw, ta, L.tiles_max, tbase, seg_off, nseg, n, ties, reduction, acc, c2, out_loss, hdrs);
+    mark();
+    k_tile_grad<<<tiles, TS_THREADS, 0, st>>>(ks, is, wv, seg_off, tbase, nseg, n, tw, c1, c2, efron, acc, grad_unit);
+    mark();
+    if (trace) {
+        static const char *names[] = {"keys", "sort", "weights", "tile_w", "scan1", "terms", "scan2", "grad"};
+        cudaEventSynchronize(ev[nev - 1]);
+        fprintf(stderr, "[sorted n=%lld]", (long long)n);
+        for (int i = 0; i + 1 < nev; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            fprintf(stderr, " %s %.1f us", names[i], ms * 1e3f);
+        }
+        fprintf(stderr, "\n");
+        for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+    }
     B200_CHECK_CUDA(cudaGetLastError());
-    count_launches(2 + 4 * (4 + seg_bits / 8) + 6 + 2);
+    count_launches(2 + 4 * (4 + seg_bits / 8) + 1 + (seg_off ? 1 : 0) + 5);
     return B200SURV_OK;
 }
 

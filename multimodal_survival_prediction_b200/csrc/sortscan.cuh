@@ -296,7 +296,7 @@ inline RsLayout rs_layout(int64_t n) {
     L.total = o;
     return L;
 }
-inline size_t radix_sort_temp_bytes(int64_t n) { return rs_layout(n).total; }
+inline size_t radix_sort_temp_bytes_twokernel(int64_t n) { return rs_layout(n).total; }
 
 struct RsLoadHist {
     const int *hist;
@@ -612,29 +612,261 @@ inline int32_t radix_pass2(const uint32_t *ka, const uint32_t *va, uint32_t *kb,
     return B200SURV_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ round 2b: one sweep
+// LSD radix sort, ONE kernel per 8-bit pass ("onesweep"): a tile of 4096 pairs is ranked on chip (warp-level match ranking,
+// warps in order), publishes its 256 digit counts and finds the counts of all earlier tiles by DECOUPLED LOOK-BACK -- one
+// thread per digit, 64-bit words that carry their own state in the top two bits (0 = nothing yet, 1 = this tile's count,
+// 2 = inclusive count up to this tile), so there is no flag to order against -- then writes its pairs as digit runs from
+// shared memory.  The pairs are read once and written once per pass; the (digit, tile) count matrix, its scan and the
+// second read of the keys of the two-kernel pass above are gone.  The global digit totals a pass needs up front are counted
+// by the PREVIOUS pass (or by k_os_hist for the first).  Tile ids come from a ticket counter, so every tile a look-back
+// waits for is already running.
+constexpr int OS_THREADS = 256, OS_ITEMS = 16, OS_TILE = OS_THREADS * OS_ITEMS, OS_WARPS = OS_THREADS / 32;
+constexpr unsigned long long OS_VAL = (1ull << 62) - 1;
+constexpr int OS_MAX_PASSES = 8;
+
+struct DigitFn {   // digit of a pair: 8 bits of the key, or of table[value] (e.g. the cohort of a row)
+    const uint32_t *table;
+    int shift;
+};
+__device__ __forceinline__ int os_digit(const DigitFn &f, uint32_t key, uint32_t val) {
+    return (int)(((f.table ? f.table[val] : key) >> f.shift) & 255u);
+}
+
+static __global__ void __launch_bounds__(256)
+k_os_hist(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t n, DigitFn f, unsigned *__restrict__ hist) {
+    __shared__ unsigned s_cnt[256];
+    s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&s_cnt[os_digit(f, keys[i], f.table ? (vals ? vals[i] : (uint32_t)i) : 0u)], 1u);
+    __syncthreads();
+    if (s_cnt[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// VIA_VAL: a digit (of this pass or of the next one) is looked up through the value, so the values are needed before the
+// ranking; otherwise they are loaded late (fewer live registers while ranking).  vals == nullptr: the value of pair i is i.
+template <bool VIA_VAL>
+static __global__ void __launch_bounds__(OS_THREADS, 3)
+k_onesweep(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t n, DigitFn cur, DigitFn nxt, int count_next,
+           const unsigned *__restrict__ hist_cur, unsigned *__restrict__ hist_nxt, unsigned long long *state, unsigned *ticket,
+           uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+    __shared__ unsigned s_cnt[OS_WARPS][256];   // per warp: count of each digit, then its start inside the digit's run
+    __shared__ uint32_t s_k[OS_TILE], s_v[OS_TILE];
+    __shared__ int s_start[256];                // first staged position of each digit
+    __shared__ long long s_goff[256];           // global position of staged position 0 minus nothing: dst = s_goff[d] + p
+    __shared__ unsigned s_next[256];
+    __shared__ unsigned s_wt[2][OS_WARPS];
+    __shared__ unsigned s_tile;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = t; i < OS_WARPS * 256; i += OS_THREADS) (&s_cnt[0][0])[i] = 0;
+    s_next[t] = 0;
+    __syncthreads();
+    const int64_t tile = s_tile, tbase = tile * OS_TILE, base = tbase + (int64_t)warp * (OS_ITEMS * 32);
+    uint32_t k[OS_ITEMS], v[OS_ITEMS];
+    int rank[OS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        const int64_t i = base + r * 32 + lane;
+        k[r] = i < n ? keys[i] : 0xffffffffu;
+    }
+    if (VIA_VAL) {
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) {
+            const int64_t i = base + r * 32 + lane;
+            v[r] = i < n ? (vals ? vals[i] : (uint32_t)i) : 0u;
+        }
+    }
+    // ranking in three phases of 16 independent instructions each (match, add, shuffle), so that their latencies overlap:
+    // lanes of a round with the same digit form a group; the group's first lane adds the group to the warp's running count
+    // and hands the old value (= pairs of earlier rounds; shared atomics of one warp execute in program order) to the others
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned peers[OS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        const int64_t i = base + r * 32 + lane;
+        const bool in = i < n;
+        const int d = in ? os_digit(cur, k[r], VIA_VAL ? v[r] : 0u) : 0;
+        // lanes with the same digit, one ballot per digit bit (MATCH.ANY iterates over the distinct values of the warp:
+        // ~30 of them for uniform digits, and it was the longest stall of the pass)
+        unsigned m = __ballot_sync(FULL, in);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const unsigned bal = __ballot_sync(FULL, (d >> b) & 1);
+            m &= ((d >> b) & 1) ? bal : ~bal;
+        }
+        peers[r] = in ? m : (1u << lane);
+    }
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        const int64_t i = base + r * 32 + lane;
+        rank[r] = 0;
+        if (i < n && (peers[r] & lt) == 0)
+            rank[r] = (int)atomicAdd(&s_cnt[warp][os_digit(cur, k[r], VIA_VAL ? v[r] : 0u)], (unsigned)__popc(peers[r]));
+    }
+    if (count_next) {
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) {
+            const int64_t i = base + r * 32 + lane;
+            if (i < n) atomicAdd(&s_next[os_digit(nxt, k[r], VIA_VAL ? v[r] : 0u)], 1u);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r)
+        rank[r] = __shfl_sync(FULL, rank[r], __ffs(peers[r]) - 1) + __popc(peers[r] & lt);
+    __syncthreads();
+    // digit t: per-warp starts inside the run, the tile's count (published at once), starts of the runs on chip
+    unsigned run = 0;
+#pragma unroll
+    for (int w = 0; w < OS_WARPS; ++w) { const unsigned c = s_cnt[w][t]; s_cnt[w][t] = run; run += c; }
+    unsigned long long *slot = state + (size_t)tile * 256 + t;
+    if (tile > 0) scan_st(slot, (1ull << 62) | run);
+    // the first window of the look-back is requested now and examined after the staging (its latency hides behind it)
+    constexpr int LBW = 4;
+    unsigned long long win[LBW];
+    int64_t q = tile - 1;
+#pragma unroll
+    for (int j = 0; j < LBW; ++j) win[j] = q - j >= 0 ? scan_ld(state + (size_t)(q - j) * 256 + t) : (2ull << 62);
+    long long gbase;
+    int start;
+    {
+        unsigned inc_c = run, inc_h = hist_cur[t];
+        const unsigned h = inc_h;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned uc = __shfl_up_sync(FULL, inc_c, d), uh = __shfl_up_sync(FULL, inc_h, d);
+            if (lane >= d) { inc_c += uc; inc_h += uh; }
+        }
+        if (lane == 31) { s_wt[0][warp] = inc_c; s_wt[1][warp] = inc_h; }
+        __syncthreads();
+        unsigned pre_c = 0, pre_h = 0;
+#pragma unroll
+        for (int w = 0; w < OS_WARPS; ++w) { pre_c += (w < warp) ? s_wt[0][w] : 0u; pre_h += (w < warp) ? s_wt[1][w] : 0u; }
+        start = (int)(pre_c + inc_c - run);
+        gbase = (long long)(pre_h + inc_h - h);
+        s_start[t] = start;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        const int64_t i = base + r * 32 + lane;
+        if (i < n) {
+            const int d = os_digit(cur, k[r], VIA_VAL ? v[r] : 0u);
+            rank[r] += s_start[d] + (int)s_cnt[warp][d];
+            s_k[rank[r]] = k[r];
+        }
+    }
+    if (!VIA_VAL) {
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) {
+            const int64_t i = base + r * 32 + lane;
+            v[r] = i < n ? (vals ? vals[i] : (uint32_t)i) : 0u;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        const int64_t i = base + r * 32 + lane;
+        if (i < n) s_v[rank[r]] = v[r];
+    }
+    {   // look back over the earlier tiles' words for this digit, LBW words per round trip
+        unsigned long long excl = 0;
+        bool done = q < 0;
+        while (!done) {
+            int used = 0;
+#pragma unroll
+            for (int j = 0; j < LBW; ++j) {
+                const unsigned fl = (unsigned)(win[j] >> 62);
+                if (!done && used == j && fl != 0) {
+                    excl += win[j] & OS_VAL; ++used;
+                    if (fl == 2) done = true;
+                }
+            }
+            q -= used;
+            if (q < 0) done = true;
+            if (!done) {
+#pragma unroll
+                for (int j = 0; j < LBW; ++j) win[j] = q - j >= 0 ? scan_ld(state + (size_t)(q - j) * 256 + t) : (2ull << 62);
+            }
+        }
+        scan_st(slot, (2ull << 62) | (excl + run));
+        s_goff[t] = gbase + (long long)excl - start;
+    }
+    __syncthreads();
+    const int cnt = (int)(n - tbase < OS_TILE ? n - tbase : OS_TILE);
+#pragma unroll 4
+    for (int p = t; p < cnt; p += OS_THREADS) {
+        const uint32_t key = s_k[p], val = s_v[p];
+        const long long dst = s_goff[os_digit(cur, key, val)] + p;
+        keys_out[dst] = key;
+        vals_out[dst] = val;
+    }
+    if (count_next && s_next[t]) atomicAdd(&hist_nxt[t], s_next[t]);
+}
+
+struct OsLayout {
+    size_t off_hist, off_ticket, off_state, total;
+    int ntiles;
+};
+inline OsLayout os_layout(int64_t n) {
+    OsLayout L;
+    L.ntiles = (int)((n + OS_TILE - 1) / OS_TILE);
+    if (L.ntiles < 1) L.ntiles = 1;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    L.off_hist = take((size_t)OS_MAX_PASSES * 256 * sizeof(unsigned));
+    L.off_ticket = take((size_t)OS_MAX_PASSES * sizeof(unsigned));
+    L.off_state = take((size_t)L.ntiles * 256 * sizeof(unsigned long long));
+    L.total = o;
+    return L;
+}
+inline size_t onesweep_temp_bytes(int64_t n) { return os_layout(n).total; }
+inline size_t radix_sort_temp_bytes(int64_t n) { return os_layout(n).total; }
+
 // Stable sort of (key, value) pairs by keys[0, end_bit) and then -- if seg_table != nullptr -- by seg_table[value]
 // (seg_bits of it, a multiple of 8): pairs of one cohort end up contiguous, sorted by key inside the cohort.
-// keys_in / vals_in are overwritten (ping-pong); the result is in keys_in / vals_in when the TOTAL number of passes is
-// even, else in keys_out / vals_out: the function returns which through *in_first (1 = keys_in / vals_in).
+// vals_in == nullptr: the value of pair i is i (nothing is read for the first pass).  keys_in / vals_in are overwritten
+// (ping-pong; vals_in must still be a buffer of n values); the result is in keys_in / vals_in when the TOTAL number of
+// passes is even, else in keys_out / vals_out: the function returns which through *in_first (1 = keys_in / vals_in).
 inline int32_t radix_sort_pairs2(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n, int end_bit,
-                                 const uint32_t *seg_table, int seg_bits, void *temp, cudaStream_t st, int *in_first) {
-    uint32_t *ka = keys_in, *va = vals_in, *kb = keys_out, *vb = vals_out;
+                                 const uint32_t *seg_table, int seg_bits, void *temp, cudaStream_t st, int *in_first,
+                                 bool vals_are_iota = false) {
+    const OsLayout L = os_layout(n);
+    unsigned char *t8 = static_cast<unsigned char *>(temp);
+    unsigned *hist = reinterpret_cast<unsigned *>(t8 + L.off_hist), *ticket = reinterpret_cast<unsigned *>(t8 + L.off_ticket);
+    unsigned long long *state = reinterpret_cast<unsigned long long *>(t8 + L.off_state);
+    DigitFn fn[OS_MAX_PASSES + 1];
     int passes = 0;
-    for (int shift = 0; shift < end_bit; shift += 8, ++passes) {
-        const int32_t rc = radix_pass2(ka, va, kb, vb, KeyDirect{}, n, shift, temp, st);
-        if (rc) return rc;
+    for (int shift = 0; shift < end_bit; shift += 8) fn[passes++] = DigitFn{nullptr, shift};
+    if (seg_table != nullptr)
+        for (int shift = 0; shift < seg_bits; shift += 8) fn[passes++] = DigitFn{seg_table, shift};
+    if (passes > OS_MAX_PASSES) { set_error("radix sort: %d passes > %d", passes, OS_MAX_PASSES); return B200SURV_BAD_ARG; }
+    *in_first = (passes % 2 == 0) ? 1 : 0;
+    if (n <= 0 || passes == 0) return B200SURV_OK;
+    B200_CHECK_CUDA(cudaMemsetAsync(t8 + L.off_hist, 0, L.off_state - L.off_hist, st));   // digit totals and tickets
+    int hg = (int)((n + 255) / 256);
+    if (hg > 8 * num_sms()) hg = 8 * num_sms();
+    const uint32_t *va0 = vals_are_iota ? nullptr : vals_in;
+    k_os_hist<<<hg, 256, 0, st>>>(keys_in, va0, n, fn[0], hist);
+    uint32_t *ka = keys_in, *va = vals_in, *kb = keys_out, *vb = vals_out;
+    for (int p = 0; p < passes; ++p) {
+        B200_CHECK_CUDA(cudaMemsetAsync(state, 0, (size_t)L.ntiles * 256 * sizeof(unsigned long long), st));
+        const bool has_next = p + 1 < passes;
+        const DigitFn nxt = has_next ? fn[p + 1] : DigitFn{nullptr, 0};
+        const uint32_t *vsrc = (p == 0 && vals_are_iota) ? nullptr : va;
+        const bool via_val = fn[p].table != nullptr || (has_next && nxt.table != nullptr);
+        if (via_val)
+            k_onesweep<true><<<L.ntiles, OS_THREADS, 0, st>>>(ka, vsrc, n, fn[p], nxt, has_next ? 1 : 0, hist + p * 256,
+                                                              hist + (p + 1) * 256, state, ticket + p, kb, vb);
+        else
+            k_onesweep<false><<<L.ntiles, OS_THREADS, 0, st>>>(ka, vsrc, n, fn[p], nxt, has_next ? 1 : 0, hist + p * 256,
+                                                               hist + (p + 1) * 256, state, ticket + p, kb, vb);
         uint32_t *tk = ka; ka = kb; kb = tk;
         uint32_t *tv = va; va = vb; vb = tv;
     }
-    if (seg_table != nullptr) {
-        for (int shift = 0; shift < seg_bits; shift += 8, ++passes) {
-            const int32_t rc = radix_pass2(ka, va, kb, vb, KeyViaValue{seg_table}, n, shift, temp, st);
-            if (rc) return rc;
-            uint32_t *tk = ka; ka = kb; kb = tk;
-            uint32_t *tv = va; va = vb; vb = tv;
-        }
-    }
-    *in_first = (passes % 2 == 0) ? 1 : 0;
+    B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
 
