@@ -89,6 +89,9 @@ uint64_t b200surv_debug_launch_count(void);
                                          round to zero.  Re-run with a larger shift if the spread allows,
                                          else with SORTED (fp64).  The loss is poisoned with NaN.        */
 
+#define B200SURV_COXF_NOT_PARTITIONED 32u /* b200surv_cox_sorted_shard_*: a shard holds a time above the next shard's
+                                         smallest time (the shards are not time ranges).  Loss NaN.          */
+
 /* One 64-byte header per segment in the state buffer (device memory).  SMALL and SORTED: the n_seg headers are
  * contiguous at the start of the buffer.  BINNED: segment s owns the slice [s * stride, (s + 1) * stride) with
  * stride = b200surv_cox_state_bytes(n, 1, BINNED, nbins) = 64 + 8 * nbins; its header is the first 64 bytes of
@@ -181,6 +184,40 @@ int32_t b200surv_cox_binned_fwd_peer(const float *log_hz, const float *time, con
                                      float *out_loss, void *state, size_t state_bytes, void *workspace,
                                      size_t workspace_bytes, void *const *peer_bufs, int32_t world,
                                      int32_t rank, uint32_t epoch, b200surv_stream_t stream);
+
+/* SORTED mode over TIME-RANGE SHARDS for multi-GPU (path "Cox (B)"; BASELINE.json north_star: "an NCCL
+ * allgather of per-shard (time, event, log_hz) boundary aggregates, with exact carry-in of each shard's scan prefix").
+ * One cohort; shard r (rank r) holds n_r >= 1 rows in any order, every time of shard r <= every time of shard r + 1
+ * (equal times may sit on both sides of an edge: tie groups that cross shards are merged exactly).  What the reference does
+ * on one device with argsort + logcumsumexp (scripts/training/partial_modality_training.py:303-309) runs as four phases per
+ * shard; between two phases the caller all-gathers ONE record of b200surv_cox_shard_record_bytes() (128) bytes per shard
+ * (opaque; world * 128 bytes, shard order = time order) -- no other data crosses shards:
+ *   _keys    sort keys, the shard's max log_hz / min / max time                                   -> rec0
+ *   _sort    radix sort of the shard's rows (independent of rec0: overlap the all-gather with it)
+ *   _reduce  (all rec0) common exponent shift = global max log_hz, edge times of the neighbours, order check; weights,
+ *            per-tile sums, first tile scan; the shard's tile sequence folded into one element per chain   -> rec1
+ *   _terms   (all rec1) carry-in: risk-set weight of the later shards, open tie groups at both edges;
+ *            per-row Efron / Breslow terms, second tile scan                                              -> rec2
+ *   _finish  (all rec2) carry-in of the prefix sums; loss, scale and header (identical on every shard), the per-row
+ *            gradient of the shard's rows into `state`
+ * then b200surv_cox_bwd(mode SORTED, n = n_r, n_seg = 1) on the shard's state.  workspace / state sizes:
+ * b200surv_cox_workspace_bytes(n_r, 1, SORTED, 0) / b200surv_cox_state_bytes(n_r, 1, SORTED, 0).  The workspace carries
+ * the shard's intermediate results from phase to phase.  world <= 64.  The result equals b200surv_cox_fwd(SORTED) on the
+ * concatenated cohort up to fp64 summation order (fp32 loss / gradient: 1e-6 relative). */
+size_t b200surv_cox_shard_record_bytes(void);
+int32_t b200surv_cox_sorted_shard_keys(const float *log_hz, const float *time, const uint8_t *event, int64_t n,
+                                       void *rec0_out, void *workspace, size_t workspace_bytes,
+                                       b200surv_stream_t stream);
+int32_t b200surv_cox_sorted_shard_sort(int64_t n, void *workspace, size_t workspace_bytes, b200surv_stream_t stream);
+int32_t b200surv_cox_sorted_shard_reduce(const float *log_hz, int64_t n, const void *all_rec0, int32_t rank, int32_t world,
+                                         void *rec1_out, void *workspace, size_t workspace_bytes,
+                                         b200surv_stream_t stream);
+int32_t b200surv_cox_sorted_shard_terms(int64_t n, int32_t ties, const void *all_rec1, int32_t rank, int32_t world,
+                                        void *rec2_out, void *workspace, size_t workspace_bytes,
+                                        b200surv_stream_t stream);
+int32_t b200surv_cox_sorted_shard_finish(int64_t n, int32_t ties, int32_t reduction, const void *all_rec2, int32_t rank,
+                                         int32_t world, float *out_loss, void *state, size_t state_bytes,
+                                         void *workspace, size_t workspace_bytes, b200surv_stream_t stream);
 
 /* ---- Harrell's concordance index: integer pair counts -------------------------------------- */
 /* out_counts: int64[n_seg][6], ADDED to (caller zeroes): over rows i in [row_begin, row_end) of

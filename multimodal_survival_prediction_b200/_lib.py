@@ -16,6 +16,7 @@ COX_SMALL, COX_BINNED, COX_SORTED = 1, 2, 3
 COX_SMALL_MAX = 2048
 COX_MAX_BINS = 8192
 COXF_NOT_BINNABLE, COXF_EXP_RANGE, COXF_BAD_TIME, COXF_PEER_TIMEOUT, COXF_LOW_PRECISION = 1, 2, 4, 8, 16
+COXF_NOT_PARTITIONED = 32
 COX_HEADER_BYTES = 64
 
 
@@ -60,6 +61,15 @@ SIGNATURES = {
     "b200surv_cox_binned_fwd_peer": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
                                                c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p,
                                                c_int32, c_int32, ctypes.c_uint32, c_void_p]),
+    "b200surv_cox_shard_record_bytes": (c_size_t, []),
+    "b200surv_cox_sorted_shard_keys": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200surv_cox_sorted_shard_sort": (c_int32, [c_int64, c_void_p, c_size_t, c_void_p]),
+    "b200surv_cox_sorted_shard_reduce": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
+                                                   c_void_p]),
+    "b200surv_cox_sorted_shard_terms": (c_int32, [c_int64, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
+                                                  c_void_p]),
+    "b200surv_cox_sorted_shard_finish": (c_int32, [c_int64, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
+                                                   c_size_t, c_void_p, c_size_t, c_void_p]),
     "b200surv_gemm_bf16": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                      c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
     "b200surv_gemm_bf16_ex": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,

@@ -27,6 +27,11 @@ int32_t cox_scale_grad_launch(const float *, const void *, const int64_t *, int6
 size_t cox_sorted_workspace_bytes(int64_t n, int64_t n_seg);
 int32_t cox_sorted_fwd_launch(const float *, const float *, const uint8_t *, const int64_t *, int64_t, int64_t, int, int, float *,
                               void *, size_t, void *, size_t, cudaStream_t);
+int32_t cox_sorted_shard_keys(const float *, const float *, const uint8_t *, int64_t, void *, void *, size_t, cudaStream_t);
+int32_t cox_sorted_shard_sort(int64_t, void *, size_t, cudaStream_t);
+int32_t cox_sorted_shard_reduce(const float *, int64_t, const void *, int, int, void *, void *, size_t, cudaStream_t);
+int32_t cox_sorted_shard_terms(int64_t, int, const void *, int, int, void *, void *, size_t, cudaStream_t);
+int32_t cox_sorted_shard_finish(int64_t, int, int, const void *, int, int, float *, void *, size_t, void *, size_t, cudaStream_t);
 // cindex.cu
 size_t cindex_workspace_bytes(int64_t n, int algo);
 int32_t cindex_counts_launch(const float *, const float *, const uint8_t *, int64_t, int64_t, int64_t, float, int, int,
@@ -162,6 +167,34 @@ int32_t b200surv_cox_binned_fwd_peer(const float *log_hz, const float *time, con
     B200_REQUIRE(n >= 1, "n must be >= 1");
     return cox_binned_fwd_peer(log_hz, time, event, n, ties, reduction, nbins, shift, out_loss, state, state_bytes,
                                workspace, workspace_bytes, peer_bufs, world, rank, epoch, as_stream(stream));
+}
+
+size_t b200surv_cox_shard_record_bytes(void) { return 128; }
+
+int32_t b200surv_cox_sorted_shard_keys(const float *log_hz, const float *time, const uint8_t *event, int64_t n,
+                                       void *rec0_out, void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
+    B200_REQUIRE(log_hz && time && event && rec0_out, "null pointer");
+    return cox_sorted_shard_keys(log_hz, time, event, n, rec0_out, workspace, workspace_bytes, as_stream(stream));
+}
+int32_t b200surv_cox_sorted_shard_sort(int64_t n, void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
+    return cox_sorted_shard_sort(n, workspace, workspace_bytes, as_stream(stream));
+}
+int32_t b200surv_cox_sorted_shard_reduce(const float *log_hz, int64_t n, const void *all_rec0, int32_t rank, int32_t world,
+                                         void *rec1_out, void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
+    B200_REQUIRE(log_hz && all_rec0 && rec1_out, "null pointer");
+    return cox_sorted_shard_reduce(log_hz, n, all_rec0, rank, world, rec1_out, workspace, workspace_bytes, as_stream(stream));
+}
+int32_t b200surv_cox_sorted_shard_terms(int64_t n, int32_t ties, const void *all_rec1, int32_t rank, int32_t world,
+                                        void *rec2_out, void *workspace, size_t workspace_bytes, b200surv_stream_t stream) {
+    B200_REQUIRE(all_rec1 && rec2_out, "null pointer");
+    return cox_sorted_shard_terms(n, ties, all_rec1, rank, world, rec2_out, workspace, workspace_bytes, as_stream(stream));
+}
+int32_t b200surv_cox_sorted_shard_finish(int64_t n, int32_t ties, int32_t reduction, const void *all_rec2, int32_t rank,
+                                         int32_t world, float *out_loss, void *state, size_t state_bytes, void *workspace,
+                                         size_t workspace_bytes, b200surv_stream_t stream) {
+    B200_REQUIRE(all_rec2 && out_loss && state, "null pointer");
+    return cox_sorted_shard_finish(n, ties, reduction, all_rec2, rank, world, out_loss, state, state_bytes, workspace,
+                                   workspace_bytes, as_stream(stream));
 }
 
 size_t b200surv_cindex_workspace_bytes(int64_t n, int64_t n_seg, int32_t algo) {

@@ -33,8 +33,40 @@ struct SegAcc {  // per cohort, device accumulators
     double sum_eta, sum_log;
     unsigned long long n_ev, n_times;
     float max_eta, max_time;
-    unsigned flags, pad;
-    double scale;  // d loss / d pll, written by k_tile_scan2
+    unsigned flags;
+    float neg_min_time;  // max of -time (single cohort only; time-range shards exchange it)
+    double scale;  // d loss / d pll, written by k_tile_scan2 (shards: k_shard_finish)
+};
+
+// ---- time-range shards (multi-GPU, SURVEY.md 8e "Cox (B)"): shard r holds rows whose times are <= those of shard r + 1
+// (ties across an edge allowed).  Every shard sorts and tiles its own rows; what crosses shards are three fixed-size
+// records per shard, all-gathered by the caller, and the carries every shard folds out of them (k_shard_ctx*).
+constexpr int SHARD_REC_BYTES = 128, SHARD_MAX = 64;
+struct ShardRec0 {   // after the keys: what the neighbours and the common exponent shift need
+    float max_eta, min_time, max_time;
+    unsigned flags;
+    long long n;
+};
+struct ShardRec1 {   // after the first tile scan: the shard's whole tile sequence folded into one element per chain
+    double W;                       // total weight
+    double RE, Rm; int Rflag;       // reverse chain of first fragments (event weight, events); flag: the shard holds a head
+    int pad0;
+    double LW, LE, Lm, Lrows; int Lflag, pad1;   // forward chain of last fragments
+};
+struct ShardRec2 {   // after the second tile scan
+    double A, sum_log, sum_eta;     // sums of a, of log-denominators, of the event rows' log_hz
+    long long n_times, n_ev;
+    double AR, FR; int ARflag, pad0;   // reverse chain of first fragments (a, f)
+    double FL; int FLflag; unsigned flags;
+};
+static_assert(sizeof(ShardRec0) <= SHARD_REC_BYTES && sizeof(ShardRec1) <= SHARD_REC_BYTES && sizeof(ShardRec2) <= SHARD_REC_BYTES,
+              "shard records");
+struct ShardCtx {    // device-resident, one per call: what the tile kernels of this shard add to their shard-local values
+    uint32_t key_prev, key_next;    // time bits << 1 of the rows across the shard's edges
+    int has_prev, has_next;
+    double carS, carRE; int carRm, pad0;
+    double carLW, carLE; int carLm, carLrows;
+    double carC, carAR, carFR, carFL;
 };
 
 __device__ __forceinline__ uint32_t time_key(float t, bool ev) {
@@ -56,7 +88,7 @@ k_init_acc(SegAcc *acc, int n_seg) {
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_seg; s += gridDim.x * blockDim.x) {
         SegAcc a;
         a.sum_eta = 0.0; a.sum_log = 0.0; a.n_ev = 0; a.n_times = 0;
-        a.max_eta = -INFINITY; a.max_time = -INFINITY; a.flags = 0; a.pad = 0; a.scale = 0.0;
+        a.max_eta = -INFINITY; a.max_time = -INFINITY; a.flags = 0; a.neg_min_time = -INFINITY; a.scale = 0.0;
         acc[s] = a;
     }
 }
@@ -70,7 +102,7 @@ k_make_keys(const float *__restrict__ log_hz, const float *__restrict__ time, co
             uint32_t *__restrict__ segid, SegAcc *acc) {
     __shared__ float red_f[32];
     __shared__ unsigned red_u[32];
-    float mx = -INFINITY, mt = -INFINITY;
+    float mx = -INFINITY, mt = -INFINITY, mn = -INFINITY;
     unsigned flags = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n_round = (n + 31) / 32 * 32;  // whole warps iterate together (the shuffles below need every lane)
@@ -80,7 +112,7 @@ k_make_keys(const float *__restrict__ log_hz, const float *__restrict__ time, co
         const unsigned bad = (in && !(t >= 0.f)) ? B200SURV_COXF_BAD_TIME : 0u;
         if (in) { keys[i] = time_key(t, event[i] != 0); vals[i] = (uint32_t)i; }
         if (seg_off == nullptr) {
-            mx = fmaxf(mx, e); mt = fmaxf(mt, in ? t : -INFINITY); flags |= bad;
+            mx = fmaxf(mx, e); mt = fmaxf(mt, in ? t : -INFINITY); mn = fmaxf(mn, in ? -t : -INFINITY); flags |= bad;
         } else {
             const int s = in ? seg_of(seg_off, n_seg, i) : -1;
             if (in) segid[i] = (uint32_t)s;
@@ -101,10 +133,12 @@ k_make_keys(const float *__restrict__ log_hz, const float *__restrict__ time, co
     if (seg_off == nullptr) {
         mx = block_reduce<float>(mx, -INFINITY, OpMaxF(), red_f);
         mt = block_reduce<float>(mt, -INFINITY, OpMaxF(), red_f);
+        mn = block_reduce<float>(mn, -INFINITY, OpMaxF(), red_f);
         flags = block_reduce<unsigned>(flags, 0u, OpOrU(), red_u);
         if (threadIdx.x == 0) {
             atomic_max_float(&acc->max_eta, mx);
             atomic_max_float(&acc->max_time, mt);
+            atomic_max_float(&acc->neg_min_time, mn);
             if (flags) atomicOr(&acc->flags, flags);
         }
     }
@@ -178,30 +212,38 @@ struct TileW {   // 64 bytes
 };
 struct TileC1 {  // 48 bytes
     double S, RE, LW, LE;
-    int Rm, Lm, Lrows, pad;
+    int Rm, Lm, Lrows;
+    int cf;   // shards: bit 0 = no head in the shard's later tiles (add the R carry), bit 1 = ... earlier tiles (add the L carry)
 };
 struct TileA {   // 64 bytes
     double sumA, sumL, Af, Ff, Al, Fl;
     int n_times, n_ev, pad0, pad1;
 };
-struct TileC2 { double C, AR, FR, FL; };
-static_assert(sizeof(TileW) == 64 && sizeof(TileA) == 64 && sizeof(TileC1) == 48 && sizeof(TileC2) == 32, "tile records");
+struct TileC2 { double C, AR, FR, FL; int cr, cfw; };   // cr / cfw: as TileC1::cf, for (AR, FR) / FL
+static_assert(sizeof(TileW) == 64 && sizeof(TileA) == 64 && sizeof(TileC1) == 48 && sizeof(TileC2) == 40, "tile records");
 
 struct TileGeo {
     int64_t p0;
     int rows, seg, flags;
     bool valid;
+    int halo;                      // shards: bit 0 / 1 = the row before / after the tile lives on the previous / next shard
+    uint32_t key_prev, key_next;
 };
 // tile -> (cohort, first row, rows).  One cohort: tiles of the whole range; packed cohorts: tile_base[s] = number of tiles
 // of the cohorts before s (k_tile_base), every cohort starts a new tile.
 __device__ __forceinline__ TileGeo tile_geo(int64_t t, const int64_t *__restrict__ seg_off, const int64_t *__restrict__ tile_base,
-                                            int n_seg, int64_t n) {
+                                            int n_seg, int64_t n, const ShardCtx *__restrict__ ctx = nullptr) {
     TileGeo g;
+    g.halo = 0; g.key_prev = 0u; g.key_next = 0u;
     if (seg_off == nullptr) {
         const int64_t nt = (n + TS_TILE - 1) / TS_TILE;
         g.valid = t < nt; g.p0 = t * TS_TILE; g.seg = 0;
         g.rows = (int)(n - g.p0 < TS_TILE ? n - g.p0 : TS_TILE);
         g.flags = (t == 0 ? TF_FIRST : 0) | (t == nt - 1 ? TF_LAST : 0);
+        if (ctx != nullptr) {   // the cohort goes on across the shard's edges
+            if (t == 0 && ctx->has_prev) { g.flags &= ~TF_FIRST; g.halo |= 1; g.key_prev = ctx->key_prev; }
+            if (t == nt - 1 && ctx->has_next) { g.flags &= ~TF_LAST; g.halo |= 2; g.key_next = ctx->key_next; }
+        }
         return g;
     }
     g.valid = t < tile_base[n_seg];
@@ -330,8 +372,10 @@ __device__ __forceinline__ void tile_load(const TileGeo &g, const uint32_t *__re
 #pragma unroll
     for (int k = 0; k < TS_ITEMS + 1; ++k) {
         const int j = t + k * TS_THREADS;
-        const bool edge = (j == 0 && (g.flags & TF_FIRST)) || (j == g.rows + 1 && (g.flags & TF_LAST));
+        const bool edge = (j == 0 && ((g.flags & TF_FIRST) || (g.halo & 1))) || (j == g.rows + 1 && ((g.flags & TF_LAST) || (g.halo & 2)));
         kk[k] = (j < g.rows + 2 && !edge) ? keys_s[g.p0 + j - 1] : 0u;
+        if (j == 0 && (g.halo & 1)) kk[k] = g.key_prev;
+        if (j == g.rows + 1 && (g.halo & 2)) kk[k] = g.key_next;
     }
 #pragma unroll
     for (int k = 0; k < TS_ITEMS; ++k) {
@@ -387,13 +431,13 @@ __device__ __forceinline__ double fast_log(double x) {
 // first sweep: the tile's total weight and its two fragments, as masked sums (no scan needed yet)
 __global__ void __launch_bounds__(TS_THREADS)
 k_tile_w(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, const int64_t *__restrict__ seg_off,
-         const int64_t *__restrict__ tile_base, int n_seg, int64_t n, TileW *__restrict__ tw) {
+         const int64_t *__restrict__ tile_base, int n_seg, int64_t n, const ShardCtx *__restrict__ ctx, TileW *__restrict__ tw) {
     __shared__ uint32_t s_key[TS_KN];
     __shared__ float s_w[TS_KN];
     __shared__ int s_hf[TS_NW], s_hl[TS_NW], s_nh[TS_NW];
     __shared__ double s_sum[5][TS_NW];
     __shared__ int s_cnt[2][TS_NW];
-    const TileGeo g = tile_geo(blockIdx.x, seg_off, tile_base, n_seg, n);
+    const TileGeo g = tile_geo(blockIdx.x, seg_off, tile_base, n_seg, n, ctx);
     if (!g.valid) return;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     TileRows R;
@@ -516,7 +560,7 @@ constexpr int SC_ITEMS = 8, SC_ROUND = SC_THREADS * SC_ITEMS;
 // grid = 2: CTA 0 scans the tiles in reverse (S, R), CTA 1 forward (L)
 __global__ void __launch_bounds__(SC_THREADS)
 k_tile_scan1(const TileW *__restrict__ tw, int64_t n_tiles_max, const int64_t *__restrict__ tile_base, int n_seg,
-             TileC1 *__restrict__ c1) {
+             TileC1 *__restrict__ c1, ShardRec1 *__restrict__ rec /* shards: the folded sequence, else nullptr */) {
     __shared__ SegN<1> bufS[33];
     __shared__ SegN<2> bufR[33];
     __shared__ SegN<4> bufL[33];
@@ -554,11 +598,13 @@ k_tile_scan1(const TileW *__restrict__ tw, int64_t n_tiles_max, const int64_t *_
                     o->S = last[k] ? 0.0 : stS.v[0];
                     o->RE = last[k] ? 0.0 : stR.v[0];
                     o->Rm = last[k] ? 0 : (int)(stR.v[1] + 0.5);
+                    if (rec != nullptr && !last[k] && !stR.flag) atomicOr(&o->cf, 1);   // the forward CTA owns bit 1 of the same word
                 }
                 stS = SegN<1>::combine(stS, eS[k]); stR = SegN<2>::combine(stR, eR[k]);
             }
             carS = SegN<1>::combine(carS, bufS[32]); carR = SegN<2>::combine(carR, bufR[32]);
         }
+        if (rec != nullptr && threadIdx.x == 0) { rec->W = carS.v[0]; rec->RE = carR.v[0]; rec->Rm = carR.v[1]; rec->Rflag = carR.flag; rec->pad0 = 0; }
     } else {                 // forward: chain of last fragments (W, E, m, rows)
         SegN<4> carL = SegN<4>::identity();
         for (int64_t r = 0; r < rounds; ++r) {
@@ -584,13 +630,31 @@ k_tile_scan1(const TileW *__restrict__ tw, int64_t n_tiles_max, const int64_t *_
                 if (q < T) {
                     TileC1 *o = c1 + q;
                     o->LW = open[k] ? st.v[0] : 0.0; o->LE = open[k] ? st.v[1] : 0.0;
-                    o->Lm = open[k] ? (int)(st.v[2] + 0.5) : 0; o->Lrows = open[k] ? (int)(st.v[3] + 0.5) : 0; o->pad = 0;
+                    o->Lm = open[k] ? (int)(st.v[2] + 0.5) : 0; o->Lrows = open[k] ? (int)(st.v[3] + 0.5) : 0;
+                    if (rec != nullptr && open[k] && !st.flag) atomicOr(&o->cf, 2);
                 }
                 st = SegN<4>::combine(st, e[k]);
             }
             carL = SegN<4>::combine(carL, bufL[32]);
         }
+        if (rec != nullptr && threadIdx.x == 0) {
+            rec->LW = carL.v[0]; rec->LE = carL.v[1]; rec->Lm = carL.v[2]; rec->Lrows = carL.v[3]; rec->Lflag = carL.flag; rec->pad1 = 0;
+        }
     }
+}
+
+// shards: a tile's shard-local scan values plus what the other shards contribute (k_shard_ctx1 / k_shard_finish)
+__device__ __forceinline__ void shard_fix(TileC1 &c, const ShardCtx *__restrict__ ctx) {
+    if (ctx == nullptr) return;
+    c.S += ctx->carS;
+    if (c.cf & 1) { c.RE += ctx->carRE; c.Rm += ctx->carRm; }
+    if (c.cf & 2) { c.LW += ctx->carLW; c.LE += ctx->carLE; c.Lm += ctx->carLm; c.Lrows += ctx->carLrows; }
+}
+__device__ __forceinline__ void shard_fix(TileC2 &c, const ShardCtx *__restrict__ ctx) {
+    if (ctx == nullptr) return;
+    c.C += ctx->carC;
+    if (c.cr) { c.AR += ctx->carAR; c.FR += ctx->carFR; }
+    if (c.cfw) c.FL += ctx->carFL;
 }
 
 // ---- per-row terms of a tile (shared by k_tile_terms and k_tile_grad): reverse scan -> every head publishes its group's
@@ -654,7 +718,9 @@ __device__ __forceinline__ void tile_terms(const TileGeo &g, const TileRows &R, 
         if (R.flg[k] & RF_EV) {
             const int j = t * TS_ITEMS + k, h = X.gs[k];
             const double D = h >= 0 ? s_D[sk(h)] : Df, E = h >= 0 ? s_E[sk(h)] : Ef;
-            const int m = h >= 0 ? s_m[sk4(h)] : mf, l = h >= 0 ? j - h : c.Lrows + j;
+            // a group's events come first on every shard, so the events of the group before this row are j - h of this tile
+            // or, when the group began earlier, all the events of the earlier tiles (on one GPU that equals c.Lrows)
+            const int m = h >= 0 ? s_m[sk4(h)] : mf, l = h >= 0 ? j - h : c.Lm + j;
             double den = D, frac = 0.0;
             if (efron && l > 0) { frac = (double)l * fast_rcp((double)m); den -= frac * E; }
             const double a = fast_rcp(den);
@@ -667,7 +733,7 @@ __device__ __forceinline__ void tile_terms(const TileGeo &g, const TileRows &R, 
 __global__ void __launch_bounds__(TS_THREADS, 3)
 k_tile_terms(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, const int64_t *__restrict__ seg_off,
              const int64_t *__restrict__ tile_base, int n_seg, int64_t n, const TileW *__restrict__ tws,
-             const TileC1 *__restrict__ c1, int efron, TileA *__restrict__ ta) {
+             const TileC1 *__restrict__ c1, int efron, const ShardCtx *__restrict__ ctx, TileA *__restrict__ ta) {
     // (keys, weights) are staged only until the rows sit in registers; the group tables then take their place
     __shared__ double s_pool[2 * TS_DN + (TS_KN + 1) / 2];
     double *s_D = s_pool, *s_E = s_pool + TS_DN;
@@ -678,11 +744,12 @@ k_tile_terms(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, c
     __shared__ MaxT s_max[TS_NW];
     __shared__ double s_red[6][TS_NW];
     __shared__ int s_redi[2][TS_NW];
-    const TileGeo g = tile_geo(blockIdx.x, seg_off, tile_base, n_seg, n);
+    const TileGeo g = tile_geo(blockIdx.x, seg_off, tile_base, n_seg, n, ctx);
     if (!g.valid) return;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const TileW tw = tws[blockIdx.x];
-    const TileC1 c = c1[blockIdx.x];
+    TileC1 c = c1[blockIdx.x];
+    shard_fix(c, ctx);
     TileRows R;
     tile_load(g, keys_s, w, s_key, s_w, R);
     TileTerms X;
@@ -697,7 +764,10 @@ k_tile_terms(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, c
         v[0] += X.a[k];
         if (j < tw.rowsf) { v[2] += X.a[k]; v[3] += X.f[k]; }
         if (j >= last) { v[4] += X.a[k]; v[5] += X.f[k]; }
-        ne += (R.flg[k] & RF_EV) ? 1 : 0; nt += (R.flg[k] & (RF_EV | RF_HEAD)) == (RF_EV | RF_HEAD) ? 1 : 0;
+        // a distinct event time is counted at its event with l = 0: the group's head, or (shards only: the head is a censored
+        // row of the previous shard) the first row of a tile that continues a group without events so far
+        ne += (R.flg[k] & RF_EV) ? 1 : 0;
+        nt += ((R.flg[k] & (RF_EV | RF_HEAD)) == (RF_EV | RF_HEAD) || ((R.flg[k] & RF_EV) && j == 0 && X.gs[k] < 0 && c.Lm == 0)) ? 1 : 0;
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) v[i] = warp_sum(v[i]);
@@ -726,7 +796,8 @@ k_tile_terms(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, c
 __global__ void __launch_bounds__(SC_THREADS)
 k_tile_scan2(const TileW *__restrict__ tw, const TileA *__restrict__ ta, int64_t n_tiles_max, const int64_t *__restrict__ tile_base,
              const int64_t *__restrict__ seg_off, int n_seg, int64_t n, int ties, int reduction, SegAcc *acc,
-             TileC2 *__restrict__ c2, float *__restrict__ out_loss, b200surv_cox_header *__restrict__ hdrs) {
+             TileC2 *__restrict__ c2, float *__restrict__ out_loss, b200surv_cox_header *__restrict__ hdrs,
+             ShardRec2 *__restrict__ rec /* shards: the folded sequence (loss and header come from k_shard_finish), else nullptr */) {
     __shared__ SegN<2> buf[33];
     __shared__ SegN<4> bufC[33];
     __shared__ SegN<1> bufF[33];
@@ -755,11 +826,15 @@ k_tile_scan2(const TileW *__restrict__ tw, const TileA *__restrict__ ta, int64_t
 #pragma unroll
             for (int k = 0; k < SC_ITEMS; ++k) {
                 const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)t * SC_ITEMS + k);
-                if (q >= 0) { c2[q].AR = last[k] ? 0.0 : st.v[0]; c2[q].FR = last[k] ? 0.0 : st.v[1]; }
+                if (q >= 0) {
+                    c2[q].AR = last[k] ? 0.0 : st.v[0]; c2[q].FR = last[k] ? 0.0 : st.v[1];
+                    c2[q].cr = (!last[k] && !st.flag) ? 1 : 0;
+                }
                 st = SegN<2>::combine(st, e[k]);
             }
             car = SegN<2>::combine(car, buf[32]);
         }
+        if (rec != nullptr && t == 0) { rec->AR = car.v[0]; rec->FR = car.v[1]; rec->ARflag = car.flag; rec->pad0 = 0; }
         return;
     }
     {   // forward: C and the cohort's loss sums (restart at a cohort's first tile); chain of last fragments (F)
@@ -793,15 +868,24 @@ k_tile_scan2(const TileW *__restrict__ tw, const TileA *__restrict__ ta, int64_t
                 if (q < T) {
                     c2[q].C = (fl[k] & TF_FIRST) ? 0.0 : stC.v[0];
                     c2[q].FL = (fl[k] & 4) ? stF.v[0] : 0.0;
+                    c2[q].cfw = ((fl[k] & 4) && !stF.flag) ? 1 : 0;
                 }
                 stC = SegN<4>::combine(stC, e[k]); stF = SegN<1>::combine(stF, ef[k]);
-                if (q < T && (fl[k] & TF_LAST)) {   // the cohort's totals are complete: its sums of log-denominators / event times
+                if (rec == nullptr && q < T && (fl[k] & TF_LAST)) {   // the cohort's totals are complete: its sums of log-denominators / event times
                     const TileGeo g = tile_geo(q, seg_off, tile_base, n_seg, n);
                     acc[g.seg].sum_log = stC.v[1];
                     acc[g.seg].n_times = (unsigned long long)(stC.v[2] + 0.5);
                 }
             }
             carC = SegN<4>::combine(carC, bufC[32]); carF = SegN<1>::combine(carF, bufF[32]);
+        }
+        if (rec != nullptr) {
+            if (t == 0) {
+                rec->A = carC.v[0]; rec->sum_log = carC.v[1]; rec->n_times = (long long)(carC.v[2] + 0.5);
+                rec->n_ev = (long long)acc->n_ev; rec->sum_eta = acc->sum_eta;
+                rec->FL = carF.v[0]; rec->FLflag = carF.flag; rec->flags = acc->flags;
+            }
+            return;
         }
     }
     __syncthreads();
@@ -830,7 +914,7 @@ __global__ void __launch_bounds__(TS_THREADS, 3)
 k_tile_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ idx_s, const float *__restrict__ w,
             const int64_t *__restrict__ seg_off, const int64_t *__restrict__ tile_base, int n_seg, int64_t n,
             const TileW *__restrict__ tws, const TileC1 *__restrict__ c1, const TileC2 *__restrict__ c2, int efron,
-            const SegAcc *__restrict__ acc, float *__restrict__ grad_unit) {
+            const SegAcc *__restrict__ acc, const ShardCtx *__restrict__ ctx, float *__restrict__ grad_unit) {
     __shared__ double s_pool[2 * TS_DN + (TS_KN + 1) / 2];
     double *s_D = s_pool, *s_E = s_pool + TS_DN;
     int *s_m = reinterpret_cast<int *>(s_pool + 2 * TS_DN);
@@ -839,12 +923,14 @@ k_tile_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ id
     __shared__ RevT s_rev[TS_NW];
     __shared__ MaxT s_max[TS_NW];
     __shared__ FwdT s_fwd[TS_NW];
-    const TileGeo g = tile_geo(blockIdx.x, seg_off, tile_base, n_seg, n);
+    const TileGeo g = tile_geo(blockIdx.x, seg_off, tile_base, n_seg, n, ctx);
     if (!g.valid) return;
     const int t = threadIdx.x;
     const TileW tw = tws[blockIdx.x];
-    const TileC1 c = c1[blockIdx.x];
-    const TileC2 cc = c2[blockIdx.x];
+    TileC1 c = c1[blockIdx.x];
+    TileC2 cc = c2[blockIdx.x];
+    shard_fix(c, ctx);
+    shard_fix(cc, ctx);
     const double scale = acc[g.seg].scale;
     TileRows R;
     tile_load(g, keys_s, w, s_key, s_w, R);
@@ -888,8 +974,96 @@ k_tile_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ id
     }
 }
 
+// ---- time-range shards: record / carry kernels (one thread each: <= 64 shards)
+__global__ void k_shard_rec0(const SegAcc *__restrict__ acc, int64_t n, ShardRec0 *__restrict__ rec) {
+    if (threadIdx.x || blockIdx.x) return;
+    ShardRec0 r;
+    r.max_eta = acc->max_eta; r.min_time = -acc->neg_min_time; r.max_time = acc->max_time; r.flags = acc->flags; r.n = n;
+    *rec = r;
+}
+__device__ __forceinline__ const unsigned char *rec_at(const void *all, int r) {
+    return static_cast<const unsigned char *>(all) + (size_t)r * SHARD_REC_BYTES;
+}
+// common exponent shift, the neighbours' edge times, the order check: shard r's times must not exceed shard r + 1's
+__global__ void k_shard_ctx0(const void *__restrict__ all0, int rank, int world, SegAcc *acc, ShardCtx *ctx) {
+    if (threadIdx.x || blockIdx.x) return;
+    float mx = -INFINITY, mt = -INFINITY;
+    unsigned flags = 0;
+    for (int r = 0; r < world; ++r) {
+        const ShardRec0 *x = reinterpret_cast<const ShardRec0 *>(rec_at(all0, r));
+        mx = fmaxf(mx, x->max_eta); mt = fmaxf(mt, x->max_time); flags |= x->flags;
+        if (r + 1 < world) {
+            const ShardRec0 *y = reinterpret_cast<const ShardRec0 *>(rec_at(all0, r + 1));
+            if (!(x->max_time <= y->min_time)) flags |= B200SURV_COXF_NOT_PARTITIONED;
+        }
+    }
+    acc->max_eta = mx; acc->max_time = mt; acc->flags = flags;
+    ShardCtx c;
+    memset(&c, 0, sizeof(c));
+    c.has_prev = rank > 0; c.has_next = rank + 1 < world;
+    if (c.has_prev) c.key_prev = __float_as_uint(reinterpret_cast<const ShardRec0 *>(rec_at(all0, rank - 1))->max_time + 0.f) << 1;
+    if (c.has_next) c.key_next = __float_as_uint(reinterpret_cast<const ShardRec0 *>(rec_at(all0, rank + 1))->min_time + 0.f) << 1;
+    *ctx = c;
+}
+// carries of the first tile scan: the later shards' weight and chain of first fragments, the earlier shards' chain of last
+// fragments, folded in scan order with the restart rule of SegN::combine
+__global__ void k_shard_ctx1(const void *__restrict__ all1, int rank, int world, ShardCtx *ctx) {
+    if (threadIdx.x || blockIdx.x) return;
+    double S = 0.0, RE = 0.0, Rm = 0.0;
+    for (int r = world - 1; r > rank; --r) {
+        const ShardRec1 *x = reinterpret_cast<const ShardRec1 *>(rec_at(all1, r));
+        S += x->W;
+        if (x->Rflag) { RE = x->RE; Rm = x->Rm; } else { RE += x->RE; Rm += x->Rm; }
+    }
+    double LW = 0.0, LE = 0.0, Lm = 0.0, Lrows = 0.0;
+    for (int r = 0; r < rank; ++r) {
+        const ShardRec1 *x = reinterpret_cast<const ShardRec1 *>(rec_at(all1, r));
+        if (x->Lflag) { LW = x->LW; LE = x->LE; Lm = x->Lm; Lrows = x->Lrows; }
+        else { LW += x->LW; LE += x->LE; Lm += x->Lm; Lrows += x->Lrows; }
+    }
+    ctx->carS = S; ctx->carRE = RE; ctx->carRm = (int)(Rm + 0.5);
+    ctx->carLW = LW; ctx->carLE = LE; ctx->carLm = (int)(Lm + 0.5); ctx->carLrows = (int)(Lrows + 0.5);
+}
+// carries of the second tile scan, and the cohort's loss / scale / header from the shards' sums (every shard computes the
+// same values in the same order)
+__global__ void k_shard_finish(const void *__restrict__ all2, int rank, int world, int ties, int reduction, SegAcc *acc,
+                               ShardCtx *ctx, float *__restrict__ out_loss, b200surv_cox_header *__restrict__ hdr) {
+    if (threadIdx.x || blockIdx.x) return;
+    double AR = 0.0, FR = 0.0;
+    for (int r = world - 1; r > rank; --r) {
+        const ShardRec2 *x = reinterpret_cast<const ShardRec2 *>(rec_at(all2, r));
+        if (x->ARflag) { AR = x->AR; FR = x->FR; } else { AR += x->AR; FR += x->FR; }
+    }
+    double C = 0.0, FL = 0.0;
+    for (int r = 0; r < rank; ++r) {
+        const ShardRec2 *x = reinterpret_cast<const ShardRec2 *>(rec_at(all2, r));
+        C += x->A;
+        if (x->FLflag) FL = x->FL; else FL += x->FL;
+    }
+    ctx->carAR = AR; ctx->carFR = FR; ctx->carC = C; ctx->carFL = FL;
+    double sum_eta = 0.0, sum_log = 0.0;
+    long long n_ev = 0, n_times = 0;
+    unsigned flags = acc->flags;
+    for (int r = 0; r < world; ++r) {
+        const ShardRec2 *x = reinterpret_cast<const ShardRec2 *>(rec_at(all2, r));
+        sum_eta += x->sum_eta; sum_log += x->sum_log; n_ev += x->n_ev; n_times += x->n_times; flags |= x->flags;
+    }
+    const double pll = sum_eta - (sum_log + (double)n_ev * (double)acc->max_eta);
+    double norm = 1.0;
+    if (reduction == B200SURV_REDUCE_MEAN_EVENTS) norm = (double)n_ev;
+    else if (reduction == B200SURV_REDUCE_MEAN_TERMS) norm = (ties == B200SURV_TIES_EFRON) ? (double)n_times : (double)n_ev;
+    double scale = n_ev > 0 ? -1.0 / norm : 0.0, loss = n_ev > 0 ? -pll / norm : 0.0;
+    if (flags) { loss = __longlong_as_double(0x7ff8000000000000ll); scale = loss; }
+    acc->scale = scale; acc->flags = flags; acc->sum_eta = sum_eta; acc->sum_log = sum_log;
+    acc->n_ev = (unsigned long long)n_ev; acc->n_times = (unsigned long long)n_times;
+    hdr->flags = flags; hdr->mode = B200SURV_COX_SORTED; hdr->loss = (float)loss; hdr->scale = (float)scale;
+    hdr->shift = acc->max_eta; hdr->max_log_hz = acc->max_eta; hdr->max_time = acc->max_time; hdr->nbins = 0;
+    hdr->n_events = n_ev; hdr->n_event_times = n_times; hdr->pll = pll; hdr->min_log_hz = 0.f; hdr->reserved = 0;
+    out_loss[0] = (float)loss;
+}
+
 struct SortedLayout {
-    size_t off_acc, off_keys, off_vals, off_keys_s, off_idx_s, off_segid, off_w, off_tbase, off_tw, off_c1, off_ta, off_c2, off_tmp, total;
+    size_t off_acc, off_ctx, off_keys, off_vals, off_keys_s, off_idx_s, off_segid, off_w, off_tbase, off_tw, off_c1, off_ta, off_c2, off_tmp, total;
     int64_t tiles_max;
 };
 
@@ -901,6 +1075,7 @@ SortedLayout sorted_layout(int64_t n, int64_t n_seg) {
     L.tiles_max = (int64_t)((N + TS_TILE - 1) / TS_TILE) + (n_seg > 1 ? n_seg : 0);   // every cohort starts a new tile
     const size_t T = (size_t)L.tiles_max;
     L.off_acc = take((size_t)n_seg * sizeof(SegAcc));
+    L.off_ctx = take(sizeof(ShardCtx));
     L.off_keys = take(N * 4 + 4); L.off_vals = take(N * 4); L.off_keys_s = take(N * 4 + 4); L.off_idx_s = take(N * 4);
     L.off_segid = take(n_seg > 1 ? N * 4 : 4);
     L.off_w = take(N * 4);
@@ -970,15 +1145,15 @@ int32_t cox_sorted_fwd_launch(const float *log_hz, const float *time, const uint
     k_weights<<<grid, 256, 0, st>>>(log_hz, ks, is, seg_off, nseg, n, acc, wv);
     mark();
     if (seg_off) k_tile_base<<<1, 1024, 0, st>>>(seg_off, nseg, tbase);
-    k_tile_w<<<tiles, TS_THREADS, 0, st>>>(ks, wv, seg_off, tbase, nseg, n, tw);
+    k_tile_w<<<tiles, TS_THREADS, 0, st>>>(ks, wv, seg_off, tbase, nseg, n, nullptr, tw);
     mark();
-    k_tile_scan1<<<2, SC_THREADS, 0, st>>>(tw, L.tiles_max, tbase, nseg, c1);
+    k_tile_scan1<<<2, SC_THREADS, 0, st>>>(tw, L.tiles_max, tbase, nseg, c1, nullptr);
     mark();
-    k_tile_terms<<<tiles, TS_THREADS, 0, st>>>(ks, wv, seg_off, tbase, nseg, n, tw, c1, efron, ta);
+    k_tile_terms<<<tiles, TS_THREADS, 0, st>>>(ks, wv, seg_off, tbase, nseg, n, tw, c1, efron, nullptr, ta);
     mark();
-    k_tile_scan2<<<2, SC_THREADS, 0, st>>>(tw, ta, L.tiles_max, tbase, seg_off, nseg, n, ties, reduction, acc, c2, out_loss, hdrs);
+    k_tile_scan2<<<2, SC_THREADS, 0, st>>>(tw, ta, L.tiles_max, tbase, seg_off, nseg, n, ties, reduction, acc, c2, out_loss, hdrs, nullptr);
     mark();
-    k_tile_grad<<<tiles, TS_THREADS, 0, st>>>(ks, is, wv, seg_off, tbase, nseg, n, tw, c1, c2, efron, acc, grad_unit);
+    k_tile_grad<<<tiles, TS_THREADS, 0, st>>>(ks, is, wv, seg_off, tbase, nseg, n, tw, c1, c2, efron, acc, nullptr, grad_unit);
     mark();
     if (trace) {
         static const char *names[] = {"keys", "sort", "weights", "tile_w", "scan1", "terms", "scan2", "grad"};
@@ -994,6 +1169,122 @@ int32_t cox_sorted_fwd_launch(const float *log_hz, const float *time, const uint
     }
     B200_CHECK_CUDA(cudaGetLastError());
     count_launches(2 + 4 * (4 + seg_bits / 8) + 1 + (seg_off ? 1 : 0) + 5);
+    return B200SURV_OK;
+}
+
+
+// ---- time-range shards: the same kernels in four phases; the caller all-gathers one 128-byte record per shard between them
+namespace {
+struct ShardPtrs {
+    SortedLayout L;
+    SegAcc *acc; ShardCtx *ctx;
+    uint32_t *keys, *vals, *keys_s, *idx_s;
+    float *wv;
+    TileW *tw; TileC1 *c1; TileA *ta; TileC2 *c2;
+    void *tmp;
+    int grid; unsigned tiles;
+};
+int32_t shard_ptrs(int64_t n, void *ws, size_t ws_bytes, ShardPtrs &P) {
+    B200_REQUIRE(ws != nullptr, "workspace");
+    B200_REQUIRE(n >= 1 && n < (int64_t)INT_MAX - 2, "every shard needs n in [1, 2^31) rows");
+    P.L = sorted_layout(n, 1);
+    if (ws_bytes < P.L.total) { set_error("cox sorted shard: workspace %zu < %zu", ws_bytes, P.L.total); return B200SURV_WORKSPACE_TOO_SMALL; }
+    unsigned char *w8 = static_cast<unsigned char *>(ws);
+    P.acc = reinterpret_cast<SegAcc *>(w8 + P.L.off_acc);
+    P.ctx = reinterpret_cast<ShardCtx *>(w8 + P.L.off_ctx);
+    P.keys = reinterpret_cast<uint32_t *>(w8 + P.L.off_keys); P.vals = reinterpret_cast<uint32_t *>(w8 + P.L.off_vals);
+    P.keys_s = reinterpret_cast<uint32_t *>(w8 + P.L.off_keys_s); P.idx_s = reinterpret_cast<uint32_t *>(w8 + P.L.off_idx_s);
+    P.wv = reinterpret_cast<float *>(w8 + P.L.off_w);
+    P.tw = reinterpret_cast<TileW *>(w8 + P.L.off_tw); P.c1 = reinterpret_cast<TileC1 *>(w8 + P.L.off_c1);
+    P.ta = reinterpret_cast<TileA *>(w8 + P.L.off_ta); P.c2 = reinterpret_cast<TileC2 *>(w8 + P.L.off_c2);
+    P.tmp = w8 + P.L.off_tmp;
+    P.grid = (int)((n + 255) / 256);
+    const int cap = 16 * num_sms();
+    if (P.grid > cap) P.grid = cap;
+    P.tiles = (unsigned)P.L.tiles_max;
+    return B200SURV_OK;
+}
+// the radix sort ends in a buffer pair that depends only on the number of passes (32 key bits, no cohort passes): 4 passes
+// of 8 bits end where they started
+constexpr int SHARD_IN_FIRST = 1;
+}  // namespace
+
+int32_t cox_sorted_shard_keys(const float *log_hz, const float *time, const uint8_t *event, int64_t n, void *rec0_out, void *ws,
+                              size_t ws_bytes, cudaStream_t st) {
+    ShardPtrs P;
+    int32_t rc = shard_ptrs(n, ws, ws_bytes, P);
+    if (rc) return rc;
+    k_init_acc<<<1, 256, 0, st>>>(P.acc, 1);
+    k_make_keys<<<P.grid, 256, 0, st>>>(log_hz, time, event, nullptr, 1, n, P.keys_s, P.idx_s, nullptr, P.acc);
+    k_shard_rec0<<<1, 32, 0, st>>>(P.acc, n, static_cast<ShardRec0 *>(rec0_out));
+    B200_CHECK_CUDA(cudaGetLastError());
+    count_launches(3);
+    return B200SURV_OK;
+}
+
+int32_t cox_sorted_shard_sort(int64_t n, void *ws, size_t ws_bytes, cudaStream_t st) {
+    ShardPtrs P;
+    int32_t rc = shard_ptrs(n, ws, ws_bytes, P);
+    if (rc) return rc;
+    int in_first = 1;
+    rc = sortscan::radix_sort_pairs2(P.keys_s, P.idx_s, P.keys, P.vals, n, 32, nullptr, 0, P.tmp, st, &in_first);
+    if (rc) return rc;
+    if (in_first != SHARD_IN_FIRST) { set_error("cox sorted shard: unexpected sort buffer parity"); return B200SURV_UNSUPPORTED; }
+    count_launches(16);
+    return B200SURV_OK;
+}
+
+int32_t cox_sorted_shard_reduce(const float *log_hz, int64_t n, const void *all_rec0, int rank, int world, void *rec1_out,
+                                void *ws, size_t ws_bytes, cudaStream_t st) {
+    B200_REQUIRE(world >= 1 && world <= SHARD_MAX && rank >= 0 && rank < world, "rank / world");
+    ShardPtrs P;
+    int32_t rc = shard_ptrs(n, ws, ws_bytes, P);
+    if (rc) return rc;
+    k_shard_ctx0<<<1, 32, 0, st>>>(all_rec0, rank, world, P.acc, P.ctx);
+    k_weights<<<P.grid, 256, 0, st>>>(log_hz, P.keys_s, P.idx_s, nullptr, 1, n, P.acc, P.wv);
+    k_tile_w<<<P.tiles, TS_THREADS, 0, st>>>(P.keys_s, P.wv, nullptr, nullptr, 1, n, P.ctx, P.tw);
+    B200_CHECK_CUDA(cudaMemsetAsync(P.c1, 0, (size_t)P.L.tiles_max * sizeof(TileC1), st));   // the carry bits are OR-ed in
+    k_tile_scan1<<<2, SC_THREADS, 0, st>>>(P.tw, P.L.tiles_max, nullptr, 1, P.c1, static_cast<ShardRec1 *>(rec1_out));
+    B200_CHECK_CUDA(cudaGetLastError());
+    count_launches(4);
+    return B200SURV_OK;
+}
+
+int32_t cox_sorted_shard_terms(int64_t n, int ties, const void *all_rec1, int rank, int world, void *rec2_out, void *ws,
+                               size_t ws_bytes, cudaStream_t st) {
+    B200_REQUIRE(world >= 1 && world <= SHARD_MAX && rank >= 0 && rank < world, "rank / world");
+    B200_REQUIRE(ties == B200SURV_TIES_EFRON || ties == B200SURV_TIES_BRESLOW, "ties");
+    ShardPtrs P;
+    int32_t rc = shard_ptrs(n, ws, ws_bytes, P);
+    if (rc) return rc;
+    const int efron = ties == B200SURV_TIES_EFRON ? 1 : 0;
+    k_shard_ctx1<<<1, 32, 0, st>>>(all_rec1, rank, world, P.ctx);
+    k_tile_terms<<<P.tiles, TS_THREADS, 0, st>>>(P.keys_s, P.wv, nullptr, nullptr, 1, n, P.tw, P.c1, efron, P.ctx, P.ta);
+    k_tile_scan2<<<2, SC_THREADS, 0, st>>>(P.tw, P.ta, P.L.tiles_max, nullptr, nullptr, 1, n, ties, 0, P.acc, P.c2, nullptr, nullptr,
+                                           static_cast<ShardRec2 *>(rec2_out));
+    B200_CHECK_CUDA(cudaGetLastError());
+    count_launches(3);
+    return B200SURV_OK;
+}
+
+int32_t cox_sorted_shard_finish(int64_t n, int ties, int reduction, const void *all_rec2, int rank, int world, float *out_loss,
+                                void *state, size_t state_bytes, void *ws, size_t ws_bytes, cudaStream_t st) {
+    B200_REQUIRE(world >= 1 && world <= SHARD_MAX && rank >= 0 && rank < world, "rank / world");
+    B200_REQUIRE(ties == B200SURV_TIES_EFRON || ties == B200SURV_TIES_BRESLOW, "ties");
+    B200_REQUIRE(reduction >= 0 && reduction <= 2, "reduction");
+    ShardPtrs P;
+    int32_t rc = shard_ptrs(n, ws, ws_bytes, P);
+    if (rc) return rc;
+    const size_t need = sizeof(b200surv_cox_header) + (size_t)n * sizeof(float);
+    if (state_bytes < need) { set_error("cox sorted shard: state buffer %zu < %zu", state_bytes, need); return B200SURV_WORKSPACE_TOO_SMALL; }
+    b200surv_cox_header *hdr = static_cast<b200surv_cox_header *>(state);
+    float *grad_unit = reinterpret_cast<float *>(hdr + 1);
+    const int efron = ties == B200SURV_TIES_EFRON ? 1 : 0;
+    k_shard_finish<<<1, 32, 0, st>>>(all_rec2, rank, world, ties, reduction, P.acc, P.ctx, out_loss, hdr);
+    k_tile_grad<<<P.tiles, TS_THREADS, 0, st>>>(P.keys_s, P.idx_s, P.wv, nullptr, nullptr, 1, n, P.tw, P.c1, P.c2, efron, P.acc, P.ctx,
+                                                grad_unit);
+    B200_CHECK_CUDA(cudaGetLastError());
+    count_launches(2);
     return B200SURV_OK;
 }
 

@@ -6,6 +6,7 @@ this is the scale-out of the two operators it calls:
 * C-index: every rank holds the full (estimate, event, time) vectors (9 bytes/row), counts the pairs
   of its own row tiles (dealt out round-robin in sorted order) against all columns, then ONE int64 SUM all-reduce of the six counters
   (48 bytes) -- integer, so the result is bit-identical to the single-GPU result.
+* Cox loss (SORTED mode, time-range shards): `ShardedCoxSorted` below.
 * Cox loss (BINNED mode): every rank accumulates per-bin aggregates of its own rows
   (b200surv_cox_binned_partial; 32.32 fixed-point integers), ONE int64 SUM all-reduce of
   3*nbins+4 words (exact, so the loss is bit-identical for every sharding) plus a 2-float MAX
@@ -184,3 +185,117 @@ class ShardedCoxBinned:
                                        None, self.n, 1, L.COX_BINNED, self.nb, L.ptr(out_grad), L.stream_ptr(self.dev))
         L.check(rc, "b200surv_cox_bwd")
         return out_grad
+
+
+# ------------------------------------------------------------------ Cox (SORTED, time-range shards)
+class ShardedCoxSorted:
+    """SORTED Cox loss over TIME-RANGE shards (SURVEY.md 8e path "Cox (B)", the formulation BASELINE.json's north_star
+    gives for several GPUs): rank r holds ``n_local`` rows in any order whose times do not exceed the times of rank
+    r + 1 (equal times may sit on both sides of an edge).  Every rank sorts and scans its own rows; between the phases
+    the ranks all-gather ONE 128-byte record each (``b200surv_cox_sorted_shard_*``, include/b200surv.h): max log_hz and
+    edge times, then the shard's tile sequence folded into one element per scan chain, then the sums behind the loss.
+    Every rank folds the records of the other ranks into its exact carry-in on the device; no host synchronisation.
+    The first all-gather overlaps the radix sort.  The gradient stays sharded like the input.
+
+    ``rank`` / ``world`` default to the process group's; passing them explicitly (with ``gather=`` a callable that maps
+    this shard's record to the ``world`` records) lets one process drive several shards, which is how the single-GPU
+    parity test runs the multi-shard arithmetic."""
+
+    REC = 128
+
+    def __init__(self, n_local: int, device, ties: str = "efron", reduction: int = L.REDUCE_MEAN_TERMS, rank=None,
+                 world=None):
+        self.lib = L.load()
+        L.require_device(device.index)
+        r, w = _world()
+        self.rank = r if rank is None else rank
+        self.world = w if world is None else world
+        if self.world > 64:
+            raise L.B200SurvError("ShardedCoxSorted: at most 64 shards")
+        if n_local < 1:
+            raise ValueError("every shard needs at least one row")
+        assert self.lib.b200surv_cox_shard_record_bytes() == self.REC
+        self.n, self.dev = n_local, device
+        self.ties, self.red = L.TIES[ties], reduction
+        self.sb = self.lib.b200surv_cox_state_bytes(n_local, 1, L.COX_SORTED, 0)
+        self.wb = self.lib.b200surv_cox_workspace_bytes(n_local, 1, L.COX_SORTED, 0)
+        self.state = torch.empty(self.sb, dtype=torch.uint8, device=device)
+        self.ws = torch.empty(self.wb, dtype=torch.uint8, device=device)
+        self.rec = torch.zeros(3, self.REC, dtype=torch.uint8, device=device)
+        self.all = torch.zeros(3, self.world * self.REC, dtype=torch.uint8, device=device)
+        self.loss = torch.empty(1, dtype=torch.float32, device=device)
+        self.ones = torch.ones(1, dtype=torch.float32, device=device)
+
+    # -- the four phases (each returns the record the caller must all-gather before the next one)
+    def phase_keys(self, log_hz, time, event):
+        L.check(self.lib.b200surv_cox_sorted_shard_keys(L.ptr(log_hz), L.ptr(time), L.ptr(event), self.n, L.ptr(self.rec[0]),
+                                                        L.ptr(self.ws), self.wb, L.stream_ptr(self.dev)),
+                "b200surv_cox_sorted_shard_keys")
+        return self.rec[0]
+
+    def phase_sort(self):
+        L.check(self.lib.b200surv_cox_sorted_shard_sort(self.n, L.ptr(self.ws), self.wb, L.stream_ptr(self.dev)),
+                "b200surv_cox_sorted_shard_sort")
+
+    def phase_reduce(self, log_hz, all_rec0):
+        L.check(self.lib.b200surv_cox_sorted_shard_reduce(L.ptr(log_hz), self.n, L.ptr(all_rec0), self.rank, self.world,
+                                                          L.ptr(self.rec[1]), L.ptr(self.ws), self.wb, L.stream_ptr(self.dev)),
+                "b200surv_cox_sorted_shard_reduce")
+        return self.rec[1]
+
+    def phase_terms(self, all_rec1):
+        L.check(self.lib.b200surv_cox_sorted_shard_terms(self.n, self.ties, L.ptr(all_rec1), self.rank, self.world,
+                                                         L.ptr(self.rec[2]), L.ptr(self.ws), self.wb, L.stream_ptr(self.dev)),
+                "b200surv_cox_sorted_shard_terms")
+        return self.rec[2]
+
+    def phase_finish(self, all_rec2):
+        L.check(self.lib.b200surv_cox_sorted_shard_finish(self.n, self.ties, self.red, L.ptr(all_rec2), self.rank, self.world,
+                                                          L.ptr(self.loss), L.ptr(self.state), self.sb, L.ptr(self.ws), self.wb,
+                                                          L.stream_ptr(self.dev)),
+                "b200surv_cox_sorted_shard_finish")
+        return self.loss
+
+    def forward(self, log_hz, time, event, group=None):
+        """Loss of the whole cohort (the same value on every rank); the state keeps this rank's gradient."""
+        rec0 = self.phase_keys(log_hz, time, event)
+        if self.world == 1:
+            self.all[0].copy_(rec0)
+            self.phase_sort()
+        else:
+            work = dist.all_gather_into_tensor(self.all[0], rec0, group=group, async_op=True)
+            self.phase_sort()              # does not need the records: the collective runs beside it
+            work.wait()
+        rec1 = self.phase_reduce(log_hz, self.all[0])
+        if self.world == 1:
+            self.all[1].copy_(rec1)
+        else:
+            dist.all_gather_into_tensor(self.all[1], rec1, group=group)
+        rec2 = self.phase_terms(self.all[1])
+        if self.world == 1:
+            self.all[2].copy_(rec2)
+        else:
+            dist.all_gather_into_tensor(self.all[2], rec2, group=group)
+        return self.phase_finish(self.all[2])
+
+    def backward(self, out_grad, grad_out=None):
+        g = self.ones if grad_out is None else grad_out
+        rc = self.lib.b200surv_cox_bwd(L.ptr(g), L.ptr(self.state), self.sb, None, None, None, None, self.n, 1, L.COX_SORTED,
+                                       0, L.ptr(out_grad), L.stream_ptr(self.dev))
+        L.check(rc, "b200surv_cox_bwd")
+        return out_grad
+
+    def header(self) -> "L.CoxHeader":
+        """The cohort's header (synchronises): flags, loss, number of events / distinct event times ..."""
+        raw = self.state[:L.COX_HEADER_BYTES].cpu().numpy().tobytes()
+        return L.CoxHeader.from_buffer_copy(raw)
+
+    def check(self):
+        """Raise like the single-GPU operator does: ValueError for bad times, B200SurvError for shards out of time order."""
+        flags = self.header().flags
+        if flags & L.COXF_BAD_TIME:
+            raise ValueError("time must be finite and non-negative")
+        if flags & L.COXF_NOT_PARTITIONED:
+            raise L.B200SurvError("ShardedCoxSorted: the shards are not time ranges (a rank holds a time above the next "
+                                  "rank's smallest time); use time_range_partition first")
+        return flags
