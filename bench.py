@@ -234,28 +234,128 @@ def sorted_few_ties(n, dev, reps=5):
 
 
 def run_few_ties(args):
-    """--workload few_ties: the SORTED path as its own bench line (one GPU)."""
+    """--workload few_ties: the SORTED path as its own bench line.  N = 1: b200surv_cox_fwd / _bwd (mode SORTED).  N > 1 (torchrun):
+    TIME-RANGE shards (dist.ShardedCoxSorted: three 128-byte records per rank all-gathered over NCCL, carry-in folded on the
+    device); weak scaling (16,777,216 rows per rank, rank r's times in [r, r + 1) * T), a parity check of the sharded result
+    against one GPU on the same cohort, and the strong-scaling figure."""
     import torch
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
+    import torch.distributed as dist
+    from multimodal_survival_prediction_b200 import _lib as L
+    from multimodal_survival_prediction_b200 import cox as gcox
+    from multimodal_survival_prediction_b200 import dist as gdist
+    from multimodal_survival_prediction_b200 import synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     n = args.rows
-    sampler = ClockSampler(0)
-    sampler.start()
-    fwd_ms, bwd_ms, loss = sorted_few_ties(n, dev, reps=max(args.steps, 3))
-    clocks = sampler.stop()
+    steps = max(args.steps, 3)
+    sampler = ClockSampler(local_rank)
+    parity = strong = None
+    if world == 1:
+        sampler.start()
+        fwd_ms, bwd_ms, loss = sorted_few_ties(n, dev, reps=steps)
+        clocks = sampler.stop()
+        ms = fwd_ms + bwd_ms
+        launches = None
+    else:
+        def barrier():
+            dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed(op, x, tt, e, grad):
+            for _ in range(3):
+                op.forward(x, tt, e); op.backward(grad)
+            barrier()
+            l0 = L.load().b200surv_debug_launch_count()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            for _ in range(steps):
+                op.forward(x, tt, e); op.backward(grad)
+            e1.record()
+            nl = int(L.load().b200surv_debug_launch_count() - l0)
+            barrier()
+            tm = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            return float(tm.item()), nl
+
+        # weak scaling: every rank its own 16.7M rows; the global cohort's time axis is cut into one range per rank
+        lh, ev, t = synth.cohort(n, SEED + rank, few_ties=True)
+        t = t + rank * 20000.0                       # Exp(1000) never reaches 20000 at this n: rank r's times lie in its own range
+        x, e, tt = lh.to(dev), ev.to(dev), t.to(dev)
+        grad = torch.empty(n, dtype=torch.float32, device=dev)
+        op = gdist.ShardedCoxSorted(n, dev, ties="efron")
+        sampler.start()
+        ms, launches = timed(op, x, tt, e, grad)
+        clocks = sampler.stop()
+        if op.check():
+            raise SystemExit("few_ties: flags raised on synthetic data")
+        loss = float(op.loss.item())
+        fwd_ms = bwd_ms = None
+        del op, x, e, tt, grad
+        # parity + strong scaling: the SAME 16.7M-row cohort, sorted by time on the host and cut into contiguous time ranges
+        glh, gev, gt = synth.cohort(n, SEED, few_ties=True)
+        order = torch.argsort(gt, stable=True)
+        a_, b_ = gdist.shard_bounds(n, rank, world)
+        idx = order[a_:b_][torch.randperm(b_ - a_, generator=torch.Generator().manual_seed(rank))]   # a shard is an unordered row set
+        sx, se, st_ = glh[idx].to(dev), gev[idx].to(dev), gt[idx].to(dev)
+        sgrad = torch.empty(b_ - a_, dtype=torch.float32, device=dev)
+        sop = gdist.ShardedCoxSorted(b_ - a_, dev, ties="efron")
+        sms, _ = timed(sop, sx, st_, se, sgrad)
+        ref = torch.zeros(1, dtype=torch.float32, device=dev)
+        if rank == 0:
+            fx, fe, ft = glh.to(dev), gev.to(dev), gt.to(dev)
+            l1, state1 = gcox.cox_fwd_raw(fx, ft, fe, None, 1, L.TIES["efron"], L.REDUCE_MEAN_TERMS, L.COX_SORTED, 0)
+            full_grad = gcox.cox_bwd_raw(torch.ones(1, device=dev), state1, fx, ft, fe, None, 1, L.COX_SORTED, 0)
+            ref[0] = l1[0]
+        dist.broadcast(ref, 0)
+        loss_rel = abs(float(sop.loss.item()) - float(ref.item())) / max(abs(float(ref.item())), 1e-30)
+        didx = idx.to(dev)
+        if rank == 0:
+            gmax = float(full_grad.abs().max())
+            err = float((sgrad - full_grad[didx]).abs().max())
+            for r in range(1, world):
+                ra, rb = gdist.shard_bounds(n, r, world)
+                gi = torch.empty(rb - ra, dtype=torch.int64, device=dev); gg = torch.empty(rb - ra, dtype=torch.float32, device=dev)
+                dist.recv(gi, src=r); dist.recv(gg, src=r)
+                err = max(err, float((gg - full_grad[gi]).abs().max()))
+            grad_rel = err / gmax
+        else:
+            dist.send(didx, dst=0); dist.send(sgrad, dst=0)
+            grad_rel = 0.0
+        ok = torch.tensor([int(loss_rel <= 2e-6 and grad_rel <= 2e-6)], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        parity = {"ok": bool(ok.item()), "loss_rel_diff": loss_rel, "grad_max_abs_diff_over_max": grad_rel, "tolerance": 2e-6,
+                  "rows_total": n, "exchange": "3 x all_gather of one 128-byte record per rank (NCCL)",
+                  "what": "the same 16,777,216-row few-ties cohort cut into time-range shards over the ranks vs one GPU (rank 0, mode sorted); "
+                          "fp64 sums in another order, so a tolerance and not bit equality"}
+        strong = {"rows_total": n, "rows_per_gpu": b_ - a_, "ms_per_step": sms, "value": n / (sms * 1e-3), "unit": "patients/s",
+                  "scaling": "strong"}
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "n_gpus": world, "parity_check": parity, "error": "sharded result differs from one GPU"}))
+            dist.destroy_process_group()
+            raise SystemExit(3)
     peak, peak_src = load_peaks()
-    ms = fwd_ms + bwd_ms
-    achieved = ALGO_BYTES_PER_ROW * n / (ms * 1e-3) / 1e9
-    print(json.dumps({
-        "metric": METRIC, "value": n / (ms * 1e-3), "unit": "patients/s", "n_gpus": 1, "steps": max(args.steps, 3), "warmup": 3,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 sums over f32 inputs",
-        "data": "synthetic",
-        "config": {"workload": "cox_nll_fwd_bwd_efron_16M_few_ties", "rows_per_gpu": n, "ties": "efron", "time": "Exp(1000), continuous",
-                   "event_rate": 0.30, "mode": "sorted", "l2": "inputs and scratch (68 B/row) far larger than L2"},
-        "loss": loss,
-        "roofline": {"bound": "hbm", "scope": "step = sort + scans + gradient scatter, 22 algorithmic B/row", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "traffic": None},
-        "clocks": clocks}))
+    achieved = ALGO_BYTES_PER_ROW * n / (ms * 1e-3) / 1e9          # per GPU
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": world * n / (ms * 1e-3), "unit": "patients/s", "n_gpus": world, "steps": steps, "warmup": 3,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 sums over f32 inputs",
+            "data": "synthetic",
+            "config": {"workload": "cox_nll_fwd_bwd_efron_16M_few_ties", "rows_per_gpu": n, "ties": "efron", "time": "Exp(1000), continuous",
+                       "event_rate": 0.30, "mode": "sorted", "l2": "inputs and scratch (68 B/row) far larger than L2",
+                       "parallelism": "single GPU" if world == 1 else f"{world} time-range shards, boundary records all-gathered (NCCL)"},
+            "loss": loss,
+            "roofline": {"bound": "hbm", "scope": "step = sort + scans + gradient scatter, 22 algorithmic B/row, per GPU", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+                         "traffic": None},
+            "gpu_launches": launches, "parity_check": parity, "strong_scaling": strong, "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_b200(args):

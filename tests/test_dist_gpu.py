@@ -89,3 +89,67 @@ def test_sharded_cox_two_gpus_bit_identical():
         for key, (loss, loss_single, grad_equal) in res.items():
             assert loss == loss_single, (rank, key, loss, loss_single)   # bit-identical fp32 loss
             assert grad_equal, (rank, key)
+
+
+def _worker_sorted(rank, world, port, n, out_q):
+    import numpy as np
+    import torch.distributed as dist
+    import multimodal_survival_prediction_b200 as pkg
+    from multimodal_survival_prediction_b200 import dist as bd
+    from multimodal_survival_prediction_b200 import synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    res = {}
+    try:
+        for it, few in enumerate((True, False)):     # continuous times; integer days (tie groups across the shard edge)
+            lh, ev, t = synth.cohort(n, 200 + it, few_ties=few)
+            order = torch.argsort(t, stable=True)
+            a, b = bd.shard_bounds(n, rank, world)
+            idx = order[a:b][torch.randperm(b - a, generator=torch.Generator().manual_seed(rank))]
+            op = bd.ShardedCoxSorted(b - a, dev, ties="efron")
+            x, tt, e = lh[idx].to(dev), t[idx].to(dev), ev[idx].to(dev)
+            grad = torch.empty(b - a, dtype=torch.float32, device=dev)
+            for _ in range(2):                       # twice: the workspace and the records are reused
+                loss = op.forward(x, tt, e)
+                op.backward(grad)
+            assert op.check() == 0
+            xf = lh.to(dev).requires_grad_(True)
+            l1 = pkg.neg_partial_log_likelihood(xf, ev.to(dev), t.to(dev), "efron", mode="sorted")
+            l1.backward()
+            torch.cuda.synchronize()
+            gref = xf.grad[idx.to(dev)]
+            res[it] = (float(loss), float(l1), float((grad - gref).abs().max()), float(xf.grad.abs().max()))
+        out_q.put((rank, res, None))
+    except Exception as ex:  # noqa: BLE001 -- reported to the parent
+        out_q.put((rank, res, repr(ex)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_cox_sorted_two_gpus_time_range_shards():
+    """north_star's multi-GPU Cox: time-range shards, NCCL all-gather of the per-shard boundary records, exact carry-in.
+    The loss (same on both ranks) and every rank's gradient rows equal the single-GPU SORTED result to 2e-6 (fp64 sums
+    in another order)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    n, world = (1 << 19) + 11, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sorted, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, res, err in got:
+        assert err is None, f"rank {rank}: {err}"
+        assert len(res) == 2
+        for key, (loss, loss_single, gerr, gmax) in res.items():
+            assert abs(loss - loss_single) <= 2e-6 * abs(loss_single), (rank, key, loss, loss_single)
+            assert gerr <= 2e-6 * gmax, (rank, key, gerr, gmax)
+    assert got[0][1][0][0] == got[1][1][0][0]        # both ranks hold the same loss bits
