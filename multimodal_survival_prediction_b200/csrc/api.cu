@@ -3,6 +3,8 @@
 
 #include <atomic>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200surv {
@@ -17,6 +19,10 @@ void set_error(const char *fmt, ...) {
 }
 
 static std::atomic<unsigned long long> g_launches{0};
+bool pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("B200SURV_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 void count_launches(int k) { g_launches.fetch_add((unsigned long long)k, std::memory_order_relaxed); }
 unsigned long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 

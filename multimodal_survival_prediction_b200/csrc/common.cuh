@@ -54,6 +54,25 @@ struct PerDeviceOnce {
 #ifdef __CUDACC__
 constexpr unsigned FULL = 0xffffffffu;
 
+// ---- programmatic dependent launch for chains of short kernels (head, CT encoder): a chained kernel lets its successor
+// start its own set-up at once (pdl_trigger) and waits for its predecessor's results before it touches global memory
+// (pdl_wait: returns when the preceding grid has completed and its writes are visible).  Launched without the attribute
+// (B200SURV_PDL=0, or behind a kernel of another library) both instructions are no-ops and the edge is a plain one.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+bool pdl_enabled();   // api.cu: B200SURV_PDL != "0"
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args &&>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);

@@ -50,6 +50,7 @@ template <typename IDX>
 __global__ void __launch_bounds__(256)
 k_conv_first_fwd(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, int64_t B,
                  Grid3 g, int Cout, float *__restrict__ h) {
+    pdl_prologue();
     extern __shared__ float sw[];           // [27][Cout] then bias[Cout]
     for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) { const int c = i % Cout, t = i / Cout; sw[i] = w[c * 27 + t]; }
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
@@ -99,6 +100,7 @@ constexpr int WG_THREADS = 1024;
 __global__ void __launch_bounds__(WG_THREADS, 1)
 k_conv_first_wgrad(const float *__restrict__ x, const bf16 *__restrict__ dx, int64_t B, Grid3 g, int Cout,
                    float *__restrict__ partial) {
+    pdl_prologue();
     __shared__ float red[WG_THREADS * 9];
     const int c = threadIdx.x % Cout, lane_r = threadIdx.x / Cout, lanes = WG_THREADS / Cout;
     const int64_t vox = (int64_t)g.Do * g.Ho * g.Wo, R = B * vox;
@@ -160,6 +162,7 @@ k_conv_first_wgrad(const float *__restrict__ x, const bf16 *__restrict__ dx, int
 __global__ void __launch_bounds__(WG_THREADS, 1)
 k_conv_first_wgrad32(const float *__restrict__ x, const bf16 *__restrict__ dx, int64_t B, Grid3 g,
                      float *__restrict__ partial) {
+    pdl_prologue();
     __shared__ float red[WG_THREADS * 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = WG_THREADS / 32;
     const int tap = lane < 27 ? lane : 26;
@@ -218,6 +221,7 @@ k_conv_first_wgrad32(const float *__restrict__ x, const bf16 *__restrict__ dx, i
 // out[i] = sum over the slices, in a fixed order: 32 elements x 8 slice lanes per CTA
 __global__ void __launch_bounds__(256)
 k_sum_slices(const float *__restrict__ part, int slices, int64_t elems, float *__restrict__ out) {
+    pdl_prologue();
     __shared__ double sh[8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * 32 + tx;
@@ -240,6 +244,7 @@ k_sum_slices(const float *__restrict__ part, int slices, int64_t elems, float *_
 template <int CV>
 __global__ void __launch_bounds__(256)
 k_im2col(const bf16 *__restrict__ a, int64_t Bc, Grid3 g, int C, bf16 *__restrict__ col) {
+    pdl_prologue();
     const int cv = CV ? CV : C / 8, nvec = 27 * cv;
     const int lane = threadIdx.x & 31;
     const int64_t vox = (int64_t)g.Do * g.Ho * g.Wo, rows = Bc * vox, vin = (int64_t)g.D * g.H * g.W;
@@ -272,6 +277,7 @@ __device__ __forceinline__ void add_bf16x8(float *acc, uint4 v) {
 template <typename IDX>
 __global__ void __launch_bounds__(256)
 k_col2im(const bf16 *__restrict__ dcol, int64_t Bc, Grid3 g, int C, float *__restrict__ da) {
+    pdl_prologue();
     const IDX cv = (IDX)(C / 8);
     const IDX vin = (IDX)g.D * g.H * g.W, total = (IDX)Bc * vin * cv;
     const int64_t vox = (int64_t)g.Do * g.Ho * g.Wo;
@@ -308,6 +314,7 @@ k_col2im(const bf16 *__restrict__ dcol, int64_t Bc, Grid3 g, int C, float *__res
 
 // ---------------------------------------------------------------- weights: torch (Cout,Cin,3,3,3) <-> tap-major
 __global__ void k_weight_pack(const float *__restrict__ w, int Cout, int Cin, bf16 *__restrict__ wr) {
+    pdl_prologue();
     const int total = Cout * Cin * 27;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int c = i % Cin, tap = (i / Cin) % 27, o = i / (27 * Cin);       // i indexes wr
@@ -316,6 +323,7 @@ __global__ void k_weight_pack(const float *__restrict__ w, int Cout, int Cin, bf
 }
 __global__ void k_weight_unpack(const float *__restrict__ dwr, int slices, int Cout, int Cin, int accumulate,
                                 float *__restrict__ dw) {
+    pdl_prologue();
     const int total = Cout * Cin * 27;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int tap = i % 27, c = (i / 27) % Cin, o = i / (27 * Cin);        // i indexes dw
@@ -333,6 +341,7 @@ __global__ void __launch_bounds__(256)
 k_bn_colsums(const float *__restrict__ x, const float *__restrict__ dA, const float *__restrict__ mu,
              const float *__restrict__ rstd, const float *__restrict__ gamma, const float *__restrict__ beta, int64_t R,
              int C, double *__restrict__ partial) {
+    pdl_prologue();
     __shared__ double sh[256][8];
     const int t = threadIdx.x, c0 = (4 * t) % C;
     const int64_t nvec = R * C / 4;
@@ -389,6 +398,7 @@ __global__ void __launch_bounds__(256)
 k_bn_finalize(const double *__restrict__ partial, int nparts, int64_t R, int C, int training,
               float *__restrict__ run_mean, float *__restrict__ run_var, float *__restrict__ mu,
               float *__restrict__ rstd) {
+    pdl_prologue();
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     if (!training) {
@@ -415,6 +425,7 @@ __global__ void __launch_bounds__(256)
 k_bn_bwd_finalize(const double *__restrict__ partial, int nparts, int C, int training, const float *__restrict__ gamma,
                   const float *__restrict__ rstd, float *__restrict__ sums, float *__restrict__ dgamma,
                   float *__restrict__ dbeta, float *__restrict__ dbias) {
+    pdl_prologue();
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     double s, sx;
@@ -435,6 +446,7 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d)
 __global__ void __launch_bounds__(256)
 k_bn_relu(const float *__restrict__ x, const float *__restrict__ mu, const float *__restrict__ rstd,
           const float *__restrict__ gamma, const float *__restrict__ beta, int64_t R, int C, bf16 *__restrict__ y) {
+    pdl_prologue();
     const int64_t nvec = R * C / 4;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
         const int c0 = (int)((4 * v) & (C - 1));      // C is a power of two
@@ -453,6 +465,7 @@ __global__ void __launch_bounds__(1024)
 k_bn_relu_pool(const float *__restrict__ x, const float *__restrict__ mu, const float *__restrict__ rstd,
                const float *__restrict__ gamma, const float *__restrict__ beta, int64_t B, int V, int C,
                float *__restrict__ feat) {
+    pdl_prologue();
     __shared__ float sh[1024];
     const int c = threadIdx.x % C, lane_v = threadIdx.x / C, lanes = 1024 / C;
     const float m = mu[c], sc = rstd[c] * gamma[c], be = beta[c];
@@ -469,6 +482,7 @@ k_bn_relu_pool(const float *__restrict__ x, const float *__restrict__ mu, const 
     }
 }
 __global__ void k_pool_bwd(const float *__restrict__ dfeat, int64_t B, int V, int C, float *__restrict__ dA) {
+    pdl_prologue();
     const int64_t total = B * V * C;
     const float inv = 1.f / (float)V;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -482,6 +496,7 @@ __global__ void __launch_bounds__(256)
 k_bn_dx(const float *__restrict__ x, const float *__restrict__ dA, const float *__restrict__ mu,
         const float *__restrict__ rstd, const float *__restrict__ gamma, const float *__restrict__ beta,
         const float *__restrict__ sums, int64_t R, int C, int training, bf16 *__restrict__ dx) {
+    pdl_prologue();
     const int64_t nvec = R * C / 4;
     const float invR = 1.f / (float)R;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
@@ -527,11 +542,9 @@ int32_t b200surv_ct_conv_first_fwd(const float *x, const float *w, const float *
     const Grid3 g = make_grid(D, H, W);
     const int64_t total = B * (int64_t)g.Do * g.Ho * g.Wo * (Cout / 8);
     if (total < ((int64_t)1 << 30))
-        k_conv_first_fwd<uint32_t><<<blocks_for(total, 256, 16), 256, (size_t)28 * Cout * sizeof(float), as_stream(stream)>>>(
-            x, w, bias, B, g, Cout, h);
+        launch_chain(k_conv_first_fwd<uint32_t>, blocks_for(total, 256, 16), 256, (size_t)28 * Cout * sizeof(float), as_stream(stream), x, w, bias, B, g, Cout, h);
     else
-        k_conv_first_fwd<int64_t><<<blocks_for(total, 256, 16), 256, (size_t)28 * Cout * sizeof(float), as_stream(stream)>>>(
-            x, w, bias, B, g, Cout, h);
+        launch_chain(k_conv_first_fwd<int64_t>, blocks_for(total, 256, 16), 256, (size_t)28 * Cout * sizeof(float), as_stream(stream), x, w, bias, B, g, Cout, h);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -560,11 +573,11 @@ int32_t b200surv_ct_conv_first_wgrad(const float *x, const void *dx_bf16, int64_
     if (Cout == 32) {
         ctas = num_sms();
         if ((int64_t)ctas * (WG_THREADS / 32) > R) ctas = (int)((R + WG_THREADS / 32 - 1) / (WG_THREADS / 32));
-        k_conv_first_wgrad32<<<ctas, WG_THREADS, 0, st>>>(x, static_cast<const bf16 *>(dx_bf16), B, g, partial);
+        launch_chain(k_conv_first_wgrad32, ctas, WG_THREADS, 0, st, x, static_cast<const bf16 *>(dx_bf16), B, g, partial);
     } else {
-        k_conv_first_wgrad<<<ctas, WG_THREADS, 0, st>>>(x, static_cast<const bf16 *>(dx_bf16), B, g, Cout, partial);
+        launch_chain(k_conv_first_wgrad, ctas, WG_THREADS, 0, st, x, static_cast<const bf16 *>(dx_bf16), B, g, Cout, partial);
     }
-    k_sum_slices<<<(Cout * 27 + 31) / 32, 256, 0, st>>>(partial, ctas, (int64_t)Cout * 27, dw);
+    launch_chain(k_sum_slices, (Cout * 27 + 31) / 32, 256, 0, st, partial, ctas, (int64_t)Cout * 27, dw);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -578,9 +591,9 @@ int32_t b200surv_ct_im2col(const void *a_bf16, int64_t Bc, int32_t D, int32_t H,
     const unsigned grid = blocks_for(rows, 8 * 4, 16);
     const bf16 *ap = static_cast<const bf16 *>(a_bf16);
     bf16 *cp = static_cast<bf16 *>(col_bf16);
-    if (C == 32) k_im2col<4><<<grid, 256, 0, as_stream(stream)>>>(ap, Bc, g, C, cp);
-    else if (C == 64) k_im2col<8><<<grid, 256, 0, as_stream(stream)>>>(ap, Bc, g, C, cp);
-    else k_im2col<0><<<grid, 256, 0, as_stream(stream)>>>(ap, Bc, g, C, cp);
+    if (C == 32) launch_chain(k_im2col<4>, grid, 256, 0, as_stream(stream), ap, Bc, g, C, cp);
+    else if (C == 64) launch_chain(k_im2col<8>, grid, 256, 0, as_stream(stream), ap, Bc, g, C, cp);
+    else launch_chain(k_im2col<0>, grid, 256, 0, as_stream(stream), ap, Bc, g, C, cp);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -592,16 +605,16 @@ int32_t b200surv_ct_col2im(const void *dcol_bf16, int64_t Bc, int32_t D, int32_t
     const Grid3 g = make_grid(D, H, W);
     const int64_t total = Bc * (int64_t)D * H * W * (C / 8);
     if (total < ((int64_t)1 << 30))
-        k_col2im<uint32_t><<<blocks_for(total, 256 * 2, 16), 256, 0, as_stream(stream)>>>(static_cast<const bf16 *>(dcol_bf16), Bc, g, C, da);
+        launch_chain(k_col2im<uint32_t>, blocks_for(total, 256 * 2, 16), 256, 0, as_stream(stream), static_cast<const bf16 *>(dcol_bf16), Bc, g, C, da);
     else
-        k_col2im<int64_t><<<blocks_for(total, 256 * 2, 16), 256, 0, as_stream(stream)>>>(static_cast<const bf16 *>(dcol_bf16), Bc, g, C, da);
+        launch_chain(k_col2im<int64_t>, blocks_for(total, 256 * 2, 16), 256, 0, as_stream(stream), static_cast<const bf16 *>(dcol_bf16), Bc, g, C, da);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
 
 int32_t b200surv_ct_weight_pack(const float *w, int32_t Cout, int32_t Cin, void *wr_bf16, b200surv_stream_t stream) {
     B200_REQUIRE(w && wr_bf16 && Cout >= 1 && Cin >= 1, "arguments");
-    k_weight_pack<<<(Cout * Cin * 27 + 255) / 256, 256, 0, as_stream(stream)>>>(w, Cout, Cin, static_cast<bf16 *>(wr_bf16));
+    launch_chain(k_weight_pack, (Cout * Cin * 27 + 255) / 256, 256, 0, as_stream(stream), w, Cout, Cin, static_cast<bf16 *>(wr_bf16));
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -609,7 +622,7 @@ int32_t b200surv_ct_weight_pack(const float *w, int32_t Cout, int32_t Cin, void 
 int32_t b200surv_ct_weight_unpack(const float *dwr_slices, int32_t slices, int32_t Cout, int32_t Cin, int32_t accumulate,
                                   float *dw, b200surv_stream_t stream) {
     B200_REQUIRE(dwr_slices && dw && slices >= 1 && Cout >= 1 && Cin >= 1, "arguments");
-    k_weight_unpack<<<(Cout * Cin * 27 + 255) / 256, 256, 0, as_stream(stream)>>>(dwr_slices, slices, Cout, Cin, accumulate, dw);
+    launch_chain(k_weight_unpack, (Cout * Cin * 27 + 255) / 256, 256, 0, as_stream(stream), dwr_slices, slices, Cout, Cin, accumulate, dw);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -624,8 +637,8 @@ int32_t b200surv_ct_bn_stats(const float *x, int64_t R, int32_t C, int32_t train
     double *partial = static_cast<double *>(workspace);
     const int parts = bn_parts(R, C);
     if (training)
-        k_bn_colsums<0><<<parts, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, nullptr, R, C, partial);
-    k_bn_finalize<<<(C + 7) / 8, 256, 0, st>>>(partial, parts, R, C, training, run_mean, run_var, mu, rstd);
+        launch_chain(k_bn_colsums<0>, parts, 256, 0, st, x, nullptr, nullptr, nullptr, nullptr, nullptr, R, C, partial);
+    launch_chain(k_bn_finalize, (C + 7) / 8, 256, 0, st, partial, parts, R, C, training, run_mean, run_var, mu, rstd);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -634,7 +647,7 @@ int32_t b200surv_ct_bn_relu(const float *x, const float *mu, const float *rstd, 
                             int64_t R, int32_t C, void *y_bf16, b200surv_stream_t stream) {
     B200_REQUIRE(x && mu && rstd && gamma && beta && y_bf16, "null pointer");
     B200_REQUIRE(R >= 1 && pow2_channels(C), "C must be a power of two in [8, 256]");
-    k_bn_relu<<<blocks_for(R * C / 4, 256 * 4, 16), 256, 0, as_stream(stream)>>>(x, mu, rstd, gamma, beta, R, C,
+    launch_chain(k_bn_relu, blocks_for(R * C / 4, 256 * 4, 16), 256, 0, as_stream(stream), x, mu, rstd, gamma, beta, R, C,
                                                                              static_cast<bf16 *>(y_bf16));
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
@@ -645,14 +658,14 @@ int32_t b200surv_ct_bn_relu_pool(const float *x, const float *mu, const float *r
                                  b200surv_stream_t stream) {
     B200_REQUIRE(x && mu && rstd && gamma && beta && feat, "null pointer");
     B200_REQUIRE(B >= 1 && V >= 1 && pow2_channels(C), "shape (C a power of two in [8, 256])");
-    k_bn_relu_pool<<<blocks_for(B, 1, 2), 1024, 0, as_stream(stream)>>>(x, mu, rstd, gamma, beta, B, V, C, feat);
+    launch_chain(k_bn_relu_pool, blocks_for(B, 1, 2), 1024, 0, as_stream(stream), x, mu, rstd, gamma, beta, B, V, C, feat);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
 
 int32_t b200surv_ct_pool_bwd(const float *dfeat, int64_t B, int32_t V, int32_t C, float *dA, b200surv_stream_t stream) {
     B200_REQUIRE(dfeat && dA && B >= 1 && V >= 1 && C >= 1, "arguments");
-    k_pool_bwd<<<blocks_for(B * V * C, 256 * 4, 16), 256, 0, as_stream(stream)>>>(dfeat, B, V, C, dA);
+    launch_chain(k_pool_bwd, blocks_for(B * V * C, 256 * 4, 16), 256, 0, as_stream(stream), dfeat, B, V, C, dA);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -670,9 +683,9 @@ int32_t b200surv_ct_bn_bwd(const float *x, const float *dA, const float *mu, con
     // the 2 C fp32 column sums live behind the partials (b200surv_ct_workspace_bytes() reserves them)
     float *sums = reinterpret_cast<float *>(partial + (size_t)parts * 2 * C);
     B200_REQUIRE((size_t)parts * 2 * C * sizeof(double) + 2 * C * sizeof(float) <= workspace_bytes, "workspace layout");
-    k_bn_colsums<1><<<parts, 256, 0, st>>>(x, dA, mu, rstd, gamma, beta, R, C, partial);
-    k_bn_bwd_finalize<<<(C + 7) / 8, 256, 0, st>>>(partial, parts, C, training, gamma, rstd, sums, dgamma, dbeta, dbias);
-    k_bn_dx<<<blocks_for(R * C / 4, 256 * 4, 16), 256, 0, st>>>(x, dA, mu, rstd, gamma, beta, sums, R, C, training,
+    launch_chain(k_bn_colsums<1>, parts, 256, 0, st, x, dA, mu, rstd, gamma, beta, R, C, partial);
+    launch_chain(k_bn_bwd_finalize, (C + 7) / 8, 256, 0, st, partial, parts, C, training, gamma, rstd, sums, dgamma, dbeta, dbias);
+    launch_chain(k_bn_dx, blocks_for(R * C / 4, 256 * 4, 16), 256, 0, st, x, dA, mu, rstd, gamma, beta, sums, R, C, training,
                                                                static_cast<bf16 *>(dx_bf16));
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;

@@ -283,6 +283,7 @@ template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
              Epilogue ep) {
+    pdl_trigger();   // the next kernel of the chain may set itself up while this one runs
     constexpr int STAGES = TileCfg<BN>::STAGES, TILE_B = TileCfg<BN>::TILE_B, TMEM_COLS = TileCfg<BN>::TMEM_COLS;
     extern __shared__ unsigned char smem_raw[];
     // 128B swizzle needs 1024-byte aligned tiles
@@ -314,6 +315,7 @@ gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();      // barriers, TMEM and tensor maps are set up: now the previous kernel's results are needed
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -438,6 +440,7 @@ template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
               Epilogue ep) {
+    pdl_trigger();   // the next kernel of the chain may set itself up while this one runs
     constexpr int STAGES = STAGES2, BN = 256;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -472,6 +475,7 @@ gemm_bf16_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();      // barriers, TMEM and tensor maps are set up: now the previous kernel's results are needed
 
     if (warp == 0) {
         // ===== TMA producer (one per CTA): own A rows, own half of the B columns; completion on the leader's barrier =====
@@ -587,7 +591,7 @@ int32_t launch(const CUtensorMap &ma, const CUtensorMap &mb, int M, int N, int K
         attr_once.mark();
     }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
-    gemm_bf16_tc<A_MN, B_MN, BN><<<grid, GEMM_THREADS, TileCfg<BN>::SMEM, st>>>(ma, mb, M, N, K, ep);
+    launch_chain(gemm_bf16_tc<A_MN, B_MN, BN>, grid, GEMM_THREADS, TileCfg<BN>::SMEM, st, ma, mb, M, N, K, ep);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -628,7 +632,7 @@ int32_t launch_pair(const CUtensorMap &ma, const CUtensorMap &mb, int M, int N, 
         attr_once.mark();
     }
     dim3 grid(2 * ((M + 255) / 256), (N + 255) / 256, splits);
-    gemm_bf16_tc2<A_MN, B_MN><<<grid, GEMM_THREADS, GEMM2_SMEM, st>>>(ma, mb, M, N, K, ep);
+    launch_chain(gemm_bf16_tc2<A_MN, B_MN>, grid, GEMM_THREADS, GEMM2_SMEM, st, ma, mb, M, N, K, ep);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }

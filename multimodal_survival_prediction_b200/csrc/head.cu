@@ -69,6 +69,7 @@ __device__ __forceinline__ int64_t row_of(int64_t i, int N) {
 // dst[r][0..Cp) = bf16(src[r][0..C)), zero padded; grid (column chunks, row groups): no per-element division
 __global__ void k_cast_pad(const float *__restrict__ src, int64_t lds, bf16 *__restrict__ dst, int64_t ldd, int64_t R,
                            int C, int Cp) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= Cp) return;
     const int64_t step = gridDim.y;
@@ -87,7 +88,7 @@ static void cast_pad(const float *src, int64_t lds, bf16 *dst, int64_t ldd, int6
     int64_t gy = R < 65535 ? R : 65535;
     const int64_t cap = (int64_t)32 * num_sms() / gx + 1;  // ~32 CTAs per SM are plenty
     if (gy > cap) gy = cap;
-    k_cast_pad<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(src, lds, dst, ldd, R, C, Cp);
+    launch_chain(k_cast_pad, dim3(gx, (unsigned)gy), 256, 0, st, src, lds, dst, ldd, R, C, Cp);
 }
 
 // ---------------------------------------------------------------- column reductions (deterministic)
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256)
 k_colreduce(const float *__restrict__ a, int64_t lda, const float *__restrict__ x, int64_t ldx,
             const float *__restrict__ mu, const float *__restrict__ rstd, const float *__restrict__ s, int64_t s_stride,
             int64_t B, int N, double *__restrict__ partial) {
+    pdl_prologue();
     __shared__ double sh0[8][32], sh1[8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + tx;
@@ -148,6 +150,7 @@ __device__ __forceinline__ void slice_sums(const double *__restrict__ partial, i
 inline unsigned colfinal_grid(int N) { return (unsigned)((N + 7) / 8); }
 __global__ void __launch_bounds__(256)
 k_colreduce_final(const double *__restrict__ partial, int nslices, int N, float scale, float *out0, float *out1) {
+    pdl_prologue();
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
     double v0, v1;
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(256)
 k_bn_finalize(const double *__restrict__ partial, int nslices, int64_t B, int N, int training,
               float *__restrict__ run_mean, float *__restrict__ run_var, float *__restrict__ mu,
               float *__restrict__ rstd) {
+    pdl_prologue();
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
     if (training) {
@@ -192,6 +196,7 @@ __global__ void k_bn_apply(const float *__restrict__ x, int64_t ldx, const float
                            const float *__restrict__ beta, int64_t B, int N, uint32_t thresh, float inv_keep,
                            uint64_t seed, const uint64_t *__restrict__ seed_dev, uint32_t layer, bf16 *__restrict__ y,
                            int64_t ldy, uint8_t *__restrict__ keep_out) {
+    pdl_prologue();
     if (seed_dev != nullptr) seed = *seed_dev;  // (CUDA-graph replays: the seed lives in device memory)
     const int n4 = N >> 2;
     const int64_t total = B * n4;
@@ -227,6 +232,7 @@ __global__ void k_bn_apply(const float *__restrict__ x, int64_t ldx, const float
 __global__ void k_gate_prep(const float *__restrict__ ct, const float *__restrict__ R, const float *__restrict__ clin,
                             const float *__restrict__ mask, const float *__restrict__ wc, const float *__restrict__ bc,
                             int64_t B, float *__restrict__ feat, bf16 *__restrict__ z, bf16 *__restrict__ fused) {
+    pdl_prologue();
     const int64_t total = B * GZP;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = row_of(i, GZP);
@@ -252,6 +258,7 @@ __global__ void __launch_bounds__(256)
 k_gate_apply(const float *__restrict__ zh, const float *__restrict__ wg2, const float *__restrict__ bg2,
              const float *__restrict__ feat, int64_t B, float *__restrict__ gate, float *__restrict__ gate_out,
              bf16 *__restrict__ fused) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     for (int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < B; b += (int64_t)gridDim.x * 8) {
         const float z0 = zh[b * GH + lane], z1 = zh[b * GH + 32 + lane];
@@ -277,6 +284,7 @@ k_gate_apply(const float *__restrict__ zh, const float *__restrict__ wg2, const 
 __global__ void __launch_bounds__(256)
 k_cox_head(const float *__restrict__ f2, const float *__restrict__ w, const float *__restrict__ bias, int64_t B,
            float *__restrict__ hazard) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     for (int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < B; b += (int64_t)gridDim.x * 8) {
         float s = 0.f;
@@ -303,6 +311,7 @@ k_bn_colstats(const float *__restrict__ a, const float *__restrict__ s1, const f
               const float *__restrict__ gamma, const float *__restrict__ beta, int64_t B, int N, uint32_t thresh, float inv_keep,
               uint64_t seed, const uint64_t *__restrict__ seed_dev, uint32_t layer, int want_stats, float *__restrict__ h,
               double *__restrict__ partial) {
+    pdl_prologue();
     __shared__ double sh[8][2][BC];
     if (MODE == 1 && seed_dev != nullptr) seed = *seed_dev;
     const int tq = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -383,6 +392,7 @@ k_bn_apply2(const float *__restrict__ x, const double *__restrict__ partial, int
             float *__restrict__ run_var, float *__restrict__ mu_out, float *__restrict__ rstd_out, uint32_t thresh,
             float inv_keep, uint64_t seed, const uint64_t *__restrict__ seed_dev, uint32_t layer, bf16 *__restrict__ y,
             uint8_t *__restrict__ keep_out) {
+    pdl_prologue();
     __shared__ double sums[2][BC];
     __shared__ float s_mu[BC], s_rs[BC];
     if (seed_dev != nullptr) seed = *seed_dev;  // (CUDA-graph replays: the seed lives in device memory)
@@ -447,6 +457,7 @@ k_bn_bwd_dx3(const float *__restrict__ dA, const float *__restrict__ x, const do
              const float *__restrict__ beta, int64_t B, int N, int training, uint32_t thresh, float inv_keep, uint64_t seed,
              const uint64_t *__restrict__ seed_dev, uint32_t layer, float *__restrict__ dbeta, float *__restrict__ dgamma,
              float *__restrict__ dbias, bf16 *__restrict__ dx) {
+    pdl_prologue();
     __shared__ double sums[2][BC];
     if (seed_dev != nullptr) seed = *seed_dev;
     const int cbase = blockIdx.x * BC;
@@ -494,6 +505,7 @@ constexpr int CAST_ROWS = 8;
 struct CastSegs { CastSeg s[5]; int b0[6]; int n; };
 __global__ void __launch_bounds__(256)
 k_cast_multi(const CastSegs segs, uint64_t *seed_advance) {
+    pdl_prologue();
     if (seed_advance != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *seed_advance += 1;  // (see B200SURV_HEAD_SEED_ADVANCE)
     int k = 0;
 #pragma unroll
@@ -516,6 +528,7 @@ k_cast_multi(const CastSegs segs, uint64_t *seed_advance) {
 __global__ void __launch_bounds__(256)
 k_bn_stats_combine(const float *__restrict__ s0, const float *__restrict__ s1, const float *__restrict__ bias, int64_t B, int N,
                    int want_stats, float *__restrict__ h, double *__restrict__ partial) {
+    pdl_prologue();
     __shared__ double sh0[8][32], sh1[8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + tx, slice = blockIdx.y, nslices = gridDim.y;
@@ -559,6 +572,7 @@ k_bn_bwd_stats(const float *__restrict__ dA, int64_t ldd, const float *__restric
                const float *__restrict__ rstd, const float *__restrict__ gamma, const float *__restrict__ beta, int64_t B, int N,
                uint32_t thresh, float inv_keep, uint64_t seed, const uint64_t *__restrict__ seed_dev, uint32_t layer,
                double *__restrict__ partial) {
+    pdl_prologue();
     __shared__ double sh0[8][32], sh1[8][32];
     if (seed_dev != nullptr) seed = *seed_dev;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -602,6 +616,7 @@ __global__ void __launch_bounds__(256)
 k_bn_bwd_final(const double *__restrict__ partial, int nslices, int N, const float *__restrict__ gamma,
                const float *__restrict__ rstd, int training, float *__restrict__ dbeta, float *__restrict__ dgamma,
                float *__restrict__ dbias) {
+    pdl_prologue();
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
     double v0, v1;
@@ -618,6 +633,7 @@ __global__ void k_bn_bwd_dx2(const float *__restrict__ dA, int64_t ldd, const fl
                              const float *__restrict__ beta, const float *__restrict__ sdy, const float *__restrict__ sdyx,
                              int64_t B, int N, int training, uint32_t thresh, float inv_keep, uint64_t seed,
                              const uint64_t *__restrict__ seed_dev, uint32_t layer, bf16 *__restrict__ dx, int64_t lddx) {
+    pdl_prologue();
     if (seed_dev != nullptr) seed = *seed_dev;
     const int n4 = N >> 2;
     const int64_t total = B * n4;
@@ -658,6 +674,7 @@ __global__ void k_bn_bwd_dx2(const float *__restrict__ dA, int64_t ldd, const fl
 __global__ void __launch_bounds__(F2N)
 k_cox_bwd_fused(const float *__restrict__ dhz, const float *__restrict__ f2, const float *__restrict__ w, int64_t B,
                 bf16 *__restrict__ df2, double *__restrict__ partial) {
+    pdl_prologue();
     const int j = threadIdx.x, slice = blockIdx.x, nslices = gridDim.x;
     const int64_t rows_per = (B + nslices - 1) / nslices, r0 = slice * rows_per, r1 = min(B, r0 + rows_per);
     const float wj = w[j];
@@ -688,6 +705,7 @@ k_cox_bwd_fused(const float *__restrict__ dhz, const float *__restrict__ f2, con
 struct SumSegs { float *out[4]; int c0[5]; int n; };
 __global__ void __launch_bounds__(256)
 k_sum_slices(const double *__restrict__ partial, int nslices, int ncols, const SumSegs segs) {
+    pdl_prologue();
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= ncols) return;
     double v = 0.0;
@@ -709,6 +727,7 @@ __global__ void __launch_bounds__(256)
 k_gate_bwd_fused(const float *__restrict__ dfused, const float *__restrict__ feat, const float *__restrict__ gate,
                  const float *__restrict__ zh, const float *__restrict__ wg2, const float *__restrict__ d_gate_ext, int64_t B,
                  float *__restrict__ dfeat, bf16 *__restrict__ dzh, double *__restrict__ partial) {
+    pdl_prologue();
     __shared__ double sh[8][GP_COLS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, slice = blockIdx.x, nslices = gridDim.x;
     const int64_t rows_per = (B + nslices - 1) / nslices, r0 = slice * rows_per, r1 = min(B, r0 + rows_per);
@@ -766,6 +785,7 @@ k_prep_bwd_fused(const float *__restrict__ dfeat, const float *__restrict__ dz, 
                  const float *__restrict__ R, const float *__restrict__ clin, const float *__restrict__ wc,
                  const float *__restrict__ bc, int64_t B, float *__restrict__ d_ct, bf16 *__restrict__ dR,
                  double *__restrict__ partial) {
+    pdl_prologue();
     const int j = threadIdx.x, slice = blockIdx.x, nslices = gridDim.x;
     const int64_t rows_per = (B + nslices - 1) / nslices, r0 = slice * rows_per, r1 = min(B, r0 + rows_per);
     const int grp = j < CT ? 0 : (j < CT + R1 ? 1 : 2);
@@ -903,11 +923,12 @@ HeadLanes *head_lanes() {
 template <int MODE>
 void colreduce(const float *a, int64_t lda, const float *x, int64_t ldx, const float *mu, const float *rstd,
                const float *s, int64_t s_stride, int64_t B, int N, double *partial, int nsl, cudaStream_t st) {
-    k_colreduce<MODE><<<dim3((N + 31) / 32, nsl), 256, 0, st>>>(a, lda, x, ldx, mu, rstd, s, s_stride, B, N, partial);
+    launch_chain(k_colreduce<MODE>, dim3((N + 31) / 32, nsl), 256, 0, st, a, lda, x, ldx, mu, rstd, s, s_stride, B, N, partial);
 }
 // weight gradient dW[M][N] = A^T B over K = batch rows (both operands MN-major).  The small ones (one to six output
 // tiles for 64 k-blocks) are split along K over the SMs into fp32 slices and summed in a fixed order (deterministic).
 __global__ void k_splitk_sum(const float *__restrict__ part, int slices, int64_t elems, float *__restrict__ out) {
+    pdl_prologue();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (int64_t)gridDim.x * blockDim.x) {
         float v = 0.f;
         for (int k = 0; k < slices; ++k) v += part[(size_t)k * elems + i];
@@ -921,7 +942,7 @@ int32_t gemm_wgrad(const void *a, int64_t lda, const void *b, int64_t ldb, int M
     const int32_t rc = gemm_bf16(a, lda, 1, b, ldb, 1, M, N, K, c, ldc, nullptr, 0, nullptr, 0, splitk_ws, st);
     if (rc) return rc;
     const int64_t elems = (int64_t)M * ldc;
-    k_splitk_sum<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(splitk_ws, slices, elems, c);
+    launch_chain(k_splitk_sum, (unsigned)((elems + 255) / 256), 256, 0, st, splitk_ws, slices, elems, c);
     return B200SURV_OK;
 }
 
@@ -930,6 +951,7 @@ int32_t gemm_wgrad(const void *a, int64_t lda, const void *b, int64_t ldb, int M
 // One CTA (the value is one scalar; 3 B elements), fixed summation order: deterministic.
 __global__ void __launch_bounds__(1024)
 k_gate_entropy_fwd(const float *__restrict__ gate, int64_t B, float eps, float *__restrict__ out) {
+    pdl_prologue();
     __shared__ double red[32];
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < 3 * B; i += blockDim.x) {
@@ -942,6 +964,7 @@ k_gate_entropy_fwd(const float *__restrict__ gate, int64_t B, float eps, float *
 // d loss / d g = (log(g + eps) + g / (g + eps)) / B
 __global__ void k_gate_entropy_bwd(const float *__restrict__ gate, const float *__restrict__ grad_out, int64_t B, float eps,
                                    float *__restrict__ d_gate) {
+    pdl_prologue();
     const float k = grad_out[0] / (float)B;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * B; i += (int64_t)gridDim.x * blockDim.x) {
         const float g = gate[i], ge = g + eps;
@@ -1023,7 +1046,7 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
             cs.b0[k + 1] = cs.b0[k] + ((cs.s[k].R + CAST_ROWS - 1) / CAST_ROWS) * ((cs.s[k].Cp + 255) / 256);
         // B200SURV_HEAD_SEED_ADVANCE: the device-resident dropout seed is bumped here, by the first kernel of the forward
         // pass -- every later kernel of this forward / backward pair reads the new value
-        k_cast_multi<<<cs.b0[cs.n], 256, 0, st>>>(cs, (seed_adv && seed_dev) ? const_cast<uint64_t *>(seed_dev) : nullptr);
+        launch_chain(k_cast_multi, cs.b0[cs.n], 256, 0, st, cs, (seed_adv && seed_dev) ? const_cast<uint64_t *>(seed_dev) : nullptr);
     }
 
     // rna encoder: Linear(rna_dim, 512) -> BN -> ReLU -> Dropout -> Linear(512, 128) -> ReLU
@@ -1033,42 +1056,42 @@ int32_t b200surv_head_fwd(const b200surv_head_params *p, const float *ct_feat, c
     if (pair1) {
         rc = gemm_bf16_ex(s.xb, Kp, 0, s.w1b, Kp, 0, (int)B, H1, rna_dim, w.slices, H1, nullptr, 0, nullptr, 0, w.slices, 512, 2, st);
         if (rc) return rc;
-        k_bn_colstats<2><<<dim3(H1 / BC, bsl), 256, 0, st>>>(w.slices, w.slices + (size_t)B * H1, p->rna0_b, nullptr, nullptr, nullptr,
+        launch_chain(k_bn_colstats<2>, dim3(H1 / BC, bsl), 256, 0, st, w.slices, w.slices + (size_t)B * H1, p->rna0_b, nullptr, nullptr, nullptr,
                                                              nullptr, nullptr, B, H1, 0, 0.f, 0, nullptr, 0, training ? 1 : 0, s.h1,
                                                              w.partial);
     } else {
         rc = gemm_bf16(s.xb, Kp, 0, s.w1b, Kp, 0, (int)B, H1, rna_dim, s.h1, H1, nullptr, 0, p->rna0_b, 0, nullptr, st);
         if (rc) return rc;
         if (training)
-            k_bn_colstats<0><<<dim3(H1 / BC, bsl), 256, 0, st>>>(s.h1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B, H1,
+            launch_chain(k_bn_colstats<0>, dim3(H1 / BC, bsl), 256, 0, st, s.h1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B, H1,
                                                                  0, 0.f, 0, nullptr, 0, 1, nullptr, w.partial);
     }
-    k_bn_apply2<<<dim3(H1 / BC, (unsigned)((B + BR - 1) / BR)), 256, 0, st>>>(s.h1, w.partial, bsl, p->bn1_w, p->bn1_b, B, H1, training,
+    launch_chain(k_bn_apply2, dim3(H1 / BC, (unsigned)((B + BR - 1) / BR)), 256, 0, st, s.h1, w.partial, bsl, p->bn1_w, p->bn1_b, B, H1, training,
                                                                               p->bn1_rm, p->bn1_rv, s.mu1, s.rstd1, thresh, inv_keep,
                                                                               seed, seed_dev, 1, s.a1, keep1);
     rc = gemm_bf16(s.a1, H1, 0, s.w2b, H1, 0, (int)B, R1, H1, s.r, R1, nullptr, 0, p->rna4_b, 1, nullptr, st);
     if (rc) return rc;
 
     // clinical encoder, masks, gate
-    k_gate_prep<<<gs(B * GZP), 256, 0, st>>>(ct_feat, s.r, clinical, mask, p->clin_w, p->clin_b, B, s.feat,
+    launch_chain(k_gate_prep, gs(B * GZP), 256, 0, st, ct_feat, s.r, clinical, mask, p->clin_w, p->clin_b, B, s.feat,
                                              gated ? s.z : nullptr, gated ? nullptr : s.fused);
     if (gated) {
         rc = gemm_bf16(s.z, GZP, 0, s.wg1b, GZP, 0, (int)B, GH, GZ, s.zh, GH, nullptr, 0, p->gate0_b, 1, nullptr, st);
         if (rc) return rc;
-        k_gate_apply<<<gs(B * 32), 256, 0, st>>>(s.zh, p->gate2_w, p->gate2_b, s.feat, B, s.gate, gate, s.fused);
+        launch_chain(k_gate_apply, gs(B * 32), 256, 0, st, s.zh, p->gate2_w, p->gate2_b, s.feat, B, s.gate, gate, s.fused);
     }
     // fusion: Linear(288, 256) -> BN -> ReLU -> Dropout -> Linear(256, 128) -> ReLU ; cox head
     rc = gemm_bf16(s.fused, FEAT, 0, s.wf1b, FEAT, 0, (int)B, H2, FEAT, s.h2, H2, nullptr, 0, p->fus0_b, 0, nullptr, st);
     if (rc) return rc;
     if (training)
-        k_bn_colstats<0><<<dim3(H2 / BC, bsl), 256, 0, st>>>(s.h2, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B, H2, 0,
+        launch_chain(k_bn_colstats<0>, dim3(H2 / BC, bsl), 256, 0, st, s.h2, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B, H2, 0,
                                                              0.f, 0, nullptr, 0, 1, nullptr, w.partial);
-    k_bn_apply2<<<dim3(H2 / BC, (unsigned)((B + BR - 1) / BR)), 256, 0, st>>>(s.h2, w.partial, bsl, p->bn2_w, p->bn2_b, B, H2, training,
+    launch_chain(k_bn_apply2, dim3(H2 / BC, (unsigned)((B + BR - 1) / BR)), 256, 0, st, s.h2, w.partial, bsl, p->bn2_w, p->bn2_b, B, H2, training,
                                                                               p->bn2_rm, p->bn2_rv, s.mu2, s.rstd2, thresh, inv_keep,
                                                                               seed, seed_dev, 2, s.a2, keep2);
     rc = gemm_bf16(s.a2, H2, 0, s.wf2b, H2, 0, (int)B, F2N, H2, s.f2, F2N, nullptr, 0, p->fus4_b, 1, nullptr, st);
     if (rc) return rc;
-    k_cox_head<<<gs(B * 32), 256, 0, st>>>(s.f2, p->cox_w, p->cox_b, B, hazard);
+    launch_chain(k_cox_head, gs(B * 32), 256, 0, st, s.f2, p->cox_w, p->cox_b, B, hazard);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
@@ -1118,11 +1141,11 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     };
     const int fsl = fslices_for(B);
     auto sums = [&](const double *partial, int ncols, SumSegs sg) {
-        k_sum_slices<<<(ncols + 7) / 8, 256, 0, sd>>>(partial, fsl, ncols, sg);
+        launch_chain(k_sum_slices, (ncols + 7) / 8, 256, 0, sd, partial, fsl, ncols, sg);
     };
 
     // ---- cox head: df2 (ReLU-masked, bf16) + partial sums of cox_head.weight / .bias and fusion.4.bias, one launch
-    k_cox_bwd_fused<<<fsl, F2N, 0, st>>>(d_hazard, s.f2, p->cox_w, B, w.df2, w.p_cox);
+    launch_chain(k_cox_bwd_fused, fsl, F2N, 0, st, d_hazard, s.f2, p->cox_w, B, w.df2, w.p_cox);
     if ((rc = fork())) return rc;
     {
         SumSegs sg; sg.n = 3;
@@ -1136,9 +1159,9 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     rc = gemm_bf16(w.df2, F2N, 0, s.wf2b, H2, 1, (int)B, H2, F2N, w.t0, H2, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dA2 [B][256]
     if (rc) return rc;
     // ---- fusion.1-3 (BN, ReLU, Dropout) backward -> dH2 (bf16); fusion.0.bias with it
-    k_bn_colstats<1><<<dim3(H2 / BC, bsl), 256, 0, st>>>(w.t0, nullptr, nullptr, s.h2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh,
+    launch_chain(k_bn_colstats<1>, dim3(H2 / BC, bsl), 256, 0, st, w.t0, nullptr, nullptr, s.h2, s.mu2, s.rstd2, p->bn2_w, p->bn2_b, B, H2, thresh,
                                                          inv_keep, seed, seed_dev, 2, 1, nullptr, w.partial);
-    k_bn_bwd_dx3<<<dim3(H2 / BC, (unsigned)((B + BR - 1) / BR)), 256, 0, st>>>(w.t0, s.h2, w.partial, bsl, s.mu2, s.rstd2, p->bn2_w,
+    launch_chain(k_bn_bwd_dx3, dim3(H2 / BC, (unsigned)((B + BR - 1) / BR)), 256, 0, st, w.t0, s.h2, w.partial, bsl, s.mu2, s.rstd2, p->bn2_w,
                                                                                p->bn2_b, B, H2, training, thresh, inv_keep, seed,
                                                                                seed_dev, 2, g->bn2_b, g->bn2_w, g->fus0_b, w.dh2);
     // ---- fusion.0: dW = dH2^T fused (side), dfused = dH2 Wf1
@@ -1151,7 +1174,7 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     const float *dz = nullptr;
     if (gated) {
         // ---- gate: softmax / scaling backward with the gate.2 gradients and gate.0.bias as partial sums; gate.0
-        k_gate_bwd_fused<<<fsl, 256, 0, st>>>(w.t0, s.feat, s.gate, s.zh, p->gate2_w, d_gate, B, w.t1, w.dzh, w.p_gate);
+        launch_chain(k_gate_bwd_fused, fsl, 256, 0, st, w.t0, s.feat, s.gate, s.zh, p->gate2_w, d_gate, B, w.t1, w.dzh, w.p_gate);
         if ((rc = fork())) return rc;
         {
             SumSegs sg; sg.n = 3;
@@ -1167,7 +1190,7 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
         dz = w.t0;
     }
     // ---- masks, clinical encoder (its two gradients and rna_encoder.4.bias as partial sums)
-    k_prep_bwd_fused<<<fsl, FEAT, 0, st>>>(dfeat, dz, GZP, mask, s.r, clinical, p->clin_w, p->clin_b, B, d_ct_feat, w.dR, w.p_prep);
+    launch_chain(k_prep_bwd_fused, fsl, FEAT, 0, st, dfeat, dz, GZP, mask, s.r, clinical, p->clin_w, p->clin_b, B, d_ct_feat, w.dR, w.p_prep);
     if ((rc = fork())) return rc;
     {
         SumSegs sg; sg.n = 3;
@@ -1181,9 +1204,9 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
     rc = gemm_bf16(w.dR, R1, 0, s.w2b, H1, 1, (int)B, H1, R1, w.t0, H1, nullptr, 0, nullptr, 0, nullptr, st);  // t0 = dA1 [B][512]
     if (rc) return rc;
     // ---- rna_encoder.1-3 backward -> dH1 (bf16); rna_encoder.0.bias with it
-    k_bn_colstats<1><<<dim3(H1 / BC, bsl), 256, 0, st>>>(w.t0, nullptr, nullptr, s.h1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh,
+    launch_chain(k_bn_colstats<1>, dim3(H1 / BC, bsl), 256, 0, st, w.t0, nullptr, nullptr, s.h1, s.mu1, s.rstd1, p->bn1_w, p->bn1_b, B, H1, thresh,
                                                          inv_keep, seed, seed_dev, 1, 1, nullptr, w.partial);
-    k_bn_bwd_dx3<<<dim3(H1 / BC, (unsigned)((B + BR - 1) / BR)), 256, 0, st>>>(w.t0, s.h1, w.partial, bsl, s.mu1, s.rstd1, p->bn1_w,
+    launch_chain(k_bn_bwd_dx3, dim3(H1 / BC, (unsigned)((B + BR - 1) / BR)), 256, 0, st, w.t0, s.h1, w.partial, bsl, s.mu1, s.rstd1, p->bn1_w,
                                                                                p->bn1_b, B, H1, training, thresh, inv_keep, seed,
                                                                                seed_dev, 1, g->bn1_b, g->bn1_w, g->rna0_b, w.dh1);
     // ---- rna_encoder.0: dW1 [512][rna_dim] = dH1^T x  (the big one; x is an input, no dx): CTA pairs for large batches
@@ -1202,14 +1225,14 @@ int32_t b200surv_head_bwd(const b200surv_head_params *p, const b200surv_head_gra
 
 int32_t b200surv_gate_entropy_fwd(const float *gate, int64_t B, float eps, float *out_loss, b200surv_stream_t stream) {
     B200_REQUIRE(gate && out_loss && B >= 1, "arguments");
-    k_gate_entropy_fwd<<<1, 1024, 0, as_stream(stream)>>>(gate, B, eps, out_loss);
+    launch_chain(k_gate_entropy_fwd, 1, 1024, 0, as_stream(stream), gate, B, eps, out_loss);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
 int32_t b200surv_gate_entropy_bwd(const float *gate, const float *grad_out, int64_t B, float eps, float *d_gate,
                                   b200surv_stream_t stream) {
     B200_REQUIRE(gate && grad_out && d_gate && B >= 1, "arguments");
-    k_gate_entropy_bwd<<<gs(3 * B), 256, 0, as_stream(stream)>>>(gate, grad_out, B, eps, d_gate);
+    launch_chain(k_gate_entropy_bwd, gs(3 * B), 256, 0, as_stream(stream), gate, grad_out, B, eps, d_gate);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }
