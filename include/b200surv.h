@@ -338,6 +338,13 @@ size_t b200surv_head_workspace_bytes(int64_t B, int32_t rna_dim); /* scratch of 
 #define B200SURV_HEAD_SEED_ADVANCE 8
 int32_t b200surv_head_stage_rna(const float *rna, int64_t B, int32_t rna_dim, void *saved, size_t saved_bytes,
                                 b200surv_stream_t stream);
+/* The same plus up to three plain fp32 copies (copy_dst[k][0..copy_elems[k]) = copy_src[k][...]; HOST arrays of device
+ * pointers) in the same launch: a new batch -- RNA matrix, CT features, age, modality mask -- reaches a captured step's
+ * static buffers with one kernel instead of four (the batch-4 loop of partial_modality_training.py:382-400 hands over
+ * exactly these four tensors per step). */
+int32_t b200surv_head_stage_batch(const float *rna, int64_t B, int32_t rna_dim, void *saved, size_t saved_bytes,
+                                  const float *const *copy_src, float *const *copy_dst, const int64_t *copy_elems,
+                                  int32_t n_copies, b200surv_stream_t stream);
 int32_t b200surv_head_fwd(const b200surv_head_params *params, const float *ct_feat, const float *rna,
                           const float *clinical, const float *mask, int64_t B, int32_t rna_dim,
                           int32_t training, float dropout_p, uint64_t seed, float *hazard, float *gate,

@@ -84,6 +84,8 @@ SIGNATURES = {
     "b200surv_head_fwd": (c_int32, [c_void_p] * 5 + [c_int64, c_int32, c_int32, c_float, ctypes.c_uint64] +
                           [c_void_p] * 5 + [c_size_t, c_void_p, c_size_t, c_void_p]),
     "b200surv_head_stage_rna": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
+    "b200surv_head_stage_batch": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int32,
+                                            c_void_p]),
     "b200surv_head_bwd": (c_int32, [c_void_p] * 6 + [c_int64, c_int32, c_int32, c_float, ctypes.c_uint64, c_void_p,
                                                      c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "b200surv_cindex_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),

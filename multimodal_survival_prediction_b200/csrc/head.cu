@@ -91,6 +91,44 @@ static void cast_pad(const float *src, int64_t lds, bf16 *dst, int64_t ldd, int6
     launch_chain(k_cast_pad, dim3(gx, (unsigned)gy), 256, 0, st, src, lds, dst, ldd, R, C, Cp);
 }
 
+// A whole batch staged for a captured step in ONE launch: the RNA matrix as bf16 (4 columns per thread: scalar loads -- a
+// row of 5005 floats starts on a 4-byte boundary only -- and one 8-byte store; two rows in flight) and up to three small
+// fp32 inputs copied into the graph's static buffers by the blocks behind the cast blocks.
+struct StageCopies { const float *src[3]; float *dst[3]; int64_t n[3]; int count; };
+__global__ void __launch_bounds__(256)
+k_stage_batch(const float *__restrict__ src, int64_t lds, bf16 *__restrict__ dst, int64_t ldd, int64_t R, int C, int Cp, int gx,
+              int gy, const StageCopies cp) {
+    pdl_prologue();
+    const int ncast = gx * gy;
+    if ((int)blockIdx.x >= ncast) {   // copy blocks
+        const int64_t stride = (int64_t)(gridDim.x - ncast) * blockDim.x;
+        for (int k = 0; k < cp.count; ++k)
+            for (int64_t i = (int64_t)(blockIdx.x - ncast) * blockDim.x + threadIdx.x; i < cp.n[k]; i += stride) cp.dst[k][i] = cp.src[k][i];
+        return;
+    }
+    const int bx = blockIdx.x % gx, by = blockIdx.x / gx;
+    const int c = 4 * (bx * blockDim.x + threadIdx.x);
+    if (c >= Cp) return;
+    auto load4 = [&](int64_t r, float (&v)[4]) {
+        const float *row = src + r * lds;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = c + u < C ? row[c + u] : 0.f;
+    };
+    auto store4 = [&](int64_t r, const float (&v)[4]) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t *>(&lo); pk.y = *reinterpret_cast<uint32_t *>(&hi);
+        *reinterpret_cast<uint2 *>(dst + r * ldd + c) = pk;   // ldd and c are multiples of 4: 8-byte aligned
+    };
+    int64_t r = by;
+    for (; r + gy < R; r += 2 * (int64_t)gy) {
+        float a[4], b[4];
+        load4(r, a); load4(r + gy, b);
+        store4(r, a); store4(r + gy, b);
+    }
+    if (r < R) { float a[4]; load4(r, a); store4(r, a); }
+}
+
 // ---------------------------------------------------------------- column reductions (deterministic)
 // partial[slice][2][N] (double).  MODE 0: (sum a, sum a^2)   MODE 1: (sum a, sum a * xhat), xhat from x, mu, rstd
 // MODE 2: (sum a * s[row], sum s[row])   MODE 3: (sum a, 0)
@@ -1103,6 +1141,34 @@ int32_t b200surv_head_stage_rna(const float *rna, int64_t B, int32_t rna_dim, vo
     const Saved s = carve_saved(saved, B, rna_dim, &need);
     if (saved_bytes < need) { set_error("head stage: saved buffer %zu < %zu", saved_bytes, need); return B200SURV_WORKSPACE_TOO_SMALL; }
     cast_pad(rna, rna_dim, s.xb, kpad(rna_dim), B, rna_dim, kpad(rna_dim), as_stream(stream));
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+int32_t b200surv_head_stage_batch(const float *rna, int64_t B, int32_t rna_dim, void *saved, size_t saved_bytes,
+                                  const float *const *copy_src, float *const *copy_dst, const int64_t *copy_elems,
+                                  int32_t n_copies, b200surv_stream_t stream) {
+    B200_REQUIRE(rna && saved && B >= 1 && rna_dim >= 1, "arguments");
+    B200_REQUIRE(n_copies >= 0 && n_copies <= 3 && (n_copies == 0 || (copy_src && copy_dst && copy_elems)), "copies");
+    size_t need = 0;
+    const Saved s = carve_saved(saved, B, rna_dim, &need);
+    if (saved_bytes < need) { set_error("head stage: saved buffer %zu < %zu", saved_bytes, need); return B200SURV_WORKSPACE_TOO_SMALL; }
+    StageCopies cp;
+    cp.count = 0;
+    for (int k = 0; k < n_copies; ++k) {
+        if (copy_elems[k] <= 0) continue;
+        B200_REQUIRE(copy_src[k] && copy_dst[k], "copy pointers");
+        cp.src[cp.count] = copy_src[k]; cp.dst[cp.count] = copy_dst[k]; cp.n[cp.count] = copy_elems[k]; ++cp.count;
+    }
+    const int Kp = kpad(rna_dim);
+    B200_REQUIRE(Kp % 4 == 0, "padded row length");
+    const int gx = (Kp / 4 + 255) / 256;
+    int64_t gy = (B + 1) / 2;                                // two rows per thread and round
+    const int64_t cap = (int64_t)16 * num_sms() / gx + 1;
+    if (gy > cap) gy = cap;
+    const int ncopy = cp.count ? 2 * num_sms() : 0;
+    launch_chain(k_stage_batch, (unsigned)(gx * gy + ncopy), 256, 0, as_stream(stream), rna, (int64_t)rna_dim, s.xb, (int64_t)Kp, B,
+                 (int)rna_dim, Kp, gx, (int)gy, cp);
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;
 }

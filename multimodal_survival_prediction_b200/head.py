@@ -162,6 +162,24 @@ def stage_rna(rna, saved):
                 "b200surv_head_stage_rna")
 
 
+def stage_batch(rna, saved, copies):
+    """``stage_rna`` plus up to three fp32 copies ``(dst, src)`` into static buffers, all in ONE launch
+    (b200surv_head_stage_batch)."""
+    dev = saved.device
+    x = _f32c(rna, dev)
+    pairs = [(d, _f32c(s, dev)) for d, s in copies]
+    n = len(pairs)
+    src = (ctypes.c_void_p * 3)(*[p[1].data_ptr() for p in pairs], *([0] * (3 - n)))
+    dst = (ctypes.c_void_p * 3)(*[p[0].data_ptr() for p in pairs], *([0] * (3 - n)))
+    cnt = (ctypes.c_int64 * 3)(*[p[0].numel() for p in pairs], *([0] * (3 - n)))
+    for d, s in pairs:
+        if d.numel() != s.numel() or not d.is_contiguous() or d.dtype != torch.float32:
+            raise ValueError("stage_batch: static buffers must be contiguous fp32 of the sources' sizes")
+    with torch.cuda.device(dev):
+        L.check(L.load().b200surv_head_stage_batch(L.ptr(x), x.shape[0], x.shape[1], L.ptr(saved), saved.numel(), src, dst, cnt, n,
+                                                   L.stream_ptr(dev)), "b200surv_head_stage_batch")
+
+
 def fused_head(module, ct_feat, rna, clinical, mask=None, want_masks=False, seed=None, staged_saved=None):
     """Run the head of ``module`` (a PartialModalityNet / MultiModalSurvivalNet from this file) on CUDA."""
     params = _param_list(module)
@@ -278,12 +296,22 @@ class GraphedHeadStep:
         return self.loss, self.outputs
 
     def step(self, ct_feat, rna, clinical, mask=None):
+        copies, big = [], []
         for i, (dst, src) in enumerate(zip(self.inputs, (ct_feat, rna, clinical, mask))):
-            if dst is None or src is dst:
+            if dst is None or src is dst or i == 1:
                 continue
-            if i == 1:
-                stage_rna(src, self.saved)      # fp32 -> bf16 into the saved buffer; self.inputs[1] is not read by the graph
+            # small device-resident fp32 inputs ride along with the RNA cast; anything else (host tensors, CT volumes) is copied
+            if src.is_cuda and src.dtype == torch.float32 and src.is_contiguous() and dst.numel() <= (1 << 22):
+                copies.append((dst, src))
             else:
+                big.append((dst, src))
+        for dst, src in big:
+            dst.copy_(src, non_blocking=True)
+        if rna is not self.inputs[1]:
+            # fp32 -> bf16 into the saved buffer; self.inputs[1] is not read by the graph
+            stage_batch(rna, self.saved, copies)
+        else:
+            for dst, src in copies:
                 dst.copy_(src, non_blocking=True)
         return self.replay()
 

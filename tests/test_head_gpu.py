@@ -252,3 +252,23 @@ def test_gate_entropy_loss_matches_the_reference_expression():
         assert float((g.grad - g2.grad).abs().max()) <= 1e-5 * float(g2.grad.abs().max()) + 1e-9, B
     with pytest.raises(ValueError):      # no eager path for other gate widths
         ghead.gate_entropy_loss(torch.softmax(torch.randn(5, 4, device=dev), dim=1))
+
+
+def test_stage_batch_equals_stage_rna_plus_copies():
+    """b200surv_head_stage_batch: the RNA cast (4 columns per thread) and the small-input copies in one launch."""
+    from multimodal_survival_prediction_b200 import head as H
+    dev = torch.device("cuda", 0)
+    for B, rna_dim in ((4, 5005), (301, 5005), (4096, 40), (37, 8)):
+        rna = torch.randn(B, rna_dim, device=dev)
+        a, b = H.head_saved_buffer(B, rna_dim, dev), H.head_saved_buffer(B, rna_dim, dev)
+        a.zero_(); b.zero_()
+        H.stage_rna(rna, a)
+        src = [torch.randn(B, 128, device=dev), torch.rand(B, 1, device=dev), torch.rand(B, 3, device=dev)]
+        dst = [torch.zeros_like(x) for x in src]
+        H.stage_batch(rna, b, list(zip(dst, src)))
+        torch.cuda.synchronize()
+        assert torch.equal(a, b), (B, rna_dim)
+        for d, s_ in zip(dst, src):
+            assert torch.equal(d, s_)
+        H.stage_batch(rna, b, [])                     # no copies
+        assert torch.equal(a, b)
