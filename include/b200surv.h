@@ -219,6 +219,25 @@ int32_t b200surv_cox_sorted_shard_finish(int64_t n, int32_t ties, int32_t reduct
                                          int32_t world, float *out_loss, void *state, size_t state_bytes,
                                          void *workspace, size_t workspace_bytes, b200surv_stream_t stream);
 
+/* Row-block shards -> time-range shards (the sample sort in front of the shard phases above): rank-local part.
+ * b200surv_route_rows: dest[i] = number of `splitters` (device, n_dest - 1 ascending floats, the same on every rank) that are
+ * <= time[i]; rows are grouped by destination, stable inside a destination:
+ *   out_perm[j]     source row of the j-th routed row (int32; the way back for the gradient)
+ *   out_counts[d]   rows for destination d (device int64[n_dest]; the caller reads them to size the all-to-all)
+ *   out_log_hz / out_time / out_event [n]   the packed send buffers (any of them may be NULL)
+ * The caller exchanges the groups (all-to-all with the counts as split sizes) and runs the shard phases on what it received.
+ * Per step only log_hz changes: b200surv_route_gather(src, perm, n, out) packs a new vector with a kept permutation
+ * (out[j] = src[perm[j]]), b200surv_route_scatter puts the returned gradient back (out[perm[j]] = src[j]).
+ * workspace: b200surv_route_workspace_bytes(n).  n_dest <= 64.  Replaces, across GPUs, the reference's single-device
+ * argsort(time) (scripts/training/partial_modality_training.py:303). */
+size_t b200surv_route_workspace_bytes(int64_t n);
+int32_t b200surv_route_rows(const float *log_hz, const float *time, const uint8_t *event, int64_t n,
+                            const float *splitters, int32_t n_dest, float *out_log_hz, float *out_time,
+                            uint8_t *out_event, int32_t *out_perm, int64_t *out_counts, void *workspace,
+                            size_t workspace_bytes, b200surv_stream_t stream);
+int32_t b200surv_route_gather(const float *src, const int32_t *perm, int64_t n, float *out, b200surv_stream_t stream);
+int32_t b200surv_route_scatter(const float *src, const int32_t *perm, int64_t n, float *out, b200surv_stream_t stream);
+
 /* ---- Harrell's concordance index: integer pair counts -------------------------------------- */
 /* out_counts: int64[n_seg][6], ADDED to (caller zeroes): over rows i in [row_begin, row_end) of
  * each segment and all columns j of the same segment,

@@ -70,6 +70,11 @@ SIGNATURES = {
                                                   c_void_p]),
     "b200surv_cox_sorted_shard_finish": (c_int32, [c_int64, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
                                                    c_size_t, c_void_p, c_size_t, c_void_p]),
+    "b200surv_route_workspace_bytes": (c_size_t, [c_int64]),
+    "b200surv_route_rows": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200surv_route_gather": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "b200surv_route_scatter": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "b200surv_gemm_bf16": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                      c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
     "b200surv_gemm_bf16_ex": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,

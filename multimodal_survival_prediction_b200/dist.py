@@ -215,7 +215,7 @@ class ShardedCoxSorted:
         if n_local < 1:
             raise ValueError("every shard needs at least one row")
         assert self.lib.b200surv_cox_shard_record_bytes() == self.REC
-        self.n, self.dev = n_local, device
+        self.n, self.capacity, self.dev = n_local, n_local, device     # n may shrink per call (set_rows), never above capacity
         self.ties, self.red = L.TIES[ties], reduction
         self.sb = self.lib.b200surv_cox_state_bytes(n_local, 1, L.COX_SORTED, 0)
         self.wb = self.lib.b200surv_cox_workspace_bytes(n_local, 1, L.COX_SORTED, 0)
@@ -225,6 +225,13 @@ class ShardedCoxSorted:
         self.all = torch.zeros(3, self.world * self.REC, dtype=torch.uint8, device=device)
         self.loss = torch.empty(1, dtype=torch.float32, device=device)
         self.ones = torch.ones(1, dtype=torch.float32, device=device)
+
+    def set_rows(self, n: int):
+        """Rows of this shard for the next forward / backward pair (1 <= n <= the capacity given at construction): the
+        buffers are sized once, a re-partitioned cohort may hand a rank a different number of rows."""
+        if not 1 <= n <= self.capacity:
+            raise ValueError(f"shard rows {n} outside [1, {self.capacity}]")
+        self.n = n
 
     # -- the four phases (each returns the record the caller must all-gather before the next one)
     def phase_keys(self, log_hz, time, event):
@@ -299,3 +306,131 @@ class ShardedCoxSorted:
             raise L.B200SurvError("ShardedCoxSorted: the shards are not time ranges (a rank holds a time above the next "
                                   "rank's smallest time); use time_range_partition first")
         return flags
+
+
+# ------------------------------------------------------------------ row blocks -> time ranges (sample sort) + SORTED shards
+def choose_splitters(samples: torch.Tensor, world: int) -> torch.Tensor:
+    """world - 1 ascending cut points of the time axis from the pooled samples of all ranks (the same tensor on every rank
+    gives the same cuts): the k/world quantiles of the sorted sample."""
+    s, _ = torch.sort(samples.flatten())
+    idx = (torch.arange(1, world, device=s.device) * s.numel()) // world
+    return s[idx].contiguous()
+
+
+def _all_to_all(out, inp, out_splits, in_splits, group=None):
+    """all_to_all_single with uneven splits; on backends without it (gloo: the CPU tests of this host logic) the same exchange
+    as one broadcast per (source, destination) pair of a padded all-gather."""
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(out, inp, out_splits, in_splits, group=group)
+        return
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    sizes = [None] * world
+    dist.all_gather_object(sizes, list(in_splits), group=group)
+    cap = max(sum(x) for x in sizes)
+    pad = torch.zeros(cap, dtype=inp.dtype)
+    pad[:inp.numel()] = inp
+    bufs = [torch.zeros(cap, dtype=inp.dtype) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    o = 0
+    for src in range(world):
+        a = sum(sizes[src][:rank])
+        k = sizes[src][rank]
+        out[o:o + k] = bufs[src][a:a + k]
+        o += k
+
+
+class RowBlockCoxSorted:
+    """SORTED Cox loss for patients sharded by ROW BLOCK over the ranks (BASELINE.json north_star): a sample sort on
+    survival time puts every rank in charge of one time range, then `ShardedCoxSorted` (boundary records all-gathered,
+    exact carry-in).  What the reference does with one argsort on one device (partial_modality_training.py:303-309).
+
+    ``plan(time, event)`` -- once per cohort; times and events do not change between training steps: pooled samples ->
+    world - 1 splitters, rank-local routing (b200surv_route_rows: destination of every row, rows grouped by destination,
+    the permutation back), one all-to-all each for time and event.  Reads the per-destination counts on the host (the only
+    synchronisation).  ``forward(log_hz)`` -- per step: pack through the kept permutation (b200surv_route_gather), one
+    all-to-all of 4 bytes per row, the shard phases; returns the loss of the WHOLE cohort (same value on every rank).
+    ``backward(out_grad)``: the shard's gradient rows travel back (all-to-all) into the caller's row order
+    (b200surv_route_scatter)."""
+
+    def __init__(self, n_local: int, device, ties: str = "efron", reduction: int = L.REDUCE_MEAN_TERMS, slack: float = 1.25,
+                 samples_per_rank: int = 4096, group=None):
+        self.lib = L.load()
+        L.require_device(device.index)
+        self.rank, self.world = _world()
+        self.n, self.dev, self.group = n_local, device, group
+        self.ties, self.red, self.slack, self.samples = ties, reduction, slack, samples_per_rank
+        self.rwb = self.lib.b200surv_route_workspace_bytes(n_local)
+        self.rws = torch.empty(self.rwb, dtype=torch.uint8, device=device)
+        self.perm = torch.empty(n_local, dtype=torch.int32, device=device)
+        self.counts = torch.zeros(max(self.world, 1), dtype=torch.int64, device=device)
+        self.send = torch.empty(n_local, dtype=torch.float32, device=device)
+        self.shard = None
+        self.n_recv = 0
+
+    def plan(self, time, event):
+        n, dev, world = self.n, self.dev, self.world
+        if world > 1:
+            stride = max(1, n // self.samples)
+            mine = time[::stride][:self.samples].contiguous()
+            if mine.numel() < self.samples:        # short shards: repeat (weights the pooled quantiles by shard, roughly)
+                mine = mine.repeat((self.samples + mine.numel() - 1) // mine.numel())[:self.samples].contiguous()
+            pooled = torch.empty(world * self.samples, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(pooled, mine, group=self.group)
+            self.splitters = choose_splitters(pooled, world)
+        else:
+            self.splitters = torch.empty(0, dtype=torch.float32, device=dev)
+        t_send = torch.empty(n, dtype=torch.float32, device=dev)
+        e_send = torch.empty(n, dtype=torch.bool, device=dev)
+        L.check(self.lib.b200surv_route_rows(None, L.ptr(time), L.ptr(event), n, L.ptr(self.splitters) if world > 1 else None, world,
+                                             None, L.ptr(t_send), L.ptr(e_send), L.ptr(self.perm), L.ptr(self.counts), L.ptr(self.rws),
+                                             self.rwb, L.stream_ptr(dev)), "b200surv_route_rows")
+        self.in_splits = [int(x) for x in self.counts.cpu().tolist()]                # the one host synchronisation
+        if world > 1:
+            recv_counts = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_to_all_single(recv_counts, self.counts, group=self.group)
+            self.out_splits = [int(x) for x in recv_counts.cpu().tolist()]
+        else:
+            self.out_splits = list(self.in_splits)
+        self.n_recv = sum(self.out_splits)
+        if self.n_recv < 1:
+            raise L.B200SurvError("RowBlockCoxSorted: a rank received no rows (fewer distinct times than ranks?)")
+        if self.shard is None or self.n_recv > self.shard.capacity:
+            self.shard = ShardedCoxSorted(max(int(self.n_recv * self.slack), self.n_recv), dev, ties=self.ties, reduction=self.red)
+            cap = self.shard.capacity
+            self.t_recv = torch.empty(cap, dtype=torch.float32, device=dev)
+            self.e_recv = torch.empty(cap, dtype=torch.bool, device=dev)
+            self.x_recv = torch.empty(cap, dtype=torch.float32, device=dev)
+            self.g_recv = torch.empty(cap, dtype=torch.float32, device=dev)
+        self.shard.set_rows(self.n_recv)
+        if world > 1:
+            _all_to_all(self.t_recv[:self.n_recv], t_send, self.out_splits, self.in_splits, self.group)
+            _all_to_all(self.e_recv[:self.n_recv].view(torch.uint8), e_send.view(torch.uint8), self.out_splits, self.in_splits, self.group)
+        else:
+            self.t_recv[:n].copy_(t_send); self.e_recv[:n].copy_(e_send)
+        return self
+
+    def forward(self, log_hz):
+        if self.shard is None:
+            raise L.B200SurvError("RowBlockCoxSorted.forward before plan(time, event)")
+        L.check(self.lib.b200surv_route_gather(L.ptr(log_hz), L.ptr(self.perm), self.n, L.ptr(self.send), L.stream_ptr(self.dev)),
+                "b200surv_route_gather")
+        x = self.x_recv[:self.n_recv]
+        if self.world > 1:
+            _all_to_all(x, self.send, self.out_splits, self.in_splits, self.group)
+        else:
+            x.copy_(self.send)
+        return self.shard.forward(x, self.t_recv[:self.n_recv], self.e_recv[:self.n_recv], group=self.group)
+
+    def backward(self, out_grad, grad_out=None):
+        g = self.g_recv[:self.n_recv]
+        self.shard.backward(g, grad_out)
+        if self.world > 1:
+            _all_to_all(self.send, g, self.in_splits, self.out_splits, self.group)
+        else:
+            self.send.copy_(g)
+        L.check(self.lib.b200surv_route_scatter(L.ptr(self.send), L.ptr(self.perm), self.n, L.ptr(out_grad), L.stream_ptr(self.dev)),
+                "b200surv_route_scatter")
+        return out_grad
+
+    def check(self):
+        return self.shard.check()

@@ -223,13 +223,32 @@ class _HeadBase(nn.Module):
 
 
 class PartialModalityNet(_HeadBase):
-    """Gated head: forward(ct, rna, clinical, mask) -> (hazard [B], gate_weights [B,3])."""
+    """Gated head: forward(ct, rna, clinical, mask) -> (hazard [B], gate_weights [B,3]).
 
-    def __init__(self, rna_dim=5005, clinical_dim=1):
+    ``skip_missing_ct`` (default False = the reference): the reference runs the CT encoder on every
+    row, zero volumes of patients without imaging included, and multiplies their features by mask[:, 0] = 0 afterwards
+    (partial_modality_training.py:245-259).  With the flag set the encoder only sees the rows that have a volume -- 142 of
+    608 patients in the reference cohort -- and the others get zero features directly.  Hazards of an eval-mode model are
+    unchanged; in training mode BatchNorm3d then takes its batch statistics over the present volumes only, which is NOT
+    what the reference computes (contract a4), hence a flag and not the default.  Costs one device->host read (the number
+    of present rows)."""
+
+    def __init__(self, rna_dim=5005, clinical_dim=1, skip_missing_ct: bool = False):
         super().__init__(rna_dim, clinical_dim, gated=True)
+        self.skip_missing_ct = skip_missing_ct
+
+    def _ct_features_present(self, ct, mask):
+        present = torch.nonzero(mask[:, 0] != 0).squeeze(1)          # (synchronises: the subset's size shapes the launch)
+        feat = torch.zeros(ct.size(0), 128, dtype=ct.dtype, device=ct.device)
+        if present.numel() == 0:
+            return feat
+        if present.numel() == ct.size(0):
+            return self._ct_features(ct)
+        return feat.index_copy(0, present, self._ct_features(ct.index_select(0, present)))
 
     def forward(self, ct, rna, clinical, mask):
-        hazard, gate = fused_head(self, self._ct_features(ct), rna, clinical, mask)
+        ct_feat = self._ct_features_present(ct, mask) if self.skip_missing_ct else self._ct_features(ct)
+        hazard, gate = fused_head(self, ct_feat, rna, clinical, mask)
         return hazard, gate
 
     def forward_features(self, ct_feat, rna, clinical, mask):

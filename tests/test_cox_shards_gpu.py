@@ -147,3 +147,50 @@ def test_one_shard_equals_the_plain_sorted_path():
     l1 = pkg.neg_partial_log_likelihood(x, ev.cuda(), t.cuda(), "efron", mode="sorted")
     l1.backward()
     assert float(loss) == float(l1) and torch.equal(g, x.grad)   # same kernels, same tiles: bit-identical
+
+
+def test_route_rows_groups_by_destination_stably():
+    """b200surv_route_rows: destination = number of splitters <= time, rows grouped by destination in their original order,
+    per-destination counts, packed send buffers; gather / scatter through the permutation are inverse to each other."""
+    dev = torch.device("cuda", 0)
+    lib = L.load()
+    for n, n_dest in ((1, 1), (5, 3), (10_000, 8), (300_001, 64)):
+        lh, ev, t = synth.cohort(n, 90 + n_dest)
+        spl = np.sort(np.random.default_rng(n).choice(np.unique(t.numpy()), size=min(n_dest - 1, len(np.unique(t.numpy()))), replace=False)).astype(np.float32)
+        spl = np.concatenate([spl, np.full(n_dest - 1 - len(spl), np.inf, np.float32)])
+        x, tt, e = lh.to(dev), t.to(dev), ev.to(dev)
+        ws = torch.empty(lib.b200surv_route_workspace_bytes(n), dtype=torch.uint8, device=dev)
+        o_lh, o_t = torch.empty(n, device=dev), torch.empty(n, device=dev)
+        o_e = torch.empty(n, dtype=torch.bool, device=dev)
+        perm = torch.empty(n, dtype=torch.int32, device=dev)
+        counts = torch.empty(n_dest, dtype=torch.int64, device=dev)
+        sp = torch.as_tensor(spl).to(dev)
+        L.check(lib.b200surv_route_rows(L.ptr(x), L.ptr(tt), L.ptr(e), n, L.ptr(sp) if n_dest > 1 else None, n_dest, L.ptr(o_lh),
+                                        L.ptr(o_t), L.ptr(o_e), L.ptr(perm), L.ptr(counts), L.ptr(ws), ws.numel(), L.stream_ptr(dev)),
+                "b200surv_route_rows")
+        dest = np.searchsorted(spl, t.numpy(), side="right")
+        want = np.argsort(dest, kind="stable")
+        assert np.array_equal(perm.cpu().numpy(), want)
+        assert np.array_equal(counts.cpu().numpy(), np.bincount(dest, minlength=n_dest))
+        assert torch.equal(o_lh.cpu(), lh[want]) and torch.equal(o_t.cpu(), t[want]) and torch.equal(o_e.cpu(), ev[want])
+        g = torch.empty(n, device=dev)
+        L.check(lib.b200surv_route_gather(L.ptr(x), L.ptr(perm), n, L.ptr(g), L.stream_ptr(dev)), "gather")
+        assert torch.equal(g, o_lh)
+        back = torch.empty(n, device=dev)
+        L.check(lib.b200surv_route_scatter(L.ptr(g), L.ptr(perm), n, L.ptr(back), L.stream_ptr(dev)), "scatter")
+        assert torch.equal(back, x)
+
+
+def test_row_block_operator_on_one_rank_equals_sorted():
+    dev = torch.device("cuda", 0)
+    n = 70_001
+    lh, ev, t = synth.cohort(n, 95, few_ties=True)
+    op = bd.RowBlockCoxSorted(n, dev).plan(t.to(dev), ev.to(dev))
+    loss = op.forward(lh.to(dev))
+    g = torch.empty(n, device=dev)
+    op.backward(g)
+    assert op.check() == 0
+    x = lh.cuda().requires_grad_(True)
+    l1 = pkg.neg_partial_log_likelihood(x, ev.cuda(), t.cuda(), "efron", mode="sorted")
+    l1.backward()
+    assert float(loss) == float(l1.detach()) and torch.equal(g, x.grad)

@@ -76,3 +76,57 @@ def test_sharded_cindex_and_cox_exchange_world2():
         assert counts == full                      # every rank ends with the global counters, bit-exact
         assert bins == ref_bins.tolist()           # integer aggregates: exact for any sharding
         assert abs(mx[0] - lh.max().item()) < 1e-12
+
+
+def _a2a_worker(rank, world, port, q):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from multimodal_survival_prediction_b200 import dist as bd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # host logic of the sample sort in front of the SORTED shard phases: pooled samples -> identical splitters on every
+        # rank; rows routed by destination; the uneven all-to-all (gloo has none: the fallback path)
+        n = 1000 + 37 * rank
+        g = torch.Generator().manual_seed(50 + rank)
+        t = torch.empty(n).exponential_(1.0 / 1000.0, generator=g)
+        pooled = [torch.empty(256) for _ in range(world)]
+        dist.all_gather(pooled, t[:256].contiguous())
+        spl = bd.choose_splitters(torch.cat(pooled), world)
+        dest = np.searchsorted(spl.numpy(), t.numpy(), side="right")
+        perm = np.argsort(dest, kind="stable")
+        in_splits = np.bincount(dest, minlength=world).tolist()
+        all_splits = [None] * world
+        dist.all_gather_object(all_splits, in_splits)
+        out_splits = [all_splits[src][rank] for src in range(world)]
+        recv = torch.empty(sum(out_splits))
+        bd._all_to_all(recv, t[perm].contiguous(), out_splits, in_splits)
+        lo = -np.inf if rank == 0 else float(spl[rank - 1])
+        hi = np.inf if rank == world - 1 else float(spl[rank])
+        ok = bool(((recv.numpy() >= lo) & (recv.numpy() < hi)).all())
+        sums = [None] * world
+        dist.all_gather_object(sums, (float(recv.double().sum()), float(t.double().sum()), recv.numel(), n))
+        q.put((rank, ok, spl.tolist(), sums))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sample_sort_host_logic_gloo_world2():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_a2a_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+    assert got[0][2] == got[1][2] and len(got[0][2]) == 1            # one splitter, the same on both ranks
+    assert got[0][1] and got[1][1]                                    # every received time lies in the rank's range
+    sums = got[0][3]
+    assert abs(sum(x[0] for x in sums) - sum(x[1] for x in sums)) < 1e-6 * sum(x[1] for x in sums)   # nothing lost
+    assert sum(x[2] for x in sums) == sum(x[3] for x in sums)

@@ -153,3 +153,65 @@ def test_sharded_cox_sorted_two_gpus_time_range_shards():
             assert abs(loss - loss_single) <= 2e-6 * abs(loss_single), (rank, key, loss, loss_single)
             assert gerr <= 2e-6 * gmax, (rank, key, gerr, gmax)
     assert got[0][1][0][0] == got[1][1][0][0]        # both ranks hold the same loss bits
+
+
+def _worker_rowblock(rank, world, port, n, out_q):
+    import torch.distributed as dist
+    import multimodal_survival_prediction_b200 as pkg
+    from multimodal_survival_prediction_b200 import dist as bd
+    from multimodal_survival_prediction_b200 import synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    res = {}
+    try:
+        for it, few in enumerate((True, False)):
+            lh, ev, t = synth.cohort(n, 300 + it, few_ties=few)
+            a, b = bd.shard_bounds(n, rank, world)                  # ROW blocks: every rank holds times of the whole range
+            op = bd.RowBlockCoxSorted(b - a, dev).plan(t[a:b].to(dev), ev[a:b].to(dev))
+            grad = torch.empty(b - a, dtype=torch.float32, device=dev)
+            for step in range(2):                                   # the plan is reused: only log_hz travels per step
+                x = (lh[a:b] + 0.25 * step).to(dev)
+                loss = op.forward(x)
+                op.backward(grad)
+            assert op.check() == 0
+            xf = (lh + 0.25).to(dev).requires_grad_(True)
+            l1 = pkg.neg_partial_log_likelihood(xf, ev.to(dev), t.to(dev), "efron", mode="sorted")
+            l1.backward()
+            torch.cuda.synchronize()
+            res[it] = (float(loss), float(l1.detach()), float((grad - xf.grad[a:b]).abs().max()), float(xf.grad.abs().max()),
+                       op.n_recv)
+        out_q.put((rank, res, None))
+    except Exception as ex:  # noqa: BLE001 -- reported to the parent
+        out_q.put((rank, res, repr(ex)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_block_cox_sorted_two_gpus():
+    """Patients sharded by ROW BLOCK (north_star): sample sort on time across the ranks (b200surv_route_rows + all-to-all),
+    then the time-range shard phases.  Loss and each rank's gradient rows equal the single-GPU SORTED result (2e-6)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    n, world = (1 << 19) + 5, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_rowblock, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    total = {0: 0, 1: 0}
+    for rank, res, err in got:
+        assert err is None, f"rank {rank}: {err}"
+        for key, (loss, loss_single, gerr, gmax, n_recv) in res.items():
+            assert abs(loss - loss_single) <= 2e-6 * abs(loss_single), (rank, key, loss, loss_single)
+            assert gerr <= 2e-6 * gmax, (rank, key, gerr, gmax)
+            assert 0.4 * n <= n_recv <= 0.6 * n, (rank, key, n_recv)        # the sample sort balances the ranks
+            total[key] += n_recv
+    assert total[0] == n and total[1] == n

@@ -272,3 +272,42 @@ def test_stage_batch_equals_stage_rna_plus_copies():
             assert torch.equal(d, s_)
         H.stage_batch(rna, b, [])                     # no copies
         assert torch.equal(a, b)
+
+
+def test_skip_missing_ct_flag():
+    """with skip_missing_ct the CT encoder only runs on rows with mask[:, 0] = 1.  Eval mode (running
+    statistics): hazards and gates equal the reference behaviour bit for bit -- the skipped rows' features are multiplied
+    by mask 0 either way.  Training mode: the present rows' features equal the encoder run on exactly those rows (batch
+    statistics over present volumes only), gradients reach the encoder, rows without imaging contribute none."""
+    dev = torch.device("cuda", 0)
+    B = 12
+    torch.manual_seed(11)
+    ref = ghead.PartialModalityNet().to(dev)
+    skp = ghead.PartialModalityNet(skip_missing_ct=True).to(dev)
+    skp.load_state_dict(ref.state_dict())
+    _, rna, clin, mask = [t.to(dev) for t in synth.modality_batch(B, seed=9)]
+    mask[:, 0] = torch.tensor([1, 0, 0, 1, 1, 0, 0, 0, 1, 0, 1, 0], device=dev).float()
+    ct = torch.rand(B, 1, 32, 32, 16, device=dev) * mask[:, 0].view(B, 1, 1, 1, 1)   # the dataset zero-fills missing volumes
+    ref.eval(); skp.eval()
+    with torch.no_grad():
+        h0, g0 = ref(ct, rna, clin, mask)
+        h1, g1 = skp(ct, rna, clin, mask)
+    assert torch.equal(h0, h1) and torch.equal(g0, g1)
+    skp.train()
+    present = torch.nonzero(mask[:, 0] != 0).squeeze(1)
+    enc = ghead.PartialModalityNet().to(dev).train()
+    enc.load_state_dict(ref.state_dict())
+    want = enc._ct_features(ct[present])
+    got = skp._ct_features_present(ct, mask)
+    assert torch.equal(got[present], want)
+    absent = torch.nonzero(mask[:, 0] == 0).squeeze(1)
+    assert float(got[absent].abs().max()) == 0.0
+    hz, _ = skp(ct, rna, clin, mask)
+    hz.sum().backward()
+    gw = skp.ct_encoder[0].weight.grad
+    assert gw is not None and torch.isfinite(gw).all() and float(gw.abs().max()) > 0
+    # all rows present / no row present
+    m1 = mask.clone(); m1[:, 0] = 1
+    assert skp._ct_features_present(ct, m1).shape == (B, 128)
+    m0 = mask.clone(); m0[:, 0] = 0
+    assert float(skp._ct_features_present(ct, m0).abs().max()) == 0.0
