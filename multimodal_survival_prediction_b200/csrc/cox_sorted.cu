@@ -578,14 +578,15 @@ k_tile_scan1(const TileW *__restrict__ tw, int64_t n_tiles_max, const int64_t *_
 #pragma unroll
             for (int k = 0; k < SC_ITEMS; ++k) {
                 const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k);
-                eS[k] = SegN<1>::identity(); eR[k] = SegN<2>::identity(); last[k] = 0;
-                if (q >= 0) {
-                    const TileW *x = tw + q;
-                    const int rowsf = x->rowsf, fl = x->flags;
-                    eS[k].v[0] = x->Wtot; eS[k].flag = (fl & TF_LAST) ? 1 : 0;
-                    eR[k].v[0] = rowsf ? x->Ef : 0.0; eR[k].v[1] = rowsf ? (double)x->mf : 0.0; eR[k].flag = x->nheads > 0;
-                    last[k] = fl & TF_LAST;
-                }
+                // branch-free: every field is loaded from a clamped record and masked afterwards, so that the loads of all
+                // SC_ITEMS records are in flight together (behind `if (q >= 0)` each record cost its own memory round trips)
+                const bool in = q >= 0;
+                const TileW *x = tw + (in ? q : 0);
+                const double Wtot = x->Wtot, Ef = x->Ef;
+                const int mf = x->mf, rowsf = x->rowsf, nheads = x->nheads, fl = x->flags;
+                eS[k].v[0] = in ? Wtot : 0.0; eS[k].flag = (in && (fl & TF_LAST)) ? 1 : 0;
+                eR[k].v[0] = (in && rowsf) ? Ef : 0.0; eR[k].v[1] = (in && rowsf) ? (double)mf : 0.0; eR[k].flag = in && nheads > 0;
+                last[k] = in ? (fl & TF_LAST) : 0;
                 aggS = SegN<1>::combine(aggS, eS[k]); aggR = SegN<2>::combine(aggR, eR[k]);
             }
             SegN<1> stS = SegN<1>::combine(carS, round_prefix<1>(aggS, bufS));
@@ -614,13 +615,13 @@ k_tile_scan1(const TileW *__restrict__ tw, int64_t n_tiles_max, const int64_t *_
 #pragma unroll
             for (int k = 0; k < SC_ITEMS; ++k) {
                 const int64_t q = r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k;
-                e[k] = SegN<4>::identity(); open[k] = 0;
-                if (q < T) {
-                    const TileW *x = tw + q;
-                    e[k].v[0] = x->Wl; e[k].v[1] = x->El; e[k].v[2] = (double)x->ml; e[k].v[3] = (double)x->rowsl;
-                    e[k].flag = x->nheads > 0;
-                    open[k] = x->rowsf > 0 && !(x->flags & TF_FIRST);
-                }
+                const bool in = q < T;
+                const TileW *x = tw + (in ? q : 0);
+                const double Wl = x->Wl, El = x->El;
+                const int ml = x->ml, rowsl = x->rowsl, nheads = x->nheads, rowsf = x->rowsf, fl = x->flags;
+                e[k].v[0] = in ? Wl : 0.0; e[k].v[1] = in ? El : 0.0; e[k].v[2] = in ? (double)ml : 0.0; e[k].v[3] = in ? (double)rowsl : 0.0;
+                e[k].flag = in && nheads > 0;
+                open[k] = in && rowsf > 0 && !(fl & TF_FIRST);
                 agg = SegN<4>::combine(agg, e[k]);
             }
             SegN<4> st = SegN<4>::combine(carL, round_prefix<4>(agg, bufL));
@@ -813,13 +814,12 @@ k_tile_scan2(const TileW *__restrict__ tw, const TileA *__restrict__ ta, int64_t
 #pragma unroll
             for (int k = 0; k < SC_ITEMS; ++k) {
                 const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)t * SC_ITEMS + k);
-                e[k] = SegN<2>::identity(); last[k] = 0;
-                if (q >= 0) {
-                    const TileW *x = tw + q; const TileA *y = ta + q;
-                    const int rowsf = x->rowsf;
-                    e[k].v[0] = rowsf ? y->Af : 0.0; e[k].v[1] = rowsf ? y->Ff : 0.0; e[k].flag = x->nheads > 0;
-                    last[k] = x->flags & TF_LAST;
-                }
+                const bool in = q >= 0;
+                const TileW *x = tw + (in ? q : 0); const TileA *y = ta + (in ? q : 0);
+                const int rowsf = x->rowsf, nheads = x->nheads, fl = x->flags;
+                const double Af = y->Af, Ff = y->Ff;
+                e[k].v[0] = (in && rowsf) ? Af : 0.0; e[k].v[1] = (in && rowsf) ? Ff : 0.0; e[k].flag = in && nheads > 0;
+                last[k] = in ? (fl & TF_LAST) : 0;
                 agg = SegN<2>::combine(agg, e[k]);
             }
             SegN<2> st = SegN<2>::combine(car, round_prefix<2>(agg, buf));
@@ -849,15 +849,14 @@ k_tile_scan2(const TileW *__restrict__ tw, const TileA *__restrict__ ta, int64_t
 #pragma unroll
             for (int k = 0; k < SC_ITEMS; ++k) {
                 const int64_t q = r * SC_ROUND + (int64_t)t * SC_ITEMS + k;
-                e[k] = SegN<4>::identity(); ef[k] = SegN<1>::identity(); fl[k] = 0;
-                if (q < T) {
-                    const TileW *x = tw + q; const TileA *y = ta + q;
-                    const int xf = x->flags;
-                    e[k].v[0] = y->sumA; e[k].v[1] = y->sumL; e[k].v[2] = (double)y->n_times; e[k].v[3] = (double)y->n_ev;
-                    e[k].flag = (xf & TF_FIRST) ? 1 : 0;
-                    ef[k].v[0] = y->Fl; ef[k].flag = x->nheads > 0;
-                    fl[k] = (xf & (TF_FIRST | TF_LAST)) | ((x->rowsf > 0 && !(xf & TF_FIRST)) ? 4 : 0);
-                }
+                const bool in = q < T;
+                const TileW *x = tw + (in ? q : 0); const TileA *y = ta + (in ? q : 0);
+                const int xf = x->flags, nheads = x->nheads, rowsf = x->rowsf, ynt = y->n_times, yne = y->n_ev;
+                const double sumA = y->sumA, sumL = y->sumL, Fl = y->Fl;
+                e[k].v[0] = in ? sumA : 0.0; e[k].v[1] = in ? sumL : 0.0; e[k].v[2] = in ? (double)ynt : 0.0; e[k].v[3] = in ? (double)yne : 0.0;
+                e[k].flag = (in && (xf & TF_FIRST)) ? 1 : 0;
+                ef[k].v[0] = in ? Fl : 0.0; ef[k].flag = in && nheads > 0;
+                fl[k] = in ? ((xf & (TF_FIRST | TF_LAST)) | ((rowsf > 0 && !(xf & TF_FIRST)) ? 4 : 0)) : 0;
                 aggC = SegN<4>::combine(aggC, e[k]); aggF = SegN<1>::combine(aggF, ef[k]);
             }
             SegN<4> stC = SegN<4>::combine(carC, round_prefix<4>(aggC, bufC));

@@ -34,6 +34,9 @@ def close_norm(a, ref, what, tol=TOL, atol=1e-5):
     a, ref = a.detach().double().cpu(), ref.detach().double().cpu()
     nr = ref.norm().item()
     err = (a - ref).norm().item()
+    import os
+    if os.environ.get("B200SURV_TEST_REPORT"):
+        print(f"RELERR {what!r} tol={tol} rel={err / max(nr, 1e-30):.4g} err={err:.3g} nr={nr:.3g} atol={atol:.3g}")
     assert err <= tol * nr + atol, (what, err, nr)
 
 
