@@ -3,12 +3,18 @@
 MultiModalSurvivalNet classes.
 
 Tolerance (north_star: 2e-2, bf16 GEMM path): outputs |d| <= 2e-2 * max|ref| against the full-precision
-oracle.  Gradients are compared per tensor, ||d||_F <= 3e-2 * ||ref||_F, against the oracle evaluated with
+oracle.  Gradients are compared per tensor, ||d||_F <= tol * ||ref||_F, against the oracle evaluated with
 bf16-rounded GEMM operands (oracle/head.py bf16_operands=True): gradients are discontinuous in the
 pre-activations (ReLU and dropout masks), so a handful of sign flips between a bf16 and an fp64 forward
 pass moves the full-precision gradient by several percent without any kernel being wrong; with matching
-operand precision the masks agree and the comparison is tight.  The deviation from the full-precision
-gradient is reported in DESIGN.md."""
+operand precision the masks agree and the comparison is tight:
+  GRAD_TOL_GOLDEN = 2e-2  reference-class golden, rna_dim 40, B = 6          (observed <= 1.6e-2, most tensors <= 4e-3)
+  GRAD_TOL        = 4e-2  rna_dim 5005, B in {4, 300, 4096}, dropout 0.3     (observed <= 3.1e-2: rna_encoder.1.weight,
+                          rna_encoder.0.weight 2.9e-2 -- K = 5005 products of bf16 operands summed in fp32)
+  0.35                    the same golden gradients against the reference's own fp64 autograd values WITHOUT operand
+                          rounding (observed 0.34 for the 3-element gate.2.bias at B = 6, 0.10-0.14 elsewhere): this is
+                          the cost of bf16 operands, recorded, not a kernel tolerance
+(B200SURV_TEST_REPORT=1 prints every tensor's relative error; profiles/r2_v3_head_grad_relerr.txt).  DESIGN.md section 5."""
 import numpy as np
 import pytest
 import torch
@@ -19,7 +25,8 @@ from oracle import head as ohead
 
 pytestmark = pytest.mark.gpu
 TOL = 2e-2
-GRAD_TOL = 6e-2
+GRAD_TOL = 4e-2
+GRAD_TOL_GOLDEN = 2e-2
 
 
 def close(a, ref, what, tol=TOL):
@@ -83,11 +90,11 @@ def test_golden_reference_modules(golden, tag):
     m0 = load_golden_model(g, gated).cpu()
     _, _, p_ref, dct_ref, _ = oracle_run(m0, ct, rna, clin, mask, torch.from_numpy(g["train/hazard_weights"]).float(),
                                          train=True, bf16=True)
-    close_norm(ct.grad, dct_ref, "d ct_feat", tol=GRAD_TOL)
+    close_norm(ct.grad, dct_ref, "d ct_feat", tol=GRAD_TOL_GOLDEN)
     gmax = max(p_ref[k[5:]].grad.norm().item() for k in g.files if k.startswith("grad/"))
     for k in g.files:
         if k.startswith("grad/"):
-            close_norm(params[k[5:]].grad, p_ref[k[5:]].grad, k, tol=GRAD_TOL, atol=1e-3 * gmax)
+            close_norm(params[k[5:]].grad, p_ref[k[5:]].grad, k, tol=GRAD_TOL_GOLDEN, atol=1e-3 * gmax)
             close_norm(params[k[5:]].grad, torch.from_numpy(g[k]), k + " (vs reference fp64, loose)", tol=0.35,
                        atol=1e-3 * gmax)
     sd = m.state_dict()
