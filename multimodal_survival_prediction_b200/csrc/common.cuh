@@ -164,6 +164,28 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint
 }
 
 // write-once 128-bit store, evict-first (st.global.cs): the gradient must not displace the inputs in L2
+// L2 residency hints for kernels that mix a stream with a random gather / scatter over an array that fits the 126 MB L2:
+// the stream is marked evict-first, the gathered / scattered array evict-last, so that the 4-byte random accesses merge in
+// L2 instead of costing one 32-byte DRAM sector each (a partly written sector is a read-modify-write in HBM).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ldg_hint_u32(const void *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ldg_hint_f32(const void *p, uint64_t pol) { return __uint_as_float(ldg_hint_u32(p, pol)); }
+__device__ __forceinline__ void stg_hint_f32(float *p, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void stg_stream_f4(float *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
 #endif  // __CUDACC__
 

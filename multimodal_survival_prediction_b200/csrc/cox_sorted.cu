@@ -21,6 +21,8 @@
 #include <climits>
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "sortscan.cuh"
 
@@ -28,6 +30,7 @@ namespace b200surv {
 namespace {
 
 using sortscan::Tup4;
+namespace cg = cooperative_groups;
 
 struct SegAcc {  // per cohort, device accumulators
     double sum_eta, sum_log;
@@ -99,9 +102,12 @@ k_init_acc(SegAcc *acc, int n_seg) {
 __global__ void __launch_bounds__(256)
 k_make_keys(const float *__restrict__ log_hz, const float *__restrict__ time, const uint8_t *__restrict__ event,
             const int64_t *__restrict__ seg_off, int n_seg, int64_t n, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
-            uint32_t *__restrict__ segid, SegAcc *acc) {
+            uint32_t *__restrict__ segid, SegAcc *acc, unsigned *__restrict__ hist0 /* the sort's first digit totals */) {
     __shared__ float red_f[32];
     __shared__ unsigned red_u[32];
+    __shared__ unsigned s_hist[256];
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
     float mx = -INFINITY, mt = -INFINITY, mn = -INFINITY;
     unsigned flags = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -110,7 +116,11 @@ k_make_keys(const float *__restrict__ log_hz, const float *__restrict__ time, co
         const bool in = i < n;
         const float t = in ? time[i] : 0.f, e = in ? log_hz[i] : -INFINITY;
         const unsigned bad = (in && !(t >= 0.f)) ? B200SURV_COXF_BAD_TIME : 0u;
-        if (in) { keys[i] = time_key(t, event[i] != 0); vals[i] = (uint32_t)i; }
+        if (in) {   // the value of pair i is i: the sort's first pass does not read it
+            const uint32_t key = time_key(t, event[i] != 0);
+            keys[i] = key;
+            atomicAdd(&s_hist[key & 255u], 1u);
+        }
         if (seg_off == nullptr) {
             mx = fmaxf(mx, e); mt = fmaxf(mt, in ? t : -INFINITY); mn = fmaxf(mn, in ? -t : -INFINITY); flags |= bad;
         } else {
@@ -130,6 +140,8 @@ k_make_keys(const float *__restrict__ log_hz, const float *__restrict__ time, co
             }
         }
     }
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&hist0[threadIdx.x], s_hist[threadIdx.x]);
     if (seg_off == nullptr) {
         mx = block_reduce<float>(mx, -INFINITY, OpMaxF(), red_f);
         mt = block_reduce<float>(mt, -INFINITY, OpMaxF(), red_f);
@@ -141,45 +153,6 @@ k_make_keys(const float *__restrict__ log_hz, const float *__restrict__ time, co
             atomic_max_float(&acc->neg_min_time, mn);
             if (flags) atomicOr(&acc->flags, flags);
         }
-    }
-}
-
-// ---- weights in sorted order (a plain element-wise kernel: the two dependent gathers and the fp64 exp need the occupancy
-// a 148-register scan kernel does not have -- fused into the scan's load they cost 240 us per 4M rows at 12 % warp
-// occupancy, ncu r2_segscan); per-cohort sum of the event rows' log_hz and event count ride along
-__global__ void __launch_bounds__(256)
-k_weights(const float *__restrict__ log_hz, const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ idx_s,
-          const int64_t *__restrict__ seg_off, int n_seg, int64_t n, SegAcc *acc, float *__restrict__ w) {
-    __shared__ double red_d[32];
-    __shared__ long long red_l[32];
-    double se = 0.0;
-    long long ne = 0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x, n_round = (n + 31) / 32 * 32;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
-        const bool in = p < n;
-        const int s = in ? seg_of(seg_off, n_seg, p) : -1;
-        const float eta = in ? log_hz[idx_s[p]] : 0.f;
-        const bool d = in && !(keys_s[p] & 1u);
-        if (in) w[p] = (float)exp((double)eta - (double)acc[s].max_eta);
-        if (seg_off == nullptr) {
-            if (d) { se += (double)eta; ne += 1; }
-        } else {  // packed cohorts: one pair of atomics per warp and iteration when its 32 positions share a cohort
-            const int s0 = __shfl_sync(FULL, s, 0);
-            if (__all_sync(FULL, s == s0 || s < 0)) {
-                const double ws = warp_sum(d ? (double)eta : 0.0);
-                const long long wc = warp_sum(d ? 1ll : 0ll);
-                if ((threadIdx.x & 31) == 0 && s0 >= 0 && wc > 0) {
-                    atomicAdd(&acc[s0].sum_eta, ws); atomicAdd(&acc[s0].n_ev, (unsigned long long)wc);
-                }
-            } else if (d) {
-                atomicAdd(&acc[s].sum_eta, (double)eta); atomicAdd(&acc[s].n_ev, 1ull);
-            }
-        }
-    }
-    if (seg_off == nullptr) {
-        se = block_reduce<double>(se, 0.0, OpAddD(), red_d);
-        ne = block_reduce<long long>(ne, 0ll, OpAddLL(), red_l);
-        if (threadIdx.x == 0 && ne > 0) { atomicAdd(&acc->sum_eta, se); atomicAdd(&acc->n_ev, (unsigned long long)ne); }
     }
 }
 
@@ -205,6 +178,13 @@ constexpr int TS_NW = TS_THREADS / 32;
 constexpr int TF_FIRST = 1, TF_LAST = 2;   // first / last tile of its cohort
 constexpr int TS_KN = TS_TILE + 2 + (TS_TILE + 2) / 32 + 2;   // skewed 4-byte array with a halo of two
 constexpr int TS_DN = TS_TILE + TS_TILE / 8;                  // skewed 8-byte array
+constexpr int TG_POOL_BYTES = (2 * TS_DN + (TS_KN + 1) / 2) * 8;   // k_tile_grad: group tables ...
+constexpr int TG_SMEM_BYTES = TG_POOL_BYTES + TS_KN * 4;            // ... + the tile's row indices (skewed)
+__device__ __forceinline__ void cp_async_u32(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all_groups() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct TileW {   // 64 bytes
     double Wtot, Ef, Wl, El;
@@ -362,9 +342,22 @@ constexpr unsigned RF_HEAD = 1, RF_TAIL = 2, RF_EV = 4;
 // keys and weights of the tile through shared memory (coalesced loads at any alignment), then the blocked rows' flags.
 // A tile's first row continues the previous tile's group unless it is a head: equal time bits across the edge.  Rows past
 // the end of a partial tile are neutral (weight 0, no flags).
+// Where a tile's weights come from in the FIRST sweep: w = exp(log_hz - shift) gathered through the permutation and written
+// out in sorted order for the later sweeps (the element-wise k_weights kernel of earlier versions, fused into the tile's
+// loader: one launch, one read of the keys and one write + read of w less).  The cohort's sum of the event rows' log_hz and
+// its event count ride along (eta_sum / n_ev, per thread).
+struct WeightSrc {
+    const float *log_hz;
+    const uint32_t *idx_s;
+    float *w_out;
+    float shift;
+};
+template <bool STREAM = false, bool GATHER = false>
 __device__ __forceinline__ void tile_load(const TileGeo &g, const uint32_t *__restrict__ keys_s, const float *__restrict__ w,
-                                          uint32_t *s_key /*[TS_KN]*/, float *s_w /*[TS_KN]*/, TileRows &R) {
+                                          uint32_t *s_key /*[TS_KN]*/, float *s_w /*[TS_KN]*/, TileRows &R,
+                                          const WeightSrc *src = nullptr, double *eta_sum = nullptr, int *n_ev = nullptr) {
     const int t = threadIdx.x;
+    const uint64_t pol = STREAM ? l2_policy_evict_first() : 0ull;   // last reader of (keys, w): do not displace the scatter target
     // s_key[1 + j] = key of row j; s_key[0] / s_key[rows + 1] = the neighbours across the tile edges.  All loads of a thread
     // are issued before the first store (one memory latency per tile, not one per element).
     uint32_t kk[TS_ITEMS + 1];
@@ -373,14 +366,42 @@ __device__ __forceinline__ void tile_load(const TileGeo &g, const uint32_t *__re
     for (int k = 0; k < TS_ITEMS + 1; ++k) {
         const int j = t + k * TS_THREADS;
         const bool edge = (j == 0 && ((g.flags & TF_FIRST) || (g.halo & 1))) || (j == g.rows + 1 && ((g.flags & TF_LAST) || (g.halo & 2)));
-        kk[k] = (j < g.rows + 2 && !edge) ? keys_s[g.p0 + j - 1] : 0u;
+        kk[k] = (j < g.rows + 2 && !edge) ? (STREAM ? ldg_hint_u32(keys_s + g.p0 + j - 1, pol) : keys_s[g.p0 + j - 1]) : 0u;
         if (j == 0 && (g.halo & 1)) kk[k] = g.key_prev;
         if (j == g.rows + 1 && (g.halo & 2)) kk[k] = g.key_next;
     }
+    if (GATHER) {
+        const uint64_t pol_s = l2_policy_evict_first(), pol_k = l2_policy_evict_last();   // the gather over log_hz stays in L2
+        uint32_t ri[TS_ITEMS], kc[TS_ITEMS];
+        float eta[TS_ITEMS];
 #pragma unroll
-    for (int k = 0; k < TS_ITEMS; ++k) {
-        const int j = t + k * TS_THREADS;
-        ww[k] = j < g.rows ? w[g.p0 + j] : 0.f;
+        for (int k = 0; k < TS_ITEMS; ++k) {
+            const int j = t + k * TS_THREADS;
+            ri[k] = j < g.rows ? ldg_hint_u32(src->idx_s + g.p0 + j, pol_s) : 0u;
+            kc[k] = j < g.rows ? keys_s[g.p0 + j] : 1u;
+        }
+#pragma unroll
+        for (int k = 0; k < TS_ITEMS; ++k) {
+            const int j = t + k * TS_THREADS;
+            eta[k] = j < g.rows ? ldg_hint_f32(src->log_hz + ri[k], pol_k) : 0.f;
+        }
+        double se = 0.0;
+        int ne = 0;
+#pragma unroll
+        for (int k = 0; k < TS_ITEMS; ++k) {
+            const int j = t + k * TS_THREADS;
+            // fp32: the difference of two floats rounds once, expf is good to 1 ulp, and w is kept as fp32 anyway
+            ww[k] = j < g.rows ? expf(eta[k] - src->shift) : 0.f;
+            if (j < g.rows) src->w_out[g.p0 + j] = ww[k];
+            if (!(kc[k] & 1u)) { se += (double)eta[k]; ++ne; }
+        }
+        *eta_sum = se; *n_ev = ne;
+    } else {
+#pragma unroll
+        for (int k = 0; k < TS_ITEMS; ++k) {
+            const int j = t + k * TS_THREADS;
+            ww[k] = j < g.rows ? (STREAM ? ldg_hint_f32(w + g.p0 + j, pol) : w[g.p0 + j]) : 0.f;
+        }
     }
 #pragma unroll
     for (int k = 0; k < TS_ITEMS + 1; ++k) {
@@ -429,19 +450,24 @@ __device__ __forceinline__ double fast_log(double x) {
 }
 
 // first sweep: the tile's total weight and its two fragments, as masked sums (no scan needed yet)
-__global__ void __launch_bounds__(TS_THREADS)
-k_tile_w(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, const int64_t *__restrict__ seg_off,
-         const int64_t *__restrict__ tile_base, int n_seg, int64_t n, const ShardCtx *__restrict__ ctx, TileW *__restrict__ tw) {
+__global__ void __launch_bounds__(TS_THREADS, 5)
+k_tile_w(const float *__restrict__ log_hz, const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ idx_s,
+         float *__restrict__ w, const int64_t *__restrict__ seg_off, const int64_t *__restrict__ tile_base, int n_seg, int64_t n,
+         const ShardCtx *__restrict__ ctx, SegAcc *acc, TileW *__restrict__ tw) {
     __shared__ uint32_t s_key[TS_KN];
     __shared__ float s_w[TS_KN];
     __shared__ int s_hf[TS_NW], s_hl[TS_NW], s_nh[TS_NW];
     __shared__ double s_sum[5][TS_NW];
-    __shared__ int s_cnt[2][TS_NW];
+    __shared__ int s_cnt[3][TS_NW];
     const TileGeo g = tile_geo(blockIdx.x, seg_off, tile_base, n_seg, n, ctx);
     if (!g.valid) return;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     TileRows R;
-    tile_load(g, keys_s, w, s_key, s_w, R);
+    WeightSrc src;
+    src.log_hz = log_hz; src.idx_s = idx_s; src.w_out = w; src.shift = acc[g.seg].max_eta;
+    double se;
+    int ne;
+    tile_load<false, true>(g, keys_s, nullptr, s_key, s_w, R, &src, &se, &ne);
     int hf = INT_MAX, hl = -1, nh = 0;
 #pragma unroll
     for (int k = 0; k < TS_ITEMS; ++k)
@@ -456,7 +482,7 @@ k_tile_w(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, const
 #pragma unroll
     for (int q = 0; q < TS_NW; ++q) { first = min(first, s_hf[q]); last = max(last, s_hl[q]); nheads += s_nh[q]; }
     if (!nheads) { first = g.rows; last = 0; }   // no head: both fragments are the whole tile
-    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};     // Wtot, Ef, Wl, El
+    double v[5] = {0.0, 0.0, 0.0, 0.0, se};      // Wtot, Ef, Wl, El; the event rows' log_hz
     int mf = 0, ml = 0;
 #pragma unroll
     for (int k = 0; k < TS_ITEMS; ++k) {
@@ -468,21 +494,22 @@ k_tile_w(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, const
         if (j >= last) { v[2] += wk; v[3] += ek; ml += dk; }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = warp_sum(v[i]);
-    mf = (int)warp_sum((long long)mf); ml = (int)warp_sum((long long)ml);
+    for (int i = 0; i < 5; ++i) v[i] = warp_sum(v[i]);
+    mf = (int)warp_sum((long long)mf); ml = (int)warp_sum((long long)ml); ne = (int)warp_sum((long long)ne);
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s_sum[i][warp] = v[i];
-        s_cnt[0][warp] = mf; s_cnt[1][warp] = ml;
+        for (int i = 0; i < 5; ++i) s_sum[i][warp] = v[i];
+        s_cnt[0][warp] = mf; s_cnt[1][warp] = ml; s_cnt[2][warp] = ne;
     }
     __syncthreads();
     if (t == 0) {
-        double r[4] = {0.0, 0.0, 0.0, 0.0};
-        int cf = 0, cl = 0;
+        double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        int cf = 0, cl = 0, ce = 0;
         for (int q = 0; q < TS_NW; ++q) {
-            for (int i = 0; i < 4; ++i) r[i] += s_sum[i][q];
-            cf += s_cnt[0][q]; cl += s_cnt[1][q];
+            for (int i = 0; i < 5; ++i) r[i] += s_sum[i][q];
+            cf += s_cnt[0][q]; cl += s_cnt[1][q]; ce += s_cnt[2][q];
         }
+        if (ce > 0) { atomicAdd(&acc[g.seg].sum_eta, r[4]); atomicAdd(&acc[g.seg].n_ev, (unsigned long long)ce); }
         TileW o;
         o.Wtot = r[0]; o.Ef = r[1]; o.Wl = r[2]; o.El = r[3]; o.mf = cf; o.ml = cl;
         o.rowsf = first; o.rowsl = g.rows - last; o.nheads = nheads; o.flags = g.flags; o.pad0 = 0; o.pad1 = 0;
@@ -555,93 +582,140 @@ __device__ __forceinline__ SegN<N> round_prefix(const SegN<N> &e, SegN<N> *s_war
 // A round covers SC_THREADS * SC_ITEMS tiles: every thread folds SC_ITEMS consecutive tiles (in scan order) on its own, one
 // block-wide prefix per round joins the threads, a carry joins the rounds.  pos = position in scan order; a reverse scan
 // visits tile T - 1 - pos.
-constexpr int SC_ITEMS = 8, SC_ROUND = SC_THREADS * SC_ITEMS;
+// One CTA per direction was bound by what ONE SM can keep in flight (512 KB of tile records per scan at 16.7M rows: 50 us,
+// ncu r2_v3).  Each direction is now a CLUSTER of SC_CLUSTER CTAs: CTA k of the cluster takes a contiguous run of rounds,
+// walks it twice -- first for its total only, then, after the totals have met through distributed shared memory, with the
+// fold of the earlier CTAs' totals as carry-in (the second walk reads from L1 / L2).
+constexpr int SC_ITEMS = 2, SC_ROUND = SC_THREADS * SC_ITEMS, SC_CLUSTER = 8;
 
-// grid = 2: CTA 0 scans the tiles in reverse (S, R), CTA 1 forward (L)
-__global__ void __launch_bounds__(SC_THREADS)
+struct ScanRange { int64_t r0, r1; };
+__device__ __forceinline__ ScanRange scan_range(int64_t T, unsigned rank) {
+    const int64_t rounds = (T + SC_ROUND - 1) / SC_ROUND, per = (rounds + SC_CLUSTER - 1) / SC_CLUSTER;
+    ScanRange g;
+    g.r0 = (int64_t)rank * per < rounds ? (int64_t)rank * per : rounds;
+    g.r1 = g.r0 + per < rounds ? g.r0 + per : rounds;
+    return g;
+}
+// total of this CTA's rounds -> fold of the totals of the cluster's earlier CTAs (identical in every thread).
+// s_x[0]: this CTA's total, read by the later CTAs; s_x[1]: the fold.  The caller ends with one more cluster.sync().
+template <typename S>
+__device__ __forceinline__ S cluster_carry(cg::cluster_group &cl, const S &total, S *s_x /*[2]*/) {
+    if (threadIdx.x == 0) s_x[0] = total;
+    cl.sync();
+    if (threadIdx.x == 0) {
+        S c = S::identity();
+        const unsigned me = cl.block_rank();
+        for (unsigned k = 0; k < me; ++k) c = S::combine(c, *cl.map_shared_rank(&s_x[0], k));
+        s_x[1] = c;
+    }
+    __syncthreads();
+    return s_x[1];
+}
+
+// grid = 2 clusters: cluster 0 scans the tiles in reverse (S, R), cluster 1 forward (L)
+__global__ void __cluster_dims__(SC_CLUSTER, 1, 1) __launch_bounds__(SC_THREADS)
 k_tile_scan1(const TileW *__restrict__ tw, int64_t n_tiles_max, const int64_t *__restrict__ tile_base, int n_seg,
              TileC1 *__restrict__ c1, ShardRec1 *__restrict__ rec /* shards: the folded sequence, else nullptr */) {
-    __shared__ SegN<1> bufS[33];
-    __shared__ SegN<2> bufR[33];
-    __shared__ SegN<4> bufL[33];
+    __shared__ SegN<1> bufS[33], xS[2];
+    __shared__ SegN<2> bufR[33], xR[2];
+    __shared__ SegN<4> bufL[33], xL[2];
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned rank = cl.block_rank();
     const int64_t T = tile_base ? tile_base[n_seg] : n_tiles_max;
-    const int64_t rounds = (T + SC_ROUND - 1) / SC_ROUND;
-    if (blockIdx.x == 0) {   // reverse: S (restart at a cohort's last tile), chain of first fragments (E, m)
+    const ScanRange rg = scan_range(T, rank);
+    if (blockIdx.x < SC_CLUSTER) {   // reverse: S (restart at a cohort's last tile), chain of first fragments (E, m)
         SegN<1> carS = SegN<1>::identity();
         SegN<2> carR = SegN<2>::identity();
-        for (int64_t r = 0; r < rounds; ++r) {
-            SegN<1> eS[SC_ITEMS];
-            SegN<2> eR[SC_ITEMS];
-            int last[SC_ITEMS];
-            SegN<1> aggS = SegN<1>::identity();
-            SegN<2> aggR = SegN<2>::identity();
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+            for (int64_t r = rg.r0; r < rg.r1; ++r) {
+                SegN<1> eS[SC_ITEMS];
+                SegN<2> eR[SC_ITEMS];
+                int last[SC_ITEMS];
+                SegN<1> aggS = SegN<1>::identity();
+                SegN<2> aggR = SegN<2>::identity();
 #pragma unroll
-            for (int k = 0; k < SC_ITEMS; ++k) {
-                const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k);
-                // branch-free: every field is loaded from a clamped record and masked afterwards, so that the loads of all
-                // SC_ITEMS records are in flight together (behind `if (q >= 0)` each record cost its own memory round trips)
-                const bool in = q >= 0;
-                const TileW *x = tw + (in ? q : 0);
-                const double Wtot = x->Wtot, Ef = x->Ef;
-                const int mf = x->mf, rowsf = x->rowsf, nheads = x->nheads, fl = x->flags;
-                eS[k].v[0] = in ? Wtot : 0.0; eS[k].flag = (in && (fl & TF_LAST)) ? 1 : 0;
-                eR[k].v[0] = (in && rowsf) ? Ef : 0.0; eR[k].v[1] = (in && rowsf) ? (double)mf : 0.0; eR[k].flag = in && nheads > 0;
-                last[k] = in ? (fl & TF_LAST) : 0;
-                aggS = SegN<1>::combine(aggS, eS[k]); aggR = SegN<2>::combine(aggR, eR[k]);
-            }
-            SegN<1> stS = SegN<1>::combine(carS, round_prefix<1>(aggS, bufS));
-            SegN<2> stR = SegN<2>::combine(carR, round_prefix<2>(aggR, bufR));
-#pragma unroll
-            for (int k = 0; k < SC_ITEMS; ++k) {
-                const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k);
-                if (q >= 0) {
-                    TileC1 *o = c1 + q;
-                    o->S = last[k] ? 0.0 : stS.v[0];
-                    o->RE = last[k] ? 0.0 : stR.v[0];
-                    o->Rm = last[k] ? 0 : (int)(stR.v[1] + 0.5);
-                    if (rec != nullptr && !last[k] && !stR.flag) atomicOr(&o->cf, 1);   // the forward CTA owns bit 1 of the same word
+                for (int k = 0; k < SC_ITEMS; ++k) {
+                    const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k);
+                    // branch-free: every field is loaded from a clamped record and masked afterwards, so that the loads of all
+                    // SC_ITEMS records are in flight together
+                    const bool in = q >= 0;
+                    const TileW *x = tw + (in ? q : 0);
+                    const double Wtot = x->Wtot, Ef = x->Ef;
+                    const int mf = x->mf, rowsf = x->rowsf, nheads = x->nheads, fl = x->flags;
+                    eS[k].v[0] = in ? Wtot : 0.0; eS[k].flag = (in && (fl & TF_LAST)) ? 1 : 0;
+                    eR[k].v[0] = (in && rowsf) ? Ef : 0.0; eR[k].v[1] = (in && rowsf) ? (double)mf : 0.0; eR[k].flag = in && nheads > 0;
+                    last[k] = in ? (fl & TF_LAST) : 0;
+                    aggS = SegN<1>::combine(aggS, eS[k]); aggR = SegN<2>::combine(aggR, eR[k]);
                 }
-                stS = SegN<1>::combine(stS, eS[k]); stR = SegN<2>::combine(stR, eR[k]);
+                SegN<1> stS = SegN<1>::combine(carS, round_prefix<1>(aggS, bufS));
+                SegN<2> stR = SegN<2>::combine(carR, round_prefix<2>(aggR, bufR));
+                if (phase) {
+#pragma unroll
+                    for (int k = 0; k < SC_ITEMS; ++k) {
+                        const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k);
+                        if (q >= 0) {
+                            TileC1 *o = c1 + q;
+                            o->S = last[k] ? 0.0 : stS.v[0];
+                            o->RE = last[k] ? 0.0 : stR.v[0];
+                            o->Rm = last[k] ? 0 : (int)(stR.v[1] + 0.5);
+                            if (rec != nullptr && !last[k] && !stR.flag) atomicOr(&o->cf, 1);   // the forward cluster owns bit 1 of the same word
+                        }
+                        stS = SegN<1>::combine(stS, eS[k]); stR = SegN<2>::combine(stR, eR[k]);
+                    }
+                }
+                carS = SegN<1>::combine(carS, bufS[32]); carR = SegN<2>::combine(carR, bufR[32]);
             }
-            carS = SegN<1>::combine(carS, bufS[32]); carR = SegN<2>::combine(carR, bufR[32]);
+            if (phase == 0) { carS = cluster_carry(cl, carS, xS); carR = cluster_carry(cl, carR, xR); }
         }
-        if (rec != nullptr && threadIdx.x == 0) { rec->W = carS.v[0]; rec->RE = carR.v[0]; rec->Rm = carR.v[1]; rec->Rflag = carR.flag; rec->pad0 = 0; }
+        if (rec != nullptr && rank == SC_CLUSTER - 1 && threadIdx.x == 0) {
+            rec->W = carS.v[0]; rec->RE = carR.v[0]; rec->Rm = carR.v[1]; rec->Rflag = carR.flag; rec->pad0 = 0;
+        }
     } else {                 // forward: chain of last fragments (W, E, m, rows)
         SegN<4> carL = SegN<4>::identity();
-        for (int64_t r = 0; r < rounds; ++r) {
-            SegN<4> e[SC_ITEMS];
-            int open[SC_ITEMS];
-            SegN<4> agg = SegN<4>::identity();
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+            for (int64_t r = rg.r0; r < rg.r1; ++r) {
+                SegN<4> e[SC_ITEMS];
+                int open[SC_ITEMS];
+                SegN<4> agg = SegN<4>::identity();
 #pragma unroll
-            for (int k = 0; k < SC_ITEMS; ++k) {
-                const int64_t q = r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k;
-                const bool in = q < T;
-                const TileW *x = tw + (in ? q : 0);
-                const double Wl = x->Wl, El = x->El;
-                const int ml = x->ml, rowsl = x->rowsl, nheads = x->nheads, rowsf = x->rowsf, fl = x->flags;
-                e[k].v[0] = in ? Wl : 0.0; e[k].v[1] = in ? El : 0.0; e[k].v[2] = in ? (double)ml : 0.0; e[k].v[3] = in ? (double)rowsl : 0.0;
-                e[k].flag = in && nheads > 0;
-                open[k] = in && rowsf > 0 && !(fl & TF_FIRST);
-                agg = SegN<4>::combine(agg, e[k]);
-            }
-            SegN<4> st = SegN<4>::combine(carL, round_prefix<4>(agg, bufL));
-#pragma unroll
-            for (int k = 0; k < SC_ITEMS; ++k) {
-                const int64_t q = r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k;
-                if (q < T) {
-                    TileC1 *o = c1 + q;
-                    o->LW = open[k] ? st.v[0] : 0.0; o->LE = open[k] ? st.v[1] : 0.0;
-                    o->Lm = open[k] ? (int)(st.v[2] + 0.5) : 0; o->Lrows = open[k] ? (int)(st.v[3] + 0.5) : 0;
-                    if (rec != nullptr && open[k] && !st.flag) atomicOr(&o->cf, 2);
+                for (int k = 0; k < SC_ITEMS; ++k) {
+                    const int64_t q = r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k;
+                    const bool in = q < T;
+                    const TileW *x = tw + (in ? q : 0);
+                    const double Wl = x->Wl, El = x->El;
+                    const int ml = x->ml, rowsl = x->rowsl, nheads = x->nheads, rowsf = x->rowsf, fl = x->flags;
+                    e[k].v[0] = in ? Wl : 0.0; e[k].v[1] = in ? El : 0.0; e[k].v[2] = in ? (double)ml : 0.0; e[k].v[3] = in ? (double)rowsl : 0.0;
+                    e[k].flag = in && nheads > 0;
+                    open[k] = in && rowsf > 0 && !(fl & TF_FIRST);
+                    agg = SegN<4>::combine(agg, e[k]);
                 }
-                st = SegN<4>::combine(st, e[k]);
+                SegN<4> st = SegN<4>::combine(carL, round_prefix<4>(agg, bufL));
+                if (phase) {
+#pragma unroll
+                    for (int k = 0; k < SC_ITEMS; ++k) {
+                        const int64_t q = r * SC_ROUND + (int64_t)threadIdx.x * SC_ITEMS + k;
+                        if (q < T) {
+                            TileC1 *o = c1 + q;
+                            o->LW = open[k] ? st.v[0] : 0.0; o->LE = open[k] ? st.v[1] : 0.0;
+                            o->Lm = open[k] ? (int)(st.v[2] + 0.5) : 0; o->Lrows = open[k] ? (int)(st.v[3] + 0.5) : 0;
+                            if (rec != nullptr && open[k] && !st.flag) atomicOr(&o->cf, 2);
+                        }
+                        st = SegN<4>::combine(st, e[k]);
+                    }
+                }
+                carL = SegN<4>::combine(carL, bufL[32]);
             }
-            carL = SegN<4>::combine(carL, bufL[32]);
+            if (phase == 0) carL = cluster_carry(cl, carL, xL);
         }
-        if (rec != nullptr && threadIdx.x == 0) {
+        if (rec != nullptr && rank == SC_CLUSTER - 1 && threadIdx.x == 0) {
             rec->LW = carL.v[0]; rec->LE = carL.v[1]; rec->Lm = carL.v[2]; rec->Lrows = carL.v[3]; rec->Lflag = carL.flag; rec->pad1 = 0;
         }
     }
+    cl.sync();   // no CTA leaves while a later one may still read its total
 }
 
 // shards: a tile's shard-local scan values plus what the other shards contribute (k_shard_ctx1 / k_shard_finish)
@@ -731,7 +805,7 @@ __device__ __forceinline__ void tile_terms(const TileGeo &g, const TileRows &R, 
     }
 }
 
-__global__ void __launch_bounds__(TS_THREADS, 3)
+__global__ void __launch_bounds__(TS_THREADS, 4)
 k_tile_terms(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, const int64_t *__restrict__ seg_off,
              const int64_t *__restrict__ tile_base, int n_seg, int64_t n, const TileW *__restrict__ tws,
              const TileC1 *__restrict__ c1, int efron, const ShardCtx *__restrict__ ctx, TileA *__restrict__ ta) {
@@ -793,102 +867,122 @@ k_tile_terms(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, c
     }
 }
 
-// second tile scan + per-cohort loss / scale / header.  grid = 2: CTA 0 reverse (AR, FR), CTA 1 forward (C, FL, loss).
-__global__ void __launch_bounds__(SC_THREADS)
+// second tile scan + per-cohort loss / scale / header.  grid = 2 clusters: cluster 0 reverse (AR, FR), cluster 1 forward
+// (C, FL, loss).
+__global__ void __cluster_dims__(SC_CLUSTER, 1, 1) __launch_bounds__(SC_THREADS)
 k_tile_scan2(const TileW *__restrict__ tw, const TileA *__restrict__ ta, int64_t n_tiles_max, const int64_t *__restrict__ tile_base,
              const int64_t *__restrict__ seg_off, int n_seg, int64_t n, int ties, int reduction, SegAcc *acc,
              TileC2 *__restrict__ c2, float *__restrict__ out_loss, b200surv_cox_header *__restrict__ hdrs,
              ShardRec2 *__restrict__ rec /* shards: the folded sequence (loss and header come from k_shard_finish), else nullptr */) {
-    __shared__ SegN<2> buf[33];
-    __shared__ SegN<4> bufC[33];
-    __shared__ SegN<1> bufF[33];
+    __shared__ SegN<2> buf[33], xA[2];
+    __shared__ SegN<4> bufC[33], xC[2];
+    __shared__ SegN<1> bufF[33], xF[2];
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned rank = cl.block_rank();
     const int64_t T = tile_base ? tile_base[n_seg] : n_tiles_max;
-    const int64_t rounds = (T + SC_ROUND - 1) / SC_ROUND;
+    const ScanRange rg = scan_range(T, rank);
     const int t = threadIdx.x;
-    if (blockIdx.x == 0) {   // reverse: chain of first fragments (A, F)
+    if (blockIdx.x < SC_CLUSTER) {   // reverse: chain of first fragments (A, F)
         SegN<2> car = SegN<2>::identity();
-        for (int64_t r = 0; r < rounds; ++r) {
-            SegN<2> e[SC_ITEMS];
-            int last[SC_ITEMS];
-            SegN<2> agg = SegN<2>::identity();
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+            for (int64_t r = rg.r0; r < rg.r1; ++r) {
+                SegN<2> e[SC_ITEMS];
+                int last[SC_ITEMS];
+                SegN<2> agg = SegN<2>::identity();
 #pragma unroll
-            for (int k = 0; k < SC_ITEMS; ++k) {
-                const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)t * SC_ITEMS + k);
-                const bool in = q >= 0;
-                const TileW *x = tw + (in ? q : 0); const TileA *y = ta + (in ? q : 0);
-                const int rowsf = x->rowsf, nheads = x->nheads, fl = x->flags;
-                const double Af = y->Af, Ff = y->Ff;
-                e[k].v[0] = (in && rowsf) ? Af : 0.0; e[k].v[1] = (in && rowsf) ? Ff : 0.0; e[k].flag = in && nheads > 0;
-                last[k] = in ? (fl & TF_LAST) : 0;
-                agg = SegN<2>::combine(agg, e[k]);
-            }
-            SegN<2> st = SegN<2>::combine(car, round_prefix<2>(agg, buf));
-#pragma unroll
-            for (int k = 0; k < SC_ITEMS; ++k) {
-                const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)t * SC_ITEMS + k);
-                if (q >= 0) {
-                    c2[q].AR = last[k] ? 0.0 : st.v[0]; c2[q].FR = last[k] ? 0.0 : st.v[1];
-                    c2[q].cr = (!last[k] && !st.flag) ? 1 : 0;
+                for (int k = 0; k < SC_ITEMS; ++k) {
+                    const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)t * SC_ITEMS + k);
+                    const bool in = q >= 0;
+                    const TileW *x = tw + (in ? q : 0); const TileA *y = ta + (in ? q : 0);
+                    const int rowsf = x->rowsf, nheads = x->nheads, fl = x->flags;
+                    const double Af = y->Af, Ff = y->Ff;
+                    e[k].v[0] = (in && rowsf) ? Af : 0.0; e[k].v[1] = (in && rowsf) ? Ff : 0.0; e[k].flag = in && nheads > 0;
+                    last[k] = in ? (fl & TF_LAST) : 0;
+                    agg = SegN<2>::combine(agg, e[k]);
                 }
-                st = SegN<2>::combine(st, e[k]);
+                SegN<2> st = SegN<2>::combine(car, round_prefix<2>(agg, buf));
+                if (phase) {
+#pragma unroll
+                    for (int k = 0; k < SC_ITEMS; ++k) {
+                        const int64_t q = T - 1 - (r * SC_ROUND + (int64_t)t * SC_ITEMS + k);
+                        if (q >= 0) {
+                            c2[q].AR = last[k] ? 0.0 : st.v[0]; c2[q].FR = last[k] ? 0.0 : st.v[1];
+                            c2[q].cr = (!last[k] && !st.flag) ? 1 : 0;
+                        }
+                        st = SegN<2>::combine(st, e[k]);
+                    }
+                }
+                car = SegN<2>::combine(car, buf[32]);
             }
-            car = SegN<2>::combine(car, buf[32]);
+            if (phase == 0) car = cluster_carry(cl, car, xA);
         }
-        if (rec != nullptr && t == 0) { rec->AR = car.v[0]; rec->FR = car.v[1]; rec->ARflag = car.flag; rec->pad0 = 0; }
+        if (rec != nullptr && rank == SC_CLUSTER - 1 && t == 0) { rec->AR = car.v[0]; rec->FR = car.v[1]; rec->ARflag = car.flag; rec->pad0 = 0; }
+        cl.sync();
         return;
     }
     {   // forward: C and the cohort's loss sums (restart at a cohort's first tile); chain of last fragments (F)
         SegN<4> carC = SegN<4>::identity();
         SegN<1> carF = SegN<1>::identity();
-        for (int64_t r = 0; r < rounds; ++r) {
-            SegN<4> e[SC_ITEMS];
-            SegN<1> ef[SC_ITEMS];
-            int fl[SC_ITEMS];   // bit 0: first tile of a cohort, 1: last, 2: the first row continues an earlier tile's group
-            SegN<4> aggC = SegN<4>::identity();
-            SegN<1> aggF = SegN<1>::identity();
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+            for (int64_t r = rg.r0; r < rg.r1; ++r) {
+                SegN<4> e[SC_ITEMS];
+                SegN<1> ef[SC_ITEMS];
+                int fl[SC_ITEMS];   // bit 0: first tile of a cohort, 1: last, 2: the first row continues an earlier tile's group
+                SegN<4> aggC = SegN<4>::identity();
+                SegN<1> aggF = SegN<1>::identity();
 #pragma unroll
-            for (int k = 0; k < SC_ITEMS; ++k) {
-                const int64_t q = r * SC_ROUND + (int64_t)t * SC_ITEMS + k;
-                const bool in = q < T;
-                const TileW *x = tw + (in ? q : 0); const TileA *y = ta + (in ? q : 0);
-                const int xf = x->flags, nheads = x->nheads, rowsf = x->rowsf, ynt = y->n_times, yne = y->n_ev;
-                const double sumA = y->sumA, sumL = y->sumL, Fl = y->Fl;
-                e[k].v[0] = in ? sumA : 0.0; e[k].v[1] = in ? sumL : 0.0; e[k].v[2] = in ? (double)ynt : 0.0; e[k].v[3] = in ? (double)yne : 0.0;
-                e[k].flag = (in && (xf & TF_FIRST)) ? 1 : 0;
-                ef[k].v[0] = in ? Fl : 0.0; ef[k].flag = in && nheads > 0;
-                fl[k] = in ? ((xf & (TF_FIRST | TF_LAST)) | ((rowsf > 0 && !(xf & TF_FIRST)) ? 4 : 0)) : 0;
-                aggC = SegN<4>::combine(aggC, e[k]); aggF = SegN<1>::combine(aggF, ef[k]);
-            }
-            SegN<4> stC = SegN<4>::combine(carC, round_prefix<4>(aggC, bufC));
-            SegN<1> stF = SegN<1>::combine(carF, round_prefix<1>(aggF, bufF));
+                for (int k = 0; k < SC_ITEMS; ++k) {
+                    const int64_t q = r * SC_ROUND + (int64_t)t * SC_ITEMS + k;
+                    const bool in = q < T;
+                    const TileW *x = tw + (in ? q : 0); const TileA *y = ta + (in ? q : 0);
+                    const int xf = x->flags, nheads = x->nheads, rowsf = x->rowsf, ynt = y->n_times, yne = y->n_ev;
+                    const double sumA = y->sumA, sumL = y->sumL, Fl = y->Fl;
+                    e[k].v[0] = in ? sumA : 0.0; e[k].v[1] = in ? sumL : 0.0; e[k].v[2] = in ? (double)ynt : 0.0; e[k].v[3] = in ? (double)yne : 0.0;
+                    e[k].flag = (in && (xf & TF_FIRST)) ? 1 : 0;
+                    ef[k].v[0] = in ? Fl : 0.0; ef[k].flag = in && nheads > 0;
+                    fl[k] = in ? ((xf & (TF_FIRST | TF_LAST)) | ((rowsf > 0 && !(xf & TF_FIRST)) ? 4 : 0)) : 0;
+                    aggC = SegN<4>::combine(aggC, e[k]); aggF = SegN<1>::combine(aggF, ef[k]);
+                }
+                SegN<4> stC = SegN<4>::combine(carC, round_prefix<4>(aggC, bufC));
+                SegN<1> stF = SegN<1>::combine(carF, round_prefix<1>(aggF, bufF));
+                if (phase) {
 #pragma unroll
-            for (int k = 0; k < SC_ITEMS; ++k) {
-                const int64_t q = r * SC_ROUND + (int64_t)t * SC_ITEMS + k;
-                if (q < T) {
-                    c2[q].C = (fl[k] & TF_FIRST) ? 0.0 : stC.v[0];
-                    c2[q].FL = (fl[k] & 4) ? stF.v[0] : 0.0;
-                    c2[q].cfw = ((fl[k] & 4) && !stF.flag) ? 1 : 0;
+                    for (int k = 0; k < SC_ITEMS; ++k) {
+                        const int64_t q = r * SC_ROUND + (int64_t)t * SC_ITEMS + k;
+                        if (q < T) {
+                            c2[q].C = (fl[k] & TF_FIRST) ? 0.0 : stC.v[0];
+                            c2[q].FL = (fl[k] & 4) ? stF.v[0] : 0.0;
+                            c2[q].cfw = ((fl[k] & 4) && !stF.flag) ? 1 : 0;
+                        }
+                        stC = SegN<4>::combine(stC, e[k]); stF = SegN<1>::combine(stF, ef[k]);
+                        if (rec == nullptr && q < T && (fl[k] & TF_LAST)) {   // the cohort's totals are complete: its sums of log-denominators / event times
+                            const TileGeo g = tile_geo(q, seg_off, tile_base, n_seg, n);
+                            acc[g.seg].sum_log = stC.v[1];
+                            acc[g.seg].n_times = (unsigned long long)(stC.v[2] + 0.5);
+                        }
+                    }
                 }
-                stC = SegN<4>::combine(stC, e[k]); stF = SegN<1>::combine(stF, ef[k]);
-                if (rec == nullptr && q < T && (fl[k] & TF_LAST)) {   // the cohort's totals are complete: its sums of log-denominators / event times
-                    const TileGeo g = tile_geo(q, seg_off, tile_base, n_seg, n);
-                    acc[g.seg].sum_log = stC.v[1];
-                    acc[g.seg].n_times = (unsigned long long)(stC.v[2] + 0.5);
-                }
+                carC = SegN<4>::combine(carC, bufC[32]); carF = SegN<1>::combine(carF, bufF[32]);
             }
-            carC = SegN<4>::combine(carC, bufC[32]); carF = SegN<1>::combine(carF, bufF[32]);
+            if (phase == 0) { carC = cluster_carry(cl, carC, xC); carF = cluster_carry(cl, carF, xF); }
         }
         if (rec != nullptr) {
-            if (t == 0) {
+            if (rank == SC_CLUSTER - 1 && t == 0) {
                 rec->A = carC.v[0]; rec->sum_log = carC.v[1]; rec->n_times = (long long)(carC.v[2] + 0.5);
                 rec->n_ev = (long long)acc->n_ev; rec->sum_eta = acc->sum_eta;
                 rec->FL = carF.v[0]; rec->FLflag = carF.flag; rec->flags = acc->flags;
             }
+            cl.sync();
             return;
         }
     }
-    __syncthreads();
-    for (int s = t; s < n_seg; s += SC_THREADS) {
+    __threadfence();
+    cl.sync();   // every cohort's sum_log / n_times is written (and no CTA leaves while its total may still be read)
+    for (int s = t + (int)rank * SC_THREADS; s < n_seg; s += SC_THREADS * SC_CLUSTER) {
         SegAcc &A = acc[s];
         // sum_log holds the logs of the SHIFTED denominators: log sum w e^{shift} = log sum w + shift
         const double pll = A.sum_eta - (A.sum_log + (double)A.n_ev * (double)A.max_eta);
@@ -914,7 +1008,11 @@ k_tile_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ id
             const int64_t *__restrict__ seg_off, const int64_t *__restrict__ tile_base, int n_seg, int64_t n,
             const TileW *__restrict__ tws, const TileC1 *__restrict__ c1, const TileC2 *__restrict__ c2, int efron,
             const SegAcc *__restrict__ acc, const ShardCtx *__restrict__ ctx, float *__restrict__ grad_unit) {
-    __shared__ double s_pool[2 * TS_DN + (TS_KN + 1) / 2];
+    // dynamic: the group tables (as in k_tile_terms) and the tile's row indices, fetched with cp.async at the start so that
+    // the scatter at the end does not wait for them (the loads used to sit behind the last scan: 40 % long-scoreboard stalls)
+    extern __shared__ __align__(16) unsigned char tg_dyn[];
+    double *s_pool = reinterpret_cast<double *>(tg_dyn);
+    uint32_t *s_idx = reinterpret_cast<uint32_t *>(tg_dyn + TG_POOL_BYTES);
     double *s_D = s_pool, *s_E = s_pool + TS_DN;
     int *s_m = reinterpret_cast<int *>(s_pool + 2 * TS_DN);
     uint32_t *s_key = reinterpret_cast<uint32_t *>(s_pool);
@@ -931,8 +1029,14 @@ k_tile_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ id
     shard_fix(c, ctx);
     shard_fix(cc, ctx);
     const double scale = acc[g.seg].scale;
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        const int j = t + k * TS_THREADS;
+        if (j < g.rows) cp_async_u32(smem_addr_u32(&s_idx[sk4(j)]), idx_s + g.p0 + j);
+    }
+    cp_async_commit_group();
     TileRows R;
-    tile_load(g, keys_s, w, s_key, s_w, R);
+    tile_load<true>(g, keys_s, w, s_key, s_w, R);
     TileTerms X;
     double sl;
     tile_terms<false>(g, R, tw, c, efron, s_D, s_E, s_m, s_rev, s_max, X, sl);
@@ -951,12 +1055,8 @@ k_tile_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ id
         const int j = t * TS_ITEMS + k;
         if (j < g.rows) { s_D[sk(j)] = run.A; s_E[sk(j)] = run.F; }   // (P, F) at every row
     }
-    uint32_t ridx[TS_ITEMS];   // the rows' original positions
-#pragma unroll
-    for (int k = 0; k < TS_ITEMS; ++k) {
-        const int j = t * TS_ITEMS + k;
-        ridx[k] = j < g.rows ? idx_s[g.p0 + j] : 0u;
-    }
+    const uint64_t pol_keep = l2_policy_evict_last();
+    cp_async_wait_all_groups();
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < TS_ITEMS; ++k) {
@@ -968,7 +1068,7 @@ k_tile_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ id
             const double Fg = s_E[sk(e)] + (open ? cc.FR : 0.0) + (X.gs[k] < 0 ? cc.FL : 0.0);
             const double d = (R.flg[k] & RF_EV) ? 1.0 : 0.0;
             const double gr = d - (double)R.w[k] * (PQ - d * Fg);
-            grad_unit[ridx[k]] = (float)(scale * gr);
+            stg_hint_f32(grad_unit + s_idx[sk4(j)], (float)(scale * gr), pol_keep);   // 4-byte scatter over n rows: merged in L2
         }
     }
 }
@@ -1090,6 +1190,16 @@ SortedLayout sorted_layout(int64_t n, int64_t n_seg) {
 
 size_t cox_sorted_workspace_bytes(int64_t n, int64_t n_seg) { return sorted_layout(n, n_seg < 1 ? 1 : n_seg).total; }
 
+// k_tile_grad needs more than 48 KB of (dynamic) shared memory: opt in once per device
+static int32_t tile_grad_prepare() {
+    static PerDeviceOnce once;
+    if (once.pending()) {
+        B200_CHECK_CUDA(cudaFuncSetAttribute(k_tile_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES));
+        once.mark();
+    }
+    return B200SURV_OK;
+}
+
 int32_t cox_sorted_fwd_launch(const float *log_hz, const float *time, const uint8_t *event, const int64_t *seg_off, int64_t n,
                               int64_t n_seg, int ties, int reduction, float *out_loss, void *state, size_t state_bytes,
                               void *ws, size_t ws_bytes, cudaStream_t st) {
@@ -1133,26 +1243,31 @@ int32_t cox_sorted_fwd_launch(const float *log_hz, const float *time, const uint
     mark();
     k_init_acc<<<(nseg + 255) / 256, 256, 0, st>>>(acc, nseg);
     // keys are generated into (keys_s, idx_s); radix_sort_pairs2 reports which buffer pair holds the result
-    k_make_keys<<<grid, 256, 0, st>>>(log_hz, time, event, seg_off, nseg, n, keys_s, idx_s, segid, acc);
+    unsigned *hist0 = nullptr;   // the key kernel counts the sort's first digit while it has the keys in registers
+    rc = sortscan::radix_sort_prepare(n, tmp, st, &hist0);
+    if (rc) return rc;
+    k_make_keys<<<grid, 256, 0, st>>>(log_hz, time, event, seg_off, nseg, n, keys_s, idx_s, segid, acc, hist0);
     mark();
     const int seg_bits = n_seg == 1 ? 0 : (n_seg <= 256 ? 8 : 16);
     int in_first = 1;
-    rc = sortscan::radix_sort_pairs2(keys_s, idx_s, keys, vals, n, 32, n_seg > 1 ? segid : nullptr, seg_bits, tmp, st, &in_first);
+    rc = sortscan::radix_sort_pairs2(keys_s, idx_s, keys, vals, n, 32, n_seg > 1 ? segid : nullptr, seg_bits, tmp, st, &in_first, true,
+                                     true);
     if (rc) return rc;
     mark();
     const uint32_t *ks = in_first ? keys_s : keys, *is = in_first ? idx_s : vals;
-    k_weights<<<grid, 256, 0, st>>>(log_hz, ks, is, seg_off, nseg, n, acc, wv);
     mark();
     if (seg_off) k_tile_base<<<1, 1024, 0, st>>>(seg_off, nseg, tbase);
-    k_tile_w<<<tiles, TS_THREADS, 0, st>>>(ks, wv, seg_off, tbase, nseg, n, nullptr, tw);
+    k_tile_w<<<tiles, TS_THREADS, 0, st>>>(log_hz, ks, is, wv, seg_off, tbase, nseg, n, nullptr, acc, tw);
     mark();
-    k_tile_scan1<<<2, SC_THREADS, 0, st>>>(tw, L.tiles_max, tbase, nseg, c1, nullptr);
+    k_tile_scan1<<<2 * SC_CLUSTER, SC_THREADS, 0, st>>>(tw, L.tiles_max, tbase, nseg, c1, nullptr);
     mark();
     k_tile_terms<<<tiles, TS_THREADS, 0, st>>>(ks, wv, seg_off, tbase, nseg, n, tw, c1, efron, nullptr, ta);
     mark();
-    k_tile_scan2<<<2, SC_THREADS, 0, st>>>(tw, ta, L.tiles_max, tbase, seg_off, nseg, n, ties, reduction, acc, c2, out_loss, hdrs, nullptr);
+    k_tile_scan2<<<2 * SC_CLUSTER, SC_THREADS, 0, st>>>(tw, ta, L.tiles_max, tbase, seg_off, nseg, n, ties, reduction, acc, c2, out_loss, hdrs, nullptr);
     mark();
-    k_tile_grad<<<tiles, TS_THREADS, 0, st>>>(ks, is, wv, seg_off, tbase, nseg, n, tw, c1, c2, efron, acc, nullptr, grad_unit);
+    rc = tile_grad_prepare();
+    if (rc) return rc;
+    k_tile_grad<<<tiles, TS_THREADS, TG_SMEM_BYTES, st>>>(ks, is, wv, seg_off, tbase, nseg, n, tw, c1, c2, efron, acc, nullptr, grad_unit);
     mark();
     if (trace) {
         static const char *names[] = {"keys", "sort", "weights", "tile_w", "scan1", "terms", "scan2", "grad"};
@@ -1167,7 +1282,7 @@ int32_t cox_sorted_fwd_launch(const float *log_hz, const float *time, const uint
         for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
     }
     B200_CHECK_CUDA(cudaGetLastError());
-    count_launches(2 + 4 * (4 + seg_bits / 8) + 1 + (seg_off ? 1 : 0) + 5);
+    count_launches(2 + (4 + seg_bits / 8) + (seg_off ? 1 : 0) + 5);   // acc, keys (+ first digit totals); one sweep per digit; tile kernels
     return B200SURV_OK;
 }
 
@@ -1214,7 +1329,10 @@ int32_t cox_sorted_shard_keys(const float *log_hz, const float *time, const uint
     int32_t rc = shard_ptrs(n, ws, ws_bytes, P);
     if (rc) return rc;
     k_init_acc<<<1, 256, 0, st>>>(P.acc, 1);
-    k_make_keys<<<P.grid, 256, 0, st>>>(log_hz, time, event, nullptr, 1, n, P.keys_s, P.idx_s, nullptr, P.acc);
+    unsigned *hist0 = nullptr;
+    rc = sortscan::radix_sort_prepare(n, P.tmp, st, &hist0);
+    if (rc) return rc;
+    k_make_keys<<<P.grid, 256, 0, st>>>(log_hz, time, event, nullptr, 1, n, P.keys_s, P.idx_s, nullptr, P.acc, hist0);
     k_shard_rec0<<<1, 32, 0, st>>>(P.acc, n, static_cast<ShardRec0 *>(rec0_out));
     B200_CHECK_CUDA(cudaGetLastError());
     count_launches(3);
@@ -1226,10 +1344,10 @@ int32_t cox_sorted_shard_sort(int64_t n, void *ws, size_t ws_bytes, cudaStream_t
     int32_t rc = shard_ptrs(n, ws, ws_bytes, P);
     if (rc) return rc;
     int in_first = 1;
-    rc = sortscan::radix_sort_pairs2(P.keys_s, P.idx_s, P.keys, P.vals, n, 32, nullptr, 0, P.tmp, st, &in_first);
+    rc = sortscan::radix_sort_pairs2(P.keys_s, P.idx_s, P.keys, P.vals, n, 32, nullptr, 0, P.tmp, st, &in_first, true, true);
     if (rc) return rc;
     if (in_first != SHARD_IN_FIRST) { set_error("cox sorted shard: unexpected sort buffer parity"); return B200SURV_UNSUPPORTED; }
-    count_launches(16);
+    count_launches(4);   // one sweep per digit
     return B200SURV_OK;
 }
 
@@ -1240,12 +1358,11 @@ int32_t cox_sorted_shard_reduce(const float *log_hz, int64_t n, const void *all_
     int32_t rc = shard_ptrs(n, ws, ws_bytes, P);
     if (rc) return rc;
     k_shard_ctx0<<<1, 32, 0, st>>>(all_rec0, rank, world, P.acc, P.ctx);
-    k_weights<<<P.grid, 256, 0, st>>>(log_hz, P.keys_s, P.idx_s, nullptr, 1, n, P.acc, P.wv);
-    k_tile_w<<<P.tiles, TS_THREADS, 0, st>>>(P.keys_s, P.wv, nullptr, nullptr, 1, n, P.ctx, P.tw);
+    k_tile_w<<<P.tiles, TS_THREADS, 0, st>>>(log_hz, P.keys_s, P.idx_s, P.wv, nullptr, nullptr, 1, n, P.ctx, P.acc, P.tw);
     B200_CHECK_CUDA(cudaMemsetAsync(P.c1, 0, (size_t)P.L.tiles_max * sizeof(TileC1), st));   // the carry bits are OR-ed in
-    k_tile_scan1<<<2, SC_THREADS, 0, st>>>(P.tw, P.L.tiles_max, nullptr, 1, P.c1, static_cast<ShardRec1 *>(rec1_out));
+    k_tile_scan1<<<2 * SC_CLUSTER, SC_THREADS, 0, st>>>(P.tw, P.L.tiles_max, nullptr, 1, P.c1, static_cast<ShardRec1 *>(rec1_out));
     B200_CHECK_CUDA(cudaGetLastError());
-    count_launches(4);
+    count_launches(3);
     return B200SURV_OK;
 }
 
@@ -1259,7 +1376,7 @@ int32_t cox_sorted_shard_terms(int64_t n, int ties, const void *all_rec1, int ra
     const int efron = ties == B200SURV_TIES_EFRON ? 1 : 0;
     k_shard_ctx1<<<1, 32, 0, st>>>(all_rec1, rank, world, P.ctx);
     k_tile_terms<<<P.tiles, TS_THREADS, 0, st>>>(P.keys_s, P.wv, nullptr, nullptr, 1, n, P.tw, P.c1, efron, P.ctx, P.ta);
-    k_tile_scan2<<<2, SC_THREADS, 0, st>>>(P.tw, P.ta, P.L.tiles_max, nullptr, nullptr, 1, n, ties, 0, P.acc, P.c2, nullptr, nullptr,
+    k_tile_scan2<<<2 * SC_CLUSTER, SC_THREADS, 0, st>>>(P.tw, P.ta, P.L.tiles_max, nullptr, nullptr, 1, n, ties, 0, P.acc, P.c2, nullptr, nullptr,
                                            static_cast<ShardRec2 *>(rec2_out));
     B200_CHECK_CUDA(cudaGetLastError());
     count_launches(3);
@@ -1279,8 +1396,10 @@ int32_t cox_sorted_shard_finish(int64_t n, int ties, int reduction, const void *
     b200surv_cox_header *hdr = static_cast<b200surv_cox_header *>(state);
     float *grad_unit = reinterpret_cast<float *>(hdr + 1);
     const int efron = ties == B200SURV_TIES_EFRON ? 1 : 0;
+    rc = tile_grad_prepare();
+    if (rc) return rc;
     k_shard_finish<<<1, 32, 0, st>>>(all_rec2, rank, world, ties, reduction, P.acc, P.ctx, out_loss, hdr);
-    k_tile_grad<<<P.tiles, TS_THREADS, 0, st>>>(P.keys_s, P.idx_s, P.wv, nullptr, nullptr, 1, n, P.tw, P.c1, P.c2, efron, P.acc, P.ctx,
+    k_tile_grad<<<P.tiles, TS_THREADS, TG_SMEM_BYTES, st>>>(P.keys_s, P.idx_s, P.wv, nullptr, nullptr, 1, n, P.tw, P.c1, P.c2, efron, P.acc, P.ctx,
                                                 grad_unit);
     B200_CHECK_CUDA(cudaGetLastError());
     count_launches(2);

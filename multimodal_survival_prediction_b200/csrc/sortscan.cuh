@@ -11,6 +11,7 @@
 // They replace cub::DeviceScan / cub::DeviceRadixSort in cox_sorted.cu and cindex.cu.
 #pragma once
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -650,8 +651,8 @@ k_os_hist(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, 
 template <bool VIA_VAL>
 static __global__ void __launch_bounds__(OS_THREADS, 3)
 k_onesweep(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t n, DigitFn cur, DigitFn nxt, int count_next,
-           const unsigned *__restrict__ hist_cur, unsigned *__restrict__ hist_nxt, unsigned long long *state, unsigned *ticket,
-           uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+           const unsigned *__restrict__ hist_cur, unsigned *__restrict__ hist_nxt, unsigned long long *state,
+           unsigned long long *state_next, unsigned *ticket, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
     __shared__ unsigned s_cnt[OS_WARPS][256];   // per warp: count of each digit, then its start inside the digit's run
     __shared__ uint32_t s_k[OS_TILE], s_v[OS_TILE];
     __shared__ int s_start[256];                // first staged position of each digit
@@ -723,6 +724,7 @@ k_onesweep(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
 #pragma unroll
     for (int w = 0; w < OS_WARPS; ++w) { const unsigned c = s_cnt[w][t]; s_cnt[w][t] = run; run += c; }
     unsigned long long *slot = state + (size_t)tile * 256 + t;
+    state_next[(size_t)tile * 256 + t] = 0ull;   // the next pass's look-back words (its kernel starts after this one ends)
     if (tile > 0) scan_st(slot, (1ull << 62) | run);
     // the first window of the look-back is requested now and examined after the staging (its latency hides behind it)
     constexpr int LBW = 4;
@@ -806,8 +808,187 @@ k_onesweep(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
     if (count_next && s_next[t]) atomicAdd(&hist_nxt[t], s_next[t]);
 }
 
+// The same pass when both digits (this pass's and the next one's) are bits of the KEY and n < 2^31: the common case (every
+// pass of a single cohort / of the C-index; all but the last passes of packed cohorts).  k_onesweep above is issue-bound at
+// ~220 SASS instructions per pair (ncu r2_v3: 115 M warp instructions per pass at 16.7M pairs); here the per-pair work is
+// 32-bit throughout: no bounds tests on full tiles (a partial tile pads with key 0xffffffff -- the pads rank last in digit
+// 255 and are taken out of the published count), one 8-byte staged word per pair, 32-bit run offsets modulo 2^32.
+// lanes whose bit b of d DIFFERS from this lane's: ballot and one predicated complement.  PTX, so that the eight bit tests
+// of a digit become one R2P (the C form `m &= bit ? bal : ~bal` compiles to five or six instructions per bit).
+__device__ __forceinline__ unsigned os_mismatch_bit(unsigned d, int b) {
+    unsigned x;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.b32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+        "@p not.b32 %0, %0;\n\t}"
+        : "=r"(x) : "r"(d), "r"(1u << b));
+    return x;
+}
+// lanes of the warp whose low 8 bits of d equal this lane's (three-input ORs: 8 + 8 + 4 instructions and the R2P)
+__device__ __forceinline__ unsigned os_match8(unsigned d) {
+    const unsigned x0 = os_mismatch_bit(d, 0), x1 = os_mismatch_bit(d, 1), x2 = os_mismatch_bit(d, 2), x3 = os_mismatch_bit(d, 3),
+                   x4 = os_mismatch_bit(d, 4), x5 = os_mismatch_bit(d, 5), x6 = os_mismatch_bit(d, 6), x7 = os_mismatch_bit(d, 7);
+    const unsigned a = x0 | x1 | x2, b = x3 | x4 | x5, c = x6 | x7 | a;
+    return ~(b | c);
+}
+template <int MINB>
+static __global__ void __launch_bounds__(OS_THREADS, MINB)
+k_onesweep_key(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, unsigned n, int shift, int shift_next,
+               int count_next, const unsigned *__restrict__ hist_cur, unsigned *__restrict__ hist_nxt, unsigned long long *state,
+               unsigned long long *state_next, unsigned *ticket, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+    __shared__ unsigned s_cnt[OS_WARPS][256];   // per warp: count of each digit, then staged start of the warp's run
+    __shared__ uint32_t s_k[OS_TILE], s_v[OS_TILE];
+    __shared__ unsigned s_goff[256];            // global position minus staged position of a digit's run (mod 2^32)
+    __shared__ unsigned s_next[256];
+    __shared__ unsigned s_wt[2][OS_WARPS];
+    __shared__ unsigned s_tile;
+    const unsigned t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    if (t == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int w = 0; w < OS_WARPS; ++w) s_cnt[w][t] = 0;
+    s_next[t] = 0;
+    __syncthreads();
+    const unsigned tile = s_tile, tbase = tile * OS_TILE, wbase = tbase + warp * (OS_ITEMS * 32) + lane;
+    const unsigned cnt = n - tbase < (unsigned)OS_TILE ? n - tbase : (unsigned)OS_TILE;
+    const bool full = cnt == (unsigned)OS_TILE;
+    uint32_t k[OS_ITEMS];
+    if (full) {
+        const uint32_t *kp = keys + wbase;
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) k[r] = kp[r * 32];
+    } else {
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) k[r] = wbase + r * 32 < n ? keys[wbase + r * 32] : 0xffffffffu;
+    }
+    // ranking: lanes of a round with the same digit form a group (one ballot per digit bit); the group's first lane adds the
+    // group to the warp's running count (shared atomics of one warp execute in program order) and hands the old value on
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned peers[OS_ITEMS], rank[OS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        peers[r] = os_match8(k[r] >> shift);
+    }
+    unsigned *my_cnt = &s_cnt[warp][0];
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        rank[r] = 0;
+        if ((peers[r] & lt) == 0) rank[r] = atomicAdd(my_cnt + ((k[r] >> shift) & 255u), (unsigned)__popc(peers[r]));
+    }
+    if (count_next) {
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) atomicAdd(&s_next[(k[r] >> shift_next) & 255u], 1u);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r)
+        rank[r] = __shfl_sync(FULL, rank[r], __ffs(peers[r]) - 1) + __popc(peers[r] & lt);
+    __syncthreads();
+    // digit t: per-warp counts -> the tile's count (published at once), staged starts of the runs
+    unsigned c[OS_WARPS], run = 0;
+#pragma unroll
+    for (int w = 0; w < OS_WARPS; ++w) { c[w] = run; run += s_cnt[w][t]; }
+    const unsigned pads = (unsigned)OS_TILE - cnt;          // all in digit 255, behind the real pairs
+    const unsigned run_pub = t == 255u ? run - pads : run;
+    unsigned long long *slot = state + (size_t)tile * 256 + t;
+    state_next[(size_t)tile * 256 + t] = 0ull;   // the next pass's look-back words (its kernel starts after this one ends)
+    if (tile > 0) scan_st(slot, (1ull << 62) | run_pub);
+    constexpr int LBW = 4;
+    unsigned long long win[LBW];
+    int q = (int)tile - 1;
+#pragma unroll
+    for (int j = 0; j < LBW; ++j) win[j] = q - j >= 0 ? scan_ld(state + (size_t)(q - j) * 256 + t) : (2ull << 62);
+    unsigned gbase, start;
+    {
+        unsigned inc_c = run, inc_h = hist_cur[t];
+        const unsigned h = inc_h;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned uc = __shfl_up_sync(FULL, inc_c, d), uh = __shfl_up_sync(FULL, inc_h, d);
+            if (lane >= (unsigned)d) { inc_c += uc; inc_h += uh; }
+        }
+        if (lane == 31u) { s_wt[0][warp] = inc_c; s_wt[1][warp] = inc_h; }
+        __syncthreads();
+        unsigned pre_c = 0, pre_h = 0;
+#pragma unroll
+        for (int w = 0; w < OS_WARPS; ++w) { pre_c += ((unsigned)w < warp) ? s_wt[0][w] : 0u; pre_h += ((unsigned)w < warp) ? s_wt[1][w] : 0u; }
+        start = pre_c + inc_c - run;
+        gbase = pre_h + inc_h - h;
+    }
+#pragma unroll
+    for (int w = 0; w < OS_WARPS; ++w) s_cnt[w][t] = start + c[w];
+    __syncthreads();
+    // keys into their staged places; the values are loaded only now (the keys' registers are free) and land after the
+    // look-back, which hides their latency
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        rank[r] += my_cnt[(k[r] >> shift) & 255u];
+        s_k[rank[r]] = k[r];
+    }
+    uint32_t v[OS_ITEMS];
+    if (vals == nullptr) {
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) v[r] = wbase + r * 32;
+    } else if (full) {
+        const uint32_t *vp = vals + wbase;
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) v[r] = vp[r * 32];
+    } else {
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) v[r] = wbase + r * 32 < n ? vals[wbase + r * 32] : 0u;
+    }
+    {   // look back over the earlier tiles' words for this digit, LBW words per round trip
+        unsigned excl = 0;
+        bool done = q < 0;
+        while (!done) {
+            int used = 0;
+#pragma unroll
+            for (int j = 0; j < LBW; ++j) {
+                const unsigned fl = (unsigned)(win[j] >> 62);
+                if (!done && used == j && fl != 0) {
+                    excl += (unsigned)win[j]; ++used;
+                    if (fl == 2) done = true;
+                }
+            }
+            q -= used;
+            if (q < 0) done = true;
+            if (!done) {
+#pragma unroll
+                for (int j = 0; j < LBW; ++j) win[j] = q - j >= 0 ? scan_ld(state + (size_t)(q - j) * 256 + t) : (2ull << 62);
+            }
+        }
+        scan_st(slot, (2ull << 62) | (unsigned long long)(excl + run_pub));
+        s_goff[t] = gbase + excl - start;
+    }
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r) s_v[rank[r]] = v[r];
+    __syncthreads();
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < OS_ITEMS; ++i) {
+            const unsigned p = t + i * OS_THREADS;
+            const uint32_t key = s_k[p];
+            const unsigned dst = s_goff[(key >> shift) & 255u] + p;
+            keys_out[dst] = key;
+            vals_out[dst] = s_v[p];
+        }
+    } else {
+        for (unsigned p = t; p < cnt; p += OS_THREADS) {
+            const uint32_t key = s_k[p];
+            const unsigned dst = s_goff[(key >> shift) & 255u] + p;
+            keys_out[dst] = key;
+            vals_out[dst] = s_v[p];
+        }
+    }
+    if (count_next) {
+        const unsigned cn = (t == ((0xffffffffu >> shift_next) & 255u)) ? s_next[t] - pads : s_next[t];
+        if (cn) atomicAdd(&hist_nxt[t], cn);
+    }
+}
+
 struct OsLayout {
-    size_t off_hist, off_ticket, off_state, total;
+    size_t off_hist, off_ticket, off_state, off_state2, total;
     int ntiles;
 };
 inline OsLayout os_layout(int64_t n) {
@@ -818,7 +999,8 @@ inline OsLayout os_layout(int64_t n) {
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     L.off_hist = take((size_t)OS_MAX_PASSES * 256 * sizeof(unsigned));
     L.off_ticket = take((size_t)OS_MAX_PASSES * sizeof(unsigned));
-    L.off_state = take((size_t)L.ntiles * 256 * sizeof(unsigned long long));
+    L.off_state = take((size_t)L.ntiles * 256 * sizeof(unsigned long long));    // look-back words of the even passes ...
+    L.off_state2 = take((size_t)L.ntiles * 256 * sizeof(unsigned long long));   // ... and of the odd ones (each pass zeroes the other set)
     L.total = o;
     return L;
 }
@@ -830,13 +1012,18 @@ inline size_t radix_sort_temp_bytes(int64_t n) { return os_layout(n).total; }
 // vals_in == nullptr: the value of pair i is i (nothing is read for the first pass).  keys_in / vals_in are overwritten
 // (ping-pong; vals_in must still be a buffer of n values); the result is in keys_in / vals_in when the TOTAL number of
 // passes is even, else in keys_out / vals_out: the function returns which through *in_first (1 = keys_in / vals_in).
+// The producer of the keys may count the first pass's digits itself (low 8 bits of the key) and save the sort one read of the
+// keys: radix_sort_prepare() zeroes the sort's counters and returns the 256 totals to add into; the sort is then called
+// with first_hist_done = true.
+inline int32_t radix_sort_prepare(int64_t n, void *temp, cudaStream_t st, unsigned **hist0);
 inline int32_t radix_sort_pairs2(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n, int end_bit,
                                  const uint32_t *seg_table, int seg_bits, void *temp, cudaStream_t st, int *in_first,
-                                 bool vals_are_iota = false) {
+                                 bool vals_are_iota = false, bool first_hist_done = false) {
     const OsLayout L = os_layout(n);
     unsigned char *t8 = static_cast<unsigned char *>(temp);
     unsigned *hist = reinterpret_cast<unsigned *>(t8 + L.off_hist), *ticket = reinterpret_cast<unsigned *>(t8 + L.off_ticket);
-    unsigned long long *state = reinterpret_cast<unsigned long long *>(t8 + L.off_state);
+    unsigned long long *state_ab[2] = {reinterpret_cast<unsigned long long *>(t8 + L.off_state),
+                                       reinterpret_cast<unsigned long long *>(t8 + L.off_state2)};
     DigitFn fn[OS_MAX_PASSES + 1];
     int passes = 0;
     for (int shift = 0; shift < end_bit; shift += 8) fn[passes++] = DigitFn{nullptr, shift};
@@ -845,28 +1032,44 @@ inline int32_t radix_sort_pairs2(uint32_t *keys_in, uint32_t *vals_in, uint32_t 
     if (passes > OS_MAX_PASSES) { set_error("radix sort: %d passes > %d", passes, OS_MAX_PASSES); return B200SURV_BAD_ARG; }
     *in_first = (passes % 2 == 0) ? 1 : 0;
     if (n <= 0 || passes == 0) return B200SURV_OK;
-    B200_CHECK_CUDA(cudaMemsetAsync(t8 + L.off_hist, 0, L.off_state - L.off_hist, st));   // digit totals and tickets
-    int hg = (int)((n + 255) / 256);
-    if (hg > 8 * num_sms()) hg = 8 * num_sms();
-    const uint32_t *va0 = vals_are_iota ? nullptr : vals_in;
-    k_os_hist<<<hg, 256, 0, st>>>(keys_in, va0, n, fn[0], hist);
+    if (!first_hist_done) {
+        B200_CHECK_CUDA(cudaMemsetAsync(t8 + L.off_hist, 0, L.off_state2 - L.off_hist, st));   // digit totals, tickets, first pass's look-back words
+        int hg = (int)((n + 255) / 256);
+        if (hg > 8 * num_sms()) hg = 8 * num_sms();
+        const uint32_t *va0 = vals_are_iota ? nullptr : vals_in;
+        k_os_hist<<<hg, 256, 0, st>>>(keys_in, va0, n, fn[0], hist);
+    }
     uint32_t *ka = keys_in, *va = vals_in, *kb = keys_out, *vb = vals_out;
     for (int p = 0; p < passes; ++p) {
-        B200_CHECK_CUDA(cudaMemsetAsync(state, 0, (size_t)L.ntiles * 256 * sizeof(unsigned long long), st));
+        unsigned long long *state = state_ab[p & 1], *state_next = state_ab[(p + 1) & 1];
         const bool has_next = p + 1 < passes;
         const DigitFn nxt = has_next ? fn[p + 1] : DigitFn{nullptr, 0};
         const uint32_t *vsrc = (p == 0 && vals_are_iota) ? nullptr : va;
         const bool via_val = fn[p].table != nullptr || (has_next && nxt.table != nullptr);
         if (via_val)
             k_onesweep<true><<<L.ntiles, OS_THREADS, 0, st>>>(ka, vsrc, n, fn[p], nxt, has_next ? 1 : 0, hist + p * 256,
-                                                              hist + (p + 1) * 256, state, ticket + p, kb, vb);
+                                                              hist + (p + 1) * 256, state, state_next, ticket + p, kb, vb);
+        else if (n < (1ll << 31)) {
+            static const int minb = [] { const char *e = getenv("B200SURV_OS_MINB"); return e ? atoi(e) : 3; }();
+            auto kern = minb == 2 ? k_onesweep_key<2> : (minb == 4 ? k_onesweep_key<4> : k_onesweep_key<3>);
+            kern<<<L.ntiles, OS_THREADS, 0, st>>>(ka, vsrc, (unsigned)n, fn[p].shift, nxt.shift, has_next ? 1 : 0, hist + p * 256,
+                                                  hist + (p + 1) * 256, state, state_next, ticket + p, kb, vb);
+        }
         else
             k_onesweep<false><<<L.ntiles, OS_THREADS, 0, st>>>(ka, vsrc, n, fn[p], nxt, has_next ? 1 : 0, hist + p * 256,
-                                                               hist + (p + 1) * 256, state, ticket + p, kb, vb);
+                                                               hist + (p + 1) * 256, state, state_next, ticket + p, kb, vb);
         uint32_t *tk = ka; ka = kb; kb = tk;
         uint32_t *tv = va; va = vb; vb = tv;
     }
     B200_CHECK_CUDA(cudaGetLastError());
+    return B200SURV_OK;
+}
+
+inline int32_t radix_sort_prepare(int64_t n, void *temp, cudaStream_t st, unsigned **hist0) {
+    const OsLayout L = os_layout(n);
+    unsigned char *t8 = static_cast<unsigned char *>(temp);
+    B200_CHECK_CUDA(cudaMemsetAsync(t8 + L.off_hist, 0, L.off_state2 - L.off_hist, st));
+    *hist0 = reinterpret_cast<unsigned *>(t8 + L.off_hist);
     return B200SURV_OK;
 }
 
