@@ -10,12 +10,13 @@
 //   a_p = 1 / (D - (l/m) E), f_p = (l/m) a_p;  P = sum of a over the cohort's rows up to ge - 1;  F = the group's sum of f;
 //   grad = scale * (d - w (P - d F)).
 // Launch sequence (all hand-written):
-//   keys    (time bits, censored bit) and the row index; per-cohort max log_hz (the exponent shift), flags
-//   sort    stable LSD radix sort (csrc/sortscan.cuh), 4 passes of 8 bits on the key (+ 1-2 passes on the cohort id for
-//           packed cohorts)
-//   weights w = exp(log_hz - shift) gathered through the permutation, as fp32 in sorted order
-//   tiles   reduce-then-scan over tiles of 2048 sorted rows (see "tile kernels" below): three sweeps over (key, w) and two
-//           single-CTA scans over the per-tile records; the last sweep scatters the gradient through the permutation
+//   keys    (time bits, censored bit); per-cohort max log_hz (the exponent shift), flags; the totals of the sort's first digit
+//   sort    stable LSD radix sort (csrc/sortscan.cuh), 4 one-sweep passes of 8 bits on the key (+ 1-2 passes on the cohort
+//           id for packed cohorts); the value of pair i is i, so the first pass reads no values
+//   tiles   reduce-then-scan over tiles of 2048 sorted rows (see "tile kernels" below): the first sweep gathers
+//           w = exp(log_hz - shift) through the permutation (kept as fp32 in sorted order), the second leaves per row what
+//           of the gradient is known inside the tile, the third is element-wise and scatters the gradient through the
+//           permutation; between them two scans over the per-tile records (one 8-CTA cluster per direction)
 // Every group sum is a SEGMENTED sum of the group's own terms -- never a difference of two running totals: with hazards
 // spread over tens of nats a late group's weights are 1e-15 of the total and a difference would be rounding noise.
 #include <climits>
@@ -160,14 +161,18 @@ k_make_keys(const float *__restrict__ log_hz, const float *__restrict__ time, co
 // Risk-set sums, Efron terms, loss and gradient as REDUCE-THEN-SCAN over tiles of 2048 sorted rows: no look-back chain and
 // no per-row fp64 intermediate in HBM.  A tile never crosses a cohort.  Tie groups that cross tile boundaries are handled
 // through per-tile FRAGMENT records (rows before the tile's first group head / from its last head on) chained by the two
-// single-CTA tile scans:
-//   k_tile_w      per tile: total weight, the two fragments' (weight, event weight, event count, rows)          [reads 8 B/row]
+// tile scans (one cluster of 8 CTAs per direction):
+//   k_tile_w      per tile: w gathered and stored; total weight, the two fragments' (weight, event weight, event count,
+//                 rows); the cohort's sum of event log_hz and event count                [12 B/row + the gather, 4 B/row written]
 //   k_tile_scan1  over tiles: S = weight of the cohort's later tiles; R = (E, m) of the rows AFTER the tile that belong to
 //                 its last row's group; L = (W, E, m, rows) of the rows BEFORE the tile that belong to its first row's group
-//   k_tile_terms  per tile: every group's (D, E, m) -> a_p, f_p, log-denominators; tile sums and fragment sums   [8 B/row]
+//   k_tile_terms  per tile: every group's (D, E, m) -> a_p, f_p, log-denominators; in-tile prefix P and group sums F; tile
+//                 sums and fragment sums (read off the same forward scan); per row g0 = d - w (P - d F) at its group's end
+//                 inside the tile and three flag bits                                            [8 B/row read, 5 B/row written]
 //   k_tile_scan2  over tiles: C = sum of a over the cohort's earlier tiles; AR, FR / FL = the open groups' sums of a, f in
-//                 later / earlier tiles; per-cohort loss, scale and header (the old k_loss)
-//   k_tile_grad   per tile: terms again, P at each group's end, gradient scattered through the permutation  [12 B/row + scatter]
+//                 later / earlier tiles; per-cohort loss, scale and header
+//   k_tile_apply  element-wise: grad = scale (g0 - w (C + [open] AR) + w d ([open] FR + [began earlier] FL)), scattered
+//                 through the permutation with L2 evict-last stores                              [13 B/row + the scatter]
 // Inside a tile the work is three block-wide scans over a blocked arrangement (8 consecutive rows per thread): reverse
 // (suffix weight; group-suffix event weight / count restarting at group tails; nearest tail), forward max (group start),
 // forward (prefix of a; group-prefix of f restarting at heads); group values reach their rows through shared memory.
@@ -178,13 +183,6 @@ constexpr int TS_NW = TS_THREADS / 32;
 constexpr int TF_FIRST = 1, TF_LAST = 2;   // first / last tile of its cohort
 constexpr int TS_KN = TS_TILE + 2 + (TS_TILE + 2) / 32 + 2;   // skewed 4-byte array with a halo of two
 constexpr int TS_DN = TS_TILE + TS_TILE / 8;                  // skewed 8-byte array
-constexpr int TG_POOL_BYTES = (2 * TS_DN + (TS_KN + 1) / 2) * 8;   // k_tile_grad: group tables ...
-constexpr int TG_SMEM_BYTES = TG_POOL_BYTES + TS_KN * 4;            // ... + the tile's row indices (skewed)
-__device__ __forceinline__ void cp_async_u32(uint32_t dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all_groups() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct TileW {   // 64 bytes
     double Wtot, Ef, Wl, El;
@@ -313,18 +311,19 @@ struct MaxT {   // forward max scan of head positions (-1: none)
     static __device__ __forceinline__ MaxT combine(const MaxT &x, const MaxT &y) { MaxT r; r.h = max(x.h, y.h); return r; }
     __device__ __forceinline__ MaxT shfl(int src) const { MaxT r; r.h = __shfl_sync(FULL, h, src); return r; }
 };
-struct FwdT {   // forward scan: A = prefix of a; F = group-prefix of f (restart at heads)
-    double A, F;
+struct FwdT {   // forward scan: A = prefix of a; As, F = group-prefixes of a, f (restart at heads)
+    double A, As, F;
     int head;
-    static __device__ __forceinline__ FwdT identity() { FwdT r; r.A = 0.0; r.F = 0.0; r.head = 0; return r; }
+    static __device__ __forceinline__ FwdT identity() { FwdT r; r.A = 0.0; r.As = 0.0; r.F = 0.0; r.head = 0; return r; }
     static __device__ __forceinline__ FwdT combine(const FwdT &x, const FwdT &y) {
         FwdT r;
-        r.A = x.A + y.A; r.F = y.head ? y.F : x.F + y.F; r.head = x.head | y.head;
+        r.A = x.A + y.A; r.As = y.head ? y.As : x.As + y.As; r.F = y.head ? y.F : x.F + y.F; r.head = x.head | y.head;
         return r;
     }
     __device__ __forceinline__ FwdT shfl(int src) const {
         FwdT r;
-        r.A = __shfl_sync(FULL, A, src); r.F = __shfl_sync(FULL, F, src); r.head = __shfl_sync(FULL, head, src);
+        r.A = __shfl_sync(FULL, A, src); r.As = __shfl_sync(FULL, As, src); r.F = __shfl_sync(FULL, F, src);
+        r.head = __shfl_sync(FULL, head, src);
         return r;
     }
 };
@@ -732,12 +731,17 @@ __device__ __forceinline__ void shard_fix(TileC2 &c, const ShardCtx *__restrict_
     if (c.cfw) c.FL += ctx->carFL;
 }
 
-// ---- per-row terms of a tile (shared by k_tile_terms and k_tile_grad): reverse scan -> every head publishes its group's
+// ---- per-row terms of a tile (k_tile_terms): reverse scan -> every head publishes its group's
 // (D, E, m) -> forward max scan (group starts) -> a_p, f_p of the event rows
+static_assert(TS_TILE < 0xfff, "tile positions are packed into 12 bits");
 struct TileTerms {
     double a[TS_ITEMS], f[TS_ITEMS];
-    int gs[TS_ITEMS];     // start of the row's group inside the tile, -1: the group began in an earlier tile
-    int tpos[TS_ITEMS];   // last row of the row's group inside the tile, INT_MAX: the group reaches past the tile
+    // packed (a register each would spill the sweep): bits 0-11 = 1 + start of the row's group inside the tile (0: the group
+    // began in an earlier tile), bits 12-23 = last row of the row's group inside the tile (0xfff: it reaches past the tile)
+    unsigned gt[TS_ITEMS];
+    __device__ __forceinline__ int gs(int k) const { return (int)(gt[k] & 0xfffu) - 1; }
+    __device__ __forceinline__ bool open(int k) const { return (gt[k] >> 12) == 0xfffu; }
+    __device__ __forceinline__ int tpos(int k) const { return (int)(gt[k] >> 12); }
 };
 template <bool WITH_LOG>
 __device__ __forceinline__ void tile_terms(const TileGeo &g, const TileRows &R, const TileW &tw, const TileC1 &c, int efron,
@@ -763,7 +767,7 @@ __device__ __forceinline__ void tile_terms(const TileGeo &g, const TileRows &R, 
             e.W = w; e.E = (R.flg[k] & RF_EV) ? w : 0.0; e.m = (R.flg[k] & RF_EV) ? 1 : 0;
             e.tpos = (R.flg[k] & RF_TAIL) ? j : INT_MAX;
             acc = RevT::combine(acc, e);
-            X.tpos[k] = acc.tpos;
+            X.gt[k] = (acc.tpos == INT_MAX ? 0xfffu : (unsigned)acc.tpos) << 12;
             if (R.flg[k] & RF_HEAD) {   // a group that reaches the tile's end continues in later tiles (R)
                 const bool open = acc.tpos == INT_MAX;
                 s_D[sk(j)] = c.S + acc.W;
@@ -780,7 +784,7 @@ __device__ __forceinline__ void tile_terms(const TileGeo &g, const TileRows &R, 
 #pragma unroll
         for (int k = 0; k < TS_ITEMS; ++k) {
             if (R.flg[k] & RF_HEAD) acc.h = t * TS_ITEMS + k;
-            X.gs[k] = acc.h;
+            X.gt[k] |= (unsigned)(acc.h + 1);
         }
     }
     // the group of the rows before the first head began in an earlier tile (L); it may also reach past this tile (R)
@@ -791,7 +795,7 @@ __device__ __forceinline__ void tile_terms(const TileGeo &g, const TileRows &R, 
     for (int k = 0; k < TS_ITEMS; ++k) {
         X.a[k] = 0.0; X.f[k] = 0.0;
         if (R.flg[k] & RF_EV) {
-            const int j = t * TS_ITEMS + k, h = X.gs[k];
+            const int j = t * TS_ITEMS + k, h = X.gs(k);
             const double D = h >= 0 ? s_D[sk(h)] : Df, E = h >= 0 ? s_E[sk(h)] : Ef;
             // a group's events come first on every shard, so the events of the group before this row are j - h of this tile
             // or, when the group began earlier, all the events of the earlier tiles (on one GPU that equals c.Lrows)
@@ -805,10 +809,17 @@ __device__ __forceinline__ void tile_terms(const TileGeo &g, const TileRows &R, 
     }
 }
 
-__global__ void __launch_bounds__(TS_THREADS, 4)
+// Besides the tile's sums the sweep leaves, per row, everything of the gradient that does not depend on the SECOND tile scan:
+//   g0 = d - w (P_tile - d F_tile)   (P_tile, F_tile: the in-tile prefix of a / group sum of f at the row's group end)
+//   rfl = bit 0: event row, bit 1: the row's group reaches past the tile, bit 2: the group began in an earlier tile
+// so that the last sweep (k_tile_apply) is element-wise: grad = scale (g0 - w (C + [bit 1] AR) + w d ([bit 1] FR + [bit 2] FL)).
+// Earlier versions recomputed the scans and the terms in the gradient sweep (k_tile_grad: 320 us at 16.7M rows against
+// 180 us for this kernel, 80 registers with the scatter's latency on top).
+__global__ void __launch_bounds__(TS_THREADS, 3)
 k_tile_terms(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, const int64_t *__restrict__ seg_off,
              const int64_t *__restrict__ tile_base, int n_seg, int64_t n, const TileW *__restrict__ tws,
-             const TileC1 *__restrict__ c1, int efron, const ShardCtx *__restrict__ ctx, TileA *__restrict__ ta) {
+             const TileC1 *__restrict__ c1, int efron, const ShardCtx *__restrict__ ctx, TileA *__restrict__ ta,
+             float *__restrict__ g0, uint8_t *__restrict__ rfl) {
     // (keys, weights) are staged only until the rows sit in registers; the group tables then take their place
     __shared__ double s_pool[2 * TS_DN + (TS_KN + 1) / 2];
     double *s_D = s_pool, *s_E = s_pool + TS_DN;
@@ -817,6 +828,7 @@ k_tile_terms(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, c
     float *s_w = reinterpret_cast<float *>(s_key + TS_KN);
     __shared__ RevT s_rev[TS_NW];
     __shared__ MaxT s_max[TS_NW];
+    __shared__ FwdT s_fwd[TS_NW];
     __shared__ double s_red[6][TS_NW];
     __shared__ int s_redi[2][TS_NW];
     const TileGeo g = tile_geo(blockIdx.x, seg_off, tile_base, n_seg, n, ctx);
@@ -830,40 +842,72 @@ k_tile_terms(const uint32_t *__restrict__ keys_s, const float *__restrict__ w, c
     TileTerms X;
     double sl;
     tile_terms<true>(g, R, tw, c, efron, s_D, s_E, s_m, s_rev, s_max, X, sl);
-    const int last = tw.nheads ? g.rows - tw.rowsl : 0;   // first row of the last fragment
-    double v[6] = {0.0, sl, 0.0, 0.0, 0.0, 0.0};
+    // reductions: the log-denominators and the event / event-time counts.  The sums of a, f over the tile and over its two
+    // fragments are read off the forward scan below (they are prefixes / group-prefixes at the fragment ends).
     int nt = 0, ne = 0;
 #pragma unroll
     for (int k = 0; k < TS_ITEMS; ++k) {
         const int j = t * TS_ITEMS + k;
-        v[0] += X.a[k];
-        if (j < tw.rowsf) { v[2] += X.a[k]; v[3] += X.f[k]; }
-        if (j >= last) { v[4] += X.a[k]; v[5] += X.f[k]; }
         // a distinct event time is counted at its event with l = 0: the group's head, or (shards only: the head is a censored
         // row of the previous shard) the first row of a tile that continues a group without events so far
         ne += (R.flg[k] & RF_EV) ? 1 : 0;
-        nt += ((R.flg[k] & (RF_EV | RF_HEAD)) == (RF_EV | RF_HEAD) || ((R.flg[k] & RF_EV) && j == 0 && X.gs[k] < 0 && c.Lm == 0)) ? 1 : 0;
+        nt += ((R.flg[k] & (RF_EV | RF_HEAD)) == (RF_EV | RF_HEAD) || ((R.flg[k] & RF_EV) && j == 0 && X.gs(k) < 0 && c.Lm == 0)) ? 1 : 0;
     }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) v[i] = warp_sum(v[i]);
+    sl = warp_sum(sl);
     nt = (int)warp_sum((long long)nt); ne = (int)warp_sum((long long)ne);
-    if (lane == 0) {
+    if (lane == 0) { s_red[0][warp] = sl; s_redi[0][warp] = nt; s_redi[1][warp] = ne; }
+    // forward: P (prefix of a inside the tile), group-prefixes of a and f; (P, F) at every row take the place of the group tables
+    FwdT agg = FwdT::identity();
 #pragma unroll
-        for (int i = 0; i < 6; ++i) s_red[i][warp] = v[i];
-        s_redi[0][warp] = nt; s_redi[1][warp] = ne;
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        FwdT e; e.A = X.a[k]; e.As = X.a[k]; e.F = X.f[k]; e.head = (R.flg[k] & RF_HEAD) ? 1 : 0;
+        agg = FwdT::combine(agg, e);
     }
+    FwdT run = block_prefix<FwdT, false>(agg, s_fwd);   // its barriers: every thread is done with the (D, E, m) tables
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        FwdT e; e.A = X.a[k]; e.As = X.a[k]; e.F = X.f[k]; e.head = (R.flg[k] & RF_HEAD) ? 1 : 0;
+        run = FwdT::combine(run, e);
+        const int j = t * TS_ITEMS + k;
+        if (j < g.rows) { s_D[sk(j)] = run.A; s_E[sk(j)] = run.F; }
+    }
+    if (t == (g.rows - 1) / TS_ITEMS) s_red[1][0] = run.As;   // sum of a from the tile's last head on (rows past the end are neutral)
     __syncthreads();
     if (t == 0) {
-        double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        double sumL = 0.0;
         int rt = 0, re = 0;
-        for (int q = 0; q < TS_NW; ++q) {
-            for (int i = 0; i < 6; ++i) r[i] += s_red[i][q];
-            rt += s_redi[0][q]; re += s_redi[1][q];
-        }
+        for (int q = 0; q < TS_NW; ++q) { sumL += s_red[0][q]; rt += s_redi[0][q]; re += s_redi[1][q]; }
         TileA o;
-        o.sumA = r[0]; o.sumL = r[1]; o.Af = r[2]; o.Ff = r[3]; o.Al = r[4]; o.Fl = r[5]; o.n_times = rt; o.n_ev = re;
-        o.pad0 = 0; o.pad1 = 0;
+        o.sumA = s_D[sk(g.rows - 1)]; o.sumL = sumL;
+        o.Af = tw.rowsf > 0 ? s_D[sk(tw.rowsf - 1)] : 0.0; o.Ff = tw.rowsf > 0 ? s_E[sk(tw.rowsf - 1)] : 0.0;
+        o.Al = s_red[1][0]; o.Fl = s_E[sk(g.rows - 1)];
+        o.n_times = rt; o.n_ev = re; o.pad0 = 0; o.pad1 = 0;
         ta[blockIdx.x] = o;
+    }
+    float gv[TS_ITEMS];
+    unsigned fv[TS_ITEMS];
+#pragma unroll
+    for (int k = 0; k < TS_ITEMS; ++k) {
+        const int j = t * TS_ITEMS + k;
+        gv[k] = 0.f; fv[k] = 0u;
+        if (j < g.rows) {
+            const bool open = X.open(k);                        // the row's group reaches past the tile
+            const int e = open ? g.rows - 1 : X.tpos(k);        // its last row inside the tile
+            const double d = (R.flg[k] & RF_EV) ? 1.0 : 0.0;
+            gv[k] = (float)(d - (double)R.w[k] * (s_D[sk(e)] - d * s_E[sk(e)]));
+            fv[k] = ((R.flg[k] & RF_EV) ? 1u : 0u) | (open ? 2u : 0u) | (X.gs(k) < 0 ? 4u : 0u);
+        }
+    }
+    const int64_t pb = g.p0 + (int64_t)t * TS_ITEMS;
+    if ((g.p0 & 7) == 0 && t * TS_ITEMS + TS_ITEMS <= g.rows) {   // whole 32-byte / 8-byte runs (always, for one cohort)
+        *reinterpret_cast<float4 *>(g0 + pb) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        *reinterpret_cast<float4 *>(g0 + pb + 4) = make_float4(gv[4], gv[5], gv[6], gv[7]);
+        *reinterpret_cast<uint2 *>(rfl + pb) = make_uint2(fv[0] | (fv[1] << 8) | (fv[2] << 16) | (fv[3] << 24),
+                                                           fv[4] | (fv[5] << 8) | (fv[6] << 16) | (fv[7] << 24));
+    } else {
+#pragma unroll
+        for (int k = 0; k < TS_ITEMS; ++k)
+            if (t * TS_ITEMS + k < g.rows) { g0[pb + k] = gv[k]; rfl[pb + k] = (uint8_t)fv[k]; }
     }
 }
 
@@ -1002,73 +1046,41 @@ k_tile_scan2(const TileW *__restrict__ tw, const TileA *__restrict__ ta, int64_t
     }
 }
 
-// the state keeps the UNSCALED per-row gradient d loss / d log_hz for grad_out = 1 (cox_scale_grad multiplies by grad_out)
-__global__ void __launch_bounds__(TS_THREADS, 3)
-k_tile_grad(const uint32_t *__restrict__ keys_s, const uint32_t *__restrict__ idx_s, const float *__restrict__ w,
-            const int64_t *__restrict__ seg_off, const int64_t *__restrict__ tile_base, int n_seg, int64_t n,
-            const TileW *__restrict__ tws, const TileC1 *__restrict__ c1, const TileC2 *__restrict__ c2, int efron,
-            const SegAcc *__restrict__ acc, const ShardCtx *__restrict__ ctx, float *__restrict__ grad_unit) {
-    // dynamic: the group tables (as in k_tile_terms) and the tile's row indices, fetched with cp.async at the start so that
-    // the scatter at the end does not wait for them (the loads used to sit behind the last scan: 40 % long-scoreboard stalls)
-    extern __shared__ __align__(16) unsigned char tg_dyn[];
-    double *s_pool = reinterpret_cast<double *>(tg_dyn);
-    uint32_t *s_idx = reinterpret_cast<uint32_t *>(tg_dyn + TG_POOL_BYTES);
-    double *s_D = s_pool, *s_E = s_pool + TS_DN;
-    int *s_m = reinterpret_cast<int *>(s_pool + 2 * TS_DN);
-    uint32_t *s_key = reinterpret_cast<uint32_t *>(s_pool);
-    float *s_w = reinterpret_cast<float *>(s_key + TS_KN);
-    __shared__ RevT s_rev[TS_NW];
-    __shared__ MaxT s_max[TS_NW];
-    __shared__ FwdT s_fwd[TS_NW];
+// the state keeps the UNSCALED per-row gradient d loss / d log_hz for grad_out = 1 (cox_scale_grad multiplies by grad_out).
+// Last sweep, element-wise: the tile's second-scan carries on top of what k_tile_terms left per row, scattered through the
+// permutation (4-byte stores over n rows: marked evict-last so that they merge in L2; the streams are evict-first).
+__global__ void __launch_bounds__(TS_THREADS, 6)
+k_tile_apply(const float *__restrict__ g0, const uint8_t *__restrict__ rfl, const float *__restrict__ w,
+             const uint32_t *__restrict__ idx_s, const int64_t *__restrict__ seg_off, const int64_t *__restrict__ tile_base, int n_seg,
+             int64_t n, const TileC2 *__restrict__ c2, const SegAcc *__restrict__ acc, const ShardCtx *__restrict__ ctx,
+             float *__restrict__ grad_unit) {
     const TileGeo g = tile_geo(blockIdx.x, seg_off, tile_base, n_seg, n, ctx);
     if (!g.valid) return;
-    const int t = threadIdx.x;
-    const TileW tw = tws[blockIdx.x];
-    TileC1 c = c1[blockIdx.x];
     TileC2 cc = c2[blockIdx.x];
-    shard_fix(c, ctx);
     shard_fix(cc, ctx);
     const double scale = acc[g.seg].scale;
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    const int t = threadIdx.x;
+    float gv[TS_ITEMS], wv[TS_ITEMS];
+    uint32_t ri[TS_ITEMS];
+    unsigned fv[TS_ITEMS];
 #pragma unroll
     for (int k = 0; k < TS_ITEMS; ++k) {
         const int j = t + k * TS_THREADS;
-        if (j < g.rows) cp_async_u32(smem_addr_u32(&s_idx[sk4(j)]), idx_s + g.p0 + j);
+        const int64_t p = g.p0 + (j < g.rows ? j : 0);
+        ri[k] = ldg_hint_u32(idx_s + p, pol_stream);
+        gv[k] = ldg_hint_f32(g0 + p, pol_stream);
+        wv[k] = ldg_hint_f32(w + p, pol_stream);
+        fv[k] = rfl[p];
     }
-    cp_async_commit_group();
-    TileRows R;
-    tile_load<true>(g, keys_s, w, s_key, s_w, R);
-    TileTerms X;
-    double sl;
-    tile_terms<false>(g, R, tw, c, efron, s_D, s_E, s_m, s_rev, s_max, X, sl);
-    // forward: P (prefix of a inside the tile), group-prefix of f
-    FwdT agg = FwdT::identity();
 #pragma unroll
     for (int k = 0; k < TS_ITEMS; ++k) {
-        FwdT e; e.A = X.a[k]; e.F = X.f[k]; e.head = (R.flg[k] & RF_HEAD) ? 1 : 0;
-        agg = FwdT::combine(agg, e);
-    }
-    FwdT run = block_prefix<FwdT, false>(agg, s_fwd);   // its barriers: every thread is done with the (D, E, m) tables
-#pragma unroll
-    for (int k = 0; k < TS_ITEMS; ++k) {
-        FwdT e; e.A = X.a[k]; e.F = X.f[k]; e.head = (R.flg[k] & RF_HEAD) ? 1 : 0;
-        run = FwdT::combine(run, e);
-        const int j = t * TS_ITEMS + k;
-        if (j < g.rows) { s_D[sk(j)] = run.A; s_E[sk(j)] = run.F; }   // (P, F) at every row
-    }
-    const uint64_t pol_keep = l2_policy_evict_last();
-    cp_async_wait_all_groups();
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < TS_ITEMS; ++k) {
-        const int j = t * TS_ITEMS + k;
+        const int j = t + k * TS_THREADS;
         if (j < g.rows) {
-            const bool open = X.tpos[k] == INT_MAX;             // the row's group reaches past the tile
-            const int e = open ? g.rows - 1 : X.tpos[k];        // its last row inside the tile
-            const double PQ = cc.C + s_D[sk(e)] + (open ? cc.AR : 0.0);
-            const double Fg = s_E[sk(e)] + (open ? cc.FR : 0.0) + (X.gs[k] < 0 ? cc.FL : 0.0);
-            const double d = (R.flg[k] & RF_EV) ? 1.0 : 0.0;
-            const double gr = d - (double)R.w[k] * (PQ - d * Fg);
-            stg_hint_f32(grad_unit + s_idx[sk4(j)], (float)(scale * gr), pol_keep);   // 4-byte scatter over n rows: merged in L2
+            const double wk = (double)wv[k];
+            double gr = (double)gv[k] - wk * (cc.C + ((fv[k] & 2u) ? cc.AR : 0.0));
+            if (fv[k] & 1u) gr += wk * (((fv[k] & 2u) ? cc.FR : 0.0) + ((fv[k] & 4u) ? cc.FL : 0.0));
+            stg_hint_f32(grad_unit + ri[k], (float)(scale * gr), pol_keep);
         }
     }
 }
@@ -1190,16 +1202,6 @@ SortedLayout sorted_layout(int64_t n, int64_t n_seg) {
 
 size_t cox_sorted_workspace_bytes(int64_t n, int64_t n_seg) { return sorted_layout(n, n_seg < 1 ? 1 : n_seg).total; }
 
-// k_tile_grad needs more than 48 KB of (dynamic) shared memory: opt in once per device
-static int32_t tile_grad_prepare() {
-    static PerDeviceOnce once;
-    if (once.pending()) {
-        B200_CHECK_CUDA(cudaFuncSetAttribute(k_tile_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES));
-        once.mark();
-    }
-    return B200SURV_OK;
-}
-
 int32_t cox_sorted_fwd_launch(const float *log_hz, const float *time, const uint8_t *event, const int64_t *seg_off, int64_t n,
                               int64_t n_seg, int ties, int reduction, float *out_loss, void *state, size_t state_bytes,
                               void *ws, size_t ws_bytes, cudaStream_t st) {
@@ -1261,13 +1263,14 @@ int32_t cox_sorted_fwd_launch(const float *log_hz, const float *time, const uint
     mark();
     k_tile_scan1<<<2 * SC_CLUSTER, SC_THREADS, 0, st>>>(tw, L.tiles_max, tbase, nseg, c1, nullptr);
     mark();
-    k_tile_terms<<<tiles, TS_THREADS, 0, st>>>(ks, wv, seg_off, tbase, nseg, n, tw, c1, efron, nullptr, ta);
+    // the buffer pair the sort did not end in is free: per-row partial gradient and flags between the last two sweeps
+    float *g0 = reinterpret_cast<float *>(in_first ? keys : keys_s);
+    uint8_t *rfl = reinterpret_cast<uint8_t *>(in_first ? vals : idx_s);
+    k_tile_terms<<<tiles, TS_THREADS, 0, st>>>(ks, wv, seg_off, tbase, nseg, n, tw, c1, efron, nullptr, ta, g0, rfl);
     mark();
     k_tile_scan2<<<2 * SC_CLUSTER, SC_THREADS, 0, st>>>(tw, ta, L.tiles_max, tbase, seg_off, nseg, n, ties, reduction, acc, c2, out_loss, hdrs, nullptr);
     mark();
-    rc = tile_grad_prepare();
-    if (rc) return rc;
-    k_tile_grad<<<tiles, TS_THREADS, TG_SMEM_BYTES, st>>>(ks, is, wv, seg_off, tbase, nseg, n, tw, c1, c2, efron, acc, nullptr, grad_unit);
+    k_tile_apply<<<tiles, TS_THREADS, 0, st>>>(g0, rfl, wv, is, seg_off, tbase, nseg, n, c2, acc, nullptr, grad_unit);
     mark();
     if (trace) {
         static const char *names[] = {"keys", "sort", "weights", "tile_w", "scan1", "terms", "scan2", "grad"};
@@ -1375,7 +1378,8 @@ int32_t cox_sorted_shard_terms(int64_t n, int ties, const void *all_rec1, int ra
     if (rc) return rc;
     const int efron = ties == B200SURV_TIES_EFRON ? 1 : 0;
     k_shard_ctx1<<<1, 32, 0, st>>>(all_rec1, rank, world, P.ctx);
-    k_tile_terms<<<P.tiles, TS_THREADS, 0, st>>>(P.keys_s, P.wv, nullptr, nullptr, 1, n, P.tw, P.c1, efron, P.ctx, P.ta);
+    k_tile_terms<<<P.tiles, TS_THREADS, 0, st>>>(P.keys_s, P.wv, nullptr, nullptr, 1, n, P.tw, P.c1, efron, P.ctx, P.ta,
+                                                 reinterpret_cast<float *>(P.keys), reinterpret_cast<uint8_t *>(P.vals));
     k_tile_scan2<<<2 * SC_CLUSTER, SC_THREADS, 0, st>>>(P.tw, P.ta, P.L.tiles_max, nullptr, nullptr, 1, n, ties, 0, P.acc, P.c2, nullptr, nullptr,
                                            static_cast<ShardRec2 *>(rec2_out));
     B200_CHECK_CUDA(cudaGetLastError());
@@ -1396,11 +1400,9 @@ int32_t cox_sorted_shard_finish(int64_t n, int ties, int reduction, const void *
     b200surv_cox_header *hdr = static_cast<b200surv_cox_header *>(state);
     float *grad_unit = reinterpret_cast<float *>(hdr + 1);
     const int efron = ties == B200SURV_TIES_EFRON ? 1 : 0;
-    rc = tile_grad_prepare();
-    if (rc) return rc;
     k_shard_finish<<<1, 32, 0, st>>>(all_rec2, rank, world, ties, reduction, P.acc, P.ctx, out_loss, hdr);
-    k_tile_grad<<<P.tiles, TS_THREADS, TG_SMEM_BYTES, st>>>(P.keys_s, P.idx_s, P.wv, nullptr, nullptr, 1, n, P.tw, P.c1, P.c2, efron, P.acc, P.ctx,
-                                                grad_unit);
+    k_tile_apply<<<P.tiles, TS_THREADS, 0, st>>>(reinterpret_cast<const float *>(P.keys), reinterpret_cast<const uint8_t *>(P.vals), P.wv,
+                                                 P.idx_s, nullptr, nullptr, 1, n, P.c2, P.acc, P.ctx, grad_unit);
     B200_CHECK_CUDA(cudaGetLastError());
     count_launches(2);
     return B200SURV_OK;

@@ -11,7 +11,6 @@
 // They replace cub::DeviceScan / cub::DeviceRadixSort in cox_sorted.cu and cindex.cu.
 #pragma once
 #include <climits>
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -1049,12 +1048,9 @@ inline int32_t radix_sort_pairs2(uint32_t *keys_in, uint32_t *vals_in, uint32_t 
         if (via_val)
             k_onesweep<true><<<L.ntiles, OS_THREADS, 0, st>>>(ka, vsrc, n, fn[p], nxt, has_next ? 1 : 0, hist + p * 256,
                                                               hist + (p + 1) * 256, state, state_next, ticket + p, kb, vb);
-        else if (n < (1ll << 31)) {
-            static const int minb = [] { const char *e = getenv("B200SURV_OS_MINB"); return e ? atoi(e) : 3; }();
-            auto kern = minb == 2 ? k_onesweep_key<2> : (minb == 4 ? k_onesweep_key<4> : k_onesweep_key<3>);
-            kern<<<L.ntiles, OS_THREADS, 0, st>>>(ka, vsrc, (unsigned)n, fn[p].shift, nxt.shift, has_next ? 1 : 0, hist + p * 256,
-                                                  hist + (p + 1) * 256, state, state_next, ticket + p, kb, vb);
-        }
+        else if (n < (1ll << 31))   // 2, 3 or 4 CTAs per SM time alike (121-126 us per pass at 16.7M pairs): the LSU pipe is the bound
+            k_onesweep_key<3><<<L.ntiles, OS_THREADS, 0, st>>>(ka, vsrc, (unsigned)n, fn[p].shift, nxt.shift, has_next ? 1 : 0,
+                                                               hist + p * 256, hist + (p + 1) * 256, state, state_next, ticket + p, kb, vb);
         else
             k_onesweep<false><<<L.ntiles, OS_THREADS, 0, st>>>(ka, vsrc, n, fn[p], nxt, has_next ? 1 : 0, hist + p * 256,
                                                                hist + (p + 1) * 256, state, state_next, ticket + p, kb, vb);
