@@ -225,11 +225,13 @@ def sorted_few_ties(n, dev, reps=5):
         fwd(); bwd()
     torch.cuda.synchronize()
     tf = tb = 0.0
+    launches0 = lib.b200surv_debug_launch_count()
     for _ in range(reps):
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record(); fwd(); b.record(); bwd(); c.record()
         torch.cuda.synchronize()
         tf += a.elapsed_time(b); tb += b.elapsed_time(c)
+    sorted_few_ties.launches = int(lib.b200surv_debug_launch_count() - launches0)   # counted by the library at its launch sites
     return tf / reps, tb / reps, float(loss.item())
 
 
@@ -260,7 +262,7 @@ def run_few_ties(args):
         fwd_ms, bwd_ms, loss = sorted_few_ties(n, dev, reps=steps)
         clocks = sampler.stop()
         ms = fwd_ms + bwd_ms
-        launches = None
+        launches = getattr(sorted_few_ties, "launches", None)
     else:
         def barrier():
             dist.barrier()
@@ -341,6 +343,7 @@ def run_few_ties(args):
             raise SystemExit(3)
     peak, peak_src = load_peaks()
     achieved = ALGO_BYTES_PER_ROW * n / (ms * 1e-3) / 1e9          # per GPU
+    traffic, traffic_src = load_traffic("cox_sorted_step", n)     # all kernels of one fwd+bwd step, ncu --set full
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": world * n / (ms * 1e-3), "unit": "patients/s", "n_gpus": world, "steps": steps, "warmup": 3,
@@ -352,7 +355,9 @@ def run_few_ties(args):
             "loss": loss,
             "roofline": {"bound": "hbm", "scope": "step = sort + scans + gradient scatter, 22 algorithmic B/row, per GPU", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
-                         "traffic": None},
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "note": "the path is bound by instruction issue and the LSU pipe (radix ranking, fp64 struct scans), not by DRAM: "
+                                 "traffic / ms is a fraction of the HBM peak (DESIGN.md 3.2)"},
             "gpu_launches": launches, "parity_check": parity, "strong_scaling": strong, "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()
