@@ -12,6 +12,15 @@
 //   #(e_j < lo) and #(e_j <= hi) over upper-triangular tiles only.  Column tiles are staged in shared
 //   memory and broadcast; each thread keeps 8 rows in registers; per-thread 32-bit counters are
 //   reduced with warp shuffles into int64 atomics once per CTA.
+// algo 2: algo 1's preprocessing, then ranks instead of pairs.  Every full column tile is ALSO kept sorted by estimate
+//   (k_ci_tile_sort: one bitonic sort of 1024 floats per tile, NaN last), and the thresholds of every row tile are also kept
+//   sorted (k_ci_row_sort).  Where a whole column tile is strictly later than every row of the row tile -- all tiles but the
+//   handful around the row tile's own time span -- #(e_j < lo) and #(e_j <= hi) are two 11-step binary searches per row in
+//   shared memory instead of 2 x 1024 compares; the searches of neighbouring lanes walk the same path because their
+//   thresholds are neighbours in sorted order (the sums over a row tile do not care which row a threshold belongs to).
+//   In the tiles around the diagonal the rows keep their time order: the columns before a row's strictly-later range are
+//   visited pair by pair and taken off the whole-tile ranks.  The same six integers (ranks in a sorted tile ARE the pair
+//   counts); the partial last column tile is counted pair by pair as in algo 1.
 // The radix sort and the prefix sum of the preprocessing are hand-written (sortscan.cuh: stable LSD radix sort,
 // single-pass scan with decoupled look-back).
 #include <climits>
@@ -277,6 +286,223 @@ k_ci_count(const float *__restrict__ est_s, int64_t n, const float *__restrict__
     }
 }
 
+// ------------------------------------------------------------------ algo 2: sorted tiles, ranks instead of pairs
+// every FULL column tile sorted by estimate (ascending, NaN last) into est_t.  One CTA per tile, bitonic network on
+// order-preserving keys in shared memory (-0 sorts before +0: a refinement of the float order, the searches' predicates
+// treat them alike).
+template <int N, bool PAYLOAD>
+__device__ __forceinline__ void bitonic_sort_smem(uint32_t *s_k, float *s_p) {
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int p = threadIdx.x; p < N / 2; p += CT_THREADS) {
+                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i | j;   // the p-th pair (i, i ^ j) with i < l
+                const uint32_t a = s_k[i], b = s_k[l];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) {
+                    s_k[i] = b; s_k[l] = a;
+                    if (PAYLOAD) { const float t = s_p[i]; s_p[i] = s_p[l]; s_p[l] = t; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+__global__ void __launch_bounds__(CT_THREADS)
+k_ci_tile_sort(const float *__restrict__ est_s, int64_t n, float *__restrict__ est_t) {
+    __shared__ uint32_t s_k[CT_TILE];
+    const int64_t c0 = (int64_t)blockIdx.x * CT_TILE;
+    if (c0 + CT_TILE > n) return;   // the partial last tile is never searched
+    for (int q = threadIdx.x; q < CT_TILE; q += CT_THREADS) {
+        const float e = est_s[c0 + q];
+        s_k[q] = (e == e) ? f2o(e) : 0xffffffffu;
+    }
+    __syncthreads();
+    bitonic_sort_smem<CT_TILE, false>(s_k, nullptr);
+    for (int q = threadIdx.x; q < CT_TILE; q += CT_THREADS) {
+        const uint32_t o = s_k[q];
+        est_t[c0 + q] = (o == 0xffffffffu) ? __int_as_float(0x7fc00000) : o2f(o);
+    }
+}
+// every row tile: its rows' thresholds sorted by lo (hi rides along: it is a monotone function of the same estimate) into
+// r_lo2 / r_hi2, padded to the full tile with NaN thresholds (they never count), and the tile's [min s, max ge) in tile_rng
+__global__ void __launch_bounds__(CT_THREADS)
+k_ci_row_sort(const float *__restrict__ r_lo, const float *__restrict__ r_hi, const int *__restrict__ r_s,
+              const int *__restrict__ r_ge, const Acc1 *__restrict__ acc, float *__restrict__ r_lo2, float *__restrict__ r_hi2,
+              int *__restrict__ tile_rng) {
+    __shared__ uint32_t s_k[CT_ROWS];
+    __shared__ float s_p[CT_ROWS];
+    __shared__ int s_red[2][32];
+    const long long n_rows = (long long)acc->n_rows, k0 = (long long)blockIdx.x * CT_ROWS;
+    if (k0 >= n_rows) return;
+    int mins = INT_MAX, maxge = 0;
+    for (int q = threadIdx.x; q < CT_ROWS; q += CT_THREADS) {
+        const long long k = k0 + q;
+        uint32_t key = 0xffffffffu;
+        float pay = __int_as_float(0x7fc00000);
+        if (k < n_rows) {
+            const float lo = r_lo[k];
+            key = (lo == lo) ? f2o(lo) : 0xffffffffu;
+            pay = r_hi[k];
+            mins = min(mins, r_s[k]); maxge = max(maxge, r_ge[k]);
+        }
+        s_k[q] = key; s_p[q] = pay;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mins = min(mins, __shfl_xor_sync(FULL, mins, o));
+        maxge = max(maxge, __shfl_xor_sync(FULL, maxge, o));
+    }
+    if (lane == 0) { s_red[0][wid] = mins; s_red[1][wid] = maxge; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < CT_THREADS / 32; ++w) { mins = min(mins, s_red[0][w]); maxge = max(maxge, s_red[1][w]); }
+        tile_rng[2 * blockIdx.x] = mins; tile_rng[2 * blockIdx.x + 1] = maxge;
+    }
+    bitonic_sort_smem<CT_ROWS, true>(s_k, s_p);
+    for (int q = threadIdx.x; q < CT_ROWS; q += CT_THREADS) {
+        const uint32_t o = s_k[q];
+        const bool nan = o == 0xffffffffu;
+        r_lo2[k0 + q] = nan ? __int_as_float(0x7fc00000) : o2f(o);
+        r_hi2[k0 + q] = nan ? __int_as_float(0x7fc00000) : s_p[q];
+    }
+}
+// number of elements of the sorted tile s[0, 1024) (NaN last) with s[q] < v / s[q] <= v: ordered compares, so NaN elements
+// and a NaN threshold count nothing -- exactly the sums the pair loop forms
+__device__ __forceinline__ unsigned tile_rank_lt(const float *s, float v) {
+    unsigned pos = 0;
+#pragma unroll
+    for (int step = CT_TILE / 2; step > 0; step >>= 1) pos += (s[pos + step - 1] < v) ? step : 0;
+    return pos + ((s[pos] < v) ? 1u : 0u);
+}
+__device__ __forceinline__ unsigned tile_rank_le(const float *s, float v) {
+    unsigned pos = 0;
+#pragma unroll
+    for (int step = CT_TILE / 2; step > 0; step >>= 1) pos += (s[pos + step - 1] <= v) ? step : 0;
+    return pos + ((s[pos] <= v) ? 1u : 0u);
+}
+
+// the count kernel of algo 2: same work items as k_ci_count; thread 0 steps over the items whose column tile precedes the
+// row tile's comparable range on its own (no block-wide round per skipped item)
+__global__ void __launch_bounds__(CT_THREADS)
+k_ci_count2(const float *__restrict__ est_s, const float *__restrict__ est_t, int64_t n, const float *__restrict__ r_lo,
+            const float *__restrict__ r_hi, const int *__restrict__ r_s, const int *__restrict__ r_ge,
+            const float *__restrict__ r_lo2, const float *__restrict__ r_hi2, const int *__restrict__ tile_rng, int shard,
+            int n_shards, Acc1 *acc) {
+    __shared__ __align__(16) float s_e[CT_TILE];
+    __shared__ __align__(16) float s_t[CT_TILE];
+    __shared__ long long red[32];
+    __shared__ unsigned long long s_item;
+    const long long n_rows = (long long)acc->n_rows;
+    const long long tiles_all = (n_rows + CT_ROWS - 1) / CT_ROWS;
+    const long long my_tiles = tiles_all > shard ? (tiles_all - shard + n_shards - 1) / n_shards : 0;
+    const long long col_tiles = (n + CT_TILE - 1) / CT_TILE;
+    const unsigned long long total = (unsigned long long)(my_tiles * col_tiles);
+    long long a = 0, b = 0, c = 0, d = 0;  // this CTA's strict conc / le and same-time conc / le counts
+    for (;;) {
+        __syncthreads();  // (s_item, s_e and s_t of the previous item are no longer read)
+        if (threadIdx.x == 0) {
+            unsigned long long item;
+            for (;;) {
+                item = atomicAdd(&acc->work, 1ull);
+                if (item >= total) break;
+                const long long ty = (long long)(item / (unsigned long long)col_tiles);
+                const long long c1 = min((long long)n, ((long long)(item - (unsigned long long)ty * (unsigned long long)col_tiles) + 1) * CT_TILE);
+                if (c1 > tile_rng[2 * (ty * n_shards + shard)]) break;   // else: the column tile precedes every row's range
+            }
+            s_item = item;
+        }
+        __syncthreads();
+        const unsigned long long item = s_item;
+        if (item >= total) break;
+        const long long ty = (long long)(item / (unsigned long long)col_tiles);
+        const int c0 = (int)(item - (unsigned long long)ty * (unsigned long long)col_tiles) * CT_TILE;
+        const int c1 = (int)min((long long)n, (long long)c0 + CT_TILE);
+        const long long tg = ty * n_shards + shard, k0 = tg * CT_ROWS;  // row tile ty of this shard
+        const int maxge = tile_rng[2 * tg + 1];
+        const bool full = c1 - c0 == CT_TILE;
+        if (full && c0 >= maxge) {
+            // every (row, column) pair of this item is a strict comparable pair: ranks of the tile's sorted thresholds
+            for (int q = threadIdx.x; q < CT_TILE; q += CT_THREADS) s_t[q] = est_t[c0 + q];
+            float lo[CT_R], hi[CT_R];
+#pragma unroll
+            for (int u = 0; u < CT_R; ++u) {
+                const long long k = k0 + threadIdx.x + (long long)u * CT_THREADS;   // padded to the full tile with NaN
+                lo[u] = r_lo2[k]; hi[u] = r_hi2[k];
+            }
+            __syncthreads();
+            unsigned sa = 0, sb = 0;
+#pragma unroll
+            for (int u = 0; u < CT_R; ++u) { sa += tile_rank_lt(s_t, lo[u]); sb += tile_rank_le(s_t, hi[u]); }
+            a += sa; b += sb;
+            continue;
+        }
+        float lo[CT_R], hi[CT_R];
+        int rs[CT_R], rg[CT_R];
+#pragma unroll
+        for (int u = 0; u < CT_R; ++u) {
+            const long long k = k0 + threadIdx.x + (long long)u * CT_THREADS;
+            if (k < n_rows) {
+                lo[u] = r_lo[k]; hi[u] = r_hi[k]; rs[u] = r_s[k]; rg[u] = r_ge[k];
+            } else {  // padding row: empty comparable range, NaN thresholds never compare true
+                lo[u] = __int_as_float(0x7fc00000); hi[u] = lo[u]; rs[u] = INT_MAX; rg[u] = INT_MAX;
+            }
+        }
+        for (int q = threadIdx.x; q < CT_TILE; q += CT_THREADS) s_e[q] = (c0 + q < n) ? est_s[c0 + q] : 0.f;
+        if (full)
+            for (int q = threadIdx.x; q < CT_TILE; q += CT_THREADS) s_t[q] = est_t[c0 + q];
+        __syncthreads();
+        unsigned long long conc_t = 0, le_t = 0;
+        if (full) {
+            // Around the diagonal.  Per row the tile splits into columns before its comparable range [0, qt), same-time
+            // censored columns [qt, qs) and strictly later columns [qs, 1024): strict counts = ranks of the thresholds in the
+            // whole sorted tile minus the counts over [0, qs); only the columns before qs are visited one by one.
+#pragma unroll
+            for (int u = 0; u < CT_R; ++u) {
+                const int qs = min(max(rg[u] - c0, 0), CT_TILE), qt = min(max(rs[u] - c0, 0), CT_TILE);   // padding rows: both 1024
+                unsigned pre_lt = 0, pre_le = 0, st_lt = 0, st_le = 0;
+                const bool strict_here = qs < CT_TILE;
+                for (int q = strict_here ? 0 : qt; q < qs; ++q) {
+                    const float ej = s_e[q];
+                    const bool lt = ej < lo[u], le = ej <= hi[u];
+                    pre_lt += lt; pre_le += le;
+                    if (q >= qt) { st_lt += lt; st_le += le; }
+                }
+                if (strict_here) { a += tile_rank_lt(s_t, lo[u]) - pre_lt; b += tile_rank_le(s_t, hi[u]) - pre_le; }
+                conc_t += st_lt; le_t += st_le;
+            }
+        } else {   // the partial last column tile: pair by pair
+            const int lim = c1 - c0;
+            unsigned cs[CT_R], ls[CT_R];
+#pragma unroll
+            for (int u = 0; u < CT_R; ++u) { cs[u] = 0; ls[u] = 0; }
+            for (int q = 0; q < lim; ++q) {
+                const float ej = s_e[q];
+                const int j = c0 + q;
+#pragma unroll
+                for (int u = 0; u < CT_R; ++u) {
+                    const bool lt = ej < lo[u], le = ej <= hi[u];
+                    if (j >= rg[u]) { cs[u] += lt; ls[u] += le; }
+                    else if (j >= rs[u]) { conc_t += lt; le_t += le; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < CT_R; ++u) { a += cs[u]; b += ls[u]; }
+        }
+        c += (long long)conc_t; d += (long long)le_t;
+    }
+    a = block_reduce<long long>(a, 0ll, OpAddLL(), red);
+    b = block_reduce<long long>(b, 0ll, OpAddLL(), red);
+    c = block_reduce<long long>(c, 0ll, OpAddLL(), red);
+    d = block_reduce<long long>(d, 0ll, OpAddLL(), red);
+    if (threadIdx.x == 0) {
+        if (a) atomicAdd(&acc->conc_s, (unsigned long long)a);
+        if (b) atomicAdd(&acc->le_s, (unsigned long long)b);
+        if (c) atomicAdd(&acc->conc_t, (unsigned long long)c);
+        if (d) atomicAdd(&acc->le_t, (unsigned long long)d);
+    }
+}
+
 __global__ void k_ci_final(const Acc1 *acc, long long *out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         out[0] += (long long)acc->conc_s;
@@ -299,7 +525,7 @@ struct StoreRank {  // exclusive prefix = index of the row among the selected ev
 
 struct CiLayout {
     size_t off_acc, off_keys, off_vals, off_keys_s, off_idx_s, off_est_s, off_isrow, off_rank, off_lo, off_hi,
-        off_s, off_ge, off_cub, cub_bytes, total;
+        off_s, off_ge, off_cub, cub_bytes, off_est_t, off_lo2, off_hi2, off_rng, total;
 };
 CiLayout ci_layout(int64_t n) {
     CiLayout L;
@@ -313,6 +539,9 @@ CiLayout ci_layout(int64_t n) {
     const size_t tmp = sortscan::radix_sort_temp_bytes((int64_t)N), sc = sortscan::scan_state_bytes((int64_t)N);
     L.cub_bytes = (tmp > sc ? tmp : sc) + 256;
     L.off_cub = take(L.cub_bytes);
+    // algo 2: the column tiles sorted by estimate, the row tiles' sorted thresholds (padded to whole tiles), [min s, max ge) per row tile
+    L.off_est_t = take(N * 4 + 16); L.off_lo2 = take((N + CT_ROWS) * 4); L.off_hi2 = take((N + CT_ROWS) * 4);
+    L.off_rng = take((N / CT_ROWS + 2) * 8);
     L.total = o;
     return L;
 }
@@ -328,7 +557,7 @@ int32_t cindex_counts_launch(const float *est, const float *time, const uint8_t 
     B200_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n, "row range");
     B200_REQUIRE(tol >= 0.f, "tied_tol must be >= 0");
     B200_REQUIRE(n_shards >= 1 && shard >= 0 && shard < n_shards, "shard in [0, n_shards)");
-    B200_REQUIRE(algo == 1 || n_shards == 1, "tile shards need algo 1");
+    B200_REQUIRE(algo == 1 || algo == 2 || n_shards == 1, "tile shards need algo 1 or 2");
     if (n == 0 || row_begin == row_end) return B200SURV_OK;
     if (algo == 0) {
         const int64_t rows = row_end - row_begin;
@@ -340,7 +569,7 @@ int32_t cindex_counts_launch(const float *est, const float *time, const uint8_t 
         B200_CHECK_CUDA(cudaGetLastError());
         return B200SURV_OK;
     }
-    B200_REQUIRE(algo == 1, "algo must be 0 or 1");
+    B200_REQUIRE(algo == 1 || algo == 2, "algo must be 0, 1 or 2");
     const CiLayout L = ci_layout(n);
     if (ws_bytes < L.total) { set_error("cindex: workspace %zu < %zu", ws_bytes, L.total); return B200SURV_WORKSPACE_TOO_SMALL; }
     unsigned char *w8 = static_cast<unsigned char *>(ws);
@@ -368,7 +597,16 @@ int32_t cindex_counts_launch(const float *est, const float *time, const uint8_t 
         if (rc) return rc;
     }
     k_ci_rows<<<grid, 256, 0, st>>>(keys_s, est_s, isrow, rank, n, tol, r_lo, r_hi, r_s, r_ge, shard, n_shards, acc);
-    k_ci_count<<<8 * num_sms(), CT_THREADS, 0, st>>>(est_s, n, r_lo, r_hi, r_s, r_ge, shard, n_shards, acc);
+    if (algo == 2) {
+        float *est_t = reinterpret_cast<float *>(w8 + L.off_est_t);
+        float *r_lo2 = reinterpret_cast<float *>(w8 + L.off_lo2), *r_hi2 = reinterpret_cast<float *>(w8 + L.off_hi2);
+        int *tile_rng = reinterpret_cast<int *>(w8 + L.off_rng);
+        k_ci_tile_sort<<<(unsigned)((n + CT_TILE - 1) / CT_TILE), CT_THREADS, 0, st>>>(est_s, n, est_t);
+        k_ci_row_sort<<<(unsigned)((n + CT_ROWS - 1) / CT_ROWS), CT_THREADS, 0, st>>>(r_lo, r_hi, r_s, r_ge, acc, r_lo2, r_hi2, tile_rng);
+        k_ci_count2<<<8 * num_sms(), CT_THREADS, 0, st>>>(est_s, est_t, n, r_lo, r_hi, r_s, r_ge, r_lo2, r_hi2, tile_rng, shard, n_shards, acc);
+    } else {
+        k_ci_count<<<8 * num_sms(), CT_THREADS, 0, st>>>(est_s, n, r_lo, r_hi, r_s, r_ge, shard, n_shards, acc);
+    }
     k_ci_final<<<1, 32, 0, st>>>(acc, reinterpret_cast<long long *>(out));
     B200_CHECK_CUDA(cudaGetLastError());
     return B200SURV_OK;

@@ -26,7 +26,7 @@ def cohort(n, seed, tmax=7, risk_ties=False):
     return est, ev, t
 
 
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_golden_reference_fallback_vectors(golden, algo):
     g = golden("cindex_fallback.npz")
     for c in g["cases"]:
@@ -36,7 +36,7 @@ def test_golden_reference_fallback_vectors(golden, algo):
         assert np.float32(pkg.cindex_from_counts(counts, "fallback")) == g[f"{c}/value"], c
 
 
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 @pytest.mark.parametrize("tol", [0.0, 1e-8, 0.3])
 def test_counts_bit_exact_small_and_ragged(algo, tol):
     for n, seed, tmax, rt in ((1, 0, 3, False), (2, 1, 1, False), (5, 2, 2, True), (100, 3, 7, True),
@@ -45,7 +45,7 @@ def test_counts_bit_exact_small_and_ragged(algo, tol):
         assert (gpu_counts(est, ev, t, tol, algo) == oci.counts_brute(est, ev, t, tol)).all(), (n, seed)
 
 
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_known_answers_and_special_values(algo):
     est = np.zeros(64, np.float32); ev = np.ones(64, bool); t = np.arange(64, dtype=np.float32)
     c = gpu_counts(est, ev, t, 1e-8, algo)
@@ -64,7 +64,7 @@ def test_known_answers_and_special_values(algo):
     assert (gpu_counts(est, ev, t2, 1e-8, algo) == oci.counts_brute(est, ev, t2, 1e-8)).all()
 
 
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_row_sharding_adds_up(algo):
     lh, ev, t = synth.cohort(30_000, 5, risk_tie_frac=0.1)
     full = oci.counts_fast(lh.numpy(), ev.numpy(), t.numpy())
@@ -83,11 +83,29 @@ def test_moderate_and_full_size():
             lh, ev, t = synth.cohort(n, seed, risk_tie_frac=frac)
             ref = oci.counts_fast(lh.numpy(), ev.numpy(), t.numpy())
             assert (gpu_counts(lh, ev, t, 1e-8, 1) == ref).all(), (n, frac)
+            assert (gpu_counts(lh, ev, t, 1e-8, 2) == ref).all(), (n, frac, "sorted column tiles")
     lh, ev, t = synth.cohort(200_000, 2, risk_tie_frac=0.1)
     assert (gpu_counts(lh, ev, t, 1e-8, 0) == oci.counts_fast(lh.numpy(), ev.numpy(), t.numpy())).all()
     # few ties in time (float times)
     lh, ev, t = synth.cohort(100_000, 3, few_ties=True)
     assert (gpu_counts(lh, ev, t, 1e-8, 1) == oci.counts_fast(lh.numpy(), ev.numpy(), t.numpy())).all()
+    assert (gpu_counts(lh, ev, t, 1e-8, 2) == oci.counts_fast(lh.numpy(), ev.numpy(), t.numpy())).all()
+
+
+@pytest.mark.parametrize("tol", [0.0, 1e-8, 0.3])
+def test_sorted_column_tiles_equal_pair_counting(tol):
+    """algo 2 answers the strictly-later tiles with two binary searches per row in a tile sorted by estimate; the six
+    integers must equal algo 1's pair-by-pair counts, also with infinite / NaN / signed-zero estimates, heavy risk ties
+    and tie tolerances wider than the spacing of the estimates."""
+    for n, seed, frac in ((60_000, 21, 0.0), (60_000, 22, 0.3), (131_072, 23, 0.05), (9_000, 24, 0.5)):
+        lh, ev, t = synth.cohort(n, seed, risk_tie_frac=frac)
+        est = lh.numpy().copy()
+        est[::97] = np.inf; est[3::101] = -np.inf; est[5::103] = np.nan; est[7::107] = 0.0; est[11::109] = -0.0
+        a = gpu_counts(est, ev, t, tol, 1)
+        b = gpu_counts(est, ev, t, tol, 2)
+        assert (a == b).all(), (n, seed, tol, a, b)
+    lh, ev, t = synth.cohort(60_000, 25, few_ties=True)
+    assert (gpu_counts(lh, ev, t, tol, 2) == gpu_counts(lh, ev, t, tol, 1)).all()
 
 
 def test_concordance_index_object_api():
@@ -103,7 +121,7 @@ def test_concordance_index_object_api():
     assert pkg.ConcordanceIndex()(lh[:0], ev[:0], t[:0]).item() == 0.5
 
 
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_packed_cohorts_match_per_cohort_counts(algo):
     """CV-sweep shape: ragged cohorts packed back to back (one empty), one launch sequence, counts per cohort."""
     from multimodal_survival_prediction_b200.cindex import cindex_counts_cohorts
