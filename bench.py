@@ -545,21 +545,28 @@ def run_b200(args):
     cn = 1 << 20
     clh, cev, ct = synth.cohort(cn, SEED)
     cx, ce, ctt = clh.to(dev), cev.to(dev), ct.to(dev)
-    for _ in range(2):
-        gdist.cindex_counts_sharded(cx, ce, ctt)
-    barrier()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    c0.record()
-    for _ in range(reps):
-        counts = gdist.cindex_counts_sharded(cx, ce, ctt)
-    c1.record()
-    barrier()
-    ci_ms = torch.tensor([c0.elapsed_time(c1) / reps], device=dev)
-    if world > 1:
-        dist.all_reduce(ci_ms, op=dist.ReduceOp.MAX)
-    ci_ms = float(ci_ms.item())
-    counts = counts.cpu().tolist()
+    def timed_cindex(algo):
+        for _ in range(2):
+            gdist.cindex_counts_sharded(cx, ce, ctt, algo=algo)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        c0.record()
+        for _ in range(reps):
+            cnt = gdist.cindex_counts_sharded(cx, ce, ctt, algo=algo)
+        c1.record()
+        barrier()
+        ms_ = torch.tensor([c0.elapsed_time(c1) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_, op=dist.ReduceOp.MAX)
+        return float(ms_.item()), cnt.cpu().tolist()
+
+    # algo 1: the tiled pair-by-pair kernel BASELINE.json's north_star describes (and its 8-GPU scaling target is quoted on);
+    # algo 2 (the library's default): ranks in sorted tiles, the same six integers
+    ci_ms, counts = timed_cindex(1)
+    ci2_ms, counts2 = timed_cindex(2)
+    if counts2 != counts:
+        raise SystemExit(f"C-index: algo 2 counters {counts2} differ from algo 1 {counts}")
 
     # ---- gated fusion head fwd+bwd, B = 4096 rows, bf16 tcgen05 GEMMs (BASELINE.json configs[1]); per rank
     from multimodal_survival_prediction_b200 import head as ghead
@@ -842,7 +849,13 @@ def run_b200(args):
             "extra": {"cindex_1m": {"n": cn, "ms": ci_ms, "patients_per_s": cn / (ci_ms * 1e-3),
                                     "ordered_pairs_per_s": sum(counts) / (ci_ms * 1e-3), "counts": counts,
                                     "n_gpus": world, "scaling": "strong (row tiles sharded, int64 all-reduce)",
+                                    "algo": "1: tiled pair counting (north_star design)",
                                     "cpu_baseline": ci_cpu},
+                      "cindex_1m_ranks": {"n": cn, "ms": ci2_ms, "patients_per_s": cn / (ci2_ms * 1e-3), "counts_equal_algo1": True,
+                                          "n_gpus": world, "speedup_vs_pair_counting": ci_ms / ci2_ms,
+                                          "algo": "2 (library default): column tiles sorted by estimate, two binary searches per "
+                                                  "row and strictly-later tile, prefix subtraction around the diagonal; same "
+                                                  "int64 counters bit for bit; row tiles sharded like algo 1"},
                       "cv_sweep": {"replicas_per_gpu": sw_rep, "rows_per_replica": sw_rows, "n_gpus": world,
                                    "cox_fwd_bwd_ms": sweep_cox_ms, "cindex_ms": sweep_ci_ms,
                                    "replica_evals_per_s": world * sw_rep / ((sweep_cox_ms + sweep_ci_ms) * 1e-3),

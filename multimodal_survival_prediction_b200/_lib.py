@@ -133,6 +133,8 @@ SIGNATURES = {
                                       c_void_p]),
     "b200surv_cindex_counts_shard": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,
                                                c_void_p, c_size_t, c_void_p]),
+    "b200surv_cindex_counts_shard_algo": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_int32,
+                                                    c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200surv_cindex_counts": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                          c_int64, c_float, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
 }

@@ -29,7 +29,7 @@ from . import _lib as L
 COUNTER_NAMES = ("conc", "disc", "tied_risk", "conc_st", "disc_st", "tied_st")
 
 
-def cindex_counts(estimate, event, time, tied_tol=1e-8, row_begin=0, row_end=None, algo=1, out=None):
+def cindex_counts(estimate, event, time, tied_tol=1e-8, row_begin=0, row_end=None, algo=2, out=None):
     """int64[6] pair counters (device tensor) for rows [row_begin,row_end) x all columns.
     Asynchronous; ADDS into ``out`` if given."""
     dev = estimate.device
@@ -48,9 +48,9 @@ def cindex_counts(estimate, event, time, tied_tol=1e-8, row_begin=0, row_end=Non
     return out
 
 
-def cindex_counts_shard(estimate, event, time, shard, n_shards, tied_tol=1e-8, out=None):
+def cindex_counts_shard(estimate, event, time, shard, n_shards, tied_tol=1e-8, out=None, algo=1):
     """Six int64 counters of shard ``shard`` of ``n_shards`` (row tiles of the sorted event rows dealt out round-robin,
-    b200surv_cindex_counts_shard); the shards' counters sum to cindex_counts(...) exactly."""
+    b200surv_cindex_counts_shard / _shard_algo); the shards' counters sum to cindex_counts(...) exactly."""
     dev = estimate.device
     L.require_device(dev.index)
     lib = L.load()
@@ -59,15 +59,20 @@ def cindex_counts_shard(estimate, event, time, shard, n_shards, tied_tol=1e-8, o
         out = torch.zeros(6, dtype=torch.int64, device=dev)
     if n == 0:
         return out
-    wb = lib.b200surv_cindex_workspace_bytes(n, 1, 1)
+    wb = lib.b200surv_cindex_workspace_bytes(n, 1, algo)
     ws = torch.empty(max(wb, 256), dtype=torch.uint8, device=dev)
-    rc = lib.b200surv_cindex_counts_shard(L.ptr(estimate), L.ptr(time), L.ptr(event), n, shard, n_shards,
-                                          ctypes.c_float(tied_tol), L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    if algo == 1:
+        rc = lib.b200surv_cindex_counts_shard(L.ptr(estimate), L.ptr(time), L.ptr(event), n, shard, n_shards,
+                                              ctypes.c_float(tied_tol), L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    else:
+        rc = lib.b200surv_cindex_counts_shard_algo(L.ptr(estimate), L.ptr(time), L.ptr(event), n, shard, n_shards,
+                                                   ctypes.c_float(tied_tol), algo, L.ptr(out), L.ptr(ws), ws.numel(),
+                                                   L.stream_ptr(dev))
     L.check(rc, "b200surv_cindex_counts_shard")
     return out
 
 
-def cindex_counts_cohorts(estimate, event, time, offsets, tied_tol=1e-8, algo=1):
+def cindex_counts_cohorts(estimate, event, time, offsets, tied_tol=1e-8, algo=2):
     """int64[n_cohorts][6] pair counters for cohorts packed back to back; ``offsets`` is a host sequence of
     n_cohorts+1 row offsets (the CV sweep: one C-index per fold and replica).  Asynchronous."""
     dev = estimate.device
@@ -112,7 +117,7 @@ class ConcordanceIndex:
     """``ConcordanceIndex(tied_tol=1e-8, checks=True)(estimate, event, time)`` -> 0-dim float32 tensor."""
 
     def __init__(self, tied_tol: float = 1e-8, checks: bool = True, *, convention: str = "harrell",
-                 algo: int = 1):
+                 algo: int = 2):
         self.tied_tol = float(tied_tol)
         self.checks = checks
         self.convention = convention

@@ -226,6 +226,17 @@ int32_t b200surv_cindex_counts_shard(const float *estimate, const float *time, c
                                 workspace_bytes, as_stream(stream));
 }
 
+int32_t b200surv_cindex_counts_shard_algo(const float *estimate, const float *time, const uint8_t *event, int64_t n,
+                                          int32_t shard, int32_t n_shards, float tied_tol, int32_t algo,
+                                          int64_t *out_counts, void *workspace, size_t workspace_bytes,
+                                          b200surv_stream_t stream) {
+    B200_REQUIRE(estimate && time && event && out_counts && workspace, "null pointer");
+    B200_REQUIRE(n >= 0, "n");
+    B200_REQUIRE(algo == 1 || algo == 2, "tile shards need algo 1 or 2");
+    return cindex_counts_launch(estimate, time, event, n, 0, n, tied_tol, algo, shard, n_shards, out_counts, workspace,
+                                workspace_bytes, as_stream(stream));
+}
+
 int32_t b200surv_cindex_counts_cohorts(const float *estimate, const float *time, const uint8_t *event,
                                        const int64_t *cohort_offsets_host, int64_t n_cohorts, float tied_tol,
                                        int32_t algo, int64_t *out_counts, void *workspace, size_t workspace_bytes,

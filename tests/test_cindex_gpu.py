@@ -135,18 +135,19 @@ def test_packed_cohorts_match_per_cohort_counts(algo):
         assert (out[c] == ref).all(), (c, a, b)
 
 
+@pytest.mark.parametrize("algo", [1, 2])
 @pytest.mark.parametrize("n_shards", [2, 3, 8])
-def test_tile_shards_partition_the_pairs(n_shards):
-    """b200surv_cindex_counts_shard: the shards' counters add up to the single-GPU counters bit for bit (what the
-    multi-GPU int64 all-reduce relies on), on a cohort with time ties, risk ties and several row tiles."""
+def test_tile_shards_partition_the_pairs(n_shards, algo):
+    """b200surv_cindex_counts_shard / _shard_algo: the shards' counters add up to the single-GPU counters bit for bit (what
+    the multi-GPU int64 all-reduce relies on), on a cohort with time ties, risk ties and several row tiles."""
     from multimodal_survival_prediction_b200 import synth
     from multimodal_survival_prediction_b200.cindex import cindex_counts, cindex_counts_shard
-    lh, ev, t = synth.cohort(30_011, 21, risk_tie_frac=0.1)
+    lh, ev, t = synth.cohort(30_011 if algo == 1 else 90_011, 21, risk_tie_frac=0.1)
     x, e, tt = lh.cuda(), ev.cuda(), t.cuda()
-    full = cindex_counts(x, e, tt, 1e-8).cpu()
+    full = cindex_counts(x, e, tt, 1e-8, algo=1).cpu()
     acc = torch.zeros(6, dtype=torch.int64)
     for s in range(n_shards):
-        part = cindex_counts_shard(x, e, tt, s, n_shards, 1e-8).cpu()
+        part = cindex_counts_shard(x, e, tt, s, n_shards, 1e-8, algo=algo).cpu()
         assert (part >= 0).all()
         acc += part
     assert torch.equal(acc, full), (acc.tolist(), full.tolist())
