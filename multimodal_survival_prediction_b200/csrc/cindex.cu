@@ -368,19 +368,26 @@ k_ci_row_sort(const float *__restrict__ r_lo, const float *__restrict__ r_hi, co
     }
 }
 // number of elements of the sorted tile s[0, 1024) (NaN last) with s[q] < v / s[q] <= v: ordered compares, so NaN elements
-// and a NaN threshold count nothing -- exactly the sums the pair loop forms
-__device__ __forceinline__ unsigned tile_rank_lt(const float *s, float v) {
-    unsigned pos = 0;
-#pragma unroll
-    for (int step = CT_TILE / 2; step > 0; step >>= 1) pos += (s[pos + step - 1] < v) ? step : 0;
-    return pos + ((s[pos] < v) ? 1u : 0u);
+// and a NaN threshold count nothing -- exactly the sums the pair loop forms.  Branch-free bisection on the shared-window
+// BYTE address: load with an immediate offset, compare, predicated add = three instructions per step (the C form of the
+// same loop compiles to five: the select and the address add stay separate).
+template <int STEP, bool LE>
+__device__ __forceinline__ void tile_rank_step(uint32_t &a, float v) {
+    float x;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(x) : "r"(a), "n"((STEP - 1) * 4));
+    if (LE) asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}" : "+r"(a) : "f"(x), "f"(v), "n"(STEP * 4));
+    else asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}" : "+r"(a) : "f"(x), "f"(v), "n"(STEP * 4));
+    if constexpr (STEP > 1) tile_rank_step<STEP / 2, LE>(a, v);
 }
-__device__ __forceinline__ unsigned tile_rank_le(const float *s, float v) {
-    unsigned pos = 0;
-#pragma unroll
-    for (int step = CT_TILE / 2; step > 0; step >>= 1) pos += (s[pos + step - 1] <= v) ? step : 0;
-    return pos + ((s[pos] <= v) ? 1u : 0u);
+template <bool LE>
+__device__ __forceinline__ unsigned tile_rank(uint32_t s_addr, float v) {   // s_addr: shared-window address of s[0]
+    uint32_t a = s_addr;
+    tile_rank_step<CT_TILE / 2, LE>(a, v);   // a <= s_addr + 1023 * 4
+    tile_rank_step<1, LE>(a, v);             // the element the bisection ended on
+    return (a - s_addr) >> 2;
 }
+__device__ __forceinline__ unsigned tile_rank_lt(const float *s, float v) { return tile_rank<false>(smem_addr_u32(s), v); }
+__device__ __forceinline__ unsigned tile_rank_le(const float *s, float v) { return tile_rank<true>(smem_addr_u32(s), v); }
 
 // the count kernel of algo 2: same work items as k_ci_count; thread 0 steps over the items whose column tile precedes the
 // row tile's comparable range on its own (no block-wide round per skipped item)
