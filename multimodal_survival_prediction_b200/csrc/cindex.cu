@@ -15,9 +15,10 @@
 // algo 2: algo 1's preprocessing, then ranks instead of pairs.  Every full column tile is ALSO kept sorted by estimate
 //   (k_ci_tile_sort: one bitonic sort of 1024 floats per tile, NaN last), and the thresholds of every row tile are also kept
 //   sorted (k_ci_row_sort).  Where a whole column tile is strictly later than every row of the row tile -- all tiles but the
-//   handful around the row tile's own time span -- #(e_j < lo) and #(e_j <= hi) are two 11-step binary searches per row in
-//   shared memory instead of 2 x 1024 compares; the searches of neighbouring lanes walk the same path because their
-//   thresholds are neighbours in sorted order (the sums over a row tile do not care which row a threshold belongs to).
+//   handful around the row tile's own time span -- the sums over the row tile of #(e_j < lo) and #(e_j <= hi) are bisections
+//   in shared memory instead of 2 x 1024 compares per row, taken from the column side (1024 sorted columns against the row
+//   tile's 2048 sorted lo / hi thresholds); the searches of neighbouring lanes walk the same path because their values are
+//   neighbours in sorted order (the sums over a row tile do not care which row a threshold belongs to).
 //   In the tiles around the diagonal the rows keep their time order: the columns before a row's strictly-later range are
 //   visited pair by pair and taken off the whole-tile ranks.  The same six integers (ranks in a sorted tile ARE the pair
 //   counts); the partial last column tile is counted pair by pair as in algo 1.
@@ -89,6 +90,7 @@ constexpr int CT_TILE = 1024;                 // columns per shared-memory tile
 struct Acc1 {
     unsigned long long conc_s, le_s, conc_t, le_t, tot_s, tot_t;
     unsigned long long n_rows, work;  // work: the counter the count kernel's CTAs pull their items from
+    unsigned long long work2;         // algo 2: the second pass over the items
 };
 
 __device__ __forceinline__ uint32_t time_key(float t, bool ev) {
@@ -105,7 +107,7 @@ __device__ __forceinline__ float o2f(uint32_t o) {
 __global__ void __launch_bounds__(256)
 k_ci_keys(const float *__restrict__ time, const uint8_t *__restrict__ event, int64_t n,
           uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, Acc1 *acc) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *acc = Acc1{0, 0, 0, 0, 0, 0, 0, 0};
+    if (blockIdx.x == 0 && threadIdx.x == 0) *acc = Acc1{0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         keys[i] = time_key(time[i], event[i] != 0);
         vals[i] = (uint32_t)i;
@@ -323,48 +325,53 @@ k_ci_tile_sort(const float *__restrict__ est_s, int64_t n, float *__restrict__ e
         est_t[c0 + q] = (o == 0xffffffffu) ? __int_as_float(0x7fc00000) : o2f(o);
     }
 }
-// every row tile: its rows' thresholds sorted by lo (hi rides along: it is a monotone function of the same estimate) into
-// r_lo2 / r_hi2, padded to the full tile with NaN thresholds (they never count), and the tile's [min s, max ge) in tile_rng
+// every row tile: its rows' lo thresholds and its hi thresholds, each sorted on its own (NaN last, padded to the full tile with
+// NaN: they never count) into r_lo2 / r_hi2 -- the sums over a row tile need neither the row a threshold belongs to nor the
+// pairing of lo with hi -- and tile_rng[4 tile + {0, 1, 2, 3}] = min s, max ge, number of non-NaN lo, of non-NaN hi
 __global__ void __launch_bounds__(CT_THREADS)
 k_ci_row_sort(const float *__restrict__ r_lo, const float *__restrict__ r_hi, const int *__restrict__ r_s,
               const int *__restrict__ r_ge, const Acc1 *__restrict__ acc, float *__restrict__ r_lo2, float *__restrict__ r_hi2,
               int *__restrict__ tile_rng) {
-    __shared__ uint32_t s_k[CT_ROWS];
-    __shared__ float s_p[CT_ROWS];
-    __shared__ int s_red[2][32];
+    __shared__ uint32_t s_k[CT_ROWS], s_k2[CT_ROWS];
+    __shared__ int s_red[4][32];
     const long long n_rows = (long long)acc->n_rows, k0 = (long long)blockIdx.x * CT_ROWS;
     if (k0 >= n_rows) return;
-    int mins = INT_MAX, maxge = 0;
+    int mins = INT_MAX, maxge = 0, nvl = 0, nvh = 0;
     for (int q = threadIdx.x; q < CT_ROWS; q += CT_THREADS) {
         const long long k = k0 + q;
-        uint32_t key = 0xffffffffu;
-        float pay = __int_as_float(0x7fc00000);
+        uint32_t kl = 0xffffffffu, kh = 0xffffffffu;
         if (k < n_rows) {
-            const float lo = r_lo[k];
-            key = (lo == lo) ? f2o(lo) : 0xffffffffu;
-            pay = r_hi[k];
+            const float lo = r_lo[k], hi = r_hi[k];
+            if (lo == lo) { kl = f2o(lo); ++nvl; }
+            if (hi == hi) { kh = f2o(hi); ++nvh; }
             mins = min(mins, r_s[k]); maxge = max(maxge, r_ge[k]);
         }
-        s_k[q] = key; s_p[q] = pay;
+        s_k[q] = kl; s_k2[q] = kh;
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mins = min(mins, __shfl_xor_sync(FULL, mins, o));
         maxge = max(maxge, __shfl_xor_sync(FULL, maxge, o));
+        nvl += __shfl_xor_sync(FULL, nvl, o);
+        nvh += __shfl_xor_sync(FULL, nvh, o);
     }
-    if (lane == 0) { s_red[0][wid] = mins; s_red[1][wid] = maxge; }
+    if (lane == 0) { s_red[0][wid] = mins; s_red[1][wid] = maxge; s_red[2][wid] = nvl; s_red[3][wid] = nvh; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 0; w < CT_THREADS / 32; ++w) { mins = min(mins, s_red[0][w]); maxge = max(maxge, s_red[1][w]); }
-        tile_rng[2 * blockIdx.x] = mins; tile_rng[2 * blockIdx.x + 1] = maxge;
+        mins = INT_MAX; maxge = 0; nvl = 0; nvh = 0;
+        for (int w = 0; w < CT_THREADS / 32; ++w) {
+            mins = min(mins, s_red[0][w]); maxge = max(maxge, s_red[1][w]); nvl += s_red[2][w]; nvh += s_red[3][w];
+        }
+        int *o = tile_rng + 4 * blockIdx.x;
+        o[0] = mins; o[1] = maxge; o[2] = nvl; o[3] = nvh;
     }
-    bitonic_sort_smem<CT_ROWS, true>(s_k, s_p);
+    bitonic_sort_smem<CT_ROWS, false>(s_k, nullptr);
+    bitonic_sort_smem<CT_ROWS, false>(s_k2, nullptr);
     for (int q = threadIdx.x; q < CT_ROWS; q += CT_THREADS) {
-        const uint32_t o = s_k[q];
-        const bool nan = o == 0xffffffffu;
-        r_lo2[k0 + q] = nan ? __int_as_float(0x7fc00000) : o2f(o);
-        r_hi2[k0 + q] = nan ? __int_as_float(0x7fc00000) : s_p[q];
+        const uint32_t a = s_k[q], b = s_k2[q];
+        r_lo2[k0 + q] = (a == 0xffffffffu) ? __int_as_float(0x7fc00000) : o2f(a);
+        r_hi2[k0 + q] = (b == 0xffffffffu) ? __int_as_float(0x7fc00000) : o2f(b);
     }
 }
 // number of elements of the sorted tile s[0, 1024) (NaN last) with s[q] < v / s[q] <= v: ordered compares, so NaN elements
@@ -379,18 +386,26 @@ __device__ __forceinline__ void tile_rank_step(uint32_t &a, float v) {
     else asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}" : "+r"(a) : "f"(x), "f"(v), "n"(STEP * 4));
     if constexpr (STEP > 1) tile_rank_step<STEP / 2, LE>(a, v);
 }
-template <bool LE>
-__device__ __forceinline__ unsigned tile_rank(uint32_t s_addr, float v) {   // s_addr: shared-window address of s[0]
+template <bool LE, int N = CT_TILE>
+__device__ __forceinline__ unsigned tile_rank(uint32_t s_addr, float v) {   // s_addr: shared-window address of s[0]; N a power of 2
     uint32_t a = s_addr;
-    tile_rank_step<CT_TILE / 2, LE>(a, v);   // a <= s_addr + 1023 * 4
-    tile_rank_step<1, LE>(a, v);             // the element the bisection ended on
+    tile_rank_step<N / 2, LE>(a, v);   // a <= s_addr + (N - 1) * 4
+    tile_rank_step<1, LE>(a, v);       // the element the bisection ended on
     return (a - s_addr) >> 2;
 }
 __device__ __forceinline__ unsigned tile_rank_lt(const float *s, float v) { return tile_rank<false>(smem_addr_u32(s), v); }
 __device__ __forceinline__ unsigned tile_rank_le(const float *s, float v) { return tile_rank<true>(smem_addr_u32(s), v); }
 
-// the count kernel of algo 2: same work items as k_ci_count; thread 0 steps over the items whose column tile precedes the
-// row tile's comparable range on its own (no block-wide round per skipped item)
+// the count kernel of algo 2: same work items as k_ci_count, pulled CI2_CHUNK consecutive items at a time (they share the row
+// tile but for the chunk that crosses into the next one).
+//   * column tile strictly later than every row of the row tile: the sums over the tile's rows are taken from the COLUMN side,
+//       sum_rows #(e_j < lo_r) = sum_j #(lo_r > e_j) = sum_j (n_lo - rank_le(lo sorted, e_j)),
+//       sum_rows #(e_j <= hi_r) = sum_j (n_hi - rank_lt(hi sorted, e_j))        (NaN columns count nothing),
+//     1024 columns x 2 bisections of 12 steps against 2048 rows x 2 x 11 from the row side.  The row tile's two sorted
+//     threshold arrays stay in shared memory while the items of a chunk share the row tile; a thread's four columns come
+//     straight from the sorted column tile (neighbouring lanes hold neighbouring values: the bisections walk together).
+//   * around the diagonal the rows keep their time order and their (lo, hi, s, ge): see below.
+constexpr int CI2_CHUNK = 8;
 __global__ void __launch_bounds__(CT_THREADS)
 k_ci_count2(const float *__restrict__ est_s, const float *__restrict__ est_t, int64_t n, const float *__restrict__ r_lo,
             const float *__restrict__ r_hi, const int *__restrict__ r_s, const int *__restrict__ r_ge,
@@ -398,6 +413,7 @@ k_ci_count2(const float *__restrict__ est_s, const float *__restrict__ est_t, in
             int n_shards, Acc1 *acc) {
     __shared__ __align__(16) float s_e[CT_TILE];
     __shared__ __align__(16) float s_t[CT_TILE];
+    __shared__ __align__(16) float s_lo[CT_ROWS], s_hi[CT_ROWS];
     __shared__ long long red[32];
     __shared__ unsigned long long s_item;
     const long long n_rows = (long long)acc->n_rows;
@@ -405,98 +421,114 @@ k_ci_count2(const float *__restrict__ est_s, const float *__restrict__ est_t, in
     const long long my_tiles = tiles_all > shard ? (tiles_all - shard + n_shards - 1) / n_shards : 0;
     const long long col_tiles = (n + CT_TILE - 1) / CT_TILE;
     const unsigned long long total = (unsigned long long)(my_tiles * col_tiles);
+    const uint32_t lo_addr = smem_addr_u32(s_lo), hi_addr = smem_addr_u32(s_hi);
     long long a = 0, b = 0, c = 0, d = 0;  // this CTA's strict conc / le and same-time conc / le counts
+    long long cached_tg = -1;              // the row tile whose sorted thresholds sit in s_lo / s_hi
+    // two passes over the items: first the few expensive ones around the diagonal, one at a time (balance), then the many
+    // strictly-later ones in chunks that share their row tile's thresholds
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+    const int chunk = pass == 0 ? 1 : CI2_CHUNK;
+    unsigned long long *counter = pass == 0 ? &acc->work : &acc->work2;
     for (;;) {
-        __syncthreads();  // (s_item, s_e and s_t of the previous item are no longer read)
-        if (threadIdx.x == 0) {
-            unsigned long long item;
-            for (;;) {
-                item = atomicAdd(&acc->work, 1ull);
-                if (item >= total) break;
-                const long long ty = (long long)(item / (unsigned long long)col_tiles);
-                const long long c1 = min((long long)n, ((long long)(item - (unsigned long long)ty * (unsigned long long)col_tiles) + 1) * CT_TILE);
-                if (c1 > tile_rng[2 * (ty * n_shards + shard)]) break;   // else: the column tile precedes every row's range
-            }
-            s_item = item;
-        }
+        __syncthreads();  // (s_item of the previous chunk is no longer read)
+        if (threadIdx.x == 0) s_item = atomicAdd(counter, (unsigned long long)chunk);
         __syncthreads();
-        const unsigned long long item = s_item;
-        if (item >= total) break;
-        const long long ty = (long long)(item / (unsigned long long)col_tiles);
-        const int c0 = (int)(item - (unsigned long long)ty * (unsigned long long)col_tiles) * CT_TILE;
-        const int c1 = (int)min((long long)n, (long long)c0 + CT_TILE);
-        const long long tg = ty * n_shards + shard, k0 = tg * CT_ROWS;  // row tile ty of this shard
-        const int maxge = tile_rng[2 * tg + 1];
-        const bool full = c1 - c0 == CT_TILE;
-        if (full && c0 >= maxge) {
-            // every (row, column) pair of this item is a strict comparable pair: ranks of the tile's sorted thresholds
-            for (int q = threadIdx.x; q < CT_TILE; q += CT_THREADS) s_t[q] = est_t[c0 + q];
-            float lo[CT_R], hi[CT_R];
+        const unsigned long long first = s_item;
+        if (first >= total) break;
+        for (int gi = 0; gi < chunk; ++gi) {
+            const unsigned long long item = first + (unsigned long long)gi;
+            if (item >= total) break;
+            const long long ty = (long long)(item / (unsigned long long)col_tiles);
+            const int c0 = (int)(item - (unsigned long long)ty * (unsigned long long)col_tiles) * CT_TILE;
+            const int c1 = (int)min((long long)n, (long long)c0 + CT_TILE);
+            const long long tg = ty * n_shards + shard, k0 = tg * CT_ROWS;  // row tile ty of this shard
+            const int4 rng = *reinterpret_cast<const int4 *>(tile_rng + 4 * tg);   // min s, max ge, valid lo, valid hi
+            if (c1 <= rng.x) continue;   // the column tile precedes every row's comparable range (block-uniform)
+            const bool full = c1 - c0 == CT_TILE;
+            const bool strictly_later = full && c0 >= rng.y;
+            if (strictly_later != (pass == 1)) continue;   // not this pass's kind
+            if (strictly_later) {
+                // every (row, column) pair of this item is a strict comparable pair
+                float e[CT_TILE / CT_THREADS];
 #pragma unroll
-            for (int u = 0; u < CT_R; ++u) {
-                const long long k = k0 + threadIdx.x + (long long)u * CT_THREADS;   // padded to the full tile with NaN
-                lo[u] = r_lo2[k]; hi[u] = r_hi2[k];
-            }
-            __syncthreads();
-            unsigned sa = 0, sb = 0;
-#pragma unroll
-            for (int u = 0; u < CT_R; ++u) { sa += tile_rank_lt(s_t, lo[u]); sb += tile_rank_le(s_t, hi[u]); }
-            a += sa; b += sb;
-            continue;
-        }
-        float lo[CT_R], hi[CT_R];
-        int rs[CT_R], rg[CT_R];
-#pragma unroll
-        for (int u = 0; u < CT_R; ++u) {
-            const long long k = k0 + threadIdx.x + (long long)u * CT_THREADS;
-            if (k < n_rows) {
-                lo[u] = r_lo[k]; hi[u] = r_hi[k]; rs[u] = r_s[k]; rg[u] = r_ge[k];
-            } else {  // padding row: empty comparable range, NaN thresholds never compare true
-                lo[u] = __int_as_float(0x7fc00000); hi[u] = lo[u]; rs[u] = INT_MAX; rg[u] = INT_MAX;
-            }
-        }
-        for (int q = threadIdx.x; q < CT_TILE; q += CT_THREADS) s_e[q] = (c0 + q < n) ? est_s[c0 + q] : 0.f;
-        if (full)
-            for (int q = threadIdx.x; q < CT_TILE; q += CT_THREADS) s_t[q] = est_t[c0 + q];
-        __syncthreads();
-        unsigned long long conc_t = 0, le_t = 0;
-        if (full) {
-            // Around the diagonal.  Per row the tile splits into columns before its comparable range [0, qt), same-time
-            // censored columns [qt, qs) and strictly later columns [qs, 1024): strict counts = ranks of the thresholds in the
-            // whole sorted tile minus the counts over [0, qs); only the columns before qs are visited one by one.
-#pragma unroll
-            for (int u = 0; u < CT_R; ++u) {
-                const int qs = min(max(rg[u] - c0, 0), CT_TILE), qt = min(max(rs[u] - c0, 0), CT_TILE);   // padding rows: both 1024
-                unsigned pre_lt = 0, pre_le = 0, st_lt = 0, st_le = 0;
-                const bool strict_here = qs < CT_TILE;
-                for (int q = strict_here ? 0 : qt; q < qs; ++q) {
-                    const float ej = s_e[q];
-                    const bool lt = ej < lo[u], le = ej <= hi[u];
-                    pre_lt += lt; pre_le += le;
-                    if (q >= qt) { st_lt += lt; st_le += le; }
+                for (int i = 0; i < CT_TILE / CT_THREADS; ++i) e[i] = est_t[c0 + threadIdx.x + i * CT_THREADS];
+                if (cached_tg != tg) {
+                    __syncthreads();   // the previous row tile's thresholds are no longer searched
+                    for (int q = threadIdx.x; q < CT_ROWS / 4; q += CT_THREADS) {
+                        reinterpret_cast<float4 *>(s_lo)[q] = reinterpret_cast<const float4 *>(r_lo2 + k0)[q];
+                        reinterpret_cast<float4 *>(s_hi)[q] = reinterpret_cast<const float4 *>(r_hi2 + k0)[q];
+                    }
+                    cached_tg = tg;
+                    __syncthreads();
                 }
-                if (strict_here) { a += tile_rank_lt(s_t, lo[u]) - pre_lt; b += tile_rank_le(s_t, hi[u]) - pre_le; }
-                conc_t += st_lt; le_t += st_le;
-            }
-        } else {   // the partial last column tile: pair by pair
-            const int lim = c1 - c0;
-            unsigned cs[CT_R], ls[CT_R];
+                unsigned sa = 0, sb = 0;
 #pragma unroll
-            for (int u = 0; u < CT_R; ++u) { cs[u] = 0; ls[u] = 0; }
-            for (int q = 0; q < lim; ++q) {
-                const float ej = s_e[q];
-                const int j = c0 + q;
+                for (int i = 0; i < CT_TILE / CT_THREADS; ++i) {
+                    const unsigned ra = tile_rank<true, CT_ROWS>(lo_addr, e[i]), rb = tile_rank<false, CT_ROWS>(hi_addr, e[i]);
+                    const bool ok = e[i] == e[i];
+                    sa += ok ? (unsigned)rng.z - ra : 0u;
+                    sb += ok ? (unsigned)rng.w - rb : 0u;
+                }
+                a += sa; b += sb;
+                continue;
+            }
+            float lo[CT_R], hi[CT_R];
+            int rs[CT_R], rg[CT_R];
+#pragma unroll
+            for (int u = 0; u < CT_R; ++u) {
+                const long long k = k0 + threadIdx.x + (long long)u * CT_THREADS;
+                if (k < n_rows) {
+                    lo[u] = r_lo[k]; hi[u] = r_hi[k]; rs[u] = r_s[k]; rg[u] = r_ge[k];
+                } else {  // padding row: empty comparable range, NaN thresholds never compare true
+                    lo[u] = __int_as_float(0x7fc00000); hi[u] = lo[u]; rs[u] = INT_MAX; rg[u] = INT_MAX;
+                }
+            }
+            __syncthreads();   // (s_e and s_t of the previous diagonal item are no longer read)
+            for (int q = threadIdx.x; q < CT_TILE; q += CT_THREADS) s_e[q] = (c0 + q < n) ? est_s[c0 + q] : 0.f;
+            if (full)
+                for (int q = threadIdx.x; q < CT_TILE; q += CT_THREADS) s_t[q] = est_t[c0 + q];
+            __syncthreads();
+            unsigned long long conc_t = 0, le_t = 0;
+            if (full) {
+                // Around the diagonal.  Per row the tile splits into columns before its comparable range [0, qt), same-time
+                // censored columns [qt, qs) and strictly later columns [qs, 1024): strict counts = ranks of the thresholds in
+                // the whole sorted tile minus the counts over [0, qs); only the columns before qs are visited one by one.
 #pragma unroll
                 for (int u = 0; u < CT_R; ++u) {
-                    const bool lt = ej < lo[u], le = ej <= hi[u];
-                    if (j >= rg[u]) { cs[u] += lt; ls[u] += le; }
-                    else if (j >= rs[u]) { conc_t += lt; le_t += le; }
+                    const int qs = min(max(rg[u] - c0, 0), CT_TILE), qt = min(max(rs[u] - c0, 0), CT_TILE);   // padding rows: both 1024
+                    unsigned pre_lt = 0, pre_le = 0, st_lt = 0, st_le = 0;
+                    const bool strict_here = qs < CT_TILE;
+                    for (int q = strict_here ? 0 : qt; q < qs; ++q) {
+                        const float ej = s_e[q];
+                        const bool lt = ej < lo[u], le = ej <= hi[u];
+                        pre_lt += lt; pre_le += le;
+                        if (q >= qt) { st_lt += lt; st_le += le; }
+                    }
+                    if (strict_here) { a += tile_rank_lt(s_t, lo[u]) - pre_lt; b += tile_rank_le(s_t, hi[u]) - pre_le; }
+                    conc_t += st_lt; le_t += st_le;
                 }
-            }
+            } else {   // the partial last column tile: pair by pair
+                const int lim = c1 - c0;
+                unsigned cs[CT_R], ls[CT_R];
 #pragma unroll
-            for (int u = 0; u < CT_R; ++u) { a += cs[u]; b += ls[u]; }
+                for (int u = 0; u < CT_R; ++u) { cs[u] = 0; ls[u] = 0; }
+                for (int q = 0; q < lim; ++q) {
+                    const float ej = s_e[q];
+                    const int j = c0 + q;
+#pragma unroll
+                    for (int u = 0; u < CT_R; ++u) {
+                        const bool lt = ej < lo[u], le = ej <= hi[u];
+                        if (j >= rg[u]) { cs[u] += lt; ls[u] += le; }
+                        else if (j >= rs[u]) { conc_t += lt; le_t += le; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < CT_R; ++u) { a += cs[u]; b += ls[u]; }
+            }
+            c += (long long)conc_t; d += (long long)le_t;
         }
-        c += (long long)conc_t; d += (long long)le_t;
+    }
     }
     a = block_reduce<long long>(a, 0ll, OpAddLL(), red);
     b = block_reduce<long long>(b, 0ll, OpAddLL(), red);
@@ -548,7 +580,7 @@ CiLayout ci_layout(int64_t n) {
     L.off_cub = take(L.cub_bytes);
     // algo 2: the column tiles sorted by estimate, the row tiles' sorted thresholds (padded to whole tiles), [min s, max ge) per row tile
     L.off_est_t = take(N * 4 + 16); L.off_lo2 = take((N + CT_ROWS) * 4); L.off_hi2 = take((N + CT_ROWS) * 4);
-    L.off_rng = take((N / CT_ROWS + 2) * 8);
+    L.off_rng = take((N / CT_ROWS + 2) * 16);
     L.total = o;
     return L;
 }
