@@ -406,7 +406,7 @@ __device__ __forceinline__ unsigned tile_rank_le(const float *s, float v) { retu
 //     straight from the sorted column tile (neighbouring lanes hold neighbouring values: the bisections walk together).
 //   * around the diagonal the rows keep their time order and their (lo, hi, s, ge): see below.
 constexpr int CI2_CHUNK = 8;
-__global__ void __launch_bounds__(CT_THREADS)
+__global__ void __launch_bounds__(CT_THREADS, 4)
 k_ci_count2(const float *__restrict__ est_s, const float *__restrict__ est_t, int64_t n, const float *__restrict__ r_lo,
             const float *__restrict__ r_hi, const int *__restrict__ r_s, const int *__restrict__ r_ge,
             const float *__restrict__ r_lo2, const float *__restrict__ r_hi2, const int *__restrict__ tile_rng, int shard,
@@ -416,6 +416,7 @@ k_ci_count2(const float *__restrict__ est_s, const float *__restrict__ est_t, in
     __shared__ __align__(16) float s_lo[CT_ROWS], s_hi[CT_ROWS];
     __shared__ long long red[32];
     __shared__ unsigned long long s_item;
+    __shared__ long long s_ty;
     const long long n_rows = (long long)acc->n_rows;
     const long long tiles_all = (n_rows + CT_ROWS - 1) / CT_ROWS;
     const long long my_tiles = tiles_all > shard ? (tiles_all - shard + n_shards - 1) / n_shards : 0;
@@ -432,15 +433,21 @@ k_ci_count2(const float *__restrict__ est_s, const float *__restrict__ est_t, in
     unsigned long long *counter = pass == 0 ? &acc->work : &acc->work2;
     for (;;) {
         __syncthreads();  // (s_item of the previous chunk is no longer read)
-        if (threadIdx.x == 0) s_item = atomicAdd(counter, (unsigned long long)chunk);
+        if (threadIdx.x == 0) {
+            const unsigned long long it = atomicAdd(counter, (unsigned long long)chunk);
+            s_item = it;
+            s_ty = (long long)(it / (unsigned long long)col_tiles);   // one 64-bit division per chunk, not per item and thread
+        }
         __syncthreads();
         const unsigned long long first = s_item;
         if (first >= total) break;
-        for (int gi = 0; gi < chunk; ++gi) {
+        long long ty = s_ty;
+        long long ct = (long long)(first - (unsigned long long)ty * (unsigned long long)col_tiles);   // column tile of the chunk's first item
+        for (int gi = 0; gi < chunk; ++gi, ++ct) {
             const unsigned long long item = first + (unsigned long long)gi;
             if (item >= total) break;
-            const long long ty = (long long)(item / (unsigned long long)col_tiles);
-            const int c0 = (int)(item - (unsigned long long)ty * (unsigned long long)col_tiles) * CT_TILE;
+            while (ct >= col_tiles) { ct -= col_tiles; ++ty; }
+            const int c0 = (int)ct * CT_TILE;
             const int c1 = (int)min((long long)n, (long long)c0 + CT_TILE);
             const long long tg = ty * n_shards + shard, k0 = tg * CT_ROWS;  // row tile ty of this shard
             const int4 rng = *reinterpret_cast<const int4 *>(tile_rng + 4 * tg);   // min s, max ge, valid lo, valid hi
