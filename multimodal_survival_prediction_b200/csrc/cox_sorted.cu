@@ -112,8 +112,30 @@ k_make_keys(const float *__restrict__ log_hz, const float *__restrict__ time, co
     float mx = -INFINITY, mt = -INFINITY, mn = -INFINITY;
     unsigned flags = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t n_round = (n + 31) / 32 * 32;  // whole warps iterate together (the shuffles below need every lane)
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    int64_t first = 0;   // rows [0, first) are done four at a time below
+    if (seg_off == nullptr && ((reinterpret_cast<uintptr_t>(log_hz) | reinterpret_cast<uintptr_t>(time) | reinterpret_cast<uintptr_t>(keys)) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(event) & 3) == 0) {
+        // one cohort, aligned inputs: four rows per thread and iteration (16-byte loads and stores; the scalar loop below issues
+        // 65 instructions per row, most of them index arithmetic and bounds tests)
+        const int64_t ngroups = n >> 2;
+        for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4 *>(time) + g), e4 = __ldg(reinterpret_cast<const float4 *>(log_hz) + g);
+            const uint32_t v4 = __ldg(reinterpret_cast<const uint32_t *>(event) + g);
+            uint4 k4;
+            k4.x = time_key(t4.x, (v4 & 0xffu) != 0); k4.y = time_key(t4.y, (v4 & 0xff00u) != 0);
+            k4.z = time_key(t4.z, (v4 & 0xff0000u) != 0); k4.w = time_key(t4.w, (v4 & 0xff000000u) != 0);
+            reinterpret_cast<uint4 *>(keys)[g] = k4;
+            atomicAdd(&s_hist[k4.x & 255u], 1u); atomicAdd(&s_hist[k4.y & 255u], 1u);
+            atomicAdd(&s_hist[k4.z & 255u], 1u); atomicAdd(&s_hist[k4.w & 255u], 1u);
+            mx = fmaxf(fmaxf(mx, fmaxf(e4.x, e4.y)), fmaxf(e4.z, e4.w));
+            const float tmax = fmaxf(fmaxf(t4.x, t4.y), fmaxf(t4.z, t4.w)), tmin = fminf(fminf(t4.x, t4.y), fminf(t4.z, t4.w));
+            mt = fmaxf(mt, tmax); mn = fmaxf(mn, -tmin);
+            if (!(t4.x >= 0.f) || !(t4.y >= 0.f) || !(t4.z >= 0.f) || !(t4.w >= 0.f)) flags |= B200SURV_COXF_BAD_TIME;
+        }
+        first = ngroups << 2;
+    }
+    const int64_t n_round = first + (n - first + 31) / 32 * 32;  // whole warps iterate together (the shuffles below need every lane)
+    for (int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         const bool in = i < n;
         const float t = in ? time[i] : 0.f, e = in ? log_hz[i] : -INFINITY;
         const unsigned bad = (in && !(t >= 0.f)) ? B200SURV_COXF_BAD_TIME : 0u;
