@@ -163,6 +163,32 @@ def test_unaligned_views_and_dtypes():
     assert np.abs(x64.grad.numpy()[:, 0] - 2.5 * ref_g).max() <= GRAD_RTOL * 2.5 * np.abs(ref_g).max()
 
 
+@pytest.mark.parametrize("n", [4099, 65_537, 300_002])
+def test_sorted_mode_unaligned_views_equal_aligned_run(n):
+    """SORTED mode: the key kernel takes four rows per thread when the vectors are 16-byte aligned and a scalar loop for the
+    rest (misaligned views, the n mod 4 tail).  Views at 4 / 12-byte (1 / 3-byte for the event vector) offsets must give the
+    aligned run's loss (to one fp32 ulp: the fp64 sums meet through atomics) and the oracle's values to the usual tolerance; few-ties and heavy-ties cohorts."""
+    for few in (True, False):
+        lh, ev, t = synth.cohort(n + 3, 40 + n % 7, few_ties=few)
+        outs = []
+        for off in (0, 1, 3):
+            base = [v.cuda() for v in (lh, ev, t)]
+            # a fresh buffer whose element `off` holds row 0 of the cohort: same rows, different alignment
+            bx = torch.empty(n + 8, device="cuda"); bt = torch.empty(n + 8, device="cuda")
+            be = torch.empty(n + 8, dtype=torch.bool, device="cuda")
+            bx[off:off + n] = base[0][:n]; bt[off:off + n] = base[2][:n]; be[off:off + n] = base[1][:n]
+            x = bx[off:off + n].requires_grad_(True)
+            loss = pkg.neg_partial_log_likelihood(x, be[off:off + n], bt[off:off + n], mode="sorted")
+            loss.backward()
+            outs.append((loss.detach().cpu(), x.grad.cpu()))
+        for l, g in outs[1:]:
+            assert abs(float(l) - float(outs[0][0])) <= 2e-7 * abs(float(outs[0][0]))    # fp64 sums by atomics: one fp32 ulp
+            assert torch.allclose(g, outs[0][1], rtol=0, atol=1e-7 * float(outs[0][1].abs().max()))
+        ref_l, ref_g = ocox.cox_nll(lh[:n].numpy().astype(np.float64), ev[:n].numpy(), t[:n].numpy())
+        assert abs(float(outs[0][0]) - ref_l) <= LOSS_RTOL * abs(ref_l)
+        assert np.abs(outs[0][1].numpy() - ref_g).max() <= GRAD_RTOL * np.abs(ref_g).max()
+
+
 @pytest.mark.parametrize("mode", ["small", "binned"])
 def test_segmented_cohorts(mode):
     rng = np.random.default_rng(9)
