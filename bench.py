@@ -717,7 +717,11 @@ def run_b200(args):
     # one all-gather of the replica-fold C-indices.  Replicas are independent: no other collective.
     folds = 5
     fold_nets = [ghead.PartialModalityNet().to(dev).eval() for _ in range(sw_rep)]
-    fold_saved = ghead.head_saved_buffer(sw_rows, 5005, dev)
+    # the replicas' forward passes run on SWEEP_STREAMS streams (one staged copy of the fold's RNA matrix per stream): one
+    # replica's tensor-core GEMM overlaps the others' memory-bound layers
+    SWEEP_STREAMS = 4
+    sweep_streams = [torch.cuda.Stream(device=dev) for _ in range(SWEEP_STREAMS)]
+    fold_saved = [ghead.head_saved_buffer(sw_rows, 5005, dev) for _ in range(SWEEP_STREAMS)]
     g_ = torch.Generator(device=dev).manual_seed(4321 + rank)
     fold_x = torch.randn(sw_rows, 5005, device=dev, generator=g_)
     fold_ct = torch.relu(torch.randn(sw_rows, 128, device=dev, generator=g_))
@@ -735,10 +739,18 @@ def run_b200(args):
         with torch.no_grad():
             for f in range(folds):
                 # (synthetic: the same feature matrices stand for every fold; the labels differ per fold)
-                ghead.stage_rna(fold_x, fold_saved)
+                main_ = torch.cuda.current_stream(dev)
+                for st_, sv_ in zip(sweep_streams, fold_saved):
+                    st_.wait_stream(main_)                 # (the previous fold's loss / C-index read hz_packed)
+                    with torch.cuda.stream(st_):
+                        ghead.stage_rna(fold_x, sv_)
                 for r_, net_ in enumerate(fold_nets):
-                    hz_, _ = ghead.fused_head(net_, fold_ct, fold_x, fold_clin, fold_mask, staged_saved=fold_saved)
-                    hz_packed[r_ * sw_rows:(r_ + 1) * sw_rows].copy_(hz_)
+                    with torch.cuda.stream(sweep_streams[r_ % SWEEP_STREAMS]):
+                        hz_, _ = ghead.fused_head(net_, fold_ct, fold_x, fold_clin, fold_mask,
+                                                  staged_saved=fold_saved[r_ % SWEEP_STREAMS])
+                        hz_packed[r_ * sw_rows:(r_ + 1) * sw_rows].copy_(hz_)
+                for st_ in sweep_streams:
+                    main_.wait_stream(st_)
                 fev_, ft_ = fold_labels[f]
                 loss_, state_ = gcox.cox_fwd_raw(hz_packed, ft_, fev_, soff_d, sw_rep, L.TIES["efron"], L.REDUCE_MEAN_TERMS, L.COX_BINNED, 4096)
                 gcox.cox_bwd_raw(sones, state_, hz_packed, ft_, fev_, soff_d, sw_rep, L.COX_BINNED, 4096)
