@@ -406,7 +406,7 @@ __device__ __forceinline__ unsigned tile_rank_le(const float *s, float v) { retu
 //     straight from the sorted column tile (neighbouring lanes hold neighbouring values: the bisections walk together).
 //   * around the diagonal the rows keep their time order and their (lo, hi, s, ge): see below.
 constexpr int CI2_CHUNK = 8;
-__global__ void __launch_bounds__(CT_THREADS, 4)
+__global__ void __launch_bounds__(CT_THREADS, 3)
 k_ci_count2(const float *__restrict__ est_s, const float *__restrict__ est_t, int64_t n, const float *__restrict__ r_lo,
             const float *__restrict__ r_hi, const int *__restrict__ r_s, const int *__restrict__ r_ge,
             const float *__restrict__ r_lo2, const float *__restrict__ r_hi2, const int *__restrict__ tile_rng, int shard,
@@ -429,24 +429,31 @@ k_ci_count2(const float *__restrict__ est_s, const float *__restrict__ est_t, in
     // strictly-later ones in chunks that share their row tile's thresholds
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-    const int chunk = pass == 0 ? 1 : CI2_CHUNK;
+    // pass 0 enumerates the items column tile by column tile (item = column tile * row tiles + row tile): the items around
+    // the diagonal of one row tile are ~8 consecutive column tiles, so consecutive items of this order hold at most one or
+    // two of them and a chunk of 32 stays balanced; pass 1 goes row tile by row tile (its chunk shares the thresholds)
+    const unsigned long long per_cta = total / (4ull * gridDim.x);   // small cohorts: single items (balance before pull latency)
+    const int cmax = pass == 0 ? 32 : CI2_CHUNK;
+    const int chunk = (int)(per_cta < 1 ? 1 : (per_cta > (unsigned long long)cmax ? (unsigned long long)cmax : per_cta));
     unsigned long long *counter = pass == 0 ? &acc->work : &acc->work2;
     for (;;) {
         __syncthreads();  // (s_item of the previous chunk is no longer read)
+        const long long inner = pass == 0 ? my_tiles : col_tiles;   // the fast index of this pass's enumeration
         if (threadIdx.x == 0) {
             const unsigned long long it = atomicAdd(counter, (unsigned long long)chunk);
             s_item = it;
-            s_ty = (long long)(it / (unsigned long long)col_tiles);   // one 64-bit division per chunk, not per item and thread
+            s_ty = (long long)(it / (unsigned long long)inner);   // one 64-bit division per chunk, not per item and thread
         }
         __syncthreads();
         const unsigned long long first = s_item;
         if (first >= total) break;
-        long long ty = s_ty;
-        long long ct = (long long)(first - (unsigned long long)ty * (unsigned long long)col_tiles);   // column tile of the chunk's first item
-        for (int gi = 0; gi < chunk; ++gi, ++ct) {
+        long long outer = s_ty;
+        long long in_ = (long long)(first - (unsigned long long)outer * (unsigned long long)inner);
+        for (int gi = 0; gi < chunk; ++gi, ++in_) {
             const unsigned long long item = first + (unsigned long long)gi;
             if (item >= total) break;
-            while (ct >= col_tiles) { ct -= col_tiles; ++ty; }
+            while (in_ >= inner) { in_ -= inner; ++outer; }
+            const long long ty = pass == 0 ? in_ : outer, ct = pass == 0 ? outer : in_;
             const int c0 = (int)ct * CT_TILE;
             const int c1 = (int)min((long long)n, (long long)c0 + CT_TILE);
             const long long tg = ty * n_shards + shard, k0 = tg * CT_ROWS;  // row tile ty of this shard
@@ -454,7 +461,9 @@ k_ci_count2(const float *__restrict__ est_s, const float *__restrict__ est_t, in
             if (c1 <= rng.x) continue;   // the column tile precedes every row's comparable range (block-uniform)
             const bool full = c1 - c0 == CT_TILE;
             const bool strictly_later = full && c0 >= rng.y;
-            if (strictly_later != (pass == 1)) continue;   // not this pass's kind
+            // pass 0: the full tiles around the diagonal; pass 1: the strictly-later tiles and the partial last column tile
+            // (one per row tile: in pass 0's order they would all land in one chunk)
+            if ((full && !strictly_later) != (pass == 0)) continue;
             if (strictly_later) {
                 // every (row, column) pair of this item is a strict comparable pair
                 float e[CT_TILE / CT_THREADS];
@@ -506,13 +515,12 @@ k_ci_count2(const float *__restrict__ est_s, const float *__restrict__ est_t, in
                     const int qs = min(max(rg[u] - c0, 0), CT_TILE), qt = min(max(rs[u] - c0, 0), CT_TILE);   // padding rows: both 1024
                     unsigned pre_lt = 0, pre_le = 0, st_lt = 0, st_le = 0;
                     const bool strict_here = qs < CT_TILE;
-                    for (int q = strict_here ? 0 : qt; q < qs; ++q) {
-                        const float ej = s_e[q];
-                        const bool lt = ej < lo[u], le = ej <= hi[u];
-                        pre_lt += lt; pre_le += le;
-                        if (q >= qt) { st_lt += lt; st_le += le; }
+                    if (strict_here)   // columns before the row's comparable range: only taken off the whole-tile ranks
+                        for (int q = 0; q < qt; ++q) { const float ej = s_e[q]; inc_lt(pre_lt, ej, lo[u]); inc_le(pre_le, ej, hi[u]); }
+                    for (int q = qt; q < qs; ++q) { const float ej = s_e[q]; inc_lt(st_lt, ej, lo[u]); inc_le(st_le, ej, hi[u]); }
+                    if (strict_here) {
+                        a += tile_rank_lt(s_t, lo[u]) - (pre_lt + st_lt); b += tile_rank_le(s_t, hi[u]) - (pre_le + st_le);
                     }
-                    if (strict_here) { a += tile_rank_lt(s_t, lo[u]) - pre_lt; b += tile_rank_le(s_t, hi[u]) - pre_le; }
                     conc_t += st_lt; le_t += st_le;
                 }
             } else {   // the partial last column tile: pair by pair

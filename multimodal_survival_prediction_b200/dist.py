@@ -45,7 +45,7 @@ def cindex_counts_sharded(estimate, event, time, tied_tol=1e-8, algo=1, group=No
 
     On the GPU rank r counts the row TILES r, r + world, ... of the sorted event rows (cindex_counts_shard): its
     kernel keeps the tile structure of the single-GPU run.  algo 1 (the default here): the pair-by-pair tile kernel the
-    8-GPU scaling target is quoted on; algo 2: ranks in sorted tiles (21x faster on one GPU at 1M patients, so its shards
+    8-GPU scaling target is quoted on; algo 2: ranks in sorted tiles (25x faster on one GPU at 1M patients, so its shards
     are short against the replicated preprocessing).  A caller-supplied ``_count_fn(est, ev, time, tol, a, b,
     algo)`` (the CPU tests of this host logic) gets the contiguous row block ``shard_bounds(n, rank, world)``."""
     rank, world = _world()
