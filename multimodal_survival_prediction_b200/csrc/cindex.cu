@@ -442,7 +442,7 @@ k_ci_count2(const float *__restrict__ est_s, const float *__restrict__ est_t, in
         if (threadIdx.x == 0) {
             const unsigned long long it = atomicAdd(counter, (unsigned long long)chunk);
             s_item = it;
-            s_ty = (long long)(it / (unsigned long long)inner);   // one 64-bit division per chunk, not per item and thread
+            s_ty = inner > 0 ? (long long)(it / (unsigned long long)inner) : 0;   // one 64-bit division per chunk, not per item and thread
         }
         __syncthreads();
         const unsigned long long first = s_item;
