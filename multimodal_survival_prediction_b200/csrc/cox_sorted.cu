@@ -298,12 +298,18 @@ __device__ __forceinline__ T block_prefix(const T &agg, T *s_warp) {
     __syncthreads();  // s_warp may still be read from the previous scan
     if (lane == (REV ? 0 : 31)) s_warp[warp] = inc;
     __syncthreads();
-    T pre = T::identity();
+    // the warps' totals: every warp scans them itself, lane l holding the total at scan position l (three shuffle steps and one
+    // broadcast instead of a loop of TS_NW - 1 combines out of shared memory in every thread)
+    static_assert(TS_NW <= 32, "one lane per warp total");
+    const int pos = REV ? TS_NW - 1 - warp : warp;
+    T v = lane < TS_NW ? s_warp[REV ? TS_NW - 1 - lane : lane] : T::identity();
 #pragma unroll
-    for (int k = 0; k < TS_NW; ++k) {
-        const int w = REV ? TS_NW - 1 - k : k;
-        if (REV ? (w > warp) : (w < warp)) pre = T::combine(pre, s_warp[w]);
+    for (int d = 1; d < TS_NW; d <<= 1) {
+        const T u = v.shfl((lane - d) & 31);
+        if (lane >= d) v = T::combine(u, v);
     }
+    T pre = v.shfl((pos - 1) & 31);
+    if (pos == 0) pre = T::identity();
     T ex = inc.shfl((REV ? lane + 1 : lane - 1) & 31);
     if (lane == (REV ? 31 : 0)) ex = T::identity();
     return T::combine(pre, ex);
@@ -378,6 +384,31 @@ __device__ __forceinline__ void tile_load(const TileGeo &g, const uint32_t *__re
                                           uint32_t *s_key /*[TS_KN]*/, float *s_w /*[TS_KN]*/, TileRows &R,
                                           const WeightSrc *src = nullptr, double *eta_sum = nullptr, int *n_ev = nullptr) {
     const int t = threadIdx.x;
+    if (!GATHER && !STREAM && g.rows == TS_TILE && !(g.flags & (TF_FIRST | TF_LAST)) && g.halo == 0) {
+        // a whole tile inside its cohort (all but the first, the last and the partial ones): no bounds or edge tests
+        const uint32_t *kp = keys_s + (g.p0 - 1) + t;
+        const float *wp = w + g.p0 + t;
+        uint32_t kq[TS_ITEMS + 1];
+        float wq[TS_ITEMS];
+#pragma unroll
+        for (int k = 0; k < TS_ITEMS; ++k) { kq[k] = kp[k * TS_THREADS]; wq[k] = wp[k * TS_THREADS]; }
+        kq[TS_ITEMS] = t < 2 ? kp[TS_ITEMS * TS_THREADS] : 0u;
+#pragma unroll
+        for (int k = 0; k < TS_ITEMS; ++k) {
+            const int j = t + k * TS_THREADS;
+            s_key[j + (j >> 5)] = kq[k]; s_w[j + (j >> 5)] = wq[k];
+        }
+        if (t < 2) s_key[t + TS_TILE + ((t + TS_TILE) >> 5)] = kq[TS_ITEMS];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TS_ITEMS; ++k) {
+            const int j = t * TS_ITEMS + k;
+            const uint32_t a = s_key[j + (j >> 5)], b = s_key[j + 1 + ((j + 1) >> 5)], c = s_key[j + 2 + ((j + 2) >> 5)];
+            R.w[k] = s_w[j + (j >> 5)];
+            R.flg[k] = ((a >> 1) != (b >> 1) ? RF_HEAD : 0u) | ((c >> 1) != (b >> 1) ? RF_TAIL : 0u) | ((b & 1u) ? 0u : RF_EV);
+        }
+        return;
+    }
     const uint64_t pol = STREAM ? l2_policy_evict_first() : 0ull;   // last reader of (keys, w): do not displace the scatter target
     // s_key[1 + j] = key of row j; s_key[0] / s_key[rows + 1] = the neighbours across the tile edges.  All loads of a thread
     // are issued before the first store (one memory latency per tile, not one per element).
@@ -813,6 +844,9 @@ __device__ __forceinline__ void tile_terms(const TileGeo &g, const TileRows &R, 
     const double Df = c.S + tw.Wtot + c.LW, Ef = c.LE + tw.Ef + (tw.nheads ? 0.0 : c.RE);
     const int mf = c.Lm + tw.mf + (tw.nheads ? 0 : c.Rm);
     sum_log = 0.0;
+    // the logs of a thread's denominators as ONE logarithm: exponents summed as integers, mantissas (each in [1, 2)) multiplied
+    double lprod = 1.0;
+    int lexp = 0;
 #pragma unroll
     for (int k = 0; k < TS_ITEMS; ++k) {
         X.a[k] = 0.0; X.f[k] = 0.0;
@@ -826,9 +860,14 @@ __device__ __forceinline__ void tile_terms(const TileGeo &g, const TileRows &R, 
             if (efron && l > 0) { frac = (double)l * fast_rcp((double)m); den -= frac * E; }
             const double a = fast_rcp(den);
             X.a[k] = a; X.f[k] = frac * a;
-            if (WITH_LOG) sum_log += fast_log(den);
+            if (WITH_LOG) {
+                const int hi = __double2hiint(den);
+                lexp += ((hi >> 20) & 0x7ff) - 1023;
+                lprod *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(den));
+            }
         }
     }
+    if (WITH_LOG) sum_log = (double)lexp * 0.6931471805599453 + fast_log(lprod);   // lprod in [1, 2^TS_ITEMS)
 }
 
 // Besides the tile's sums the sweep leaves, per row, everything of the gradient that does not depend on the SECOND tile scan:
