@@ -189,6 +189,40 @@ def test_sorted_mode_unaligned_views_equal_aligned_run(n):
         assert np.abs(outs[0][1].numpy() - ref_g).max() <= GRAD_RTOL * np.abs(ref_g).max()
 
 
+def test_sorted_beyond_one_scan_round_per_cluster_cta_equals_binned():
+    """More than 8 x 1024 tiles (n > 16.7M rows): every CTA of the tile-scan clusters walks several rounds and carries between
+    them.  No CPU oracle at this size; the check is the BINNED path, which shares no kernel with SORTED (integer days, Efron
+    and Breslow): loss and gradient agree to the usual tolerance.  Also packed cohorts at a size where the packed tile count
+    passes 8192."""
+    n = 20_000_003
+    lh, ev, t = synth.cohort(n, 77)
+    e, tt = ev.cuda(), t.cuda()
+    for ties in ("efron", "breslow"):
+        out = {}
+        for mode in ("binned", "sorted"):
+            x = lh.cuda().requires_grad_(True)
+            loss = pkg.neg_partial_log_likelihood(x, e, tt, ties_method=ties, mode=mode)
+            loss.backward()
+            out[mode] = (float(loss), x.grad)
+        assert abs(out["sorted"][0] - out["binned"][0]) <= LOSS_RTOL * abs(out["binned"][0]), (ties, out["sorted"][0], out["binned"][0])
+        gmax = float(out["binned"][1].abs().max())
+        assert float((out["sorted"][1] - out["binned"][1]).abs().max()) <= GRAD_RTOL * gmax, ties
+    del out
+    # packed cohorts: 3 x 5.6M rows -> 8,205 + 3 tiles
+    lens = [5_600_001, 5_600_002, 5_600_003]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    m = int(off[-1])
+    losses = {}
+    for mode in ("binned", "sorted"):
+        x = lh[:m].cuda().requires_grad_(True)
+        ls = pkg.neg_partial_log_likelihood_segmented(x, ev[:m].cuda(), t[:m].cuda(), torch.tensor(off), mode=mode)
+        ls.sum().backward()
+        losses[mode] = (ls.detach().cpu().numpy(), x.grad)
+    np.testing.assert_allclose(losses["sorted"][0], losses["binned"][0], rtol=LOSS_RTOL)
+    gmax = float(losses["binned"][1].abs().max())
+    assert float((losses["sorted"][1] - losses["binned"][1]).abs().max()) <= GRAD_RTOL * gmax
+
+
 @pytest.mark.parametrize("mode", ["small", "binned"])
 def test_segmented_cohorts(mode):
     rng = np.random.default_rng(9)
